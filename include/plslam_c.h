@@ -1,0 +1,255 @@
+/*
+ * plslam_c.h — C ABI of the B200-native point+line front-end.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of
+ * wolfcanli/ORB_SLAM2_Modification_with-point-and-line-feature.  The reference has no FFI layer; its boundary
+ * is four C++ classes (ORBextractor, LineExtractor, ORBmatcher, LineMatcher).  The host-side mirrors of those
+ * classes (package host/ directory) flatten Frame / MapPoint / MapLine state into the POD arrays declared here
+ * and call these entry points.  Every entry point cites the reference interface it replaces (file:line, relative
+ * to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ / torch / OpenCV types.
+ *   - every function returns PL_OK (0) or a negative pl_status; pl_last_error() gives a thread-local message.
+ *     (The reference itself has no error convention: empty image -> silent return, ORBextractor.cc:1046; wrong
+ *     type -> assert, :1050.  The host mirrors translate PL_ERR_EMPTY into the silent return.)
+ *   - "host" entry points take host pointers and perform the H2D / D2H copies themselves on the handle's stream;
+ *     "_dev" entry points take device pointers (inputs already resident in HBM) and are asynchronous on the
+ *     handle's stream until pl_*_sync().
+ *   - there is NO CPU fallback: if no sm_100-class device is usable, creation fails with PL_ERR_CUDA.
+ */
+#ifndef PLSLAM_C_H
+#define PLSLAM_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PL_API __attribute__((visibility("default")))
+
+typedef enum {
+    PL_OK = 0,
+    PL_ERR_ARG = -1,      /* bad argument (null pointer, non-positive size, capacity too small) */
+    PL_ERR_EMPTY = -2,    /* empty image: mirrors the reference's silent return                  */
+    PL_ERR_CUDA = -3,     /* CUDA runtime failure or no usable device                            */
+    PL_ERR_CAPACITY = -4, /* an internal or caller capacity was exceeded; output not valid       */
+    PL_ERR_STATE = -5     /* call sequence error (e.g. reading a pyramid before an extract)      */
+} pl_status;
+
+/* == cv::KeyPoint (28 bytes).  reference: every std::vector<cv::KeyPoint> crossing ORBextractor.h:59-61 */
+typedef struct {
+    float x, y;      /* pt */
+    float size;
+    float angle;     /* degrees, [0,360) */
+    float response;
+    int octave;
+    int class_id;
+} pl_keypoint;
+
+/* == cv::line_descriptor::KeyLine (68 bytes, 17 four-byte fields in declaration order).
+ * reference: std::vector<KeyLine> crossing LineExtractor.h:25-30 */
+typedef struct {
+    float angle;     /* radians, atan2(dy,dx) */
+    int class_id;
+    int octave;
+    float pt_x, pt_y;
+    float response;
+    float size;
+    float sx, sy, ex, ey;                       /* start/end in the original image      */
+    float sx_oct, sy_oct, ex_oct, ey_oct;       /* start/end in the octave image        */
+    float length;
+    int num_pixels;
+} pl_keyline;
+
+PL_API const char* pl_last_error(void);
+PL_API int pl_device_count(void);
+/* version / build tag of the native library ("sm_100a") */
+PL_API const char* pl_build_info(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A. ORB extraction — replaces ORBextractor::ORBextractor (ORBextractor.cc:410-470) and
+ *    ORBextractor::operator() (ORBextractor.cc:1043-1105; header ORBextractor.h:51-61).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pl_orb pl_orb;
+
+/* ctor: same five parameters as the reference constructor, plus device ordinal and the maximum image size /
+ * batch this handle will see (device buffers are sized once; nothing is allocated per call). */
+PL_API int pl_orb_create(pl_orb** out, int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
+                         int min_th_fast, int device, int max_cols, int max_rows, int max_batch);
+PL_API void pl_orb_destroy(pl_orb* h);
+
+/* getters — ORBextractor.h:63-84.  Each writes nlevels floats (or ints). */
+PL_API int pl_orb_levels(const pl_orb* h);
+PL_API float pl_orb_scale_factor(const pl_orb* h);
+PL_API int pl_orb_scale_factors(const pl_orb* h, float* out);
+PL_API int pl_orb_inv_scale_factors(const pl_orb* h, float* out);
+PL_API int pl_orb_level_sigma2(const pl_orb* h, float* out);
+PL_API int pl_orb_inv_level_sigma2(const pl_orb* h, float* out);
+PL_API int pl_orb_features_per_level(const pl_orb* h, int* out);
+/* capacity (in keypoints) that is always sufficient for one frame: sum over levels of quota+3 */
+PL_API int pl_orb_max_keypoints(const pl_orb* h);
+
+/* operator(): one 8UC1 image (host pointer, row stride `step` bytes) -> keypoints + 32-byte descriptors.
+ * `cap` = capacity of kps / desc in keypoints.  Synchronous.  */
+PL_API int pl_orb_extract(pl_orb* h, const uint8_t* gray, int rows, int cols, size_t step, pl_keypoint* kps,
+                          uint8_t* desc, int cap, int* n_out);
+
+/* Batched operator() over n_frames independent images of identical size (config 5 of BASELINE.json; frames are
+ * independent because operator() keeps no state across calls, ORBextractor.cc:1053-1073).
+ * frame f starts at gray + f*frame_stride.  Outputs for frame f are written at kps + f*cap, desc + f*cap*32;
+ * n_out[f] receives its count.  Host pointers; synchronous. */
+PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step,
+                                size_t frame_stride, pl_keypoint* kps, uint8_t* desc, int cap, int* n_out);
+
+/* Same, but every pointer is a DEVICE pointer on the handle's device; asynchronous on the handle's stream.
+ * Used for HBM-resident measurement and for chaining extract -> match without a host round trip. */
+PL_API int pl_orb_extract_batch_dev(pl_orb* h, const uint8_t* d_gray, int n_frames, int rows, int cols,
+                                    size_t step, size_t frame_stride, pl_keypoint* d_kps, uint8_t* d_desc, int cap,
+                                    int* d_n_out);
+PL_API int pl_orb_sync(pl_orb* h);
+/* the CUDA stream of the handle as an opaque pointer (cudaStream_t) — for event timing by the caller */
+PL_API void* pl_orb_stream(pl_orb* h);
+
+/* Backs the PUBLIC member ORBextractor::mvImagePyramid (ORBextractor.h:85; read by Frame.cc:895,985,997,1002).
+ * Copies pyramid level `level` of frame `frame` of the LAST extract call into `out` (host) as the BORDERED plane
+ * (EDGE_THRESHOLD=19 px of BORDER_REFLECT_101 on each side, ORBextractor.cc:1107-1130).  The un-bordered image
+ * is the ROI at (19,19).  out_step >= cols+38. */
+PL_API int pl_orb_pyramid_dims(const pl_orb* h, int level, int* rows, int* cols);
+PL_API int pl_orb_pyramid_read(pl_orb* h, int frame, int level, uint8_t* out, size_t out_step);
+
+/* Debug / test hook: the ordered FAST candidate list handed to DistributeOctTree for (frame, level) of the last
+ * extract call (ORBextractor.cc:779-829: vToDistributeKeys), coordinates relative to minBorder. */
+PL_API int pl_orb_candidates_read(pl_orb* h, int frame, int level, float* xs, float* ys, float* responses, int cap,
+                                  int* n_out);
+/* Test hook: the 7x7 sigma=2 blurred plane (ORBextractor.cc:1085-1086) of (frame, level): cols x rows bytes. */
+PL_API int pl_orb_blurred_read(pl_orb* h, int frame, int level, uint8_t* out, size_t out_step);
+/* number of kernel launches issued by the last extract call (bench.py's gpu_launches claim) */
+PL_API int pl_orb_last_launches(const pl_orb* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * B. Line extraction — replaces LineExtractor::ExtractLineSegment (LineExtractor.cpp:12-70; LineExtractor.h:25-30):
+ *    LSD (cv::line_descriptor::LSDDetector::detect, 1 octave, LSD_REFINE_ADV) -> keep `max_lines` longest ->
+ *    LBD 256-bit descriptors (BinaryDescriptor::compute) -> normalised homogeneous line coefficients.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pl_line pl_line;
+
+PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows, int max_batch);
+PL_API void pl_line_destroy(pl_line* h);
+
+/* one image -> <= max_lines keylines (reference constant 80, LineExtractor.cpp:23), n x 32 descriptor bytes,
+ * n x 3 doubles of unit-norm line coefficients (LineExtractor.cpp:60-69).  Host pointers, synchronous. */
+PL_API int pl_line_extract(pl_line* h, const uint8_t* gray, int rows, int cols, size_t step, int max_lines,
+                           pl_keyline* kls, uint8_t* desc, double* coeffs, int* n_out);
+PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step,
+                                 size_t frame_stride, int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs,
+                                 int* n_out);
+PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols,
+                                     size_t step, size_t frame_stride, int max_lines, pl_keyline* d_kls,
+                                     uint8_t* d_desc, double* d_coeffs, int* d_n_out);
+PL_API int pl_line_sync(pl_line* h);
+PL_API void* pl_line_stream(pl_line* h);
+PL_API int pl_line_last_launches(const pl_line* h);
+
+/* Test hook: ALL LSD segments of frame `frame` of the last call before the top-`max_lines` filter, in detection
+ * order: x1,y1,x2,y2 (float, image coordinates) + width, prec(p), nfa as doubles
+ * (cv::LineSegmentDetector::detect outputs). */
+PL_API int pl_line_lsd_read(pl_line* h, int frame, float* xyxy, double* width, double* prec, double* nfa, int cap,
+                            int* n_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * C/D. Descriptor search.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pl_match pl_match;
+PL_API int pl_match_create(pl_match** out, int device);
+PL_API void pl_match_destroy(pl_match* h);
+PL_API int pl_match_sync(pl_match* h);
+PL_API void* pl_match_stream(pl_match* h);
+PL_API int pl_match_last_launches(const pl_match* h);
+
+/* C1/D1: ORBmatcher::DescriptorDistance (ORBmatcher.cc:2083-2103) == LineMatcher::DescriptorDistance
+ * (LineMatcher.cpp:20-39): 256-bit Hamming distance of row pairs (a[i], b[i]), i < n. */
+PL_API int pl_hamming_pairs(pl_match* h, const uint8_t* a, const uint8_t* b, int n, int* dist);
+
+/* D6: brute-force 2-nearest-neighbour Hamming search == cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)
+ * (LineMatcher.cpp:496-503, :1179-1185).  idx/dist are nq x 2; ties resolve to the lowest train index; when
+ * nt < 2 the missing entries are idx=-1, dist=-1 (the reference reads them out of bounds, :507). */
+PL_API int pl_hamming_knn2(pl_match* h, const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist);
+PL_API int pl_hamming_knn2_dev(pl_match* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int* d_idx,
+                               int* d_dist);
+
+/* Candidate scoring shared by ORBmatcher::SearchByProjection / SearchByBoW (ORBmatcher.cc:123-164, :1802-1829,
+ * :306-336): for query row i, distances to train rows cand_idx[cand_off[i] .. cand_off[i+1]) in that order. */
+PL_API int pl_hamming_candidates(pl_match* h, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                                 const int* cand_off, const int* cand_idx, int* dist_out);
+
+/* Frame-side view used by the projection searches: the subset of ORB_SLAM2::Frame the matcher reads. */
+typedef struct {
+    int n;                        /* Frame::N                                                    */
+    const pl_keypoint* keys_un;   /* Frame::mvKeysUn (x,y,octave,angle read)                     */
+    const uint8_t* desc;          /* Frame::mDescriptors, n x 32                                 */
+    const float* u_right;         /* Frame::mvuRight, n (<=0: no stereo)                         */
+    const int* claimed;           /* n; 1 when mvpMapPoints[i] && Observations()>0 (ORBmatcher.cc:128-130) */
+    float min_x, min_y, max_x, max_y;   /* Frame::mnMinX.. (Frame.cc:184-185)                    */
+    float fx, fy, cx, cy, bf, b;  /* intrinsics, mbf, mb                                         */
+    float tcw[12];                /* Frame::mTcw rows 0..2 (row-major 3x4)                       */
+    int n_levels;
+    const float* scale_factors;   /* Frame::mvScaleFactors                                       */
+} pl_frame_view;
+
+/* C2: ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) — ORBmatcher.cc:72-183.
+ * Map points are given as the fields IsInFrustum (Frame.cc:345-401) leaves on them.  match_of_feature[n] receives,
+ * per frame feature, the index of the map point assigned to it or -1 (== F.mvpMapPoints writes).  Returns the
+ * count through n_matches. */
+typedef struct {
+    int n;
+    const uint8_t* desc;          /* MapPoint::GetDescriptor(), n x 32            */
+    const uint8_t* track_in_view; /* mbTrackInView && !isBad()                    */
+    const float* proj_x;          /* mTrackProjX                                  */
+    const float* proj_y;          /* mTrackProjY                                  */
+    const float* proj_xr;         /* mTrackProjXR                                 */
+    const int* scale_level;       /* mnTrackScaleLevel                            */
+    const float* view_cos;        /* mTrackViewCos                                */
+} pl_mappoint_view;
+PL_API int pl_orb_search_local_points(pl_match* h, const pl_frame_view* F, const pl_mappoint_view* mps, float th,
+                                      float nn_ratio, int* match_of_feature, int* n_matches);
+
+/* C3: ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) — ORBmatcher.cc:1710-1879.
+ * last_* describe LastFrame.mvpMapPoints: per Last feature i, valid[i] = (pMP && !mvbOutlier[i]), world position,
+ * the map point's descriptor, mvKeys[i].octave, mvKeysUn[i].angle and Last's Tcw.  match_of_feature as above
+ * (index i of the Last feature whose map point was assigned, or -1). */
+typedef struct {
+    int n;
+    const uint8_t* valid;
+    const float* world_pos;       /* n x 3 */
+    const uint8_t* desc;          /* n x 32 */
+    const int* octave;
+    const float* angle;
+    float tcw[12];
+} pl_lastframe_view;
+PL_API int pl_orb_search_last_frame(pl_match* h, const pl_frame_view* Cur, const pl_lastframe_view* Last, float th,
+                                    int mono, int check_orientation, int* match_of_feature, int* n_matches);
+
+/* D2: LineMatcher::LineMatching predicate (LineMatcher.cpp:1463-1504) evaluated for all pairs, followed by the
+ * "last matching i wins, every hit counts" rule of LineMatcher::SearchByProjection (LineMatcher.cpp:215-233) and
+ * its relaxed retry (:235-261).  proj = already projected/clipped keylines (new_KeyLines) with descriptors;
+ * cur = current frame's keylines.  cur_claimed[j]=1 skips j (:217-219).  match_of_line[j] = index into proj or -1.
+ * (D3/D4/D5 differ only in how proj is produced; see pl_line_project.) */
+PL_API int pl_line_match_pairs(pl_match* h, const pl_keyline* proj, const uint8_t* proj_desc, int n_proj,
+                               const pl_keyline* cur, const uint8_t* cur_desc, const uint8_t* cur_claimed, int n_cur,
+                               int* match_of_line, int* n_matches, int* used_relaxed);
+
+/* D3/D4/D5 front half: project 3-D map lines with Tcw, handle the behind-camera endpoint, LiangBarsky clip and
+ * UpdateKeyLineData (LineMatcher.cpp:96-212, :1389-1460, :1601-1624).  valid[i] gates line i.  Outputs the
+ * compacted new_KeyLines, new_kl_index. */
+PL_API int pl_line_project(pl_match* h, const double* start3d, const double* end3d, const pl_keyline* src_kl,
+                           const uint8_t* valid, int n, const float tcw[12], float fx, float fy, float cx, float cy,
+                           float min_x, float min_y, float max_x, float max_y, int img_cols, int img_rows,
+                           pl_keyline* out_kl, int* out_index, int* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSLAM_C_H */

@@ -1,0 +1,37 @@
+/* oracle.h — C interface of the CPU oracle (TEST INFRASTRUCTURE ONLY; see the header of each .cpp).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it. */
+#ifndef PL_ORACLE_H
+#define PL_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#include "../include/plslam_c.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+#define ORC_API __attribute__((visibility("default")))
+
+/* ---- OpenCV primitives restated (pinned to cv2 4.13 by tests/test_oracle_orb.py) ---- */
+ORC_API float orc_fast_atan2(float y, float x);
+ORC_API void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep);
+ORC_API void orc_border_reflect101_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep, int border);
+ORC_API void orc_gaussian_blur_fixed_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep, const int* kernel, int ksize);
+ORC_API void orc_gaussian_blur7_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep);
+ORC_API int orc_fast_score_9_16(const uint8_t* p, size_t step);
+ORC_API int orc_fast_detect(const uint8_t* img, int w, int h, size_t step, int threshold, int nonmax, float* xs, float* ys, float* resp, int cap);
+
+/* ---- ORBextractor ---- */
+typedef struct orc_orb orc_orb;
+ORC_API orc_orb* orc_orb_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh);
+ORC_API void orc_orb_destroy(orc_orb* o);
+ORC_API void orc_orb_tables(const orc_orb* o, float* sf, float* invsf, float* sigma2, float* invsigma2, int* perLevel, int* umax);
+ORC_API int orc_distribute_octtree(const float* xs, const float* ys, const float* resp, int n, int minX, int maxX, int minY, int maxY, int N, float* oxs, float* oys, float* oresp, int cap);
+ORC_API int orc_orb_extract(orc_orb* o, const uint8_t* img, int rows, int cols, size_t step, pl_keypoint* kps, uint8_t* desc, int cap, int* n_out);
+ORC_API int orc_orb_level_dims(const orc_orb* o, int level, int* w, int* h);
+ORC_API int orc_orb_level_bordered(const orc_orb* o, int level, uint8_t* out);
+ORC_API int orc_orb_level_blurred(const orc_orb* o, int level, uint8_t* out);
+ORC_API int orc_orb_level_candidates(const orc_orb* o, int level, float* xs, float* ys, float* resp, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

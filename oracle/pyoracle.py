@@ -1,0 +1,189 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libploracle.so).  TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs — never by
+the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libploracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+KL_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                     ("response", "<f4"), ("size", "<f4"), ("sx", "<f4"), ("sy", "<f4"), ("ex", "<f4"), ("ey", "<f4"),
+                     ("sx_oct", "<f4"), ("sy_oct", "<f4"), ("ex_oct", "<f4"), ("ey_oct", "<f4"), ("length", "<f4"),
+                     ("num_pixels", "<i4")])
+assert KP_DTYPE.itemsize == 28 and KL_DTYPE.itemsize == 68
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "plslam_c.h"))
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_fast_atan2.restype = C.c_float
+        _lib.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _lib.orc_orb_create.restype = C.c_void_p
+        _lib.orc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        _lib.orc_orb_destroy.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(img):
+    img = np.asarray(img)
+    assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+    return img
+
+
+def fast_atan2(y, x):
+    y = np.asarray(y, np.float32)
+    x = np.asarray(x, np.float32)
+    f = lib().orc_fast_atan2
+    return np.array([f(float(a), float(b)) for a, b in zip(y.ravel(), x.ravel())], np.float32).reshape(y.shape)
+
+
+def resize_linear(img, dw, dh):
+    img = _u8(img)
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_size_t(img.strides[0]), _p(out),
+                               C.c_int(dw), C.c_int(dh), C.c_size_t(dw))
+    return out
+
+
+def border_reflect101(img, border):
+    img = _u8(img)
+    h, w = img.shape
+    out = np.empty((h + 2 * border, w + 2 * border), np.uint8)
+    lib().orc_border_reflect101_u8(_p(img), C.c_int(w), C.c_int(h), C.c_size_t(img.strides[0]), _p(out),
+                                   C.c_size_t(out.strides[0]), C.c_int(border))
+    return out
+
+
+def gaussian_blur7(img):
+    img = _u8(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orc_gaussian_blur7_u8(_p(img), C.c_int(w), C.c_int(h), C.c_size_t(img.strides[0]), _p(out), C.c_size_t(w))
+    return out
+
+
+def gaussian_blur_fixed(img, kernel):
+    img = _u8(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    k = np.asarray(kernel, np.int32)
+    lib().orc_gaussian_blur_fixed_u8(_p(img), C.c_int(w), C.c_int(h), C.c_size_t(img.strides[0]), _p(out), C.c_size_t(w),
+                                     _p(k), C.c_int(len(k)))
+    return out
+
+
+def fast_detect(img, threshold, nonmax=True):
+    img = _u8(img)
+    h, w = img.shape
+    cap = max(16, h * w)
+    xs = np.empty(cap, np.float32)
+    ys = np.empty(cap, np.float32)
+    rs = np.empty(cap, np.float32)
+    n = lib().orc_fast_detect(_p(img), C.c_int(w), C.c_int(h), C.c_size_t(img.strides[0]), C.c_int(threshold),
+                              C.c_int(1 if nonmax else 0), _p(xs), _p(ys), _p(rs), C.c_int(cap))
+    return xs[:n].copy(), ys[:n].copy(), rs[:n].copy()
+
+
+def distribute_octtree(xs, ys, resp, minX, maxX, minY, maxY, N):
+    xs = np.ascontiguousarray(xs, np.float32)
+    ys = np.ascontiguousarray(ys, np.float32)
+    resp = np.ascontiguousarray(resp, np.float32)
+    n = len(xs)
+    cap = n + 8
+    ox = np.empty(cap, np.float32)
+    oy = np.empty(cap, np.float32)
+    orr = np.empty(cap, np.float32)
+    m = lib().orc_distribute_octtree(_p(xs), _p(ys), _p(resp), C.c_int(n), C.c_int(minX), C.c_int(maxX), C.c_int(minY),
+                                     C.c_int(maxY), C.c_int(N), _p(ox), _p(oy), _p(orr), C.c_int(cap))
+    return ox[:m].copy(), oy[:m].copy(), orr[:m].copy()
+
+
+class OrbOracle:
+    """Mirror of ORB_SLAM2::ORBextractor on the CPU oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self._h = C.c_void_p(lib().orc_orb_create(nfeatures, C.c_float(scale_factor), nlevels, ini_th, min_th))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_orb_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        per = np.empty(n, np.int32)
+        umax = np.empty(16, np.int32)
+        lib().orc_orb_tables(self._h, _p(sf), _p(isf), _p(s2), _p(is2), _p(per), _p(umax))
+        return dict(scale_factors=sf, inv_scale_factors=isf, sigma2=s2, inv_sigma2=is2, per_level=per, umax=umax)
+
+    def extract(self, img):
+        img = _u8(img)
+        cap = self.nfeatures + 4 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        rc = lib().orc_orb_extract(self._h, _p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]),
+                                   C.c_size_t(img.strides[0]), _p(kps), _p(desc), C.c_int(cap), C.byref(n))
+        if rc == -2:
+            return kps[:0], desc[:0]
+        assert rc == 0, rc
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level_dims(self, level):
+        w, h = C.c_int(), C.c_int()
+        assert lib().orc_orb_level_dims(self._h, C.c_int(level), C.byref(w), C.byref(h)) == 0
+        return w.value, h.value
+
+    def level_bordered(self, level):
+        w, h = self.level_dims(level)
+        out = np.empty((h + 38, w + 38), np.uint8)
+        assert lib().orc_orb_level_bordered(self._h, C.c_int(level), _p(out)) == 0
+        return out
+
+    def level_blurred(self, level):
+        w, h = self.level_dims(level)
+        out = np.empty((h, w), np.uint8)
+        rc = lib().orc_orb_level_blurred(self._h, C.c_int(level), _p(out))
+        return out if rc == 0 else None
+
+    def level_candidates(self, level):
+        cap = 1 << 18
+        xs = np.empty(cap, np.float32)
+        ys = np.empty(cap, np.float32)
+        rs = np.empty(cap, np.float32)
+        n = lib().orc_orb_level_candidates(self._h, C.c_int(level), _p(xs), _p(ys), _p(rs), C.c_int(cap))
+        return xs[:n].copy(), ys[:n].copy(), rs[:n].copy()
