@@ -31,6 +31,12 @@ ORC_API int orc_orb_level_bordered(const orc_orb* o, int level, uint8_t* out);
 ORC_API int orc_orb_level_blurred(const orc_orb* o, int level, uint8_t* out);
 ORC_API int orc_orb_level_candidates(const orc_orb* o, int level, float* xs, float* ys, float* resp, int cap);
 
+/* ---- descriptor search (match_oracle.cpp) ---- */
+ORC_API int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+ORC_API void orc_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int* dist);
+ORC_API void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist, int threads);
+ORC_API void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* t, const int* off, const int* cidx, int* dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -187,3 +187,36 @@ class OrbOracle:
         rs = np.empty(cap, np.float32)
         n = lib().orc_orb_level_candidates(self._h, C.c_int(level), _p(xs), _p(ys), _p(rs), C.c_int(cap))
         return xs[:n].copy(), ys[:n].copy(), rs[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# descriptor search
+# ---------------------------------------------------------------------------------------------------------------
+def _rows(a):
+    a = np.ascontiguousarray(a, np.uint8)
+    assert a.ndim == 2 and a.shape[1] == 32
+    return a
+
+
+def hamming_pairs(a, b):
+    a, b = _rows(a), _rows(b)
+    out = np.empty(a.shape[0], np.int32)
+    lib().orc_hamming_pairs(_p(a), _p(b), C.c_int(a.shape[0]), _p(out))
+    return out
+
+
+def hamming_knn2(q, t, threads=1):
+    q, t = _rows(q), _rows(t)
+    idx = np.empty((q.shape[0], 2), np.int32)
+    dist = np.empty((q.shape[0], 2), np.int32)
+    lib().orc_hamming_knn2(_p(q), C.c_int(q.shape[0]), _p(t), C.c_int(t.shape[0]), _p(idx), _p(dist), C.c_int(threads))
+    return idx, dist
+
+
+def hamming_candidates(q, t, off, cidx):
+    q, t = _rows(q), _rows(t)
+    off = np.ascontiguousarray(off, np.int32)
+    cidx = np.ascontiguousarray(cidx, np.int32)
+    out = np.empty(cidx.shape[0], np.int32)
+    lib().orc_hamming_candidates(_p(q), C.c_int(q.shape[0]), _p(t), _p(off), _p(cidx), _p(out))
+    return out

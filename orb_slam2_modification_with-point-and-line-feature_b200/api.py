@@ -1,0 +1,222 @@
+"""Python mirrors of the reference's front-end classes, on top of the C ABI (include/plslam_c.h).
+
+Names, argument meaning and error behaviour follow the reference:
+
+* :class:`ORBextractor`  — reference include/ORBextractor.h:44-107 (ctor, ``operator()``, the getters, the public
+  ``mvImagePyramid``).  An empty image returns silently with no keypoints (src/ORBextractor.cc:1046-1047); a
+  non-uint8 / non-2-D image raises (the reference asserts, :1050).
+* :class:`LineExtractor` — include/LineExtractor.h:23-30.
+* :class:`DescriptorMatcher` — the Hamming searches of ORBmatcher / LineMatcher.
+
+These classes are plumbing for tests and bench.py; the product is the native library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import KL_DTYPE, KP_DTYPE, PlError, check, ptr
+
+
+def _as_gray(image):
+    a = np.asarray(image)
+    if a.size == 0:
+        return None
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise AssertionError("image.type() == CV_8UC1")  # ORBextractor.cc:1050
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class ORBextractor:
+    """ORB_SLAM2::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, device=0, max_cols=640,
+                 max_rows=480, max_batch=1):
+        self._h = C.c_void_p()
+        self.nlevels = nlevels
+        check(N.lib().pl_orb_create(C.byref(self._h), C.c_int(nfeatures), C.c_float(scaleFactor), C.c_int(nlevels),
+                                    C.c_int(iniThFAST), C.c_int(minThFAST), C.c_int(device), C.c_int(max_cols),
+                                    C.c_int(max_rows), C.c_int(max_batch)))
+        self.max_batch = max_batch
+        self._last = None  # (n_frames, rows, cols)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().pl_orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- getters (ORBextractor.h:63-84) ----
+    def GetLevels(self):
+        return N.lib().pl_orb_levels(self._h)
+
+    def GetScaleFactor(self):
+        return float(N.lib().pl_orb_scale_factor(self._h))
+
+    def _vec(self, fn, dtype=np.float32):
+        out = np.empty(self.nlevels, dtype)
+        check(fn(self._h, ptr(out)))
+        return out
+
+    def GetScaleFactors(self):
+        return self._vec(N.lib().pl_orb_scale_factors)
+
+    def GetInverseScaleFactors(self):
+        return self._vec(N.lib().pl_orb_inv_scale_factors)
+
+    def GetScaleSigmaSquares(self):
+        return self._vec(N.lib().pl_orb_level_sigma2)
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._vec(N.lib().pl_orb_inv_level_sigma2)
+
+    def features_per_level(self):
+        return self._vec(N.lib().pl_orb_features_per_level, np.int32)
+
+    def max_keypoints(self):
+        return N.lib().pl_orb_max_keypoints(self._h)
+
+    def last_launches(self):
+        return N.lib().pl_orb_last_launches(self._h)
+
+    # ---- operator() ----
+    def __call__(self, image, mask=None):
+        """Returns (keypoints[KP_DTYPE], descriptors uint8 (n,32)).  `mask` is ignored, as in the reference."""
+        img = _as_gray(image)
+        if img is None:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        cap = self.max_keypoints()
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        check(N.lib().pl_orb_extract(self._h, ptr(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]),
+                                     C.c_size_t(img.strides[0]), ptr(kps), ptr(desc), C.c_int(cap), C.byref(n)))
+        self._last = (1, img.shape[0], img.shape[1])
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, frames):
+        """frames: uint8 (n, rows, cols) C-contiguous.  Returns (kps (n,cap), desc (n,cap,32), counts (n,))."""
+        fr = np.asarray(frames)
+        assert fr.dtype == np.uint8 and fr.ndim == 3 and fr.strides[2] == 1
+        n, rows, cols = fr.shape
+        cap = self.max_keypoints()
+        kps = np.zeros((n, cap), KP_DTYPE)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        cnt = np.zeros(n, np.int32)
+        check(N.lib().pl_orb_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols),
+                                           C.c_size_t(fr.strides[1]), C.c_size_t(fr.strides[0]), ptr(kps), ptr(desc),
+                                           C.c_int(cap), ptr(cnt)))
+        self._last = (min(n, self.max_batch) if n % self.max_batch == 0 else n % self.max_batch, rows, cols)
+        return kps, desc, cnt
+
+    def extract_batch_dev(self, d_gray, n, rows, cols, step, frame_stride, d_kps, d_desc, cap, d_nout):
+        """All pointers are raw device addresses (ints); asynchronous on the handle's stream."""
+        check(N.lib().pl_orb_extract_batch_dev(self._h, ptr(d_gray), C.c_int(n), C.c_int(rows), C.c_int(cols),
+                                               C.c_size_t(step), C.c_size_t(frame_stride), ptr(d_kps), ptr(d_desc),
+                                               C.c_int(cap), ptr(d_nout)))
+
+    def sync(self):
+        check(N.lib().pl_orb_sync(self._h))
+
+    def stream(self):
+        return N.lib().pl_orb_stream(self._h)
+
+    # ---- mvImagePyramid (ORBextractor.h:85) and test hooks ----
+    def pyramid_level(self, level, frame=0, bordered=False):
+        rows, cols = C.c_int(), C.c_int()
+        check(N.lib().pl_orb_pyramid_dims(self._h, C.c_int(level), C.byref(rows), C.byref(cols)))
+        out = np.empty((rows.value + 38, cols.value + 38), np.uint8)
+        check(N.lib().pl_orb_pyramid_read(self._h, C.c_int(frame), C.c_int(level), ptr(out), C.c_size_t(out.strides[0])))
+        return out if bordered else out[19:-19, 19:-19]
+
+    @property
+    def mvImagePyramid(self):
+        return [self.pyramid_level(l) for l in range(self.nlevels)]
+
+    def blurred_level(self, level, frame=0):
+        rows, cols = C.c_int(), C.c_int()
+        check(N.lib().pl_orb_pyramid_dims(self._h, C.c_int(level), C.byref(rows), C.byref(cols)))
+        out = np.empty((rows.value, cols.value), np.uint8)
+        check(N.lib().pl_orb_blurred_read(self._h, C.c_int(frame), C.c_int(level), ptr(out), C.c_size_t(out.strides[0])))
+        return out
+
+    def candidates(self, level, frame=0):
+        cap = 1 << 16
+        xs, ys, rs = (np.empty(cap, np.float32) for _ in range(3))
+        n = C.c_int(0)
+        check(N.lib().pl_orb_candidates_read(self._h, C.c_int(frame), C.c_int(level), ptr(xs), ptr(ys), ptr(rs),
+                                             C.c_int(cap), C.byref(n)))
+        return xs[:n.value].copy(), ys[:n.value].copy(), rs[:n.value].copy()
+
+
+class DescriptorMatcher:
+    """Hamming searches shared by ORBmatcher (src/ORBmatcher.cc) and LineMatcher (src/LineMatcher.cpp)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(N.lib().pl_match_create(C.byref(self._h), C.c_int(device)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().pl_match_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(N.lib().pl_match_sync(self._h))
+
+    def stream(self):
+        return N.lib().pl_match_stream(self._h)
+
+    def last_launches(self):
+        return N.lib().pl_match_last_launches(self._h)
+
+    @staticmethod
+    def _rows(a):
+        a = np.ascontiguousarray(a, np.uint8)
+        assert a.ndim == 2 and a.shape[1] == 32
+        return a
+
+    def DescriptorDistance(self, a, b):
+        """ORBmatcher::DescriptorDistance / LineMatcher::DescriptorDistance for row pairs."""
+        a, b = self._rows(a), self._rows(b)
+        assert a.shape == b.shape
+        out = np.empty(a.shape[0], np.int32)
+        check(N.lib().pl_hamming_pairs(self._h, ptr(a), ptr(b), C.c_int(a.shape[0]), ptr(out)))
+        return out
+
+    def knnMatch2(self, query, train):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) -> (idx (nq,2), dist (nq,2))."""
+        q, t = self._rows(query), self._rows(train)
+        idx = np.empty((q.shape[0], 2), np.int32)
+        dist = np.empty((q.shape[0], 2), np.int32)
+        check(N.lib().pl_hamming_knn2(self._h, ptr(q), C.c_int(q.shape[0]), ptr(t) if t.shape[0] else ptr(None),
+                                      C.c_int(t.shape[0]), ptr(idx), ptr(dist)))
+        return idx, dist
+
+    def knn2_dev(self, d_q, nq, d_t, nt, d_idx, d_dist):
+        check(N.lib().pl_hamming_knn2_dev(self._h, ptr(d_q), C.c_int(nq), ptr(d_t), C.c_int(nt), ptr(d_idx), ptr(d_dist)))
+
+    def candidate_distances(self, query, train, cand_off, cand_idx):
+        q, t = self._rows(query), self._rows(train)
+        off = np.ascontiguousarray(cand_off, np.int32)
+        ci = np.ascontiguousarray(cand_idx, np.int32)
+        assert off.shape[0] == q.shape[0] + 1
+        out = np.empty(ci.shape[0], np.int32)
+        check(N.lib().pl_hamming_candidates(self._h, ptr(q), C.c_int(q.shape[0]), ptr(t), C.c_int(t.shape[0]), ptr(off),
+                                            ptr(ci), ptr(out)))
+        return out
