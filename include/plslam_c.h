@@ -128,6 +128,14 @@ PL_API int pl_orb_candidates_read(pl_orb* h, int frame, int level, float* xs, fl
 PL_API int pl_orb_blurred_read(pl_orb* h, int frame, int level, uint8_t* out, size_t out_step);
 /* number of kernel launches issued by the last extract call (bench.py's gpu_launches claim) */
 PL_API int pl_orb_last_launches(const pl_orb* h);
+/* Measurement hooks.  With profiling on, every chunk records CUDA events on the launching stream between the
+ * stages {0 pyramid, 1 FAST cells, 2 quadtree, 3 blur, 4 orientation+BRIEF} and pl_orb_stage_ms returns the
+ * accumulated milliseconds per stage since profiling was switched on (and the number of chunks). */
+PL_API int pl_orb_set_profiling(pl_orb* h, int on);
+PL_API int pl_orb_stage_ms(pl_orb* h, float* out5, int* chunks);
+/* sizes of the current geometry: allocated pyramid / blurred bytes per frame, sum of level pixels (P) and of
+ * bordered level pixels (Pb) — the quantities SURVEY.md §8(d)'s algorithmic-bytes formulas use */
+PL_API int pl_orb_bytes_per_frame(const pl_orb* h, long long* pyr, long long* blur, long long* level_px, long long* bordered_px);
 
 /* ------------------------------------------------------------------------------------------------------------
  * B. Line extraction — replaces LineExtractor::ExtractLineSegment (LineExtractor.cpp:12-70; LineExtractor.h:25-30):

@@ -37,6 +37,13 @@ ORC_API void orc_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int* d
 ORC_API void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist, int threads);
 ORC_API void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* t, const int* off, const int* cidx, int* dist);
 
+/* ---- line extraction (line_oracle.cpp) ---- */
+ORC_API int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t step, int order_mode, float* xyxy, double* width, double* prec, double* nfa, int cap);
+ORC_API int orc_lsd_angles(const uint8_t* img, int rows, int cols, size_t step, double* out, int* ow, int* oh);
+ORC_API int orc_lsd_scaled(const uint8_t* img, int rows, int cols, size_t step, uint8_t* out, int* ow, int* oh);
+ORC_API int orc_lbd_compute(const uint8_t* img, int rows, int cols, size_t step, const pl_keyline* kls, int n, uint8_t* desc, float* fdesc);
+ORC_API int orc_line_extract(const uint8_t* img, int rows, int cols, size_t step, int max_lines, int order_mode, pl_keyline* kls, uint8_t* desc, double* coeffs, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,7 @@ def _p(a: np.ndarray):
 
 def _u8(img):
     img = np.asarray(img)
-    assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+    assert img.dtype == np.uint8 and img.ndim == 2 and (img.size == 0 or img.strides[1] == 1)
     return img
 
 
@@ -220,3 +220,55 @@ def hamming_candidates(q, t, off, cidx):
     out = np.empty(cidx.shape[0], np.int32)
     lib().orc_hamming_candidates(_p(q), C.c_int(q.shape[0]), _p(t), _p(off), _p(cidx), _p(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# line extraction
+# ---------------------------------------------------------------------------------------------------------------
+def lsd_detect(img, order_mode=0, cap=20000):
+    """cv::createLineSegmentDetector(LSD_REFINE_ADV).detect -> (lines (n,4) f32, width, prec, nfa f64)."""
+    img = _u8(img)
+    xy = np.empty((cap, 4), np.float32)
+    w, p, nf = (np.empty(cap, np.float64) for _ in range(3))
+    n = lib().orc_lsd_detect(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]),
+                             C.c_int(order_mode), _p(xy), _p(w), _p(p), _p(nf), C.c_int(cap))
+    assert n <= cap
+    return xy[:n].copy(), w[:n].copy(), p[:n].copy(), nf[:n].copy()
+
+
+def lsd_scaled(img):
+    img = _u8(img)
+    ow, oh = C.c_int(), C.c_int()
+    lib().orc_lsd_scaled(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]), None,
+                         C.byref(ow), C.byref(oh))
+    out = np.empty((oh.value, ow.value), np.uint8)
+    lib().orc_lsd_scaled(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]), _p(out),
+                         C.byref(ow), C.byref(oh))
+    return out
+
+
+def lbd_compute(img, kls):
+    img = _u8(img)
+    kls = np.ascontiguousarray(kls, KL_DTYPE)
+    n = len(kls)
+    desc = np.zeros((n, 32), np.uint8)
+    fdesc = np.zeros((n, 72), np.float32)
+    lib().orc_lbd_compute(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]), _p(kls),
+                          C.c_int(n), _p(desc), _p(fdesc))
+    return desc, fdesc
+
+
+def line_extract(img, max_lines=80, order_mode=0):
+    """LineExtractor::ExtractLineSegment -> (keylines[KL_DTYPE], desc (n,32), coeffs (n,3) f64)."""
+    img = _u8(img)
+    cap = max(max_lines, 1)
+    kls = np.zeros(cap, KL_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    co = np.zeros((cap, 3), np.float64)
+    n = C.c_int(0)
+    rc = lib().orc_line_extract(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]),
+                                C.c_int(max_lines), C.c_int(order_mode), _p(kls), _p(desc), _p(co), C.byref(n))
+    if rc == -2:
+        return kls[:0], desc[:0], co[:0]
+    assert rc == 0, rc
+    return kls[:n.value].copy(), desc[:n.value].copy(), co[:n.value].copy()

@@ -842,6 +842,11 @@ struct pl_orb {
     int last_batch = 0;      // frames of the last chunk (for debug reads)
     int last_launches = 0;
     size_t oct_smem = 0;
+    // optional per-stage timing (CUDA events on the launching stream)
+    bool profiling = false;
+    cudaEvent_t ev[8] = {nullptr};
+    float stage_ms[8] = {0};
+    int stage_chunks = 0;
 };
 
 namespace {
@@ -1047,6 +1052,8 @@ int launch_chunk(pl_orb* h, const uint8_t* d_gray, int nf, size_t step, size_t f
     int launches = 0;
     PL_CUDA_TRY(cudaMemsetAsync(h->d_lvl_count, 0, sizeof(int) * (size_t)nf * G.nlevels, st));
     PL_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * (size_t)nf, st));
+    const bool prof = h->profiling;
+    if (prof) cudaEventRecord(h->ev[0], st);
     {
         const LevelGeom& L = G.lv[0];
         dim3 grid((L.pitch / 4 + 255) / 256, L.h + 2 * kEdge, nf);
@@ -1060,19 +1067,33 @@ int launch_chunk(pl_orb* h, const uint8_t* d_gray, int nf, size_t step, size_t f
         else k_pyr_resize<<<grid, 256, 0, st>>>(h->d_geom, l, h->d_tabs, h->d_pyr);
         launches++;
     }
+    if (prof) cudaEventRecord(h->ev[1], st);
     k_fast_cells<<<dim3(G.total_cells, nf), kFastThreads, 0, st>>>(h->d_geom, h->d_cells, h->d_pyr, h->d_cand, h->d_cell_off,
                                                                   h->d_cell_cnt, h->d_lvl_count, h->d_flags);
     launches++;
+    if (prof) cudaEventRecord(h->ev[2], st);
     k_octree<<<dim3(G.nlevels, nf), kOctThreads, h->oct_smem, st>>>(h->d_geom, h->d_cand, h->d_cell_off, h->d_cell_cnt,
                                                                    h->d_lvl_count, h->d_ord, h->d_node, h->d_lvl_kp, h->d_lvl_n,
                                                                    h->d_flags);
     launches++;
+    if (prof) cudaEventRecord(h->ev[3], st);
     k_blur7<<<dim3(G.total_tiles, nf), 256, 0, st>>>(h->d_geom, h->d_tiles, h->d_pyr, h->d_blur);
     launches++;
+    if (prof) cudaEventRecord(h->ev[4], st);
     k_orient_brief<<<dim3((G.out_per_frame + 7) / 8, nf), 256, 0, st>>>(h->d_geom, h->d_pyr, h->d_blur, h->d_lvl_kp, h->d_lvl_n,
                                                                         d_kps, d_desc, cap, d_nout, h->d_flags);
     launches++;
     PL_CUDA_TRY(cudaGetLastError());
+    if (prof) {
+        cudaEventRecord(h->ev[5], st);
+        PL_CUDA_TRY(cudaEventSynchronize(h->ev[5]));
+        for (int i = 0; i < 5; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+            h->stage_ms[i] += ms;
+        }
+        h->stage_chunks++;
+    }
     h->last_batch = nf;
     h->last_launches += launches;
     return PL_OK;
@@ -1178,6 +1199,8 @@ PL_API void pl_orb_destroy(pl_orb* h) {
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    for (int i = 0; i < 8; i++)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1201,6 +1224,36 @@ PL_API int pl_orb_features_per_level(const pl_orb* h, int* out) {
 PL_API int pl_orb_max_keypoints(const pl_orb* h) { return h ? h->geom.out_per_frame : 0; }
 PL_API void* pl_orb_stream(pl_orb* h) { return h ? (void*)h->stream : nullptr; }
 PL_API int pl_orb_last_launches(const pl_orb* h) { return h ? h->last_launches : 0; }
+
+PL_API int pl_orb_set_profiling(pl_orb* h, int on) {
+    PL_CHECK_ARG(h);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    if (on && !h->ev[0])
+        for (int i = 0; i < 8; i++) PL_CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    h->profiling = on != 0;
+    for (int i = 0; i < 8; i++) h->stage_ms[i] = 0;
+    h->stage_chunks = 0;
+    return PL_OK;
+}
+PL_API int pl_orb_stage_ms(pl_orb* h, float* out5, int* chunks) {
+    PL_CHECK_ARG(h && out5);
+    for (int i = 0; i < 5; i++) out5[i] = h->stage_ms[i];
+    if (chunks) *chunks = h->stage_chunks;
+    return PL_OK;
+}
+PL_API int pl_orb_bytes_per_frame(const pl_orb* h, long long* pyr, long long* blur, long long* level_px, long long* bordered_px) {
+    PL_CHECK_ARG(h);
+    long long P = 0, Pb = 0;
+    for (int l = 0; l < h->nlevels; l++) {
+        P += (long long)h->geom.lv[l].w * h->geom.lv[l].h;
+        Pb += (long long)(h->geom.lv[l].w + 2 * kEdge) * (h->geom.lv[l].h + 2 * kEdge);
+    }
+    if (pyr) *pyr = (long long)h->pyr_bytes_per_frame;
+    if (blur) *blur = (long long)h->blur_bytes_per_frame;
+    if (level_px) *level_px = P;
+    if (bordered_px) *bordered_px = Pb;
+    return PL_OK;
+}
 
 PL_API int pl_orb_sync(pl_orb* h) {
     PL_CHECK_ARG(h);
