@@ -161,6 +161,16 @@ PL_API int pl_line_sync(pl_line* h);
 PL_API void* pl_line_stream(pl_line* h);
 PL_API int pl_line_last_launches(const pl_line* h);
 
+/* Measurement hooks: stages {0 blur+scale+gradient, 1 seed sort, 2 region growing/NFA, 3 KeyLines+blur5+Sobel, 4 LBD} */
+PL_API int pl_line_set_profiling(pl_line* h, int on);
+PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
+/* Test hooks: the 0.8-scaled 8-bit image LSD works on, its level-line angle map (float degrees, -1024 = undefined,
+ * rows x cols of the scaled image) and the float LBD descriptors (n x 72) of frame `frame` of the last call. */
+PL_API int pl_line_scaled_dims(const pl_line* h, int* rows, int* cols);
+PL_API int pl_line_scaled_read(pl_line* h, int frame, uint8_t* out, size_t out_step);
+PL_API int pl_line_angles_read(pl_line* h, int frame, float* out);
+PL_API int pl_line_fdesc_read(pl_line* h, int frame, float* out, int n);
+
 /* Test hook: ALL LSD segments of frame `frame` of the last call before the top-`max_lines` filter, in detection
  * order: x1,y1,x2,y2 (float, image coordinates) + width, prec(p), nfa as doubles
  * (cv::LineSegmentDetector::detect outputs). */

@@ -714,8 +714,9 @@ extern "C" int orc_line_extract(const uint8_t* img, int rows, int cols, size_t s
     std::vector<pl_keyline> key_lines(segs.size());
     for (size_t i = 0; i < segs.size(); i++) fill_keyline(segs[i], cols, rows, (int)i, key_lines[i]);
     if ((int)key_lines.size() > max_lines) {
-        // :27-30 — std::sort by response, descending (ties: libstdc++ introsort order, as in the reference build)
-        std::sort(key_lines.begin(), key_lines.end(), [](const pl_keyline& a, const pl_keyline& b) { return a.response > b.response; });
+        // :27-30 — sort by response, descending.  The reference uses std::sort, whose order among EXACT float ties is
+        // an artefact of libstdc++'s introsort; the contract here is: ties keep detection order (stable).
+        std::stable_sort(key_lines.begin(), key_lines.end(), [](const pl_keyline& a, const pl_keyline& b) { return a.response > b.response; });
         key_lines.resize(max_lines);
     }
     const int n = (int)key_lines.size();

@@ -158,6 +158,94 @@ class ORBextractor:
         return xs[:n.value].copy(), ys[:n.value].copy(), rs[:n.value].copy()
 
 
+class LineExtractor:
+    """ORB_SLAM2::LineExtractor — ExtractLineSegment(img, key_lines, line_descriptor, keyline_coefficients)."""
+
+    NUMS_LINE_FEATURE = 80  # LineExtractor.cpp:23
+
+    def __init__(self, device=0, max_cols=640, max_rows=480, max_batch=1):
+        self._h = C.c_void_p()
+        check(N.lib().pl_line_create(C.byref(self._h), C.c_int(device), C.c_int(max_cols), C.c_int(max_rows), C.c_int(max_batch)))
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().pl_line_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ExtractLineSegment(self, img, max_lines=NUMS_LINE_FEATURE):
+        """Returns (key_lines[KL_DTYPE], line_descriptor uint8 (n,32), keyline_coefficients float64 (n,3))."""
+        im = _as_gray(img)
+        if im is None:
+            return np.zeros(0, KL_DTYPE), np.zeros((0, 32), np.uint8), np.zeros((0, 3), np.float64)
+        kls = np.zeros(max_lines, KL_DTYPE)
+        desc = np.zeros((max_lines, 32), np.uint8)
+        co = np.zeros((max_lines, 3), np.float64)
+        n = C.c_int(0)
+        check(N.lib().pl_line_extract(self._h, ptr(im), C.c_int(im.shape[0]), C.c_int(im.shape[1]), C.c_size_t(im.strides[0]),
+                                      C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), C.byref(n)))
+        return kls[:n.value].copy(), desc[:n.value].copy(), co[:n.value].copy()
+
+    def extract_batch(self, frames, max_lines=NUMS_LINE_FEATURE):
+        fr = np.asarray(frames)
+        assert fr.dtype == np.uint8 and fr.ndim == 3 and fr.strides[2] == 1
+        n, rows, cols = fr.shape
+        kls = np.zeros((n, max_lines), KL_DTYPE)
+        desc = np.zeros((n, max_lines, 32), np.uint8)
+        co = np.zeros((n, max_lines, 3), np.float64)
+        cnt = np.zeros(n, np.int32)
+        check(N.lib().pl_line_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(fr.strides[1]),
+                                            C.c_size_t(fr.strides[0]), C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), ptr(cnt)))
+        return kls, desc, co, cnt
+
+    def extract_batch_dev(self, d_gray, n, rows, cols, step, frame_stride, max_lines, d_kls, d_desc, d_coef, d_nout):
+        check(N.lib().pl_line_extract_batch_dev(self._h, ptr(d_gray), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(step),
+                                                C.c_size_t(frame_stride), C.c_int(max_lines), ptr(d_kls), ptr(d_desc), ptr(d_coef),
+                                                ptr(d_nout)))
+
+    def sync(self):
+        check(N.lib().pl_line_sync(self._h))
+
+    def stream(self):
+        return N.lib().pl_line_stream(self._h)
+
+    def last_launches(self):
+        return N.lib().pl_line_last_launches(self._h)
+
+    # ---- test hooks ----
+    def lsd_segments(self, frame=0, cap=30000):
+        xy = np.empty((cap, 4), np.float32)
+        w, p, nf = (np.empty(cap, np.float64) for _ in range(3))
+        n = C.c_int(0)
+        check(N.lib().pl_line_lsd_read(self._h, C.c_int(frame), ptr(xy), ptr(w), ptr(p), ptr(nf), C.c_int(cap), C.byref(n)))
+        return xy[:n.value].copy(), w[:n.value].copy(), p[:n.value].copy(), nf[:n.value].copy()
+
+    def scaled_image(self, frame=0):
+        r, c = C.c_int(), C.c_int()
+        check(N.lib().pl_line_scaled_dims(self._h, C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), np.uint8)
+        check(N.lib().pl_line_scaled_read(self._h, C.c_int(frame), ptr(out), C.c_size_t(out.strides[0])))
+        return out
+
+    def angle_map(self, frame=0):
+        r, c = C.c_int(), C.c_int()
+        check(N.lib().pl_line_scaled_dims(self._h, C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), np.float32)
+        check(N.lib().pl_line_angles_read(self._h, C.c_int(frame), ptr(out)))
+        return out
+
+    def float_descriptors(self, n, frame=0):
+        out = np.empty((n, 72), np.float32)
+        check(N.lib().pl_line_fdesc_read(self._h, C.c_int(frame), ptr(out), C.c_int(n)))
+        return out
+
+
 class DescriptorMatcher:
     """Hamming searches shared by ORBmatcher (src/ORBmatcher.cc) and LineMatcher (src/LineMatcher.cpp)."""
 

@@ -1,0 +1,1496 @@
+// line_kernels.cu — line extraction on sm_100a: the CUDA path behind pl_line_* (include/plslam_c.h).
+//
+// Replaces LineExtractor::ExtractLineSegment (reference src/LineExtractor.cpp:12-70) and the OpenCV code it calls:
+//   LSDDetector::detect -> cv::LineSegmentDetector(LSD_REFINE_ADV)  (imgproc/src/lsd.cpp, OpenCV 4.13 behaviour)
+//       k_lsd_scale      GaussianBlur 7x7 sigma 0.75 (8.8 fixed point) + resize 0.8 INTER_LINEAR_EXACT, fused, smem tile
+//       k_lsd_grad       2x2 gradient, level-line angle (fastAtan2), |grad|^2, per-frame max        (streaming)
+//       k_lsd_bin_count / k_lsd_bin_scan / k_lsd_scatter   stable counting sort of the seeds by 1024 gradient bins
+//       k_lsd_grow       sequential-semantics region growing + rect fit + refine + NFA (one warp per frame)
+//   top-80 by response (:23-35) + KeyLine fields (LSDDetector.cpp)  -> k_line_finalize
+//   BinaryDescriptor::compute (binary_descriptor.cpp)               -> k_lbd_sobel (blur 5x5 sigma 1 + Sobel, fused),
+//                                                                     k_lbd_rows, k_lbd_finish
+//   line coefficients (:60-69)                                      -> k_lbd_finish
+//
+// Region growing is inherently ordered (greedy by gradient bin, shared USED map, running region angle); it is
+// executed with the reference's visiting order by one warp per frame whose lanes test the 3x3 neighbourhoods of
+// up to three region points at once and resolve acceptances in order.  Throughput comes from many frames in
+// flight; it is a latency-bound stage and is reported as time, not as an HBM fraction.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "pl_common.cuh"
+
+namespace pl {
+
+constexpr double kPiD = 3.14159265358979323846;
+constexpr double kDegToRad = kPiD / 180;
+constexpr double k2Pi = 2 * kPiD;
+constexpr double k32Pi = (3 * kPiD) / 2;
+constexpr float kNotDefDeg = -1024.0f;  // stored angle of pixels with undefined gradient
+constexpr int kBins = 1024;
+constexpr int kTileRows = 8;  // rows per sort tile (one warp walks a tile in raster order)
+
+struct LineGeom {
+    int cols, rows;        // input image
+    int W, H;              // LSD works on the 0.8-scaled image
+    int in_pitch;          // staged input pitch
+    int spitch;            // scaled image pitch (bytes)
+    int n_tiles;           // sort tiles per frame
+    int seg_cap;           // max LSD segments per frame
+    int reg_cap;           // max region size (= W*H)
+    int min_reg_size;
+    double log_nt;
+    int max_lines;
+    int dpitch;            // Sobel plane pitch in elements
+};
+struct ExactTab {  // INTER_LINEAR_EXACT coefficients (8.8 fixed point)
+    short ofs, c0, c1, pad;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_lsd_scale: GaussianBlur(7x7, 0.75) -> 8-bit, then resize(0.8, INTER_LINEAR_EXACT)  (lsd.cpp flsd())
+// fixed-point blur kernel {0,4,56,136,56,4,0}/256 (the outer taps are zero: a 5-tap filter)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kScTW = 64, kScTH = 16;                    // output tile
+constexpr int kScSW = kScTW * 5 / 4 + 4, kScSH = kScTH * 5 / 4 + 4;  // source tile bound (scale 1.25 + bilinear + slack)
+
+__global__ void __launch_bounds__(256) k_lsd_scale(LineGeom g, const uint8_t* __restrict__ in, size_t in_pitch,
+                                                   size_t in_frame_stride, const ExactTab* __restrict__ xtab,
+                                                   const ExactTab* __restrict__ ytab, uint8_t* __restrict__ scaled,
+                                                   size_t scaled_frame_stride) {
+    __shared__ uint8_t s_src[(kScSH + 4) * (kScSW + 4)];   // source tile + 2 px blur halo
+    __shared__ uint16_t s_h[(kScSH + 4) * kScSW];           // after horizontal pass
+    __shared__ uint8_t s_b[kScSH * kScSW];                  // blurred 8-bit
+    const int f = blockIdx.z, tid = threadIdx.x;
+    const int ox0 = blockIdx.x * kScTW, oy0 = blockIdx.y * kScTH;
+    const int ox1 = min(ox0 + kScTW, g.W) - 1, oy1 = min(oy0 + kScTH, g.H) - 1;
+    // source span needed by this output tile
+    const int sx0 = xtab[ox0].ofs, sx1 = min((int)xtab[ox1].ofs + 1, g.cols - 1);
+    const int sy0 = ytab[oy0].ofs, sy1 = min((int)ytab[oy1].ofs + 1, g.rows - 1);
+    const int sw = sx1 - sx0 + 1, sh = sy1 - sy0 + 1;  // <= kScSW, kScSH
+    const uint8_t* src = in + (size_t)f * in_frame_stride;
+    constexpr int SP = kScSW + 4;
+    for (int i = tid; i < (sh + 4) * (sw + 4); i += 256) {
+        int r = i / (sw + 4), c = i - r * (sw + 4);
+        int yy = reflect101(sy0 + r - 2, g.rows), xx = reflect101(sx0 + c - 2, g.cols);
+        s_src[r * SP + c] = __ldg(src + (size_t)yy * in_pitch + xx);
+    }
+    __syncthreads();
+    for (int i = tid; i < (sh + 4) * sw; i += 256) {
+        int r = i / sw, c = i - r * sw;
+        const uint8_t* p = s_src + r * SP + c;
+        s_h[r * kScSW + c] = (uint16_t)(4 * (p[0] + p[4]) + 56 * (p[1] + p[3]) + 136 * p[2]);
+    }
+    __syncthreads();
+    for (int i = tid; i < sh * sw; i += 256) {
+        int r = i / sw, c = i - r * sw;
+        const uint16_t* p = s_h + r * kScSW + c;
+        uint32_t acc = 4u * (p[0] + p[4 * kScSW]) + 56u * (p[kScSW] + p[3 * kScSW]) + 136u * p[2 * kScSW];
+        s_b[r * kScSW + c] = (uint8_t)((acc + 0x8000u) >> 16);
+    }
+    __syncthreads();
+    uint8_t* dst = scaled + (size_t)f * scaled_frame_stride;
+    for (int i = tid; i < kScTW * kScTH; i += 256) {
+        int r = i / kScTW, c = i - r * kScTW;
+        int ox = ox0 + c, oy = oy0 + r;
+        if (ox >= g.W || oy >= g.H) continue;
+        const ExactTab tx = xtab[ox], ty = ytab[oy];
+        const int ax = tx.ofs - sx0, bx = min(tx.ofs + 1, g.cols - 1) - sx0;
+        const int ay = ty.ofs - sy0, by = min(ty.ofs + 1, g.rows - 1) - sy0;
+        uint32_t r0 = s_b[ay * kScSW + ax] * tx.c0 + s_b[ay * kScSW + bx] * tx.c1;
+        uint32_t r1 = s_b[by * kScSW + ax] * tx.c0 + s_b[by * kScSW + bx] * tx.c1;
+        dst[(size_t)oy * g.spitch + ox] = (uint8_t)((r0 * ty.c0 + r1 * ty.c1 + 32768u) >> 16);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_lsd_grad: ll_angle() — gradient with a 2x2 mask, level-line angle, squared modulus, per-frame max
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __restrict__ scaled, size_t scaled_frame_stride,
+                                                  float* __restrict__ angdeg, int* __restrict__ g2, size_t plane, double rho,
+                                                  int* __restrict__ max_g2) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    int my = -1;
+    if (x < g.W && y < g.H) {
+        float a = kNotDefDeg;
+        int q = 0;
+        if (x < g.W - 1 && y < g.H - 1) {
+            const uint8_t* r0 = scaled + (size_t)f * scaled_frame_stride + (size_t)y * g.spitch + x;
+            const uint8_t* r1 = r0 + g.spitch;
+            const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
+            const int gx = DA + BC, gy = DA - BC;
+            q = gx * gx + gy * gy;
+            const double norm = sqrt((double)q / 4.0);
+            if (norm > rho) {
+                a = fast_atan2_deg((float)gx, (float)(-gy));
+                my = q;
+            }
+        }
+        angdeg[(size_t)f * plane + (size_t)y * g.W + x] = a;
+        g2[(size_t)f * plane + (size_t)y * g.W + x] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my = max(my, __shfl_xor_sync(0xffffffffu, my, o));
+    if ((threadIdx.x & 31) == 0 && my >= 0) atomicMax(max_g2 + f, my);
+}
+
+// gradient bin of a pixel (ll_angle(): int(norm * bin_coef)), or -1 when the gradient is undefined
+__device__ __forceinline__ int lsd_bin(float a, int q, double bin_coef) {
+    if (a == kNotDefDeg) return -1;
+    return (int)(sqrt((double)q / 4.0) * bin_coef);
+}
+__device__ __forceinline__ double lsd_bin_coef(int maxq) {
+    if (maxq < 0) return 0.0;
+    const double max_grad = sqrt((double)maxq / 4.0);
+    return max_grad > 0 ? (double)(kBins - 1) / max_grad : 0.0;
+}
+
+// per-tile histograms: one warp walks kTileRows rows
+__global__ void __launch_bounds__(256) k_lsd_bin_count(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
+                                                       size_t plane, const int* __restrict__ max_g2,
+                                                       unsigned short* __restrict__ tile_hist) {
+    __shared__ int s_hist[8][kBins];
+    const int f = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 8 + w;
+    for (int i = lane; i < kBins; i += 32) s_hist[w][i] = 0;
+    __syncwarp();
+    if (tile < g.n_tiles) {
+        const double coef = lsd_bin_coef(max_g2[f]);
+        const int y0 = tile * kTileRows, y1 = min(y0 + kTileRows, g.H - 1);
+        for (int y = y0; y < y1; y++) {
+            const size_t row = (size_t)f * plane + (size_t)y * g.W;
+            for (int x = lane; x < g.W - 1; x += 32) {
+                int b = lsd_bin(angdeg[row + x], g2[row + x], coef);
+                if (b >= 0) atomicAdd(&s_hist[w][b], 1);
+            }
+        }
+        __syncwarp();
+        unsigned short* out = tile_hist + ((size_t)f * g.n_tiles + tile) * kBins;
+        for (int i = lane; i < kBins; i += 32) out[i] = (unsigned short)s_hist[w][i];
+    }
+}
+
+// per frame: exclusive offsets over (bin descending, tile ascending); tile_off[tile][bin]; n_seeds[f] = total
+__global__ void __launch_bounds__(kBins) k_lsd_bin_scan(LineGeom g, const unsigned short* __restrict__ tile_hist,
+                                                        int* __restrict__ tile_off, int* __restrict__ n_seeds) {
+    __shared__ int s_warp[33];
+    const int f = blockIdx.x, t = threadIdx.x;
+    const int bin = kBins - 1 - t;  // thread t owns the t-th bin in visiting order
+    const unsigned short* h = tile_hist + (size_t)f * g.n_tiles * kBins;
+    int tot = 0;
+    for (int k = 0; k < g.n_tiles; k++) tot += h[(size_t)k * kBins + bin];
+    // block exclusive scan over t
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        int v = s_warp[t], w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (t >= o) w += u;
+        }
+        s_warp[t] = w - v;
+        if (t == 31) s_warp[32] = w;
+    }
+    __syncthreads();
+    int run = s_warp[t >> 5] + incl - tot;
+    int* o = tile_off + (size_t)f * g.n_tiles * kBins;
+    for (int k = 0; k < g.n_tiles; k++) {
+        o[(size_t)k * kBins + bin] = run;
+        run += h[(size_t)k * kBins + bin];
+    }
+    if (t == 0) n_seeds[f] = s_warp[32];
+}
+
+// stable scatter: seeds[f][pos] = raster index (y*W+x); order = bin descending, raster ascending inside a bin
+__global__ void __launch_bounds__(256) k_lsd_scatter(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
+                                                     size_t plane, const int* __restrict__ max_g2, const int* __restrict__ tile_off,
+                                                     unsigned int* __restrict__ seeds) {
+    __shared__ int s_off[8][kBins];
+    const int f = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 8 + w;
+    if (tile >= g.n_tiles) return;
+    const int* off = tile_off + ((size_t)f * g.n_tiles + tile) * kBins;
+    for (int i = lane; i < kBins; i += 32) s_off[w][i] = off[i];
+    __syncwarp();
+    const double coef = lsd_bin_coef(max_g2[f]);
+    unsigned int* out = seeds + (size_t)f * plane;
+    const int y0 = tile * kTileRows, y1 = min(y0 + kTileRows, g.H - 1);
+    const unsigned lt = (1u << lane) - 1u;
+    for (int y = y0; y < y1; y++) {
+        const size_t row = (size_t)f * plane + (size_t)y * g.W;
+        for (int xb = 0; xb < g.W - 1; xb += 32) {
+            const int x = xb + lane;
+            int b = -1;
+            if (x < g.W - 1) b = lsd_bin(angdeg[row + x], g2[row + x], coef);
+            const unsigned valid = __ballot_sync(0xffffffffu, b >= 0);
+            if (b >= 0) {
+                const unsigned peers = __match_any_sync(valid, b);
+                const int rank = __popc(peers & lt);
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (lane == leader) {
+                    base = s_off[w][b];
+                    s_off[w][b] = base + __popc(peers);
+                }
+                base = __shfl_sync(peers, base, leader);
+                out[base + rank] = (unsigned)(y * g.W + x);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace pl
+
+// =================================================================================================================
+// k_lsd_grow — the ordered part of LSD: one warp per frame
+// =================================================================================================================
+namespace pl {
+
+struct LsdSeg {  // one detected segment, in detection order (== cv::LineSegmentDetector::detect outputs)
+    float x1, y1, x2, y2;
+    double width, p, nfa;
+};
+struct LsdRect {
+    double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
+};
+struct LsdFrame {  // per-frame device views
+    const float* ang;   // level-line angle in degrees or kNotDefDeg
+    const int* g2;      // gx^2 + gy^2
+    uint8_t* used;
+    unsigned int* reg;  // region points, packed y<<16 | x
+    int W, H;
+};
+
+__device__ __forceinline__ double lsd_angle_diff_signed(double a, double b) {
+    double diff = a - b;
+    while (diff <= -kPiD) diff += k2Pi;
+    while (diff > kPiD) diff -= k2Pi;
+    return diff;
+}
+// isAligned() without the bounds / NOTDEF checks: |theta - a| folded, <= prec
+__device__ __forceinline__ bool lsd_aligned(double theta, double a, double prec) {
+    double n = theta - a;
+    if (n < 0) n = -n;
+    if (n > k32Pi) {
+        n -= k2Pi;
+        if (n < 0) n = -n;
+    }
+    return n <= prec;
+}
+__device__ __forceinline__ double lsd_dist_sq(double x1, double y1, double x2, double y2) {
+    return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
+}
+
+// region_grow(): returns the region size; reg_angle (radians) is returned through *out_angle.
+// Lanes 0..26 hold the 3x3 neighbourhoods of up to three consecutive region points, in the reference's visiting
+// order (point, then row, then column); acceptances are resolved in that order with the running region angle.
+__device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, double* out_angle) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double reg_angle = (double)F.ang[(size_t)sy * F.W + sx] * kDegToRad;
+    // float(std::cos(reg_angle)) — double cosine of the seed angle, rounded to float
+    float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+    if (lane == 0) {
+        F.reg[0] = ((unsigned)sy << 16) | (unsigned)sx;
+        F.used[(size_t)sy * F.W + sx] = 1;
+    }
+    __syncwarp();
+    int n = 1, i = 0;
+    const int b = lane / 9, k = lane - b * 9;
+    const int ddy = k / 3 - 1, ddx = k - (k / 3) * 3 - 1;
+    while (i < n) {
+        const int nb = min(3, n - i);
+        bool cand = false;
+        int xx = 0, yy = 0;
+        float adeg = 0.f, ca = 0.f, sa = 0.f;
+        double arad = 0.0;
+        if (lane < 27 && b < nb) {
+            const unsigned p = F.reg[i + b];
+            xx = (int)(p & 0xffffu) + ddx;
+            yy = (int)(p >> 16) + ddy;
+            if (xx >= 0 && yy >= 0 && xx < F.W && yy < F.H) {
+                const size_t o = (size_t)yy * F.W + xx;
+                adeg = F.ang[o];
+                cand = F.used[o] == 0 && adeg != kNotDefDeg;
+            }
+        }
+        if (cand) {
+            arad = (double)adeg * kDegToRad;
+            const float af = (float)arad;  // cos(float(angle)) / sin(float(angle)) of the reference resolve to cosf / sinf
+            ca = glibc_sincosf(af, 1);
+            sa = glibc_sincosf(af, 0);
+        }
+        unsigned mask = __ballot_sync(FULL, cand);
+        while (mask) {
+            const bool ok = ((mask >> lane) & 1u) && lsd_aligned(reg_angle, arad, prec);
+            const unsigned pass = __ballot_sync(FULL, ok);
+            if (!pass) break;
+            const int j = __ffs(pass) - 1;
+            // accept lane j's pixel
+            const int ax = __shfl_sync(FULL, xx, j), ay = __shfl_sync(FULL, yy, j);
+            const float cj = __shfl_sync(FULL, ca, j), sj = __shfl_sync(FULL, sa, j);
+            if (lane == j) {
+                F.reg[n] = ((unsigned)ay << 16) | (unsigned)ax;
+                F.used[(size_t)ay * F.W + ax] = 1;
+            }
+            n++;
+            sumdx = __fadd_rn(sumdx, cj);
+            sumdy = __fadd_rn(sumdy, sj);
+            reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
+            // drop lanes up to j (tested, failed or accepted) and every later lane that looks at the same pixel
+            const bool same = (xx == ax && yy == ay);
+            const unsigned dup = __ballot_sync(FULL, same);
+            mask &= ~((2u << j) - 1u);
+            mask &= ~dup;
+        }
+        __syncwarp();
+        i += nb;
+    }
+    *out_angle = reg_angle;
+    return n;
+}
+
+// sequential (reference-order) accumulation helper: every lane loads one region point, then all lanes replay the
+// 32 points in order through shuffles, so floating-point sums are formed exactly as the scalar loop forms them.
+struct RegPt { double x, y, w; float adeg; };
+__device__ __forceinline__ RegPt lsd_load_pt(const LsdFrame& F, int idx, int n) {
+    RegPt r;
+    r.x = r.y = r.w = 0;
+    r.adeg = 0;
+    if (idx < n) {
+        const unsigned p = F.reg[idx];
+        const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
+        r.x = (double)x;
+        r.y = (double)y;
+        const size_t o = (size_t)y * F.W + x;
+        r.w = sqrt((double)F.g2[o] / 4.0);  // modgrad
+        r.adeg = F.ang[o];
+    }
+    return r;
+}
+
+// region2rect() + get_theta()
+__device__ void lsd_region2rect(const LsdFrame& F, int n, double reg_angle, double prec, double p, LsdRect& rec) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double x = 0, y = 0, sum = 0;
+    for (int base = 0; base < n; base += 32) {
+        const RegPt pt = lsd_load_pt(F, base + lane, n);
+        const int cnt = min(32, n - base);
+        for (int j = 0; j < cnt; j++) {
+            const double px = __shfl_sync(FULL, pt.x, j), py = __shfl_sync(FULL, pt.y, j), w = __shfl_sync(FULL, pt.w, j);
+            x = __dadd_rn(x, __dmul_rn(px, w));
+            y = __dadd_rn(y, __dmul_rn(py, w));
+            sum = __dadd_rn(sum, w);
+        }
+    }
+    x = x / sum;
+    y = y / sum;
+    // get_theta
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int base = 0; base < n; base += 32) {
+        const RegPt pt = lsd_load_pt(F, base + lane, n);
+        const int cnt = min(32, n - base);
+        for (int j = 0; j < cnt; j++) {
+            const double px = __shfl_sync(FULL, pt.x, j), py = __shfl_sync(FULL, pt.y, j), w = __shfl_sync(FULL, pt.w, j);
+            const double dx = __dsub_rn(px, x), dy = __dsub_rn(py, y);
+            Ixx = __dadd_rn(Ixx, __dmul_rn(__dmul_rn(dy, dy), w));
+            Iyy = __dadd_rn(Iyy, __dmul_rn(__dmul_rn(dx, dx), w));
+            Ixy = __dsub_rn(Ixy, __dmul_rn(__dmul_rn(dx, dy), w));
+        }
+    }
+    const double dI = __dsub_rn(Ixx, Iyy);
+    const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy), sqrt(__dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy)))));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)__dsub_rn(lambda, Ixx), (float)Ixy)
+                                           : (double)fast_atan2_deg((float)Ixy, (float)__dsub_rn(lambda, Iyy));
+    theta *= kDegToRad;
+    if (fabs(lsd_angle_diff_signed(theta, reg_angle)) > prec) theta += kPiD;
+    const double dx = cos(theta), dy = sin(theta);
+    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+    for (int idx = lane; idx < n; idx += 32) {
+        const unsigned pp = F.reg[idx];
+        const double rdx = __dsub_rn((double)(int)(pp & 0xffffu), x), rdy = __dsub_rn((double)(int)(pp >> 16), y);
+        const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
+        const double w = __dadd_rn(__dmul_rn(-rdx, dy), __dmul_rn(rdy, dx));
+        l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+        w_max = fmax(w_max, w); w_min = fmin(w_min, w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l_max = fmax(l_max, __shfl_xor_sync(FULL, l_max, o));
+        l_min = fmin(l_min, __shfl_xor_sync(FULL, l_min, o));
+        w_max = fmax(w_max, __shfl_xor_sync(FULL, w_max, o));
+        w_min = fmin(w_min, __shfl_xor_sync(FULL, w_min, o));
+    }
+    rec.x1 = __dadd_rn(x, __dmul_rn(l_min, dx)); rec.y1 = __dadd_rn(y, __dmul_rn(l_min, dy));
+    rec.x2 = __dadd_rn(x, __dmul_rn(l_max, dx)); rec.y2 = __dadd_rn(y, __dmul_rn(l_max, dy));
+    rec.width = __dsub_rn(w_max, w_min);
+    rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
+    if (rec.width < 1.0) rec.width = 1.0;
+}
+
+__device__ __forceinline__ double lsd_density(int n, const LsdRect& rec) {
+    return (double)n / (sqrt(lsd_dist_sq(rec.x1, rec.y1, rec.x2, rec.y2)) * rec.width);
+}
+
+// reduce_region_radius(): sequential swap-with-last removal keeps the reference's point order
+__device__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n, double reg_angle, double prec, double p, LsdRect& rec,
+                                         double density, double density_th) {
+    const int lane = threadIdx.x & 31;
+    const unsigned p0 = F.reg[0];
+    const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
+    const double r1 = lsd_dist_sq(xc, yc, rec.x1, rec.y1), r2 = lsd_dist_sq(xc, yc, rec.x2, rec.y2);
+    double radSq = r1 > r2 ? r1 : r2;
+    while (density < density_th) {
+        radSq *= 0.75 * 0.75;
+        if (lane == 0) {
+            int m = n;
+            for (int i = 0; i < m; ++i) {
+                const unsigned q = F.reg[i];
+                const int qx = (int)(q & 0xffffu), qy = (int)(q >> 16);
+                if (lsd_dist_sq(xc, yc, (double)qx, (double)qy) > radSq) {
+                    F.used[(size_t)qy * F.W + qx] = 0;
+                    F.reg[i] = F.reg[m - 1];
+                    F.reg[m - 1] = q;
+                    --m;
+                    --i;
+                }
+            }
+            n = m;
+        }
+        n = __shfl_sync(0xffffffffu, n, 0);
+        __syncwarp();
+        if (n < 2) return false;
+        lsd_region2rect(F, n, reg_angle, prec, p, rec);
+        density = lsd_density(n, rec);
+    }
+    return true;
+}
+
+// refine()
+__device__ bool lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double prec, double p, LsdRect& rec, double density_th) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double density = lsd_density(n, rec);
+    if (density >= density_th) return true;
+    const unsigned p0 = F.reg[0];
+    const int sx = (int)(p0 & 0xffffu), sy = (int)(p0 >> 16);
+    const double xc = (double)sx, yc = (double)sy;
+    const double ang_c = (double)F.ang[(size_t)sy * F.W + sx] * kDegToRad;
+    double sum = 0, s_sum = 0;
+    int cnt_in = 0;
+    for (int base = 0; base < n; base += 32) {
+        const RegPt pt = lsd_load_pt(F, base + lane, n);
+        if (base + lane < n) F.used[(size_t)(int)pt.y * F.W + (int)pt.x] = 0;
+        const int cnt = min(32, n - base);
+        for (int j = 0; j < cnt; j++) {
+            const double px = __shfl_sync(FULL, pt.x, j), py = __shfl_sync(FULL, pt.y, j);
+            const float ad = __shfl_sync(FULL, pt.adeg, j);
+            if (sqrt(lsd_dist_sq(xc, yc, px, py)) < rec.width) {
+                const double ang_d = lsd_angle_diff_signed((double)ad * kDegToRad, ang_c);
+                sum = __dadd_rn(sum, ang_d);
+                s_sum = __dadd_rn(s_sum, __dmul_rn(ang_d, ang_d));
+                ++cnt_in;
+            }
+        }
+    }
+    __syncwarp();
+    const double mean_angle = sum / (double)cnt_in;
+    const double tau = 2.0 * sqrt(__dadd_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)) / (double)cnt_in,
+                                            __dmul_rn(mean_angle, mean_angle)));
+    n = lsd_region_grow(F, sx, sy, tau, &reg_angle);
+    if (n < 2) return false;
+    lsd_region2rect(F, n, reg_angle, prec, p, rec);
+    density = lsd_density(n, rec);
+    if (density < density_th) return lsd_reduce_region_radius(F, n, reg_angle, prec, p, rec, density, density_th);
+    return true;
+}
+
+// ---- NFA ----
+__device__ __forceinline__ double lsd_log_gamma(double x) {
+    if (x > 15.0) {  // Windschitl
+        return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+    }
+    const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+    double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
+    double b = 0;
+    for (int n = 0; n < 7; ++n) {
+        a -= log(x + (double)n);
+        b += q[n] * pow(x, (double)n);
+    }
+    return a + log(b);
+}
+__device__ __forceinline__ bool lsd_double_equal(double a, double b) {
+    if (a == b) return true;
+    const double abs_diff = fabs(a - b), aa = fabs(a), bb = fabs(b);
+    double abs_max = aa > bb ? aa : bb;
+    if (abs_max < 2.2250738585072014e-308) abs_max = 2.2250738585072014e-308;
+    return (abs_diff / abs_max) <= (100.0 * 2.2204460492503131e-16);
+}
+__device__ double lsd_nfa(int n, int k, double p, double log_nt) {
+    if (n == 0 || k == 0) return -log_nt;
+    if (n == k) return -log_nt - (double)n * log10(p);
+    const double p_term = p / (1 - p);
+    const double log1term = lsd_log_gamma((double)n + 1) - lsd_log_gamma((double)k + 1) - lsd_log_gamma((double)(n - k) + 1) +
+                            (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+    double term = exp(log1term);
+    if (lsd_double_equal(term, 0)) {
+        if (k > n * p) return -log1term / 2.30258509299404568402 - log_nt;
+        return -log_nt;
+    }
+    double bin_tail = term;
+    const double tolerance = 0.1;
+    for (int i = k + 1; i <= n; ++i) {
+        const double bin_term = (double)(n - i + 1) / (double)i;
+        const double mult_term = bin_term * p_term;
+        term *= mult_term;
+        bin_tail += term;
+        if (bin_term < 1) {
+            const double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+            if (err < tolerance * fabs(-log10(bin_tail) - log_nt) * bin_tail) break;
+        }
+    }
+    return -log10(bin_tail) - log_nt;
+}
+
+__device__ __forceinline__ double lsd_slope(double px, double py, double qx, double qy) {
+    return ((int)ceil(py) == (int)ceil(qy)) ? 0.0 : (qx - px) / (qy - py);
+}
+// rect_nfa() of OpenCV >= 4.5 (real-valued corner scan); rows are distributed over the lanes
+__device__ double lsd_rect_nfa(const LsdFrame& F, const LsdRect& rec, double log_nt) {
+    const int lane = threadIdx.x & 31;
+    const double half_width = rec.width / 2.0;
+    const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
+    const double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
+    const double vy[4] = {rec.y1 + dxhw, rec.y2 + dxhw, rec.y2 - dxhw, rec.y1 - dxhw};
+    int offset = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (vy[i] < vy[offset] || (vy[i] == vy[offset] && vx[i] < vx[offset])) offset = i;
+    double ox[4], oy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ox[i] = vx[(i + offset) & 3];
+        oy[i] = vy[(i + offset) & 3];
+    }
+    const double flstep = lsd_slope(ox[0], oy[0], ox[1], oy[1]), slstep = lsd_slope(ox[1], oy[1], ox[2], oy[2]);
+    const double frstep = lsd_slope(ox[0], oy[0], ox[3], oy[3]), srstep = lsd_slope(ox[3], oy[3], ox[2], oy[2]);
+    const int y_begin = (int)ceil(oy[0]), y_end = (int)ceil(oy[2]);
+    const int c1 = (int)ceil(oy[1]), c3 = (int)ceil(oy[3]);
+    int total = 0, alg = 0;
+    const bool by_rows = (y_end - y_begin) >= 12;
+    for (int yb = y_begin; yb <= y_end; yb += (by_rows ? 32 : 1)) {
+        const int y = by_rows ? yb + lane : yb;
+        if (y > y_end || y < 0 || y >= F.H) continue;
+        const double left_limit = (y <= c1) ? ox[0] + ((double)y - oy[0]) * flstep : ox[1] + ((double)y - oy[1]) * slstep;
+        const double right_limit = (y < c3) ? ox[0] + ((double)y - oy[0]) * frstep : ox[3] + ((double)y - oy[3]) * srstep;
+        int xs = (int)ceil(left_limit), xe = (int)right_limit;
+        xs = max(xs, 0);
+        xe = min(xe, F.W - 1);
+        if (xe < xs) continue;
+        const float* arow = F.ang + (size_t)y * F.W;
+        if (by_rows) {
+            total += xe - xs + 1;
+            for (int x = xs; x <= xe; ++x) {
+                const float a = arow[x];
+                alg += (a != kNotDefDeg) && lsd_aligned(rec.theta, (double)a * kDegToRad, rec.prec);
+            }
+        } else {
+            if (lane == 0) total += xe - xs + 1;
+            for (int x = xs + lane; x <= xe; x += 32) {
+                const float a = arow[x];
+                alg += (a != kNotDefDeg) && lsd_aligned(rec.theta, (double)a * kDegToRad, rec.prec);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+        alg += __shfl_xor_sync(0xffffffffu, alg, o);
+    }
+    return lsd_nfa(total, alg, rec.p, log_nt);
+}
+
+// rect_improve()
+__device__ double lsd_rect_improve(const LsdFrame& F, LsdRect& rec, double log_nt, double log_eps) {
+    const double delta = 0.5, delta_2 = delta / 2.0;
+    double log_nfa = lsd_rect_nfa(F, rec, log_nt);
+    if (log_nfa > log_eps) return log_nfa;
+    LsdRect r = rec;
+    for (int n = 0; n < 5; ++n) {
+        r.p /= 2;
+        r.prec = r.p * kPiD;
+        const double v = lsd_rect_nfa(F, r, log_nt);
+        if (v > log_nfa) { log_nfa = v; rec = r; }
+    }
+    if (log_nfa > log_eps) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.width -= delta;
+            const double v = lsd_rect_nfa(F, r, log_nt);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    }
+    if (log_nfa > log_eps) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2;
+            r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
+            r.width -= delta;
+            const double v = lsd_rect_nfa(F, r, log_nt);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    }
+    if (log_nfa > log_eps) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2;
+            r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
+            r.width -= delta;
+            const double v = lsd_rect_nfa(F, r, log_nt);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    }
+    if (log_nfa > log_eps) return log_nfa;
+    r = rec;
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.p /= 2;
+            r.prec = r.p * kPiD;
+            const double v = lsd_rect_nfa(F, r, log_nt);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    }
+    return log_nfa;
+}
+
+// flsd() main loop
+__global__ void __launch_bounds__(32) k_lsd_grow(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
+                                                 uint8_t* __restrict__ used, unsigned int* __restrict__ reg,
+                                                 const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
+                                                 size_t plane, LsdSeg* __restrict__ segs, int* __restrict__ n_segs,
+                                                 int* __restrict__ flags) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    LsdFrame F;
+    F.ang = angdeg + (size_t)f * plane;
+    F.g2 = g2 + (size_t)f * plane;
+    F.used = used + (size_t)f * plane;
+    F.reg = reg + (size_t)f * plane;
+    F.W = g.W;
+    F.H = g.H;
+    const unsigned int* sd = seeds + (size_t)f * plane;
+    const int ns = n_seeds[f];
+    const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
+    const double density_th = 0.7, log_eps = 0.0;
+    LsdSeg* out = segs + (size_t)f * g.seg_cap;
+    int nout = 0;
+    int pos = 0;
+    while (pos < ns) {
+        // next unused seed at or after pos (32 candidates per probe)
+        const int idx = pos + lane;
+        unsigned pix = 0;
+        bool free_ = false;
+        if (idx < ns) {
+            pix = sd[idx];
+            free_ = F.used[pix] == 0;
+        }
+        const unsigned m = __ballot_sync(FULL, free_);
+        if (!m) { pos += 32; continue; }
+        const int j = __ffs(m) - 1;
+        pix = __shfl_sync(FULL, pix, j);
+        pos += j + 1;
+        const int sx = (int)(pix % (unsigned)g.W), sy = (int)(pix / (unsigned)g.W);
+        double reg_angle;
+        int n = lsd_region_grow(F, sx, sy, prec, &reg_angle);
+        if (n < g.min_reg_size) continue;
+        LsdRect rec;
+        lsd_region2rect(F, n, reg_angle, prec, p, rec);
+        if (!lsd_refine(F, n, reg_angle, prec, p, rec, density_th)) continue;
+        const double log_nfa = lsd_rect_improve(F, rec, g.log_nt, log_eps);
+        if (log_nfa <= log_eps) continue;
+        if (nout < g.seg_cap) {
+            if (lane == 0) {
+                LsdSeg s;
+                s.x1 = (float)((rec.x1 + 0.5) / 0.8); s.y1 = (float)((rec.y1 + 0.5) / 0.8);
+                s.x2 = (float)((rec.x2 + 0.5) / 0.8); s.y2 = (float)((rec.y2 + 0.5) / 0.8);
+                s.width = rec.width / 0.8;
+                s.p = rec.p;
+                s.nfa = log_nfa;
+                out[nout] = s;
+            }
+        } else if (lane == 0) {
+            atomicOr(flags + f, 1);
+        }
+        nout++;
+    }
+    if (lane == 0) n_segs[f] = min(nout, g.seg_cap);
+}
+
+}  // namespace pl
+
+// =================================================================================================================
+// KeyLine assembly + top-N by response, LBD
+// =================================================================================================================
+namespace pl {
+
+// LSDDetector::detectImpl: clamp extremes, fill KeyLine (opencv_contrib LSDDetector.cpp)
+__device__ __forceinline__ pl_keyline make_keyline(const LsdSeg& s, int cols, int rows, int class_id) {
+    float e0 = s.x1, e1 = s.y1, e2 = s.x2, e3 = s.y2;
+    if (e0 < 0) e0 = 0;
+    if (e0 >= cols) e0 = (float)cols - 1.0f;
+    if (e2 < 0) e2 = 0;
+    if (e2 >= cols) e2 = (float)cols - 1.0f;
+    if (e1 < 0) e1 = 0;
+    if (e1 >= rows) e1 = (float)rows - 1.0f;
+    if (e3 < 0) e3 = 0;
+    if (e3 >= rows) e3 = (float)rows - 1.0f;
+    pl_keyline kl;
+    kl.sx = e0; kl.sy = e1; kl.ex = e2; kl.ey = e3;  // octaveScale = 1
+    kl.sx_oct = e0; kl.sy_oct = e1; kl.ex_oct = e2; kl.ey_oct = e3;
+    const double ddx = (double)__fsub_rn(e0, e2), ddy = (double)__fsub_rn(e1, e3);
+    kl.length = (float)sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+    const int x0 = cv_round(e0), y0 = cv_round(e1), x1 = cv_round(e2), y1 = cv_round(e3);
+    kl.num_pixels = max(abs(x1 - x0), abs(y1 - y0)) + 1;  // cv::LineIterator::count, 8-connected, inside the image
+    kl.angle = (float)atan2((double)__fsub_rn(kl.ey, kl.sy), (double)__fsub_rn(kl.ex, kl.sx));
+    kl.class_id = class_id;
+    kl.octave = 0;
+    kl.size = __fmul_rn(__fsub_rn(kl.ex, kl.sx), __fsub_rn(kl.ey, kl.sy));
+    kl.response = __fdiv_rn(kl.length, (float)max(cols, rows));
+    kl.pt_x = __fdiv_rn(__fadd_rn(kl.ex, kl.sx), 2.f);
+    kl.pt_y = __fdiv_rn(__fadd_rn(kl.ey, kl.sy), 2.f);
+    return kl;
+}
+
+// LineExtractor.cpp:23-35: if more than max_lines, keep the max_lines largest responses (ties: detection order),
+// ordered by response descending; otherwise keep detection order.  One CTA per frame.
+constexpr int kFinThreads = 256;
+constexpr int kMaxKeep = 512;
+__global__ void __launch_bounds__(kFinThreads) k_line_finalize(LineGeom g, const LsdSeg* __restrict__ segs, const int* __restrict__ n_segs,
+                                                               float* __restrict__ resp_scratch, pl_keyline* __restrict__ kls,
+                                                               int* __restrict__ n_out, int cap) {
+    __shared__ int s_hist[4096];
+    __shared__ unsigned long long s_key[kMaxKeep];
+    __shared__ int s_sel, s_need, s_bin;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = n_segs[f];
+    const LsdSeg* sg = segs + (size_t)f * g.seg_cap;
+    pl_keyline* out = kls + (size_t)f * cap;
+    const int keep = min(g.max_lines, cap);
+    if (n <= keep) {
+        for (int i = tid; i < n; i += kFinThreads) out[i] = make_keyline(sg[i], g.cols, g.rows, i);
+        if (tid == 0) n_out[f] = n;
+        return;
+    }
+    float* resp = resp_scratch + (size_t)f * g.seg_cap;
+    for (int i = tid; i < n; i += kFinThreads) resp[i] = make_keyline(sg[i], g.cols, g.rows, i).response;
+    __syncthreads();
+    // radix select of the keep-th largest response on the float bits (non-negative floats order like unsigned ints)
+    unsigned prefix = 0, pmask = 0;
+    int need = keep;  // how many elements are still to be taken from the current candidate set
+    const int shifts[3] = {20, 8, 0};
+    const int widths[3] = {12, 12, 8};
+    for (int lvl = 0; lvl < 3; lvl++) {
+        const int nb = 1 << widths[lvl];
+        for (int i = tid; i < nb; i += kFinThreads) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kFinThreads) {
+            const unsigned b = __float_as_uint(resp[i]);
+            if ((b & pmask) == prefix) atomicAdd(&s_hist[(b >> shifts[lvl]) & (nb - 1)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0, bin = nb - 1;
+            for (; bin >= 0; bin--) {
+                if (acc + s_hist[bin] >= need) break;
+                acc += s_hist[bin];
+            }
+            s_bin = bin;
+            s_need = need - acc;
+        }
+        __syncthreads();
+        prefix |= (unsigned)s_bin << shifts[lvl];
+        pmask |= (unsigned)(nb - 1) << shifts[lvl];
+        need = s_need;
+        __syncthreads();
+    }
+    // prefix == bits of the keep-th largest response; take all strictly larger + the first `need` equal ones (by index)
+    const unsigned thr = prefix;
+    if (tid == 0) s_sel = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kFinThreads) {
+        const unsigned b = __float_as_uint(resp[i]);
+        if (b > thr) {
+            const int k = atomicAdd(&s_sel, 1);
+            s_key[k] = ((unsigned long long)(0xFFFFFFFFu - b) << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {  // equal ones in index order (rare: exact float ties)
+        int k = s_sel, taken = 0;
+        for (int i = 0; i < n && taken < need; i++)
+            if (__float_as_uint(resp[i]) == thr) {
+                s_key[k++] = ((unsigned long long)(0xFFFFFFFFu - thr) << 32) | (unsigned)i;
+                taken++;
+            }
+        s_sel = k;
+    }
+    __syncthreads();
+    const int m = s_sel;  // == keep
+    int m2 = 1;
+    while (m2 < m) m2 <<= 1;
+    for (int i = m + tid; i < m2; i += kFinThreads) s_key[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= m2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < m2; i += kFinThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = s_key[i], b = s_key[ixj];
+                    if (up ? (a > b) : (a < b)) { s_key[i] = b; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < m; i += kFinThreads) {
+        const int idx = (int)(s_key[i] & 0xFFFFFFFFull);
+        out[i] = make_keyline(sg[idx], g.cols, g.rows, idx);
+    }
+    if (tid == 0) n_out[f] = m;
+}
+
+// GaussianBlur(5x5, sigma 1) in 8.8 fixed point {14,62,104,62,14} (BinaryDescriptor::computeGaussianPyramid)
+__global__ void __launch_bounds__(256) k_blur5(LineGeom g, const uint8_t* __restrict__ in, size_t in_pitch, size_t in_frame_stride,
+                                               uint8_t* __restrict__ out) {
+    constexpr int TW = 64, TH = 32;
+    __shared__ uint8_t s_in[(TH + 4) * (TW + 4)];
+    __shared__ uint16_t s_h[(TH + 4) * TW];
+    const int f = blockIdx.z, tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const uint8_t* src = in + (size_t)f * in_frame_stride;
+    for (int i = tid; i < (TH + 4) * (TW + 4); i += 256) {
+        const int r = i / (TW + 4), c = i - r * (TW + 4);
+        s_in[i] = __ldg(src + (size_t)reflect101(y0 + r - 2, g.rows) * in_pitch + reflect101(x0 + c - 2, g.cols));
+    }
+    __syncthreads();
+    for (int i = tid; i < (TH + 4) * TW; i += 256) {
+        const int r = i / TW, c = i - r * TW;
+        const uint8_t* p = s_in + r * (TW + 4) + c;
+        s_h[i] = (uint16_t)(14 * (p[0] + p[4]) + 62 * (p[1] + p[3]) + 104 * p[2]);
+    }
+    __syncthreads();
+    uint8_t* dst = out + (size_t)f * g.in_pitch * g.rows;
+    for (int i = tid; i < TH * TW; i += 256) {
+        const int r = i / TW, c = i - r * TW;
+        const int x = x0 + c, y = y0 + r;
+        if (x < g.cols && y < g.rows) {
+            const uint16_t* p = s_h + r * TW + c;
+            const uint32_t acc = 14u * (p[0] + p[4 * TW]) + 62u * (p[TW] + p[3 * TW]) + 104u * p[2 * TW];
+            dst[(size_t)y * g.in_pitch + x] = (uint8_t)((acc + 0x8000u) >> 16);
+        }
+    }
+}
+
+// cv::Sobel(img, CV_16S, 1,0,3) and (0,1,3), BORDER_REFLECT_101 (BinaryDescriptor::computeSobel)
+__global__ void __launch_bounds__(256) k_sobel3(LineGeom g, const uint8_t* __restrict__ blur, short* __restrict__ dxo, short* __restrict__ dyo) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= g.cols || y >= g.rows) return;
+    const uint8_t* b = blur + (size_t)f * g.in_pitch * g.rows;
+    const uint8_t* r0 = b + (size_t)reflect101(y - 1, g.rows) * g.in_pitch;
+    const uint8_t* r1 = b + (size_t)y * g.in_pitch;
+    const uint8_t* r2 = b + (size_t)reflect101(y + 1, g.rows) * g.in_pitch;
+    const int xm = reflect101(x - 1, g.cols), xp = reflect101(x + 1, g.cols);
+    const int gx = (r0[xp] + 2 * r1[xp] + r2[xp]) - (r0[xm] + 2 * r1[xm] + r2[xm]);
+    const int gy = (r2[xm] + 2 * r2[x] + r2[xp]) - (r0[xm] + 2 * r0[x] + r0[xp]);
+    const size_t o = (size_t)f * g.dpitch * g.rows + (size_t)y * g.dpitch + x;
+    dxo[o] = (short)gx;
+    dyo[o] = (short)gy;
+}
+
+constexpr int kLbdBands = 9, kLbdBandW = 7, kLbdRows = kLbdBands * kLbdBandW;  // 63
+struct LbdTabs { float gaussL[kLbdBandW * 3]; float gaussG[kLbdRows]; };
+
+// computeLBD(), part 1: one thread per (line, row of the line support region): projected-gradient row sums,
+// accumulated in the reference's order (left to right along the line)
+__global__ void __launch_bounds__(64) k_lbd_rows(LineGeom g, LbdTabs tabs, const pl_keyline* __restrict__ kls, const int* __restrict__ n_lines,
+                                                 int cap, const short* __restrict__ dxi, const short* __restrict__ dyi,
+                                                 float* __restrict__ rowsum) {
+    const int f = blockIdx.y, line = blockIdx.x, hID = threadIdx.x;
+    if (line >= n_lines[f] || hID >= kLbdRows) return;
+    const pl_keyline kl = kls[(size_t)f * cap + line];
+    const short* pdx = dxi + (size_t)f * g.dpitch * g.rows;
+    const short* pdy = dyi + (size_t)f * g.dpitch * g.rows;
+    const short heightOfLSP = (short)kLbdRows;
+    const short halfHeight = (heightOfLSP - 1) / 2;
+    const short imageWidth = (short)(g.cols - 1), imageHeight = (short)(g.rows - 1);
+    const short lengthOfLSP = (short)kl.num_pixels;
+    const short halfWidth = (lengthOfLSP - 1) / 2;
+    const float midX = __fdiv_rn(__fadd_rn(kl.sx_oct, kl.ex_oct), 2.f), midY = __fdiv_rn(__fadd_rn(kl.sy_oct, kl.ey_oct), 2.f);
+    const float dL0 = (float)cos((double)kl.angle), dL1 = (float)sin((double)kl.angle);
+    const float dO0 = -dL1, dO1 = dL0;
+    float sCorX0 = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, (float)halfHeight)), midX);
+    float sCorY0 = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, (float)halfHeight)), midY);
+    for (int h = 0; h < hID; h++) {
+        sCorX0 = __fsub_rn(sCorX0, dL1);
+        sCorY0 = __fadd_rn(sCorY0, dL0);
+    }
+    float sCorX = sCorX0, sCorY = sCorY0;
+    float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
+    for (short wID = 0; wID < lengthOfLSP; wID++) {
+        short t = (short)(int)round((double)sCorX);
+        const short xCor = (t < 0) ? 0 : (t > imageWidth) ? imageWidth : t;
+        t = (short)(int)round((double)sCorY);
+        const short yCor = (t < 0) ? 0 : (t > imageHeight) ? imageHeight : t;
+        const float ddx = (float)pdx[(size_t)yCor * g.dpitch + xCor], ddy = (float)pdy[(size_t)yCor * g.dpitch + xCor];
+        const float gDL = __fadd_rn(__fmul_rn(ddx, dL0), __fmul_rn(ddy, dL1));
+        const float gDO = __fadd_rn(__fmul_rn(ddx, dO0), __fmul_rn(ddy, dO1));
+        if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
+        if (gDO > 0) pgdO = __fadd_rn(pgdO, gDO); else ngdO = __fsub_rn(ngdO, gDO);
+        sCorX = __fadd_rn(sCorX, dL0);
+        sCorY = __fadd_rn(sCorY, dL1);
+    }
+    const float coef = tabs.gaussG[hID];
+    float* o = rowsum + (((size_t)f * cap + line) * kLbdRows + hID) * 4;
+    o[0] = __fmul_rn(coef, pgdL);
+    o[1] = __fmul_rn(coef, ngdL);
+    o[2] = __fmul_rn(coef, pgdO);
+    o[3] = __fmul_rn(coef, ngdO);
+}
+
+__constant__ int c_lbd_comb[32][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7},
+                                      {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8}, {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
+
+// computeLBD(), part 2 + binaryConversion + line coefficients (LineExtractor.cpp:60-69): one thread per line
+__global__ void __launch_bounds__(128) k_lbd_finish(LineGeom g, LbdTabs tabs, const pl_keyline* __restrict__ kls, const int* __restrict__ n_lines,
+                                                    int cap, const float* __restrict__ rowsum, uint8_t* __restrict__ desc,
+                                                    float* __restrict__ fdesc, double* __restrict__ coeffs) {
+    const int f = blockIdx.y, line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= n_lines[f]) return;
+    const float* rs = rowsum + ((size_t)f * cap + line) * kLbdRows * 4;
+    float band[kLbdBands][8];
+#pragma unroll
+    for (int b = 0; b < kLbdBands; b++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) band[b][k] = 0.f;
+    for (int hID = 0; hID < kLbdRows; hID++) {
+        const float pgdL = rs[hID * 4], ngdL = rs[hID * 4 + 1], pgdO = rs[hID * 4 + 2], ngdO = rs[hID * 4 + 3];
+        const float pgdL2 = __fmul_rn(pgdL, pgdL), ngdL2 = __fmul_rn(ngdL, ngdL), pgdO2 = __fmul_rn(pgdO, pgdO), ngdO2 = __fmul_rn(ngdO, ngdO);
+        const int bandID = hID / kLbdBandW, r = hID % kLbdBandW;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {  // current band, band above, band below — in the reference's order
+            const int bb = t == 0 ? bandID : (t == 1 ? bandID - 1 : bandID + 1);
+            if (bb < 0 || bb >= kLbdBands) continue;
+            const float c = tabs.gaussL[t == 0 ? r + kLbdBandW : (t == 1 ? r + 2 * kLbdBandW : r)];
+            const float cc = __fmul_rn(c, c);
+            float* B = band[bb];
+            B[0] = __fadd_rn(B[0], __fmul_rn(c, pgdL));
+            B[1] = __fadd_rn(B[1], __fmul_rn(c, ngdL));
+            B[2] = __fadd_rn(B[2], __fmul_rn(cc, pgdL2));
+            B[3] = __fadd_rn(B[3], __fmul_rn(cc, ngdL2));
+            B[4] = __fadd_rn(B[4], __fmul_rn(c, pgdO));
+            B[5] = __fadd_rn(B[5], __fmul_rn(c, ngdO));
+            B[6] = __fadd_rn(B[6], __fmul_rn(cc, pgdO2));
+            B[7] = __fadd_rn(B[7], __fmul_rn(cc, ngdO2));
+        }
+    }
+    float d[kLbdBands * 8];
+    const float invN2 = (float)(1.0 / (kLbdBandW * 2.0)), invN3 = (float)(1.0 / (kLbdBandW * 3.0));
+#pragma unroll
+    for (int b = 0; b < kLbdBands; b++) {
+        const float invN = (b == 0 || b == kLbdBands - 1) ? invN2 : invN3;
+        const float* B = band[b];
+        float temp = __fmul_rn(B[0], invN);
+        d[b * 8] = temp;
+        d[b * 8 + 4] = sqrtf(__fsub_rn(__fmul_rn(B[2], invN), __fmul_rn(temp, temp)));
+        temp = __fmul_rn(B[1], invN);
+        d[b * 8 + 1] = temp;
+        d[b * 8 + 5] = sqrtf(__fsub_rn(__fmul_rn(B[3], invN), __fmul_rn(temp, temp)));
+        temp = __fmul_rn(B[4], invN);
+        d[b * 8 + 2] = temp;
+        d[b * 8 + 6] = sqrtf(__fsub_rn(__fmul_rn(B[6], invN), __fmul_rn(temp, temp)));
+        temp = __fmul_rn(B[5], invN);
+        d[b * 8 + 3] = temp;
+        d[b * 8 + 7] = sqrtf(__fsub_rn(__fmul_rn(B[7], invN), __fmul_rn(temp, temp)));
+    }
+    float tempM = 0, tempS = 0;
+#pragma unroll
+    for (int b = 0; b < kLbdBands; b++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) tempM = __fadd_rn(tempM, __fmul_rn(d[b * 8 + k], d[b * 8 + k]));
+#pragma unroll
+        for (int k = 4; k < 8; k++) tempS = __fadd_rn(tempS, __fmul_rn(d[b * 8 + k], d[b * 8 + k]));
+    }
+    tempM = __fdiv_rn(1.f, sqrtf(tempM));
+    tempS = __fdiv_rn(1.f, sqrtf(tempS));
+#pragma unroll
+    for (int b = 0; b < kLbdBands; b++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[b * 8 + k] = __fmul_rn(d[b * 8 + k], tempM);
+#pragma unroll
+        for (int k = 4; k < 8; k++) d[b * 8 + k] = __fmul_rn(d[b * 8 + k], tempS);
+    }
+#pragma unroll
+    for (int i = 0; i < kLbdBands * 8; i++)
+        if ((double)d[i] > 0.4) d[i] = (float)0.4;
+    float temp = 0;
+#pragma unroll
+    for (int i = 0; i < kLbdBands * 8; i++) temp = __fadd_rn(temp, __fmul_rn(d[i], d[i]));
+    temp = __fdiv_rn(1.f, sqrtf(temp));
+#pragma unroll
+    for (int i = 0; i < kLbdBands * 8; i++) d[i] = __fmul_rn(d[i], temp);
+    uint8_t* od = desc + ((size_t)f * cap + line) * 32;
+    for (int c = 0; c < 32; c++) {
+        const float* f1 = d + 8 * c_lbd_comb[c][0];
+        const float* f2 = d + 8 * c_lbd_comb[c][1];
+        unsigned r = 0;
+        for (int i = 0; i < 8; i++) r += (f1[i] > f2[i]) ? (1u << i) : 0u;
+        od[c] = (uint8_t)r;
+    }
+    if (fdesc) {
+        float* of = fdesc + ((size_t)f * cap + line) * 72;
+        for (int i = 0; i < 72; i++) of[i] = d[i];
+    }
+    const pl_keyline kl = kls[(size_t)f * cap + line];
+    const double sx = kl.sx, sy = kl.sy, ex = kl.ex, ey = kl.ey;
+    double l0 = __dsub_rn(sy, ey), l1 = __dsub_rn(ex, sx), l2 = __dsub_rn(__dmul_rn(sx, ey), __dmul_rn(sy, ex));
+    const double nrm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(l0, l0), __dmul_rn(l1, l1)), __dmul_rn(l2, l2)));
+    if (nrm > 0) { l0 /= nrm; l1 /= nrm; l2 /= nrm; }
+    double* oc = coeffs + ((size_t)f * cap + line) * 3;
+    oc[0] = l0; oc[1] = l1; oc[2] = l2;
+}
+
+}  // namespace pl
+
+// =================================================================================================================
+// host side
+// =================================================================================================================
+using namespace pl;
+
+struct pl_line {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int max_cols = 0, max_rows = 0, max_batch = 0;
+    int rows = 0, cols = 0, max_lines = 0;
+    LineGeom geom;
+    LbdTabs tabs;
+    size_t plane = 0, scaled_stride = 0;
+    // device buffers (sized for max_cols x max_rows x max_batch at creation)
+    uint8_t *d_in = nullptr, *d_scaled = nullptr, *d_used = nullptr, *d_blur5 = nullptr;
+    float* d_ang = nullptr;
+    int* d_g2 = nullptr;
+    unsigned int *d_reg = nullptr, *d_seeds = nullptr;
+    int *d_maxg2 = nullptr, *d_tile_off = nullptr, *d_nseeds = nullptr, *d_nsegs = nullptr, *d_flags = nullptr, *d_nout = nullptr;
+    unsigned short* d_tile_hist = nullptr;
+    LsdSeg* d_segs = nullptr;
+    float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
+    short *d_dx = nullptr, *d_dy = nullptr;
+    ExactTab *d_xtab = nullptr, *d_ytab = nullptr;
+    pl_keyline* d_kls = nullptr;
+    uint8_t* d_desc = nullptr;
+    double* d_coef = nullptr;
+    int out_cap = 0;  // capacity (lines per frame) of d_kls / d_desc / d_coef / d_rowsum
+    int seg_cap_alloc = 0, tiles_alloc = 0;
+    size_t plane_alloc = 0, in_alloc = 0;
+    int* h_flags = nullptr;
+    int last_batch = 0, last_launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[8] = {nullptr};
+    float stage_ms[8] = {0};
+    int stage_chunks = 0;
+};
+
+namespace {
+
+inline int cvRoundD(double v) { return (int)lrint(v); }
+
+void build_exact_axis(std::vector<ExactTab>& t, int dn, int sn, double inv_scale) {
+    t.assign(dn, ExactTab{0, 256, 0, 0});
+    const double scale = 1.0 / inv_scale;
+    for (int v = 0; v < dn; v++) {
+        double fv = scale * (v + 0.5) - 0.5;
+        int i = (int)floor(fv);
+        if (i >= 0 && sn > 1) {
+            if (i < sn - 1) {
+                t[v].ofs = (short)i;
+                t[v].c1 = (short)cvRoundD((fv - i) * 256);
+                t[v].c0 = (short)(256 - t[v].c1);
+            } else {
+                t[v].ofs = (short)(sn - 1);
+            }
+        }
+    }
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    PL_CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return PL_OK;
+}
+
+int line_geometry(pl_line* h, int rows, int cols, int max_lines) {
+    if (rows == h->rows && cols == h->cols && max_lines == h->max_lines) return PL_OK;
+    LineGeom& G = h->geom;
+    G.cols = cols; G.rows = rows;
+    G.W = cvRoundD(cols * 0.8);
+    G.H = cvRoundD(rows * 0.8);
+    if (G.W < 8 || G.H < 8) {
+        set_error("image %dx%d too small for LSD", cols, rows);
+        return PL_ERR_ARG;
+    }
+    G.in_pitch = (int)align_up((size_t)cols, 16);
+    G.spitch = (int)align_up((size_t)G.W, 16);
+    G.n_tiles = (G.H - 1 + kTileRows - 1) / kTileRows;
+    G.reg_cap = G.W * G.H;
+    G.log_nt = 5 * (log10((double)G.W) + log10((double)G.H)) / 2 + log10(11.0);
+    const double p = 22.5 / 180;
+    G.min_reg_size = (int)(size_t)(-G.log_nt / log10(p));
+    G.seg_cap = std::min(G.W * G.H / std::max(G.min_reg_size, 1) + 1, h->seg_cap_alloc);
+    G.max_lines = max_lines;
+    G.dpitch = (int)align_up((size_t)cols, 8);
+    h->plane = (size_t)G.W * G.H;
+    h->scaled_stride = (size_t)G.spitch * G.H;
+    std::vector<ExactTab> xt, yt;
+    build_exact_axis(xt, G.W, cols, 0.8);
+    build_exact_axis(yt, G.H, rows, 0.8);
+    PL_CUDA_TRY(cudaMemcpyAsync(h->d_xtab, xt.data(), xt.size() * sizeof(ExactTab), cudaMemcpyHostToDevice, h->stream));
+    PL_CUDA_TRY(cudaMemcpyAsync(h->d_ytab, yt.data(), yt.size() * sizeof(ExactTab), cudaMemcpyHostToDevice, h->stream));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->rows = rows; h->cols = cols; h->max_lines = max_lines;
+    return PL_OK;
+}
+
+int line_ensure_out(pl_line* h, int cap) {
+    if (cap <= h->out_cap) return PL_OK;
+    const size_t B = h->max_batch;
+    int rc;
+    if ((rc = dev_alloc(&h->d_kls, B * cap)) != PL_OK) return rc;
+    if ((rc = dev_alloc(&h->d_desc, B * cap * 32)) != PL_OK) return rc;
+    if ((rc = dev_alloc(&h->d_coef, B * cap * 3)) != PL_OK) return rc;
+    if ((rc = dev_alloc(&h->d_rowsum, B * cap * kLbdRows * 4)) != PL_OK) return rc;
+    if ((rc = dev_alloc(&h->d_fdesc, B * cap * 72)) != PL_OK) return rc;
+    h->out_cap = cap;
+    return PL_OK;
+}
+
+// one chunk; every pointer is a device pointer
+int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, size_t frame_stride, pl_keyline* d_kls, uint8_t* d_desc,
+                      double* d_coef, int cap, int* d_nout) {
+    const LineGeom& G = h->geom;
+    cudaStream_t st = h->stream;
+    const size_t plane = h->plane;
+    int launches = 0;
+    const bool prof = h->profiling;
+    PL_CUDA_TRY(cudaMemsetAsync(h->d_maxg2, 0xff, sizeof(int) * nf, st));  // -1
+    PL_CUDA_TRY(cudaMemsetAsync(h->d_used, 0, plane * nf, st));
+    PL_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * nf, st));
+    if (prof) cudaEventRecord(h->ev[0], st);
+    {
+        dim3 grid((G.W + kScTW - 1) / kScTW, (G.H + kScTH - 1) / kScTH, nf);
+        k_lsd_scale<<<grid, 256, 0, st>>>(G, d_gray, step, frame_stride, h->d_xtab, h->d_ytab, h->d_scaled, h->scaled_stride);
+        launches++;
+    }
+    {
+        const double rho = 2.0 / sin(kPiD * 22.5 / 180);
+        dim3 grid((G.W + 63) / 64, (G.H + 3) / 4, nf);
+        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, plane, rho, h->d_maxg2);
+        launches++;
+    }
+    if (prof) cudaEventRecord(h->ev[1], st);
+    k_lsd_bin_count<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_hist);
+    k_lsd_bin_scan<<<nf, kBins, 0, st>>>(G, h->d_tile_hist, h->d_tile_off, h->d_nseeds);
+    k_lsd_scatter<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_off, h->d_seeds);
+    launches += 3;
+    if (prof) cudaEventRecord(h->ev[2], st);
+    k_lsd_grow<<<nf, 32, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_seeds, h->d_nseeds, plane, h->d_segs, h->d_nsegs, h->d_flags);
+    launches++;
+    if (prof) cudaEventRecord(h->ev[3], st);
+    k_line_finalize<<<nf, kFinThreads, 0, st>>>(G, h->d_segs, h->d_nsegs, h->d_resp, d_kls, d_nout, cap);
+    launches++;
+    {
+        dim3 grid((G.cols + 63) / 64, (G.rows + 31) / 32, nf);
+        k_blur5<<<grid, 256, 0, st>>>(G, d_gray, step, frame_stride, h->d_blur5);
+        dim3 grid2((G.cols + 63) / 64, (G.rows + 3) / 4, nf);
+        k_sobel3<<<grid2, 256, 0, st>>>(G, h->d_blur5, h->d_dx, h->d_dy);
+        launches += 2;
+    }
+    if (prof) cudaEventRecord(h->ev[4], st);
+    const int keep = std::min(G.max_lines, cap);
+    k_lbd_rows<<<dim3(keep, nf), 64, 0, st>>>(G, h->tabs, d_kls, d_nout, cap, h->d_dx, h->d_dy, h->d_rowsum);
+    k_lbd_finish<<<dim3((keep + 127) / 128, nf), 128, 0, st>>>(G, h->tabs, d_kls, d_nout, cap, h->d_rowsum, d_desc, h->d_fdesc, d_coef);
+    launches += 2;
+    PL_CUDA_TRY(cudaGetLastError());
+    if (prof) {
+        cudaEventRecord(h->ev[5], st);
+        PL_CUDA_TRY(cudaEventSynchronize(h->ev[5]));
+        for (int i = 0; i < 5; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+            h->stage_ms[i] += ms;
+        }
+        h->stage_chunks++;
+    }
+    h->last_batch = nf;
+    h->last_launches += launches;
+    return PL_OK;
+}
+
+int line_check_flags(pl_line* h, int nf) {
+    PL_CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < nf; i++)
+        if (h->h_flags[i]) {
+            set_error("frame %d of the chunk exceeded the LSD segment capacity", i);
+            return PL_ERR_CAPACITY;
+        }
+    return PL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows, int max_batch) {
+    PL_CHECK_ARG(out != nullptr);
+    *out = nullptr;
+    PL_CHECK_ARG(max_cols >= 16 && max_rows >= 16 && max_cols <= 4000 && max_rows <= 4000 && max_batch >= 1);
+    int ndev = 0;
+    PL_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_error("device %d not available (%d CUDA devices); this library has no CPU fallback", device, ndev);
+        return PL_ERR_CUDA;
+    }
+    PL_CUDA_TRY(cudaSetDevice(device));
+    pl_line* h = new pl_line();
+    h->device = device;
+    h->max_cols = max_cols; h->max_rows = max_rows; h->max_batch = max_batch;
+    // BinaryDescriptor constructor: local / global Gaussian weights (integer divisions as in the original)
+    {
+        double u = (kLbdBandW * 3 - 1) / 2, sigma = (kLbdBandW * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < kLbdBandW * 3; i++) h->tabs.gaussL[i] = (float)exp((i - u) * (i - u) * inv);
+        u = (kLbdRows - 1) / 2; sigma = kLbdRows / 2; inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < kLbdRows; i++) h->tabs.gaussG[i] = (float)exp((i - u) * (i - u) * inv);
+    }
+    const size_t B = max_batch;
+    const int W = cvRoundD(max_cols * 0.8) + 1, H = cvRoundD(max_rows * 0.8) + 1;
+    const size_t plane = (size_t)W * H;
+    const size_t in_pitch = align_up((size_t)max_cols, 16);
+    const int tiles = (H + kTileRows - 1) / kTileRows + 1;
+    const int seg_cap = (int)(plane / 8) + 1;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    auto A = [&](auto** p, size_t n) {
+        if (e == cudaSuccess) e = cudaMalloc((void**)p, n * sizeof(**p));
+    };
+    A(&h->d_in, B * in_pitch * max_rows);
+    A(&h->d_blur5, B * in_pitch * max_rows);
+    A(&h->d_scaled, B * align_up((size_t)W, 16) * H);
+    A(&h->d_used, B * plane);
+    A(&h->d_ang, B * plane);
+    A(&h->d_g2, B * plane);
+    A(&h->d_reg, B * plane);
+    A(&h->d_seeds, B * plane);
+    A(&h->d_maxg2, B);
+    A(&h->d_nseeds, B);
+    A(&h->d_nsegs, B);
+    A(&h->d_flags, B);
+    A(&h->d_nout, B);
+    A(&h->d_tile_hist, B * tiles * kBins);
+    A(&h->d_tile_off, B * tiles * kBins);
+    A(&h->d_segs, B * seg_cap);
+    A(&h->d_resp, B * seg_cap);
+    A(&h->d_dx, B * align_up((size_t)max_cols, 8) * max_rows);
+    A(&h->d_dy, B * align_up((size_t)max_cols, 8) * max_rows);
+    A(&h->d_xtab, (size_t)W);
+    A(&h->d_ytab, (size_t)H);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_flags, sizeof(int) * B);
+    if (e != cudaSuccess) {
+        set_error("pl_line_create: %s", cudaGetErrorString(e));
+        pl_line_destroy(h);
+        return PL_ERR_CUDA;
+    }
+    h->seg_cap_alloc = seg_cap;
+    *out = h;
+    return PL_OK;
+}
+
+PL_API void pl_line_destroy(pl_line* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* bufs[] = {h->d_in, h->d_scaled, h->d_used, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
+                    h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    for (int i = 0; i < 8; i++)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+PL_API int pl_line_sync(pl_line* h) {
+    PL_CHECK_ARG(h);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PL_OK;
+}
+PL_API void* pl_line_stream(pl_line* h) { return h ? (void*)h->stream : nullptr; }
+PL_API int pl_line_last_launches(const pl_line* h) { return h ? h->last_launches : 0; }
+
+PL_API int pl_line_set_profiling(pl_line* h, int on) {
+    PL_CHECK_ARG(h);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    if (on && !h->ev[0])
+        for (int i = 0; i < 8; i++) PL_CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    h->profiling = on != 0;
+    for (int i = 0; i < 8; i++) h->stage_ms[i] = 0;
+    h->stage_chunks = 0;
+    return PL_OK;
+}
+PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks) {
+    PL_CHECK_ARG(h && out5);
+    for (int i = 0; i < 5; i++) out5[i] = h->stage_ms[i];
+    if (chunks) *chunks = h->stage_chunks;
+    return PL_OK;
+}
+
+static int line_check_common(pl_line* h, const void* gray, int n_frames, int rows, int cols, size_t step, int max_lines) {
+    if (!gray || rows <= 0 || cols <= 0 || n_frames <= 0) {
+        set_error("empty image");
+        return PL_ERR_EMPTY;
+    }
+    PL_CHECK_ARG(cols <= h->max_cols && rows <= h->max_rows && step >= (size_t)cols);
+    PL_CHECK_ARG(max_lines >= 1 && max_lines <= kMaxKeep);
+    return PL_OK;
+}
+
+PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols, size_t step,
+                                     size_t frame_stride, int max_lines, pl_keyline* d_kls, uint8_t* d_desc, double* d_coeffs,
+                                     int* d_n_out) {
+    PL_CHECK_ARG(h && d_kls && d_desc && d_coeffs && d_n_out);
+    int rc = line_check_common(h, d_gray, n_frames, rows, cols, step, max_lines);
+    if (rc != PL_OK) return rc;
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    if ((rc = line_geometry(h, rows, cols, max_lines)) != PL_OK) return rc;
+    if ((rc = line_ensure_out(h, max_lines)) != PL_OK) return rc;
+    h->last_launches = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = std::min(h->max_batch, n_frames - f0);
+        rc = line_launch_chunk(h, d_gray + (size_t)f0 * frame_stride, nf, step, frame_stride, d_kls + (size_t)f0 * max_lines,
+                               d_desc + (size_t)f0 * max_lines * 32, d_coeffs + (size_t)f0 * max_lines * 3, max_lines, d_n_out + f0);
+        if (rc != PL_OK) return rc;
+    }
+    return PL_OK;
+}
+
+PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride,
+                                 int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs, int* n_out) {
+    PL_CHECK_ARG(h && kls && desc && coeffs && n_out);
+    int rc = line_check_common(h, gray, n_frames, rows, cols, step, max_lines);
+    if (rc != PL_OK) return rc;
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    if ((rc = line_geometry(h, rows, cols, max_lines)) != PL_OK) return rc;
+    if ((rc = line_ensure_out(h, max_lines)) != PL_OK) return rc;
+    const size_t in_pitch = h->geom.in_pitch;
+    h->last_launches = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int nf = std::min(h->max_batch, n_frames - f0);
+        for (int f = 0; f < nf; f++)
+            PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride, step,
+                                          cols, rows, cudaMemcpyHostToDevice, h->stream));
+        rc = line_launch_chunk(h, h->d_in, nf, in_pitch, in_pitch * rows, h->d_kls, h->d_desc, h->d_coef, max_lines, h->d_nout);
+        if (rc != PL_OK) return rc;
+        PL_CUDA_TRY(cudaMemcpyAsync(n_out + f0, h->d_nout, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        if ((rc = line_check_flags(h, nf)) != PL_OK) return rc;
+        PL_CUDA_TRY(cudaMemcpyAsync(kls + (size_t)f0 * max_lines, h->d_kls, sizeof(pl_keyline) * (size_t)nf * max_lines,
+                                    cudaMemcpyDeviceToHost, h->stream));
+        PL_CUDA_TRY(cudaMemcpyAsync(desc + (size_t)f0 * max_lines * 32, h->d_desc, (size_t)nf * max_lines * 32, cudaMemcpyDeviceToHost,
+                                    h->stream));
+        PL_CUDA_TRY(cudaMemcpyAsync(coeffs + (size_t)f0 * max_lines * 3, h->d_coef, sizeof(double) * (size_t)nf * max_lines * 3,
+                                    cudaMemcpyDeviceToHost, h->stream));
+        PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return PL_OK;
+}
+
+PL_API int pl_line_extract(pl_line* h, const uint8_t* gray, int rows, int cols, size_t step, int max_lines, pl_keyline* kls,
+                           uint8_t* desc, double* coeffs, int* n_out) {
+    return pl_line_extract_batch(h, gray, 1, rows, cols, step, step * (size_t)(rows > 0 ? rows : 0), max_lines, kls, desc, coeffs, n_out);
+}
+
+PL_API int pl_line_lsd_read(pl_line* h, int frame, float* xyxy, double* width, double* prec, double* nfa, int cap, int* n_out) {
+    PL_CHECK_ARG(h && xyxy && n_out);
+    if (frame < 0 || frame >= h->last_batch) {
+        set_error("no extract result for frame %d", frame);
+        return PL_ERR_STATE;
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    int n = 0;
+    PL_CUDA_TRY(cudaMemcpyAsync(&n, h->d_nsegs + frame, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *n_out = n;
+    if (n > cap) return PL_ERR_CAPACITY;
+    std::vector<LsdSeg> tmp(n);
+    if (n) {
+        PL_CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_segs + (size_t)frame * h->geom.seg_cap, sizeof(LsdSeg) * n, cudaMemcpyDeviceToHost, h->stream));
+        PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    for (int i = 0; i < n; i++) {
+        xyxy[4 * i] = tmp[i].x1; xyxy[4 * i + 1] = tmp[i].y1; xyxy[4 * i + 2] = tmp[i].x2; xyxy[4 * i + 3] = tmp[i].y2;
+        if (width) width[i] = tmp[i].width;
+        if (prec) prec[i] = tmp[i].p;
+        if (nfa) nfa[i] = tmp[i].nfa;
+    }
+    return PL_OK;
+}
+
+/* test hooks: the 0.8-scaled 8-bit image, the level-line angle map (degrees, -1024 = undefined) and the float LBD
+ * descriptors (n x 72) of the last call */
+PL_API int pl_line_scaled_dims(const pl_line* h, int* rows, int* cols) {
+    PL_CHECK_ARG(h && rows && cols && h->rows > 0);
+    *rows = h->geom.H;
+    *cols = h->geom.W;
+    return PL_OK;
+}
+PL_API int pl_line_scaled_read(pl_line* h, int frame, uint8_t* out, size_t out_step) {
+    PL_CHECK_ARG(h && out && frame >= 0 && frame < h->last_batch && out_step >= (size_t)h->geom.W);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    PL_CUDA_TRY(cudaMemcpy2DAsync(out, out_step, h->d_scaled + (size_t)frame * h->scaled_stride, h->geom.spitch, h->geom.W, h->geom.H,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PL_OK;
+}
+PL_API int pl_line_angles_read(pl_line* h, int frame, float* out) {
+    PL_CHECK_ARG(h && out && frame >= 0 && frame < h->last_batch);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    PL_CUDA_TRY(cudaMemcpyAsync(out, h->d_ang + (size_t)frame * h->plane, sizeof(float) * h->plane, cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PL_OK;
+}
+PL_API int pl_line_fdesc_read(pl_line* h, int frame, float* out, int n) {
+    PL_CHECK_ARG(h && out && frame >= 0 && frame < h->last_batch && n >= 0 && n <= h->out_cap);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    PL_CUDA_TRY(cudaMemcpyAsync(out, h->d_fdesc + (size_t)frame * h->max_lines * 72, sizeof(float) * 72 * n, cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PL_OK;
+}
+
+}  // extern "C"
