@@ -164,6 +164,9 @@ PL_API int pl_line_last_launches(const pl_line* h);
 /* Measurement hooks: stages {0 blur+scale+gradient, 1 seed sort, 2 region growing/NFA, 3 KeyLines+blur5+Sobel, 4 LBD} */
 PL_API int pl_line_set_profiling(pl_line* h, int on);
 PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
+/* with profiling on: SM cycles that frame `frame` of the last chunk spent in {0 seed scan, 1 region growing, 2 rectangle
+ * fit, 3 refine, 4 NFA}, then {5 regions tried, 6 regions that reached the minimum size} */
+PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out7);
 /* Test hooks: the 0.8-scaled 8-bit image LSD works on, its level-line angle map (float degrees, -1024 = undefined,
  * rows x cols of the scaled image) and the float LBD descriptors (n x 72) of frame `frame` of the last call. */
 PL_API int pl_line_scaled_dims(const pl_line* h, int* rows, int* cols);
@@ -230,6 +233,7 @@ typedef struct {
     const float* proj_xr;         /* mTrackProjXR                                 */
     const int* scale_level;       /* mnTrackScaleLevel                            */
     const float* view_cos;        /* mTrackViewCos                                */
+    const uint8_t* has_observations; /* Observations()>0: a feature assigned to such a point becomes "claimed" (:128-130) */
 } pl_mappoint_view;
 PL_API int pl_orb_search_local_points(pl_match* h, const pl_frame_view* F, const pl_mappoint_view* mps, float th,
                                       float nn_ratio, int* match_of_feature, int* n_matches);
@@ -245,6 +249,7 @@ typedef struct {
     const uint8_t* desc;          /* n x 32 */
     const int* octave;
     const float* angle;
+    const uint8_t* has_observations; /* pMP->Observations()>0 (temporal VO points have 0, ORBmatcher.cc:1807-1809) */
     float tcw[12];
 } pl_lastframe_view;
 PL_API int pl_orb_search_last_frame(pl_match* h, const pl_frame_view* Cur, const pl_lastframe_view* Last, float th,

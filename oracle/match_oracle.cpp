@@ -64,3 +64,389 @@ extern "C" void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* 
     for (int i = 0; i < nq; i++)
         for (int k = off[i]; k < off[i + 1]; k++) dist[k] = descriptor_distance(q + 32 * (size_t)i, t + 32 * (size_t)cidx[k]);
 }
+
+// =================================================================================================================
+// Projection searches (ORBmatcher) and line matching (LineMatcher) over the POD views of include/plslam_c.h
+// =================================================================================================================
+#include <cmath>
+#include <utility>
+
+#include "../include/plslam_c.h"
+
+namespace {
+const int FRAME_GRID_ROWS = 48, FRAME_GRID_COLS = 64;  // include/Frame.h
+const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;  // src/ORBmatcher.cc:49-51
+
+// Frame::AssignFeaturesToGrid (Frame.cc:265-287) + PosInGrid (:527-538)
+struct Grid {
+    std::vector<int> cell[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    float invW, invH;
+    explicit Grid(const pl_frame_view& F) {
+        invW = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(F.max_x - F.min_x);
+        invH = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(F.max_y - F.min_y);
+        for (int i = 0; i < F.n; i++) {
+            const pl_keypoint& kp = F.keys_un[i];
+            int posX = (int)std::round((kp.x - F.min_x) * invW);
+            int posY = (int)std::round((kp.y - F.min_y) * invH);
+            if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) continue;
+            cell[posX][posY].push_back(i);
+        }
+    }
+    // Frame::GetFeaturesInArea — Frame.cc:432-485
+    void in_area(const pl_frame_view& F, float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
+        out.clear();
+        const int nMinCellX = std::max(0, (int)std::floor((x - F.min_x - r) * invW));
+        if (nMinCellX >= FRAME_GRID_COLS) return;
+        const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)std::ceil((x - F.min_x + r) * invW));
+        if (nMaxCellX < 0) return;
+        const int nMinCellY = std::max(0, (int)std::floor((y - F.min_y - r) * invH));
+        if (nMinCellY >= FRAME_GRID_ROWS) return;
+        const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)std::ceil((y - F.min_y + r) * invH));
+        if (nMaxCellY < 0) return;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+                for (int idx : cell[ix][iy]) {
+                    const pl_keypoint& kp = F.keys_un[idx];
+                    if (bCheckLevels) {
+                        if (kp.octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                    }
+                    const float distx = kp.x - x, disty = kp.y - y;
+                    if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+                }
+    }
+};
+
+// ORBmatcher::ComputeThreeMaxima — ORBmatcher.cc:2035-2077
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// cv::Mat (CV_32F) expression R*x + t as OpenCV evaluates it: one gemm with double accumulation, rounded once
+inline void mat_rx_plus_t(const float* T /*3x4 row-major*/, const float* X, float* out) {
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)T[4 * r + k] * (double)X[k];
+        out[r] = (float)(s * 1.0 + (double)T[4 * r + 3] * 1.0);
+    }
+}
+}  // namespace
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) — ORBmatcher.cc:72-183
+extern "C" int orc_orb_search_local_points(const pl_frame_view* Fp, const pl_mappoint_view* M, float th, float nn_ratio,
+                                           int* match_of_feature, int* n_matches) {
+    const pl_frame_view& F = *Fp;
+    Grid grid(F);
+    std::vector<uint8_t> claimed(F.n);
+    for (int i = 0; i < F.n; i++) { claimed[i] = F.claimed ? (F.claimed[i] != 0) : 0; match_of_feature[i] = -1; }
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < M->n; iMP++) {
+        if (!M->track_in_view[iMP]) continue;
+        const int nPredictedLevel = M->scale_level[iMP];
+        float r = M->view_cos[iMP] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos :186-193
+        if (bFactor) r *= th;
+        grid.in_area(F, M->proj_x[iMP], M->proj_y[iMP], r * F.scale_factors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* d = M->desc + 32 * (size_t)iMP;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (claimed[idx]) continue;
+            if (F.u_right[idx] > 0) {
+                const float er = std::fabs(M->proj_xr[iMP] - F.u_right[idx]);
+                if (er > r * F.scale_factors[nPredictedLevel]) continue;
+            }
+            const int dist = descriptor_distance(d, F.desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F.keys_un[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F.keys_un[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nn_ratio * bestDist2) continue;
+            match_of_feature[bestIdx] = iMP;
+            claimed[bestIdx] = M->has_observations ? (M->has_observations[iMP] != 0) : 1;
+            nmatches++;
+        }
+    }
+    *n_matches = nmatches;
+    return 0;
+}
+
+// ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) — ORBmatcher.cc:1710-1879
+extern "C" int orc_orb_search_last_frame(const pl_frame_view* Cp, const pl_lastframe_view* L, float th, int mono, int check_orientation,
+                                         int* match_of_feature, int* n_matches) {
+    const pl_frame_view& C = *Cp;
+    Grid grid(C);
+    std::vector<uint8_t> claimed(C.n);
+    for (int i = 0; i < C.n; i++) { claimed[i] = C.claimed ? (C.claimed[i] != 0) : 0; match_of_feature[i] = -1; }
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    // twc = -Rcw^T * tcw ; tlc = Rlw*twc + tlw   (cv::Mat float expressions: gemm with double accumulation)
+    float twc[3], tlc[3];
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)C.tcw[4 * k + r] * (double)C.tcw[4 * k + 3];
+        twc[r] = (float)(s * -1.0);
+    }
+    mat_rx_plus_t(L->tcw, twc, tlc);
+    const bool bForward = tlc[2] > C.b && !mono;
+    const bool bBackward = -tlc[2] > C.b && !mono;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < L->n; i++) {
+        if (!L->valid[i]) continue;
+        float x3Dc[3];
+        mat_rx_plus_t(C.tcw, L->world_pos + 3 * (size_t)i, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = (float)(1.0 / x3Dc[2]);
+        if (invzc < 0) continue;
+        float u = C.fx * xc * invzc + C.cx;
+        float v = C.fy * yc * invzc + C.cy;
+        if (u < C.min_x || u > C.max_x) continue;
+        if (v < C.min_y || v > C.max_y) continue;
+        const int nLastOctave = L->octave[i];
+        const float radius = th * C.scale_factors[nLastOctave];
+        if (bForward) grid.in_area(C, u, v, radius, nLastOctave, -1, vIndices2);
+        else if (bBackward) grid.in_area(C, u, v, radius, 0, nLastOctave, vIndices2);
+        else grid.in_area(C, u, v, radius, nLastOctave - 1, nLastOctave + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = L->desc + 32 * (size_t)i;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (claimed[i2]) continue;
+            if (C.u_right[i2] > 0) {
+                const float ur = u - C.bf * invzc;
+                const float er = std::fabs(ur - C.u_right[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(dMP, C.desc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            match_of_feature[bestIdx2] = i;
+            claimed[bestIdx2] = L->has_observations ? (L->has_observations[i] != 0) : 1;
+            nmatches++;
+            if (check_orientation) {
+                float rot = L->angle[i] - C.keys_un[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    match_of_feature[rotHist[i][j]] = -1;
+                    nmatches--;
+                }
+    }
+    *n_matches = nmatches;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LineMatcher
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+// LineMatcher::LiangBarsky — LineMatcher.cpp:1389-1460 (bugs and all: round() of the deltas, the horizontal-line test)
+bool liang_barsky(const double line[4], double out[4], const float bounds[4]) {
+    const double sx = line[0], sy = line[1], ex = line[2], ey = line[3];
+    double p[4], q[4];
+    p[0] = sx - ex; p[1] = ex - sx; p[2] = sy - ey; p[3] = ey - sy;
+    q[0] = sx - bounds[0]; q[1] = bounds[2] - sx; q[2] = sy - bounds[1]; q[3] = bounds[3] - sy;
+    if (p[0] == 0) { if (q[0] <= 0 || q[2] <= 0) return false; }
+    if (p[2] == 0) { if (q[2] >= 0 || q[3] >= 0) return false; }
+    double u[4];
+    for (int i = 0; i < 4; i++) u[i] = q[i] / p[i];
+    double u_min = 0, u_max = 1;
+    for (int i = 0; i < 4; i++) {
+        if (p[i] < 0) { if (u_min < u[i]) u_min = u[i]; }
+        else { if (u_max > u[i]) u_max = u[i]; }
+    }
+    if (u_max >= u_min) {
+        out[0] = sx + std::round(u_min * (ex - sx));
+        out[1] = sy + std::round(u_min * (ey - sy));
+        out[2] = sx + std::round(u_max * (ex - sx));
+        out[3] = sy + std::round(u_max * (ey - sy));
+        return true;
+    }
+    return false;
+}
+
+// cv::LineIterator(img, Point2f a, Point2f b).count (8-connected; points are cvRound'ed; the segment is clipped to the
+// image first — cv::clipLine; count 0 when it lies completely outside)
+int clip_code(long x, long y, long right, long bottom) { return (x < 0) + (x > right) * 2 + (y < 0) * 4 + (y > bottom) * 8; }
+int line_iterator_count(float fx0, float fy0, float fx1, float fy1, int cols, int rows) {
+    long x1 = lrintf(fx0), y1 = lrintf(fy0), x2 = lrintf(fx1), y2 = lrintf(fy1);
+    const long right = cols - 1, bottom = rows - 1;
+    if (cols <= 0 || rows <= 0) return 0;
+    int c1 = clip_code(x1, y1, right, bottom), c2 = clip_code(x2, y2, right, bottom);
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {  // cv::clipLine (imgproc/src/drawing.cpp), 64-bit arithmetic
+        long a;
+        if (c1 & 12) { a = c1 < 8 ? 0 : bottom; x1 += (long)((double)(a - y1) * (x2 - x1) / (y2 - y1)); y1 = a; c1 = (x1 < 0) + (x1 > right) * 2; }
+        if (c2 & 12) { a = c2 < 8 ? 0 : bottom; x2 += (long)((double)(a - y2) * (x2 - x1) / (y2 - y1)); y2 = a; c2 = (x2 < 0) + (x2 > right) * 2; }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) { a = c1 == 1 ? 0 : right; y1 += (long)((double)(a - x1) * (y2 - y1) / (x2 - x1)); x1 = a; c1 = 0; }
+            if (c2) { a = c2 == 1 ? 0 : right; y2 += (long)((double)(a - x2) * (y2 - y1) / (x2 - x1)); x2 = a; c2 = 0; }
+        }
+    }
+    if ((c1 | c2) != 0) return 0;
+    const long dx = std::labs(x2 - x1), dy = std::labs(y2 - y1);
+    return (int)std::max(dx, dy) + 1;
+}
+
+// LineMatcher::UpdateKeyLineData — LineMatcher.cpp:1601-1624
+void update_keyline(const double nl[4], pl_keyline& k, int cols, int rows) {
+    k.sx = (float)nl[0]; k.sy = (float)nl[1]; k.ex = (float)nl[2]; k.ey = (float)nl[3];
+    k.sx_oct = (float)nl[0]; k.sy_oct = (float)nl[1]; k.ex_oct = (float)nl[2]; k.ey_oct = (float)nl[3];
+    k.pt_x = (k.ex + k.sx) / 2; k.pt_y = (k.ey + k.sy) / 2;
+    k.length = float(std::sqrt(std::pow(k.sx - k.ex, 2) + std::pow(k.sy - k.ey, 2)));
+    k.num_pixels = line_iterator_count(k.sx, k.sy, k.ex, k.ey, cols, rows);
+    k.angle = atan2f((k.ey - k.sy), (k.ex - k.sx));  // std::atan2(float, float) under `using namespace std`
+    k.size = (k.ex - k.sx) * (k.ey - k.sy);
+    k.response = k.length / std::max(cols, rows);
+}
+
+// LineMatcher::LineOverLap — LineMatcher.cpp:1508-1559
+bool line_overlap(const pl_keyline& a, const pl_keyline& b, double threshold) {
+    double d1_x = std::fabs(a.sx - a.ex), d2_x = std::fabs(b.sx - b.ex);
+    double min_x = std::min(std::min(a.sx, a.ex), std::min(b.sx, b.ex));
+    double max_x = std::max(std::max(a.sx, a.ex), std::max(b.sx, b.ex));
+    double d1_y = std::fabs(a.sy - a.ey), d2_y = std::fabs(b.sy - b.ey);
+    double min_y = std::min(std::min(a.sy, a.ey), std::min(b.sy, b.ey));
+    double max_y = std::max(std::max(a.sy, a.ey), std::max(b.sy, b.ey));
+    if (d1_x == 0 || d2_x == 0) { if ((d1_y + d2_y - max_y + min_y) / std::min(d1_y, d2_y) >= threshold) return true; }
+    if (d1_y == 0 || d2_y == 0) { if ((d1_x + d2_x - max_x + min_x) / std::min(d1_x, d2_x) >= threshold) return true; }
+    if ((d1_x + d2_x - max_x + min_x) / std::min(d1_x, d2_x) >= threshold) {
+        if (d1_y + d2_y + min_y >= max_y) return true;
+        else if (max_y - min_y - d1_y - d2_y < 0.3 * std::min(d1_y, d2_y)) return true;
+    } else if ((d1_x + d2_x - max_x + min_x) / std::min(d1_x, d2_x) < threshold && (max_x - min_x - d1_x - d2_x) < 0.3 * std::min(d1_x, d2_x)) {
+        if ((d1_y + d2_y - max_y + min_y) / std::min(d1_y, d2_y) >= threshold) return true;
+    }
+    return false;
+}
+
+// LineMatcher::ReprojectionError — LineMatcher.cpp:1579-1596
+double reprojection_error(const pl_keyline& l1, const pl_keyline& l2) {
+    const double a[3] = {l1.sx, l1.sy, 1}, b[3] = {l1.ex, l1.ey, 1};
+    const double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    const double den = std::sqrt(std::pow(c[0], 2) + std::pow(c[1], 2));
+    const double ds = (l2.sx * c[0] + l2.sy * c[1] + 1.0 * c[2]) / den;
+    const double de = (l2.ex * c[0] + l2.ey * c[1] + 1.0 * c[2]) / den;
+    return std::sqrt(ds * ds + de * de);
+}
+
+// LineMatcher::LineMatching — LineMatcher.cpp:1463-1504; thresholds LineMatcher.h:94-98
+bool line_matching(const pl_keyline& kl1, const pl_keyline& kl2, const uint8_t* d1, const uint8_t* d2, const double off[5]) {
+    const double angle_threshold = 15.0 * M_PI / 180.0, length_threshold = 0.45, overlap_threshold = 0.5, desc_dist_threshold = 45,
+                 reproj_error_threshold = 45;
+    if (descriptor_distance(d1, d2) > desc_dist_threshold + off[3]) return false;
+    if (std::fabs(kl1.angle - kl2.angle) > angle_threshold + off[0] * M_PI / 180.0) return false;
+    if (std::min(kl1.length, kl2.length) / std::max(kl1.length, kl2.length) < length_threshold + off[1]) return false;
+    if (!line_overlap(kl1, kl2, overlap_threshold + off[2])) return false;
+    if (reprojection_error(kl1, kl2) > reproj_error_threshold) return false;
+    return true;
+}
+}  // namespace
+
+extern "C" int orc_line_iterator_count(float x0, float y0, float x1, float y1, int cols, int rows) {
+    return line_iterator_count(x0, y0, x1, y1, cols, rows);
+}
+
+// front half of LineMatcher::SearchByProjection (all three overloads): LineMatcher.cpp:96-212 / :558-… / :790-…
+extern "C" int orc_line_project(const double* start3d, const double* end3d, const pl_keyline* src_kl, const uint8_t* valid, int n,
+                                const float tcw[12], float fx, float fy, float cx, float cy, float min_x, float min_y, float max_x,
+                                float max_y, int img_cols, int img_rows, pl_keyline* out_kl, int* out_index, int* n_out) {
+    double T[12];
+    for (int i = 0; i < 12; i++) T[i] = tcw[i];  // Eigen::Isometry3d filled from the float Tcw (:77-92)
+    const float bounds[4] = {min_x, min_y, max_x, max_y};
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (!valid[i]) continue;
+        const double* Xs = start3d + 3 * (size_t)i;
+        const double* Xe = end3d + 3 * (size_t)i;
+        double cs[3], ce[3];
+        for (int r = 0; r < 3; r++) {  // Isometry3d * Vector3d: linear part times vector, plus translation
+            cs[r] = T[4 * r] * Xs[0] + T[4 * r + 1] * Xs[1] + T[4 * r + 2] * Xs[2] + T[4 * r + 3];
+            ce[r] = T[4 * r] * Xe[0] + T[4 * r + 1] * Xe[1] + T[4 * r + 2] * Xe[2] + T[4 * r + 3];
+        }
+        if (cs[2] < 0 && ce[2] < 0) continue;
+        double proj[4], clipped[4];
+        bool have = false, ok = false;
+        if (cs[2] < 0.0 || ce[2] < 0.0) {
+            const double lambda = -1.0 * cs[2] / (cs[2] - ce[2]);
+            const double x_c_cross = cs[0] + lambda * (cs[0] - ce[0]);
+            const double y_c_cross = cs[1] + lambda * (cs[1] - ce[1]);
+            if (cs[2] < 0.0) {
+                const float u_end = (float)(fx * ce[0] / ce[2] + cx), v_end = (float)(fy * ce[1] / ce[2] + cy);
+                proj[0] = x_c_cross; proj[1] = y_c_cross; proj[2] = u_end; proj[3] = v_end;
+                have = true;
+            } else if (ce[2] < 0.0) {
+                const float u_start = (float)(fx * cs[0] / cs[2] + cx), v_start = (float)(fy * cs[1] / cs[2] + cy);
+                proj[0] = u_start; proj[1] = v_start; proj[2] = x_c_cross; proj[3] = y_c_cross;
+                have = true;
+            }
+            if (have) {
+                ok = liang_barsky(proj, clipped, bounds);
+                if (ok) {
+                    pl_keyline k = src_kl[i];
+                    update_keyline(clipped, k, img_cols, img_rows);
+                    out_kl[m] = k; out_index[m] = i; m++;
+                }
+            }
+        }
+        if (cs[2] > 0.0 && ce[2] > 0.0) {
+            const float u_start = (float)(fx * cs[0] / cs[2] + cx), v_start = (float)(fy * cs[1] / cs[2] + cy);
+            const float u_end = (float)(fx * ce[0] / ce[2] + cx), v_end = (float)(fy * ce[1] / ce[2] + cy);
+            proj[0] = u_start; proj[1] = v_start; proj[2] = u_end; proj[3] = v_end;
+            if (liang_barsky(proj, clipped, bounds)) {
+                pl_keyline k = src_kl[i];
+                update_keyline(clipped, k, img_cols, img_rows);
+                out_kl[m] = k; out_index[m] = i; m++;
+            }
+        }
+    }
+    *n_out = m;
+    return 0;
+}
+
+// back half: all-pairs LineMatching with "last matching i wins, every hit counts" and the relaxed retry (:215-261)
+extern "C" int orc_line_match_pairs(const pl_keyline* proj, const uint8_t* proj_desc, int n_proj, const pl_keyline* cur, const uint8_t* cur_desc,
+                                    const uint8_t* cur_claimed, int n_cur, int* match_of_line, int* n_matches, int* used_relaxed) {
+    const double zero[5] = {0, 0, 0, 0, 0}, relaxed[5] = {10.0, -0.1, -0.1, 5, 10};
+    int cnt = 0;
+    for (int j = 0; j < n_cur; j++) match_of_line[j] = -1;
+    for (int j = 0; j < n_cur; j++) {
+        if (cur_claimed && cur_claimed[j]) continue;
+        for (int i = 0; i < n_proj; i++)
+            if (line_matching(proj[i], cur[j], proj_desc + 32 * (size_t)i, cur_desc + 32 * (size_t)j, zero)) { match_of_line[j] = i; cnt++; }
+    }
+    *used_relaxed = 0;
+    if (cnt * 1.0 / n_cur < 0.2) {
+        *used_relaxed = 1;
+        cnt = 0;
+        for (int j = 0; j < n_cur; j++) match_of_line[j] = -1;
+        for (int j = 0; j < n_cur; j++)
+            for (int i = 0; i < n_proj; i++)
+                if (line_matching(proj[i], cur[j], proj_desc + 32 * (size_t)i, cur_desc + 32 * (size_t)j, relaxed)) { match_of_line[j] = i; cnt++; }
+    }
+    *n_matches = cnt;
+    return 0;
+}

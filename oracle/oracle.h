@@ -37,6 +37,13 @@ ORC_API void orc_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int* d
 ORC_API void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist, int threads);
 ORC_API void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* t, const int* off, const int* cidx, int* dist);
 
+/* ---- projection searches / line matching over the POD views of plslam_c.h (match_oracle.cpp) ---- */
+ORC_API int orc_orb_search_local_points(const pl_frame_view* F, const pl_mappoint_view* M, float th, float nn_ratio, int* match_of_feature, int* n_matches);
+ORC_API int orc_orb_search_last_frame(const pl_frame_view* C, const pl_lastframe_view* L, float th, int mono, int check_orientation, int* match_of_feature, int* n_matches);
+ORC_API int orc_line_iterator_count(float x0, float y0, float x1, float y1, int cols, int rows);
+ORC_API int orc_line_project(const double* start3d, const double* end3d, const pl_keyline* src_kl, const uint8_t* valid, int n, const float tcw[12], float fx, float fy, float cx, float cy, float min_x, float min_y, float max_x, float max_y, int img_cols, int img_rows, pl_keyline* out_kl, int* out_index, int* n_out);
+ORC_API int orc_line_match_pairs(const pl_keyline* proj, const uint8_t* proj_desc, int n_proj, const pl_keyline* cur, const uint8_t* cur_desc, const uint8_t* cur_claimed, int n_cur, int* match_of_line, int* n_matches, int* used_relaxed);
+
 /* ---- line extraction (line_oracle.cpp) ---- */
 ORC_API int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t step, int order_mode, float* xyxy, double* width, double* prec, double* nfa, int cap);
 ORC_API int orc_lsd_angles(const uint8_t* img, int rows, int cols, size_t step, double* out, int* ow, int* oh);

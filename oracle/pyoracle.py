@@ -272,3 +272,84 @@ def line_extract(img, max_lines=80, order_mode=0):
         return kls[:0], desc[:0], co[:0]
     assert rc == 0, rc
     return kls[:n.value].copy(), desc[:n.value].copy(), co[:n.value].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# projection searches / line matching (views are the ctypes structures of the product's _native module)
+# ---------------------------------------------------------------------------------------------------------------
+def search_last_frame(cur_view, last_view, th, mono=False, check_orientation=True):
+    match = np.empty(max(cur_view.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().orc_orb_search_last_frame(C.byref(cur_view), C.byref(last_view), C.c_float(th), C.c_int(int(mono)),
+                                    C.c_int(int(check_orientation)), _p(match), C.byref(n))
+    return match[:cur_view.n], n.value
+
+
+def search_local_points(frame_view, mp_view, th, nn_ratio):
+    match = np.empty(max(frame_view.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().orc_orb_search_local_points(C.byref(frame_view), C.byref(mp_view), C.c_float(th), C.c_float(nn_ratio), _p(match), C.byref(n))
+    return match[:frame_view.n], n.value
+
+
+def project_lines(start3d, end3d, src_kl, valid, tcw, K, bounds, img_size):
+    s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)
+    e3 = np.ascontiguousarray(end3d, np.float64).reshape(-1, 3)
+    kl = np.ascontiguousarray(src_kl, KL_DTYPE)
+    va = np.ascontiguousarray(valid, np.uint8)
+    n = len(kl)
+    out = np.zeros(max(n, 1), KL_DTYPE)
+    idx = np.zeros(max(n, 1), np.int32)
+    m = C.c_int(0)
+    t = (C.c_float * 12)(*[float(x) for x in np.asarray(tcw, np.float32).reshape(-1)[:12]])
+    lib().orc_line_project(_p(s3), _p(e3), _p(kl), _p(va), C.c_int(n), t, C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]),
+                           C.c_float(K["cy"]), C.c_float(bounds[0]), C.c_float(bounds[1]), C.c_float(bounds[2]), C.c_float(bounds[3]),
+                           C.c_int(img_size[0]), C.c_int(img_size[1]), _p(out), _p(idx), C.byref(m))
+    return out[:m.value].copy(), idx[:m.value].copy()
+
+
+def match_lines(proj_kl, proj_desc, cur_kl, cur_desc, cur_claimed=None):
+    pk = np.ascontiguousarray(proj_kl, KL_DTYPE)
+    pd = np.ascontiguousarray(proj_desc, np.uint8).reshape(-1, 32)
+    ck = np.ascontiguousarray(cur_kl, KL_DTYPE)
+    cd = np.ascontiguousarray(cur_desc, np.uint8).reshape(-1, 32)
+    cc = None if cur_claimed is None else np.ascontiguousarray(cur_claimed, np.uint8)
+    match = np.full(max(len(ck), 1), -1, np.int32)
+    n, rel = C.c_int(0), C.c_int(0)
+    lib().orc_line_match_pairs(_p(pk), _p(pd), C.c_int(len(pk)), _p(ck), _p(cd), None if cc is None else _p(cc), C.c_int(len(ck)),
+                               _p(match), C.byref(n), C.byref(rel))
+    return match[:len(ck)], n.value, rel.value
+
+
+def line_iterator_count(x0, y0, x1, y1, cols, rows):
+    lib().orc_line_iterator_count.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+    return lib().orc_line_iterator_count(x0, y0, x1, y1, cols, rows)
+
+
+class OracleBackend:
+    """CPU-oracle backend for frontend.TrackingFrontEnd (same interface as frontend.GpuBackend)."""
+
+    def __init__(self, nfeatures=1000, threads=1):
+        self.orb = OrbOracle(nfeatures)
+        self.threads = threads
+
+    def scale_factors(self):
+        return self.orb.tables()["scale_factors"]
+
+    def extract_orb(self, frames):
+        return [self.orb.extract(f) for f in frames]
+
+    def extract_lines(self, frames):
+        return [line_extract(f, 80) for f in frames]
+
+    def search_last_frame(self, cv, lv, th):
+        return search_last_frame(cv, lv, th)
+
+    def search_local_points(self, fv, mv, th, nn):
+        return search_local_points(fv, mv, th, nn)
+
+    def project_lines(self, *a):
+        return project_lines(*a)
+
+    def match_lines(self, *a):
+        return match_lines(*a)

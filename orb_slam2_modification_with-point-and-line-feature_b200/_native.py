@@ -63,3 +63,79 @@ def ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# POD views of include/plslam_c.h (same layout for the native library and for the CPU oracle)
+# ---------------------------------------------------------------------------------------------------------------
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int), ("keys_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("claimed", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float), ("b", C.c_float),
+                ("tcw", C.c_float * 12), ("n_levels", C.c_int), ("scale_factors", C.c_void_p)]
+
+
+class MapPointView(C.Structure):
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("track_in_view", C.c_void_p), ("proj_x", C.c_void_p), ("proj_y", C.c_void_p),
+                ("proj_xr", C.c_void_p), ("scale_level", C.c_void_p), ("view_cos", C.c_void_p), ("has_observations", C.c_void_p)]
+
+
+class LastFrameView(C.Structure):
+    _fields_ = [("n", C.c_int), ("valid", C.c_void_p), ("world_pos", C.c_void_p), ("desc", C.c_void_p), ("octave", C.c_void_p),
+                ("angle", C.c_void_p), ("has_observations", C.c_void_p), ("tcw", C.c_float * 12)]
+
+
+def _addr(a):
+    return None if a is None else a.ctypes.data
+
+
+def make_frame_view(keys_un, desc, u_right, claimed, bounds, K, tcw, scale_factors, keep):
+    """keep: list that receives the arrays referenced by the view (lifetime)."""
+    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    u_right = np.ascontiguousarray(u_right, np.float32)
+    claimed = None if claimed is None else np.ascontiguousarray(claimed, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    keep += [keys_un, desc, u_right, claimed, sf]
+    v = FrameView()
+    v.n = len(keys_un)
+    v.keys_un, v.desc, v.u_right, v.claimed = _addr(keys_un), _addr(desc), _addr(u_right), _addr(claimed)
+    v.min_x, v.min_y, v.max_x, v.max_y = [float(b) for b in bounds]
+    v.fx, v.fy, v.cx, v.cy, v.bf = float(K["fx"]), float(K["fy"]), float(K["cx"]), float(K["cy"]), float(K["bf"])
+    v.b = float(np.float32(K["bf"]) / np.float32(K["fx"]))
+    t = np.asarray(tcw, np.float32).reshape(-1)[:12]
+    v.tcw = (C.c_float * 12)(*[float(x) for x in t])
+    v.n_levels = len(sf)
+    v.scale_factors = _addr(sf)
+    return v
+
+
+def make_mappoint_view(desc, in_view, proj_x, proj_y, proj_xr, level, view_cos, has_obs, keep):
+    desc = np.ascontiguousarray(desc, np.uint8)
+    in_view = np.ascontiguousarray(in_view, np.uint8)
+    px, py, pxr = (np.ascontiguousarray(a, np.float32) for a in (proj_x, proj_y, proj_xr))
+    level = np.ascontiguousarray(level, np.int32)
+    vc = np.ascontiguousarray(view_cos, np.float32)
+    ho = None if has_obs is None else np.ascontiguousarray(has_obs, np.uint8)
+    keep += [desc, in_view, px, py, pxr, level, vc, ho]
+    v = MapPointView()
+    v.n = len(in_view)
+    v.desc, v.track_in_view, v.proj_x, v.proj_y, v.proj_xr = _addr(desc), _addr(in_view), _addr(px), _addr(py), _addr(pxr)
+    v.scale_level, v.view_cos, v.has_observations = _addr(level), _addr(vc), _addr(ho)
+    return v
+
+
+def make_lastframe_view(valid, world_pos, desc, octave, angle, has_obs, tcw, keep):
+    valid = np.ascontiguousarray(valid, np.uint8)
+    wp = np.ascontiguousarray(world_pos, np.float32)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    octave = np.ascontiguousarray(octave, np.int32)
+    angle = np.ascontiguousarray(angle, np.float32)
+    ho = None if has_obs is None else np.ascontiguousarray(has_obs, np.uint8)
+    keep += [valid, wp, desc, octave, angle, ho]
+    v = LastFrameView()
+    v.n = len(valid)
+    v.valid, v.world_pos, v.desc, v.octave, v.angle, v.has_observations = _addr(valid), _addr(wp), _addr(desc), _addr(octave), _addr(angle), _addr(ho)
+    t = np.asarray(tcw, np.float32).reshape(-1)[:12]
+    v.tcw = (C.c_float * 12)(*[float(x) for x in t])
+    return v

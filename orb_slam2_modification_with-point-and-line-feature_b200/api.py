@@ -308,3 +308,51 @@ class DescriptorMatcher:
         check(N.lib().pl_hamming_candidates(self._h, ptr(q), C.c_int(q.shape[0]), ptr(t), C.c_int(t.shape[0]), ptr(off),
                                             ptr(ci), ptr(out)))
         return out
+
+    # ---- ORBmatcher projection searches (views built with _native.make_*_view) ----
+    def SearchByProjectionLastFrame(self, cur_view, last_view, th, mono=False, check_orientation=True):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) -> (match_of_feature, nmatches)."""
+        match = np.empty(max(cur_view.n, 1), np.int32)
+        n = C.c_int(0)
+        check(N.lib().pl_orb_search_last_frame(self._h, C.byref(cur_view), C.byref(last_view), C.c_float(th), C.c_int(int(mono)),
+                                               C.c_int(int(check_orientation)), ptr(match), C.byref(n)))
+        return match[:cur_view.n], n.value
+
+    def SearchByProjectionLocalPoints(self, frame_view, mp_view, th, nn_ratio):
+        """ORBmatcher(nn_ratio).SearchByProjection(F, vpMapPoints, th) -> (match_of_feature, nmatches)."""
+        match = np.empty(max(frame_view.n, 1), np.int32)
+        n = C.c_int(0)
+        check(N.lib().pl_orb_search_local_points(self._h, C.byref(frame_view), C.byref(mp_view), C.c_float(th), C.c_float(nn_ratio),
+                                                 ptr(match), C.byref(n)))
+        return match[:frame_view.n], n.value
+
+    # ---- LineMatcher ----
+    def project_lines(self, start3d, end3d, src_kl, valid, tcw, K, bounds, img_size):
+        """Front half of LineMatcher::SearchByProjection -> (new_KeyLines, new_kl_index)."""
+        s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)
+        e3 = np.ascontiguousarray(end3d, np.float64).reshape(-1, 3)
+        kl = np.ascontiguousarray(src_kl, KL_DTYPE)
+        va = np.ascontiguousarray(valid, np.uint8)
+        n = len(kl)
+        out = np.zeros(max(n, 1), KL_DTYPE)
+        idx = np.zeros(max(n, 1), np.int32)
+        m = C.c_int(0)
+        t = (C.c_float * 12)(*[float(x) for x in np.asarray(tcw, np.float32).reshape(-1)[:12]])
+        check(N.lib().pl_line_project(self._h, ptr(s3), ptr(e3), ptr(kl), ptr(va), C.c_int(n), t, C.c_float(K["fx"]), C.c_float(K["fy"]),
+                                      C.c_float(K["cx"]), C.c_float(K["cy"]), C.c_float(bounds[0]), C.c_float(bounds[1]),
+                                      C.c_float(bounds[2]), C.c_float(bounds[3]), C.c_int(img_size[0]), C.c_int(img_size[1]), ptr(out),
+                                      ptr(idx), C.byref(m)))
+        return out[:m.value].copy(), idx[:m.value].copy()
+
+    def match_lines(self, proj_kl, proj_desc, cur_kl, cur_desc, cur_claimed=None):
+        """Back half of LineMatcher::SearchByProjection -> (match_of_line, nmatches, used_relaxed)."""
+        pk = np.ascontiguousarray(proj_kl, KL_DTYPE)
+        pd = np.ascontiguousarray(proj_desc, np.uint8).reshape(-1, 32)
+        ck = np.ascontiguousarray(cur_kl, KL_DTYPE)
+        cd = np.ascontiguousarray(cur_desc, np.uint8).reshape(-1, 32)
+        cc = None if cur_claimed is None else np.ascontiguousarray(cur_claimed, np.uint8)
+        match = np.full(max(len(ck), 1), -1, np.int32)
+        n, rel = C.c_int(0), C.c_int(0)
+        check(N.lib().pl_line_match_pairs(self._h, ptr(pk), ptr(pd), C.c_int(len(pk)), ptr(ck), ptr(cd), ptr(cc), C.c_int(len(ck)),
+                                          ptr(match), C.byref(n), C.byref(rel)))
+        return match[:len(ck)], n.value, rel.value

@@ -518,7 +518,16 @@ __device__ bool lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double 
 }
 
 // ---- NFA ----
-__device__ __forceinline__ double lsd_log_gamma(double x) {
+// log_gamma(x) of lsd.cpp for integer-valued x = m + 1 comes from a host-built table (computed with the same
+// Windschitl / Lanczos formulas through the host libm, i.e. the exact doubles the CPU path uses); only pixel counts
+// beyond the table fall back to the device formula.
+constexpr int kLgMax = 16384;
+constexpr int kPMax = 12;  // p = 0.125 * 2^-j, j < kPMax
+struct NfaTabs {
+    const double* lgam;  // lgam[m] = log_gamma(m + 1)
+    double logp[kPMax], log1mp[kPMax], log10p[kPMax];
+};
+__device__ double lsd_log_gamma_direct(double x) {
     if (x > 15.0) {  // Windschitl
         return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
     }
@@ -531,6 +540,9 @@ __device__ __forceinline__ double lsd_log_gamma(double x) {
     }
     return a + log(b);
 }
+__device__ __forceinline__ double lsd_lgam1(const NfaTabs& T, int m) {  // log_gamma(double(m) + 1)
+    return m < kLgMax ? T.lgam[m] : lsd_log_gamma_direct((double)m + 1);
+}
 __device__ __forceinline__ bool lsd_double_equal(double a, double b) {
     if (a == b) return true;
     const double abs_diff = fabs(a - b), aa = fabs(a), bb = fabs(b);
@@ -538,12 +550,13 @@ __device__ __forceinline__ bool lsd_double_equal(double a, double b) {
     if (abs_max < 2.2250738585072014e-308) abs_max = 2.2250738585072014e-308;
     return (abs_diff / abs_max) <= (100.0 * 2.2204460492503131e-16);
 }
-__device__ double lsd_nfa(int n, int k, double p, double log_nt) {
+// nfa(): pj indexes p = 0.125 * 2^-pj
+__device__ double lsd_nfa(const NfaTabs& T, int n, int k, double p, int pj, double log_nt) {
     if (n == 0 || k == 0) return -log_nt;
-    if (n == k) return -log_nt - (double)n * log10(p);
+    const double lp = pj < kPMax ? T.logp[pj] : log(p), l1p = pj < kPMax ? T.log1mp[pj] : log(1.0 - p);
+    if (n == k) return -log_nt - (double)n * (pj < kPMax ? T.log10p[pj] : log10(p));
     const double p_term = p / (1 - p);
-    const double log1term = lsd_log_gamma((double)n + 1) - lsd_log_gamma((double)k + 1) - lsd_log_gamma((double)(n - k) + 1) +
-                            (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+    const double log1term = lsd_lgam1(T, n) - lsd_lgam1(T, k) - lsd_lgam1(T, n - k) + (double)k * lp + (double)(n - k) * l1p;
     double term = exp(log1term);
     if (lsd_double_equal(term, 0)) {
         if (k > n * p) return -log1term / 2.30258509299404568402 - log_nt;
@@ -567,9 +580,16 @@ __device__ double lsd_nfa(int n, int k, double p, double log_nt) {
 __device__ __forceinline__ double lsd_slope(double px, double py, double qx, double qy) {
     return ((int)ceil(py) == (int)ceil(qy)) ? 0.0 : (qx - px) / (qy - py);
 }
-// rect_nfa() of OpenCV >= 4.5 (real-valued corner scan); rows are distributed over the lanes
-__device__ double lsd_rect_nfa(const LsdFrame& F, const LsdRect& rec, double log_nt) {
-    const int lane = threadIdx.x & 31;
+
+// The pixel scan of rect_nfa() (OpenCV >= 4.5: real-valued corner scan).  `grp` lanes starting at lane `g0` scan the
+// rectangle (rows round-robin over the group); every lane returns its partial counts: total points and, for each
+// of the `np` precisions, aligned points.
+struct ScanCounts { int total; int alg[5]; };
+__device__ __forceinline__ ScanCounts lsd_rect_scan(const LsdFrame& F, const LsdRect& rec, const double* precs, int np, int sub, int grp) {
+    ScanCounts c;
+    c.total = 0;
+#pragma unroll
+    for (int t = 0; t < 5; t++) c.alg[t] = 0;
     const double half_width = rec.width / 2.0;
     const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
     const double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
@@ -588,10 +608,11 @@ __device__ double lsd_rect_nfa(const LsdFrame& F, const LsdRect& rec, double log
     const double frstep = lsd_slope(ox[0], oy[0], ox[3], oy[3]), srstep = lsd_slope(ox[3], oy[3], ox[2], oy[2]);
     const int y_begin = (int)ceil(oy[0]), y_end = (int)ceil(oy[2]);
     const int c1 = (int)ceil(oy[1]), c3 = (int)ceil(oy[3]);
-    int total = 0, alg = 0;
-    const bool by_rows = (y_end - y_begin) >= 12;
-    for (int yb = y_begin; yb <= y_end; yb += (by_rows ? 32 : 1)) {
-        const int y = by_rows ? yb + lane : yb;
+    const int nrows = y_end - y_begin + 1;
+    // few rows: the group walks along x inside each row; many rows: one row per lane
+    const bool by_rows = nrows >= grp;
+    for (int yb = y_begin; yb <= y_end; yb += (by_rows ? grp : 1)) {
+        const int y = by_rows ? yb + sub : yb;
         if (y > y_end || y < 0 || y >= F.H) continue;
         const double left_limit = (y <= c1) ? ox[0] + ((double)y - oy[0]) * flstep : ox[1] + ((double)y - oy[1]) * slstep;
         const double right_limit = (y < c3) ? ox[0] + ((double)y - oy[0]) * frstep : ox[3] + ((double)y - oy[3]) * srstep;
@@ -600,81 +621,152 @@ __device__ double lsd_rect_nfa(const LsdFrame& F, const LsdRect& rec, double log
         xe = min(xe, F.W - 1);
         if (xe < xs) continue;
         const float* arow = F.ang + (size_t)y * F.W;
-        if (by_rows) {
-            total += xe - xs + 1;
-            for (int x = xs; x <= xe; ++x) {
-                const float a = arow[x];
-                alg += (a != kNotDefDeg) && lsd_aligned(rec.theta, (double)a * kDegToRad, rec.prec);
+        if (by_rows || sub == 0) c.total += xe - xs + 1;
+        for (int x = xs + (by_rows ? 0 : sub); x <= xe; x += (by_rows ? 1 : grp)) {
+            const float a = arow[x];
+            if (a == kNotDefDeg) continue;
+            double n = rec.theta - (double)a * kDegToRad;
+            if (n < 0) n = -n;
+            if (n > k32Pi) {
+                n -= k2Pi;
+                if (n < 0) n = -n;
             }
-        } else {
-            if (lane == 0) total += xe - xs + 1;
-            for (int x = xs + lane; x <= xe; x += 32) {
-                const float a = arow[x];
-                alg += (a != kNotDefDeg) && lsd_aligned(rec.theta, (double)a * kDegToRad, rec.prec);
-            }
+#pragma unroll
+            for (int t = 0; t < 5; t++)
+                if (t < np) c.alg[t] += (n <= precs[t]);
         }
     }
+    return c;
+}
+__device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        total += __shfl_xor_sync(0xffffffffu, total, o);
-        alg += __shfl_xor_sync(0xffffffffu, alg, o);
-    }
-    return lsd_nfa(total, alg, rec.p, log_nt);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
-// rect_improve()
-__device__ double lsd_rect_improve(const LsdFrame& F, LsdRect& rec, double log_nt, double log_eps) {
+// rect_nfa() of one rectangle with the whole warp
+__device__ double lsd_rect_nfa(const LsdFrame& F, const NfaTabs& T, const LsdRect& rec, int pj, double log_nt) {
+    const int lane = threadIdx.x & 31;
+    const double pr[1] = {rec.prec};
+    ScanCounts c = lsd_rect_scan(F, rec, pr, 1, lane, 32);
+    const int total = warp_sum(c.total), alg = warp_sum(c.alg[0]);
+    return lsd_nfa(T, total, alg, rec.p, pj, log_nt);
+}
+
+// rect_improve().  The five trials of a stage are known up front (the trial rectangle evolves regardless of
+// acceptance), so a stage evaluates them concurrently — precision stages with one scan counting all five
+// tolerances, geometry stages with five lane groups — and then replays the reference's sequential acceptance.
+__device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect& rec, double log_nt, double log_eps) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     const double delta = 0.5, delta_2 = delta / 2.0;
-    double log_nfa = lsd_rect_nfa(F, rec, log_nt);
+    int pj = 0;  // rec.p == 0.125 * 2^-pj
+    double log_nfa = lsd_rect_nfa(F, T, rec, pj, log_nt);
     if (log_nfa > log_eps) return log_nfa;
-    LsdRect r = rec;
-    for (int n = 0; n < 5; ++n) {
-        r.p /= 2;
-        r.prec = r.p * kPiD;
-        const double v = lsd_rect_nfa(F, r, log_nt);
-        if (v > log_nfa) { log_nfa = v; rec = r; }
-    }
-    if (log_nfa > log_eps) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n) {
-        if ((r.width - delta) >= 0.5) {
-            r.width -= delta;
-            const double v = lsd_rect_nfa(F, r, log_nt);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-    }
-    if (log_nfa > log_eps) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n) {
-        if ((r.width - delta) >= 0.5) {
-            r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2;
-            r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
-            r.width -= delta;
-            const double v = lsd_rect_nfa(F, r, log_nt);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-    }
-    if (log_nfa > log_eps) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n) {
-        if ((r.width - delta) >= 0.5) {
-            r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2;
-            r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
-            r.width -= delta;
-            const double v = lsd_rect_nfa(F, r, log_nt);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
-        }
-    }
-    if (log_nfa > log_eps) return log_nfa;
-    r = rec;
-    for (int n = 0; n < 5; ++n) {
-        if ((r.width - delta) >= 0.5) {
+
+    // precision stage (used twice): r.p halves five times
+    auto precision_stage = [&](bool need_width) {
+        LsdRect r = rec;
+        int rj = pj;
+        if (need_width && !((r.width - delta) >= 0.5)) return;  // the last stage tries only while the width allows it
+        double ps[5], precs[5];
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
             r.p /= 2;
-            r.prec = r.p * kPiD;
-            const double v = lsd_rect_nfa(F, r, log_nt);
-            if (v > log_nfa) { rec = r; log_nfa = v; }
+            ps[n] = r.p;
+            precs[n] = r.p * kPiD;
         }
-    }
+        ScanCounts c = lsd_rect_scan(F, rec, precs, 5, lane, 32);
+        const int total = warp_sum(c.total);
+        int alg[5];
+#pragma unroll
+        for (int n = 0; n < 5; ++n) alg[n] = warp_sum(c.alg[n]);
+        // lanes 0..4 evaluate the five NFAs concurrently
+        double v = 0;
+        {
+            int myk = 0;
+            double myp = 0;
+#pragma unroll
+            for (int n = 0; n < 5; ++n)
+                if (lane == n) { myk = alg[n]; myp = ps[n]; }
+            if (lane < 5) v = lsd_nfa(T, total, myk, myp, rj + lane + 1, log_nt);
+        }
+        for (int n = 0; n < 5; ++n) {
+            const double vn = __shfl_sync(FULL, v, n);
+            if (vn > log_nfa) {
+                log_nfa = vn;
+                rec.p = ps[n];
+                rec.prec = precs[n];
+                pj = rj + n + 1;
+            }
+        }
+    };
+    // geometry stage: mode 0 = reduce width, 1 = reduce one side, 2 = reduce the other side
+    auto geometry_stage = [&](int mode) {
+        LsdRect r = rec;
+        LsdRect mine = rec;  // trial rectangle of this lane's group
+        const int grp = lane / 6, sub = lane - grp * 6;  // groups 0..4 (lanes 30,31 idle)
+        int ntrial = 0;
+        for (int n = 0; n < 5; ++n) {
+            if ((r.width - delta) >= 0.5) {
+                if (mode == 1) {
+                    r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2;
+                    r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
+                } else if (mode == 2) {
+                    r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2;
+                    r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
+                }
+                r.width -= delta;
+                if (grp == ntrial) mine = r;
+                ntrial++;
+            }
+        }
+        if (ntrial == 0) return;
+        const double pr[1] = {rec.prec};
+        ScanCounts c;
+        c.total = 0;
+        c.alg[0] = 0;
+        if (grp < ntrial) c = lsd_rect_scan(F, mine, pr, 1, sub, 6);
+        // reduce inside each 6-lane group (groups are not power-of-two wide: gather through shuffles)
+        int tot[5], al[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) { tot[t] = 0; al[t] = 0; }
+#pragma unroll
+        for (int l = 0; l < 30; ++l) {
+            const int ct = __shfl_sync(FULL, c.total, l), ca = __shfl_sync(FULL, c.alg[0], l);
+            tot[l / 6] += ct;
+            al[l / 6] += ca;
+        }
+        double v = 0;
+        {
+            int myn = 0, myk = 0;
+#pragma unroll
+            for (int t = 0; t < 5; ++t)
+                if (lane == t) { myn = tot[t]; myk = al[t]; }
+            if (lane < ntrial) v = lsd_nfa(T, myn, myk, rec.p, pj, log_nt);
+        }
+        // replay: trial t's rectangle lives in group t
+        for (int t = 0; t < ntrial; ++t) {
+            const double vt = __shfl_sync(FULL, v, t);
+            if (vt > log_nfa) {
+                log_nfa = vt;
+                const int src = t * 6;
+                rec.x1 = __shfl_sync(FULL, mine.x1, src); rec.y1 = __shfl_sync(FULL, mine.y1, src);
+                rec.x2 = __shfl_sync(FULL, mine.x2, src); rec.y2 = __shfl_sync(FULL, mine.y2, src);
+                rec.width = __shfl_sync(FULL, mine.width, src);
+            }
+        }
+    };
+
+    precision_stage(false);
+    if (log_nfa > log_eps) return log_nfa;
+    geometry_stage(0);
+    if (log_nfa > log_eps) return log_nfa;
+    geometry_stage(1);
+    if (log_nfa > log_eps) return log_nfa;
+    geometry_stage(2);
+    if (log_nfa > log_eps) return log_nfa;
+    precision_stage(true);
     return log_nfa;
 }
 
@@ -683,7 +775,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineGeom g, const float* __rest
                                                  uint8_t* __restrict__ used, unsigned int* __restrict__ reg,
                                                  const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
                                                  size_t plane, LsdSeg* __restrict__ segs, int* __restrict__ n_segs,
-                                                 int* __restrict__ flags) {
+                                                 int* __restrict__ flags, NfaTabs T, long long* __restrict__ phase_cycles) {
     const int f = blockIdx.x, lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
     LsdFrame F;
@@ -700,6 +792,15 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineGeom g, const float* __rest
     LsdSeg* out = segs + (size_t)f * g.seg_cap;
     int nout = 0;
     int pos = 0;
+    // optional cycle accounting per phase {seed scan, grow, rect fit, refine, NFA, regions tried, regions >= min size}
+    long long cyc[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long t0 = clock64();
+#define PL_PHASE(k)                       \
+    do {                                  \
+        const long long t1 = clock64();   \
+        cyc[k] += t1 - t0;                \
+        t0 = t1;                          \
+    } while (0)
     while (pos < ns) {
         // next unused seed at or after pos (32 candidates per probe)
         const int idx = pos + lane;
@@ -716,12 +817,20 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineGeom g, const float* __rest
         pos += j + 1;
         const int sx = (int)(pix % (unsigned)g.W), sy = (int)(pix / (unsigned)g.W);
         double reg_angle;
+        PL_PHASE(0);
         int n = lsd_region_grow(F, sx, sy, prec, &reg_angle);
+        PL_PHASE(1);
+        cyc[5]++;
         if (n < g.min_reg_size) continue;
+        cyc[6]++;
         LsdRect rec;
         lsd_region2rect(F, n, reg_angle, prec, p, rec);
-        if (!lsd_refine(F, n, reg_angle, prec, p, rec, density_th)) continue;
-        const double log_nfa = lsd_rect_improve(F, rec, g.log_nt, log_eps);
+        PL_PHASE(2);
+        const bool refined = lsd_refine(F, n, reg_angle, prec, p, rec, density_th);
+        PL_PHASE(3);
+        if (!refined) continue;
+        const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
+        PL_PHASE(4);
         if (log_nfa <= log_eps) continue;
         if (nout < g.seg_cap) {
             if (lane == 0) {
@@ -739,6 +848,9 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineGeom g, const float* __rest
         nout++;
     }
     if (lane == 0) n_segs[f] = min(nout, g.seg_cap);
+    if (phase_cycles && lane == 0)
+        for (int k = 0; k < 7; k++) phase_cycles[(size_t)f * 8 + k] = cyc[k];
+#undef PL_PHASE
 }
 
 }  // namespace pl
@@ -1108,6 +1220,9 @@ struct pl_line {
     int seg_cap_alloc = 0, tiles_alloc = 0;
     size_t plane_alloc = 0, in_alloc = 0;
     int* h_flags = nullptr;
+    double* d_lgam = nullptr;
+    long long* d_phase = nullptr;
+    NfaTabs nfa_tabs;
     int last_batch = 0, last_launches = 0;
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr};
@@ -1219,7 +1334,8 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     k_lsd_scatter<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_off, h->d_seeds);
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
-    k_lsd_grow<<<nf, 32, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_seeds, h->d_nseeds, plane, h->d_segs, h->d_nsegs, h->d_flags);
+    k_lsd_grow<<<nf, 32, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_seeds, h->d_nseeds, plane, h->d_segs, h->d_nsegs, h->d_flags,
+                                   h->nfa_tabs, prof ? h->d_phase : nullptr);
     launches++;
     if (prof) cudaEventRecord(h->ev[3], st);
     k_line_finalize<<<nf, kFinThreads, 0, st>>>(G, h->d_segs, h->d_nsegs, h->d_resp, d_kls, d_nout, cap);
@@ -1319,6 +1435,8 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_dy, B * align_up((size_t)max_cols, 8) * max_rows);
     A(&h->d_xtab, (size_t)W);
     A(&h->d_ytab, (size_t)H);
+    A(&h->d_lgam, (size_t)kLgMax);
+    A(&h->d_phase, B * 8);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_flags, sizeof(int) * B);
     if (e != cudaSuccess) {
         set_error("pl_line_create: %s", cudaGetErrorString(e));
@@ -1326,6 +1444,37 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
         return PL_ERR_CUDA;
     }
     h->seg_cap_alloc = seg_cap;
+    {
+        // log_gamma table of lsd.cpp (#define log_gamma(x) ((x)>15.0?log_gamma_windschitl(x):log_gamma_lanczos(x)))
+        std::vector<double> lg(kLgMax);
+        for (int m = 0; m < kLgMax; m++) {
+            const double x = (double)m + 1;
+            if (x > 15.0) {
+                lg[m] = 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+            } else {
+                static const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+                double a = (x + 0.5) * log(x + 5.5) - (x + 5.5), b = 0;
+                for (int n = 0; n < 7; ++n) {
+                    a -= log(x + double(n));
+                    b += q[n] * pow(x, double(n));
+                }
+                lg[m] = a + log(b);
+            }
+        }
+        if (cudaMemcpy(h->d_lgam, lg.data(), sizeof(double) * kLgMax, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("pl_line_create: table upload failed");
+            pl_line_destroy(h);
+            return PL_ERR_CUDA;
+        }
+        h->nfa_tabs.lgam = h->d_lgam;
+        double p = 22.5 / 180;
+        for (int j = 0; j < kPMax; j++) {
+            h->nfa_tabs.logp[j] = log(p);
+            h->nfa_tabs.log1mp[j] = log(1.0 - p);
+            h->nfa_tabs.log10p[j] = log10(p);
+            p /= 2;
+        }
+    }
     *out = h;
     return PL_OK;
 }
@@ -1336,7 +1485,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_used, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -1459,6 +1608,16 @@ PL_API int pl_line_lsd_read(pl_line* h, int frame, float* xyxy, double* width, d
         if (prec) prec[i] = tmp[i].p;
         if (nfa) nfa[i] = tmp[i].nfa;
     }
+    return PL_OK;
+}
+
+/* with profiling on: cycles of frame `frame` of the last chunk spent in {seed scan, grow, rect fit, refine, NFA} and
+ * the number of regions tried / regions that reached the minimum size (k_lsd_grow's own clock64 accounting) */
+PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out7) {
+    PL_CHECK_ARG(h && out7 && frame >= 0 && frame < h->last_batch);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    PL_CUDA_TRY(cudaMemcpyAsync(out7, h->d_phase + (size_t)frame * 8, sizeof(long long) * 7, cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PL_OK;
 }
 

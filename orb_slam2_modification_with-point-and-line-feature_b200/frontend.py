@@ -1,0 +1,230 @@
+"""Host-side glue that stands in for the reference's callers of the hot path (Frame / Tracking), in numpy.
+
+The reference's `Frame` constructor (src/Frame.cc:135-205) runs the two extractors, looks depth up for every
+keypoint (ComputeStereoFromRGBD, :1065-1117) and `Tracking` (src/Tracking.cc) feeds the matchers with the last frame
+(TrackWithMotionModel, :1212-1290) and the local map (SearchLocalPoints / SearchLocalLines, :1746-1865).  Those callers
+are OUT of the hot-path scope; this module reproduces just enough of them to drive the extractors and matchers on a
+synthetic RGB-D sequence.  The SAME glue drives both arms — the CUDA library through the C
+ABI and the CPU oracle — so both see byte-identical inputs.
+
+Backends expose: extract_orb(frames) -> [(kps, desc)], extract_lines(frames) -> [(kls, desc, coeffs)],
+search_last_frame(cur_view, last_view, th), search_local_points(frame_view, mp_view, th, nn_ratio),
+project_lines(...), match_lines(...).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as N
+from .synth import TUM1
+
+f32 = np.float32
+
+
+class FrameLite:
+    """The subset of ORB_SLAM2::Frame the matchers read."""
+
+    def __init__(self, kps, desc, kls, ldesc, depth, Tcw, K, scale_factors):
+        self.kps, self.desc, self.kls, self.ldesc = kps, desc, kls, ldesc
+        self.Tcw = np.asarray(Tcw, f32)
+        self.K = K
+        self.sf = np.asarray(scale_factors, f32)
+        h, w = depth.shape
+        self.bounds = (0.0, 0.0, float(w), float(h))  # ComputeImageBounds without distortion (Frame.cc:852-887)
+        self.size = (w, h)
+        # ComputeStereoFromRGBD (Frame.cc:1065-1117): depth at the (truncated) keypoint position
+        u = kps["x"].astype(np.int64)
+        v = kps["y"].astype(np.int64)
+        d = depth[np.clip(v, 0, h - 1), np.clip(u, 0, w - 1)].astype(f32)
+        ok = d > 0
+        self.depth = np.where(ok, d, f32(-1)).astype(f32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.u_right = np.where(ok, kps["x"] - f32(K["bf"]) / d, f32(-1)).astype(f32)
+        Rcw, tcw = self.Tcw[:3, :3], self.Tcw[:3, 3]
+        self.Rwc = Rcw.T.copy()
+        self.Ow = (-self.Rwc @ tcw).astype(f32)
+        # line endpoints: depth at the rounded endpoint
+        if len(kls):
+            sx = np.clip(np.rint(kls["sx"]).astype(np.int64), 0, w - 1)
+            sy = np.clip(np.rint(kls["sy"]).astype(np.int64), 0, h - 1)
+            ex = np.clip(np.rint(kls["ex"]).astype(np.int64), 0, w - 1)
+            ey = np.clip(np.rint(kls["ey"]).astype(np.int64), 0, h - 1)
+            self.ds, self.de = depth[sy, sx].astype(np.float64), depth[ey, ex].astype(np.float64)
+        else:
+            self.ds = self.de = np.zeros(0)
+
+    # Frame::UnprojectStereo (Frame.cc:1120-1134), vectorised
+    def unproject_points(self):
+        z = self.depth
+        x = (self.kps["x"] - f32(self.K["cx"])) * z * f32(1.0 / self.K["fx"])
+        y = (self.kps["y"] - f32(self.K["cy"])) * z * f32(1.0 / self.K["fy"])
+        pc = np.stack([x, y, z], 1).astype(f32)
+        return (pc @ self.Rwc.T + self.Ow).astype(f32)
+
+    def unproject_lines(self):
+        K = self.K
+        Rwc, Ow = self.Rwc.astype(np.float64), self.Ow.astype(np.float64)
+
+        def lift(px, py, z):
+            pc = np.stack([(px - K["cx"]) * z / K["fx"], (py - K["cy"]) * z / K["fy"], z], 1)
+            return pc @ Rwc.T + Ow
+
+        s3 = lift(self.kls["sx"].astype(np.float64), self.kls["sy"].astype(np.float64), self.ds)
+        e3 = lift(self.kls["ex"].astype(np.float64), self.kls["ey"].astype(np.float64), self.de)
+        return s3, e3, (self.ds > 0) & (self.de > 0)
+
+    def view(self, claimed, keep):
+        return N.make_frame_view(self.kps, self.desc, self.u_right, claimed, self.bounds, self.K, self.Tcw[:3].reshape(-1), self.sf, keep)
+
+
+class LocalMap:
+    """Map points / lines created from depth on keyframes (Tracking.cc:633-692), with the fields IsInFrustum needs."""
+
+    def __init__(self, max_points=3000, max_lines=300):
+        self.max_points, self.max_lines = max_points, max_lines
+        self.pos = np.zeros((0, 3), f32)
+        self.desc = np.zeros((0, 32), np.uint8)
+        self.normal = np.zeros((0, 3), f32)
+        self.max_d = np.zeros(0, f32)
+        self.min_d = np.zeros(0, f32)
+        self.ls = np.zeros((0, 3))
+        self.le = np.zeros((0, 3))
+        self.lkl = np.zeros(0, N.KL_DTYPE)
+        self.ldesc = np.zeros((0, 32), np.uint8)
+
+    def add_keyframe(self, F: FrameLite):
+        ok = F.depth > 0
+        P = F.unproject_points()[ok]
+        PO = P - F.Ow
+        dist = np.linalg.norm(PO, axis=1).astype(f32)
+        octv = F.kps["octave"][ok]
+        max_d = dist * F.sf[octv]                      # MapPoint::MapPoint (MapPoint.cc:57-66)
+        min_d = max_d / F.sf[len(F.sf) - 1]
+        self.pos = np.concatenate([self.pos, P])[-self.max_points:]
+        self.desc = np.concatenate([self.desc, F.desc[ok]])[-self.max_points:]
+        self.normal = np.concatenate([self.normal, (PO / dist[:, None]).astype(f32)])[-self.max_points:]
+        self.max_d = np.concatenate([self.max_d, max_d])[-self.max_points:]
+        self.min_d = np.concatenate([self.min_d, min_d])[-self.max_points:]
+        if len(F.kls):
+            s3, e3, okl = F.unproject_lines()
+            self.ls = np.concatenate([self.ls, s3[okl]])[-self.max_lines:]
+            self.le = np.concatenate([self.le, e3[okl]])[-self.max_lines:]
+            self.lkl = np.concatenate([self.lkl, F.kls[okl]])[-self.max_lines:]
+            self.ldesc = np.concatenate([self.ldesc, F.ldesc[okl]])[-self.max_lines:]
+
+    # Frame::IsInFrustum (Frame.cc:345-401) + MapPoint::PredictScale (MapPoint.cc:416-431), vectorised float32
+    def frustum(self, F: FrameLite, cos_limit=0.5):
+        K = F.K
+        Pc = (self.pos @ F.Tcw[:3, :3].T + F.Tcw[:3, 3]).astype(f32)
+        z = Pc[:, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            invz = (f32(1.0) / z).astype(f32)
+            u = (f32(K["fx"]) * Pc[:, 0] * invz + f32(K["cx"])).astype(f32)
+            v = (f32(K["fy"]) * Pc[:, 1] * invz + f32(K["cy"])).astype(f32)
+            PO = self.pos - F.Ow
+            dist = np.linalg.norm(PO, axis=1).astype(f32)
+            view_cos = (np.sum(PO * self.normal, 1) / dist).astype(f32)
+            ratio = self.max_d / dist
+            lvl = np.ceil(np.log(ratio) / np.log(F.sf[1] / F.sf[0])).astype(np.int64)
+        ok = (z > 0) & (u >= F.bounds[0]) & (u <= F.bounds[2]) & (v >= F.bounds[1]) & (v <= F.bounds[3])
+        ok &= (dist >= self.min_d) & (dist <= self.max_d) & (view_cos >= cos_limit)
+        lvl = np.clip(np.nan_to_num(lvl), 0, len(F.sf) - 1).astype(np.int32)
+        xr = (u - f32(K["bf"]) * invz).astype(f32)
+        return ok.astype(np.uint8), np.nan_to_num(u), np.nan_to_num(v), np.nan_to_num(xr), lvl, np.nan_to_num(view_cos)
+
+
+class TrackingFrontEnd:
+    """Per-frame matching schedule of config 2: C3 + D3 against the previous frame, C2 + D5 against the local map."""
+
+    def __init__(self, backend, K=TUM1, keyframe_every=10):
+        self.b = backend
+        self.K = K
+        self.kf_every = keyframe_every
+
+    def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True):
+        n = len(gray)
+        if features is None:
+            orb = self.b.extract_orb(gray)
+            lines = self.b.extract_lines(gray)
+        else:
+            orb, lines = features
+        rng = np.random.Generator(np.random.PCG64(424242))
+        lm = LocalMap()
+        last = None
+        summary = []
+        for t in range(n):
+            T = np.array(Tcw[t], np.float64)
+            if prior_noise:  # pose prior = ground truth + small noise (stand-in for the motion model)
+                T[:3, 3] += rng.normal(0, 0.002, 3)
+            kps, desc = orb[t]
+            kls, ldesc, _ = lines[t]
+            F = FrameLite(kps, desc, kls, ldesc, depth[t], T.astype(f32), self.K, scale_factors)
+            rec = dict(frame=t, n_kp=len(kps), n_kl=len(kls))
+            keep = []
+            if last is not None:
+                # --- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ---
+                cur_v = F.view(None, keep)
+                lv = N.make_lastframe_view(last.depth > 0, last.unproject_points(), last.desc, last.kps["octave"], last.kps["angle"],
+                                           (np.arange(len(last.kps)) % 3 != 0), last.Tcw[:3].reshape(-1), keep)
+                m3, n3 = self.b.search_last_frame(cur_v, lv, 15.0)
+                rec.update(c3_matches=n3, c3_sum=int(np.sum((m3.astype(np.int64) + 1) * (np.arange(len(m3)) + 1))))
+                # --- D3: LineMatcher(0.9).SearchByProjection(Cur, Last) (Tracking.cc:1247) ---
+                if len(last.kls) and len(F.kls):
+                    s3, e3, okl = last.unproject_lines()
+                    pk, pidx = self.b.project_lines(s3, e3, last.kls, okl, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size)
+                    ml, nl, rel = self.b.match_lines(pk, last.ldesc[pidx], F.kls, F.ldesc, None)
+                    rec.update(d3_proj=len(pk), d3_matches=nl, d3_relaxed=rel, d3_sum=int(np.sum((ml.astype(np.int64) + 1) * (np.arange(len(ml)) + 1))))
+                claimed = (m3 >= 0).astype(np.int32)
+            else:
+                claimed = None
+            if len(lm.pos):
+                # --- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ---
+                fv = F.view(claimed, keep)
+                inv, u, v, xr, lvl, vc = lm.frustum(F)
+                mv = N.make_mappoint_view(lm.desc, inv, u, v, xr, lvl, vc, None, keep)
+                m2, n2 = self.b.search_local_points(fv, mv, 3.0, 0.8)
+                rec.update(c2_in_view=int(inv.sum()), c2_matches=n2, c2_sum=int(np.sum((m2.astype(np.int64) + 1) * (np.arange(len(m2)) + 1))))
+                # --- D5: LineMatcher(0.8).SearchByProjection(F, localLines) (Tracking.cc:1863) ---
+                if len(lm.lkl) and len(F.kls):
+                    pk, pidx = self.b.project_lines(lm.ls, lm.le, lm.lkl, np.ones(len(lm.lkl), np.uint8), F.Tcw[:3].reshape(-1), self.K,
+                                                    F.bounds, F.size)
+                    ml, nl, rel = self.b.match_lines(pk, lm.ldesc[pidx], F.kls, F.ldesc, None)
+                    rec.update(d5_proj=len(pk), d5_matches=nl, d5_relaxed=rel, d5_sum=int(np.sum((ml.astype(np.int64) + 1) * (np.arange(len(ml)) + 1))))
+            if t % self.kf_every == 0:
+                lm.add_keyframe(F)
+            last = F
+            summary.append(rec)
+        return summary
+
+
+class GpuBackend:
+    """The CUDA library through the C ABI (host buffers)."""
+
+    def __init__(self, api, rows, cols, nfeatures=1000, chunk=32, device=0):
+        self.api = api
+        self.orb = api.ORBextractor(nfeatures, 1.2, 8, 20, 7, device=device, max_cols=cols, max_rows=rows, max_batch=chunk)
+        self.line = api.LineExtractor(device=device, max_cols=cols, max_rows=rows, max_batch=chunk)
+        self.m = api.DescriptorMatcher(device=device)
+
+    def scale_factors(self):
+        return self.orb.GetScaleFactors()
+
+    def extract_orb(self, frames):
+        kps, desc, cnt = self.orb.extract_batch(frames)
+        return [(kps[i, :cnt[i]], desc[i, :cnt[i]]) for i in range(len(cnt))]
+
+    def extract_lines(self, frames):
+        kls, desc, co, cnt = self.line.extract_batch(frames)
+        return [(kls[i, :cnt[i]], desc[i, :cnt[i]], co[i, :cnt[i]]) for i in range(len(cnt))]
+
+    def search_last_frame(self, cv, lv, th):
+        return self.m.SearchByProjectionLastFrame(cv, lv, th)
+
+    def search_local_points(self, fv, mv, th, nn):
+        return self.m.SearchByProjectionLocalPoints(fv, mv, th, nn)
+
+    def project_lines(self, *a):
+        return self.m.project_lines(*a)
+
+    def match_lines(self, *a):
+        return self.m.match_lines(*a)

@@ -1,0 +1,180 @@
+"""GPU parity tests (-m gpu): projection searches of ORBmatcher and LineMatcher through the C ABI vs the oracle.
+Bar: every match index and count bit-exact."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PKG = "orb_slam2_modification_with-point-and-line-feature_b200"
+
+
+@pytest.fixture(scope="module")
+def seq(synth):
+    gray, depth, T = synth.room_sequence(14)
+    return gray, depth, T
+
+
+@pytest.fixture(scope="module")
+def feats(seq, oracle):
+    gray = seq[0]
+    ob = oracle.OracleBackend()
+    return ob.extract_orb(gray), ob.extract_lines(gray)
+
+
+class Recorder:
+    """Wraps a backend and records every matcher call's outputs."""
+
+    def __init__(self, b):
+        self.b = b
+        self.log = []
+
+    def __getattr__(self, k):
+        f = getattr(self.b, k)
+        if k in ("search_last_frame", "search_local_points", "project_lines", "match_lines"):
+            def w(*a):
+                r = f(*a)
+                self.log.append((k, r))
+                return r
+            return w
+        return f
+
+
+def test_sequence_matchers_bit_exact(seq, feats, api, oracle, pkg):
+    fe = importlib.import_module(PKG + ".frontend")
+    gray, depth, T = seq
+    gb = Recorder(fe.GpuBackend(api, 480, 640))
+    ob = Recorder(oracle.OracleBackend())
+    sf = ob.b.scale_factors()
+    sg = fe.TrackingFrontEnd(gb).run(gray, depth, T, sf, features=feats)
+    so = fe.TrackingFrontEnd(ob).run(gray, depth, T, sf, features=feats)
+    assert sg == so
+    assert len(gb.log) == len(ob.log) and len(gb.log) > 30
+    n_matches = 0
+    for (kg, rg), (ko, ro) in zip(gb.log, ob.log):
+        assert kg == ko
+        if kg in ("search_last_frame", "search_local_points"):
+            assert np.array_equal(rg[0], ro[0]) and rg[1] == ro[1], kg
+            n_matches += rg[1]
+        elif kg == "match_lines":
+            assert np.array_equal(rg[0], ro[0]) and rg[1:] == ro[1:], kg
+        else:  # project_lines: integer fields exact, float fields to 1e-6 relative (atan2 / sqrt in double on both sides)
+            assert np.array_equal(rg[1], ro[1])
+            for fld in ("sx", "sy", "ex", "ey", "num_pixels", "class_id"):
+                assert np.array_equal(rg[0][fld], ro[0][fld]), fld
+            for fld in ("length", "angle", "response", "size"):
+                assert np.allclose(rg[0][fld], ro[0][fld], rtol=1e-6, atol=1e-6), fld
+    assert n_matches > 1000   # the schedule really matched things
+    assert any(r.get("c2_matches", 0) > 50 for r in sg) and any(r.get("d3_matches", 0) > 5 for r in sg)
+
+
+def _rand_frame(rng, n, N):
+    kp = np.zeros(n, N.KP_DTYPE)
+    kp["x"] = rng.uniform(0, 640, n).astype(np.float32)
+    kp["y"] = rng.uniform(0, 480, n).astype(np.float32)
+    kp["octave"] = rng.integers(0, 8, n)
+    kp["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    ur = np.where(rng.random(n) < 0.7, kp["x"] - rng.uniform(5, 40, n), -1).astype(np.float32)
+    return kp, desc, ur
+
+
+@pytest.mark.parametrize("seed,n,m,th", [(1, 1000, 2500, 3.0), (2, 50, 10, 1.0), (3, 2000, 300, 5.0), (4, 0, 20, 3.0), (5, 300, 0, 3.0)])
+def test_local_points_random(seed, n, m, th, api, oracle, synth):
+    """Random (dense, colliding) inputs: many points compete for the same features -> the claim order matters."""
+    N = api.N
+    rng = np.random.default_rng(seed)
+    kp, desc, ur = _rand_frame(rng, n, N)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    K = synth.TUM1
+    claimed = (rng.random(n) < 0.1).astype(np.int32)
+    keep = []
+    fv = N.make_frame_view(kp, desc, ur, claimed, (0, 0, 640, 480), K, np.eye(4, dtype=np.float32)[:3].reshape(-1), sf, keep)
+    src = rng.integers(0, max(n, 1), m)
+    mdesc = (desc[src] if n else rng.integers(0, 256, (m, 32), dtype=np.uint8)).copy()
+    flips = rng.random((m, 256)) < 0.05
+    mdesc ^= np.packbits(flips, axis=1, bitorder="little")
+    px = (kp["x"][src] if n else np.zeros(m)) + rng.normal(0, 3, m)
+    py = (kp["y"][src] if n else np.zeros(m)) + rng.normal(0, 3, m)
+    lvl = np.clip((kp["octave"][src] if n else np.zeros(m, np.int64)) + rng.integers(0, 2, m), 0, 7)
+    mv = N.make_mappoint_view(mdesc, rng.random(m) < 0.9, px, py, px - 20, lvl, rng.uniform(0.99, 1.0, m), rng.random(m) < 0.5, keep)
+    g = api.DescriptorMatcher().SearchByProjectionLocalPoints(fv, mv, th, 0.8)
+    o = oracle.search_local_points(fv, mv, th, 0.8)
+    assert np.array_equal(g[0], o[0]) and g[1] == o[1]
+    if n >= 1000 and m >= 1000:
+        assert g[1] > 200
+
+
+@pytest.mark.parametrize("seed,n,m,th", [(11, 1000, 1000, 15.0), (12, 1000, 1000, 30.0), (13, 64, 900, 7.0), (14, 1500, 0, 15.0)])
+def test_last_frame_random(seed, n, m, th, api, oracle, synth):
+    N = api.N
+    rng = np.random.default_rng(seed)
+    kp, desc, ur = _rand_frame(rng, n, N)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    K = synth.TUM1
+    keep = []
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = rng.normal(0, 0.05, 3)
+    fv = N.make_frame_view(kp, desc, ur, (rng.random(n) < 0.05).astype(np.int32), (0, 0, 640, 480), K, T[:3].reshape(-1), sf, keep)
+    src = rng.integers(0, n, m)
+    z = rng.uniform(0.5, 6, m).astype(np.float32)
+    z[: m // 50] *= -1                                             # some points behind the camera
+    X = np.stack([(kp["x"][src] + rng.normal(0, 4, m) - K["cx"]) * z / K["fx"], (kp["y"][src] + rng.normal(0, 4, m) - K["cy"]) * z / K["fy"], z], 1)
+    X = (X - T[:3, 3]).astype(np.float32)
+    ldesc = desc[src].copy()
+    ldesc ^= np.packbits(rng.random((m, 256)) < 0.06, axis=1, bitorder="little")
+    Tl = np.eye(4, dtype=np.float32)
+    Tl[2, 3] = 0.3 if seed == 12 else 0.0                          # seed 12: camera moved forward -> bForward window
+    lv = N.make_lastframe_view(rng.random(m) < 0.95, X, ldesc, kp["octave"][src], rng.uniform(0, 360, m), rng.random(m) < 0.6,
+                               Tl[:3].reshape(-1), keep)
+    for ori in (True, False):
+        g = api.DescriptorMatcher().SearchByProjectionLastFrame(fv, lv, th, False, ori)
+        o = oracle.search_last_frame(fv, lv, th, False, ori)
+        assert np.array_equal(g[0], o[0]) and g[1] == o[1]
+    if m:
+        assert o[1] > 20
+
+
+def test_line_project_and_match_cases(api, oracle, synth):
+    N = api.N
+    K = synth.TUM1
+    rng = np.random.default_rng(21)
+    n = 200
+    kl = np.zeros(n, N.KL_DTYPE)
+    kl["class_id"] = np.arange(n)
+    z1, z2 = rng.uniform(-1, 5, n), rng.uniform(-1, 5, n)         # endpoints in front of / behind the camera
+    s3 = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), z1], 1)
+    e3 = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), z2], 1)
+    e3[:10, 1] = s3[:10, 1]                                        # horizontal in 3-D
+    e3[10:20, 0] = s3[10:20, 0]                                    # vertical
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = (0.1, -0.05, 0.2)
+    m = api.DescriptorMatcher()
+    valid = np.random.default_rng(22).random(n) < 0.9
+    g = m.project_lines(s3, e3, kl, valid, T[:3].reshape(-1), K, (0, 0, 640, 480), (640, 480))
+    o = oracle.project_lines(s3, e3, kl, valid, T[:3].reshape(-1), K, (0, 0, 640, 480), (640, 480))
+    assert np.array_equal(g[1], o[1]) and len(g[1]) > 20
+    for fld in ("sx", "sy", "ex", "ey", "num_pixels"):
+        assert np.array_equal(g[0][fld], o[0][fld]), fld
+    # match: crafted current lines = noisy copies of the projected ones
+    pk = o[0]
+    cur = pk.copy()[: len(pk) // 2]
+    for fld in ("sx", "ex"):
+        cur[fld] += rng.normal(0, 2, len(cur)).astype(np.float32)
+    pd = rng.integers(0, 256, (len(pk), 32), dtype=np.uint8)
+    cd = pd[: len(cur)].copy()
+    cd ^= np.packbits(rng.random((len(cur), 256)) < 0.05, axis=1, bitorder="little")
+    claimed = (rng.random(len(cur)) < 0.2).astype(np.uint8)
+    for cl in (None, claimed):
+        gm = m.match_lines(pk, pd, cur, cd, cl)
+        om = oracle.match_lines(pk, pd, cur, cd, cl)
+        assert np.array_equal(gm[0], om[0]) and gm[1:] == om[1:]
+    # relaxed retry: random descriptors -> < 20 % matches in the strict pass
+    cd2 = rng.integers(0, 256, cd.shape, dtype=np.uint8)
+    gm = m.match_lines(pk, pd, cur, cd2, claimed)
+    om = oracle.match_lines(pk, pd, cur, cd2, claimed)
+    assert om[2] == 1 and np.array_equal(gm[0], om[0]) and gm[1:] == om[1:]
+    # empty sides
+    assert m.match_lines(pk[:0], pd[:0], cur, cd, None)[1] == 0
+    assert len(m.project_lines(s3[:0], e3[:0], kl[:0], valid[:0], T[:3].reshape(-1), K, (0, 0, 640, 480), (640, 480))[0]) == 0
