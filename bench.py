@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the point+line front-end (extract + match) on a synthetic 640x480 RGB-D sequence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F]
+
+Workload (BASELINE.json configs[1]): a 300-frame synthetic RGB-D sequence (three textured planes, TUM1 intrinsics).
+One STEP = one pass over the whole sequence:
+    ORBextractor(1000, 1.2, 8, 20, 7) on every frame  ||  LineExtractor (LSD + LBD, 80 lines) on every frame
+    then per frame, in order: ORBmatcher::SearchByProjection(Cur, Last, 15) [C3], LineMatcher::SearchByProjection(Cur, Last) [D3],
+    ORBmatcher::SearchByProjection(F, localPoints, 3) [C2], LineMatcher::SearchByProjection(F, localLines) [D5].
+Extraction of different frames is independent, so it is batched; matching runs frame by frame with prebuilt caller state.
+
+  value : frames/s with the images already resident in HBM (device pointers into the C ABI); wall clock between
+          device synchronisations, max over ranks.
+  e2e   : the same pass through the host-pointer C ABI: images in pinned host memory, H2D copies, D2H of features,
+          the caller glue (Frame-lite, numpy) and the matcher calls — everything a user of the API pays.
+  --impl reference : the CPU oracle (oracle/, the restatement of the reference's CPU path pinned to OpenCV 4.13) on all
+          host cores, frame-parallel extraction + the same glue and matchers, on a bounded sample of the sequence.
+
+With N > 1 (torchrun) every rank processes its own copy of the sequence (weak scaling, no data-path collective);
+the only cross-rank traffic is the timing reduction and a final gather of result checksums.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "orb_slam2_modification_with-point-and-line-feature_b200"
+METRIC = "frames/s point+line extract+match @640x480"
+W, H, NFEAT, MAXL = 640, 480, 1000, 80
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--chunk", type=int, default=0, help="frames per extraction chunk (0 = whole sequence)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="frames of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.samples, self.stop_flag = dev, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------------------------
+class Prebuilt:
+    """A backend that replays extraction results and counts matcher launches (value leg: caller state prebuilt)."""
+
+    def __init__(self, gb, feats):
+        self.gb, self.feats = gb, feats
+
+    def __getattr__(self, k):
+        return getattr(self.gb, k)
+
+    def extract_orb(self, frames):
+        return self.feats[0]
+
+    def extract_lines(self, frames):
+        return self.feats[1]
+
+
+class MatchPlan:
+    """Records the matcher calls of one pass (with all their host-side inputs) so that the timed region of the
+    `value` leg replays exactly the GPU work of the matching schedule without the numpy glue."""
+
+    def __init__(self, m):
+        self.m, self.calls, self.launches = m, [], 0
+
+    def record(self, name, *args):
+        self.calls.append((name, args))
+        r = getattr(self.m, name)(*args)
+        self.launches += self.m.last_launches()
+        return r
+
+    def replay(self):
+        for name, args in self.calls:
+            getattr(self.m, name)(*args)
+
+
+class RecordingBackend:
+    def __init__(self, gb, feats, plan):
+        self.gb, self.feats, self.plan = gb, feats, plan
+
+    def extract_orb(self, frames):
+        return self.feats[0]
+
+    def extract_lines(self, frames):
+        return self.feats[1]
+
+    def search_last_frame(self, cv, lv, th):
+        return self.plan.record("SearchByProjectionLastFrame", cv, lv, th)
+
+    def search_local_points(self, fv, mv, th, nn):
+        return self.plan.record("SearchByProjectionLocalPoints", fv, mv, th, nn)
+
+    def project_lines(self, *a):
+        return self.plan.record("project_lines", *a)
+
+    def match_lines(self, *a):
+        return self.plan.record("match_lines", *a)
+
+
+def run_ours(a, rank, world, local_rank, dist):
+    import torch
+    pkg = importlib.import_module(PKG)
+    build = importlib.import_module(PKG + ".build")
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    api = pkg.load_api()          # raises if libplslam.so is missing: there is no fallback path
+    fe = importlib.import_module(PKG + ".frontend")
+    N = api.N
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    F = a.frames
+    chunk = a.chunk or F
+    t0 = time.time()
+    gray, depth, Tcw = pkg.synth.room_sequence(F, W, H, workers=min(32, os.cpu_count() or 1))
+    t_gen = time.time() - t0
+
+    gb = fe.GpuBackend(api, H, W, NFEAT, chunk=chunk, device=dev)
+    sf = gb.scale_factors()
+    cap = gb.orb.max_keypoints()
+    d_gray = torch.from_numpy(gray).cuda()
+    d_kps = torch.empty((F, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.empty((F, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.empty(F, dtype=torch.int32, device="cuda")
+    d_kls = torch.empty((F, MAXL, 17), dtype=torch.float32, device="cuda")
+    d_ldesc = torch.empty((F, MAXL, 32), dtype=torch.uint8, device="cuda")
+    d_lco = torch.empty((F, MAXL, 3), dtype=torch.float64, device="cuda")
+    d_ln = torch.empty(F, dtype=torch.int32, device="cuda")
+    h_gray = torch.from_numpy(gray).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def extract_dev():
+        gb.orb.extract_batch_dev(d_gray.data_ptr(), F, H, W, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+        gb.line.extract_batch_dev(d_gray.data_ptr(), F, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
+        gb.orb.sync()
+        gb.line.sync()
+
+    # one untimed pass through the public API: features + the matching plan (caller state) of the sequence
+    feats = (gb.extract_orb(gray), gb.extract_lines(gray))
+    plan = MatchPlan(gb.m)
+    plan_fe = fe.TrackingFrontEnd(RecordingBackend(gb, feats, plan))   # keeps the arrays behind the recorded views alive
+    summary = plan_fe.run(gray, depth, Tcw, sf, features=feats)
+    extract_dev()
+    launches_per_step = gb.orb.last_launches() + gb.line.last_launches() + plan.launches
+
+    def step_dev():
+        extract_dev()
+        plan.replay()
+        gb.m.sync()
+
+    def step_e2e():
+        f = (gb.extract_orb(h_gray.numpy()), gb.extract_lines(h_gray.numpy()))
+        return fe.TrackingFrontEnd(gb).run(h_gray.numpy(), depth, Tcw, sf, features=f)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step_dev()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    # ---- value: K steps, L2 flushed between steps outside the timed spans ----
+    barrier()
+    t_total = 0.0
+    for _ in range(a.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        step_dev()
+        torch.cuda.synchronize()
+        t_total += time.perf_counter() - t1
+    barrier()
+    # ---- dominant-kernel timing (CUDA events on the launching stream, inside the same process) ----
+    N.check(N.lib().pl_line_set_profiling(gb.line._h, 1))
+    N.check(N.lib().pl_orb_set_profiling(gb.orb._h, 1))
+    for _ in range(max(1, min(a.steps, 3))):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        extract_dev()
+    lms, oms = np.zeros(5, np.float32), np.zeros(5, np.float32)
+    lch, och = C.c_int(), C.c_int()
+    N.check(N.lib().pl_line_stage_ms(gb.line._h, N.ptr(lms), C.byref(lch)))
+    N.check(N.lib().pl_orb_stage_ms(gb.orb._h, N.ptr(oms), C.byref(och)))
+    N.check(N.lib().pl_line_set_profiling(gb.line._h, 0))
+    N.check(N.lib().pl_orb_set_profiling(gb.orb._h, 0))
+    sampler.stop_flag = True
+    # ---- e2e: host buffers through the public API, glue included ----
+    e2e_steps = max(1, min(a.steps, 3))
+    step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s2 = step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t1
+    barrier()
+    assert s2 == summary, "e2e pass produced different matches than the plan pass"
+    # ---- p50 single-frame latency (extract both + match), frame by frame ----
+    gb1 = fe.GpuBackend(api, H, W, NFEAT, chunk=1, device=dev)
+    lat = []
+    for t in range(min(F, 40)):
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        gb1.orb.extract_batch_dev(d_gray[t].data_ptr(), 1, H, W, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+        gb1.line.extract_batch_dev(d_gray[t].data_ptr(), 1, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
+        gb1.orb.sync()
+        gb1.line.sync()
+        lat.append((time.perf_counter() - t1) * 1e3)
+    p50 = float(np.median(lat[3:])) if len(lat) > 3 else float(np.median(lat))
+
+    tt = torch.tensor([t_total, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        chk = torch.tensor([sum(r.get("c3_sum", 0) + r.get("c2_sum", 0) for r in summary) % (1 << 31)], dtype=torch.int64, device="cuda")
+        gathered = [torch.zeros_like(chk) for _ in range(world)] if rank == 0 else None
+        dist.gather(chk, gathered, dst=0)   # the final gather of results (checksums here)
+        if rank == 0:
+            assert all(int(g) == int(chk) for g in gathered), "ranks disagree on the match checksum"
+    t_total, t_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = load_peaks()
+    reps = max(1, min(a.steps, 3))
+    stage = {"lsd_grow": float(lms[2]) / reps, "lsd_scale_grad": float(lms[0]) / reps, "lsd_seed_sort": float(lms[1]) / reps,
+             "keylines_sobel": float(lms[3]) / reps, "lbd": float(lms[4]) / reps, "orb_pyramid": float(oms[0]) / reps,
+             "orb_fast": float(oms[1]) / reps, "orb_octree": float(oms[2]) / reps, "orb_blur": float(oms[3]) / reps,
+             "orb_orient_brief": float(oms[4]) / reps}
+    Ws, Hs = int(round(W * 0.8)), int(round(H * 0.8))
+    P, Pb = C.c_longlong(), C.c_longlong()
+    N.check(N.lib().pl_orb_bytes_per_frame(gb.orb._h, None, None, C.byref(P), C.byref(Pb)))
+    P, Pb = P.value, Pb.value
+    alg_bytes = {  # SURVEY.md §8(d) per-frame algorithmic bytes
+        "lsd_grow": 2 * 4 * Ws * Hs,                 # angle + modulus maps re-read by the region grower
+        "lsd_scale_grad": W * H + 2 * 4 * Ws * Hs,
+        "orb_pyramid": W * H + (P - 0) + Pb,
+        "orb_fast": Pb + 16 * 10000,
+        "orb_blur": 2 * P,
+        "orb_orient_brief": (749 + 4 + 512 + 32) * NFEAT,
+        "keylines_sobel": W * H + 4 * W * H,
+    }
+    dom = max(stage, key=stage.get)
+    rl = {}
+    for k, ms in stage.items():
+        if k in alg_bytes and ms > 0:
+            ach = alg_bytes[k] * F / (ms * 1e-3) / 1e9
+            rl[k] = {"ms_per_pass": round(ms, 4), "achieved_gbs": round(ach, 2), "frac": round(ach / peak, 5)}
+        else:
+            rl[k] = {"ms_per_pass": round(ms, 4)}
+    ach = alg_bytes.get(dom, 0) * F / (stage[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6),
+                "traffic": None, "peak_source": peak_src,
+                "note": "k_lsd_grow is the ordered (sequential-semantics) region grower: one warp per frame, latency-bound, not a streaming kernel",
+                "per_kernel": rl}
+
+    # ---- cpu_baseline: the oracle on one host core, bounded sample ----
+    cpu = cpu_sample(a.cpu_sample, gray, depth, Tcw, threads=1)
+    frames_total = F * a.steps * world
+    value = frames_total / t_total
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": round(t_total / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"seq{F}-640x480-rgbd: ORB(1000,1.2,8,20,7) + LSD/LBD(80) extract, C3+D3+C2+D5 match", "frames_per_step": F,
+                   "frames_per_rank": F, "extract_chunk": chunk, "l2_flush": "256 MiB device fill between steps, outside the timed spans",
+                   "timing": "wall clock between device synchronisations around each step (3 CUDA streams), max over ranks",
+                   "sequence_render_s": round(t_gen, 1)},
+        "p50_ms_per_frame": round(p50, 3),
+        "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(F * W * H),
+                "d2h_bytes_per_step": int(F * (cap * 60 + MAXL * (68 + 32 + 24) + 8)), "steps": e2e_steps,
+                "note": "host-pointer C ABI + numpy caller glue (Frame-lite) + per-call matcher copies"},
+        "gpu_launches": int(launches_per_step * a.steps),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+        "matches_per_frame": {"c3": round(float(np.mean([r.get("c3_matches", 0) for r in summary])), 1),
+                              "c2": round(float(np.mean([r.get("c2_matches", 0) for r in summary])), 1),
+                              "d3": round(float(np.mean([r.get("d3_matches", 0) for r in summary])), 1),
+                              "d5": round(float(np.mean([r.get("d5_matches", 0) for r in summary])), 1)},
+    }
+    return out
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference CPU path) — cpu_baseline leg and --impl reference
+# -------------------------------------------------------------------------------------------------------------------
+def cpu_pass(gray, depth, Tcw, threads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    pyoracle.build()
+    fe = importlib.import_module(PKG + ".frontend")
+    n = len(gray)
+    ob = pyoracle.OracleBackend(NFEAT)
+    sf = ob.scale_factors()
+    t0 = time.perf_counter()
+    if threads <= 1:
+        feats = (ob.extract_orb(gray), ob.extract_lines(gray))
+    else:
+        # frame-parallel over all host threads (ctypes releases the GIL); ORB || lines like Frame.cc:152-155
+        local = threading.local()
+
+        def orb_job(i):
+            if not hasattr(local, "o"):
+                local.o = pyoracle.OrbOracle(NFEAT)
+            return local.o.extract(gray[i])
+
+        with concurrent.futures.ThreadPoolExecutor(threads) as ex:
+            fo = [ex.submit(orb_job, i) for i in range(n)]
+            fl = [ex.submit(pyoracle.line_extract, gray[i], 80) for i in range(n)]
+            feats = ([f.result() for f in fo], [f.result() for f in fl])
+    summary = fe.TrackingFrontEnd(ob).run(gray, depth, Tcw[:n], sf, features=feats)
+    return time.perf_counter() - t0, summary
+
+
+def cpu_sample(nframes, gray, depth, Tcw, threads):
+    n = min(nframes, len(gray))
+    dt, _ = cpu_pass(gray[:n], depth[:n], Tcw, threads)
+    return {"value": round(n / dt, 3), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"first {n} frames of the sequence: oracle ORB + LSD/LBD extraction and the same C3/D3/C2/D5 schedule, {threads} thread(s)"}
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return None
+    pkg = importlib.import_module(PKG)
+    threads = os.cpu_count() or 1
+    n = min(a.frames, max(2 * threads, 16), 96)
+    gray, depth, Tcw = pkg.synth.room_sequence(a.frames, W, H, workers=min(32, threads))
+    gray, depth = gray[:n], depth[:n]
+    for _ in range(min(a.warmup, 1)):
+        cpu_pass(gray[: max(4, n // 4)], depth[: max(4, n // 4)], Tcw, threads)
+    t = 0.0
+    for _ in range(a.steps):
+        dt, _ = cpu_pass(gray, depth, Tcw, threads)
+        t += dt
+    v = n * a.steps / t
+    cpu = {"value": round(v, 3), "unit": "frames/s", "cores": threads, "kind": "port",
+           "sample": f"first {n} frames of the {a.frames}-frame sequence per step; frame-parallel extraction on {threads} threads, sequential matching"}
+    return {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "frames/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": round(t / a.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"seq{a.frames}-640x480-rgbd: ORB(1000,1.2,8,20,7) + LSD/LBD(80) extract, C3+D3+C2+D5 match",
+                       "frames_per_step": n, "note": "CPU oracle = restatement of the reference CPU path (the reference needs the OpenCV C++ SDK, absent here)"},
+            "cpu_baseline": cpu, "e2e": {"value": round(v, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    a = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if a.impl == "reference":
+        out = run_reference(a, rank, world)
+    else:
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        out = run_ours(a, rank, world, local_rank, dist)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    if rank == 0 and out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

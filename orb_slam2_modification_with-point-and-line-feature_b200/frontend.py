@@ -140,6 +140,7 @@ class TrackingFrontEnd:
         self.b = backend
         self.K = K
         self.kf_every = keyframe_every
+        self.keepalive = []  # arrays referenced by the views handed to the backend (views hold raw addresses)
 
     def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True):
         n = len(gray)
@@ -149,6 +150,7 @@ class TrackingFrontEnd:
         else:
             orb, lines = features
         rng = np.random.Generator(np.random.PCG64(424242))
+        self.keepalive = []
         lm = LocalMap()
         last = None
         summary = []
@@ -161,6 +163,7 @@ class TrackingFrontEnd:
             F = FrameLite(kps, desc, kls, ldesc, depth[t], T.astype(f32), self.K, scale_factors)
             rec = dict(frame=t, n_kp=len(kps), n_kl=len(kls))
             keep = []
+            self.keepalive.append(keep)
             if last is not None:
                 # --- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ---
                 cur_v = F.view(None, keep)

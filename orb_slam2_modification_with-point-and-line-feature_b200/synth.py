@@ -178,14 +178,32 @@ class Room:
         return np.ascontiguousarray(gray), np.ascontiguousarray(depth)
 
 
-def room_sequence(n: int = 300, width: int = 640, height: int = 480, seed: int = 2003):
-    """Returns (gray (n,h,w) uint8, depth (n,h,w) float32 metres, Tcw (n,4,4) float32)."""
-    room = Room()
+_ROOM = None
+
+
+def _render_job(args):
+    global _ROOM
+    if _ROOM is None:
+        _ROOM = Room()
+    T, width, height = args
+    return _ROOM.render(T, width, height)
+
+
+def room_sequence(n: int = 300, width: int = 640, height: int = 480, seed: int = 2003, workers: int = 1):
+    """Returns (gray (n,h,w) uint8, depth (n,h,w) float32 metres, Tcw (n,4,4) float32).  `workers` > 1 renders the
+    frames in a process pool (rendering is pure numpy and deterministic, so the result does not depend on it)."""
     T = room_trajectory(n, seed)
     gray = np.empty((n, height, width), np.uint8)
     depth = np.empty((n, height, width), np.float32)
-    for i in range(n):
-        gray[i], depth[i] = room.render(T[i], width, height)
+    jobs = [(T[i], width, height) for i in range(n)]
+    if workers > 1 and n > 4:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, n)) as pool:
+            res = pool.map(_render_job, jobs, chunksize=max(1, n // (4 * workers)))
+    else:
+        res = [_render_job(j) for j in jobs]
+    for i, (g, d) in enumerate(res):
+        gray[i], depth[i] = g, d
     return gray, depth, T.astype(np.float32)
 
 
