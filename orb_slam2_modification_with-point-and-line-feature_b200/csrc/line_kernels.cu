@@ -264,11 +264,13 @@ struct LsdSeg {  // one detected segment, in detection order (== cv::LineSegment
 struct LsdRect {
     double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
 };
+constexpr int kRegRing = 2048;  // most recent region points kept in shared memory (the BFS frontier reads them)
 struct LsdFrame {  // per-frame device views
     const float* ang;   // level-line angle in degrees or kNotDefDeg
     const int* g2;      // gx^2 + gy^2
     uint8_t* used;
     unsigned int* reg;  // region points, packed y<<16 | x
+    unsigned int* ring; // shared-memory copy of reg[n - kRegRing .. n)
     int W, H;
 };
 
@@ -303,6 +305,7 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
     float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
     if (lane == 0) {
         F.reg[0] = ((unsigned)sy << 16) | (unsigned)sx;
+        F.ring[0] = ((unsigned)sy << 16) | (unsigned)sx;
         F.used[(size_t)sy * F.W + sx] = 1;
     }
     __syncwarp();
@@ -316,7 +319,8 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
         float adeg = 0.f, ca = 0.f, sa = 0.f;
         double arad = 0.0;
         if (lane < 27 && b < nb) {
-            const unsigned p = F.reg[i + b];
+            const int ri = i + b;
+            const unsigned p = (n - ri <= kRegRing) ? F.ring[ri & (kRegRing - 1)] : F.reg[ri];
             xx = (int)(p & 0xffffu) + ddx;
             yy = (int)(p >> 16) + ddy;
             if (xx >= 0 && yy >= 0 && xx < F.W && yy < F.H) {
@@ -342,6 +346,7 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
             const float cj = __shfl_sync(FULL, ca, j), sj = __shfl_sync(FULL, sa, j);
             if (lane == j) {
                 F.reg[n] = ((unsigned)ay << 16) | (unsigned)ax;
+                F.ring[n & (kRegRing - 1)] = ((unsigned)ay << 16) | (unsigned)ax;
                 F.used[(size_t)ay * F.W + ax] = 1;
             }
             n++;
@@ -770,87 +775,150 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
     return log_nfa;
 }
 
-// flsd() main loop
-__global__ void __launch_bounds__(32) k_lsd_grow(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
-                                                 uint8_t* __restrict__ used, unsigned int* __restrict__ reg,
-                                                 const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
-                                                 size_t plane, LsdSeg* __restrict__ segs, int* __restrict__ n_segs,
-                                                 int* __restrict__ flags, NfaTabs T, long long* __restrict__ phase_cycles) {
-    const int f = blockIdx.x, lane = threadIdx.x;
+// flsd() main loop.  CTA = 4 warps per frame: warp 0 walks the seeds in order and does everything that touches the
+// USED map (region growing, rectangle fit, refine); the NFA validation of a fitted rectangle (rect_improve) only
+// reads the angle map and does not influence later regions, so it is handed to warps 1..3 through a queue and the
+// accepted segments are compacted in seed order at the end.
+constexpr int kGrowThreads = 128;
+struct LsdQueueItem { LsdRect rec; };
+
+__global__ void __launch_bounds__(kGrowThreads) k_lsd_grow(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
+                                                           uint8_t* __restrict__ used, unsigned int* __restrict__ reg,
+                                                           const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
+                                                           size_t plane, LsdQueueItem* __restrict__ queue, LsdSeg* __restrict__ qres,
+                                                           uint8_t* __restrict__ qvalid, LsdSeg* __restrict__ segs,
+                                                           int* __restrict__ n_segs, int* __restrict__ flags, NfaTabs T,
+                                                           long long* __restrict__ phase_cycles) {
+    __shared__ unsigned int s_ring[kRegRing];
+    __shared__ volatile int s_head, s_done;
+    __shared__ int s_ticket;
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     LsdFrame F;
     F.ang = angdeg + (size_t)f * plane;
     F.g2 = g2 + (size_t)f * plane;
     F.used = used + (size_t)f * plane;
     F.reg = reg + (size_t)f * plane;
+    F.ring = s_ring;
     F.W = g.W;
     F.H = g.H;
-    const unsigned int* sd = seeds + (size_t)f * plane;
-    const int ns = n_seeds[f];
-    const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
-    const double density_th = 0.7, log_eps = 0.0;
-    LsdSeg* out = segs + (size_t)f * g.seg_cap;
-    int nout = 0;
-    int pos = 0;
-    // optional cycle accounting per phase {seed scan, grow, rect fit, refine, NFA, regions tried, regions >= min size}
+    LsdQueueItem* q = queue + (size_t)f * g.seg_cap;
+    LsdSeg* qr = qres + (size_t)f * g.seg_cap;
+    uint8_t* qv = qvalid + (size_t)f * g.seg_cap;
+    const double log_eps = 0.0;
+    if (threadIdx.x == 0) { s_head = 0; s_done = 0; s_ticket = 0; }
+    __syncthreads();
     long long cyc[7] = {0, 0, 0, 0, 0, 0, 0};
-    long long t0 = clock64();
+    if (warp == 0) {
+        // ------------------------------ producer: ordered region growing ------------------------------
+        const unsigned int* sd = seeds + (size_t)f * plane;
+        const int ns = n_seeds[f];
+        const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
+        const double density_th = 0.7;
+        int head = 0, pos = 0;
+        long long t0 = clock64();
 #define PL_PHASE(k)                       \
     do {                                  \
         const long long t1 = clock64();   \
         cyc[k] += t1 - t0;                \
         t0 = t1;                          \
     } while (0)
-    while (pos < ns) {
-        // next unused seed at or after pos (32 candidates per probe)
-        const int idx = pos + lane;
-        unsigned pix = 0;
-        bool free_ = false;
-        if (idx < ns) {
-            pix = sd[idx];
-            free_ = F.used[pix] == 0;
-        }
-        const unsigned m = __ballot_sync(FULL, free_);
-        if (!m) { pos += 32; continue; }
-        const int j = __ffs(m) - 1;
-        pix = __shfl_sync(FULL, pix, j);
-        pos += j + 1;
-        const int sx = (int)(pix % (unsigned)g.W), sy = (int)(pix / (unsigned)g.W);
-        double reg_angle;
-        PL_PHASE(0);
-        int n = lsd_region_grow(F, sx, sy, prec, &reg_angle);
-        PL_PHASE(1);
-        cyc[5]++;
-        if (n < g.min_reg_size) continue;
-        cyc[6]++;
-        LsdRect rec;
-        lsd_region2rect(F, n, reg_angle, prec, p, rec);
-        PL_PHASE(2);
-        const bool refined = lsd_refine(F, n, reg_angle, prec, p, rec, density_th);
-        PL_PHASE(3);
-        if (!refined) continue;
-        const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
-        PL_PHASE(4);
-        if (log_nfa <= log_eps) continue;
-        if (nout < g.seg_cap) {
-            if (lane == 0) {
-                LsdSeg s;
-                s.x1 = (float)((rec.x1 + 0.5) / 0.8); s.y1 = (float)((rec.y1 + 0.5) / 0.8);
-                s.x2 = (float)((rec.x2 + 0.5) / 0.8); s.y2 = (float)((rec.y2 + 0.5) / 0.8);
-                s.width = rec.width / 0.8;
-                s.p = rec.p;
-                s.nfa = log_nfa;
-                out[nout] = s;
+        while (pos < ns) {
+            // next unused seed at or after pos (32 candidates per probe)
+            const int idx = pos + lane;
+            unsigned pix = 0;
+            bool free_ = false;
+            if (idx < ns) {
+                pix = sd[idx];
+                free_ = F.used[pix] == 0;
             }
-        } else if (lane == 0) {
-            atomicOr(flags + f, 1);
+            const unsigned m = __ballot_sync(FULL, free_);
+            if (!m) { pos += 32; continue; }
+            const int j = __ffs(m) - 1;
+            pix = __shfl_sync(FULL, pix, j);
+            pos += j + 1;
+            const int sx = (int)(pix % (unsigned)g.W), sy = (int)(pix / (unsigned)g.W);
+            double reg_angle;
+            PL_PHASE(0);
+            int n = lsd_region_grow(F, sx, sy, prec, &reg_angle);
+            PL_PHASE(1);
+            cyc[5]++;
+            if (n < g.min_reg_size) continue;
+            cyc[6]++;
+            LsdRect rec;
+            lsd_region2rect(F, n, reg_angle, prec, p, rec);
+            PL_PHASE(2);
+            const bool refined = lsd_refine(F, n, reg_angle, prec, p, rec, density_th);
+            PL_PHASE(3);
+            if (!refined) continue;
+            if (head < g.seg_cap) {
+                if (lane == 0) q[head].rec = rec;
+                __syncwarp();
+                __threadfence_block();
+                head++;
+                if (lane == 0) s_head = head;
+            } else if (lane == 0) {
+                atomicOr(flags + f, 1);
+            }
         }
-        nout++;
-    }
-    if (lane == 0) n_segs[f] = min(nout, g.seg_cap);
-    if (phase_cycles && lane == 0)
-        for (int k = 0; k < 7; k++) phase_cycles[(size_t)f * 8 + k] = cyc[k];
+        PL_PHASE(0);
 #undef PL_PHASE
+        __threadfence_block();
+        if (lane == 0) s_done = 1;
+    } else {
+        // ------------------------------ consumers: NFA validation ------------------------------
+        const long long c0 = clock64();
+        long long busy = 0;
+        while (true) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&s_ticket, 1);
+            t = __shfl_sync(FULL, t, 0);
+            int go = 0;
+            if (lane == 0) {
+                while (true) {
+                    if (t < s_head) { go = 1; break; }
+                    if (s_done) { go = (t < s_head) ? 1 : 0; break; }
+                    __nanosleep(256);
+                }
+            }
+            go = __shfl_sync(FULL, go, 0);
+            if (!go) break;
+            __threadfence_block();
+            const long long b0 = clock64();
+            LsdRect rec = q[t].rec;
+            const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
+            if (lane == 0) {
+                LsdSeg sg;
+                sg.x1 = (float)((rec.x1 + 0.5) / 0.8); sg.y1 = (float)((rec.y1 + 0.5) / 0.8);
+                sg.x2 = (float)((rec.x2 + 0.5) / 0.8); sg.y2 = (float)((rec.y2 + 0.5) / 0.8);
+                sg.width = rec.width / 0.8;
+                sg.p = rec.p;
+                sg.nfa = log_nfa;
+                qr[t] = sg;
+                qv[t] = log_nfa > log_eps;
+            }
+            busy += clock64() - b0;
+        }
+        if (warp == 1) { cyc[4] = busy; (void)c0; }
+    }
+    __syncthreads();
+    // ------------------------------ ordered compaction of the accepted segments ------------------------------
+    const int total = s_head;
+    if (warp == 0) {
+        LsdSeg* out = segs + (size_t)f * g.seg_cap;
+        int cnt = 0;
+        for (int base = 0; base < total; base += 32) {
+            const bool v = (base + lane < total) && qv[base + lane];
+            const unsigned m = __ballot_sync(FULL, v);
+            if (v) out[cnt + __popc(m & ((1u << lane) - 1u))] = qr[base + lane];
+            cnt += __popc(m);
+        }
+        if (lane == 0) n_segs[f] = cnt;
+        if (phase_cycles && lane == 0)
+            for (int k = 0; k < 7; k++)
+                if (k != 4) phase_cycles[(size_t)f * 8 + k] = cyc[k];
+    }
+    if (warp == 1 && phase_cycles && lane == 0) phase_cycles[(size_t)f * 8 + 4] = cyc[4];
 }
 
 }  // namespace pl
@@ -1210,6 +1278,9 @@ struct pl_line {
     int *d_maxg2 = nullptr, *d_tile_off = nullptr, *d_nseeds = nullptr, *d_nsegs = nullptr, *d_flags = nullptr, *d_nout = nullptr;
     unsigned short* d_tile_hist = nullptr;
     LsdSeg* d_segs = nullptr;
+    LsdSeg* d_qres = nullptr;
+    LsdQueueItem* d_queue = nullptr;
+    uint8_t* d_qvalid = nullptr;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
     short *d_dx = nullptr, *d_dy = nullptr;
     ExactTab *d_xtab = nullptr, *d_ytab = nullptr;
@@ -1334,8 +1405,8 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     k_lsd_scatter<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_off, h->d_seeds);
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
-    k_lsd_grow<<<nf, 32, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_seeds, h->d_nseeds, plane, h->d_segs, h->d_nsegs, h->d_flags,
-                                   h->nfa_tabs, prof ? h->d_phase : nullptr);
+    k_lsd_grow<<<nf, kGrowThreads, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_seeds, h->d_nseeds, plane, h->d_queue, h->d_qres,
+                                            h->d_qvalid, h->d_segs, h->d_nsegs, h->d_flags, h->nfa_tabs, prof ? h->d_phase : nullptr);
     launches++;
     if (prof) cudaEventRecord(h->ev[3], st);
     k_line_finalize<<<nf, kFinThreads, 0, st>>>(G, h->d_segs, h->d_nsegs, h->d_resp, d_kls, d_nout, cap);
@@ -1430,6 +1501,9 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_tile_hist, B * tiles * kBins);
     A(&h->d_tile_off, B * tiles * kBins);
     A(&h->d_segs, B * seg_cap);
+    A(&h->d_qres, B * seg_cap);
+    A(&h->d_queue, B * seg_cap);
+    A(&h->d_qvalid, B * seg_cap);
     A(&h->d_resp, B * seg_cap);
     A(&h->d_dx, B * align_up((size_t)max_cols, 8) * max_rows);
     A(&h->d_dy, B * align_up((size_t)max_cols, 8) * max_rows);
@@ -1485,7 +1559,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_used, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);

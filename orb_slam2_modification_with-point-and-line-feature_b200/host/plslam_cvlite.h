@@ -1,0 +1,80 @@
+// plslam_cvlite.h — the handful of OpenCV / Eigen types the reference's front-end signatures mention.
+//
+// Built with -DPLSLAM_WITH_OPENCV the real <opencv2/core.hpp> types are used and the mirrors below have exactly the
+// reference's signatures.  Without OpenCV (this image has no OpenCV C++ SDK) layout-compatible stand-ins are used so
+// that the host layer still compiles and can be tested: cv::KeyPoint (28 bytes), cv::line_descriptor::KeyLine (68 bytes),
+// a minimal reference-counted cv::Mat for CV_8UC1 planes, and Eigen::Vector3d as three doubles.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/plslam_c.h"
+
+#ifdef PLSLAM_WITH_OPENCV
+#include <opencv2/core/core.hpp>
+#include <opencv2/line_descriptor.hpp>
+#include <Eigen/Core>
+#else
+namespace cv {
+struct Point2f { float x = 0, y = 0; };
+struct KeyPoint {  // same field order and size as cv::KeyPoint
+    Point2f pt;
+    float size = 0, angle = -1, response = 0;
+    int octave = 0, class_id = -1;
+};
+static_assert(sizeof(KeyPoint) == sizeof(pl_keypoint), "cv::KeyPoint layout");
+enum { CV_8U = 0, CV_8UC1 = 0 };
+class Mat {  // 8-bit single-channel matrix, shared ownership, optional ROI (data offset + step)
+public:
+    int rows = 0, cols = 0;
+    size_t step = 0;
+    uint8_t* data = nullptr;
+    Mat() {}
+    Mat(int r, int c, int /*type*/) { create(r, c, CV_8UC1); }
+    Mat(int r, int c, int /*type*/, void* ext, size_t st) : rows(r), cols(c), step(st ? st : (size_t)c), data((uint8_t*)ext) {}
+    void create(int r, int c, int /*type*/) {
+        if (r == rows && c == cols && buf_ && step == (size_t)c) return;
+        rows = r; cols = c; step = (size_t)c;
+        buf_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * c > 0 ? (size_t)r * c : 1], std::default_delete<uint8_t[]>());
+        data = buf_.get();
+    }
+    void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    int type() const { return CV_8UC1; }
+    uint8_t* ptr(int r = 0) { return data + (size_t)r * step; }
+    const uint8_t* ptr(int r = 0) const { return data + (size_t)r * step; }
+    Mat roi(int x, int y, int w, int h) const {
+        Mat m = *this;
+        m.data = data + (size_t)y * step + x;
+        m.rows = h; m.cols = w;
+        return m;
+    }
+private:
+    std::shared_ptr<uint8_t> buf_;
+};
+typedef const Mat& InputArray;
+typedef Mat& OutputArray;
+namespace line_descriptor {
+struct KeyLine {  // same field order and size as cv::line_descriptor::KeyLine
+    float angle = 0;
+    int class_id = -1, octave = 0;
+    Point2f pt;
+    float response = 0, size = 0;
+    float startPointX = 0, startPointY = 0, endPointX = 0, endPointY = 0;
+    float sPointInOctaveX = 0, sPointInOctaveY = 0, ePointInOctaveX = 0, ePointInOctaveY = 0;
+    float lineLength = 0;
+    int numOfPixels = 0;
+};
+static_assert(sizeof(KeyLine) == sizeof(pl_keyline), "cv::line_descriptor::KeyLine layout");
+}  // namespace line_descriptor
+}  // namespace cv
+namespace Eigen {
+struct Vector3d {
+    double v[3] = {0, 0, 0};
+    double& operator()(int i) { return v[i]; }
+    double operator()(int i) const { return v[i]; }
+};
+}  // namespace Eigen
+#endif
