@@ -255,6 +255,14 @@ typedef struct {
 PL_API int pl_orb_search_last_frame(pl_match* h, const pl_frame_view* Cur, const pl_lastframe_view* Last, float th,
                                     int mono, int check_orientation, int* match_of_feature, int* n_matches);
 
+/* Batched forms: n independent reference calls (e.g. the n frame pairs of an offline sequence whose pose priors are
+ * already known) evaluated in one pass — every input array travels in one packed H2D copy, the kernels run one CTA /
+ * one grid row per call, results come back in one D2H copy.  match_of_feature[i] has cur[i].n entries. */
+PL_API int pl_orb_search_last_frame_batch(pl_match* h, int n, const pl_frame_view* cur, const pl_lastframe_view* last, float th,
+                                          int mono, int check_orientation, int* const* match_of_feature, int* n_matches);
+PL_API int pl_orb_search_local_points_batch(pl_match* h, int n, const pl_frame_view* F, const pl_mappoint_view* mps, float th,
+                                            float nn_ratio, int* const* match_of_feature, int* n_matches);
+
 /* D2: LineMatcher::LineMatching predicate (LineMatcher.cpp:1463-1504) evaluated for all pairs, followed by the
  * "last matching i wins, every hit counts" rule of LineMatcher::SearchByProjection (LineMatcher.cpp:215-233) and
  * its relaxed retry (:235-261).  proj = already projected/clipped keylines (new_KeyLines) with descriptors;
@@ -271,6 +279,34 @@ PL_API int pl_line_project(pl_match* h, const double* start3d, const double* end
                            const uint8_t* valid, int n, const float tcw[12], float fx, float fy, float cx, float cy,
                            float min_x, float min_y, float max_x, float max_y, int img_cols, int img_rows,
                            pl_keyline* out_kl, int* out_index, int* n_out);
+
+/* D3/D4/D5 complete: LineMatcher::SearchByProjection(Frame& Cur, const Frame& Last) (LineMatcher.cpp:72-269),
+ * (Frame&, KeyFrame*) (:527-721) and (Frame&, const vector<MapLine*>&) (:755-952) — they differ only in which map lines
+ * are offered and how `valid` is computed by the caller.  For each of the n calls: project + clip the 3-D lines with
+ * the frame's Tcw, then all-pairs LineMatching with the relaxed retry.  match_of_line[i][j] = index of the ORIGINAL map
+ * line (into lines[i], i.e. new_kl_index applied) assigned to current line j, or -1.  The optional outputs return the
+ * reference's new_KeyLines / new_kl_index (what its test-only overloads expose). */
+typedef struct {
+    int n;
+    const double* start3d;   /* MapLine::mStart3d, n x 3 */
+    const double* end3d;     /* MapLine::mEnd3d,   n x 3 */
+    const pl_keyline* kl;    /* the KeyLine the map line was created from (mvKeyLinesUn[i]) */
+    const uint8_t* desc;     /* MapLine::mLineDescriptor, n x 32 */
+    const uint8_t* valid;    /* pML && !outlier && !isBad() (:101-107), or mbTrackInView (:790-800) */
+} pl_mapline_view;
+typedef struct {
+    int n;                   /* Frame::NL */
+    const pl_keyline* kl;    /* Frame::mvKeyLinesUn */
+    const uint8_t* desc;     /* Frame::mLineDescriptors, n x 32 */
+    const uint8_t* claimed;  /* mvpMapLines[j] && Observations()>0 (:217-219); may be NULL */
+    float tcw[12];
+    float fx, fy, cx, cy, min_x, min_y, max_x, max_y;
+    int cols, rows;          /* im_gray_ size used by UpdateKeyLineData (:1614-1623) */
+} pl_lineframe_view;
+PL_API int pl_line_search_by_projection_batch(pl_match* h, int n, const pl_lineframe_view* cur, const pl_mapline_view* lines,
+                                              int* const* match_of_line, int* n_matches, int* used_relaxed,
+                                              pl_keyline* const* new_keylines /* may be NULL */, int* const* new_kl_index /* may be NULL */,
+                                              int* n_projected /* may be NULL */);
 
 #ifdef __cplusplus
 }

@@ -326,6 +326,30 @@ def line_iterator_count(x0, y0, x1, y1, cols, rows):
     return lib().orc_line_iterator_count(x0, y0, x1, y1, cols, rows)
 
 
+def line_search_by_projection(cur_view, line_view):
+    """LineMatcher::SearchByProjection on the POD views: project + clip, then all-pairs LineMatching.
+    Returns (match_of_line -> original map-line index or -1, nmatches, used_relaxed, n_projected)."""
+    n = line_view.n
+    out = np.zeros(max(n, 1), KL_DTYPE)
+    idx = np.zeros(max(n, 1), np.int32)
+    m = C.c_int(0)
+    lib().orc_line_project(C.c_void_p(line_view.start3d), C.c_void_p(line_view.end3d), C.c_void_p(line_view.kl), C.c_void_p(line_view.valid),
+                           C.c_int(n), cur_view.tcw, C.c_float(cur_view.fx), C.c_float(cur_view.fy), C.c_float(cur_view.cx), C.c_float(cur_view.cy),
+                           C.c_float(cur_view.min_x), C.c_float(cur_view.min_y), C.c_float(cur_view.max_x), C.c_float(cur_view.max_y),
+                           C.c_int(cur_view.cols), C.c_int(cur_view.rows), _p(out), _p(idx), C.byref(m))
+    npj = m.value
+    desc = np.ctypeslib.as_array((C.c_uint8 * (max(n, 1) * 32)).from_address(line_view.desc)).reshape(-1, 32) if n else np.zeros((0, 32), np.uint8)
+    pdesc = np.ascontiguousarray(desc[idx[:npj]]) if npj else np.zeros((0, 32), np.uint8)
+    match = np.full(max(cur_view.n, 1), -1, np.int32)
+    cnt, rel = C.c_int(0), C.c_int(0)
+    if cur_view.n:
+        lib().orc_line_match_pairs(_p(out), _p(pdesc) if npj else None, C.c_int(npj), C.c_void_p(cur_view.kl), C.c_void_p(cur_view.desc),
+                                   C.c_void_p(cur_view.claimed), C.c_int(cur_view.n), _p(match), C.byref(cnt), C.byref(rel))
+    match = match[:cur_view.n]
+    res = np.where(match >= 0, idx[np.clip(match, 0, max(npj - 1, 0))], -1).astype(np.int32) if npj else match.copy()
+    return res, cnt.value, rel.value, npj
+
+
 class OracleBackend:
     """CPU-oracle backend for frontend.TrackingFrontEnd (same interface as frontend.GpuBackend)."""
 
@@ -353,3 +377,13 @@ class OracleBackend:
 
     def match_lines(self, *a):
         return match_lines(*a)
+
+    # "batched" forms: the CPU path simply loops (sequential matching, as in the reference)
+    def search_last_frame_batch(self, cvs, lvs, th):
+        return [search_last_frame(c, l, th) for c, l in zip(cvs, lvs)]
+
+    def search_local_points_batch(self, fvs, mvs, th, nn):
+        return [search_local_points(f, m, th, nn) for f, m in zip(fvs, mvs)]
+
+    def line_search_batch(self, cvs, lvs):
+        return [line_search_by_projection(c, l) for c, l in zip(cvs, lvs)]

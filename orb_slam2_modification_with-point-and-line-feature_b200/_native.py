@@ -139,3 +139,42 @@ def make_lastframe_view(valid, world_pos, desc, octave, angle, has_obs, tcw, kee
     t = np.asarray(tcw, np.float32).reshape(-1)[:12]
     v.tcw = (C.c_float * 12)(*[float(x) for x in t])
     return v
+
+
+class MapLineView(C.Structure):
+    _fields_ = [("n", C.c_int), ("start3d", C.c_void_p), ("end3d", C.c_void_p), ("kl", C.c_void_p), ("desc", C.c_void_p), ("valid", C.c_void_p)]
+
+
+class LineFrameView(C.Structure):
+    _fields_ = [("n", C.c_int), ("kl", C.c_void_p), ("desc", C.c_void_p), ("claimed", C.c_void_p), ("tcw", C.c_float * 12),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("cols", C.c_int), ("rows", C.c_int)]
+
+
+def make_mapline_view(start3d, end3d, kl, desc, valid, keep):
+    s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)
+    e3 = np.ascontiguousarray(end3d, np.float64).reshape(-1, 3)
+    kl = np.ascontiguousarray(kl, KL_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    valid = np.ascontiguousarray(valid, np.uint8)
+    keep += [s3, e3, kl, desc, valid]
+    v = MapLineView()
+    v.n = len(kl)
+    v.start3d, v.end3d, v.kl, v.desc, v.valid = _addr(s3), _addr(e3), _addr(kl), _addr(desc), _addr(valid)
+    return v
+
+
+def make_lineframe_view(kl, desc, claimed, tcw, K, bounds, img_size, keep):
+    kl = np.ascontiguousarray(kl, KL_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    claimed = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    keep += [kl, desc, claimed]
+    v = LineFrameView()
+    v.n = len(kl)
+    v.kl, v.desc, v.claimed = _addr(kl), _addr(desc), _addr(claimed)
+    t = np.asarray(tcw, np.float32).reshape(-1)[:12]
+    v.tcw = (C.c_float * 12)(*[float(x) for x in t])
+    v.fx, v.fy, v.cx, v.cy = float(K["fx"]), float(K["fy"]), float(K["cx"]), float(K["cy"])
+    v.min_x, v.min_y, v.max_x, v.max_y = [float(b) for b in bounds]
+    v.cols, v.rows = int(img_size[0]), int(img_size[1])
+    return v

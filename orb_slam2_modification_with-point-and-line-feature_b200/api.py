@@ -356,3 +356,42 @@ class DescriptorMatcher:
         check(N.lib().pl_line_match_pairs(self._h, ptr(pk), ptr(pd), C.c_int(len(pk)), ptr(ck), ptr(cd), ptr(cc), C.c_int(len(ck)),
                                           ptr(match), C.byref(n), C.byref(rel)))
         return match[:len(ck)], n.value, rel.value
+
+    # ---- batched forms: n independent reference calls in one pass ----
+    @staticmethod
+    def _view_array(views, typ):
+        arr = (typ * len(views))()
+        for i, v in enumerate(views):
+            arr[i] = v
+        return arr
+
+    def _batch_points(self, fn, frame_views, pt_views, pt_type, *scalars):
+        n = len(frame_views)
+        fa = self._view_array(frame_views, N.FrameView)
+        pa = self._view_array(pt_views, pt_type)
+        outs = [np.empty(max(v.n, 1), np.int32) for v in frame_views]
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        cnt = np.zeros(max(n, 1), np.int32)
+        check(fn(self._h, C.c_int(n), fa, pa, *scalars, ptrs, ptr(cnt)))
+        return [(outs[i][:frame_views[i].n], int(cnt[i])) for i in range(n)]
+
+    def SearchByProjectionLastFrameBatch(self, cur_views, last_views, th, mono=False, check_orientation=True):
+        return self._batch_points(N.lib().pl_orb_search_last_frame_batch, cur_views, last_views, N.LastFrameView, C.c_float(th),
+                                  C.c_int(int(mono)), C.c_int(int(check_orientation)))
+
+    def SearchByProjectionLocalPointsBatch(self, frame_views, mp_views, th, nn_ratio):
+        return self._batch_points(N.lib().pl_orb_search_local_points_batch, frame_views, mp_views, N.MapPointView, C.c_float(th),
+                                  C.c_float(nn_ratio))
+
+    def SearchLinesByProjectionBatch(self, cur_views, line_views):
+        """LineMatcher::SearchByProjection for n (frame, map lines) pairs ->
+        [(match_of_line -> original map-line index or -1, nmatches, used_relaxed, n_projected)]."""
+        n = len(cur_views)
+        ca = self._view_array(cur_views, N.LineFrameView)
+        la = self._view_array(line_views, N.MapLineView)
+        outs = [np.full(max(v.n, 1), -1, np.int32) for v in cur_views]
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        cnt, rel, npj = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+        nulls = (C.c_void_p * n)()
+        check(N.lib().pl_line_search_by_projection_batch(self._h, C.c_int(n), ca, la, ptrs, ptr(cnt), ptr(rel), nulls, nulls, ptr(npj)))
+        return [(outs[i][:cur_views[i].n], int(cnt[i]), int(rel[i]), int(npj[i])) for i in range(n)]

@@ -1,0 +1,85 @@
+// match_common.cuh — pieces shared by match_kernels.cu (Hamming searches) and search_kernels.cu (projection searches,
+// line matching): the 256-bit Hamming distance, the pl_match handle and its scratch / staging buffers.
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "pl_common.cuh"
+
+namespace pl {
+// 256-bit Hamming distance of two 32-byte rows held as 2 x uint4
+// (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:2083-2103 == LineMatcher::DescriptorDistance, src/LineMatcher.cpp:20-39)
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+           __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+}  // namespace pl
+
+// one pinned host buffer + one device buffer: every input of a call is packed into it and uploaded with ONE copy
+struct PlStage {
+    uint8_t* h = nullptr;
+    uint8_t* d = nullptr;
+    size_t cap = 0, cur = 0;
+    int reserve(size_t bytes) {
+        cur = 0;
+        if (bytes <= cap) return PL_OK;
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes + bytes / 4, (size_t)1 << 20);
+        PL_CUDA_TRY(cudaMallocHost((void**)&h, want));
+        PL_CUDA_TRY(cudaMalloc((void**)&d, want));
+        cap = want;
+        return PL_OK;
+    }
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    // copies n elements into the pinned buffer; returns the DEVICE address they will have after upload()
+    template <typename T>
+    const T* put(const T* src, size_t n) {
+        const size_t off = cur;
+        if (n && src) memcpy(h + off, src, n * sizeof(T));
+        cur += pad(n * sizeof(T));
+        return (const T*)(d + off);
+    }
+    // space that only exists on the device side (outputs / scratch): returns device address, and host mirror address
+    template <typename T>
+    T* out(size_t n, T** host_mirror = nullptr) {
+        const size_t off = cur;
+        cur += pad(n * sizeof(T));
+        if (host_mirror) *host_mirror = (T*)(h + off);
+        return (T*)(d + off);
+    }
+    void release() {
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+        cap = cur = 0;
+    }
+};
+
+struct pl_match {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int last_launches = 0;
+    // growable device scratch
+    uint8_t* d_buf[24] = {nullptr};
+    size_t d_cap[24] = {0};
+    int sm_count = 148;
+    PlStage in, res;   // packed inputs / packed results of the batched searches
+};
+
+namespace pl {
+inline int match_scratch(pl_match* h, int slot, size_t bytes, void** out) {
+    if (h->d_cap[slot] < bytes) {
+        if (h->d_buf[slot]) cudaFree(h->d_buf[slot]);
+        h->d_buf[slot] = nullptr;
+        h->d_cap[slot] = 0;
+        size_t want = std::max(bytes + bytes / 4, (size_t)1 << 16);
+        PL_CUDA_TRY(cudaMalloc((void**)&h->d_buf[slot], want));
+        h->d_cap[slot] = want;
+    }
+    *out = h->d_buf[slot];
+    return PL_OK;
+}
+}  // namespace pl

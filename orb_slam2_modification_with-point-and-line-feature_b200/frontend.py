@@ -8,8 +8,8 @@ synthetic RGB-D sequence.  The SAME glue drives bot
 ABI and the CPU oracle — so both see byte-identical inputs.
 
 Backends expose: extract_orb(frames) -> [(kps, desc)], extract_lines(frames) -> [(kls, desc, coeffs)],
-search_last_frame(cur_view, last_view, th), search_local_points(frame_view, mp_view, th, nn_ratio),
-project_lines(...), match_lines(...).
+search_last_frame(cur_view, last_view, th), search_local_points(frame_view, mp_view, th, nn_ratio) and their *_batch
+forms over lists of views, line_search_batch(line_frame_views, map_line_views).
 """
 from __future__ import annotations
 
@@ -134,7 +134,12 @@ class LocalMap:
 
 
 class TrackingFrontEnd:
-    """Per-frame matching schedule of config 2: C3 + D3 against the previous frame, C2 + D5 against the local map."""
+    """Matching schedule of config 2: per frame C3 + D3 against the previous frame and C2 + D5 against the local map.
+
+    The pose prior of every frame is known up front (ground truth + noise; no optimiser in the loop), so the caller
+    state of all frames can be prepared first and each kind of search is issued as ONE batched call over the sequence
+    (`batch=True`, the offline / throughput mode) or frame by frame (`batch=False`, the streaming mode).  Both modes
+    run the same searches on the same inputs and return the same summary."""
 
     def __init__(self, backend, K=TUM1, keyframe_every=10):
         self.b = backend
@@ -142,7 +147,11 @@ class TrackingFrontEnd:
         self.kf_every = keyframe_every
         self.keepalive = []  # arrays referenced by the views handed to the backend (views hold raw addresses)
 
-    def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True):
+    @staticmethod
+    def _chk(m):
+        return int(np.sum((m.astype(np.int64) + 1) * (np.arange(len(m)) + 1)))
+
+    def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True, batch=True):
         n = len(gray)
         if features is None:
             orb = self.b.extract_orb(gray)
@@ -150,10 +159,10 @@ class TrackingFrontEnd:
         else:
             orb, lines = features
         rng = np.random.Generator(np.random.PCG64(424242))
-        self.keepalive = []
+        keep = self.keepalive = []
+        # ---- caller state of every frame (Frame-lite, local-map snapshots) ----
+        frames, maps = [], []
         lm = LocalMap()
-        last = None
-        summary = []
         for t in range(n):
             T = np.array(Tcw[t], np.float64)
             if prior_noise:  # pose prior = ground truth + small noise (stand-in for the motion model)
@@ -161,42 +170,60 @@ class TrackingFrontEnd:
             kps, desc = orb[t]
             kls, ldesc, _ = lines[t]
             F = FrameLite(kps, desc, kls, ldesc, depth[t], T.astype(f32), self.K, scale_factors)
-            rec = dict(frame=t, n_kp=len(kps), n_kl=len(kls))
-            keep = []
-            self.keepalive.append(keep)
-            if last is not None:
-                # --- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ---
-                cur_v = F.view(None, keep)
-                lv = N.make_lastframe_view(last.depth > 0, last.unproject_points(), last.desc, last.kps["octave"], last.kps["angle"],
-                                           (np.arange(len(last.kps)) % 3 != 0), last.Tcw[:3].reshape(-1), keep)
-                m3, n3 = self.b.search_last_frame(cur_v, lv, 15.0)
-                rec.update(c3_matches=n3, c3_sum=int(np.sum((m3.astype(np.int64) + 1) * (np.arange(len(m3)) + 1))))
-                # --- D3: LineMatcher(0.9).SearchByProjection(Cur, Last) (Tracking.cc:1247) ---
-                if len(last.kls) and len(F.kls):
-                    s3, e3, okl = last.unproject_lines()
-                    pk, pidx = self.b.project_lines(s3, e3, last.kls, okl, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size)
-                    ml, nl, rel = self.b.match_lines(pk, last.ldesc[pidx], F.kls, F.ldesc, None)
-                    rec.update(d3_proj=len(pk), d3_matches=nl, d3_relaxed=rel, d3_sum=int(np.sum((ml.astype(np.int64) + 1) * (np.arange(len(ml)) + 1))))
-                claimed = (m3 >= 0).astype(np.int32)
-            else:
-                claimed = None
-            if len(lm.pos):
-                # --- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ---
-                fv = F.view(claimed, keep)
-                inv, u, v, xr, lvl, vc = lm.frustum(F)
-                mv = N.make_mappoint_view(lm.desc, inv, u, v, xr, lvl, vc, None, keep)
-                m2, n2 = self.b.search_local_points(fv, mv, 3.0, 0.8)
-                rec.update(c2_in_view=int(inv.sum()), c2_matches=n2, c2_sum=int(np.sum((m2.astype(np.int64) + 1) * (np.arange(len(m2)) + 1))))
-                # --- D5: LineMatcher(0.8).SearchByProjection(F, localLines) (Tracking.cc:1863) ---
-                if len(lm.lkl) and len(F.kls):
-                    pk, pidx = self.b.project_lines(lm.ls, lm.le, lm.lkl, np.ones(len(lm.lkl), np.uint8), F.Tcw[:3].reshape(-1), self.K,
-                                                    F.bounds, F.size)
-                    ml, nl, rel = self.b.match_lines(pk, lm.ldesc[pidx], F.kls, F.ldesc, None)
-                    rec.update(d5_proj=len(pk), d5_matches=nl, d5_relaxed=rel, d5_sum=int(np.sum((ml.astype(np.int64) + 1) * (np.arange(len(ml)) + 1))))
+            frames.append(F)
+            maps.append((lm.pos, lm.desc, lm.normal, lm.max_d, lm.min_d, lm.ls, lm.le, lm.lkl, lm.ldesc))
             if t % self.kf_every == 0:
                 lm.add_keyframe(F)
-            last = F
-            summary.append(rec)
+        summary = [dict(frame=t, n_kp=len(frames[t].kps), n_kl=len(frames[t].kls)) for t in range(n)]
+        # ---- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ----
+        c3_t = list(range(1, n))
+        cvs = [frames[t].view(None, keep) for t in c3_t]
+        lvs = []
+        for t in c3_t:
+            last = frames[t - 1]
+            lvs.append(N.make_lastframe_view(last.depth > 0, last.unproject_points(), last.desc, last.kps["octave"], last.kps["angle"],
+                                             (np.arange(len(last.kps)) % 3 != 0), last.Tcw[:3].reshape(-1), keep))
+        r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
+        claimed = [None] * n
+        for t, (m3, n3) in zip(c3_t, r3):
+            summary[t].update(c3_matches=n3, c3_sum=self._chk(m3))
+            claimed[t] = (m3 >= 0).astype(np.int32)
+        # ---- D3: LineMatcher(0.9).SearchByProjection(Cur, Last) (Tracking.cc:1247) ----
+        d3_t = [t for t in c3_t if len(frames[t - 1].kls) and len(frames[t].kls)]
+        lcv, llv = [], []
+        for t in d3_t:
+            F, last = frames[t], frames[t - 1]
+            s3, e3, okl = last.unproject_lines()
+            lcv.append(N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep))
+            llv.append(N.make_mapline_view(s3, e3, last.kls, last.ldesc, okl, keep))
+        rd3 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
+        for t, (ml, nl, rel, npj) in zip(d3_t, rd3):
+            summary[t].update(d3_proj=npj, d3_matches=nl, d3_relaxed=rel, d3_sum=self._chk(ml))
+        # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
+        c2_t = [t for t in range(n) if len(maps[t][0])]
+        fvs, mvs, inview = [], [], []
+        tmp = LocalMap()
+        for t in c2_t:
+            F = frames[t]
+            tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[t][:5]
+            inv, u, v, xr, lvl, vc = tmp.frustum(F)
+            fvs.append(F.view(claimed[t], keep))
+            mvs.append(N.make_mappoint_view(tmp.desc, inv, u, v, xr, lvl, vc, None, keep))
+            inview.append(int(inv.sum()))
+        r2 = self.b.search_local_points_batch(fvs, mvs, 3.0, 0.8) if batch else [self.b.search_local_points(f, m, 3.0, 0.8) for f, m in zip(fvs, mvs)]
+        for t, iv, (m2, n2) in zip(c2_t, inview, r2):
+            summary[t].update(c2_in_view=iv, c2_matches=n2, c2_sum=self._chk(m2))
+        # ---- D5: LineMatcher(0.8).SearchByProjection(F, localLines) (Tracking.cc:1863) ----
+        d5_t = [t for t in c2_t if len(maps[t][7]) and len(frames[t].kls)]
+        lcv, llv = [], []
+        for t in d5_t:
+            F = frames[t]
+            ls, le, lkl, ldesc = maps[t][5:9]
+            lcv.append(N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep))
+            llv.append(N.make_mapline_view(ls, le, lkl, ldesc, np.ones(len(lkl), np.uint8), keep))
+        rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
+        for t, (ml, nl, rel, npj) in zip(d5_t, rd5):
+            summary[t].update(d5_proj=npj, d5_matches=nl, d5_relaxed=rel, d5_sum=self._chk(ml))
         return summary
 
 
@@ -231,3 +258,12 @@ class GpuBackend:
 
     def match_lines(self, *a):
         return self.m.match_lines(*a)
+
+    def search_last_frame_batch(self, cvs, lvs, th):
+        return self.m.SearchByProjectionLastFrameBatch(cvs, lvs, th)
+
+    def search_local_points_batch(self, fvs, mvs, th, nn):
+        return self.m.SearchByProjectionLocalPointsBatch(fvs, mvs, th, nn)
+
+    def line_search_batch(self, cvs, lvs):
+        return self.m.SearchLinesByProjectionBatch(cvs, lvs)

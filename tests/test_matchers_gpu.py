@@ -26,13 +26,15 @@ def feats(seq, oracle):
 class Recorder:
     """Wraps a backend and records every matcher call's outputs."""
 
+    NAMES = ("search_last_frame", "search_local_points", "search_last_frame_batch", "search_local_points_batch", "line_search_batch")
+
     def __init__(self, b):
         self.b = b
         self.log = []
 
     def __getattr__(self, k):
         f = getattr(self.b, k)
-        if k in ("search_last_frame", "search_local_points", "project_lines", "match_lines"):
+        if k in self.NAMES:
             def w(*a):
                 r = f(*a)
                 self.log.append((k, r))
@@ -41,32 +43,71 @@ class Recorder:
         return f
 
 
+def _flatten(log):
+    out = []
+    for k, r in log:
+        if k.endswith("_batch"):
+            out += [(k[:-6], x) for x in r]
+        else:
+            out.append((k, r))
+    return out
+
+
 def test_sequence_matchers_bit_exact(seq, feats, api, oracle, pkg):
     fe = importlib.import_module(PKG + ".frontend")
     gray, depth, T = seq
-    gb = Recorder(fe.GpuBackend(api, 480, 640))
     ob = Recorder(oracle.OracleBackend())
     sf = ob.b.scale_factors()
-    sg = fe.TrackingFrontEnd(gb).run(gray, depth, T, sf, features=feats)
-    so = fe.TrackingFrontEnd(ob).run(gray, depth, T, sf, features=feats)
-    assert sg == so
-    assert len(gb.log) == len(ob.log) and len(gb.log) > 30
-    n_matches = 0
-    for (kg, rg), (ko, ro) in zip(gb.log, ob.log):
-        assert kg == ko
-        if kg in ("search_last_frame", "search_local_points"):
-            assert np.array_equal(rg[0], ro[0]) and rg[1] == ro[1], kg
+    so = fe.TrackingFrontEnd(ob).run(gray, depth, T, sf, features=feats, batch=False)
+    ref = _flatten(ob.log)
+    assert len(ref) > 30
+    for batch in (True, False):
+        gb = Recorder(fe.GpuBackend(api, 480, 640))
+        sg = fe.TrackingFrontEnd(gb).run(gray, depth, T, sf, features=feats, batch=batch)
+        assert sg == so, f"batch={batch}"
+        got = _flatten(gb.log)
+        assert len(got) == len(ref)
+        n_matches = 0
+        for (kg, rg), (ko, ro) in zip(got, ref):
+            assert kg == ko
+            assert np.array_equal(rg[0], ro[0]) and tuple(rg[1:]) == tuple(ro[1:]), kg    # every index and count bit-exact
             n_matches += rg[1]
-        elif kg == "match_lines":
-            assert np.array_equal(rg[0], ro[0]) and rg[1:] == ro[1:], kg
-        else:  # project_lines: integer fields exact, float fields to 1e-6 relative (atan2 / sqrt in double on both sides)
-            assert np.array_equal(rg[1], ro[1])
-            for fld in ("sx", "sy", "ex", "ey", "num_pixels", "class_id"):
-                assert np.array_equal(rg[0][fld], ro[0][fld]), fld
-            for fld in ("length", "angle", "response", "size"):
-                assert np.allclose(rg[0][fld], ro[0][fld], rtol=1e-6, atol=1e-6), fld
-    assert n_matches > 1000   # the schedule really matched things
-    assert any(r.get("c2_matches", 0) > 50 for r in sg) and any(r.get("d3_matches", 0) > 5 for r in sg)
+        assert n_matches > 1000   # the schedule really matched things
+    assert any(r.get("c2_matches", 0) > 50 for r in so) and any(r.get("d3_matches", 0) > 5 for r in so)
+    assert any(r.get("d5_matches", 0) > 5 for r in so)
+
+
+def test_batch_with_ragged_and_empty_instances(api, oracle, synth):
+    """Batched searches with instances of different sizes, including empty frames / empty point sets."""
+    N = api.N
+    rng = np.random.default_rng(5)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    K = synth.TUM1
+    keep, fvs, mvs, lvs = [], [], [], []
+    for n, m in [(500, 700), (0, 10), (40, 0), (1200, 3000), (3, 3)]:
+        kp, desc, ur = _rand_frame(rng, n, N)
+        fvs.append(N.make_frame_view(kp, desc, ur, (rng.random(n) < 0.1).astype(np.int32), (0, 0, 640, 480), K,
+                                     np.eye(4, dtype=np.float32)[:3].reshape(-1), sf, keep))
+        src = rng.integers(0, max(n, 1), m)
+        md = (desc[src] if n else rng.integers(0, 256, (m, 32), dtype=np.uint8)).copy()
+        md ^= np.packbits(rng.random((m, 256)) < 0.05, axis=1, bitorder="little")
+        px = (kp["x"][src] if n else np.zeros(m)) + rng.normal(0, 3, m)
+        py = (kp["y"][src] if n else np.zeros(m)) + rng.normal(0, 3, m)
+        lvl = np.clip((kp["octave"][src] if n else np.zeros(m, np.int64)) + rng.integers(0, 2, m), 0, 7)
+        mvs.append(N.make_mappoint_view(md, rng.random(m) < 0.9, px, py, px - 20, lvl, rng.uniform(0.99, 1.0, m), rng.random(m) < 0.5, keep))
+        z = rng.uniform(0.5, 6, m).astype(np.float32)
+        X = np.stack([(px - K["cx"]) * z / K["fx"], (py - K["cy"]) * z / K["fy"], z], 1).astype(np.float32)
+        lvs.append(N.make_lastframe_view(rng.random(m) < 0.95, X, md, lvl, rng.uniform(0, 360, m), rng.random(m) < 0.6,
+                                         np.eye(4, dtype=np.float32)[:3].reshape(-1), keep))
+    m = api.DescriptorMatcher()
+    g2 = m.SearchByProjectionLocalPointsBatch(fvs, mvs, 3.0, 0.8)
+    g3 = m.SearchByProjectionLastFrameBatch(fvs, lvs, 15.0)
+    for i in range(len(fvs)):
+        o2 = oracle.search_local_points(fvs[i], mvs[i], 3.0, 0.8)
+        o3 = oracle.search_last_frame(fvs[i], lvs[i], 15.0)
+        assert np.array_equal(g2[i][0], o2[0]) and g2[i][1] == o2[1], i
+        assert np.array_equal(g3[i][0], o3[0]) and g3[i][1] == o3[1], i
+    assert g2[3][1] > 100 and g3[3][1] > 100
 
 
 def _rand_frame(rng, n, N):
