@@ -164,9 +164,10 @@ PL_API int pl_line_last_launches(const pl_line* h);
 /* Measurement hooks: stages {0 blur+scale+gradient, 1 seed sort, 2 region growing/NFA, 3 KeyLines+blur5+Sobel, 4 LBD} */
 PL_API int pl_line_set_profiling(pl_line* h, int on);
 PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
-/* with profiling on: SM cycles that frame `frame` of the last chunk spent in {0 seed scan, 1 region growing, 2 rectangle
- * fit, 3 refine, 4 NFA}, then {5 regions tried, 6 regions that reached the minimum size} */
-PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out7);
+/* with profiling on, 8 values of frame `frame` of the last chunk from k_lsd_grow's own clock64 accounting:
+ * {0 cycles selecting seeds, 1 total cycles of the grower loop, 2 cycles validating/committing, 3 rounds,
+ *  4 busy cycles of one NFA warp, 5 regions committed, 6 regions grown exclusively, 7 speculative growths discarded} */
+PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out8);
 /* Test hooks: the 0.8-scaled 8-bit image LSD works on, its level-line angle map (float degrees, -1024 = undefined,
  * rows x cols of the scaled image) and the float LBD descriptors (n x 72) of frame `frame` of the last call. */
 PL_API int pl_line_scaled_dims(const pl_line* h, int* rows, int* cols);

@@ -108,9 +108,10 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineGeom g, const uint8_t* __
 // ---------------------------------------------------------------------------------------------------------------
 // k_lsd_grad: ll_angle() — gradient with a 2x2 mask, level-line angle, squared modulus, per-frame max
 // ---------------------------------------------------------------------------------------------------------------
+// also stores cosf/sinf of the angle (what region_grow adds to its running sums), so the ordered grower only loads them
 __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __restrict__ scaled, size_t scaled_frame_stride,
-                                                  float* __restrict__ angdeg, int* __restrict__ g2, size_t plane, double rho,
-                                                  int* __restrict__ max_g2) {
+                                                  float* __restrict__ angdeg, int* __restrict__ g2, float2* __restrict__ cs, size_t plane,
+                                                  double rho, int* __restrict__ max_g2) {
     const int f = blockIdx.z;
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     int my = -1;
@@ -127,6 +128,9 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __r
             if (norm > rho) {
                 a = fast_atan2_deg((float)gx, (float)(-gy));
                 my = q;
+                // cos(float(angle)) / sin(float(angle)) of the reference's region_grow resolve to cosf / sinf
+                const float af = (float)((double)a * kDegToRad);
+                cs[(size_t)f * plane + (size_t)y * g.W + x] = make_float2(glibc_sincosf(af, 1), glibc_sincosf(af, 0));
             }
         }
         angdeg[(size_t)f * plane + (size_t)y * g.W + x] = a;
@@ -264,15 +268,34 @@ struct LsdSeg {  // one detected segment, in detection order (== cv::LineSegment
 struct LsdRect {
     double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
 };
-constexpr int kRegRing = 2048;  // most recent region points kept in shared memory (the BFS frontier reads them)
-struct LsdFrame {  // per-frame device views
+constexpr int kRegRing = 512;    // most recent region points kept in shared memory (the BFS frontier reads them)
+constexpr int kSpecCap = 16384;  // region / touched-list capacity of a speculative grower (larger regions run exclusively)
+struct LsdFrame {  // per-frame (and per-grower) device views
     const float* ang;   // level-line angle in degrees or kNotDefDeg
     const int* g2;      // gx^2 + gy^2
-    uint8_t* used;
+    const float2* cs;   // (cosf, sinf) of the angle
+    uint8_t* used;      // the committed USED map
     unsigned int* reg;  // region points, packed y<<16 | x
     unsigned int* ring; // shared-memory copy of reg[n - kRegRing .. n)
     int W, H;
+    // speculative growing: pixels this grower marks go to a private bitmap, every accepted pixel is logged
+    bool spec;
+    unsigned int* bits;     // private USED bitmap (W*H bits)
+    unsigned int* touched;  // log of accepted pixels (packed), capacity reg_cap
+    int reg_cap;            // capacity of reg / touched
 };
+__device__ __forceinline__ bool lsd_is_used(const LsdFrame& F, size_t o) {
+    if (F.used[o] != 0) return true;
+    return F.spec && ((F.bits[o >> 5] >> (o & 31)) & 1u);
+}
+__device__ __forceinline__ void lsd_mark(const LsdFrame& F, size_t o) {
+    if (F.spec) atomicOr(&F.bits[o >> 5], 1u << (o & 31));
+    else F.used[o] = 1;
+}
+__device__ __forceinline__ void lsd_unmark(const LsdFrame& F, size_t o) {
+    if (F.spec) atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
+    else F.used[o] = 0;
+}
 
 __device__ __forceinline__ double lsd_angle_diff_signed(double a, double b) {
     double diff = a - b;
@@ -297,17 +320,21 @@ __device__ __forceinline__ double lsd_dist_sq(double x1, double y1, double x2, d
 // region_grow(): returns the region size; reg_angle (radians) is returned through *out_angle.
 // Lanes 0..26 hold the 3x3 neighbourhoods of up to three consecutive region points, in the reference's visiting
 // order (point, then row, then column); acceptances are resolved in that order with the running region angle.
-__device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, double* out_angle) {
+// `nt` counts the entries of the touched log (speculative mode); returns -1 when a capacity is exceeded.
+__device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, double* out_angle, int& nt) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     double reg_angle = (double)F.ang[(size_t)sy * F.W + sx] * kDegToRad;
     // float(std::cos(reg_angle)) — double cosine of the seed angle, rounded to float
     float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+    if (F.spec && nt >= F.reg_cap) return -1;
     if (lane == 0) {
         F.reg[0] = ((unsigned)sy << 16) | (unsigned)sx;
         F.ring[0] = ((unsigned)sy << 16) | (unsigned)sx;
-        F.used[(size_t)sy * F.W + sx] = 1;
+        lsd_mark(F, (size_t)sy * F.W + sx);
+        if (F.spec) F.touched[nt] = ((unsigned)sy << 16) | (unsigned)sx;
     }
+    nt++;
     __syncwarp();
     int n = 1, i = 0;
     const int b = lane / 9, k = lane - b * 9;
@@ -326,14 +353,14 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
             if (xx >= 0 && yy >= 0 && xx < F.W && yy < F.H) {
                 const size_t o = (size_t)yy * F.W + xx;
                 adeg = F.ang[o];
-                cand = F.used[o] == 0 && adeg != kNotDefDeg;
+                cand = adeg != kNotDefDeg && !lsd_is_used(F, o);
             }
         }
         if (cand) {
             arad = (double)adeg * kDegToRad;
-            const float af = (float)arad;  // cos(float(angle)) / sin(float(angle)) of the reference resolve to cosf / sinf
-            ca = glibc_sincosf(af, 1);
-            sa = glibc_sincosf(af, 0);
+            const float2 c2 = F.cs[(size_t)yy * F.W + xx];
+            ca = c2.x;
+            sa = c2.y;
         }
         unsigned mask = __ballot_sync(FULL, cand);
         while (mask) {
@@ -344,12 +371,15 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
             // accept lane j's pixel
             const int ax = __shfl_sync(FULL, xx, j), ay = __shfl_sync(FULL, yy, j);
             const float cj = __shfl_sync(FULL, ca, j), sj = __shfl_sync(FULL, sa, j);
+            if (n >= F.reg_cap || (F.spec && nt >= F.reg_cap)) return -1;
             if (lane == j) {
                 F.reg[n] = ((unsigned)ay << 16) | (unsigned)ax;
                 F.ring[n & (kRegRing - 1)] = ((unsigned)ay << 16) | (unsigned)ax;
-                F.used[(size_t)ay * F.W + ax] = 1;
+                lsd_mark(F, (size_t)ay * F.W + ax);
+                if (F.spec) F.touched[nt] = ((unsigned)ay << 16) | (unsigned)ax;
             }
             n++;
+            nt++;
             sumdx = __fadd_rn(sumdx, cj);
             sumdy = __fadd_rn(sumdy, sj);
             reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
@@ -465,7 +495,7 @@ __device__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n, double reg_a
                 const unsigned q = F.reg[i];
                 const int qx = (int)(q & 0xffffu), qy = (int)(q >> 16);
                 if (lsd_dist_sq(xc, yc, (double)qx, (double)qy) > radSq) {
-                    F.used[(size_t)qy * F.W + qx] = 0;
+                    lsd_unmark(F, (size_t)qy * F.W + qx);
                     F.reg[i] = F.reg[m - 1];
                     F.reg[m - 1] = q;
                     --m;
@@ -484,11 +514,12 @@ __device__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n, double reg_a
 }
 
 // refine()
-__device__ bool lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double prec, double p, LsdRect& rec, double density_th) {
+// returns 1 = refined, 0 = rejected, -1 = capacity exceeded (speculative growers)
+__device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double prec, double p, LsdRect& rec, double density_th, int& nt) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     double density = lsd_density(n, rec);
-    if (density >= density_th) return true;
+    if (density >= density_th) return 1;
     const unsigned p0 = F.reg[0];
     const int sx = (int)(p0 & 0xffffu), sy = (int)(p0 >> 16);
     const double xc = (double)sx, yc = (double)sy;
@@ -497,7 +528,7 @@ __device__ bool lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double 
     int cnt_in = 0;
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);
-        if (base + lane < n) F.used[(size_t)(int)pt.y * F.W + (int)pt.x] = 0;
+        if (base + lane < n) lsd_unmark(F, (size_t)(int)pt.y * F.W + (int)pt.x);
         const int cnt = min(32, n - base);
         for (int j = 0; j < cnt; j++) {
             const double px = __shfl_sync(FULL, pt.x, j), py = __shfl_sync(FULL, pt.y, j);
@@ -514,12 +545,13 @@ __device__ bool lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double 
     const double mean_angle = sum / (double)cnt_in;
     const double tau = 2.0 * sqrt(__dadd_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)) / (double)cnt_in,
                                             __dmul_rn(mean_angle, mean_angle)));
-    n = lsd_region_grow(F, sx, sy, tau, &reg_angle);
-    if (n < 2) return false;
+    n = lsd_region_grow(F, sx, sy, tau, &reg_angle, nt);
+    if (n < 0) return -1;
+    if (n < 2) return 0;
     lsd_region2rect(F, n, reg_angle, prec, p, rec);
     density = lsd_density(n, rec);
-    if (density < density_th) return lsd_reduce_region_radius(F, n, reg_angle, prec, p, rec, density, density_th);
-    return true;
+    if (density < density_th) return lsd_reduce_region_radius(F, n, reg_angle, prec, p, rec, density, density_th) ? 1 : 0;
+    return 1;
 }
 
 // ---- NFA ----
@@ -775,150 +807,241 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
     return log_nfa;
 }
 
-// flsd() main loop.  CTA = 4 warps per frame: warp 0 walks the seeds in order and does everything that touches the
-// USED map (region growing, rectangle fit, refine); the NFA validation of a fitted rectangle (rect_improve) only
-// reads the angle map and does not influence later regions, so it is handed to warps 1..3 through a queue and the
-// accepted segments are compacted in seed order at the end.
-constexpr int kGrowThreads = 128;
+// flsd() main loop.  One CTA per frame: kGrowers warps grow regions, kNfaWarps warps validate fitted rectangles.
+//
+// Region growing is ordered (seeds by gradient bin, shared USED map), but regions that do not touch the same pixels
+// commute.  Each round the next kGrowers unused seeds (in order) are grown SPECULATIVELY and concurrently, one warp
+// each: a grower reads the committed USED map, keeps the pixels it marks in a private bitmap and logs every pixel it
+// ever accepts (initial growth and the refine re-growth).  Warp 0 then validates the round in seed order against
+// the committed map:  seed already committed -> the seed was swallowed by an earlier region, skip it;  any logged
+// pixel already committed -> the region depended on an earlier region of this round, stop the round there and redo it
+// from that seed;  otherwise the region's execution is exactly what the sequential algorithm would have done ->
+// commit its final pixel set and hand its rectangle to the NFA queue.  Regions larger than the speculative
+// capacity are grown exclusively by warp 0 on the committed map.  rect_improve only reads the angle map and does
+// not influence later regions, so it runs asynchronously in the NFA warps; accepted segments are compacted in seed
+// order at the end.
+constexpr int kGrowers = 8;
+constexpr int kGrowThreads = kGrowers * 32;
 struct LsdQueueItem { LsdRect rec; };
+struct SpecSlot {
+    int seed_pos, seed_pix;
+    int status;  // 1: rectangle fitted, 0: region kept but no rectangle, -1: capacity exceeded -> exclusive
+    int n, nt;
+    LsdRect rec;
+};
+__device__ __forceinline__ void grower_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(kGrowers * 32) : "memory"); }
 
 __global__ void __launch_bounds__(kGrowThreads) k_lsd_grow(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
                                                            uint8_t* __restrict__ used, unsigned int* __restrict__ reg,
+                                                           unsigned int* __restrict__ spec_reg, unsigned int* __restrict__ spec_touched,
+                                                           unsigned int* __restrict__ spec_bits, int bits_words,
                                                            const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
-                                                           size_t plane, LsdQueueItem* __restrict__ queue, LsdSeg* __restrict__ qres,
-                                                           uint8_t* __restrict__ qvalid, LsdSeg* __restrict__ segs,
-                                                           int* __restrict__ n_segs, int* __restrict__ flags, NfaTabs T,
-                                                           long long* __restrict__ phase_cycles) {
-    __shared__ unsigned int s_ring[kRegRing];
-    __shared__ volatile int s_head, s_done;
-    __shared__ int s_ticket;
+                                                           const float2* __restrict__ cs, size_t plane,
+                                                           LsdQueueItem* __restrict__ queue, int* __restrict__ n_rects,
+                                                           int* __restrict__ flags, long long* __restrict__ phase_cycles) {
+    __shared__ unsigned int s_ring[kGrowers][kRegRing];
+    __shared__ SpecSlot s_slot[kGrowers];
+    __shared__ int s_nsel, s_finished;
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     LsdFrame F;
     F.ang = angdeg + (size_t)f * plane;
     F.g2 = g2 + (size_t)f * plane;
+    F.cs = cs + (size_t)f * plane;
     F.used = used + (size_t)f * plane;
-    F.reg = reg + (size_t)f * plane;
-    F.ring = s_ring;
     F.W = g.W;
     F.H = g.H;
     LsdQueueItem* q = queue + (size_t)f * g.seg_cap;
-    LsdSeg* qr = qres + (size_t)f * g.seg_cap;
-    uint8_t* qv = qvalid + (size_t)f * g.seg_cap;
-    const double log_eps = 0.0;
-    if (threadIdx.x == 0) { s_head = 0; s_done = 0; s_ticket = 0; }
+    if (threadIdx.x == 0) { s_finished = 0; s_nsel = 0; }
     __syncthreads();
-    long long cyc[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (warp == 0) {
-        // ------------------------------ producer: ordered region growing ------------------------------
-        const unsigned int* sd = seeds + (size_t)f * plane;
-        const int ns = n_seeds[f];
+    long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    {
+        // ------------------------------ growers ------------------------------
         const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
         const double density_th = 0.7;
-        int head = 0, pos = 0;
-        long long t0 = clock64();
-#define PL_PHASE(k)                       \
-    do {                                  \
-        const long long t1 = clock64();   \
-        cyc[k] += t1 - t0;                \
-        t0 = t1;                          \
-    } while (0)
-        while (pos < ns) {
-            // next unused seed at or after pos (32 candidates per probe)
-            const int idx = pos + lane;
-            unsigned pix = 0;
-            bool free_ = false;
-            if (idx < ns) {
-                pix = sd[idx];
-                free_ = F.used[pix] == 0;
-            }
-            const unsigned m = __ballot_sync(FULL, free_);
-            if (!m) { pos += 32; continue; }
-            const int j = __ffs(m) - 1;
-            pix = __shfl_sync(FULL, pix, j);
-            pos += j + 1;
-            const int sx = (int)(pix % (unsigned)g.W), sy = (int)(pix / (unsigned)g.W);
-            double reg_angle;
-            PL_PHASE(0);
-            int n = lsd_region_grow(F, sx, sy, prec, &reg_angle);
-            PL_PHASE(1);
-            cyc[5]++;
-            if (n < g.min_reg_size) continue;
-            cyc[6]++;
-            LsdRect rec;
-            lsd_region2rect(F, n, reg_angle, prec, p, rec);
-            PL_PHASE(2);
-            const bool refined = lsd_refine(F, n, reg_angle, prec, p, rec, density_th);
-            PL_PHASE(3);
-            if (!refined) continue;
+        const size_t gslot = (size_t)f * kGrowers + warp;
+        F.spec = true;
+        F.reg = spec_reg + gslot * kSpecCap;
+        F.touched = spec_touched + gslot * kSpecCap;
+        F.bits = spec_bits + gslot * bits_words;
+        F.reg_cap = kSpecCap;
+        F.ring = s_ring[warp];
+        LsdFrame FX = F;  // exclusive view (warp 0): the committed map itself, the frame-sized region buffer
+        FX.spec = false;
+        FX.reg = reg + (size_t)f * plane;
+        FX.reg_cap = (int)plane;
+        const unsigned int* sd = seeds + (size_t)f * plane;
+        const int ns = n_seeds[f];
+        int pos = 0, head = 0;  // warp 0 only
+        bool exclusive = false;
+        const long long tstart = clock64();
+        auto push_rect = [&](const LsdRect& rec) {
             if (head < g.seg_cap) {
                 if (lane == 0) q[head].rec = rec;
-                __syncwarp();
-                __threadfence_block();
                 head++;
-                if (lane == 0) s_head = head;
             } else if (lane == 0) {
                 atomicOr(flags + f, 1);
             }
-        }
-        PL_PHASE(0);
-#undef PL_PHASE
-        __threadfence_block();
-        if (lane == 0) s_done = 1;
-    } else {
-        // ------------------------------ consumers: NFA validation ------------------------------
-        const long long c0 = clock64();
-        long long busy = 0;
+        };
         while (true) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&s_ticket, 1);
-            t = __shfl_sync(FULL, t, 0);
-            int go = 0;
-            if (lane == 0) {
-                while (true) {
-                    if (t < s_head) { go = 1; break; }
-                    if (s_done) { go = (t < s_head) ? 1 : 0; break; }
-                    __nanosleep(256);
+            if (warp == 0) {
+                long long t0 = clock64();
+                if (exclusive) {  // the seed at `pos` needs more than the speculative capacity: sequential path
+                    exclusive = false;
+                    const unsigned pix = sd[pos];
+                    pos++;
+                    const int sx = (int)(pix % (unsigned)g.W), sy = (int)(pix / (unsigned)g.W);
+                    double reg_angle;
+                    int nt = 0;
+                    int n = lsd_region_grow(FX, sx, sy, prec, &reg_angle, nt);
+                    if (n < 0) {
+                        if (lane == 0) atomicOr(flags + f, 2);
+                    } else if (n >= g.min_reg_size) {
+                        LsdRect rec;
+                        lsd_region2rect(FX, n, reg_angle, prec, p, rec);
+                        const int r = lsd_refine(FX, n, reg_angle, prec, p, rec, density_th, nt);
+                        if (r == 1) push_rect(rec);
+                        else if (r < 0 && lane == 0) atomicOr(flags + f, 2);
+                    }
+                    cyc[6]++;
+                }
+                // select the next unused seeds, in order
+                int nsel = 0;
+                while (pos < ns && nsel < kGrowers) {
+                    const int idx = pos + lane;
+                    unsigned pix = 0;
+                    bool free_ = false;
+                    if (idx < ns) {
+                        pix = sd[idx];
+                        free_ = F.used[pix] == 0;
+                    }
+                    unsigned m = __ballot_sync(FULL, free_);
+                    if (!m) { pos += 32; continue; }
+                    int last = -1;
+                    while (m && nsel < kGrowers) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const unsigned pj = __shfl_sync(FULL, pix, j);
+                        if (lane == 0) { s_slot[nsel].seed_pos = pos + j; s_slot[nsel].seed_pix = (int)pj; }
+                        nsel++;
+                        last = j;
+                    }
+                    pos += (m && nsel >= kGrowers) ? last + 1 : 32;
+                    if (pos > ns) pos = ns;
+                }
+                if (lane == 0) { s_nsel = nsel; if (nsel == 0) s_finished = 1; }
+                cyc[0] += clock64() - t0;
+            }
+            grower_barrier();
+            if (s_finished) break;
+            const int nsel = s_nsel;
+            // ---- speculative growth ----
+            if (warp < nsel) {
+                const int pix = s_slot[warp].seed_pix;
+                const int sx = pix % g.W, sy = pix / g.W;
+                double reg_angle;
+                int nt = 0, status = 0;
+                LsdRect rec;
+                int n = lsd_region_grow(F, sx, sy, prec, &reg_angle, nt);
+                if (n < 0) {
+                    status = -1;
+                } else if (n >= g.min_reg_size) {
+                    lsd_region2rect(F, n, reg_angle, prec, p, rec);
+                    const int r = lsd_refine(F, n, reg_angle, prec, p, rec, density_th, nt);
+                    status = r;
+                }
+                if (lane == 0) {
+                    s_slot[warp].status = status;
+                    s_slot[warp].n = n;
+                    s_slot[warp].nt = nt;
+                    if (status == 1) s_slot[warp].rec = rec;
+                }
+                __threadfence_block();
+            }
+            grower_barrier();
+            // ---- in-order validation and commit (warp 0); the others clear their private bitmaps meanwhile ----
+            if (warp == 0) {
+                long long t0 = clock64();
+                int stop_at = -1;
+                for (int k = 0; k < nsel; k++) {
+                    const SpecSlot& sl = s_slot[k];
+                    if (F.used[sl.seed_pix] != 0) { cyc[7]++; continue; }  // swallowed by an earlier region of this round
+                    if (sl.status < 0) { stop_at = k; exclusive = true; break; }
+                    const unsigned int* tk = spec_touched + ((size_t)f * kGrowers + k) * kSpecCap;
+                    bool conflict = false;
+                    for (int i = lane; i < sl.nt; i += 32) {
+                        const unsigned pp = tk[i];
+                        conflict |= F.used[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] != 0;
+                    }
+                    if (__any_sync(FULL, conflict)) { stop_at = k; cyc[7]++; break; }
+                    const unsigned int* rk = spec_reg + ((size_t)f * kGrowers + k) * kSpecCap;
+                    for (int i = lane; i < sl.n; i += 32) {
+                        const unsigned pp = rk[i];
+                        F.used[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] = 1;
+                    }
+                    __syncwarp();
+                    cyc[5]++;
+                    if (sl.status == 1) {
+                        LsdRect rec = sl.rec;
+                        push_rect(rec);
+                    }
+                }
+                if (stop_at >= 0) {
+                    for (int k = stop_at + (exclusive ? 1 : 0); k < nsel; k++) cyc[7] += 0;
+                    pos = s_slot[stop_at].seed_pos;
+                }
+                cyc[2] += clock64() - t0;
+                cyc[3]++;
+            }
+            if (warp < nsel) {
+                const int nt = s_slot[warp].nt;
+                for (int i = lane; i < nt; i += 32) {
+                    const unsigned pp = F.touched[i];
+                    const size_t o = (size_t)(pp >> 16) * g.W + (pp & 0xffffu);
+                    atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
                 }
             }
-            go = __shfl_sync(FULL, go, 0);
-            if (!go) break;
-            __threadfence_block();
-            const long long b0 = clock64();
-            LsdRect rec = q[t].rec;
-            const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
+        }
+        if (warp == 0) {
+            cyc[1] = clock64() - tstart;
             if (lane == 0) {
-                LsdSeg sg;
-                sg.x1 = (float)((rec.x1 + 0.5) / 0.8); sg.y1 = (float)((rec.y1 + 0.5) / 0.8);
-                sg.x2 = (float)((rec.x2 + 0.5) / 0.8); sg.y2 = (float)((rec.y2 + 0.5) / 0.8);
-                sg.width = rec.width / 0.8;
-                sg.p = rec.p;
-                sg.nfa = log_nfa;
-                qr[t] = sg;
-                qv[t] = log_nfa > log_eps;
+                n_rects[f] = head;
+                if (phase_cycles)
+                    for (int k = 0; k < 8; k++) phase_cycles[(size_t)f * 8 + k] = cyc[k];
             }
-            busy += clock64() - b0;
         }
-        if (warp == 1) { cyc[4] = busy; (void)c0; }
     }
-    __syncthreads();
-    // ------------------------------ ordered compaction of the accepted segments ------------------------------
-    const int total = s_head;
-    if (warp == 0) {
-        LsdSeg* out = segs + (size_t)f * g.seg_cap;
-        int cnt = 0;
-        for (int base = 0; base < total; base += 32) {
-            const bool v = (base + lane < total) && qv[base + lane];
-            const unsigned m = __ballot_sync(FULL, v);
-            if (v) out[cnt + __popc(m & ((1u << lane) - 1u))] = qr[base + lane];
-            cnt += __popc(m);
+}
+
+// NFA validation of the fitted rectangles (rect_improve): it only reads the angle map and does not influence any
+// other region, so every rectangle of every frame is independent — one warp per rectangle, grid-strided.
+constexpr int kNfaBlocksPerFrame = 32, kNfaThreads = 256;
+__global__ void __launch_bounds__(kNfaThreads) k_lsd_nfa(LineGeom g, const float* __restrict__ angdeg, size_t plane,
+                                                         const LsdQueueItem* __restrict__ queue, const int* __restrict__ n_rects,
+                                                         LsdSeg* __restrict__ qres, uint8_t* __restrict__ qvalid, NfaTabs T) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * (kNfaThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kNfaThreads / 32);
+    LsdFrame F;
+    F.ang = angdeg + (size_t)f * plane;
+    F.g2 = nullptr; F.cs = nullptr; F.used = nullptr; F.reg = nullptr; F.ring = nullptr;
+    F.W = g.W; F.H = g.H;
+    F.spec = false; F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0;
+    const int n = min(n_rects[f], g.seg_cap);
+    const double log_eps = 0.0;
+    for (int t = wid; t < n; t += nw) {
+        LsdRect rec = queue[(size_t)f * g.seg_cap + t].rec;
+        const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
+        if (lane == 0) {
+            LsdSeg sg;
+            sg.x1 = (float)((rec.x1 + 0.5) / 0.8); sg.y1 = (float)((rec.y1 + 0.5) / 0.8);
+            sg.x2 = (float)((rec.x2 + 0.5) / 0.8); sg.y2 = (float)((rec.y2 + 0.5) / 0.8);
+            sg.width = rec.width / 0.8;
+            sg.p = rec.p;
+            sg.nfa = log_nfa;
+            qres[(size_t)f * g.seg_cap + t] = sg;
+            qvalid[(size_t)f * g.seg_cap + t] = log_nfa > log_eps;
         }
-        if (lane == 0) n_segs[f] = cnt;
-        if (phase_cycles && lane == 0)
-            for (int k = 0; k < 7; k++)
-                if (k != 4) phase_cycles[(size_t)f * 8 + k] = cyc[k];
     }
-    if (warp == 1 && phase_cycles && lane == 0) phase_cycles[(size_t)f * 8 + 4] = cyc[4];
 }
 
 }  // namespace pl
@@ -960,14 +1083,31 @@ __device__ __forceinline__ pl_keyline make_keyline(const LsdSeg& s, int cols, in
 // ordered by response descending; otherwise keep detection order.  One CTA per frame.
 constexpr int kFinThreads = 256;
 constexpr int kMaxKeep = 512;
-__global__ void __launch_bounds__(kFinThreads) k_line_finalize(LineGeom g, const LsdSeg* __restrict__ segs, const int* __restrict__ n_segs,
-                                                               float* __restrict__ resp_scratch, pl_keyline* __restrict__ kls,
-                                                               int* __restrict__ n_out, int cap) {
+__global__ void __launch_bounds__(kFinThreads) k_line_finalize(LineGeom g, const LsdSeg* __restrict__ qres, const uint8_t* __restrict__ qvalid,
+                                                               const int* __restrict__ n_rects, LsdSeg* __restrict__ segs,
+                                                               int* __restrict__ n_segs, float* __restrict__ resp_scratch,
+                                                               pl_keyline* __restrict__ kls, int* __restrict__ n_out, int cap) {
     __shared__ int s_hist[4096];
     __shared__ unsigned long long s_key[kMaxKeep];
-    __shared__ int s_sel, s_need, s_bin;
+    __shared__ int s_sel, s_need, s_bin, s_nseg;
     const int f = blockIdx.x, tid = threadIdx.x;
-    const int n = n_segs[f];
+    // accepted segments (NFA > 0) compacted in seed order == cv::LineSegmentDetector::detect output order
+    if (tid < 32) {
+        const int total = min(n_rects[f], g.seg_cap);
+        const LsdSeg* qr = qres + (size_t)f * g.seg_cap;
+        const uint8_t* qv = qvalid + (size_t)f * g.seg_cap;
+        LsdSeg* o = segs + (size_t)f * g.seg_cap;
+        int cnt = 0;
+        for (int base = 0; base < total; base += 32) {
+            const bool v = (base + tid < total) && qv[base + tid];
+            const unsigned m = __ballot_sync(0xffffffffu, v);
+            if (v) o[cnt + __popc(m & ((1u << tid) - 1u))] = qr[base + tid];
+            cnt += __popc(m);
+        }
+        if (tid == 0) { n_segs[f] = cnt; s_nseg = cnt; }
+    }
+    __syncthreads();
+    const int n = s_nseg;
     const LsdSeg* sg = segs + (size_t)f * g.seg_cap;
     pl_keyline* out = kls + (size_t)f * cap;
     const int keep = min(g.max_lines, cap);
@@ -1273,6 +1413,8 @@ struct pl_line {
     // device buffers (sized for max_cols x max_rows x max_batch at creation)
     uint8_t *d_in = nullptr, *d_scaled = nullptr, *d_used = nullptr, *d_blur5 = nullptr;
     float* d_ang = nullptr;
+    float2* d_cs = nullptr;
+    int* d_nrects = nullptr;
     int* d_g2 = nullptr;
     unsigned int *d_reg = nullptr, *d_seeds = nullptr;
     int *d_maxg2 = nullptr, *d_tile_off = nullptr, *d_nseeds = nullptr, *d_nsegs = nullptr, *d_flags = nullptr, *d_nout = nullptr;
@@ -1281,6 +1423,8 @@ struct pl_line {
     LsdSeg* d_qres = nullptr;
     LsdQueueItem* d_queue = nullptr;
     uint8_t* d_qvalid = nullptr;
+    unsigned int *d_spec_reg = nullptr, *d_spec_touched = nullptr, *d_spec_bits = nullptr;
+    int bits_words_alloc = 0;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
     short *d_dx = nullptr, *d_dy = nullptr;
     ExactTab *d_xtab = nullptr, *d_ytab = nullptr;
@@ -1396,7 +1540,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     {
         const double rho = 2.0 / sin(kPiD * 22.5 / 180);
         dim3 grid((G.W + 63) / 64, (G.H + 3) / 4, nf);
-        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, plane, rho, h->d_maxg2);
+        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, h->d_cs, plane, rho, h->d_maxg2);
         launches++;
     }
     if (prof) cudaEventRecord(h->ev[1], st);
@@ -1405,11 +1549,15 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     k_lsd_scatter<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_off, h->d_seeds);
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
-    k_lsd_grow<<<nf, kGrowThreads, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_seeds, h->d_nseeds, plane, h->d_queue, h->d_qres,
-                                            h->d_qvalid, h->d_segs, h->d_nsegs, h->d_flags, h->nfa_tabs, prof ? h->d_phase : nullptr);
-    launches++;
+    const int bits_words = (int)((plane + 31) / 32);
+    PL_CUDA_TRY(cudaMemsetAsync(h->d_spec_bits, 0, sizeof(unsigned int) * (size_t)nf * kGrowers * bits_words, st));
+    k_lsd_grow<<<nf, kGrowThreads, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_spec_reg, h->d_spec_touched, h->d_spec_bits, bits_words,
+                                            h->d_seeds, h->d_nseeds, h->d_cs, plane, h->d_queue, h->d_nrects, h->d_flags,
+                                            prof ? h->d_phase : nullptr);
+    k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
+    launches += 2;
     if (prof) cudaEventRecord(h->ev[3], st);
-    k_line_finalize<<<nf, kFinThreads, 0, st>>>(G, h->d_segs, h->d_nsegs, h->d_resp, d_kls, d_nout, cap);
+    k_line_finalize<<<nf, kFinThreads, 0, st>>>(G, h->d_qres, h->d_qvalid, h->d_nrects, h->d_segs, h->d_nsegs, h->d_resp, d_kls, d_nout, cap);
     launches++;
     {
         dim3 grid((G.cols + 63) / 64, (G.rows + 31) / 32, nf);
@@ -1444,7 +1592,7 @@ int line_check_flags(pl_line* h, int nf) {
     PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < nf; i++)
         if (h->h_flags[i]) {
-            set_error("frame %d of the chunk exceeded the LSD segment capacity", i);
+            set_error("frame %d of the chunk exceeded an LSD capacity (flags=%d: 1=segments, 2=region size)", i, h->h_flags[i]);
             return PL_ERR_CAPACITY;
         }
     return PL_OK;
@@ -1490,6 +1638,8 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_scaled, B * align_up((size_t)W, 16) * H);
     A(&h->d_used, B * plane);
     A(&h->d_ang, B * plane);
+    A(&h->d_cs, B * plane);
+    A(&h->d_nrects, B);
     A(&h->d_g2, B * plane);
     A(&h->d_reg, B * plane);
     A(&h->d_seeds, B * plane);
@@ -1504,6 +1654,10 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_qres, B * seg_cap);
     A(&h->d_queue, B * seg_cap);
     A(&h->d_qvalid, B * seg_cap);
+    h->bits_words_alloc = (int)((plane + 31) / 32);
+    A(&h->d_spec_reg, B * kGrowers * (size_t)kSpecCap);
+    A(&h->d_spec_touched, B * kGrowers * (size_t)kSpecCap);
+    A(&h->d_spec_bits, B * kGrowers * (size_t)h->bits_words_alloc);
     A(&h->d_resp, B * seg_cap);
     A(&h->d_dx, B * align_up((size_t)max_cols, 8) * max_rows);
     A(&h->d_dy, B * align_up((size_t)max_cols, 8) * max_rows);
@@ -1559,7 +1713,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_used, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_spec_bits, h->d_cs, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -1689,8 +1843,9 @@ PL_API int pl_line_lsd_read(pl_line* h, int frame, float* xyxy, double* width, d
  * the number of regions tried / regions that reached the minimum size (k_lsd_grow's own clock64 accounting) */
 PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out7) {
     PL_CHECK_ARG(h && out7 && frame >= 0 && frame < h->last_batch);
+    // out7 receives 8 values, see plslam_c.h
     PL_CUDA_TRY(cudaSetDevice(h->device));
-    PL_CUDA_TRY(cudaMemcpyAsync(out7, h->d_phase + (size_t)frame * 8, sizeof(long long) * 7, cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaMemcpyAsync(out7, h->d_phase + (size_t)frame * 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PL_OK;
 }

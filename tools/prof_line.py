@@ -58,7 +58,7 @@ names = ["scale+grad", "seed_sort", "grow+nfa", "keylines+sobel", "lbd"]
 for i in range(5):
     print(f"  {names[i]:15s} {out[i]*1000/(a.frames*a.iters):9.2f} us/frame  ({out[i]/a.iters:.3f} ms per pass)")
 print("lines/frame", float(d_n.float().mean().item()), "launches", ex.last_launches())
-ph = np.zeros(7, np.int64)
+ph = np.zeros(8, np.int64)
 N.check(N.lib().pl_line_grow_phases(ex._h, C.c_int(0), N.ptr(ph)))
-tot = ph[:5].sum()
-print("grow kernel phases (frame 0, Mcycles): " + ", ".join(f"{n}={v/1e6:.1f}" for n, v in zip(["seed_scan", "grow", "rect", "refine", "nfa"], ph[:5])) + f"; regions tried {ph[5]}, >=min size {ph[6]}")
+print(f"grow kernel (frame 0): total {ph[1]/1e6:.1f} Mcycles, select {ph[0]/1e6:.1f}, validate {ph[2]/1e6:.1f}, rounds {ph[3]}, "
+      f"nfa-warp busy {ph[4]/1e6:.1f}, committed {ph[5]}, exclusive {ph[6]}, discarded {ph[7]}")
