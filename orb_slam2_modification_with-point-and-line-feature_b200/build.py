@@ -58,6 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nv = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("PLSLAM_NVCC_EXTRA", "").split()  # developer switches, e.g. -DPL_LSD_PROF2
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src) + ".o")

@@ -5,7 +5,7 @@
 //       k_lsd_scale      GaussianBlur 7x7 sigma 0.75 (8.8 fixed point) + resize 0.8 INTER_LINEAR_EXACT, fused, smem tile
 //       k_lsd_grad       2x2 gradient, level-line angle (fastAtan2), |grad|^2, per-frame max        (streaming)
 //       k_lsd_bin_count / k_lsd_bin_scan / k_lsd_scatter   stable counting sort of the seeds by 1024 gradient bins
-//       k_lsd_grow       sequential-semantics region growing + rect fit + refine + NFA (one warp per frame)
+//       k_lsd_grow       ordered region growing + rect fit + refine (speculative grower warps, persistent CTAs)
 //   top-80 by response (:23-35) + KeyLine fields (LSDDetector.cpp)  -> k_line_finalize
 //   BinaryDescriptor::compute (binary_descriptor.cpp)               -> k_lbd_sobel (blur 5x5 sigma 1 + Sobel, fused),
 //                                                                     k_lbd_rows, k_lbd_finish
@@ -108,10 +108,11 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineGeom g, const uint8_t* __
 // ---------------------------------------------------------------------------------------------------------------
 // k_lsd_grad: ll_angle() — gradient with a 2x2 mask, level-line angle, squared modulus, per-frame max
 // ---------------------------------------------------------------------------------------------------------------
-// also stores cosf/sinf of the angle (what region_grow adds to its running sums), so the ordered grower only loads them
+// also stores cosf/sinf of the angle (what region_grow adds to its running sums) and the double-precision cos/sin
+// rounded to float (what a seed starts its sums from), so the ordered grower only loads them
 __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __restrict__ scaled, size_t scaled_frame_stride,
-                                                  float* __restrict__ angdeg, int* __restrict__ g2, float2* __restrict__ cs, size_t plane,
-                                                  double rho, int* __restrict__ max_g2) {
+                                                  float* __restrict__ angdeg, int* __restrict__ g2, float2* __restrict__ cs,
+                                                  float2* __restrict__ cs0, size_t plane, double rho, int* __restrict__ max_g2) {
     const int f = blockIdx.z;
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     int my = -1;
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __r
                 // cos(float(angle)) / sin(float(angle)) of the reference's region_grow resolve to cosf / sinf
                 const float af = (float)((double)a * kDegToRad);
                 cs[(size_t)f * plane + (size_t)y * g.W + x] = make_float2(glibc_sincosf(af, 1), glibc_sincosf(af, 0));
+                // a seed starts its sums from float(std::cos(double angle)), float(std::sin(double angle))
+                const double ad = (double)a * kDegToRad;
+                cs0[(size_t)f * plane + (size_t)y * g.W + x] = make_float2((float)cos(ad), (float)sin(ad));
             }
         }
         angdeg[(size_t)f * plane + (size_t)y * g.W + x] = a;
@@ -268,12 +272,14 @@ struct LsdSeg {  // one detected segment, in detection order (== cv::LineSegment
 struct LsdRect {
     double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
 };
-constexpr int kRegRing = 512;    // most recent region points kept in shared memory (the BFS frontier reads them)
+constexpr int kRegRing = 256;    // most recent region points kept in shared memory (the BFS frontier reads them)
 constexpr int kSpecCap = 16384;  // region / touched-list capacity of a speculative grower (larger regions run exclusively)
 struct LsdFrame {  // per-frame (and per-grower) device views
     const float* ang;   // level-line angle in degrees or kNotDefDeg
     const int* g2;      // gx^2 + gy^2
     const float2* cs;   // (cosf, sinf) of the angle
+    const float2* cs0;  // (float(cos(double angle)), float(sin(double angle))): a seed's initial sums
+    float2* sval;       // shared-memory staging of one warp, 36 entries
     uint8_t* used;      // the committed USED map
     unsigned int* reg;  // region points, packed y<<16 | x
     unsigned int* ring; // shared-memory copy of reg[n - kRegRing .. n)
@@ -282,8 +288,25 @@ struct LsdFrame {  // per-frame (and per-grower) device views
     bool spec;
     unsigned int* bits;     // private USED bitmap (W*H bits)
     unsigned int* touched;  // log of accepted pixels (packed), capacity reg_cap
-    int reg_cap;            // capacity of reg / touched
+    int reg_cap;            // capacity of reg
+    int touched_cap;        // capacity of touched
+    // in-flight claims (a hint that saves wasted growth, never needed for correctness): every accepted pixel is
+    // stamped with the low 16 bits of the grower's ticket; a grower that is about to accept a pixel stamped by an
+    // earlier ticket that is still uncommitted gives up (the seed is re-grown when its turn to commit comes).
+    unsigned short* claims;
+    int ticket;
+    const volatile int* commit_head;
+#ifdef PL_LSD_PROF3
+    unsigned long long* prof;
+#endif
 };
+#ifdef PL_LSD_PROF3
+#define PROF3_T(v) const long long v = clock64()
+#define PROF3_ADD(k, x) pr[k] += (x)
+#else
+#define PROF3_T(v)
+#define PROF3_ADD(k, x)
+#endif
 __device__ __forceinline__ bool lsd_is_used(const LsdFrame& F, size_t o) {
     if (F.used[o] != 0) return true;
     return F.spec && ((F.bits[o >> 5] >> (o & 31)) & 1u);
@@ -317,82 +340,196 @@ __device__ __forceinline__ double lsd_dist_sq(double x1, double y1, double x2, d
     return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
 }
 
+// isAligned() on the float degree values the reference converts to double radians: decided in float when the
+// distance is not within 2e-3 degrees of the tolerance or of the fold point, else with the reference's own formula.
+__device__ __forceinline__ bool lsd_aligned_deg(float th, float adeg, float precdeg, double prec) {
+    const float t = fabsf(th - adeg);
+    const float tf = t > 270.f ? fabsf(t - 360.f) : t;
+    if (fabsf(tf - precdeg) > 2e-3f && fabsf(t - 270.f) > 2e-3f) return tf <= precdeg;
+    return lsd_aligned((double)th * kDegToRad, (double)adeg * kDegToRad, prec);
+}
+
 // region_grow(): returns the region size; reg_angle (radians) is returned through *out_angle.
-// Lanes 0..26 hold the 3x3 neighbourhoods of up to three consecutive region points, in the reference's visiting
-// order (point, then row, then column); acceptances are resolved in that order with the running region angle.
+//
+// The 32 lanes hold the 8-neighbourhoods of up to four consecutive region points in the reference's visiting order
+// (point, then row, then column; the centre is always USED and is skipped).  Acceptances must be resolved in that
+// order with the RUNNING region angle, which changes after every accepted pixel.  A batch is resolved by
+// hypothesis and verification:
+//   1. hypothesis H: the lanes that pass with a hint angle (the most recent angle known);
+//   2. every lane forms, in parallel, the float sums the reference would hold when it reaches that lane IF H is what
+//      happened before it (the accepted lanes' cos/sin are staged in shared memory and added in lane order), takes
+//      fastAtan2 of them and evaluates its own exact test;
+//   3. up to and including the first lane whose exact verdict differs from H, every verdict is the sequential one
+//      (induction over the lanes); those lanes are committed, the rest goes through another pass.
+// Most batches take one pass, whose serial chain is one fastAtan2.  The global loads of the next batch are issued
+// before the current one is resolved.
 // `nt` counts the entries of the touched log (speculative mode); returns -1 when a capacity is exceeded.
+struct GrowCand {
+    int xx, yy;
+    unsigned o;
+    float adeg, ca, sa;
+    unsigned u;
+    unsigned short claim;
+    bool inb;
+};
+__device__ __forceinline__ bool lsd_claim_hit(const LsdFrame& F, unsigned short claim) {
+    const unsigned d = (unsigned)(F.ticket - (int)claim) & 0xffffu;  // tickets between the stamp and this grower
+    return d != 0 && d <= (unsigned)(F.ticket - *F.commit_head);
+}
+__device__ __forceinline__ void lsd_issue_cand(const LsdFrame& F, int ri, int n, int ddx, int ddy, GrowCand& c) {
+    const unsigned p = (n - ri <= kRegRing) ? F.ring[ri & (kRegRing - 1)] : F.reg[ri];
+    c.xx = (int)(p & 0xffffu) + ddx;
+    c.yy = (int)(p >> 16) + ddy;
+    c.inb = c.xx >= 0 && c.yy >= 0 && c.xx < F.W && c.yy < F.H;
+    c.o = 0;
+    c.adeg = kNotDefDeg;
+    c.ca = c.sa = 0.f;
+    c.u = 1;
+    c.claim = 0xffffu;
+    if (c.inb) {
+        c.o = (unsigned)c.yy * (unsigned)F.W + (unsigned)c.xx;
+        c.adeg = F.ang[c.o];
+        c.u = F.used[c.o];
+        c.claim = F.claims[c.o];
+        const float2 c2 = F.cs[c.o];
+        c.ca = c2.x;
+        c.sa = c2.y;
+    }
+}
 __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, double* out_angle, int& nt) {
     const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    double reg_angle = (double)F.ang[(size_t)sy * F.W + sx] * kDegToRad;
-    // float(std::cos(reg_angle)) — double cosine of the seed angle, rounded to float
-    float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
-    if (F.spec && nt >= F.reg_cap) return -1;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+#ifdef PL_LSD_PROF3
+    long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    PROF3_T(q0);
+    const unsigned so = (unsigned)sy * (unsigned)F.W + (unsigned)sx;
+    const float seed_deg = F.ang[so];
+    const float2 c0 = F.cs0[so];
+    float sumdx = c0.x, sumdy = c0.y;
+    float hint = seed_deg;
+    const float precdeg = (float)(prec * (180.0 / kPiD));
+    if (F.spec && nt >= F.touched_cap) return -1;
     if (lane == 0) {
         F.reg[0] = ((unsigned)sy << 16) | (unsigned)sx;
         F.ring[0] = ((unsigned)sy << 16) | (unsigned)sx;
-        lsd_mark(F, (size_t)sy * F.W + sx);
+        lsd_mark(F, (size_t)so);
         if (F.spec) F.touched[nt] = ((unsigned)sy << 16) | (unsigned)sx;
+        F.claims[so] = (unsigned short)F.ticket;
     }
     nt++;
     __syncwarp();
-    int n = 1, i = 0;
-    const int b = lane / 9, k = lane - b * 9;
-    const int ddy = k / 3 - 1, ddx = k - (k / 3) * 3 - 1;
+    int n = 1, i = 0, have = 0;
+    bool any = false;
+    const int b = lane >> 3, k8 = lane & 7, kk = k8 + (k8 >= 4 ? 1 : 0);
+    const int ddy = kk / 3 - 1, ddx = kk - (kk / 3) * 3 - 1;
+    GrowCand cur, nxt;
+    nxt.inb = false;
     while (i < n) {
-        const int nb = min(3, n - i);
+        PROF3_T(b0);
+        PROF3_ADD(4, 1);
+        const int nb = min(4, n - i);
+        if (b < have) cur = nxt;
+        else if (b < nb) lsd_issue_cand(F, i + b, n, ddx, ddy, cur);
+        else cur.inb = false;
+        // the next batch's frontier points that exist already: issue their loads now
+        const int have_next = max(0, min(4, n - (i + 4)));
+        if (b < have_next) lsd_issue_cand(F, i + 4 + b, n, ddx, ddy, nxt);
         bool cand = false;
-        int xx = 0, yy = 0;
-        float adeg = 0.f, ca = 0.f, sa = 0.f;
-        double arad = 0.0;
-        if (lane < 27 && b < nb) {
-            const int ri = i + b;
-            const unsigned p = (n - ri <= kRegRing) ? F.ring[ri & (kRegRing - 1)] : F.reg[ri];
-            xx = (int)(p & 0xffffu) + ddx;
-            yy = (int)(p >> 16) + ddy;
-            if (xx >= 0 && yy >= 0 && xx < F.W && yy < F.H) {
-                const size_t o = (size_t)yy * F.W + xx;
-                adeg = F.ang[o];
-                cand = adeg != kNotDefDeg && !lsd_is_used(F, o);
-            }
+        if (cur.inb) {
+            if (!F.spec) cur.u = F.used[cur.o];  // exclusive growth marks the committed map itself
+            const bool priv = F.spec && ((F.bits[cur.o >> 5] >> (cur.o & 31)) & 1u);
+            cand = cur.adeg != kNotDefDeg && cur.u == 0 && !priv;
         }
-        if (cand) {
-            arad = (double)adeg * kDegToRad;
-            const float2 c2 = F.cs[(size_t)yy * F.W + xx];
-            ca = c2.x;
-            sa = c2.y;
-        }
-        unsigned mask = __ballot_sync(FULL, cand);
-        while (mask) {
-            const bool ok = ((mask >> lane) & 1u) && lsd_aligned(reg_angle, arad, prec);
-            const unsigned pass = __ballot_sync(FULL, ok);
-            if (!pass) break;
-            const int j = __ffs(pass) - 1;
-            // accept lane j's pixel
-            const int ax = __shfl_sync(FULL, xx, j), ay = __shfl_sync(FULL, yy, j);
-            const float cj = __shfl_sync(FULL, ca, j), sj = __shfl_sync(FULL, sa, j);
-            if (n >= F.reg_cap || (F.spec && nt >= F.reg_cap)) return -1;
-            if (lane == j) {
-                F.reg[n] = ((unsigned)ay << 16) | (unsigned)ax;
-                F.ring[n & (kRegRing - 1)] = ((unsigned)ay << 16) | (unsigned)ax;
-                lsd_mark(F, (size_t)ay * F.W + ax);
-                if (F.spec) F.touched[nt] = ((unsigned)ay << 16) | (unsigned)ax;
+        unsigned rem = __ballot_sync(FULL, cand);
+        PROF3_T(b1);
+        PROF3_ADD(7, b1 - b0);
+        if (rem) {
+            const unsigned grp = __match_any_sync(FULL, cand ? cur.o : (0x80000000u | (unsigned)lane));  // lanes on the same pixel
+            while (rem) {
+                PROF3_ADD(5, 1);
+                PROF3_T(a0);
+                const bool inrem = (rem >> lane) & 1u;
+                // 1. hypothesis
+                float t = fabsf(hint - cur.adeg);
+                if (t > 270.f) t = fabsf(t - 360.f);
+                const bool hyp = inrem && t <= precdeg;
+                const unsigned H = __ballot_sync(FULL, hyp);
+                const bool inH = hyp && !(grp & H & lt);  // a pixel seen by several lanes is accepted by the first
+                const unsigned H2 = __ballot_sync(FULL, inH);
+                const int c = __popc(H2 & lt), cmax = __popc(H2);
+                PROF3_T(a1);
+                PROF3_ADD(0, a1 - a0);
+                if (inH) F.sval[c] = make_float2(cur.ca, cur.sa);
+                __syncwarp();
+                // 2. the sums the reference holds on reaching this lane, if H2 happened
+                float px = sumdx, py = sumdy;
+                for (int k0 = 0; k0 < cmax; k0 += 4) {
+                    const float2 v0 = F.sval[k0], v1 = F.sval[k0 + 1], v2 = F.sval[k0 + 2], v3 = F.sval[k0 + 3];
+                    if (k0 < c) { px = __fadd_rn(px, v0.x); py = __fadd_rn(py, v0.y); }
+                    if (k0 + 1 < c) { px = __fadd_rn(px, v1.x); py = __fadd_rn(py, v1.y); }
+                    if (k0 + 2 < c) { px = __fadd_rn(px, v2.x); py = __fadd_rn(py, v2.y); }
+                    if (k0 + 3 < c) { px = __fadd_rn(px, v3.x); py = __fadd_rn(py, v3.y); }
+                }
+                __syncwarp();
+                PROF3_T(a2);
+                PROF3_ADD(1, a2 - a1);
+                // the region angle is only defined by the sums after the first acceptance; before it, it is the seed's
+                const float th = (any || c > 0) ? fast_atan2_deg(py, px) : seed_deg;
+                bool v = false;
+                if (inrem && !(grp & H2 & lt)) v = lsd_aligned_deg(th, cur.adeg, precdeg, prec);
+                // 3. first lane whose verdict contradicts the hypothesis
+                const unsigned M = __ballot_sync(FULL, inrem && v != inH);
+                PROF3_T(a3);
+                PROF3_ADD(2, a3 - a2);
+                unsigned T = H2, resolved = FULL;
+                int hl = 31 - __clz(rem);
+                if (M) {
+                    const int ls = __ffs(M) - 1;
+                    const unsigned below = (1u << ls) - 1u;
+                    T = (H2 & below) | (((H2 >> ls) & 1u) ? 0u : (1u << ls));
+                    resolved = (2u << ls) - 1u;
+                    hl = ls;
+                }
+                hint = __shfl_sync(FULL, th, hl);
+                const int cnt = __popc(T);
+                if (cnt) {
+                    if (n + cnt > F.reg_cap || (F.spec && nt + cnt > F.touched_cap)) return -1;
+                    if (__any_sync(FULL, ((T >> lane) & 1u) && lsd_claim_hit(F, cur.claim))) return -2;
+                    if ((T >> lane) & 1u) {
+                        F.claims[cur.o] = (unsigned short)F.ticket;
+                        const int r = __popc(T & lt);
+                        const unsigned pk = ((unsigned)cur.yy << 16) | (unsigned)cur.xx;
+                        F.reg[n + r] = pk;
+                        F.ring[(n + r) & (kRegRing - 1)] = pk;
+                        lsd_mark(F, (size_t)cur.o);
+                        if (F.spec) F.touched[nt + r] = pk;
+                    }
+                    // sums after the last accepted lane: its own prefix plus its own pixel
+                    const int L = 31 - __clz(T);
+                    sumdx = __shfl_sync(FULL, __fadd_rn(px, cur.ca), L);
+                    sumdy = __shfl_sync(FULL, __fadd_rn(py, cur.sa), L);
+                    n += cnt;
+                    nt += cnt;
+                    any = true;
+                    rem &= ~__ballot_sync(FULL, (grp & T) != 0);
+                }
+                rem &= ~resolved;
+                PROF3_T(a4);
+                PROF3_ADD(3, a4 - a3);
             }
-            n++;
-            nt++;
-            sumdx = __fadd_rn(sumdx, cj);
-            sumdy = __fadd_rn(sumdy, sj);
-            reg_angle = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
-            // drop lanes up to j (tested, failed or accepted) and every later lane that looks at the same pixel
-            const bool same = (xx == ax && yy == ay);
-            const unsigned dup = __ballot_sync(FULL, same);
-            mask &= ~((2u << j) - 1u);
-            mask &= ~dup;
         }
         __syncwarp();
         i += nb;
+        have = have_next;
     }
-    *out_angle = reg_angle;
+#ifdef PL_LSD_PROF3
+    if (lane == 0 && F.prof) {
+        pr[6] = n;
+        for (int t = 0; t < 8; t++) atomicAdd(&F.prof[t], (unsigned long long)pr[t]);
+    }
+#endif
+    *out_angle = any ? (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad : (double)seed_deg * kDegToRad;
     return n;
 }
 
@@ -421,13 +558,13 @@ __device__ void lsd_region2rect(const LsdFrame& F, int n, double reg_angle, doub
     const unsigned FULL = 0xffffffffu;
     double x = 0, y = 0, sum = 0;
     for (int base = 0; base < n; base += 32) {
-        const RegPt pt = lsd_load_pt(F, base + lane, n);
-        const int cnt = min(32, n - base);
-        for (int j = 0; j < cnt; j++) {
-            const double px = __shfl_sync(FULL, pt.x, j), py = __shfl_sync(FULL, pt.y, j), w = __shfl_sync(FULL, pt.w, j);
-            x = __dadd_rn(x, __dmul_rn(px, w));
-            y = __dadd_rn(y, __dmul_rn(py, w));
-            sum = __dadd_rn(sum, w);
+        const RegPt pt = lsd_load_pt(F, base + lane, n);  // lanes beyond n hold zeros: adding +0.0 changes nothing
+        const double pxw = __dmul_rn(pt.x, pt.w), pyw = __dmul_rn(pt.y, pt.w);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            x = __dadd_rn(x, __shfl_sync(FULL, pxw, j));
+            y = __dadd_rn(y, __shfl_sync(FULL, pyw, j));
+            sum = __dadd_rn(sum, __shfl_sync(FULL, pt.w, j));
         }
     }
     x = x / sum;
@@ -436,13 +573,18 @@ __device__ void lsd_region2rect(const LsdFrame& F, int n, double reg_angle, doub
     double Ixx = 0, Iyy = 0, Ixy = 0;
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);
-        const int cnt = min(32, n - base);
-        for (int j = 0; j < cnt; j++) {
-            const double px = __shfl_sync(FULL, pt.x, j), py = __shfl_sync(FULL, pt.y, j), w = __shfl_sync(FULL, pt.w, j);
-            const double dx = __dsub_rn(px, x), dy = __dsub_rn(py, y);
-            Ixx = __dadd_rn(Ixx, __dmul_rn(__dmul_rn(dy, dy), w));
-            Iyy = __dadd_rn(Iyy, __dmul_rn(__dmul_rn(dx, dx), w));
-            Ixy = __dsub_rn(Ixy, __dmul_rn(__dmul_rn(dx, dy), w));
+        double txx = 0, tyy = 0, txy = 0;
+        if (base + lane < n) {
+            const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
+            txx = __dmul_rn(__dmul_rn(dy, dy), pt.w);
+            tyy = __dmul_rn(__dmul_rn(dx, dx), pt.w);
+            txy = __dmul_rn(__dmul_rn(dx, dy), pt.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            Ixx = __dadd_rn(Ixx, __shfl_sync(FULL, txx, j));
+            Iyy = __dadd_rn(Iyy, __shfl_sync(FULL, tyy, j));
+            Ixy = __dsub_rn(Ixy, __shfl_sync(FULL, txy, j));
         }
     }
     const double dI = __dsub_rn(Ixx, Iyy);
@@ -528,17 +670,21 @@ __device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double p
     int cnt_in = 0;
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);
-        if (base + lane < n) lsd_unmark(F, (size_t)(int)pt.y * F.W + (int)pt.x);
-        const int cnt = min(32, n - base);
-        for (int j = 0; j < cnt; j++) {
-            const double px = __shfl_sync(FULL, pt.x, j), py = __shfl_sync(FULL, pt.y, j);
-            const float ad = __shfl_sync(FULL, pt.adeg, j);
-            if (sqrt(lsd_dist_sq(xc, yc, px, py)) < rec.width) {
-                const double ang_d = lsd_angle_diff_signed((double)ad * kDegToRad, ang_c);
-                sum = __dadd_rn(sum, ang_d);
-                s_sum = __dadd_rn(s_sum, __dmul_rn(ang_d, ang_d));
-                ++cnt_in;
+        bool inside = false;
+        double ang_d = 0, ang_d2 = 0;
+        if (base + lane < n) {
+            lsd_unmark(F, (size_t)(int)pt.y * F.W + (int)pt.x);
+            inside = sqrt(lsd_dist_sq(xc, yc, pt.x, pt.y)) < rec.width;
+            if (inside) {
+                ang_d = lsd_angle_diff_signed((double)pt.adeg * kDegToRad, ang_c);
+                ang_d2 = __dmul_rn(ang_d, ang_d);
             }
+        }
+        cnt_in += __popc(__ballot_sync(FULL, inside));
+#pragma unroll
+        for (int j = 0; j < 32; j++) {  // points outside contribute +0.0
+            sum = __dadd_rn(sum, __shfl_sync(FULL, ang_d, j));
+            s_sum = __dadd_rn(s_sum, __shfl_sync(FULL, ang_d2, j));
         }
     }
     __syncwarp();
@@ -546,7 +692,7 @@ __device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double p
     const double tau = 2.0 * sqrt(__dadd_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)) / (double)cnt_in,
                                             __dmul_rn(mean_angle, mean_angle)));
     n = lsd_region_grow(F, sx, sy, tau, &reg_angle, nt);
-    if (n < 0) return -1;
+    if (n < 0) return n;
     if (n < 2) return 0;
     lsd_region2rect(F, n, reg_angle, prec, p, rec);
     density = lsd_density(n, rec);
@@ -807,207 +953,375 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
     return log_nfa;
 }
 
-// flsd() main loop.  One CTA per frame: kGrowers warps grow regions, kNfaWarps warps validate fitted rectangles.
+// flsd() main loop.  Persistent CTAs take frames from a counter; the G warps of a CTA are region growers.
 //
 // Region growing is ordered (seeds by gradient bin, shared USED map), but regions that do not touch the same pixels
-// commute.  Each round the next kGrowers unused seeds (in order) are grown SPECULATIVELY and concurrently, one warp
-// each: a grower reads the committed USED map, keeps the pixels it marks in a private bitmap and logs every pixel it
-// ever accepts (initial growth and the refine re-growth).  Warp 0 then validates the round in seed order against
-// the committed map:  seed already committed -> the seed was swallowed by an earlier region, skip it;  any logged
-// pixel already committed -> the region depended on an earlier region of this round, stop the round there and redo it
-// from that seed;  otherwise the region's execution is exactly what the sequential algorithm would have done ->
-// commit its final pixel set and hand its rectangle to the NFA queue.  Regions larger than the speculative
-// capacity are grown exclusively by warp 0 on the committed map.  rect_improve only reads the angle map and does
-// not influence later regions, so it runs asynchronously in the NFA warps; accepted segments are compacted in seed
-// order at the end.
-constexpr int kGrowers = 8;
-constexpr int kGrowThreads = kGrowers * 32;
+// commute.  The kernel runs the ordered loop as a window of speculative transactions with in-order commit:
+//   * select (one warp at a time): the next seed that is unused in the committed map gets the next ticket and a
+//     slot of the window (kSlots tickets may be uncommitted at once).  A seed stamped by an uncommitted ticket is
+//     most likely being swallowed by that region: it gets its ticket but is not grown ("deferred");
+//   * grow (any number of warps at once): the warp grows its seed reading the committed USED map (global bytes),
+//     keeps the pixels it marks in its private bitmap in shared memory and logs every pixel it ever accepts (initial
+//     growth and refine re-growth) in the touched list of a buffer from the CTA's pool; the final region, the fitted
+//     rectangle and the log stay in the buffer, the private bitmap is cleared, and the warp goes for the next seed.
+//     A grower that runs into a pixel stamped by an earlier uncommitted ticket gives up (deferred);
+//   * commit (one warp at a time, strictly in ticket order): seed already committed -> the seed is void (an earlier
+//     region swallowed it);  deferred, or a logged pixel already committed (the growth depended on a region that
+//     was committed after it read the map) -> the committing warp grows the seed now, when everything before it is
+//     committed, with the frame-sized buffers;  otherwise the growth is exactly what the sequential algorithm would
+//     have done.  The region is written to the USED map and its rectangle is queued.
+// Committed pixels are never released, tickets follow the seed order, and a grower only ever sees pixels of
+// earlier tickets in the map, so the result is the sequential one whatever the stamps say.  rect_improve only reads
+// the angle map and does not influence later regions: it runs afterwards in k_lsd_nfa, and accepted segments are
+// compacted in seed order.
+constexpr int kMaxGrowers = 8;
+constexpr int kSlots = 512;  // window of uncommitted tickets
+constexpr int kPool = 64;    // region buffers per CTA
+constexpr int kSvalEntries = 36;
+constexpr size_t kGrowerSmemFixed = kRegRing * sizeof(unsigned int) + kSvalEntries * sizeof(float2);
+constexpr size_t kGrowCtaSmemFixed = kSlots * sizeof(int4);
 struct LsdQueueItem { LsdRect rec; };
-struct SpecSlot {
-    int seed_pos, seed_pix;
-    int status;  // 1: rectangle fitted, 0: region kept but no rectangle, -1: capacity exceeded -> exclusive
-    int n, nt;
+// window slot (shared memory, int4): x = seed pixel, y = region size, z = touched-log size,
+// w = state | (status + 2) << 8 | (buffer + 1) << 16
+enum { kSlotFree = 0, kSlotGrowing = 1, kSlotDone = 2 };
+enum { kStDeferred = -2, kStCapacity = -1, kStNoRect = 0, kStRect = 1 };
+__device__ __forceinline__ int slot_pack(int state, int status, int buf) { return state | ((status + 2) << 8) | ((buf + 1) << 16); }
+struct GrowCtl {
+    int sel_lock, com_lock;
+    int next_pos, ticket_next, commit_head;
+    int head;        // rectangles queued
+    int all_issued;  // the seed list is exhausted
+    int frame;
+    unsigned long long free_mask;  // free buffers of the pool
+    unsigned long long stat[8];    // committed, void, regrown, deferred, busy cycles, void cycles, idle polls, regrow cycles
+};
+struct GrowResult {
+    int status, n, nt;
     LsdRect rec;
 };
-__device__ __forceinline__ void grower_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(kGrowers * 32) : "memory"); }
+__device__ __forceinline__ bool warp_try_lock(int* lock, int lane) {
+    int got = 0;
+    if (lane == 0) got = atomicCAS(lock, 0, 1) == 0;
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got) __threadfence_block();
+    return got != 0;
+}
+// a warp-uniform decision from a condition that reads state other warps change: lane 0 decides
+#define WARP_UNIFORM(cond) (__shfl_sync(0xffffffffu, (lane == 0) ? (int)(cond) : 0, 0) != 0)
+__device__ __forceinline__ void warp_unlock(int* lock, int lane) {
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) atomicExch(lock, 0);
+    __syncwarp();
+}
+__device__ __forceinline__ int pool_pop(unsigned long long* mask, int lane) {
+    int b = -1;
+    if (lane == 0) {
+        while (true) {
+            const unsigned long long m = *(volatile unsigned long long*)mask;
+            if (!m) break;
+            const int c = __ffsll((long long)m) - 1;
+            if (atomicCAS(mask, m, m & ~(1ull << c)) == m) { b = c; break; }
+        }
+    }
+    return __shfl_sync(0xffffffffu, b, 0);
+}
+// grow + fit + refine one seed into the buffers of F; leaves F.bits clean
+__device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min_reg_size, GrowResult* out) {
+    const LsdFrame F = Fin;  // a private copy the compiler keeps in registers (the caller's lives in local memory)
+    const int lane = threadIdx.x & 31;
+    const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
+    const double density_th = 0.7;
+    const int sx = pix % F.W, sy = pix / F.W;
+    double reg_angle;
+    int nt = 0, status = kStNoRect;
+    LsdRect rec;
+    int n = lsd_region_grow(F, sx, sy, prec, &reg_angle, nt);
+    if (n < 0) {
+        status = n;
+    } else if (n >= min_reg_size) {
+        lsd_region2rect(F, n, reg_angle, prec, p, rec);
+        status = lsd_refine(F, n, reg_angle, prec, p, rec, density_th, nt);
+    }
+    __syncwarp();
+    // the private bitmap goes back to all-zero: every pixel ever marked is in the log
+    for (int i = lane; i < nt; i += 32) {
+        const unsigned pp = F.touched[i];
+        const unsigned o = (pp >> 16) * (unsigned)F.W + (pp & 0xffffu);
+        atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
+    }
+    out->status = status;
+    out->n = n;
+    out->nt = nt;
+    if (status == kStRect) out->rec = rec;
+    __syncwarp();
+}
 
-__global__ void __launch_bounds__(kGrowThreads) k_lsd_grow(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
-                                                           uint8_t* __restrict__ used, unsigned int* __restrict__ reg,
-                                                           unsigned int* __restrict__ spec_reg, unsigned int* __restrict__ spec_touched,
-                                                           unsigned int* __restrict__ spec_bits, int bits_words,
-                                                           const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
-                                                           const float2* __restrict__ cs, size_t plane,
-                                                           LsdQueueItem* __restrict__ queue, int* __restrict__ n_rects,
-                                                           int* __restrict__ flags, long long* __restrict__ phase_cycles) {
-    __shared__ unsigned int s_ring[kGrowers][kRegRing];
-    __shared__ SpecSlot s_slot[kGrowers];
-    __shared__ int s_nsel, s_finished;
-    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, int nf, int* __restrict__ frame_counter,
+                                                                  const float* __restrict__ angdeg, const int* __restrict__ g2,
+                                                                  uint8_t* __restrict__ used, unsigned short* __restrict__ claims,
+                                                                  unsigned int* __restrict__ big_reg, unsigned int* __restrict__ big_touched,
+                                                                  unsigned int* __restrict__ pool_reg, unsigned int* __restrict__ pool_touched,
+                                                                  LsdRect* __restrict__ pool_rect, int bits_words,
+                                                                  const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
+                                                                  const float2* __restrict__ cs, const float2* __restrict__ cs0, size_t plane,
+                                                                  LsdQueueItem* __restrict__ queue, int* __restrict__ n_rects,
+                                                                  int* __restrict__ flags, long long* __restrict__ phase_cycles) {
+    extern __shared__ __align__(16) unsigned int s_dyn[];
+    __shared__ GrowCtl s_ctl;
+#ifdef PL_LSD_PROF3
+    __shared__ unsigned long long s_prof3[8];
+    if (threadIdx.x < 8) s_prof3[threadIdx.x] = 0;
+#endif
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    LsdFrame F;
-    F.ang = angdeg + (size_t)f * plane;
-    F.g2 = g2 + (size_t)f * plane;
-    F.cs = cs + (size_t)f * plane;
-    F.used = used + (size_t)f * plane;
-    F.W = g.W;
-    F.H = g.H;
-    LsdQueueItem* q = queue + (size_t)f * g.seg_cap;
-    if (threadIdx.x == 0) { s_finished = 0; s_nsel = 0; }
-    __syncthreads();
-    long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    {
-        // ------------------------------ growers ------------------------------
-        const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
-        const double density_th = 0.7;
-        const size_t gslot = (size_t)f * kGrowers + warp;
+    volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_dyn);                      // [kSlots]
+    float2* s_val = reinterpret_cast<float2*>(s_dyn + kSlots * 4);                        // [G][kSvalEntries]
+    unsigned int* s_ring = s_dyn + kSlots * 4 + (size_t)G * kSvalEntries * 2;             // [G][kRegRing]
+    unsigned int* s_bits = s_ring + (size_t)G * kRegRing;                                 // [G][bits_words] private USED bitmaps
+    for (int i = threadIdx.x; i < G * bits_words; i += blockDim.x) s_bits[i] = 0;
+    volatile GrowCtl* ctl = &s_ctl;
+    unsigned int* my_pool_reg = pool_reg + (size_t)blockIdx.x * kPool * kSpecCap;
+    unsigned int* my_pool_touched = pool_touched + (size_t)blockIdx.x * kPool * kSpecCap;
+    LsdRect* my_pool_rect = pool_rect + (size_t)blockIdx.x * kPool;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_ctl.frame = atomicAdd(frame_counter, 1);
+            s_ctl.sel_lock = s_ctl.com_lock = 0;
+            s_ctl.next_pos = s_ctl.ticket_next = s_ctl.commit_head = 0;
+            s_ctl.head = 0;
+            s_ctl.all_issued = 0;
+            s_ctl.free_mask = ~0ull << G;  // buffer w starts with warp w
+            for (int k = 0; k < 8; k++) s_ctl.stat[k] = 0;
+        }
+        for (int i = threadIdx.x; i < kSlots; i += blockDim.x) s_slot[i].w = slot_pack(kSlotFree, 0, -1);
+        __syncthreads();
+        const int f = s_ctl.frame;
+        if (f >= nf) break;
+        LsdFrame F;
+        F.ang = angdeg + (size_t)f * plane;
+        F.g2 = g2 + (size_t)f * plane;
+        F.cs = cs + (size_t)f * plane;
+        F.cs0 = cs0 + (size_t)f * plane;
+        F.sval = s_val + warp * kSvalEntries;
+        F.used = used + (size_t)f * plane;
+        F.claims = claims + (size_t)f * plane;
+        F.commit_head = &s_ctl.commit_head;
+        F.ticket = 0;
+        F.W = g.W;
+        F.H = g.H;
         F.spec = true;
-        F.reg = spec_reg + gslot * kSpecCap;
-        F.touched = spec_touched + gslot * kSpecCap;
-        F.bits = spec_bits + gslot * bits_words;
-        F.reg_cap = kSpecCap;
-        F.ring = s_ring[warp];
-        LsdFrame FX = F;  // exclusive view (warp 0): the committed map itself, the frame-sized region buffer
-        FX.spec = false;
-        FX.reg = reg + (size_t)f * plane;
-        FX.reg_cap = (int)plane;
+        F.bits = s_bits + (size_t)warp * bits_words;
+        F.ring = s_ring + warp * kRegRing;
+        F.reg = nullptr;
+        F.touched = nullptr;
+        F.reg_cap = F.touched_cap = 0;
+#ifdef PL_LSD_PROF3
+        F.prof = s_prof3;
+#endif
+        volatile uint8_t* vused = F.used;
+        const volatile unsigned short* vclaims = F.claims;
+        LsdQueueItem* q = queue + (size_t)f * g.seg_cap;
         const unsigned int* sd = seeds + (size_t)f * plane;
         const int ns = n_seeds[f];
-        int pos = 0, head = 0;  // warp 0 only
-        bool exclusive = false;
         const long long tstart = clock64();
-        auto push_rect = [&](const LsdRect& rec) {
-            if (head < g.seg_cap) {
-                if (lane == 0) q[head].rec = rec;
-                head++;
-            } else if (lane == 0) {
-                atomicOr(flags + f, 1);
-            }
-        };
+        long long t_com = 0;
+        int mybuf = warp;
+        GrowResult res;
         while (true) {
-            if (warp == 0) {
-                long long t0 = clock64();
-                if (exclusive) {  // the seed at `pos` needs more than the speculative capacity: sequential path
-                    exclusive = false;
-                    const unsigned pix = sd[pos];
-                    pos++;
-                    const int sx = (int)(pix % (unsigned)g.W), sy = (int)(pix / (unsigned)g.W);
-                    double reg_angle;
-                    int nt = 0;
-                    int n = lsd_region_grow(FX, sx, sy, prec, &reg_angle, nt);
-                    if (n < 0) {
-                        if (lane == 0) atomicOr(flags + f, 2);
-                    } else if (n >= g.min_reg_size) {
+            bool progressed = false;
+            // ---------------- commit duty: strictly in ticket order ----------------
+            if (WARP_UNIFORM(ctl->commit_head < ctl->ticket_next && (s_slot[ctl->commit_head % kSlots].w & 0xff) == kSlotDone) &&
+                warp_try_lock(&s_ctl.com_lock, lane)) {
+                const long long t0 = clock64();
+                while (true) {
+                    const int h = __shfl_sync(FULL, ctl->commit_head, 0);
+                    volatile int4* sl = &s_slot[h % kSlots];
+                    if (!WARP_UNIFORM(h < ctl->ticket_next && (sl->w & 0xff) == kSlotDone)) break;
+                    __threadfence_block();
+                    const int pix = sl->x, w = sl->w;
+                    int n = sl->y, nt = sl->z, status = ((w >> 8) & 0xff) - 2;
+                    const int buf = ((w >> 16) & 0xff) - 1;
+                    int kind = 0;  // 0 committed, 1 void
+                    if (vused[pix] != 0) {
+                        kind = 1;  // swallowed by an earlier region
+                        if (lane == 0 && buf >= 0) s_ctl.stat[6] += (unsigned long long)nt << 32 | 1ull;
+                    } else {
+                        const unsigned int* rg = my_pool_reg + (size_t)max(buf, 0) * kSpecCap;
+                        bool redo = status < 0;
+                        if (!redo) {
+                            const unsigned int* tk = my_pool_touched + (size_t)buf * kSpecCap;
+                            bool conflict = false;
+                            for (int i = lane; i < nt; i += 32) {
+                                const unsigned pp = tk[i];
+                                conflict |= vused[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] != 0;
+                            }
+                            redo = __any_sync(FULL, conflict);
+                        }
                         LsdRect rec;
-                        lsd_region2rect(FX, n, reg_angle, prec, p, rec);
-                        const int r = lsd_refine(FX, n, reg_angle, prec, p, rec, density_th, nt);
-                        if (r == 1) push_rect(rec);
-                        else if (r < 0 && lane == 0) atomicOr(flags + f, 2);
+                        if (redo) {  // everything before this ticket is committed: this growth is the sequential one
+                            const long long g0 = clock64();
+                            LsdFrame FS = F;
+                            FS.reg = big_reg + (size_t)f * plane;
+                            FS.touched = big_touched + (size_t)blockIdx.x * 2 * plane;
+                            FS.reg_cap = (int)plane;
+                            FS.touched_cap = (int)(2 * plane);
+                            FS.ticket = h;
+                            lsd_grow_seed(FS, pix, g.min_reg_size, &res);
+                            status = res.status;
+                            n = res.n;
+                            rec = res.rec;
+                            rg = FS.reg;
+                            if (status < 0 && lane == 0) atomicOr(flags + f, 2);
+                            if (lane == 0) {
+                                s_ctl.stat[2]++;
+                                s_ctl.stat[7] += (unsigned long long)(clock64() - g0);
+                            }
+                        } else if (status == kStRect) {
+                            rec = my_pool_rect[buf];
+                        }
+                        if (status >= 0) {
+                            for (int i = lane; i < n; i += 32) {
+                                const unsigned pp = rg[i];
+                                F.used[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] = 1;
+                            }
+                            if (status == kStRect) {
+                                const int head = __shfl_sync(FULL, ctl->head, 0);
+                                if (head < g.seg_cap) {
+                                    if (lane == 0) {
+                                        q[head].rec = rec;
+                                        s_ctl.head = head + 1;
+                                    }
+                                } else if (lane == 0) {
+                                    atomicOr(flags + f, 1);
+                                }
+                            }
+                        }
                     }
-                    cyc[6]++;
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) {
+                        s_ctl.stat[kind]++;
+                        if (buf >= 0) atomicOr(&s_ctl.free_mask, 1ull << buf);
+                        sl->w = slot_pack(kSlotFree, 0, -1);
+                        __threadfence_block();
+                        s_ctl.commit_head = h + 1;
+                    }
+                    __syncwarp();
                 }
-                // select the next unused seeds, in order
-                int nsel = 0;
-                while (pos < ns && nsel < kGrowers) {
+                t_com += clock64() - t0;
+                warp_unlock(&s_ctl.com_lock, lane);
+                progressed = true;
+            }
+            if (mybuf < 0) mybuf = pool_pop(&s_ctl.free_mask, lane);
+            // ---------------- next seed ----------------
+            int my_ticket = -1, my_pix = 0;
+            if (mybuf >= 0 && WARP_UNIFORM(!ctl->all_issued && ctl->ticket_next - ctl->commit_head < kSlots) &&
+                warp_try_lock(&s_ctl.sel_lock, lane)) {
+                int t = __shfl_sync(FULL, ctl->ticket_next, 0);
+                int pos = __shfl_sync(FULL, ctl->next_pos, 0);
+                bool exhausted = false;
+                while (my_ticket < 0 && pos < ns) {
                     const int idx = pos + lane;
                     unsigned pix = 0;
                     bool free_ = false;
+                    unsigned short cl = 0xffffu;
                     if (idx < ns) {
                         pix = sd[idx];
-                        free_ = F.used[pix] == 0;
+                        free_ = vused[pix] == 0;
+                        cl = vclaims[pix];
                     }
                     unsigned m = __ballot_sync(FULL, free_);
-                    if (!m) { pos += 32; continue; }
-                    int last = -1;
-                    while (m && nsel < kGrowers) {
+                    int consumed = 32;  // seeds of this chunk that are dealt with
+                    while (m) {
+                        const int room = __shfl_sync(FULL, kSlots - (t - ctl->commit_head), 0);
                         const int j = __ffs(m) - 1;
+                        if (room <= 0) { consumed = j; exhausted = true; break; }
                         m &= m - 1;
                         const unsigned pj = __shfl_sync(FULL, pix, j);
-                        if (lane == 0) { s_slot[nsel].seed_pos = pos + j; s_slot[nsel].seed_pix = (int)pj; }
-                        nsel++;
-                        last = j;
+                        const unsigned short cj = (unsigned short)__shfl_sync(FULL, (unsigned)cl, j);
+                        // stamped by an uncommitted earlier ticket: most likely swallowed, do not grow it now
+                        const unsigned d = (unsigned)(t - (int)cj) & 0xffffu;
+                        const bool defer = WARP_UNIFORM(d != 0 && d <= (unsigned)(t - ctl->commit_head));
+                        if (lane == 0) {
+                            volatile int4* sl = &s_slot[t % kSlots];
+                            sl->x = (int)pj;
+                            sl->y = 0;
+                            sl->z = 0;
+                            __threadfence_block();
+                            sl->w = defer ? slot_pack(kSlotDone, kStDeferred, -1) : slot_pack(kSlotGrowing, 0, -1);
+                            __threadfence_block();
+                            s_ctl.ticket_next = t + 1;
+                            if (defer) s_ctl.stat[3]++;
+                        }
+                        t++;
+                        if (!defer) {
+                            my_ticket = t - 1;
+                            my_pix = (int)pj;
+                            consumed = j + 1;
+                            break;
+                        }
                     }
-                    pos += (m && nsel >= kGrowers) ? last + 1 : 32;
-                    if (pos > ns) pos = ns;
-                }
-                if (lane == 0) { s_nsel = nsel; if (nsel == 0) s_finished = 1; }
-                cyc[0] += clock64() - t0;
-            }
-            grower_barrier();
-            if (s_finished) break;
-            const int nsel = s_nsel;
-            // ---- speculative growth ----
-            if (warp < nsel) {
-                const int pix = s_slot[warp].seed_pix;
-                const int sx = pix % g.W, sy = pix / g.W;
-                double reg_angle;
-                int nt = 0, status = 0;
-                LsdRect rec;
-                int n = lsd_region_grow(F, sx, sy, prec, &reg_angle, nt);
-                if (n < 0) {
-                    status = -1;
-                } else if (n >= g.min_reg_size) {
-                    lsd_region2rect(F, n, reg_angle, prec, p, rec);
-                    const int r = lsd_refine(F, n, reg_angle, prec, p, rec, density_th, nt);
-                    status = r;
+                    pos += consumed;
+                    if (exhausted) break;
                 }
                 if (lane == 0) {
-                    s_slot[warp].status = status;
-                    s_slot[warp].n = n;
-                    s_slot[warp].nt = nt;
-                    if (status == 1) s_slot[warp].rec = rec;
+                    s_ctl.next_pos = min(pos, ns);
+                    if (pos >= ns && !exhausted && my_ticket < 0) s_ctl.all_issued = 1;
+                    if (pos >= ns && my_ticket >= 0) {
+                        // the chunk ended exactly at the list end: the next selector finds pos >= ns and closes the list
+                    }
                 }
-                __threadfence_block();
+                warp_unlock(&s_ctl.sel_lock, lane);
+                progressed = true;
             }
-            grower_barrier();
-            // ---- in-order validation and commit (warp 0); the others clear their private bitmaps meanwhile ----
-            if (warp == 0) {
-                long long t0 = clock64();
-                int stop_at = -1;
-                for (int k = 0; k < nsel; k++) {
-                    const SpecSlot& sl = s_slot[k];
-                    if (F.used[sl.seed_pix] != 0) { cyc[7]++; continue; }  // swallowed by an earlier region of this round
-                    if (sl.status < 0) { stop_at = k; exclusive = true; break; }
-                    const unsigned int* tk = spec_touched + ((size_t)f * kGrowers + k) * kSpecCap;
-                    bool conflict = false;
-                    for (int i = lane; i < sl.nt; i += 32) {
-                        const unsigned pp = tk[i];
-                        conflict |= F.used[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] != 0;
-                    }
-                    if (__any_sync(FULL, conflict)) { stop_at = k; cyc[7]++; break; }
-                    const unsigned int* rk = spec_reg + ((size_t)f * kGrowers + k) * kSpecCap;
-                    for (int i = lane; i < sl.n; i += 32) {
-                        const unsigned pp = rk[i];
-                        F.used[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] = 1;
-                    }
-                    __syncwarp();
-                    cyc[5]++;
-                    if (sl.status == 1) {
-                        LsdRect rec = sl.rec;
-                        push_rect(rec);
-                    }
+            // ---------------- speculative growth ----------------
+            if (my_ticket >= 0) {
+                LsdFrame FS = F;
+                FS.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
+                FS.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
+                FS.reg_cap = FS.touched_cap = kSpecCap;
+                FS.ticket = my_ticket;
+                volatile int4* sl = &s_slot[my_ticket % kSlots];
+                const long long g0 = clock64();
+                lsd_grow_seed(FS, my_pix, g.min_reg_size, &res);
+                const bool keep = res.status >= 0;  // the buffer stays with the slot until it is committed
+                if (lane == 0) {
+                    atomicAdd(&s_ctl.stat[4], (unsigned long long)(clock64() - g0));
+                    if (res.status < 0) atomicAdd(&s_ctl.stat[5], (unsigned long long)(clock64() - g0));
+                    if (res.status == kStRect) my_pool_rect[mybuf] = res.rec;
+                    sl->y = res.n;
+                    sl->z = res.nt;
+                    __threadfence_block();
+                    sl->w = slot_pack(kSlotDone, res.status, keep ? mybuf : -1);
                 }
-                if (stop_at >= 0) {
-                    for (int k = stop_at + (exclusive ? 1 : 0); k < nsel; k++) cyc[7] += 0;
-                    pos = s_slot[stop_at].seed_pos;
-                }
-                cyc[2] += clock64() - t0;
-                cyc[3]++;
+                __syncwarp();
+                if (keep) mybuf = pool_pop(&s_ctl.free_mask, lane);
+                progressed = true;
             }
-            if (warp < nsel) {
-                const int nt = s_slot[warp].nt;
-                for (int i = lane; i < nt; i += 32) {
-                    const unsigned pp = F.touched[i];
-                    const size_t o = (size_t)(pp >> 16) * g.W + (pp & 0xffffu);
-                    atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
-                }
+            if (WARP_UNIFORM(ctl->all_issued && ctl->commit_head == ctl->ticket_next)) break;
+            if (!progressed) {
+                __nanosleep(200);
             }
         }
-        if (warp == 0) {
-            cyc[1] = clock64() - tstart;
-            if (lane == 0) {
-                n_rects[f] = head;
-                if (phase_cycles)
-                    for (int k = 0; k < 8; k++) phase_cycles[(size_t)f * 8 + k] = cyc[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            n_rects[f] = s_ctl.head;
+            if (phase_cycles) {
+                long long* pc = phase_cycles + (size_t)f * 8;
+                pc[0] = (long long)((s_ctl.stat[4] / 1000) + ((s_ctl.stat[7] / 1000) << 20) + ((s_ctl.stat[5] / 1000) << 40));
+                pc[2] = (long long)s_ctl.stat[6];
+                pc[1] = clock64() - tstart;
+                pc[2] = t_com;
+                pc[3] = s_ctl.ticket_next;
+                pc[4] = (long long)s_ctl.stat[2];
+                pc[5] = (long long)s_ctl.stat[0];
+                pc[6] = (long long)s_ctl.stat[3];
+                pc[7] = (long long)s_ctl.stat[1];
+#ifdef PL_LSD_PROF3
+                for (int k = 0; k < 8; k++) pc[k] = (long long)s_prof3[k];
+#endif
             }
         }
     }
@@ -1023,9 +1337,13 @@ __global__ void __launch_bounds__(kNfaThreads) k_lsd_nfa(LineGeom g, const float
     const int wid = blockIdx.x * (kNfaThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kNfaThreads / 32);
     LsdFrame F;
     F.ang = angdeg + (size_t)f * plane;
-    F.g2 = nullptr; F.cs = nullptr; F.used = nullptr; F.reg = nullptr; F.ring = nullptr;
+    F.g2 = nullptr; F.cs = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used = nullptr; F.reg = nullptr; F.ring = nullptr;
     F.W = g.W; F.H = g.H;
-    F.spec = false; F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0;
+    F.spec = false; F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
+    F.claims = nullptr; F.ticket = 0; F.commit_head = nullptr;
+#ifdef PL_LSD_PROF3
+    F.prof = nullptr;
+#endif
     const int n = min(n_rects[f], g.seg_cap);
     const double log_eps = 0.0;
     for (int t = wid; t < n; t += nw) {
@@ -1413,7 +1731,7 @@ struct pl_line {
     // device buffers (sized for max_cols x max_rows x max_batch at creation)
     uint8_t *d_in = nullptr, *d_scaled = nullptr, *d_used = nullptr, *d_blur5 = nullptr;
     float* d_ang = nullptr;
-    float2* d_cs = nullptr;
+    float2 *d_cs = nullptr, *d_cs0 = nullptr;
     int* d_nrects = nullptr;
     int* d_g2 = nullptr;
     unsigned int *d_reg = nullptr, *d_seeds = nullptr;
@@ -1423,8 +1741,11 @@ struct pl_line {
     LsdSeg* d_qres = nullptr;
     LsdQueueItem* d_queue = nullptr;
     uint8_t* d_qvalid = nullptr;
-    unsigned int *d_spec_reg = nullptr, *d_spec_touched = nullptr, *d_spec_bits = nullptr;
-    int bits_words_alloc = 0;
+    unsigned int *d_spec_reg = nullptr, *d_spec_touched = nullptr, *d_big_touched = nullptr;
+    LsdRect* d_pool_rect = nullptr;
+    unsigned short* d_claims = nullptr;
+    int* d_frame_counter = nullptr;
+    int bits_words = 0, num_sms = 0, growers_1cta = 0, growers_2cta = 0;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
     short *d_dx = nullptr, *d_dy = nullptr;
     ExactTab *d_xtab = nullptr, *d_ytab = nullptr;
@@ -1540,7 +1861,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     {
         const double rho = 2.0 / sin(kPiD * 22.5 / 180);
         dim3 grid((G.W + 63) / 64, (G.H + 3) / 4, nf);
-        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, h->d_cs, plane, rho, h->d_maxg2);
+        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, h->d_cs, h->d_cs0, plane, rho, h->d_maxg2);
         launches++;
     }
     if (prof) cudaEventRecord(h->ev[1], st);
@@ -1549,11 +1870,19 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     k_lsd_scatter<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_off, h->d_seeds);
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
-    const int bits_words = (int)((plane + 31) / 32);
-    PL_CUDA_TRY(cudaMemsetAsync(h->d_spec_bits, 0, sizeof(unsigned int) * (size_t)nf * kGrowers * bits_words, st));
-    k_lsd_grow<<<nf, kGrowThreads, 0, st>>>(G, h->d_ang, h->d_g2, h->d_used, h->d_reg, h->d_spec_reg, h->d_spec_touched, h->d_spec_bits, bits_words,
-                                            h->d_seeds, h->d_nseeds, h->d_cs, plane, h->d_queue, h->d_nrects, h->d_flags,
-                                            prof ? h->d_phase : nullptr);
+    {
+        // growers per CTA: few frames -> one CTA per SM with as many growers as shared memory holds (latency);
+        // more frames than SMs -> two CTAs per SM with half the growers each (throughput)
+        const bool two = nf > h->num_sms && h->growers_2cta > 0;
+        const int growers = two ? h->growers_2cta : h->growers_1cta;
+        const int ctas = std::min(nf, two ? 2 * h->num_sms : h->num_sms);
+        const size_t smem = kGrowCtaSmemFixed + (size_t)growers * ((size_t)h->bits_words * sizeof(unsigned int) + kGrowerSmemFixed);
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_claims, 0xff, sizeof(unsigned short) * plane * nf, st));
+        k_lsd_grow<<<ctas, growers * 32, smem, st>>>(G, nf, h->d_frame_counter, h->d_ang, h->d_g2, h->d_used, h->d_claims, h->d_reg,
+                                                     h->d_big_touched, h->d_spec_reg, h->d_spec_touched, h->d_pool_rect, h->bits_words, h->d_seeds, h->d_nseeds, h->d_cs, h->d_cs0, plane, h->d_queue,
+                                                     h->d_nrects, h->d_flags, prof ? h->d_phase : nullptr);
+    }
     k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
     launches += 2;
     if (prof) cudaEventRecord(h->ev[3], st);
@@ -1639,6 +1968,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_used, B * plane);
     A(&h->d_ang, B * plane);
     A(&h->d_cs, B * plane);
+    A(&h->d_cs0, B * plane);
     A(&h->d_nrects, B);
     A(&h->d_g2, B * plane);
     A(&h->d_reg, B * plane);
@@ -1654,10 +1984,43 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_qres, B * seg_cap);
     A(&h->d_queue, B * seg_cap);
     A(&h->d_qvalid, B * seg_cap);
-    h->bits_words_alloc = (int)((plane + 31) / 32);
-    A(&h->d_spec_reg, B * kGrowers * (size_t)kSpecCap);
-    A(&h->d_spec_touched, B * kGrowers * (size_t)kSpecCap);
-    A(&h->d_spec_bits, B * kGrowers * (size_t)h->bits_words_alloc);
+    h->bits_words = (int)((plane + 31) / 32);
+    {
+        cudaDeviceProp prop;
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+        if (e == cudaSuccess) {
+            h->num_sms = prop.multiProcessorCount;
+            // shared memory per grower: private bitmap + frontier ring; ~2 KB per CTA go to slots and the system
+            const size_t per = (size_t)h->bits_words * sizeof(unsigned int) + kGrowerSmemFixed;
+            const size_t cta_fixed = kGrowCtaSmemFixed + 512;  // window slots + static control block
+            const size_t one = prop.sharedMemPerBlockOptin > cta_fixed ? prop.sharedMemPerBlockOptin - cta_fixed : 0;
+            const size_t half = prop.sharedMemPerMultiprocessor / 2 > cta_fixed + 1024 ? prop.sharedMemPerMultiprocessor / 2 - cta_fixed - 1024 : 0;
+            h->growers_1cta = (int)std::min<size_t>(kMaxGrowers, one / per);
+            h->growers_2cta = (int)std::min<size_t>(kMaxGrowers / 2, half / per);
+            if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<1cta>,<2cta>"
+                int a = 0, b2 = 0;
+                if (sscanf(ev, "%d,%d", &a, &b2) == 2) {
+                    if (a >= 1 && a <= h->growers_1cta) h->growers_1cta = a;
+                    if (b2 >= 0 && b2 <= h->growers_2cta) h->growers_2cta = b2;
+                }
+            }
+            if (h->growers_1cta < 1) {
+                set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory per region grower, the device offers %zu", max_cols,
+                          max_rows, per, one);
+                pl_line_destroy(h);
+                return PL_ERR_CAPACITY;
+            }
+            if (h->growers_2cta < 1) h->growers_2cta = 0;
+            e = cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGrowCtaSmemFixed + h->growers_1cta * per));
+        }
+    }
+    const size_t max_ctas = std::min<size_t>(B, 2 * (size_t)std::max(h->num_sms, 1));
+    A(&h->d_spec_reg, max_ctas * kPool * (size_t)kSpecCap);
+    A(&h->d_spec_touched, max_ctas * kPool * (size_t)kSpecCap);
+    A(&h->d_pool_rect, max_ctas * kPool);
+    A(&h->d_claims, B * plane);
+    A(&h->d_big_touched, max_ctas * 2 * plane);
+    A(&h->d_frame_counter, 1);
     A(&h->d_resp, B * seg_cap);
     A(&h->d_dx, B * align_up((size_t)max_cols, 8) * max_rows);
     A(&h->d_dy, B * align_up((size_t)max_cols, 8) * max_rows);
@@ -1713,7 +2076,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_used, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_spec_bits, h->d_cs, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_claims, h->d_frame_counter, h->d_cs, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);

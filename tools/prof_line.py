@@ -60,5 +60,14 @@ for i in range(5):
 print("lines/frame", float(d_n.float().mean().item()), "launches", ex.last_launches())
 ph = np.zeros(8, np.int64)
 N.check(N.lib().pl_line_grow_phases(ex._h, C.c_int(0), N.ptr(ph)))
-print(f"grow kernel (frame 0): total {ph[1]/1e6:.1f} Mcycles, select {ph[0]/1e6:.1f}, validate {ph[2]/1e6:.1f}, rounds {ph[3]}, "
-      f"nfa-warp busy {ph[4]/1e6:.1f}, committed {ph[5]}, exclusive {ph[6]}, discarded {ph[7]}")
+if os.environ.get("PLSLAM_NVCC_EXTRA", "").find("PL_LSD_PROF3") >= 0:
+    print(f"PROF3 region_grow (frame 0, all calls, Mcycles): loads {ph[7]/1e6:.1f} | pass: hypothesis {ph[0]/1e6:.1f} prefix {ph[1]/1e6:.1f} "
+          f"atan2+verdict {ph[2]/1e6:.1f} commit {ph[3]/1e6:.1f}; batches {ph[4]} passes {ph[5]} pixels {ph[6]}")
+elif os.environ.get("PLSLAM_NVCC_EXTRA", "").find("PL_LSD_PROF2") >= 0:
+    print(f"PROF2 (frame 0): total {ph[1]/1e6:.1f} Mcycles x8 warps, rounds {ph[3]}, accepted pixels {ph[4]}, busy: grow {ph[5]/1e6:.1f} "
+          f"rect {ph[6]/1e6:.1f} refine {ph[7]/1e6:.1f} Mcycles (sum over warps)")
+else:
+    busy, regrow, aborted = ph[0] & 0xfffff, (ph[0] >> 20) & 0xfffff, ph[0] >> 40
+    print(f"grow kernel (frame 0): total {ph[1]/1e6:.1f} Mcycles; speculative growth {busy/1e3:.1f} Mcycles over all warps (given up: {aborted/1e3:.1f}), "
+          f"re-growth at commit {regrow/1e3:.1f}; tickets {ph[3]}, committed {ph[5]}, void {ph[7]} (fully grown: {ph[2] & 0xffffffff}, {ph[2] >> 32} logged pixels), "
+          f"deferred {ph[6]}, regrown {ph[4]}")
