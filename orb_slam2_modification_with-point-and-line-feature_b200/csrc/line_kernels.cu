@@ -280,14 +280,21 @@ struct LsdFrame {  // per-frame (and per-grower) device views
     const float2* cs;   // (cosf, sinf) of the angle
     const float2* cs0;  // (float(cos(double angle)), float(sin(double angle))): a seed's initial sums
     float2* sval;       // shared-memory staging of one warp, 36 entries
-    uint8_t* used;      // the committed USED map
+    const unsigned int* used_bits;  // the committed USED map: one bit per pixel, shared memory
     unsigned int* reg;  // region points, packed y<<16 | x
     unsigned int* ring; // shared-memory copy of reg[n - kRegRing .. n)
     int W, H;
-    // speculative growing: pixels this grower marks go to a private bitmap, every accepted pixel is logged
-    bool spec;
-    unsigned int* bits;     // private USED bitmap (W*H bits)
-    unsigned int* touched;  // log of accepted pixels (packed), capacity reg_cap
+    // The pixels a grower marks stay private until its region is committed.  Speculative growers keep them in a
+    // sparse bitmap in shared memory (a directory of 32x32-pixel tiles and a small pool of tile bitmaps); the
+    // commit-time re-growth, which has no size limit, uses a full bitmap in global memory.
+    bool sparse;
+    unsigned char* dir;   // [tiles] pool slot of the tile, 0xff = no pixel marked in it
+    unsigned short* rev;  // [pool_tiles] tile of a pool slot
+    unsigned int* pool;   // [pool_tiles][32] one word per tile row
+    int* ntiles;          // pool slots in use
+    int tw, pool_tiles;
+    unsigned int* bits;   // full private bitmap (W*H bits)
+    unsigned int* touched;  // log of accepted pixels (packed), capacity touched_cap
     int reg_cap;            // capacity of reg
     int touched_cap;        // capacity of touched
     // in-flight claims (a hint that saves wasted growth, never needed for correctness): every accepted pixel is
@@ -296,28 +303,62 @@ struct LsdFrame {  // per-frame (and per-grower) device views
     unsigned short* claims;
     int ticket;
     const volatile int* commit_head;
-#ifdef PL_LSD_PROF3
-    unsigned long long* prof;
-#endif
 };
-#ifdef PL_LSD_PROF3
-#define PROF3_T(v) const long long v = clock64()
-#define PROF3_ADD(k, x) pr[k] += (x)
-#else
-#define PROF3_T(v)
-#define PROF3_ADD(k, x)
-#endif
-__device__ __forceinline__ bool lsd_is_used(const LsdFrame& F, size_t o) {
-    if (F.used[o] != 0) return true;
-    return F.spec && ((F.bits[o >> 5] >> (o & 31)) & 1u);
+__device__ __forceinline__ bool lsd_committed(const LsdFrame& F, unsigned o) { return (F.used_bits[o >> 5] >> (o & 31)) & 1u; }
+__device__ __forceinline__ bool lsd_priv_test(const LsdFrame& F, int x, int y, unsigned o) {
+    if (!F.sparse) return (F.bits[o >> 5] >> (o & 31)) & 1u;
+    const unsigned d = F.dir[(y >> 5) * F.tw + (x >> 5)];
+    return d != 0xffu && ((F.pool[d * 32 + (y & 31)] >> (x & 31)) & 1u);
 }
-__device__ __forceinline__ void lsd_mark(const LsdFrame& F, size_t o) {
-    if (F.spec) atomicOr(&F.bits[o >> 5], 1u << (o & 31));
-    else F.used[o] = 1;
+// the tile must exist (lsd_priv_alloc)
+__device__ __forceinline__ void lsd_mark(const LsdFrame& F, int x, int y, unsigned o) {
+    if (!F.sparse) atomicOr(&F.bits[o >> 5], 1u << (o & 31));
+    else atomicOr(&F.pool[(unsigned)F.dir[(y >> 5) * F.tw + (x >> 5)] * 32 + (y & 31)], 1u << (x & 31));
 }
-__device__ __forceinline__ void lsd_unmark(const LsdFrame& F, size_t o) {
-    if (F.spec) atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
-    else F.used[o] = 0;
+// only called for pixels that are marked
+__device__ __forceinline__ void lsd_unmark(const LsdFrame& F, int x, int y, unsigned o) {
+    if (!F.sparse) atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
+    else atomicAnd(&F.pool[(unsigned)F.dir[(y >> 5) * F.tw + (x >> 5)] * 32 + (y & 31)], ~(1u << (x & 31)));
+}
+// warp-collective: makes sure the tiles of the lanes with `want` exist; false when the pool is exhausted
+__device__ __forceinline__ bool lsd_priv_alloc(const LsdFrame& F, bool want, int x, int y) {
+    if (!F.sparse) return true;
+    const int lane = threadIdx.x & 31;
+    const int t = want ? (y >> 5) * F.tw + (x >> 5) : -1;
+    unsigned need = __ballot_sync(0xffffffffu, want && F.dir[max(t, 0)] == 0xffu);
+    while (need) {
+        const int tj = __shfl_sync(0xffffffffu, t, __ffs(need) - 1);
+        const int k = *(volatile int*)F.ntiles;
+        if (k >= F.pool_tiles) return false;
+        F.pool[k * 32 + lane] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            F.dir[tj] = (unsigned char)k;
+            F.rev[k] = (unsigned short)tj;
+            *(volatile int*)F.ntiles = k + 1;
+        }
+        __syncwarp();
+        need &= ~__ballot_sync(0xffffffffu, t == tj);
+    }
+    return true;
+}
+// back to "nothing marked"; nt = entries of the touched log (every pixel ever marked is in it)
+__device__ __forceinline__ void lsd_priv_reset(const LsdFrame& F, int nt) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (F.sparse) {
+        const int k = *(volatile int*)F.ntiles;
+        for (int s2 = lane; s2 < k; s2 += 32) F.dir[F.rev[s2]] = 0xffu;
+        __syncwarp();
+        if (lane == 0) *(volatile int*)F.ntiles = 0;
+    } else {
+        for (int i = lane; i < nt; i += 32) {
+            const unsigned pp = F.touched[i];
+            const unsigned o = (pp >> 16) * (unsigned)F.W + (pp & 0xffffu);
+            atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
+        }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ double lsd_angle_diff_signed(double a, double b) {
@@ -368,7 +409,6 @@ struct GrowCand {
     int xx, yy;
     unsigned o;
     float adeg, ca, sa;
-    unsigned u;
     unsigned short claim;
     bool inb;
 };
@@ -384,37 +424,33 @@ __device__ __forceinline__ void lsd_issue_cand(const LsdFrame& F, int ri, int n,
     c.o = 0;
     c.adeg = kNotDefDeg;
     c.ca = c.sa = 0.f;
-    c.u = 1;
     c.claim = 0xffffu;
     if (c.inb) {
         c.o = (unsigned)c.yy * (unsigned)F.W + (unsigned)c.xx;
         c.adeg = F.ang[c.o];
-        c.u = F.used[c.o];
         c.claim = F.claims[c.o];
         const float2 c2 = F.cs[c.o];
         c.ca = c2.x;
         c.sa = c2.y;
     }
 }
-__device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, double* out_angle, int& nt) {
+__device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy, double prec, double* out_angle, int& nt) {
+    const LsdFrame F = Fin;  // in registers (the caller's copy may live in local memory)
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
-#ifdef PL_LSD_PROF3
-    long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-    PROF3_T(q0);
     const unsigned so = (unsigned)sy * (unsigned)F.W + (unsigned)sx;
     const float seed_deg = F.ang[so];
     const float2 c0 = F.cs0[so];
     float sumdx = c0.x, sumdy = c0.y;
     float hint = seed_deg;
     const float precdeg = (float)(prec * (180.0 / kPiD));
-    if (F.spec && nt >= F.touched_cap) return -1;
+    if (nt >= F.touched_cap) return -1;
+    if (!lsd_priv_alloc(F, lane == 0, sx, sy)) return -1;
     if (lane == 0) {
         F.reg[0] = ((unsigned)sy << 16) | (unsigned)sx;
         F.ring[0] = ((unsigned)sy << 16) | (unsigned)sx;
-        lsd_mark(F, (size_t)so);
-        if (F.spec) F.touched[nt] = ((unsigned)sy << 16) | (unsigned)sx;
+        lsd_mark(F, sx, sy, so);
+        F.touched[nt] = ((unsigned)sy << 16) | (unsigned)sx;
         F.claims[so] = (unsigned short)F.ticket;
     }
     nt++;
@@ -426,29 +462,29 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
     GrowCand cur, nxt;
     nxt.inb = false;
     while (i < n) {
-        PROF3_T(b0);
-        PROF3_ADD(4, 1);
         const int nb = min(4, n - i);
-        if (b < have) cur = nxt;
-        else if (b < nb) lsd_issue_cand(F, i + b, n, ddx, ddy, cur);
-        else cur.inb = false;
-        // the next batch's frontier points that exist already: issue their loads now
+        // the next batch's frontier points that exist already have their loads issued now (phase 1), so that they
+        // overlap the resolution of this batch; phase 0 loads what this batch did not get that way
         const int have_next = max(0, min(4, n - (i + 4)));
-        if (b < have_next) lsd_issue_cand(F, i + 4 + b, n, ddx, ddy, nxt);
-        bool cand = false;
-        if (cur.inb) {
-            if (!F.spec) cur.u = F.used[cur.o];  // exclusive growth marks the committed map itself
-            const bool priv = F.spec && ((F.bits[cur.o >> 5] >> (cur.o & 31)) & 1u);
-            cand = cur.adeg != kNotDefDeg && cur.u == 0 && !priv;
+#pragma unroll 1
+        for (int phase = 0; phase < 2; phase++) {
+            GrowCand tmp;
+            tmp.inb = false;
+            const bool act = phase == 0 ? (b >= have && b < nb) : (b < have_next);
+            if (act) lsd_issue_cand(F, i + 4 * phase + b, n, ddx, ddy, tmp);
+            if (phase == 0) {
+                if (b < have) cur = nxt;
+                else cur = tmp;
+            } else {
+                nxt = tmp;
+            }
         }
+        bool cand = false;
+        if (cur.inb) cand = cur.adeg != kNotDefDeg && !lsd_committed(F, cur.o) && !lsd_priv_test(F, cur.xx, cur.yy, cur.o);
         unsigned rem = __ballot_sync(FULL, cand);
-        PROF3_T(b1);
-        PROF3_ADD(7, b1 - b0);
         if (rem) {
             const unsigned grp = __match_any_sync(FULL, cand ? cur.o : (0x80000000u | (unsigned)lane));  // lanes on the same pixel
             while (rem) {
-                PROF3_ADD(5, 1);
-                PROF3_T(a0);
                 const bool inrem = (rem >> lane) & 1u;
                 // 1. hypothesis
                 float t = fabsf(hint - cur.adeg);
@@ -458,8 +494,6 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
                 const bool inH = hyp && !(grp & H & lt);  // a pixel seen by several lanes is accepted by the first
                 const unsigned H2 = __ballot_sync(FULL, inH);
                 const int c = __popc(H2 & lt), cmax = __popc(H2);
-                PROF3_T(a1);
-                PROF3_ADD(0, a1 - a0);
                 if (inH) F.sval[c] = make_float2(cur.ca, cur.sa);
                 __syncwarp();
                 // 2. the sums the reference holds on reaching this lane, if H2 happened
@@ -472,16 +506,12 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
                     if (k0 + 3 < c) { px = __fadd_rn(px, v3.x); py = __fadd_rn(py, v3.y); }
                 }
                 __syncwarp();
-                PROF3_T(a2);
-                PROF3_ADD(1, a2 - a1);
                 // the region angle is only defined by the sums after the first acceptance; before it, it is the seed's
                 const float th = (any || c > 0) ? fast_atan2_deg(py, px) : seed_deg;
                 bool v = false;
                 if (inrem && !(grp & H2 & lt)) v = lsd_aligned_deg(th, cur.adeg, precdeg, prec);
                 // 3. first lane whose verdict contradicts the hypothesis
                 const unsigned M = __ballot_sync(FULL, inrem && v != inH);
-                PROF3_T(a3);
-                PROF3_ADD(2, a3 - a2);
                 unsigned T = H2, resolved = FULL;
                 int hl = 31 - __clz(rem);
                 if (M) {
@@ -494,16 +524,17 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
                 hint = __shfl_sync(FULL, th, hl);
                 const int cnt = __popc(T);
                 if (cnt) {
-                    if (n + cnt > F.reg_cap || (F.spec && nt + cnt > F.touched_cap)) return -1;
+                    if (n + cnt > F.reg_cap || nt + cnt > F.touched_cap) return -1;
                     if (__any_sync(FULL, ((T >> lane) & 1u) && lsd_claim_hit(F, cur.claim))) return -2;
+                    if (!lsd_priv_alloc(F, (T >> lane) & 1u, cur.xx, cur.yy)) return -1;
                     if ((T >> lane) & 1u) {
                         F.claims[cur.o] = (unsigned short)F.ticket;
                         const int r = __popc(T & lt);
                         const unsigned pk = ((unsigned)cur.yy << 16) | (unsigned)cur.xx;
                         F.reg[n + r] = pk;
                         F.ring[(n + r) & (kRegRing - 1)] = pk;
-                        lsd_mark(F, (size_t)cur.o);
-                        if (F.spec) F.touched[nt + r] = pk;
+                        lsd_mark(F, cur.xx, cur.yy, cur.o);
+                        F.touched[nt + r] = pk;
                     }
                     // sums after the last accepted lane: its own prefix plus its own pixel
                     const int L = 31 - __clz(T);
@@ -515,20 +546,12 @@ __device__ int lsd_region_grow(const LsdFrame& F, int sx, int sy, double prec, d
                     rem &= ~__ballot_sync(FULL, (grp & T) != 0);
                 }
                 rem &= ~resolved;
-                PROF3_T(a4);
-                PROF3_ADD(3, a4 - a3);
             }
         }
         __syncwarp();
         i += nb;
         have = have_next;
     }
-#ifdef PL_LSD_PROF3
-    if (lane == 0 && F.prof) {
-        pr[6] = n;
-        for (int t = 0; t < 8; t++) atomicAdd(&F.prof[t], (unsigned long long)pr[t]);
-    }
-#endif
     *out_angle = any ? (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad : (double)seed_deg * kDegToRad;
     return n;
 }
@@ -553,14 +576,15 @@ __device__ __forceinline__ RegPt lsd_load_pt(const LsdFrame& F, int idx, int n) 
 }
 
 // region2rect() + get_theta()
-__device__ void lsd_region2rect(const LsdFrame& F, int n, double reg_angle, double prec, double p, LsdRect& rec) {
+__device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double reg_angle, double prec, double p, LsdRect& rec) {
+    const LsdFrame F = Fin;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     double x = 0, y = 0, sum = 0;
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);  // lanes beyond n hold zeros: adding +0.0 changes nothing
         const double pxw = __dmul_rn(pt.x, pt.w), pyw = __dmul_rn(pt.y, pt.w);
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < 32; j++) {
             x = __dadd_rn(x, __shfl_sync(FULL, pxw, j));
             y = __dadd_rn(y, __shfl_sync(FULL, pyw, j));
@@ -580,7 +604,7 @@ __device__ void lsd_region2rect(const LsdFrame& F, int n, double reg_angle, doub
             tyy = __dmul_rn(__dmul_rn(dx, dx), pt.w);
             txy = __dmul_rn(__dmul_rn(dx, dy), pt.w);
         }
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < 32; j++) {
             Ixx = __dadd_rn(Ixx, __shfl_sync(FULL, txx, j));
             Iyy = __dadd_rn(Iyy, __shfl_sync(FULL, tyy, j));
@@ -637,7 +661,7 @@ __device__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n, double reg_a
                 const unsigned q = F.reg[i];
                 const int qx = (int)(q & 0xffffu), qy = (int)(q >> 16);
                 if (lsd_dist_sq(xc, yc, (double)qx, (double)qy) > radSq) {
-                    lsd_unmark(F, (size_t)qy * F.W + qx);
+                    lsd_unmark(F, qx, qy, (unsigned)qy * (unsigned)F.W + (unsigned)qx);
                     F.reg[i] = F.reg[m - 1];
                     F.reg[m - 1] = q;
                     --m;
@@ -673,7 +697,7 @@ __device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double p
         bool inside = false;
         double ang_d = 0, ang_d2 = 0;
         if (base + lane < n) {
-            lsd_unmark(F, (size_t)(int)pt.y * F.W + (int)pt.x);
+            lsd_unmark(F, (int)pt.x, (int)pt.y, (unsigned)(int)pt.y * (unsigned)F.W + (unsigned)(int)pt.x);
             inside = sqrt(lsd_dist_sq(xc, yc, pt.x, pt.y)) < rec.width;
             if (inside) {
                 ang_d = lsd_angle_diff_signed((double)pt.adeg * kDegToRad, ang_c);
@@ -681,7 +705,7 @@ __device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double p
             }
         }
         cnt_in += __popc(__ballot_sync(FULL, inside));
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < 32; j++) {  // points outside contribute +0.0
             sum = __dadd_rn(sum, __shfl_sync(FULL, ang_d, j));
             s_sum = __dadd_rn(s_sum, __shfl_sync(FULL, ang_d2, j));
@@ -977,23 +1001,42 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
 constexpr int kMaxGrowers = 8;
 constexpr int kSlots = 512;  // window of uncommitted tickets
 constexpr int kPool = 64;    // region buffers per CTA
+constexpr int kSmall = 64;   // regions up to this size (and log length) are parked in their slot's small buffer instead
 constexpr int kSvalEntries = 36;
-constexpr size_t kGrowerSmemFixed = kRegRing * sizeof(unsigned int) + kSvalEntries * sizeof(float2);
-constexpr size_t kGrowCtaSmemFixed = kSlots * sizeof(int4);
+constexpr int kMaxPoolTiles = 64, kMinPoolTiles = 24;
 struct LsdQueueItem { LsdRect rec; };
+// shared memory of a grower warp: sval | ring | tile pool | rev | dir | ntiles, each part 16-byte aligned
+struct GrowSmem {
+    int tiles, pool_tiles;
+    int window;  // tickets that may be uncommitted at once (<= kSlots): deeper speculation wastes more growth
+    __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
+    __host__ __device__ size_t off_pool() const { return off_ring() + kRegRing * sizeof(unsigned int); }
+    __host__ __device__ size_t off_rev() const { return off_pool() + (size_t)pool_tiles * 32 * sizeof(unsigned int); }
+    __host__ __device__ size_t off_dir() const { return off_rev() + (((size_t)pool_tiles * sizeof(unsigned short) + 15) & ~(size_t)15); }
+    __host__ __device__ size_t off_ntiles() const { return off_dir() + (((size_t)tiles + 15) & ~(size_t)15); }
+    __host__ __device__ size_t per_grower() const { return off_ntiles() + 16; }
+};
+// shared memory of the CTA: window slots | committed bitmap | growers
+__host__ __device__ inline size_t grow_cta_fixed_smem(int bits_words) {
+    return kSlots * sizeof(int4) + (((size_t)bits_words * sizeof(unsigned int) + 15) & ~(size_t)15);
+}
 // window slot (shared memory, int4): x = seed pixel, y = region size, z = touched-log size,
-// w = state | (status + 2) << 8 | (buffer + 1) << 16
-enum { kSlotFree = 0, kSlotGrowing = 1, kSlotDone = 2 };
+// w = state | (status + 2) << 8 | (buffer + 1) << 16   (buffer -1 with status >= 0: the slot's small buffer)
+enum { kSlotFree = 0, kSlotReady = 1, kSlotGrowing = 2, kSlotDone = 3 };
+enum { kActNone = 0, kActCommit, kActIssue, kActTake, kActBuffer, kActExit };
 enum { kStDeferred = -2, kStCapacity = -1, kStNoRect = 0, kStRect = 1 };
 __device__ __forceinline__ int slot_pack(int state, int status, int buf) { return state | ((status + 2) << 8) | ((buf + 1) << 16); }
 struct GrowCtl {
     int sel_lock, com_lock;
-    int next_pos, ticket_next, commit_head;
-    int head;        // rectangles queued
-    int all_issued;  // the seed list is exhausted
+    int next_pos;     // next position of the seed list to look at
+    int ticket_next;  // tickets issued
+    int grow_next;    // tickets handed to a grower
+    int commit_head;  // tickets committed
+    int head;         // rectangles queued
+    int all_issued;   // the seed list is exhausted
     int frame;
     unsigned long long free_mask;  // free buffers of the pool
-    unsigned long long stat[8];    // committed, void, regrown, deferred, busy cycles, void cycles, idle polls, regrow cycles
+    unsigned long long stat[8];    // committed, void, regrown, deferred, growth cycles, given-up cycles, -, regrow cycles
 };
 struct GrowResult {
     int status, n, nt;
@@ -1026,10 +1069,9 @@ __device__ __forceinline__ int pool_pop(unsigned long long* mask, int lane) {
     }
     return __shfl_sync(0xffffffffu, b, 0);
 }
-// grow + fit + refine one seed into the buffers of F; leaves F.bits clean
+// grow + fit + refine one seed into the buffers of F; leaves the private marks clean
 __device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min_reg_size, GrowResult* out) {
     const LsdFrame F = Fin;  // a private copy the compiler keeps in registers (the caller's lives in local memory)
-    const int lane = threadIdx.x & 31;
     const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
     const double density_th = 0.7;
     const int sx = pix % F.W, sy = pix / F.W;
@@ -1043,13 +1085,7 @@ __device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min
         lsd_region2rect(F, n, reg_angle, prec, p, rec);
         status = lsd_refine(F, n, reg_angle, prec, p, rec, density_th, nt);
     }
-    __syncwarp();
-    // the private bitmap goes back to all-zero: every pixel ever marked is in the log
-    for (int i = lane; i < nt; i += 32) {
-        const unsigned pp = F.touched[i];
-        const unsigned o = (pp >> 16) * (unsigned)F.W + (pp & 0xffffu);
-        atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
-    }
+    lsd_priv_reset(F, nt);
     out->status = status;
     out->n = n;
     out->nt = nt;
@@ -1057,83 +1093,102 @@ __device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, int nf, int* __restrict__ frame_counter,
+__global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, int* __restrict__ frame_counter,
                                                                   const float* __restrict__ angdeg, const int* __restrict__ g2,
-                                                                  uint8_t* __restrict__ used, unsigned short* __restrict__ claims,
-                                                                  unsigned int* __restrict__ big_reg, unsigned int* __restrict__ big_touched,
+                                                                  unsigned short* __restrict__ claims, unsigned int* __restrict__ big_reg,
+                                                                  unsigned int* __restrict__ big_touched, unsigned int* __restrict__ big_bits,
                                                                   unsigned int* __restrict__ pool_reg, unsigned int* __restrict__ pool_touched,
-                                                                  LsdRect* __restrict__ pool_rect, int bits_words,
+                                                                  LsdRect* __restrict__ pool_rect, unsigned int* __restrict__ small_buf,
+                                                                  LsdRect* __restrict__ small_rect, int bits_words,
                                                                   const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
                                                                   const float2* __restrict__ cs, const float2* __restrict__ cs0, size_t plane,
                                                                   LsdQueueItem* __restrict__ queue, int* __restrict__ n_rects,
                                                                   int* __restrict__ flags, long long* __restrict__ phase_cycles) {
-    extern __shared__ __align__(16) unsigned int s_dyn[];
+    extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ GrowCtl s_ctl;
-#ifdef PL_LSD_PROF3
-    __shared__ unsigned long long s_prof3[8];
-    if (threadIdx.x < 8) s_prof3[threadIdx.x] = 0;
-#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_dyn);                      // [kSlots]
-    float2* s_val = reinterpret_cast<float2*>(s_dyn + kSlots * 4);                        // [G][kSvalEntries]
-    unsigned int* s_ring = s_dyn + kSlots * 4 + (size_t)G * kSvalEntries * 2;             // [G][kRegRing]
-    unsigned int* s_bits = s_ring + (size_t)G * kRegRing;                                 // [G][bits_words] private USED bitmaps
-    for (int i = threadIdx.x; i < G * bits_words; i += blockDim.x) s_bits[i] = 0;
+    volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_raw);                         // [kSlots]
+    unsigned int* s_used = reinterpret_cast<unsigned int*>(s_raw + kSlots * sizeof(int4));   // committed USED bitmap
+    unsigned char* s_mine = s_raw + grow_cta_fixed_smem(bits_words) + (size_t)warp * gs.per_grower();
     volatile GrowCtl* ctl = &s_ctl;
     unsigned int* my_pool_reg = pool_reg + (size_t)blockIdx.x * kPool * kSpecCap;
     unsigned int* my_pool_touched = pool_touched + (size_t)blockIdx.x * kPool * kSpecCap;
     LsdRect* my_pool_rect = pool_rect + (size_t)blockIdx.x * kPool;
+    unsigned int* my_big_bits = big_bits + (size_t)blockIdx.x * bits_words;  // all-zero between uses
+    unsigned int* my_small = small_buf + (size_t)blockIdx.x * kSlots * 2 * kSmall;  // [kSlots][reg kSmall | touched kSmall]
+    LsdRect* my_small_rect = small_rect + (size_t)blockIdx.x * kSlots;
+    LsdFrame F;
+    F.sval = reinterpret_cast<float2*>(s_mine);
+    F.ring = reinterpret_cast<unsigned int*>(s_mine + gs.off_ring());
+    F.pool = reinterpret_cast<unsigned int*>(s_mine + gs.off_pool());
+    F.rev = reinterpret_cast<unsigned short*>(s_mine + gs.off_rev());
+    F.dir = s_mine + gs.off_dir();
+    F.ntiles = reinterpret_cast<int*>(s_mine + gs.off_ntiles());
+    F.tw = (g.W + 31) >> 5;
+    F.pool_tiles = gs.pool_tiles;
+    F.sparse = true;
+    F.bits = nullptr;
+    F.used_bits = s_used;
+    F.commit_head = &s_ctl.commit_head;
+    F.ticket = 0;
+    F.W = g.W;
+    F.H = g.H;
+    F.reg = nullptr;
+    F.touched = nullptr;
+    F.reg_cap = F.touched_cap = 0;
+    for (int i = lane; i < gs.tiles; i += 32) F.dir[i] = 0xffu;
+    if (lane == 0) *F.ntiles = 0;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) {
             s_ctl.frame = atomicAdd(frame_counter, 1);
             s_ctl.sel_lock = s_ctl.com_lock = 0;
-            s_ctl.next_pos = s_ctl.ticket_next = s_ctl.commit_head = 0;
+            s_ctl.next_pos = s_ctl.ticket_next = s_ctl.grow_next = s_ctl.commit_head = 0;
             s_ctl.head = 0;
             s_ctl.all_issued = 0;
             s_ctl.free_mask = ~0ull << G;  // buffer w starts with warp w
             for (int k = 0; k < 8; k++) s_ctl.stat[k] = 0;
         }
         for (int i = threadIdx.x; i < kSlots; i += blockDim.x) s_slot[i].w = slot_pack(kSlotFree, 0, -1);
+        for (int i = threadIdx.x; i < bits_words; i += blockDim.x) s_used[i] = 0;
         __syncthreads();
         const int f = s_ctl.frame;
         if (f >= nf) break;
-        LsdFrame F;
         F.ang = angdeg + (size_t)f * plane;
         F.g2 = g2 + (size_t)f * plane;
         F.cs = cs + (size_t)f * plane;
         F.cs0 = cs0 + (size_t)f * plane;
-        F.sval = s_val + warp * kSvalEntries;
-        F.used = used + (size_t)f * plane;
         F.claims = claims + (size_t)f * plane;
-        F.commit_head = &s_ctl.commit_head;
-        F.ticket = 0;
-        F.W = g.W;
-        F.H = g.H;
-        F.spec = true;
-        F.bits = s_bits + (size_t)warp * bits_words;
-        F.ring = s_ring + warp * kRegRing;
-        F.reg = nullptr;
-        F.touched = nullptr;
-        F.reg_cap = F.touched_cap = 0;
-#ifdef PL_LSD_PROF3
-        F.prof = s_prof3;
-#endif
-        volatile uint8_t* vused = F.used;
+        const volatile unsigned int* vused = s_used;
         const volatile unsigned short* vclaims = F.claims;
         LsdQueueItem* q = queue + (size_t)f * g.seg_cap;
         const unsigned int* sd = seeds + (size_t)f * plane;
         const int ns = n_seeds[f];
         const long long tstart = clock64();
-        long long t_com = 0;
+        long long t_com = 0, t_sel = 0;
         int mybuf = warp;
         GrowResult res;
         while (true) {
-            bool progressed = false;
+            // ---------------- what to do next (a tight loop: idle warps must not thrash the instruction cache) ----------------
+            int action = kActNone;
+            while (true) {
+                if (lane == 0) {
+                    const int h = ctl->commit_head, tn = ctl->ticket_next, gn = ctl->grow_next, ai = ctl->all_issued;
+                    if (ai && h == tn) action = kActExit;
+                    else if (h < tn && (s_slot[h % kSlots].w & 0xff) == kSlotDone && ctl->com_lock == 0) action = kActCommit;
+                    else if (mybuf >= 0 && gn < tn) action = kActTake;
+                    else if (!ai && tn - gn < 2 * G && tn - h < gs.window && ctl->sel_lock == 0) action = kActIssue;
+                    else if (mybuf < 0 && ctl->free_mask != 0) action = kActBuffer;
+                }
+                action = __shfl_sync(FULL, action, 0);
+                if (action != kActNone) break;
+                __nanosleep(256);
+            }
+            if (action == kActExit) break;
+            if (action == kActBuffer) mybuf = pool_pop(&s_ctl.free_mask, lane);
             // ---------------- commit duty: strictly in ticket order ----------------
-            if (WARP_UNIFORM(ctl->commit_head < ctl->ticket_next && (s_slot[ctl->commit_head % kSlots].w & 0xff) == kSlotDone) &&
-                warp_try_lock(&s_ctl.com_lock, lane)) {
+            if (action == kActCommit && warp_try_lock(&s_ctl.com_lock, lane)) {
                 const long long t0 = clock64();
                 while (true) {
                     const int h = __shfl_sync(FULL, ctl->commit_head, 0);
@@ -1144,18 +1199,18 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, in
                     int n = sl->y, nt = sl->z, status = ((w >> 8) & 0xff) - 2;
                     const int buf = ((w >> 16) & 0xff) - 1;
                     int kind = 0;  // 0 committed, 1 void
-                    if (vused[pix] != 0) {
+                    if ((vused[pix >> 5] >> (pix & 31)) & 1u) {
                         kind = 1;  // swallowed by an earlier region
-                        if (lane == 0 && buf >= 0) s_ctl.stat[6] += (unsigned long long)nt << 32 | 1ull;
                     } else {
-                        const unsigned int* rg = my_pool_reg + (size_t)max(buf, 0) * kSpecCap;
+                        const unsigned int* rg = buf >= 0 ? my_pool_reg + (size_t)buf * kSpecCap : my_small + (size_t)(h % kSlots) * 2 * kSmall;
                         bool redo = status < 0;
                         if (!redo) {
-                            const unsigned int* tk = my_pool_touched + (size_t)buf * kSpecCap;
+                            const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
                             bool conflict = false;
                             for (int i = lane; i < nt; i += 32) {
                                 const unsigned pp = tk[i];
-                                conflict |= vused[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] != 0;
+                                const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
+                                conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
                             }
                             redo = __any_sync(FULL, conflict);
                         }
@@ -1163,6 +1218,8 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, in
                         if (redo) {  // everything before this ticket is committed: this growth is the sequential one
                             const long long g0 = clock64();
                             LsdFrame FS = F;
+                            FS.sparse = false;
+                            FS.bits = my_big_bits;
                             FS.reg = big_reg + (size_t)f * plane;
                             FS.touched = big_touched + (size_t)blockIdx.x * 2 * plane;
                             FS.reg_cap = (int)plane;
@@ -1179,12 +1236,13 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, in
                                 s_ctl.stat[7] += (unsigned long long)(clock64() - g0);
                             }
                         } else if (status == kStRect) {
-                            rec = my_pool_rect[buf];
+                            rec = buf >= 0 ? my_pool_rect[buf] : my_small_rect[h % kSlots];
                         }
                         if (status >= 0) {
                             for (int i = lane; i < n; i += 32) {
                                 const unsigned pp = rg[i];
-                                F.used[(size_t)(pp >> 16) * g.W + (pp & 0xffffu)] = 1;
+                                const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
+                                atomicOr(&s_used[o >> 5], 1u << (o & 31));
                             }
                             if (status == kStRect) {
                                 const int head = __shfl_sync(FULL, ctl->head, 0);
@@ -1212,97 +1270,108 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, in
                 }
                 t_com += clock64() - t0;
                 warp_unlock(&s_ctl.com_lock, lane);
-                progressed = true;
             }
-            if (mybuf < 0) mybuf = pool_pop(&s_ctl.free_mask, lane);
-            // ---------------- next seed ----------------
-            int my_ticket = -1, my_pix = 0;
-            if (mybuf >= 0 && WARP_UNIFORM(!ctl->all_issued && ctl->ticket_next - ctl->commit_head < kSlots) &&
-                warp_try_lock(&s_ctl.sel_lock, lane)) {
+            // ---------------- issue tickets: one chunk of the seed list at a time ----------------
+            if (action == kActIssue && warp_try_lock(&s_ctl.sel_lock, lane)) {
+                const long long t0 = clock64();
                 int t = __shfl_sync(FULL, ctl->ticket_next, 0);
                 int pos = __shfl_sync(FULL, ctl->next_pos, 0);
-                bool exhausted = false;
-                while (my_ticket < 0 && pos < ns) {
+                bool full = false;
+                while (!full && pos < ns && t - __shfl_sync(FULL, ctl->grow_next, 0) < 2 * G) {
                     const int idx = pos + lane;
                     unsigned pix = 0;
                     bool free_ = false;
-                    unsigned short cl = 0xffffu;
                     if (idx < ns) {
                         pix = sd[idx];
-                        free_ = vused[pix] == 0;
-                        cl = vclaims[pix];
+                        free_ = ((vused[pix >> 5] >> (pix & 31)) & 1u) == 0;
                     }
                     unsigned m = __ballot_sync(FULL, free_);
                     int consumed = 32;  // seeds of this chunk that are dealt with
                     while (m) {
-                        const int room = __shfl_sync(FULL, kSlots - (t - ctl->commit_head), 0);
+                        const int room = __shfl_sync(FULL, gs.window - (t - ctl->commit_head), 0);
                         const int j = __ffs(m) - 1;
-                        if (room <= 0) { consumed = j; exhausted = true; break; }
+                        if (room <= 0) { consumed = j; full = true; break; }
                         m &= m - 1;
                         const unsigned pj = __shfl_sync(FULL, pix, j);
-                        const unsigned short cj = (unsigned short)__shfl_sync(FULL, (unsigned)cl, j);
-                        // stamped by an uncommitted earlier ticket: most likely swallowed, do not grow it now
-                        const unsigned d = (unsigned)(t - (int)cj) & 0xffffu;
-                        const bool defer = WARP_UNIFORM(d != 0 && d <= (unsigned)(t - ctl->commit_head));
                         if (lane == 0) {
                             volatile int4* sl = &s_slot[t % kSlots];
                             sl->x = (int)pj;
                             sl->y = 0;
                             sl->z = 0;
-                            __threadfence_block();
-                            sl->w = defer ? slot_pack(kSlotDone, kStDeferred, -1) : slot_pack(kSlotGrowing, 0, -1);
+                            sl->w = slot_pack(kSlotReady, 0, -1);
                             __threadfence_block();
                             s_ctl.ticket_next = t + 1;
-                            if (defer) s_ctl.stat[3]++;
                         }
                         t++;
-                        if (!defer) {
-                            my_ticket = t - 1;
-                            my_pix = (int)pj;
-                            consumed = j + 1;
-                            break;
-                        }
                     }
                     pos += consumed;
-                    if (exhausted) break;
                 }
                 if (lane == 0) {
                     s_ctl.next_pos = min(pos, ns);
-                    if (pos >= ns && !exhausted && my_ticket < 0) s_ctl.all_issued = 1;
-                    if (pos >= ns && my_ticket >= 0) {
-                        // the chunk ended exactly at the list end: the next selector finds pos >= ns and closes the list
+                    if (pos >= ns && !full) s_ctl.all_issued = 1;
+                }
+                t_sel += clock64() - t0;
+                warp_unlock(&s_ctl.sel_lock, lane);
+            }
+            // ---------------- take the next ticket ----------------
+            int my_ticket = -1;
+            if (action == kActTake) {
+                if (lane == 0) {
+                    while (true) {
+                        const int t = ctl->grow_next;
+                        if (t >= ctl->ticket_next) break;
+                        if (atomicCAS(&s_ctl.grow_next, t, t + 1) == t) { my_ticket = t; break; }
                     }
                 }
-                warp_unlock(&s_ctl.sel_lock, lane);
-                progressed = true;
+                my_ticket = __shfl_sync(FULL, my_ticket, 0);
             }
             // ---------------- speculative growth ----------------
             if (my_ticket >= 0) {
-                LsdFrame FS = F;
-                FS.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
-                FS.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
-                FS.reg_cap = FS.touched_cap = kSpecCap;
-                FS.ticket = my_ticket;
                 volatile int4* sl = &s_slot[my_ticket % kSlots];
-                const long long g0 = clock64();
-                lsd_grow_seed(FS, my_pix, g.min_reg_size, &res);
-                const bool keep = res.status >= 0;  // the buffer stays with the slot until it is committed
-                if (lane == 0) {
-                    atomicAdd(&s_ctl.stat[4], (unsigned long long)(clock64() - g0));
-                    if (res.status < 0) atomicAdd(&s_ctl.stat[5], (unsigned long long)(clock64() - g0));
-                    if (res.status == kStRect) my_pool_rect[mybuf] = res.rec;
-                    sl->y = res.n;
-                    sl->z = res.nt;
-                    __threadfence_block();
-                    sl->w = slot_pack(kSlotDone, res.status, keep ? mybuf : -1);
+                const int my_pix = sl->x;
+                // already swallowed, or stamped by an uncommitted earlier ticket (most likely being swallowed):
+                // not grown now; the committer decides when its turn comes
+                const unsigned short cl = vclaims[my_pix];
+                const unsigned d = (unsigned)(my_ticket - (int)cl) & 0xffffu;
+                const bool defer = WARP_UNIFORM((((vused[my_pix >> 5] >> (my_pix & 31)) & 1u) != 0) ||
+                                                (d != 0 && d <= (unsigned)(my_ticket - ctl->commit_head)));
+                if (defer) {
+                    if (lane == 0) {
+                        s_ctl.stat[3]++;  // (racy counter, profiling only)
+                        __threadfence_block();
+                        sl->w = slot_pack(kSlotDone, kStDeferred, -1);
+                    }
+                } else {
+                    LsdFrame FS = F;
+                    FS.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
+                    FS.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
+                    FS.reg_cap = FS.touched_cap = kSpecCap;
+                    FS.ticket = my_ticket;
+                    const long long g0 = clock64();
+                    lsd_grow_seed(FS, my_pix, g.min_reg_size, &res);
+                    // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer
+                    const bool small = res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
+                    const bool keep = res.status >= 0 && !small;
+                    if (small) {
+                        unsigned int* dst = my_small + (size_t)(my_ticket % kSlots) * 2 * kSmall;
+                        for (int i = lane; i < res.n; i += 32) dst[i] = FS.reg[i];
+                        for (int i = lane; i < res.nt; i += 32) dst[kSmall + i] = FS.touched[i];
+                        if (lane == 0 && res.status == kStRect) my_small_rect[my_ticket % kSlots] = res.rec;
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        atomicAdd(&s_ctl.stat[4], (unsigned long long)(clock64() - g0));
+                        if (res.status < 0) atomicAdd(&s_ctl.stat[5], (unsigned long long)(clock64() - g0));
+                        if (keep && res.status == kStRect) my_pool_rect[mybuf] = res.rec;
+                        sl->y = res.n;
+                        sl->z = res.nt;
+                        __threadfence_block();
+                        sl->w = slot_pack(kSlotDone, res.status, keep ? mybuf : -1);
+                    }
+                    __syncwarp();
+                    if (keep) mybuf = pool_pop(&s_ctl.free_mask, lane);
                 }
                 __syncwarp();
-                if (keep) mybuf = pool_pop(&s_ctl.free_mask, lane);
-                progressed = true;
-            }
-            if (WARP_UNIFORM(ctl->all_issued && ctl->commit_head == ctl->ticket_next)) break;
-            if (!progressed) {
-                __nanosleep(200);
             }
         }
         __syncthreads();
@@ -1311,17 +1380,13 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, in
             if (phase_cycles) {
                 long long* pc = phase_cycles + (size_t)f * 8;
                 pc[0] = (long long)((s_ctl.stat[4] / 1000) + ((s_ctl.stat[7] / 1000) << 20) + ((s_ctl.stat[5] / 1000) << 40));
-                pc[2] = (long long)s_ctl.stat[6];
                 pc[1] = clock64() - tstart;
-                pc[2] = t_com;
+                pc[2] = (t_com / 1000) | ((t_sel / 1000) << 32);  // warp 0's share
                 pc[3] = s_ctl.ticket_next;
                 pc[4] = (long long)s_ctl.stat[2];
                 pc[5] = (long long)s_ctl.stat[0];
                 pc[6] = (long long)s_ctl.stat[3];
                 pc[7] = (long long)s_ctl.stat[1];
-#ifdef PL_LSD_PROF3
-                for (int k = 0; k < 8; k++) pc[k] = (long long)s_prof3[k];
-#endif
             }
         }
     }
@@ -1337,13 +1402,11 @@ __global__ void __launch_bounds__(kNfaThreads) k_lsd_nfa(LineGeom g, const float
     const int wid = blockIdx.x * (kNfaThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kNfaThreads / 32);
     LsdFrame F;
     F.ang = angdeg + (size_t)f * plane;
-    F.g2 = nullptr; F.cs = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used = nullptr; F.reg = nullptr; F.ring = nullptr;
+    F.g2 = nullptr; F.cs = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
     F.W = g.W; F.H = g.H;
-    F.spec = false; F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
+    F.sparse = false; F.dir = nullptr; F.rev = nullptr; F.pool = nullptr; F.ntiles = nullptr; F.tw = 0; F.pool_tiles = 0;
+    F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
     F.claims = nullptr; F.ticket = 0; F.commit_head = nullptr;
-#ifdef PL_LSD_PROF3
-    F.prof = nullptr;
-#endif
     const int n = min(n_rects[f], g.seg_cap);
     const double log_eps = 0.0;
     for (int t = wid; t < n; t += nw) {
@@ -1729,7 +1792,7 @@ struct pl_line {
     LbdTabs tabs;
     size_t plane = 0, scaled_stride = 0;
     // device buffers (sized for max_cols x max_rows x max_batch at creation)
-    uint8_t *d_in = nullptr, *d_scaled = nullptr, *d_used = nullptr, *d_blur5 = nullptr;
+    uint8_t *d_in = nullptr, *d_scaled = nullptr, *d_blur5 = nullptr;
     float* d_ang = nullptr;
     float2 *d_cs = nullptr, *d_cs0 = nullptr;
     int* d_nrects = nullptr;
@@ -1742,10 +1805,12 @@ struct pl_line {
     LsdQueueItem* d_queue = nullptr;
     uint8_t* d_qvalid = nullptr;
     unsigned int *d_spec_reg = nullptr, *d_spec_touched = nullptr, *d_big_touched = nullptr;
-    LsdRect* d_pool_rect = nullptr;
+    LsdRect *d_pool_rect = nullptr, *d_small_rect = nullptr;
+    unsigned int* d_small_buf = nullptr;
     unsigned short* d_claims = nullptr;
     int* d_frame_counter = nullptr;
-    int bits_words = 0, num_sms = 0, growers_1cta = 0, growers_2cta = 0;
+    int bits_words = 0, num_sms = 0, growers_1cta = 0, growers_2cta = 0, pool_tiles_1cta = 0, pool_tiles_2cta = 0, grow_tiles = 0, grow_window = 64;
+    unsigned int* d_big_bits = nullptr;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
     short *d_dx = nullptr, *d_dy = nullptr;
     ExactTab *d_xtab = nullptr, *d_ytab = nullptr;
@@ -1850,7 +1915,6 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     int launches = 0;
     const bool prof = h->profiling;
     PL_CUDA_TRY(cudaMemsetAsync(h->d_maxg2, 0xff, sizeof(int) * nf, st));  // -1
-    PL_CUDA_TRY(cudaMemsetAsync(h->d_used, 0, plane * nf, st));
     PL_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * nf, st));
     if (prof) cudaEventRecord(h->ev[0], st);
     {
@@ -1875,13 +1939,15 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         // more frames than SMs -> two CTAs per SM with half the growers each (throughput)
         const bool two = nf > h->num_sms && h->growers_2cta > 0;
         const int growers = two ? h->growers_2cta : h->growers_1cta;
+        const GrowSmem gs{h->grow_tiles, two ? h->pool_tiles_2cta : h->pool_tiles_1cta, h->grow_window};
         const int ctas = std::min(nf, two ? 2 * h->num_sms : h->num_sms);
-        const size_t smem = kGrowCtaSmemFixed + (size_t)growers * ((size_t)h->bits_words * sizeof(unsigned int) + kGrowerSmemFixed);
+        const size_t smem = grow_cta_fixed_smem(h->bits_words) + (size_t)growers * gs.per_grower();
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_claims, 0xff, sizeof(unsigned short) * plane * nf, st));
-        k_lsd_grow<<<ctas, growers * 32, smem, st>>>(G, nf, h->d_frame_counter, h->d_ang, h->d_g2, h->d_used, h->d_claims, h->d_reg,
-                                                     h->d_big_touched, h->d_spec_reg, h->d_spec_touched, h->d_pool_rect, h->bits_words, h->d_seeds, h->d_nseeds, h->d_cs, h->d_cs0, plane, h->d_queue,
-                                                     h->d_nrects, h->d_flags, prof ? h->d_phase : nullptr);
+        k_lsd_grow<<<ctas, growers * 32, smem, st>>>(G, gs, nf, h->d_frame_counter, h->d_ang, h->d_g2, h->d_claims, h->d_reg, h->d_big_touched,
+                                                     h->d_big_bits, h->d_spec_reg, h->d_spec_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->bits_words, h->d_seeds,
+                                                     h->d_nseeds, h->d_cs, h->d_cs0, plane, h->d_queue, h->d_nrects, h->d_flags,
+                                                     prof ? h->d_phase : nullptr);
     }
     k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
     launches += 2;
@@ -1965,7 +2031,6 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_in, B * in_pitch * max_rows);
     A(&h->d_blur5, B * in_pitch * max_rows);
     A(&h->d_scaled, B * align_up((size_t)W, 16) * H);
-    A(&h->d_used, B * plane);
     A(&h->d_ang, B * plane);
     A(&h->d_cs, B * plane);
     A(&h->d_cs0, B * plane);
@@ -1990,36 +2055,56 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
         if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
         if (e == cudaSuccess) {
             h->num_sms = prop.multiProcessorCount;
-            // shared memory per grower: private bitmap + frontier ring; ~2 KB per CTA go to slots and the system
-            const size_t per = (size_t)h->bits_words * sizeof(unsigned int) + kGrowerSmemFixed;
-            const size_t cta_fixed = kGrowCtaSmemFixed + 512;  // window slots + static control block
-            const size_t one = prop.sharedMemPerBlockOptin > cta_fixed ? prop.sharedMemPerBlockOptin - cta_fixed : 0;
-            const size_t half = prop.sharedMemPerMultiprocessor / 2 > cta_fixed + 1024 ? prop.sharedMemPerMultiprocessor / 2 - cta_fixed - 1024 : 0;
-            h->growers_1cta = (int)std::min<size_t>(kMaxGrowers, one / per);
-            h->growers_2cta = (int)std::min<size_t>(kMaxGrowers / 2, half / per);
+            // shared memory: window slots + committed bitmap per CTA, and per grower the ring, the staging area and the
+            // sparse private bitmap (a pool of 32x32-pixel tiles: as many as fit, the more the fewer regions overflow)
+            const int tiles = ((W + 31) / 32) * ((H + 31) / 32);
+            const size_t fixed = grow_cta_fixed_smem(h->bits_words) + 512;  // + static control block
+            auto choose = [&](size_t budget, int max_g, int* g_out, int* p_out) {
+                *g_out = 0;
+                *p_out = 0;
+                for (int gN = max_g; gN >= 1 && *g_out == 0; gN--)
+                    for (int pN = kMaxPoolTiles; pN >= kMinPoolTiles; pN -= 8) {
+                        GrowSmem gs{tiles, pN, 0};
+                        if (fixed + (size_t)gN * gs.per_grower() <= budget) {
+                            *g_out = gN;
+                            *p_out = pN;
+                            break;
+                        }
+                    }
+            };
+            int want1 = kMaxGrowers, want2 = kMaxGrowers;
             if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<1cta>,<2cta>"
                 int a = 0, b2 = 0;
                 if (sscanf(ev, "%d,%d", &a, &b2) == 2) {
-                    if (a >= 1 && a <= h->growers_1cta) h->growers_1cta = a;
-                    if (b2 >= 0 && b2 <= h->growers_2cta) h->growers_2cta = b2;
+                    if (a >= 1 && a <= kMaxGrowers) want1 = a;
+                    if (b2 >= 0 && b2 <= kMaxGrowers) want2 = b2;
                 }
             }
+            choose(prop.sharedMemPerBlockOptin, want1, &h->growers_1cta, &h->pool_tiles_1cta);
+            if (want2 > 0) choose(prop.sharedMemPerMultiprocessor / 2 - 1024, want2, &h->growers_2cta, &h->pool_tiles_2cta);
+            h->grow_tiles = tiles;
+            h->grow_window = 64;
+            if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));
             if (h->growers_1cta < 1) {
-                set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory per region grower, the device offers %zu", max_cols,
-                          max_rows, per, one);
+                set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region growers, the device offers %zu",
+                          max_cols, max_rows, fixed + GrowSmem{tiles, kMinPoolTiles, 0}.per_grower(), (size_t)prop.sharedMemPerBlockOptin);
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
-            if (h->growers_2cta < 1) h->growers_2cta = 0;
-            e = cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGrowCtaSmemFixed + h->growers_1cta * per));
+            e = cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(fixed - 512 + h->growers_1cta * GrowSmem{tiles, h->pool_tiles_1cta, 0}.per_grower()));
         }
     }
     const size_t max_ctas = std::min<size_t>(B, 2 * (size_t)std::max(h->num_sms, 1));
     A(&h->d_spec_reg, max_ctas * kPool * (size_t)kSpecCap);
     A(&h->d_spec_touched, max_ctas * kPool * (size_t)kSpecCap);
     A(&h->d_pool_rect, max_ctas * kPool);
+    A(&h->d_small_buf, max_ctas * kSlots * 2 * (size_t)kSmall);
+    A(&h->d_small_rect, max_ctas * kSlots);
     A(&h->d_claims, B * plane);
     A(&h->d_big_touched, max_ctas * 2 * plane);
+    A(&h->d_big_bits, max_ctas * (size_t)h->bits_words);
+    if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_ctas * (size_t)h->bits_words * sizeof(unsigned int));
     A(&h->d_frame_counter, 1);
     A(&h->d_resp, B * seg_cap);
     A(&h->d_dx, B * align_up((size_t)max_cols, 8) * max_rows);
@@ -2074,9 +2159,9 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* bufs[] = {h->d_in, h->d_scaled, h->d_used, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
+    void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_claims, h->d_frame_counter, h->d_cs, h->d_cs0, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_cs, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
