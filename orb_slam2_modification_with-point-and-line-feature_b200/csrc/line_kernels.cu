@@ -998,35 +998,39 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
 // earlier tickets in the map, so the result is the sequential one whatever the stamps say.  rect_improve only reads
 // the angle map and does not influence later regions: it runs afterwards in k_lsd_nfa, and accepted segments are
 // compacted in seed order.
-constexpr int kMaxGrowers = 8;
-constexpr int kSlots = 512;  // window of uncommitted tickets
-constexpr int kPool = 64;    // region buffers per CTA
-constexpr int kSmall = 64;   // regions up to this size (and log length) are parked in their slot's small buffer instead
+constexpr int kMaxGrowers = 12;    // grower warps per CTA
+constexpr int kMaxFrameSlots = 4;  // frames a CTA works on at once
+constexpr int kSlots = 256;        // ticket slots per frame (the window of uncommitted tickets is at most this)
+constexpr int kPool = 64;          // region buffers per CTA
+constexpr int kSmall = 64;         // regions up to this size (and log length) are parked in their slot's small buffer instead
 constexpr int kSvalEntries = 36;
 constexpr int kMaxPoolTiles = 64, kMinPoolTiles = 24;
 struct LsdQueueItem { LsdRect rec; };
 // shared memory of a grower warp: sval | ring | tile pool | rev | dir | ntiles, each part 16-byte aligned
 struct GrowSmem {
     int tiles, pool_tiles;
-    int window;  // tickets that may be uncommitted at once (<= kSlots): deeper speculation wastes more growth
+    int window;       // tickets that may be uncommitted at once (<= kSlots): deeper speculation wastes more growth
+    int frame_slots;  // frames per CTA
+    int bits_words;   // words of a W*H bitmap
     __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
     __host__ __device__ size_t off_pool() const { return off_ring() + kRegRing * sizeof(unsigned int); }
     __host__ __device__ size_t off_rev() const { return off_pool() + (size_t)pool_tiles * 32 * sizeof(unsigned int); }
     __host__ __device__ size_t off_dir() const { return off_rev() + (((size_t)pool_tiles * sizeof(unsigned short) + 15) & ~(size_t)15); }
     __host__ __device__ size_t off_ntiles() const { return off_dir() + (((size_t)tiles + 15) & ~(size_t)15); }
     __host__ __device__ size_t per_grower() const { return off_ntiles() + 16; }
+    // per frame slot: ticket slots | committed bitmap
+    __host__ __device__ size_t per_frame() const { return kSlots * sizeof(int4) + (((size_t)bits_words * sizeof(unsigned int) + 15) & ~(size_t)15); }
+    __host__ __device__ size_t total(int growers) const { return (size_t)frame_slots * per_frame() + (size_t)growers * per_grower(); }
 };
-// shared memory of the CTA: window slots | committed bitmap | growers
-__host__ __device__ inline size_t grow_cta_fixed_smem(int bits_words) {
-    return kSlots * sizeof(int4) + (((size_t)bits_words * sizeof(unsigned int) + 15) & ~(size_t)15);
-}
-// window slot (shared memory, int4): x = seed pixel, y = region size, z = touched-log size,
+// ticket slot (shared memory, int4): x = seed pixel, y = region size, z = touched-log size,
 // w = state | (status + 2) << 8 | (buffer + 1) << 16   (buffer -1 with status >= 0: the slot's small buffer)
 enum { kSlotFree = 0, kSlotReady = 1, kSlotGrowing = 2, kSlotDone = 3 };
-enum { kActNone = 0, kActCommit, kActIssue, kActTake, kActBuffer, kActExit };
+enum { kActNone = 0, kActCommit, kActIssue, kActTake, kActBuffer, kActInit, kActFinish, kActExit };
 enum { kStDeferred = -2, kStCapacity = -1, kStNoRect = 0, kStRect = 1 };
+enum { kFrameEmpty = 0, kFrameBusy = 1, kFrameRunning = 2, kFrameNoMore = 3 };
 __device__ __forceinline__ int slot_pack(int state, int status, int buf) { return state | ((status + 2) << 8) | ((buf + 1) << 16); }
-struct GrowCtl {
+struct GrowCtl {  // one per frame slot
+    int active;       // kFrame*
     int sel_lock, com_lock;
     int next_pos;     // next position of the seed list to look at
     int ticket_next;  // tickets issued
@@ -1034,9 +1038,12 @@ struct GrowCtl {
     int commit_head;  // tickets committed
     int head;         // rectangles queued
     int all_issued;   // the seed list is exhausted
-    int frame;
-    unsigned long long free_mask;  // free buffers of the pool
-    unsigned long long stat[8];    // committed, void, regrown, deferred, growth cycles, given-up cycles, -, regrow cycles
+    int frame, ns;
+    long long t_start;
+    unsigned long long stat[8];  // committed, void, regrown, deferred, growth cycles, given-up cycles, commit cycles, regrow cycles
+};
+struct GrowConfig {
+    int growers = 0, pool_tiles = 0, frame_slots = 1;
 };
 struct GrowResult {
     int status, n, nt;
@@ -1093,31 +1100,47 @@ __device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, int* __restrict__ frame_counter,
-                                                                  const float* __restrict__ angdeg, const int* __restrict__ g2,
-                                                                  unsigned short* __restrict__ claims, unsigned int* __restrict__ big_reg,
-                                                                  unsigned int* __restrict__ big_touched, unsigned int* __restrict__ big_bits,
-                                                                  unsigned int* __restrict__ pool_reg, unsigned int* __restrict__ pool_touched,
-                                                                  LsdRect* __restrict__ pool_rect, unsigned int* __restrict__ small_buf,
-                                                                  LsdRect* __restrict__ small_rect, int bits_words,
-                                                                  const unsigned int* __restrict__ seeds, const int* __restrict__ n_seeds,
-                                                                  const float2* __restrict__ cs, const float2* __restrict__ cs0, size_t plane,
-                                                                  LsdQueueItem* __restrict__ queue, int* __restrict__ n_rects,
-                                                                  int* __restrict__ flags, long long* __restrict__ phase_cycles) {
+// device buffers of k_lsd_grow
+struct GrowBufs {
+    const float* angdeg;
+    const int* g2;
+    const float2* cs;
+    const float2* cs0;
+    const unsigned int* seeds;
+    const int* n_seeds;
+    unsigned short* claims;      // [frame][plane]
+    unsigned int* big_reg;       // [frame][plane]
+    unsigned int* big_touched;   // [cta][frame slot][2 * plane]
+    unsigned int* big_bits;      // [cta][frame slot][bits_words], all-zero between uses
+    unsigned int* pool_reg;      // [cta][kPool][kSpecCap]
+    unsigned int* pool_touched;  // [cta][kPool][kSpecCap]
+    LsdRect* pool_rect;          // [cta][kPool]
+    unsigned int* small_buf;     // [cta][frame slot][kSlots][reg kSmall | touched kSmall]
+    LsdRect* small_rect;         // [cta][frame slot][kSlots]
+    LsdQueueItem* queue;         // [frame][seg_cap]
+    int* n_rects;
+    int* flags;
+    long long* phase_cycles;
+    int* frame_counter;
+    size_t plane;
+};
+
+// A CTA works on up to gs.frame_slots frames at once and its warps take whatever work any of them offers, so a warp
+// that would wait (the window of a frame is full, nothing is ready, the head region is still growing) works on
+// another frame instead.  Frames are handed out through a global counter.
+__global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, GrowBufs B) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ GrowCtl s_ctl;
+    __shared__ GrowCtl s_ctl[kMaxFrameSlots];
+    __shared__ unsigned long long s_free_mask;  // free buffers of the pool
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_raw);                         // [kSlots]
-    unsigned int* s_used = reinterpret_cast<unsigned int*>(s_raw + kSlots * sizeof(int4));   // committed USED bitmap
-    unsigned char* s_mine = s_raw + grow_cta_fixed_smem(bits_words) + (size_t)warp * gs.per_grower();
-    volatile GrowCtl* ctl = &s_ctl;
-    unsigned int* my_pool_reg = pool_reg + (size_t)blockIdx.x * kPool * kSpecCap;
-    unsigned int* my_pool_touched = pool_touched + (size_t)blockIdx.x * kPool * kSpecCap;
-    LsdRect* my_pool_rect = pool_rect + (size_t)blockIdx.x * kPool;
-    unsigned int* my_big_bits = big_bits + (size_t)blockIdx.x * bits_words;  // all-zero between uses
-    unsigned int* my_small = small_buf + (size_t)blockIdx.x * kSlots * 2 * kSmall;  // [kSlots][reg kSmall | touched kSmall]
-    LsdRect* my_small_rect = small_rect + (size_t)blockIdx.x * kSlots;
+    const int FS = gs.frame_slots;
+    const size_t plane = B.plane;
+    unsigned char* s_mine = s_raw + (size_t)FS * gs.per_frame() + (size_t)warp * gs.per_grower();
+    const size_t cta_fs = (size_t)blockIdx.x * FS;
+    unsigned int* my_pool_reg = B.pool_reg + (size_t)blockIdx.x * kPool * kSpecCap;
+    unsigned int* my_pool_touched = B.pool_touched + (size_t)blockIdx.x * kPool * kSpecCap;
+    LsdRect* my_pool_rect = B.pool_rect + (size_t)blockIdx.x * kPool;
     LsdFrame F;
     F.sval = reinterpret_cast<float2*>(s_mine);
     F.ring = reinterpret_cast<unsigned int*>(s_mine + gs.off_ring());
@@ -1129,8 +1152,6 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, Gr
     F.pool_tiles = gs.pool_tiles;
     F.sparse = true;
     F.bits = nullptr;
-    F.used_bits = s_used;
-    F.commit_head = &s_ctl.commit_head;
     F.ticket = 0;
     F.W = g.W;
     F.H = g.H;
@@ -1139,145 +1160,223 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, Gr
     F.reg_cap = F.touched_cap = 0;
     for (int i = lane; i < gs.tiles; i += 32) F.dir[i] = 0xffu;
     if (lane == 0) *F.ntiles = 0;
+    if (threadIdx.x < kMaxFrameSlots) s_ctl[threadIdx.x].active = threadIdx.x < FS ? kFrameEmpty : kFrameNoMore;
+    if (threadIdx.x == 0) s_free_mask = ~0ull << G;  // buffer w starts with warp w
+    __syncthreads();
+    int mybuf = warp, rr = warp % FS;
+    GrowResult res;
     while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            s_ctl.frame = atomicAdd(frame_counter, 1);
-            s_ctl.sel_lock = s_ctl.com_lock = 0;
-            s_ctl.next_pos = s_ctl.ticket_next = s_ctl.grow_next = s_ctl.commit_head = 0;
-            s_ctl.head = 0;
-            s_ctl.all_issued = 0;
-            s_ctl.free_mask = ~0ull << G;  // buffer w starts with warp w
-            for (int k = 0; k < 8; k++) s_ctl.stat[k] = 0;
-        }
-        for (int i = threadIdx.x; i < kSlots; i += blockDim.x) s_slot[i].w = slot_pack(kSlotFree, 0, -1);
-        for (int i = threadIdx.x; i < bits_words; i += blockDim.x) s_used[i] = 0;
-        __syncthreads();
-        const int f = s_ctl.frame;
-        if (f >= nf) break;
-        F.ang = angdeg + (size_t)f * plane;
-        F.g2 = g2 + (size_t)f * plane;
-        F.cs = cs + (size_t)f * plane;
-        F.cs0 = cs0 + (size_t)f * plane;
-        F.claims = claims + (size_t)f * plane;
-        const volatile unsigned int* vused = s_used;
-        const volatile unsigned short* vclaims = F.claims;
-        LsdQueueItem* q = queue + (size_t)f * g.seg_cap;
-        const unsigned int* sd = seeds + (size_t)f * plane;
-        const int ns = n_seeds[f];
-        const long long tstart = clock64();
-        long long t_com = 0, t_sel = 0;
-        int mybuf = warp;
-        GrowResult res;
+        // ---------------- what to do next (a tight loop: idle warps must not thrash the instruction cache) ----------------
+        int action = kActNone, fsi = 0;
         while (true) {
-            // ---------------- what to do next (a tight loop: idle warps must not thrash the instruction cache) ----------------
-            int action = kActNone;
-            while (true) {
-                if (lane == 0) {
-                    const int h = ctl->commit_head, tn = ctl->ticket_next, gn = ctl->grow_next, ai = ctl->all_issued;
-                    if (ai && h == tn) action = kActExit;
-                    else if (h < tn && (s_slot[h % kSlots].w & 0xff) == kSlotDone && ctl->com_lock == 0) action = kActCommit;
+            if (lane == 0) {
+                int nomore = 0;
+                for (int k = 0; k < FS && action == kActNone; k++) {
+                    const int cand = rr + k < FS ? rr + k : rr + k - FS;
+                    volatile GrowCtl* c = &s_ctl[cand];
+                    volatile int4* sl = reinterpret_cast<volatile int4*>(s_raw + (size_t)cand * gs.per_frame());
+                    const int st = c->active;
+                    if (st == kFrameNoMore) { nomore++; continue; }
+                    if (st == kFrameEmpty) { action = kActInit; fsi = cand; break; }
+                    if (st != kFrameRunning) continue;
+                    const int h = c->commit_head, tn = c->ticket_next, gn = c->grow_next, ai = c->all_issued;
+                    if (ai && h == tn) action = kActFinish;
+                    else if (h < tn && (sl[h % kSlots].w & 0xff) == kSlotDone && c->com_lock == 0) action = kActCommit;
                     else if (mybuf >= 0 && gn < tn) action = kActTake;
-                    else if (!ai && tn - gn < 2 * G && tn - h < gs.window && ctl->sel_lock == 0) action = kActIssue;
-                    else if (mybuf < 0 && ctl->free_mask != 0) action = kActBuffer;
+                    else if (!ai && tn - gn < G && tn - h < gs.window && c->sel_lock == 0) action = kActIssue;
+                    if (action != kActNone) fsi = cand;
                 }
-                action = __shfl_sync(FULL, action, 0);
-                if (action != kActNone) break;
-                __nanosleep(256);
+                if (action == kActNone) {
+                    if (nomore == FS) action = kActExit;
+                    else if (mybuf < 0 && *(volatile unsigned long long*)&s_free_mask != 0) action = kActBuffer;
+                }
             }
-            if (action == kActExit) break;
-            if (action == kActBuffer) mybuf = pool_pop(&s_ctl.free_mask, lane);
-            // ---------------- commit duty: strictly in ticket order ----------------
-            if (action == kActCommit && warp_try_lock(&s_ctl.com_lock, lane)) {
-                const long long t0 = clock64();
-                while (true) {
-                    const int h = __shfl_sync(FULL, ctl->commit_head, 0);
-                    volatile int4* sl = &s_slot[h % kSlots];
-                    if (!WARP_UNIFORM(h < ctl->ticket_next && (sl->w & 0xff) == kSlotDone)) break;
-                    __threadfence_block();
-                    const int pix = sl->x, w = sl->w;
-                    int n = sl->y, nt = sl->z, status = ((w >> 8) & 0xff) - 2;
-                    const int buf = ((w >> 16) & 0xff) - 1;
-                    int kind = 0;  // 0 committed, 1 void
-                    if ((vused[pix >> 5] >> (pix & 31)) & 1u) {
-                        kind = 1;  // swallowed by an earlier region
-                    } else {
-                        const unsigned int* rg = buf >= 0 ? my_pool_reg + (size_t)buf * kSpecCap : my_small + (size_t)(h % kSlots) * 2 * kSmall;
-                        bool redo = status < 0;
-                        if (!redo) {
-                            const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
-                            bool conflict = false;
-                            for (int i = lane; i < nt; i += 32) {
-                                const unsigned pp = tk[i];
-                                const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
-                                conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
-                            }
-                            redo = __any_sync(FULL, conflict);
+            action = __shfl_sync(FULL, action, 0);
+            if (action != kActNone) break;
+            __nanosleep(400);
+        }
+        if (action == kActExit) break;
+        fsi = __shfl_sync(FULL, fsi, 0);
+        rr = fsi + 1 < FS ? fsi + 1 : 0;
+        if (action == kActBuffer) {
+            mybuf = pool_pop(&s_free_mask, lane);
+            continue;
+        }
+        GrowCtl* ctlp = &s_ctl[fsi];
+        volatile GrowCtl* ctl = ctlp;
+        volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_raw + (size_t)fsi * gs.per_frame());
+        unsigned int* s_used = reinterpret_cast<unsigned int*>(s_raw + (size_t)fsi * gs.per_frame() + kSlots * sizeof(int4));
+        const volatile unsigned int* vused = s_used;
+        if (action == kActInit || action == kActFinish) {
+            // a finished frame is closed, and the slot gets the next frame, by one warp that holds both locks
+            bool mine;
+            if (action == kActInit) {
+                mine = WARP_UNIFORM(atomicCAS(&ctlp->active, kFrameEmpty, kFrameBusy) == kFrameEmpty);
+            } else {
+                mine = warp_try_lock(&ctlp->com_lock, lane);
+                if (mine && !warp_try_lock(&ctlp->sel_lock, lane)) {
+                    warp_unlock(&ctlp->com_lock, lane);
+                    mine = false;
+                }
+                if (mine) {
+                    const bool done = WARP_UNIFORM(ctl->active == kFrameRunning && ctl->all_issued && ctl->commit_head == ctl->ticket_next);
+                    if (!done) {
+                        warp_unlock(&ctlp->sel_lock, lane);
+                        warp_unlock(&ctlp->com_lock, lane);
+                        mine = false;
+                    }
+                }
+                if (mine && lane == 0) {
+                    ctl->active = kFrameBusy;
+                    const int f = ctl->frame;
+                    B.n_rects[f] = ctl->head;
+                    if (B.phase_cycles) {
+                        long long* pc = B.phase_cycles + (size_t)f * 8;
+                        pc[0] = (long long)((ctl->stat[4] / 1000) + ((ctl->stat[7] / 1000) << 20) + ((ctl->stat[5] / 1000) << 40));
+                        pc[1] = clock64() - ctl->t_start;
+                        pc[2] = (long long)ctl->stat[6];
+                        pc[3] = ctl->ticket_next;
+                        pc[4] = (long long)ctl->stat[2];
+                        pc[5] = (long long)ctl->stat[0];
+                        pc[6] = (long long)ctl->stat[3];
+                        pc[7] = (long long)ctl->stat[1];
+                    }
+                }
+                __syncwarp();
+            }
+            if (!mine) continue;
+            int f = 0;
+            if (lane == 0) f = atomicAdd(B.frame_counter, 1);
+            f = __shfl_sync(FULL, f, 0);
+            if (f < nf) {
+                for (int i = lane; i < kSlots; i += 32) s_slot[i].w = slot_pack(kSlotFree, 0, -1);
+                for (int i = lane; i < gs.bits_words; i += 32) s_used[i] = 0;
+                if (lane == 0) {
+                    ctl->next_pos = ctl->ticket_next = ctl->grow_next = ctl->commit_head = 0;
+                    ctl->head = 0;
+                    ctl->all_issued = 0;
+                    ctl->frame = f;
+                    ctl->ns = B.n_seeds[f];
+                    ctl->t_start = clock64();
+                    for (int k = 0; k < 8; k++) ctl->stat[k] = 0;
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) {
+                ctl->sel_lock = 0;
+                ctl->com_lock = 0;
+                __threadfence_block();
+                ctl->active = f < nf ? kFrameRunning : kFrameNoMore;
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---------------- commit duty: strictly in ticket order ----------------
+        if (action == kActCommit && warp_try_lock(&ctlp->com_lock, lane)) {
+            const long long t0 = clock64();
+            const int f = __shfl_sync(FULL, ctl->frame, 0);
+            F.ang = B.angdeg + (size_t)f * plane;
+            F.g2 = B.g2 + (size_t)f * plane;
+            F.cs = B.cs + (size_t)f * plane;
+            F.cs0 = B.cs0 + (size_t)f * plane;
+            F.claims = B.claims + (size_t)f * plane;
+            F.used_bits = s_used;
+            F.commit_head = &ctlp->commit_head;
+            LsdQueueItem* q = B.queue + (size_t)f * g.seg_cap;
+            const unsigned int* my_small = B.small_buf + (cta_fs + fsi) * kSlots * 2 * kSmall;
+            const LsdRect* my_small_rect = B.small_rect + (cta_fs + fsi) * kSlots;
+            while (true) {
+                const int h = __shfl_sync(FULL, ctl->commit_head, 0);
+                volatile int4* sl = &s_slot[h % kSlots];
+                if (!WARP_UNIFORM(ctl->active == kFrameRunning && h < ctl->ticket_next && (sl->w & 0xff) == kSlotDone)) break;
+                __threadfence_block();
+                const int pix = sl->x, w = sl->w;
+                int n = sl->y, nt = sl->z, status = ((w >> 8) & 0xff) - 2;
+                const int buf = ((w >> 16) & 0xff) - 1;
+                int kind = 0;  // 0 committed, 1 void
+                if ((vused[pix >> 5] >> (pix & 31)) & 1u) {
+                    kind = 1;  // swallowed by an earlier region
+                } else {
+                    const unsigned int* rg = buf >= 0 ? my_pool_reg + (size_t)buf * kSpecCap : my_small + (size_t)(h % kSlots) * 2 * kSmall;
+                    bool redo = status < 0;
+                    if (!redo) {
+                        const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
+                        bool conflict = false;
+                        for (int i = lane; i < nt; i += 32) {
+                            const unsigned pp = tk[i];
+                            const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
+                            conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
                         }
-                        LsdRect rec;
-                        if (redo) {  // everything before this ticket is committed: this growth is the sequential one
-                            const long long g0 = clock64();
-                            LsdFrame FS = F;
-                            FS.sparse = false;
-                            FS.bits = my_big_bits;
-                            FS.reg = big_reg + (size_t)f * plane;
-                            FS.touched = big_touched + (size_t)blockIdx.x * 2 * plane;
-                            FS.reg_cap = (int)plane;
-                            FS.touched_cap = (int)(2 * plane);
-                            FS.ticket = h;
-                            lsd_grow_seed(FS, pix, g.min_reg_size, &res);
-                            status = res.status;
-                            n = res.n;
-                            rec = res.rec;
-                            rg = FS.reg;
-                            if (status < 0 && lane == 0) atomicOr(flags + f, 2);
-                            if (lane == 0) {
-                                s_ctl.stat[2]++;
-                                s_ctl.stat[7] += (unsigned long long)(clock64() - g0);
-                            }
-                        } else if (status == kStRect) {
-                            rec = buf >= 0 ? my_pool_rect[buf] : my_small_rect[h % kSlots];
+                        redo = __any_sync(FULL, conflict);
+                    }
+                    LsdRect rec;
+                    if (redo) {  // everything before this ticket is committed: this growth is the sequential one
+                        const long long g0 = clock64();
+                        LsdFrame FS2 = F;
+                        FS2.sparse = false;
+                        FS2.bits = B.big_bits + (cta_fs + fsi) * gs.bits_words;
+                        FS2.reg = B.big_reg + (size_t)f * plane;
+                        FS2.touched = B.big_touched + (cta_fs + fsi) * 2 * plane;
+                        FS2.reg_cap = (int)plane;
+                        FS2.touched_cap = (int)(2 * plane);
+                        FS2.ticket = h;
+                        lsd_grow_seed(FS2, pix, g.min_reg_size, &res);
+                        status = res.status;
+                        n = res.n;
+                        rec = res.rec;
+                        rg = FS2.reg;
+                        if (status < 0 && lane == 0) atomicOr(B.flags + f, 2);
+                        if (lane == 0) {
+                            ctl->stat[2]++;
+                            ctl->stat[7] += (unsigned long long)(clock64() - g0);
                         }
-                        if (status >= 0) {
-                            for (int i = lane; i < n; i += 32) {
-                                const unsigned pp = rg[i];
-                                const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
-                                atomicOr(&s_used[o >> 5], 1u << (o & 31));
-                            }
-                            if (status == kStRect) {
-                                const int head = __shfl_sync(FULL, ctl->head, 0);
-                                if (head < g.seg_cap) {
-                                    if (lane == 0) {
-                                        q[head].rec = rec;
-                                        s_ctl.head = head + 1;
-                                    }
-                                } else if (lane == 0) {
-                                    atomicOr(flags + f, 1);
+                    } else if (status == kStRect) {
+                        rec = buf >= 0 ? my_pool_rect[buf] : my_small_rect[h % kSlots];
+                    }
+                    if (status >= 0) {
+                        for (int i = lane; i < n; i += 32) {
+                            const unsigned pp = rg[i];
+                            const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
+                            atomicOr(&s_used[o >> 5], 1u << (o & 31));
+                        }
+                        if (status == kStRect) {
+                            const int head = __shfl_sync(FULL, ctl->head, 0);
+                            if (head < g.seg_cap) {
+                                if (lane == 0) {
+                                    q[head].rec = rec;
+                                    ctl->head = head + 1;
                                 }
+                            } else if (lane == 0) {
+                                atomicOr(B.flags + f, 1);
                             }
                         }
                     }
-                    __syncwarp();
-                    __threadfence_block();
-                    if (lane == 0) {
-                        s_ctl.stat[kind]++;
-                        if (buf >= 0) atomicOr(&s_ctl.free_mask, 1ull << buf);
-                        sl->w = slot_pack(kSlotFree, 0, -1);
-                        __threadfence_block();
-                        s_ctl.commit_head = h + 1;
-                    }
-                    __syncwarp();
                 }
-                t_com += clock64() - t0;
-                warp_unlock(&s_ctl.com_lock, lane);
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) {
+                    ctl->stat[kind]++;
+                    if (buf >= 0) atomicOr(&s_free_mask, 1ull << buf);
+                    sl->w = slot_pack(kSlotFree, 0, -1);
+                    __threadfence_block();
+                    ctl->commit_head = h + 1;
+                }
+                __syncwarp();
             }
-            // ---------------- issue tickets: one chunk of the seed list at a time ----------------
-            if (action == kActIssue && warp_try_lock(&s_ctl.sel_lock, lane)) {
-                const long long t0 = clock64();
+            if (lane == 0) ctl->stat[6] += (unsigned long long)(clock64() - t0);
+            warp_unlock(&ctlp->com_lock, lane);
+            continue;
+        }
+        // ---------------- issue tickets: one chunk of the seed list at a time ----------------
+        if (action == kActIssue && warp_try_lock(&ctlp->sel_lock, lane)) {
+            if (WARP_UNIFORM(ctl->active == kFrameRunning && !ctl->all_issued)) {
+                const int f = __shfl_sync(FULL, ctl->frame, 0), ns = __shfl_sync(FULL, ctl->ns, 0);
+                const unsigned int* sd = B.seeds + (size_t)f * plane;
                 int t = __shfl_sync(FULL, ctl->ticket_next, 0);
                 int pos = __shfl_sync(FULL, ctl->next_pos, 0);
                 bool full = false;
-                while (!full && pos < ns && t - __shfl_sync(FULL, ctl->grow_next, 0) < 2 * G) {
+                while (!full && pos < ns && t - __shfl_sync(FULL, ctl->grow_next, 0) < G) {
                     const int idx = pos + lane;
                     unsigned pix = 0;
                     bool free_ = false;
@@ -1300,94 +1399,86 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 2) k_lsd_grow(LineGeom g, Gr
                             sl->z = 0;
                             sl->w = slot_pack(kSlotReady, 0, -1);
                             __threadfence_block();
-                            s_ctl.ticket_next = t + 1;
+                            ctl->ticket_next = t + 1;
                         }
                         t++;
                     }
                     pos += consumed;
                 }
                 if (lane == 0) {
-                    s_ctl.next_pos = min(pos, ns);
-                    if (pos >= ns && !full) s_ctl.all_issued = 1;
+                    ctl->next_pos = min(pos, ns);
+                    if (pos >= ns && !full) ctl->all_issued = 1;
                 }
-                t_sel += clock64() - t0;
-                warp_unlock(&s_ctl.sel_lock, lane);
             }
-            // ---------------- take the next ticket ----------------
+            warp_unlock(&ctlp->sel_lock, lane);
+            continue;
+        }
+        // ---------------- take the next ticket and grow it speculatively ----------------
+        if (action == kActTake) {
             int my_ticket = -1;
-            if (action == kActTake) {
-                if (lane == 0) {
-                    while (true) {
-                        const int t = ctl->grow_next;
-                        if (t >= ctl->ticket_next) break;
-                        if (atomicCAS(&s_ctl.grow_next, t, t + 1) == t) { my_ticket = t; break; }
-                    }
+            if (lane == 0) {
+                while (true) {
+                    const int t = ctl->grow_next;
+                    if (ctl->active != kFrameRunning || t >= ctl->ticket_next) break;
+                    if (atomicCAS(&ctlp->grow_next, t, t + 1) == t) { my_ticket = t; break; }
                 }
-                my_ticket = __shfl_sync(FULL, my_ticket, 0);
             }
-            // ---------------- speculative growth ----------------
-            if (my_ticket >= 0) {
-                volatile int4* sl = &s_slot[my_ticket % kSlots];
-                const int my_pix = sl->x;
-                // already swallowed, or stamped by an uncommitted earlier ticket (most likely being swallowed):
-                // not grown now; the committer decides when its turn comes
-                const unsigned short cl = vclaims[my_pix];
-                const unsigned d = (unsigned)(my_ticket - (int)cl) & 0xffffu;
-                const bool defer = WARP_UNIFORM((((vused[my_pix >> 5] >> (my_pix & 31)) & 1u) != 0) ||
-                                                (d != 0 && d <= (unsigned)(my_ticket - ctl->commit_head)));
-                if (defer) {
-                    if (lane == 0) {
-                        s_ctl.stat[3]++;  // (racy counter, profiling only)
-                        __threadfence_block();
-                        sl->w = slot_pack(kSlotDone, kStDeferred, -1);
-                    }
-                } else {
-                    LsdFrame FS = F;
-                    FS.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
-                    FS.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
-                    FS.reg_cap = FS.touched_cap = kSpecCap;
-                    FS.ticket = my_ticket;
-                    const long long g0 = clock64();
-                    lsd_grow_seed(FS, my_pix, g.min_reg_size, &res);
-                    // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer
-                    const bool small = res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
-                    const bool keep = res.status >= 0 && !small;
-                    if (small) {
-                        unsigned int* dst = my_small + (size_t)(my_ticket % kSlots) * 2 * kSmall;
-                        for (int i = lane; i < res.n; i += 32) dst[i] = FS.reg[i];
-                        for (int i = lane; i < res.nt; i += 32) dst[kSmall + i] = FS.touched[i];
-                        if (lane == 0 && res.status == kStRect) my_small_rect[my_ticket % kSlots] = res.rec;
-                        __syncwarp();
-                    }
-                    if (lane == 0) {
-                        atomicAdd(&s_ctl.stat[4], (unsigned long long)(clock64() - g0));
-                        if (res.status < 0) atomicAdd(&s_ctl.stat[5], (unsigned long long)(clock64() - g0));
-                        if (keep && res.status == kStRect) my_pool_rect[mybuf] = res.rec;
-                        sl->y = res.n;
-                        sl->z = res.nt;
-                        __threadfence_block();
-                        sl->w = slot_pack(kSlotDone, res.status, keep ? mybuf : -1);
-                    }
-                    __syncwarp();
-                    if (keep) mybuf = pool_pop(&s_ctl.free_mask, lane);
+            my_ticket = __shfl_sync(FULL, my_ticket, 0);
+            if (my_ticket < 0) continue;
+            // the frame cannot finish before this ticket is committed: its identity is stable from here on
+            const int f = __shfl_sync(FULL, ctl->frame, 0);
+            volatile int4* sl = &s_slot[my_ticket % kSlots];
+            const int my_pix = sl->x;
+            F.claims = B.claims + (size_t)f * plane;
+            // already swallowed, or stamped by an uncommitted earlier ticket (most likely being swallowed):
+            // not grown now; the committer decides when its turn comes
+            const unsigned short cl = ((const volatile unsigned short*)F.claims)[my_pix];
+            const unsigned d = (unsigned)(my_ticket - (int)cl) & 0xffffu;
+            const bool defer = WARP_UNIFORM((((vused[my_pix >> 5] >> (my_pix & 31)) & 1u) != 0) ||
+                                            (d != 0 && d <= (unsigned)(my_ticket - ctl->commit_head)));
+            if (defer) {
+                if (lane == 0) {
+                    atomicAdd(&ctlp->stat[3], 1ull);
+                    __threadfence_block();
+                    sl->w = slot_pack(kSlotDone, kStDeferred, -1);
                 }
                 __syncwarp();
+                continue;
             }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            n_rects[f] = s_ctl.head;
-            if (phase_cycles) {
-                long long* pc = phase_cycles + (size_t)f * 8;
-                pc[0] = (long long)((s_ctl.stat[4] / 1000) + ((s_ctl.stat[7] / 1000) << 20) + ((s_ctl.stat[5] / 1000) << 40));
-                pc[1] = clock64() - tstart;
-                pc[2] = (t_com / 1000) | ((t_sel / 1000) << 32);  // warp 0's share
-                pc[3] = s_ctl.ticket_next;
-                pc[4] = (long long)s_ctl.stat[2];
-                pc[5] = (long long)s_ctl.stat[0];
-                pc[6] = (long long)s_ctl.stat[3];
-                pc[7] = (long long)s_ctl.stat[1];
+            F.ang = B.angdeg + (size_t)f * plane;
+            F.g2 = B.g2 + (size_t)f * plane;
+            F.cs = B.cs + (size_t)f * plane;
+            F.cs0 = B.cs0 + (size_t)f * plane;
+            F.used_bits = s_used;
+            F.commit_head = &ctlp->commit_head;
+            LsdFrame FS2 = F;
+            FS2.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
+            FS2.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
+            FS2.reg_cap = FS2.touched_cap = kSpecCap;
+            FS2.ticket = my_ticket;
+            const long long g0 = clock64();
+            lsd_grow_seed(FS2, my_pix, g.min_reg_size, &res);
+            // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer
+            const bool small = res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
+            const bool keep = res.status >= 0 && !small;
+            if (small) {
+                unsigned int* dst = B.small_buf + ((cta_fs + fsi) * kSlots + (size_t)(my_ticket % kSlots)) * 2 * kSmall;
+                for (int i = lane; i < res.n; i += 32) dst[i] = FS2.reg[i];
+                for (int i = lane; i < res.nt; i += 32) dst[kSmall + i] = FS2.touched[i];
+                if (lane == 0 && res.status == kStRect) B.small_rect[(cta_fs + fsi) * kSlots + (my_ticket % kSlots)] = res.rec;
+                __syncwarp();
             }
+            if (lane == 0) {
+                atomicAdd(&ctlp->stat[4], (unsigned long long)(clock64() - g0));
+                if (res.status < 0) atomicAdd(&ctlp->stat[5], (unsigned long long)(clock64() - g0));
+                if (keep && res.status == kStRect) my_pool_rect[mybuf] = res.rec;
+                sl->y = res.n;
+                sl->z = res.nt;
+                __threadfence_block();
+                sl->w = slot_pack(kSlotDone, res.status, keep ? mybuf : -1);
+            }
+            __syncwarp();
+            if (keep) mybuf = pool_pop(&s_free_mask, lane);
         }
     }
 }
@@ -1809,7 +1900,8 @@ struct pl_line {
     unsigned int* d_small_buf = nullptr;
     unsigned short* d_claims = nullptr;
     int* d_frame_counter = nullptr;
-    int bits_words = 0, num_sms = 0, growers_1cta = 0, growers_2cta = 0, pool_tiles_1cta = 0, pool_tiles_2cta = 0, grow_tiles = 0, grow_window = 64;
+    int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
+    GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
     unsigned int* d_big_bits = nullptr;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
     short *d_dx = nullptr, *d_dy = nullptr;
@@ -1935,19 +2027,20 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
     {
-        // growers per CTA: few frames -> one CTA per SM with as many growers as shared memory holds (latency);
-        // more frames than SMs -> two CTAs per SM with half the growers each (throughput)
-        const bool two = nf > h->num_sms && h->growers_2cta > 0;
-        const int growers = two ? h->growers_2cta : h->growers_1cta;
-        const GrowSmem gs{h->grow_tiles, two ? h->pool_tiles_2cta : h->pool_tiles_1cta, h->grow_window};
-        const int ctas = std::min(nf, two ? 2 * h->num_sms : h->num_sms);
-        const size_t smem = grow_cta_fixed_smem(h->bits_words) + (size_t)growers * gs.per_grower();
+        // one CTA per SM; a CTA works on several frames at once when there are more frames than SMs
+        const bool many = nf > h->num_sms && h->cfg_many.growers > 0;
+        const GrowConfig& cf = many ? h->cfg_many : h->cfg_few;
+        GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words};
+        const int ctas = std::min(nf, h->num_sms);
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_claims, 0xff, sizeof(unsigned short) * plane * nf, st));
-        k_lsd_grow<<<ctas, growers * 32, smem, st>>>(G, gs, nf, h->d_frame_counter, h->d_ang, h->d_g2, h->d_claims, h->d_reg, h->d_big_touched,
-                                                     h->d_big_bits, h->d_spec_reg, h->d_spec_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->bits_words, h->d_seeds,
-                                                     h->d_nseeds, h->d_cs, h->d_cs0, plane, h->d_queue, h->d_nrects, h->d_flags,
-                                                     prof ? h->d_phase : nullptr);
+        GrowBufs gb;
+        gb.angdeg = h->d_ang; gb.g2 = h->d_g2; gb.cs = h->d_cs; gb.cs0 = h->d_cs0; gb.seeds = h->d_seeds; gb.n_seeds = h->d_nseeds;
+        gb.claims = h->d_claims; gb.big_reg = h->d_reg; gb.big_touched = h->d_big_touched; gb.big_bits = h->d_big_bits;
+        gb.pool_reg = h->d_spec_reg; gb.pool_touched = h->d_spec_touched; gb.pool_rect = h->d_pool_rect;
+        gb.small_buf = h->d_small_buf; gb.small_rect = h->d_small_rect; gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
+        gb.flags = h->d_flags; gb.phase_cycles = prof ? h->d_phase : nullptr; gb.frame_counter = h->d_frame_counter; gb.plane = plane;
+        k_lsd_grow<<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
     }
     k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
     launches += 2;
@@ -2055,56 +2148,56 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
         if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
         if (e == cudaSuccess) {
             h->num_sms = prop.multiProcessorCount;
-            // shared memory: window slots + committed bitmap per CTA, and per grower the ring, the staging area and the
-            // sparse private bitmap (a pool of 32x32-pixel tiles: as many as fit, the more the fewer regions overflow)
+            // shared memory: per frame slot the ticket slots + committed bitmap, per grower the ring, the staging area
+            // and the sparse private bitmap (a pool of 32x32-pixel tiles: the more, the fewer regions overflow)
             const int tiles = ((W + 31) / 32) * ((H + 31) / 32);
-            const size_t fixed = grow_cta_fixed_smem(h->bits_words) + 512;  // + static control block
-            auto choose = [&](size_t budget, int max_g, int* g_out, int* p_out) {
-                *g_out = 0;
-                *p_out = 0;
-                for (int gN = max_g; gN >= 1 && *g_out == 0; gN--)
+            const size_t budget = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;  // static control blocks
+            auto choose = [&](int fs, int max_g, GrowConfig* c) {
+                *c = GrowConfig{0, 0, fs};
+                for (int gN = max_g; gN >= 1 && c->growers == 0; gN--)
                     for (int pN = kMaxPoolTiles; pN >= kMinPoolTiles; pN -= 8) {
-                        GrowSmem gs{tiles, pN, 0};
-                        if (fixed + (size_t)gN * gs.per_grower() <= budget) {
-                            *g_out = gN;
-                            *p_out = pN;
+                        GrowSmem gs{tiles, pN, 0, fs, h->bits_words};
+                        if (gs.total(gN) <= budget) {
+                            c->growers = gN;
+                            c->pool_tiles = pN;
                             break;
                         }
                     }
             };
-            int want1 = kMaxGrowers, want2 = kMaxGrowers;
-            if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<1cta>,<2cta>"
-                int a = 0, b2 = 0;
-                if (sscanf(ev, "%d,%d", &a, &b2) == 2) {
-                    if (a >= 1 && a <= kMaxGrowers) want1 = a;
-                    if (b2 >= 0 && b2 <= kMaxGrowers) want2 = b2;
+            int g_few = 8, g_many = kMaxGrowers, fs_many = 2;
+            if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<few>,<many>,<frame slots>"
+                int a = 0, b2 = 0, c2 = 0;
+                if (sscanf(ev, "%d,%d,%d", &a, &b2, &c2) == 3) {
+                    if (a >= 1 && a <= kMaxGrowers) g_few = a;
+                    if (b2 >= 1 && b2 <= kMaxGrowers) g_many = b2;
+                    if (c2 >= 1 && c2 <= kMaxFrameSlots) fs_many = c2;
                 }
             }
-            choose(prop.sharedMemPerBlockOptin, want1, &h->growers_1cta, &h->pool_tiles_1cta);
-            if (want2 > 0) choose(prop.sharedMemPerMultiprocessor / 2 - 1024, want2, &h->growers_2cta, &h->pool_tiles_2cta);
+            choose(1, g_few, &h->cfg_few);
+            for (int fs = fs_many; fs >= 1 && h->cfg_many.growers < std::min(g_many, 4); fs--) choose(fs, g_many, &h->cfg_many);
             h->grow_tiles = tiles;
-            h->grow_window = 64;
+            h->grow_window = 128;
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));
-            if (h->growers_1cta < 1) {
+            if (h->cfg_few.growers < 1) {
                 set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region growers, the device offers %zu",
-                          max_cols, max_rows, fixed + GrowSmem{tiles, kMinPoolTiles, 0}.per_grower(), (size_t)prop.sharedMemPerBlockOptin);
+                          max_cols, max_rows, GrowSmem{tiles, kMinPoolTiles, 0, 1, h->bits_words}.total(1), budget);
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
-            e = cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(fixed - 512 + h->growers_1cta * GrowSmem{tiles, h->pool_tiles_1cta, 0}.per_grower()));
+            e = cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
         }
     }
-    const size_t max_ctas = std::min<size_t>(B, 2 * (size_t)std::max(h->num_sms, 1));
+    const size_t max_ctas = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1));
+    const size_t max_fs = max_ctas * kMaxFrameSlots;
     A(&h->d_spec_reg, max_ctas * kPool * (size_t)kSpecCap);
     A(&h->d_spec_touched, max_ctas * kPool * (size_t)kSpecCap);
     A(&h->d_pool_rect, max_ctas * kPool);
-    A(&h->d_small_buf, max_ctas * kSlots * 2 * (size_t)kSmall);
-    A(&h->d_small_rect, max_ctas * kSlots);
+    A(&h->d_small_buf, max_fs * kSlots * 2 * (size_t)kSmall);
+    A(&h->d_small_rect, max_fs * kSlots);
     A(&h->d_claims, B * plane);
-    A(&h->d_big_touched, max_ctas * 2 * plane);
-    A(&h->d_big_bits, max_ctas * (size_t)h->bits_words);
-    if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_ctas * (size_t)h->bits_words * sizeof(unsigned int));
+    A(&h->d_big_touched, max_fs * 2 * plane);
+    A(&h->d_big_bits, max_fs * (size_t)h->bits_words);
+    if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_fs * (size_t)h->bits_words * sizeof(unsigned int));
     A(&h->d_frame_counter, 1);
     A(&h->d_resp, B * seg_cap);
     A(&h->d_dx, B * align_up((size_t)max_cols, 8) * max_rows);

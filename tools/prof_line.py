@@ -69,5 +69,5 @@ elif os.environ.get("PLSLAM_NVCC_EXTRA", "").find("PL_LSD_PROF2") >= 0:
 else:
     busy, regrow, aborted = ph[0] & 0xfffff, (ph[0] >> 20) & 0xfffff, ph[0] >> 40
     print(f"grow kernel (frame 0): total {ph[1]/1e6:.1f} Mcycles; speculative growth {busy/1e3:.1f} Mcycles over all warps (given up: {aborted/1e3:.1f}), "
-          f"re-growth at commit {regrow/1e3:.1f}; warp 0: commit {(ph[2] & 0xffffffff)/1e3:.1f} issue {(ph[2] >> 32)/1e3:.1f}; tickets {ph[3]}, committed {ph[5]}, "
+          f"re-growth at commit {regrow/1e3:.1f}; commit sections {ph[2]/1e6:.1f}; tickets {ph[3]}, committed {ph[5]}, "
           f"void {ph[7]}, deferred {ph[6]}, regrown {ph[4]}")
