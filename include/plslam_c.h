@@ -165,8 +165,9 @@ PL_API int pl_line_last_launches(const pl_line* h);
 PL_API int pl_line_set_profiling(pl_line* h, int on);
 PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
 /* with profiling on, 8 values of frame `frame` of the last chunk from k_lsd_grow's own clock64 accounting:
- * {0 cycles selecting seeds, 1 total cycles of the grower loop, 2 cycles validating/committing, 3 rounds,
- *  4 busy cycles of one NFA warp, 5 regions committed, 6 regions grown exclusively, 7 speculative growths discarded} */
+ * {0 packed kcycles: speculative growth | re-growth at commit << 20 | given-up growth << 40, 1 cycles the frame was
+ *  active, 2 cycles inside commit sections, 3 tickets issued, 4 regions re-grown at commit, 5 regions committed,
+ *  6 tickets deferred, 7 tickets void} */
 PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out8);
 /* Test hooks: the 0.8-scaled 8-bit image LSD works on, its level-line angle map (float degrees, -1024 = undefined,
  * rows x cols of the scaled image) and the float LBD descriptors (n x 72) of frame `frame` of the last call. */
@@ -308,6 +309,82 @@ PL_API int pl_line_search_by_projection_batch(pl_match* h, int n, const pl_linef
                                               int* const* match_of_line, int* n_matches, int* used_relaxed,
                                               pl_keyline* const* new_keylines /* may be NULL */, int* const* new_kl_index /* may be NULL */,
                                               int* n_projected /* may be NULL */);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * C4 / C5: pose-based projection searches.  The map points are described by what the reference reads from them.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n;
+    const uint8_t* valid;        /* C4: pMP && !isBad() && !sAlreadyFound.count(pMP) (ORBmatcher.cc:1913-1918);
+                                    C5: !isBad() && !spAlreadyFound.count(pMP) (:455-459)                     */
+    const float* world_pos;      /* MapPoint::GetWorldPos(), n x 3                                            */
+    const uint8_t* desc;         /* MapPoint::GetDescriptor(), n x 32                                         */
+    const float* min_dist_inv;   /* GetMinDistanceInvariance() (0.8f * mfMinDistance, MapPoint.cc:395-399)    */
+    const float* max_dist_inv;   /* GetMaxDistanceInvariance() (1.2f * mfMaxDistance, :401-405)               */
+    const float* max_dist;       /* mfMaxDistance, what PredictScale divides (MapPoint.cc:416-431)            */
+    const float* angle;          /* C4: pKF->mvKeysUn[i].angle (rotation histogram, :1976); may be NULL for C5 */
+    const float* normal;         /* C5: GetNormal(), n x 3 (:494-497); may be NULL for C4                     */
+} pl_posepoint_view;
+
+/* C4: ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th,
+ * ORBdist) — ORBmatcher.cc:1891-2024 (relocalisation refinement).  pts[i] = pKF->GetMapPointMatches() of call i;
+ * cur[i].claimed[i2] = (CurrentFrame.mvpMapPoints[i2] != NULL) (:1965); ow = Frame::mOw, log_scale_factor =
+ * Frame::mfLogScaleFactor.  match_of_feature[i][i2] = index of the KeyFrame feature whose map point was assigned to
+ * feature i2 of the frame, or -1. */
+PL_API int pl_orb_search_keyframe_points_batch(pl_match* h, int n, const pl_frame_view* cur, const pl_posepoint_view* pts,
+                                               const float* ow /* n x 3 */, const float* log_scale_factor /* n */, float th,
+                                               int orb_dist, int check_orientation, int* const* match_of_feature, int* n_matches);
+
+/* C5: ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th) — ORBmatcher.cc:423-554
+ * (loop closing).  kf[i] is the KeyFrame as a frame view whose tcw holds Rcw | tcw AFTER the scale was divided out
+ * (:435-439, done by the caller with the reference's own cv::Mat expressions) and whose claimed[idx] =
+ * (vpMatched[idx] != NULL) (:521); ow = -Rcw^T tcw (:439).  match_of_feature[i][idx] = index into pts[i] of the map
+ * point written to vpMatched[idx], or -1. */
+PL_API int pl_orb_search_sim3_points_batch(pl_match* h, int n, const pl_frame_view* kf, const pl_posepoint_view* pts,
+                                           const float* ow /* n x 3 */, const float* log_scale_factor /* n */, int th,
+                                           int* const* match_of_feature, int* n_matches);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * C6 / C7: ORBmatcher::SearchByBoW.  A DBoW2::FeatureVector (map<NodeId, vector<unsigned>>, FeatureVector.h:21-22)
+ * travels flattened in key order: node_id[k] ascending, the features of node k = feat_idx[node_off[k]..node_off[k+1]).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n;                      /* features (KeyFrame::N / Frame::N)                                           */
+    const float* angle;         /* mvKeysUn[i].angle (KeyFrame) / mvKeys[i].angle (Frame), n                    */
+    const uint8_t* desc;        /* mDescriptors, n x 32                                                         */
+    const uint8_t* valid;       /* pMP && !isBad() per feature (:301-305, :775-780, :797-802); NULL = all valid */
+    int n_nodes;
+    const unsigned int* node_id;
+    const int* node_off;        /* n_nodes + 1                                                                  */
+    const unsigned int* feat_idx;
+} pl_bow_view;
+/* mode 0 = C6 SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) — ORBmatcher.cc:247-410: a = key frame, b = frame
+ *          (b.valid ignored); accept best <= TH_LOW && best < nn_ratio * second (:338-341);
+ *          match_out[i] has b.n entries: index of the key-frame feature whose map point went to F feature j, or -1.
+ * mode 1 = C7 SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) — :729-872: accept best < TH_LOW (strict, :814);
+ *          match_out[i] has a.n entries: index of the KF2 feature whose map point went to vpMatches12[idx1], or -1. */
+PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, const pl_bow_view* b, int mode, float nn_ratio,
+                                   int check_orientation, int* const* match_out, int* n_matches);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * D6: the brute-force line matchers (cv::BFMatcher(NORM_HAMMING) + a rule).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* LineMatcher::SearchByProjection(Frame&, KeyFrame*, vector<MapLine*>&) — LineMatcher.cpp:489-525: knnMatch(ref, cur, 2),
+ * accept best/second < 0.75; match_of_line[j] (n_cur entries) = the LAST reference line i whose best match is j
+ * (:511), n_matches counts every hit (:513).  n_cur < 2 (the reference reads out of bounds) gives no match. */
+PL_API int pl_line_match_knn_ratio(pl_match* h, const uint8_t* ref_desc, int n_ref, const uint8_t* cur_desc, int n_cur,
+                                   int* match_of_line, int* n_matches);
+/* LineMatcher::SearchForTriangulation — LineMatcher.cpp:1174-1204 with KeyFrame::lineDescriptorMAD
+ * (KeyFrame.cc:773-797): knnMatch(desc1, desc2, 2); accept query i when d2 - d1 > 0.1 * nn12_mad.
+ * pairs = n1 x 2 ints, the accepted (queryIdx, trainIdx) in query order.  n1 == 0 or n2 < 2 gives no match. */
+PL_API int pl_line_search_for_triangulation(pl_match* h, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, int* pairs,
+                                            int* n_matches, double* nn_mad, double* nn12_mad);
+/* LineMatcher::Fuse, the descriptor half of the active branch — LineMatcher.cpp:1207-1379: for every valid map line
+ * the nearest key-frame line (BruteForce-Hamming match of one row) and the 1.5 * min(100, dist) rule (:1300-1312).
+ * tdx[i] = matched key-frame line or -1; n_fused = number of hits.  The MapLine::Replace bookkeeping stays with
+ * the caller. */
+PL_API int pl_line_fuse_candidates(pl_match* h, const uint8_t* ml_desc, const uint8_t* valid, int n, const uint8_t* kf_desc,
+                                   int n_kf, int* tdx, int* n_fused);
 
 #ifdef __cplusplus
 }

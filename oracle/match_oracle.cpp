@@ -450,3 +450,291 @@ extern "C" int orc_line_match_pairs(const pl_keyline* proj, const uint8_t* proj_
     *n_matches = cnt;
     return 0;
 }
+
+// =================================================================================================================
+// C4 / C5 / C6 / C7 / D6
+// =================================================================================================================
+namespace {
+// MapPoint::PredictScale — src/MapPoint.cc:397-431 (log(float) resolves to logf: `using namespace std` reaches the
+// file through Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:36)
+inline int predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels) {
+    const float ratio = max_distance / current_dist;
+    int nScale = (int)std::ceil(std::log(ratio) / log_scale_factor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= n_levels) nScale = n_levels - 1;
+    return nScale;
+}
+// cv::norm(PO) of a 3x1 CV_32F matrix: double accumulation of exact products, sqrt, returned as double
+inline float norm3(const float* v) {
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += (double)v[k] * v[k];
+    return (float)std::sqrt(s);
+}
+}  // namespace
+
+// ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) — ORBmatcher.cc:1891-2024
+extern "C" int orc_orb_search_keyframe_points(const pl_frame_view* Cp, const pl_posepoint_view* P, const float* ow, float log_scale_factor,
+                                              float th, int orb_dist, int check_orientation, int* match_of_feature, int* n_matches) {
+    const pl_frame_view& C = *Cp;
+    Grid grid(C);
+    std::vector<uint8_t> claimed(C.n);
+    for (int i = 0; i < C.n; i++) { claimed[i] = C.claimed ? (C.claimed[i] != 0) : 0; match_of_feature[i] = -1; }
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < P->n; i++) {
+        if (!P->valid[i]) continue;
+        const float* x3Dw = P->world_pos + 3 * (size_t)i;
+        float x3Dc[3];
+        mat_rx_plus_t(C.tcw, x3Dw, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = (float)(1.0 / x3Dc[2]);
+        const float u = C.fx * xc * invzc + C.cx;
+        const float v = C.fy * yc * invzc + C.cy;
+        if (u < C.min_x || u > C.max_x) continue;
+        if (v < C.min_y || v > C.max_y) continue;
+        const float PO[3] = {x3Dw[0] - ow[0], x3Dw[1] - ow[1], x3Dw[2] - ow[2]};
+        const float dist3D = norm3(PO);
+        const float maxDistance = P->max_dist_inv[i], minDistance = P->min_dist_inv[i];
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = predict_scale(P->max_dist[i], dist3D, log_scale_factor, C.n_levels);
+        const float radius = th * C.scale_factors[nPredictedLevel];
+        grid.in_area(C, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = P->desc + 32 * (size_t)i;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (claimed[i2]) continue;
+            const int dist = descriptor_distance(dMP, C.desc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            match_of_feature[bestIdx2] = i;
+            claimed[bestIdx2] = 1;
+            nmatches++;
+            if (check_orientation) {
+                float rot = P->angle[i] - C.keys_un[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    match_of_feature[rotHist[i][j]] = -1;
+                    nmatches--;
+                }
+    }
+    *n_matches = nmatches;
+    return 0;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) — ORBmatcher.cc:423-554.
+// K->tcw = Rcw | tcw with the scale already divided out; KeyFrame::GetFeaturesInArea (KeyFrame.cc:642-681) has no
+// level filter, the level gate of :527-531 is applied with it here (same set, same order).
+extern "C" int orc_orb_search_sim3_points(const pl_frame_view* Kp, const pl_posepoint_view* P, const float* ow, float log_scale_factor, int th,
+                                          int* match_of_feature, int* n_matches) {
+    const pl_frame_view& K = *Kp;
+    Grid grid(K);
+    std::vector<uint8_t> matched(K.n);
+    for (int i = 0; i < K.n; i++) { matched[i] = K.claimed ? (K.claimed[i] != 0) : 0; match_of_feature[i] = -1; }
+    int nmatches = 0;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < P->n; iMP++) {
+        if (!P->valid[iMP]) continue;
+        const float* p3Dw = P->world_pos + 3 * (size_t)iMP;
+        float p3Dc[3];
+        mat_rx_plus_t(K.tcw, p3Dw, p3Dc);
+        if (p3Dc[2] < 0.0) continue;
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = K.fx * x + K.cx, v = K.fy * y + K.cy;
+        if (!(u >= K.min_x && u < K.max_x && v >= K.min_y && v < K.max_y)) continue;  // KeyFrame::IsInImage (KeyFrame.cc:683-686)
+        const float maxDistance = P->max_dist_inv[iMP], minDistance = P->min_dist_inv[iMP];
+        const float PO[3] = {p3Dw[0] - ow[0], p3Dw[1] - ow[1], p3Dw[2] - ow[2]};
+        const float dist = norm3(PO);
+        if (dist < minDistance || dist > maxDistance) continue;
+        const float* Pn = P->normal + 3 * (size_t)iMP;
+        double dot = 0;  // cv::Mat::dot of CV_32F: double accumulation
+        for (int k = 0; k < 3; k++) dot += (double)PO[k] * Pn[k];
+        if (dot < 0.5 * dist) continue;
+        const int nPredictedLevel = predict_scale(P->max_dist[iMP], dist, log_scale_factor, K.n_levels);
+        const float radius = th * K.scale_factors[nPredictedLevel];
+        grid.in_area(K, u, v, radius, -1, -1, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = P->desc + 32 * (size_t)iMP;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (matched[idx]) continue;
+            const int kpLevel = K.keys_un[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int d = descriptor_distance(dMP, K.desc + 32 * (size_t)idx);
+            if (d < bestDist) { bestDist = d; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) {
+            match_of_feature[bestIdx] = iMP;
+            matched[bestIdx] = 1;
+            nmatches++;
+        }
+    }
+    *n_matches = nmatches;
+    return 0;
+}
+
+// ORBmatcher::SearchByBoW — mode 0: (KeyFrame*, Frame&, vpMapPointMatches) ORBmatcher.cc:247-410;
+//                           mode 1: (KeyFrame*, KeyFrame*, vpMatches12) :729-872
+extern "C" int orc_orb_search_bow(const pl_bow_view* A, const pl_bow_view* B, int mode, float nn_ratio, int check_orientation, int* match_out,
+                                  int* n_matches) {
+    const int n_out = mode == 0 ? B->n : A->n;
+    for (int i = 0; i < n_out; i++) match_out[i] = -1;
+    std::vector<uint8_t> matchedB(B->n, 0);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    int ka = 0, kb = 0;
+    while (ka < A->n_nodes && kb < B->n_nodes) {
+        if (A->node_id[ka] == B->node_id[kb]) {
+            for (int pa = A->node_off[ka]; pa < A->node_off[ka + 1]; pa++) {
+                const int idxA = (int)A->feat_idx[pa];
+                if (A->valid && !A->valid[idxA]) continue;
+                const uint8_t* dA = A->desc + 32 * (size_t)idxA;
+                int bestDist1 = 256, bestIdxB = -1, bestDist2 = 256;
+                for (int pb = B->node_off[kb]; pb < B->node_off[kb + 1]; pb++) {
+                    const int idxB = (int)B->feat_idx[pb];
+                    if (matchedB[idxB]) continue;
+                    if (mode == 1 && B->valid && !B->valid[idxB]) continue;
+                    const int dist = descriptor_distance(dA, B->desc + 32 * (size_t)idxB);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxB = idxB; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                const bool pass = mode == 0 ? bestDist1 <= TH_LOW : bestDist1 < TH_LOW;
+                if (pass && static_cast<float>(bestDist1) < nn_ratio * static_cast<float>(bestDist2)) {
+                    matchedB[bestIdxB] = 1;
+                    if (mode == 0) match_out[bestIdxB] = idxA;
+                    else match_out[idxA] = bestIdxB;
+                    if (check_orientation) {
+                        float rot = A->angle[idxA] - B->angle[bestIdxB];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(mode == 0 ? bestIdxB : idxA);
+                    }
+                    nmatches++;
+                }
+            }
+            ka++;
+            kb++;
+        } else if (A->node_id[ka] < B->node_id[kb]) {
+            while (ka < A->n_nodes && A->node_id[ka] < B->node_id[kb]) ka++;  // lower_bound
+        } else {
+            while (kb < B->n_nodes && B->node_id[kb] < A->node_id[ka]) kb++;
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                match_out[rotHist[i][j]] = -1;
+                nmatches--;
+            }
+        }
+    }
+    *n_matches = nmatches;
+    return 0;
+}
+
+// LineMatcher::SearchByProjection(Frame&, KeyFrame*, vector<MapLine*>&) — LineMatcher.cpp:489-525
+extern "C" int orc_line_match_knn_ratio(const uint8_t* ref_desc, int n_ref, const uint8_t* cur_desc, int n_cur, int* match_of_line, int* n_matches) {
+    for (int j = 0; j < n_cur; j++) match_of_line[j] = -1;
+    *n_matches = 0;
+    if (n_ref <= 0 || n_cur < 2) return 0;
+    std::vector<int> idx(2 * (size_t)n_ref), dist(2 * (size_t)n_ref);
+    orc_hamming_knn2(ref_desc, n_ref, cur_desc, n_cur, idx.data(), dist.data(), 1);
+    int cnt = 0;
+    for (int i = 0; i < n_ref; i++) {
+        const float best = (float)dist[2 * i], better = (float)dist[2 * i + 1];
+        const float distanceRatio = best / better;
+        if (distanceRatio < 0.75) {
+            match_of_line[idx[2 * i]] = i;
+            cnt++;
+        }
+    }
+    *n_matches = cnt;
+    return 0;
+}
+
+// LineMatcher::SearchForTriangulation — LineMatcher.cpp:1174-1204, KeyFrame::lineDescriptorMAD — KeyFrame.cc:773-797
+extern "C" int orc_line_search_for_triangulation(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, int* pairs, int* n_matches,
+                                                 double* nn_mad_out, double* nn12_mad_out) {
+    *n_matches = 0;
+    if (nn_mad_out) *nn_mad_out = 0;
+    if (nn12_mad_out) *nn12_mad_out = 0;
+    if (n1 <= 0 || n2 < 2) return 0;
+    std::vector<int> idx(2 * (size_t)n1), dist(2 * (size_t)n1);
+    orc_hamming_knn2(desc1, n1, desc2, n2, idx.data(), dist.data(), 1);
+    std::vector<float> d0(n1), d1(n1);
+    for (int i = 0; i < n1; i++) { d0[i] = (float)dist[2 * i]; d1[i] = (float)dist[2 * i + 1]; }
+    // nn
+    std::vector<float> a(d0);
+    std::sort(a.begin(), a.end());
+    const double nn_dist_median = a[n1 / 2];
+    for (int i = 0; i < n1; i++) a[i] = fabsf((float)(d0[i] - nn_dist_median));
+    std::sort(a.begin(), a.end());
+    const double nn_mad = 1.4826 * a[n1 / 2];
+    // nn12
+    std::vector<float> e(n1);
+    for (int i = 0; i < n1; i++) e[i] = d1[i] - d0[i];
+    std::sort(e.begin(), e.end());
+    const double nn12_dist_median = e[n1 / 2];
+    std::vector<float> b(n1);
+    for (int i = 0; i < n1; i++) b[i] = fabsf((float)(d1[i] - d0[i] - nn12_dist_median));
+    std::sort(b.begin(), b.end());
+    double nn12_mad = 1.4826 * b[n1 / 2];
+    if (nn_mad_out) *nn_mad_out = nn_mad;
+    if (nn12_mad_out) *nn12_mad_out = nn12_mad;
+    const double nn12_dist_th = nn12_mad * 0.1;
+    int cnt = 0;
+    for (int i = 0; i < n1; i++) {
+        const double dist_12 = d1[i] - d0[i];
+        if (dist_12 > nn12_dist_th) {
+            pairs[2 * cnt] = i;
+            pairs[2 * cnt + 1] = idx[2 * i];
+            cnt++;
+        }
+    }
+    *n_matches = cnt;
+    return 0;
+}
+
+// LineMatcher::Fuse, active branch — LineMatcher.cpp:1296-1330
+extern "C" int orc_line_fuse_candidates(const uint8_t* ml_desc, const uint8_t* valid, int n, const uint8_t* kf_desc, int n_kf, int* tdx,
+                                        int* n_fused) {
+    int fused = 0;
+    for (int i = 0; i < n; i++) {
+        tdx[i] = -1;
+        if ((valid && !valid[i]) || n_kf <= 0) continue;
+        int best = 257, bi = -1;
+        for (int j = 0; j < n_kf; j++) {
+            const int d = descriptor_distance(ml_desc + 32 * (size_t)i, kf_desc + 32 * (size_t)j);
+            if (d < best) { best = d; bi = j; }
+        }
+        double min_dist = 100;
+        const double dist = (float)best;
+        if (dist < min_dist) min_dist = dist;
+        if ((float)best < 1.5 * min_dist) {
+            tdx[i] = bi;
+            fused++;
+        }
+    }
+    *n_fused = fused;
+    return 0;
+}

@@ -43,6 +43,12 @@ ORC_API int orc_orb_search_last_frame(const pl_frame_view* C, const pl_lastframe
 ORC_API int orc_line_iterator_count(float x0, float y0, float x1, float y1, int cols, int rows);
 ORC_API int orc_line_project(const double* start3d, const double* end3d, const pl_keyline* src_kl, const uint8_t* valid, int n, const float tcw[12], float fx, float fy, float cx, float cy, float min_x, float min_y, float max_x, float max_y, int img_cols, int img_rows, pl_keyline* out_kl, int* out_index, int* n_out);
 ORC_API int orc_line_match_pairs(const pl_keyline* proj, const uint8_t* proj_desc, int n_proj, const pl_keyline* cur, const uint8_t* cur_desc, const uint8_t* cur_claimed, int n_cur, int* match_of_line, int* n_matches, int* used_relaxed);
+ORC_API int orc_orb_search_keyframe_points(const pl_frame_view* C, const pl_posepoint_view* P, const float* ow, float log_scale_factor, float th, int orb_dist, int check_orientation, int* match_of_feature, int* n_matches);
+ORC_API int orc_orb_search_sim3_points(const pl_frame_view* K, const pl_posepoint_view* P, const float* ow, float log_scale_factor, int th, int* match_of_feature, int* n_matches);
+ORC_API int orc_orb_search_bow(const pl_bow_view* A, const pl_bow_view* B, int mode, float nn_ratio, int check_orientation, int* match_out, int* n_matches);
+ORC_API int orc_line_match_knn_ratio(const uint8_t* ref_desc, int n_ref, const uint8_t* cur_desc, int n_cur, int* match_of_line, int* n_matches);
+ORC_API int orc_line_search_for_triangulation(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, int* pairs, int* n_matches, double* nn_mad, double* nn12_mad);
+ORC_API int orc_line_fuse_candidates(const uint8_t* ml_desc, const uint8_t* valid, int n, const uint8_t* kf_desc, int n_kf, int* tdx, int* n_fused);
 
 /* ---- line extraction (line_oracle.cpp) ---- */
 ORC_API int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t step, int order_mode, float* xyxy, double* width, double* prec, double* nfa, int cap);

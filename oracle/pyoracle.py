@@ -350,6 +350,58 @@ def line_search_by_projection(cur_view, line_view):
     return res, cnt.value, rel.value, npj
 
 
+def search_keyframe_points(cur_view, pt_view, ow, log_sf, th, orb_dist, check_orientation=True):
+    match = np.empty(max(cur_view.n, 1), np.int32)
+    n = C.c_int(0)
+    o = np.ascontiguousarray(ow, np.float32)
+    lib().orc_orb_search_keyframe_points(C.byref(cur_view), C.byref(pt_view), _p(o), C.c_float(log_sf), C.c_float(th), C.c_int(int(orb_dist)),
+                                         C.c_int(int(check_orientation)), _p(match), C.byref(n))
+    return match[:cur_view.n], n.value
+
+
+def search_sim3_points(kf_view, pt_view, ow, log_sf, th):
+    match = np.empty(max(kf_view.n, 1), np.int32)
+    n = C.c_int(0)
+    o = np.ascontiguousarray(ow, np.float32)
+    lib().orc_orb_search_sim3_points(C.byref(kf_view), C.byref(pt_view), _p(o), C.c_float(log_sf), C.c_int(int(th)), _p(match), C.byref(n))
+    return match[:kf_view.n], n.value
+
+
+def search_bow(a_view, b_view, mode, nn_ratio, check_orientation=True):
+    sz = b_view.n if mode == 0 else a_view.n
+    match = np.empty(max(sz, 1), np.int32)
+    n = C.c_int(0)
+    lib().orc_orb_search_bow(C.byref(a_view), C.byref(b_view), C.c_int(mode), C.c_float(nn_ratio), C.c_int(int(check_orientation)), _p(match),
+                             C.byref(n))
+    return match[:sz], n.value
+
+
+def line_match_knn_ratio(ref_desc, cur_desc):
+    r, c = _rows(ref_desc), _rows(cur_desc)
+    match = np.full(max(c.shape[0], 1), -1, np.int32)
+    n = C.c_int(0)
+    lib().orc_line_match_knn_ratio(_p(r), C.c_int(r.shape[0]), _p(c), C.c_int(c.shape[0]), _p(match), C.byref(n))
+    return match[:c.shape[0]], n.value
+
+
+def line_search_for_triangulation(desc1, desc2):
+    a, b = _rows(desc1), _rows(desc2)
+    pairs = np.zeros((max(a.shape[0], 1), 2), np.int32)
+    n = C.c_int(0)
+    m1, m2 = C.c_double(0), C.c_double(0)
+    lib().orc_line_search_for_triangulation(_p(a), C.c_int(a.shape[0]), _p(b), C.c_int(b.shape[0]), _p(pairs), C.byref(n), C.byref(m1), C.byref(m2))
+    return pairs[:n.value].copy(), m1.value, m2.value
+
+
+def line_fuse_candidates(ml_desc, valid, kf_desc):
+    a, b = _rows(ml_desc), _rows(kf_desc)
+    va = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    tdx = np.full(max(a.shape[0], 1), -1, np.int32)
+    n = C.c_int(0)
+    lib().orc_line_fuse_candidates(_p(a), _p(va) if va is not None else None, C.c_int(a.shape[0]), _p(b), C.c_int(b.shape[0]), _p(tdx), C.byref(n))
+    return tdx[:a.shape[0]], n.value
+
+
 class OracleBackend:
     """CPU-oracle backend for frontend.TrackingFrontEnd (same interface as frontend.GpuBackend)."""
 

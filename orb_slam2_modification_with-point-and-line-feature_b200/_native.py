@@ -178,3 +178,54 @@ def make_lineframe_view(kl, desc, claimed, tcw, K, bounds, img_size, keep):
     v.min_x, v.min_y, v.max_x, v.max_y = [float(b) for b in bounds]
     v.cols, v.rows = int(img_size[0]), int(img_size[1])
     return v
+
+
+class PosePointView(C.Structure):
+    """pl_posepoint_view: map points offered to the pose-based projection searches (C4 / C5)."""
+    _fields_ = [("n", C.c_int), ("valid", C.c_void_p), ("world_pos", C.c_void_p), ("desc", C.c_void_p), ("min_dist_inv", C.c_void_p),
+                ("max_dist_inv", C.c_void_p), ("max_dist", C.c_void_p), ("angle", C.c_void_p), ("normal", C.c_void_p)]
+
+
+def make_posepoint_view(valid, world_pos, desc, min_dist_inv, max_dist_inv, max_dist, angle, normal, keep):
+    valid = np.ascontiguousarray(valid, np.uint8)
+    wp = np.ascontiguousarray(world_pos, np.float32).reshape(-1, 3)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    mi = np.ascontiguousarray(min_dist_inv, np.float32)
+    ma = np.ascontiguousarray(max_dist_inv, np.float32)
+    mr = np.ascontiguousarray(max_dist, np.float32)
+    an = None if angle is None else np.ascontiguousarray(angle, np.float32)
+    no = None if normal is None else np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    keep += [valid, wp, desc, mi, ma, mr, an, no]
+    v = PosePointView()
+    v.n = len(valid)
+    v.valid, v.world_pos, v.desc, v.min_dist_inv, v.max_dist_inv, v.max_dist = _addr(valid), _addr(wp), _addr(desc), _addr(mi), _addr(ma), _addr(mr)
+    v.angle, v.normal = _addr(an), _addr(no)
+    return v
+
+
+class BowView(C.Structure):
+    """pl_bow_view: one side of ORBmatcher::SearchByBoW (features + flattened DBoW2::FeatureVector)."""
+    _fields_ = [("n", C.c_int), ("angle", C.c_void_p), ("desc", C.c_void_p), ("valid", C.c_void_p), ("n_nodes", C.c_int),
+                ("node_id", C.c_void_p), ("node_off", C.c_void_p), ("feat_idx", C.c_void_p)]
+
+
+def make_bow_view(angle, desc, valid, feat_vec, keep):
+    """feat_vec: dict node id -> list of feature indices (DBoW2::FeatureVector); flattened in key order."""
+    angle = np.ascontiguousarray(angle, np.float32)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    valid = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    ids = sorted(feat_vec.keys())
+    node_id = np.asarray(ids, np.uint32)
+    off = np.zeros(len(ids) + 1, np.int32)
+    feats = []
+    for k, nid in enumerate(ids):
+        feats.extend(int(x) for x in feat_vec[nid])
+        off[k + 1] = len(feats)
+    feat_idx = np.asarray(feats, np.uint32)
+    keep += [angle, desc, valid, node_id, off, feat_idx]
+    v = BowView()
+    v.n = len(angle)
+    v.angle, v.desc, v.valid = _addr(angle), _addr(desc), _addr(valid)
+    v.n_nodes = len(ids)
+    v.node_id, v.node_off, v.feat_idx = _addr(node_id), _addr(off), _addr(feat_idx)
+    return v

@@ -395,3 +395,71 @@ class DescriptorMatcher:
         nulls = (C.c_void_p * n)()
         check(N.lib().pl_line_search_by_projection_batch(self._h, C.c_int(n), ca, la, ptrs, ptr(cnt), ptr(rel), nulls, nulls, ptr(npj)))
         return [(outs[i][:cur_views[i].n], int(cnt[i]), int(rel[i]), int(npj[i])) for i in range(n)]
+
+    # ---- C4 / C5: pose-based projection searches ----
+    def _pose_points(self, fn, frame_views, pt_views, ow, log_sf, *scalars):
+        n = len(frame_views)
+        fa = self._view_array(frame_views, N.FrameView)
+        pa = self._view_array(pt_views, N.PosePointView)
+        ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+        ls = np.ascontiguousarray(log_sf, np.float32).reshape(-1)
+        assert ow.shape[0] == n and ls.shape[0] == n
+        outs = [np.empty(max(v.n, 1), np.int32) for v in frame_views]
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        cnt = np.zeros(max(n, 1), np.int32)
+        check(fn(self._h, C.c_int(n), fa, pa, ptr(ow), ptr(ls), *scalars, ptrs, ptr(cnt)))
+        return [(outs[i][:frame_views[i].n], int(cnt[i])) for i in range(n)]
+
+    def SearchByProjectionKeyFrameBatch(self, cur_views, pt_views, ow, log_scale_factor, th, orb_dist, check_orientation=True):
+        """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) for n calls ->
+        [(match_of_feature -> key-frame feature index or -1, nmatches)]."""
+        return self._pose_points(N.lib().pl_orb_search_keyframe_points_batch, cur_views, pt_views, ow, log_scale_factor, C.c_float(th),
+                                 C.c_int(int(orb_dist)), C.c_int(int(check_orientation)))
+
+    def SearchByProjectionSim3Batch(self, kf_views, pt_views, ow, log_scale_factor, th):
+        """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) for n calls ->
+        [(match_of_feature -> index into vpPoints or -1, nmatches)]."""
+        return self._pose_points(N.lib().pl_orb_search_sim3_points_batch, kf_views, pt_views, ow, log_scale_factor, C.c_int(int(th)))
+
+    # ---- C6 / C7: SearchByBoW ----
+    def SearchByBoWBatch(self, a_views, b_views, mode, nn_ratio, check_orientation=True):
+        """mode 0: SearchByBoW(pKF, F, vpMapPointMatches) -> per call (match over F features -> KF feature, nmatches);
+        mode 1: SearchByBoW(pKF1, pKF2, vpMatches12) -> per call (match over KF1 features -> KF2 feature, nmatches)."""
+        n = len(a_views)
+        aa = self._view_array(a_views, N.BowView)
+        ba = self._view_array(b_views, N.BowView)
+        sizes = [(b_views[i].n if mode == 0 else a_views[i].n) for i in range(n)]
+        outs = [np.empty(max(sz, 1), np.int32) for sz in sizes]
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        cnt = np.zeros(max(n, 1), np.int32)
+        check(N.lib().pl_orb_search_bow_batch(self._h, C.c_int(n), aa, ba, C.c_int(mode), C.c_float(nn_ratio), C.c_int(int(check_orientation)),
+                                              ptrs, ptr(cnt)))
+        return [(outs[i][:sizes[i]], int(cnt[i])) for i in range(n)]
+
+    # ---- D6: brute-force line matchers ----
+    def LineMatchKnnRatio(self, ref_desc, cur_desc):
+        """LineMatcher::SearchByProjection(CurrentFrame, RefFrame, vpMapLineMatches) -> (match_of_line, nmatches)."""
+        r, c = self._rows(ref_desc), self._rows(cur_desc)
+        match = np.full(max(c.shape[0], 1), -1, np.int32)
+        n = C.c_int(0)
+        check(N.lib().pl_line_match_knn_ratio(self._h, ptr(r), C.c_int(r.shape[0]), ptr(c), C.c_int(c.shape[0]), ptr(match), C.byref(n)))
+        return match[:c.shape[0]], n.value
+
+    def LineSearchForTriangulation(self, desc1, desc2):
+        """LineMatcher::SearchForTriangulation -> (pairs [k,2], nn_mad, nn12_mad)."""
+        a, b = self._rows(desc1), self._rows(desc2)
+        pairs = np.zeros((max(a.shape[0], 1), 2), np.int32)
+        n = C.c_int(0)
+        m1, m2 = C.c_double(0), C.c_double(0)
+        check(N.lib().pl_line_search_for_triangulation(self._h, ptr(a), C.c_int(a.shape[0]), ptr(b), C.c_int(b.shape[0]), ptr(pairs),
+                                                       C.byref(n), C.byref(m1), C.byref(m2)))
+        return pairs[:n.value].copy(), m1.value, m2.value
+
+    def LineFuseCandidates(self, ml_desc, valid, kf_desc):
+        """LineMatcher::Fuse, descriptor half -> (tdx per map line or -1, nFused)."""
+        a, b = self._rows(ml_desc), self._rows(kf_desc)
+        va = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+        tdx = np.full(max(a.shape[0], 1), -1, np.int32)
+        n = C.c_int(0)
+        check(N.lib().pl_line_fuse_candidates(self._h, ptr(a), ptr(va), C.c_int(a.shape[0]), ptr(b), C.c_int(b.shape[0]), ptr(tdx), C.byref(n)))
+        return tdx[:a.shape[0]], n.value

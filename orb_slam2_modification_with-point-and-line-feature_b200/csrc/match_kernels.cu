@@ -120,6 +120,11 @@ int knn2_launch(pl_match* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int
 }
 }  // namespace
 
+// used by bow_kernels.cu (the D6 line matchers)
+int pl_knn2_launch_dev(pl_match* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int* d_idx, int* d_dist) {
+    return knn2_launch(h, d_q, nq, d_t, nt, d_idx, d_dist);
+}
+
 extern "C" {
 
 PL_API int pl_match_create(pl_match** out, int device) {

@@ -133,6 +133,52 @@ __host__ __device__ __forceinline__ float glibc_sincosf(float y, int is_cos) {
     const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
     return sincosf_poly(x * sgn, x * x, (n & 2) != 0, n ^ is_cos);
 }
+
+// glibc logf (sysdeps/ieee754/flt-32/e_logf.c, the ARM optimized-routines algorithm) for normal positive finite x:
+// table of 16 (1/c, log c) pairs + cubic in double.  Checked against the host libm on all 2,130,706,432 normal positive
+// floats, with and without FMA contraction (tests/test_sincos.py).
+__host__ __device__ __forceinline__ float glibc_logf(float x) {
+    const double T[16][2] = {
+        {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, {0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2},
+        {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3}, {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3},
+        {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4}, {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5},
+        {0x1p+0, 0x0p+0},                              {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4},
+        {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3},  {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},
+        {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+    const double Ln2 = 0x1.62e42fefa39efp-1, A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+    uint32_t ix;
+#ifdef __CUDA_ARCH__
+    ix = __float_as_uint(x);
+#else
+    memcpy(&ix, &x, 4);
+#endif
+    if (ix == 0x3f800000u) return 0.f;
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int32_t)tmp >> 23;
+    const uint32_t iz = ix - (tmp & (0x1ffu << 23));
+    float zf;
+#ifdef __CUDA_ARCH__
+    zf = __uint_as_float(iz);
+    const double z = (double)zf;
+    const double r = __dadd_rn(__dmul_rn(z, T[i][0]), -1.0);
+    const double y0 = __dadd_rn(T[i][1], __dmul_rn((double)k, Ln2));
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(A1, r), A2);
+    y = __dadd_rn(__dmul_rn(A0, r2), y);
+    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+#else
+    memcpy(&zf, &iz, 4);
+    const double z = (double)zf;
+    const double r = z * T[i][0] - 1.0;
+    const double y0 = T[i][1] + (double)k * Ln2;
+    const double r2 = r * r;
+    double y = A1 * r + A2;
+    y = A0 * r2 + y;
+    y = y * r2 + (y0 + r);
+#endif
+    return (float)y;
+}
 #endif  // __CUDACC__
 
 }  // namespace pl

@@ -19,7 +19,7 @@
 namespace pl {
 
 constexpr int kGridCols = 64, kGridRows = 48, kGridCells = kGridCols * kGridRows;  // include/Frame.h
-constexpr int kThHigh = 100, kHistoLen = 30;                                        // ORBmatcher.cc:49-51
+constexpr int kThHigh = 100, kThLow = 50, kHistoLen = 30;                           // ORBmatcher.cc:49-51
 
 struct FrameDev {
     int n;
@@ -30,6 +30,7 @@ struct FrameDev {
     float min_x, min_y, max_x, max_y, fx, fy, cx, cy, bf, b;
     float tcw[12];
     float sf[kMaxLevels];
+    int n_levels;
     float inv_w, inv_h;  // mfGridElementWidthInv / HeightInv (Frame.cc:184-185)
 };
 // one search instance: a frame and the points projected into it (Last-frame features for C3, local map points for C2)
@@ -44,6 +45,8 @@ struct SearchDev {
     const float* angle;        // C3
     const float *proj_x, *proj_y, *proj_xr, *view_cos;  // C2
     int forward, backward;     // C3
+    const float *min_inv, *max_inv, *max_raw, *normal;  // C4 / C5: distance invariance, mfMaxDistance, viewing normal (C5)
+    float ow[3], log_sf;                                  // C4 / C5: camera centre, mfLogScaleFactor
     int pt_base, feat_base, sort_base, n2;  // offsets into the batch-wide scratch arrays
 };
 
@@ -154,7 +157,8 @@ __device__ __forceinline__ float mat_row(const float* T, int r, float X, float Y
 }
 
 // phase A, run twice: FILL == false counts the candidates of every point (cand_n), FILL == true writes them at the
-// CSR offsets.  MODE 0 = C3 (ORBmatcher.cc:1746-1830 without the claim check), 1 = C2 (ORBmatcher.cc:84-149).
+// CSR offsets.  MODE 0 = C3 (ORBmatcher.cc:1746-1830 without the claim check), 1 = C2 (ORBmatcher.cc:84-149),
+// 2 = C4 (ORBmatcher.cc:1909-1960), 3 = C5 (ORBmatcher.cc:451-531).
 template <int MODE, bool FILL>
 __global__ void __launch_bounds__(256) k_candidates(const SearchDev* __restrict__ SD, float th, const int* __restrict__ sorted_idx,
                                                     const int* __restrict__ cell_start, int* __restrict__ cand_n,
@@ -190,6 +194,49 @@ __global__ void __launch_bounds__(256) k_candidates(const SearchDev* __restrict_
                     else { minL = oct - 1; maxL = oct + 1; }
                     const float ur = __fsub_rn(u, __fmul_rn(F.bf, invzc));
                     count = gather_candidates(F, sidx, cst, u, v, radius, minL, maxL, ur, radius, q0, q1, out);
+                }
+            }
+        } else if (MODE == 2 || MODE == 3) {
+            const float X = S.world_pos[3 * (size_t)i], Y = S.world_pos[3 * (size_t)i + 1], Z = S.world_pos[3 * (size_t)i + 2];
+            const float xc = mat_row(F.tcw, 0, X, Y, Z), yc = mat_row(F.tcw, 1, X, Y, Z), zc = mat_row(F.tcw, 2, X, Y, Z);
+            float u, v;
+            bool ok;
+            if (MODE == 2) {
+                const float invzc = (float)(1.0 / (double)zc);
+                u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, xc), invzc), F.cx);
+                v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, yc), invzc), F.cy);
+                ok = !(u < F.min_x || u > F.max_x) && !(v < F.min_y || v > F.max_y);
+            } else {
+                ok = !(zc < 0.0f);
+                const float invz = __fdiv_rn(1.0f, zc);
+                u = __fadd_rn(__fmul_rn(F.fx, __fmul_rn(xc, invz)), F.cx);
+                v = __fadd_rn(__fmul_rn(F.fy, __fmul_rn(yc, invz)), F.cy);
+                ok = ok && (u >= F.min_x && u < F.max_x && v >= F.min_y && v < F.max_y);  // KeyFrame::IsInImage
+            }
+            if (ok) {
+                const float px = __fsub_rn(X, S.ow[0]), py = __fsub_rn(Y, S.ow[1]), pz = __fsub_rn(Z, S.ow[2]);
+                // cv::norm of a 3x1 CV_32F: exact products accumulated in double, sqrt
+                double ss = __dmul_rn((double)px, (double)px);
+                ss = __dadd_rn(ss, __dmul_rn((double)py, (double)py));
+                ss = __dadd_rn(ss, __dmul_rn((double)pz, (double)pz));
+                const float dist3D = (float)sqrt(ss);
+                ok = !(dist3D < S.min_inv[i] || dist3D > S.max_inv[i]);
+                if (ok && MODE == 3) {
+                    const float* nrm = S.normal + 3 * (size_t)i;
+                    double dot = __dmul_rn((double)px, (double)nrm[0]);  // cv::Mat::dot: double accumulation
+                    dot = __dadd_rn(dot, __dmul_rn((double)py, (double)nrm[1]));
+                    dot = __dadd_rn(dot, __dmul_rn((double)pz, (double)nrm[2]));
+                    ok = !(dot < __dmul_rn(0.5, (double)dist3D));
+                }
+                if (ok) {
+                    // MapPoint::PredictScale (MapPoint.cc:397-431)
+                    const float ratio = __fdiv_rn(S.max_raw[i], dist3D);
+                    int lvl = (int)ceilf(__fdiv_rn(glibc_logf(ratio), S.log_sf));
+                    if (lvl < 0) lvl = 0;
+                    else if (lvl >= F.n_levels) lvl = F.n_levels - 1;
+                    const float radius = __fmul_rn(th, F.sf[lvl]);
+                    // C4: window lvl-1..lvl+1; C5: KeyFrame::GetFeaturesInArea + the level gate of :527-531
+                    count = gather_candidates(F, sidx, cst, u, v, radius, lvl - 1, MODE == 2 ? lvl + 1 : lvl, 0.f, __int_as_float(0x7f800000), q0, q1, out);
                 }
             }
         } else {
@@ -278,8 +325,9 @@ __device__ int resolve_load_chunk(unsigned int* s_cand, const unsigned int* __re
     return p1;
 }
 
-// C3 phase B (ORBmatcher.cc:1802-1876)
-__global__ void __launch_bounds__(kResThreads) k_last_frame_resolve(const SearchDev* __restrict__ SD, int check_orientation,
+// C3 phase B (ORBmatcher.cc:1802-1876); also C4 (:1962-2021, th_dist = ORBdist) and C5 (:519-547, th_dist = TH_LOW, no
+// orientation check): best unclaimed candidate per point, claims in point order, rotation histogram
+__global__ void __launch_bounds__(kResThreads) k_last_frame_resolve(const SearchDev* __restrict__ SD, int check_orientation, int th_dist,
                                                                     const unsigned int* __restrict__ cand_all, const int* __restrict__ cand_n,
                                                                     const int* __restrict__ cand_off, const int* __restrict__ inst_base,
                                                                     const int* __restrict__ totals, int* __restrict__ match_all,
@@ -329,7 +377,7 @@ __global__ void __launch_bounds__(kResThreads) k_last_frame_resolve(const Search
                 }
                 if (best == 0xFFFFFFFFu) continue;
                 const int bestDist = (int)(best >> 16);
-                if (bestDist <= kThHigh) {
+                if (bestDist <= th_dist) {
                     const int bestIdx2 = (int)(cd[best & 0xFFFFu] & 0xFFFFu);
                     if (lane == 0) {
                         match[bestIdx2] = i;
@@ -768,6 +816,7 @@ void put_frame(PlStage& st, const pl_frame_view& F, FrameDev& D) {
     D.fx = F.fx; D.fy = F.fy; D.cx = F.cx; D.cy = F.cy; D.bf = F.bf; D.b = F.b;
     for (int i = 0; i < 12; i++) D.tcw[i] = F.tcw[i];
     for (int i = 0; i < kMaxLevels; i++) D.sf[i] = i < F.n_levels ? F.scale_factors[i] : 0.f;
+    D.n_levels = F.n_levels;
     D.inv_w = (float)kGridCols / (F.max_x - F.min_x);
     D.inv_h = (float)kGridRows / (F.max_y - F.min_y);
 }
@@ -780,7 +829,8 @@ struct BatchScratch {
 // the common pipeline of C2 / C3 once the SearchDev array is packed: grid -> count -> scan -> fill -> resolve
 template <int MODE>
 int run_search(pl_match* h, const std::vector<SearchDev>& host_sd, const SearchDev* d_sd, int n, int total_feats, int total_pts, int total_n2,
-               int max_n2, int max_np, int max_feat, float th, float nn_ratio, int check_ori, int* const* match_out, int* n_matches) {
+               int max_n2, int max_np, int max_feat, float th, float nn_ratio, int check_ori, int* const* match_out, int* n_matches,
+               int th_dist = kThHigh) {
     cudaStream_t st = h->stream;
     BatchScratch B;
     int rc;
@@ -817,9 +867,9 @@ int run_search(pl_match* h, const std::vector<SearchDev>& host_sd, const SearchD
     PL_CUDA_TRY(cudaMemcpyAsync(B.inst_base, h_base, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     k_candidates<MODE, true><<<cgrid, 256, 0, st>>>(d_sd, th, B.sorted_idx, B.cell_start, B.cand_n, B.cand_off, B.inst_base, B.cand);
     const size_t rsm = (size_t)kResChunkCand * 4 + (size_t)std::max(max_feat, 1) + 16;
-    if (MODE == 0) {
+    if (MODE != 1) {
         PL_CUDA_TRY(cudaFuncSetAttribute(k_last_frame_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-        k_last_frame_resolve<<<n, kResThreads, rsm, st>>>(d_sd, check_ori, B.cand, B.cand_n, B.cand_off, B.inst_base, B.totals, B.match, B.rec, B.out);
+        k_last_frame_resolve<<<n, kResThreads, rsm, st>>>(d_sd, check_ori, th_dist, B.cand, B.cand_n, B.cand_off, B.inst_base, B.totals, B.match, B.rec, B.out);
     } else {
         PL_CUDA_TRY(cudaFuncSetAttribute(k_local_points_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
         k_local_points_resolve<<<n, kResThreads, rsm, st>>>(d_sd, nn_ratio, B.cand, B.cand_n, B.cand_off, B.inst_base, B.totals, B.match, B.out);
@@ -966,6 +1016,76 @@ PL_API int pl_orb_search_local_points(pl_match* h, const pl_frame_view* F, const
     PL_CHECK_ARG(F && mps && match_of_feature && n_matches);
     int* mo[1] = {match_of_feature};
     return pl_orb_search_local_points_batch(h, 1, F, mps, th, nn_ratio, mo, n_matches);
+}
+
+}  // extern "C"
+
+// C4 / C5 share the packing: pose-based projection of map points described by pl_posepoint_view
+namespace {
+template <int MODE>
+int pose_points_search(pl_match* h, int n, const pl_frame_view* fr, const pl_posepoint_view* pts, const float* ow, const float* log_sf, float th,
+                       int th_dist, int check_orientation, int* const* match_of_feature, int* n_matches) {
+    PL_CHECK_ARG(h && n >= 0 && (n == 0 || (fr && pts && ow && log_sf && match_of_feature && n_matches)));
+    if (n == 0) return PL_OK;
+    size_t bytes = padb(sizeof(SearchDev) * (size_t)n);
+    int total_feats = 0, total_pts = 0, total_n2 = 0, max_n2 = 1, max_np = 0, max_feat = 0;
+    for (int i = 0; i < n; i++) {
+        int rc = check_frame(&fr[i]);
+        if (rc != PL_OK) return rc;
+        const pl_posepoint_view& P = pts[i];
+        PL_CHECK_ARG(P.n >= 0 && (P.n == 0 || (P.valid && P.world_pos && P.desc && P.min_dist_inv && P.max_dist_inv && P.max_dist)));
+        PL_CHECK_ARG(P.n == 0 || (MODE == 2 ? (!check_orientation || P.angle) : P.normal != nullptr));
+        PL_CHECK_ARG(log_sf[i] > 0.f);
+        PL_CHECK_ARG(match_of_feature[i] != nullptr || fr[i].n == 0);
+        bytes += frame_bytes(fr[i]) + padb((size_t)P.n) + padb((size_t)P.n * 12) * 2 + padb((size_t)P.n * 32) + padb((size_t)P.n * 4) * 4;
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    int rc = h->in.reserve(bytes);
+    if (rc != PL_OK) return rc;
+    std::vector<SearchDev> sd(n);
+    for (int i = 0; i < n; i++) {
+        SearchDev& S = sd[i];
+        memset(&S, 0, sizeof(S));
+        put_frame(h->in, fr[i], S.F);
+        const pl_posepoint_view& P = pts[i];
+        S.np = P.n;
+        S.valid = h->in.put(P.valid, (size_t)P.n);
+        S.world_pos = h->in.put(P.world_pos, (size_t)P.n * 3);
+        S.pdesc = (const uint4*)h->in.put(P.desc, (size_t)P.n * 32);
+        S.min_inv = h->in.put(P.min_dist_inv, (size_t)P.n);
+        S.max_inv = h->in.put(P.max_dist_inv, (size_t)P.n);
+        S.max_raw = h->in.put(P.max_dist, (size_t)P.n);
+        S.angle = (MODE == 2 && P.angle) ? h->in.put(P.angle, (size_t)P.n) : nullptr;
+        S.normal = MODE == 3 ? h->in.put(P.normal, (size_t)P.n * 3) : nullptr;
+        S.has_obs = nullptr;  // a feature that received a map point is taken (:1965, :521)
+        for (int k = 0; k < 3; k++) S.ow[k] = ow[3 * (size_t)i + k];
+        S.log_sf = log_sf[i];
+        int n2 = 1;
+        while (n2 < std::max(fr[i].n, 1)) n2 <<= 1;
+        S.n2 = n2;
+        S.pt_base = total_pts; S.feat_base = total_feats; S.sort_base = total_n2;
+        total_pts += P.n; total_feats += fr[i].n; total_n2 += n2;
+        max_n2 = std::max(max_n2, n2); max_np = std::max(max_np, P.n); max_feat = std::max(max_feat, fr[i].n);
+    }
+    const SearchDev* d_sd = h->in.put(sd.data(), (size_t)n);
+    PL_CUDA_TRY(cudaMemcpyAsync(h->in.d, h->in.h, h->in.cur, cudaMemcpyHostToDevice, h->stream));
+    return run_search<MODE>(h, sd, d_sd, n, total_feats, total_pts, total_n2, max_n2, max_np, max_feat, th, 0.f, check_orientation,
+                            match_of_feature, n_matches, th_dist);
+}
+}  // namespace
+
+extern "C" {
+
+PL_API int pl_orb_search_keyframe_points_batch(pl_match* h, int n, const pl_frame_view* cur, const pl_posepoint_view* pts, const float* ow,
+                                               const float* log_scale_factor, float th, int orb_dist, int check_orientation,
+                                               int* const* match_of_feature, int* n_matches) {
+    return pose_points_search<2>(h, n, cur, pts, ow, log_scale_factor, th, orb_dist, check_orientation, match_of_feature, n_matches);
+}
+
+PL_API int pl_orb_search_sim3_points_batch(pl_match* h, int n, const pl_frame_view* kf, const pl_posepoint_view* pts, const float* ow,
+                                           const float* log_scale_factor, int th, int* const* match_of_feature, int* n_matches) {
+    return pose_points_search<3>(h, n, kf, pts, ow, log_scale_factor, (float)th, kThLow, 0, match_of_feature, n_matches);
 }
 
 // ---- LineMatcher ----
