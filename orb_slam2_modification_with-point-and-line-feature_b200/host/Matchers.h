@@ -7,6 +7,7 @@
 #pragma once
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "plslam_cvlite.h"
@@ -40,6 +41,49 @@ public:
         match_of_feature.resize(CurrentFrame.n > 0 ? CurrentFrame.n : 1);
         check(pl_orb_search_last_frame(h_, &CurrentFrame, &LastFrame, th, bMono ? 1 : 0, mbCheckOrientation ? 1 : 0, match_of_feature.data(), &n));
         match_of_feature.resize(CurrentFrame.n);
+        return n;
+    }
+    // SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1891-2024)
+    // KFpoints = pKF->GetMapPointMatches() as a pl_posepoint_view (valid = pMP && !isBad && !sAlreadyFound.count(pMP));
+    // Ow = CurrentFrame.mOw, logScaleFactor = CurrentFrame.mfLogScaleFactor; CurrentFrame.claimed[i] = (mvpMapPoints[i] != NULL)
+    int SearchByProjection(const pl_frame_view& CurrentFrame, const pl_posepoint_view& KFpoints, const float Ow[3], float logScaleFactor, float th,
+                           int ORBdist, std::vector<int>& match_of_feature) {
+        int n = 0;
+        match_of_feature.resize(CurrentFrame.n > 0 ? CurrentFrame.n : 1);
+        int* mo[1] = {match_of_feature.data()};
+        check(pl_orb_search_keyframe_points_batch(h_, 1, &CurrentFrame, &KFpoints, Ow, &logScaleFactor, th, ORBdist, mbCheckOrientation ? 1 : 0, mo, &n));
+        match_of_feature.resize(CurrentFrame.n);
+        return n;
+    }
+    // SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th) (ORBmatcher.cc:423-554)
+    // KF.tcw = Rcw | tcw with the scale divided out (:435-438), Ow = -Rcw^T tcw (:439), KF.claimed[i] = (vpMatched[i] != NULL)
+    int SearchByProjection(const pl_frame_view& KF, const float Ow[3], float logScaleFactor, const pl_posepoint_view& vpPoints, int th,
+                           std::vector<int>& match_of_feature) {
+        int n = 0;
+        match_of_feature.resize(KF.n > 0 ? KF.n : 1);
+        int* mo[1] = {match_of_feature.data()};
+        check(pl_orb_search_sim3_points_batch(h_, 1, &KF, &vpPoints, Ow, &logScaleFactor, th, mo, &n));
+        match_of_feature.resize(KF.n);
+        return n;
+    }
+    // SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) (ORBmatcher.cc:247-410):
+    // match_of_F_feature[j] = index of the key-frame feature whose map point goes to vpMapPointMatches[j], or -1
+    int SearchByBoW(const pl_bow_view& KF, const pl_bow_view& F, std::vector<int>& match_of_F_feature) {
+        int n = 0;
+        match_of_F_feature.resize(F.n > 0 ? F.n : 1);
+        int* mo[1] = {match_of_F_feature.data()};
+        check(pl_orb_search_bow_batch(h_, 1, &KF, &F, 0, mfNNratio, mbCheckOrientation ? 1 : 0, mo, &n));
+        match_of_F_feature.resize(F.n);
+        return n;
+    }
+    // SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (ORBmatcher.cc:729-872):
+    // match12[idx1] = index of the KF2 feature whose map point goes to vpMatches12[idx1], or -1
+    int SearchByBoW(const pl_bow_view& KF1, const pl_bow_view& KF2, std::vector<int>& match12, bool /*keyframe pair*/) {
+        int n = 0;
+        match12.resize(KF1.n > 0 ? KF1.n : 1);
+        int* mo[1] = {match12.data()};
+        check(pl_orb_search_bow_batch(h_, 1, &KF1, &KF2, 1, mfNNratio, mbCheckOrientation ? 1 : 0, mo, &n));
+        match12.resize(KF1.n);
         return n;
     }
     pl_match* handle() { return h_; }
@@ -85,7 +129,33 @@ public:
         if (used_relaxed) *used_relaxed = rel != 0;
         return n;
     }
-    // SearchByProjection(Frame&, KeyFrame*, vector<MapLine*>&) brute-force variant (LineMatcher.cpp:492-525): kNN-2
+    // SearchByProjection(Frame &CurrentFrame, KeyFrame *RefFrame, vector<MapLine*> &vpMapLineMatches) (LineMatcher.cpp:489-525):
+    // match_of_line[j] = index of the reference line whose MapLine goes to vpMapLineMatches[j], or -1
+    int SearchByProjection(const uint8_t* ref_desc, int n_ref, const uint8_t* cur_desc, int n_cur, std::vector<int>& match_of_line) {
+        int n = 0;
+        match_of_line.assign(n_cur > 0 ? n_cur : 1, -1);
+        check(pl_line_match_knn_ratio(h_, ref_desc, n_ref, cur_desc, n_cur, match_of_line.data(), &n));
+        match_of_line.resize(n_cur);
+        return n;
+    }
+    // SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, vector<pair<size_t,size_t>> &vMatchedPairs, bOnlyStereo) (LineMatcher.cpp:1174-1204)
+    int SearchForTriangulation(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs) {
+        int n = 0;
+        std::vector<int> pairs(2 * (size_t)(n1 > 0 ? n1 : 1));
+        check(pl_line_search_for_triangulation(h_, desc1, n1, desc2, n2, pairs.data(), &n, nullptr, nullptr));
+        vMatchedPairs.clear();
+        for (int i = 0; i < n; i++) vMatchedPairs.push_back(std::make_pair((size_t)pairs[2 * i], (size_t)pairs[2 * i + 1]));
+        return n;
+    }
+    // Fuse(KeyFrame *pKF, const vector<MapLine*> &vpMapLines), descriptor half (LineMatcher.cpp:1296-1330): tdx[i] = key-frame line
+    // the caller hands to MapLine::Replace, or -1
+    int FuseCandidates(const uint8_t* ml_desc, const uint8_t* valid, int n, const uint8_t* kf_desc, int n_kf, std::vector<int>& tdx) {
+        int nf = 0;
+        tdx.assign(n > 0 ? n : 1, -1);
+        check(pl_line_fuse_candidates(h_, ml_desc, valid, n, kf_desc, n_kf, tdx.data(), &nf));
+        tdx.resize(n);
+        return nf;
+    }
     void KnnMatch2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist) { check(pl_hamming_knn2(h_, q, nq, t, nt, idx, dist)); }
 
     // thresholds of LineMatcher.h:94-98 (used inside the CUDA predicate)
