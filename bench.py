@@ -309,7 +309,7 @@ def run_ours(a, rank, world, local_rank, dist):
     ach = alg_bytes.get(dom, 0) * F / (stage[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6),
                 "traffic": None, "peak_source": peak_src,
-                "note": "k_lsd_grow is the ordered (sequential-semantics) region grower: one warp per frame, latency-bound, not a streaming kernel",
+                "note": "k_lsd_grow is the ordered (sequential-semantics) region grower, run as speculative transactions with in-order commit (DESIGN.md 4.1): latency-bound, not a streaming kernel; the HBM fraction is printed for completeness only",
                 "per_kernel": rl}
 
     # ---- cpu_baseline: the oracle on one host core, bounded sample ----
@@ -405,6 +405,10 @@ def run_reference(a, rank, world):
 
 def main():
     a = parse()
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -422,6 +426,9 @@ def main():
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0 and out is not None:
         print(json.dumps(out), flush=True)
 

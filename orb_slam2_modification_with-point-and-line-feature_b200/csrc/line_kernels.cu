@@ -11,10 +11,9 @@
 //                                                                     k_lbd_rows, k_lbd_finish
 //   line coefficients (:60-69)                                      -> k_lbd_finish
 //
-// Region growing is inherently ordered (greedy by gradient bin, shared USED map, running region angle); it is
-// executed with the reference's visiting order by one warp per frame whose lanes test the 3x3 neighbourhoods of
-// up to three region points at once and resolve acceptances in order.  Throughput comes from many frames in
-// flight; it is a latency-bound stage and is reported as time, not as an HBM fraction.
+// Region growing is inherently ordered (greedy by gradient bin, shared USED map, running region angle).  It keeps the
+// reference's semantics exactly and runs as a window of speculative transactions with in-order commit (see k_lsd_grow);
+// it is a latency-bound stage and is reported as time, not as an HBM fraction.
 #include <math.h>
 
 #include <algorithm>
@@ -261,7 +260,7 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(LineGeom g, const float* __
 }  // namespace pl
 
 // =================================================================================================================
-// k_lsd_grow — the ordered part of LSD: one warp per frame
+// k_lsd_grow — the ordered part of LSD
 // =================================================================================================================
 namespace pl {
 
