@@ -43,8 +43,16 @@ class FrameLite:
         Rcw, tcw = self.Tcw[:3, :3], self.Tcw[:3, 3]
         self.Rwc = Rcw.T.copy()
         self.Ow = (-self.Rwc @ tcw).astype(f32)
+        self._depth_img = depth
+        self.set_lines(kls, ldesc)
+
+    def set_lines(self, kls, ldesc):
+        """Attaches the line features (they may arrive later than the points: the two extractors run concurrently)."""
+        self.kls, self.ldesc = kls, ldesc
+        depth = self._depth_img
+        h, w = depth.shape
         # line endpoints: depth at the rounded endpoint
-        if len(kls):
+        if kls is not None and len(kls):
             sx = np.clip(np.rint(kls["sx"]).astype(np.int64), 0, w - 1)
             sy = np.clip(np.rint(kls["sy"]).astype(np.int64), 0, h - 1)
             ex = np.clip(np.rint(kls["ex"]).astype(np.int64), 0, w - 1)
@@ -93,6 +101,10 @@ class LocalMap:
         self.ldesc = np.zeros((0, 32), np.uint8)
 
     def add_keyframe(self, F: FrameLite):
+        self.add_keyframe_points(F)
+        self.add_keyframe_lines(F)
+
+    def add_keyframe_points(self, F: FrameLite):
         ok = F.depth > 0
         P = F.unproject_points()[ok]
         PO = P - F.Ow
@@ -105,6 +117,8 @@ class LocalMap:
         self.normal = np.concatenate([self.normal, (PO / dist[:, None]).astype(f32)])[-self.max_points:]
         self.max_d = np.concatenate([self.max_d, max_d])[-self.max_points:]
         self.min_d = np.concatenate([self.min_d, min_d])[-self.max_points:]
+
+    def add_keyframe_lines(self, F: FrameLite):
         if len(F.kls):
             s3, e3, okl = F.unproject_lines()
             self.ls = np.concatenate([self.ls, s3[okl]])[-self.max_lines:]
@@ -112,25 +126,35 @@ class LocalMap:
             self.lkl = np.concatenate([self.lkl, F.kls[okl]])[-self.max_lines:]
             self.ldesc = np.concatenate([self.ldesc, F.ldesc[okl]])[-self.max_lines:]
 
-    # Frame::IsInFrustum (Frame.cc:345-401) + MapPoint::PredictScale (MapPoint.cc:416-431), vectorised float32
-    def frustum(self, F: FrameLite, cos_limit=0.5):
-        K = F.K
-        Pc = (self.pos @ F.Tcw[:3, :3].T + F.Tcw[:3, 3]).astype(f32)
-        z = Pc[:, 2]
+    # Frame::IsInFrustum (Frame.cc:345-401) + MapPoint::PredictScale (MapPoint.cc:416-431), vectorised float32 over the
+    # frames that see the same snapshot of the map
+    def frustum_group(self, Fs, cos_limit=0.5):
+        K = Fs[0].K
+        sf = Fs[0].sf
+        R = np.stack([F.Tcw[:3, :3] for F in Fs]).astype(f32)
+        t = np.stack([F.Tcw[:3, 3] for F in Fs]).astype(f32)
+        Ow = np.stack([F.Ow for F in Fs]).astype(f32)
+        Pc = (np.matmul(self.pos[None], R.transpose(0, 2, 1)) + t[:, None, :]).astype(f32)
+        z = Pc[..., 2]
         with np.errstate(divide="ignore", invalid="ignore"):
             invz = (f32(1.0) / z).astype(f32)
-            u = (f32(K["fx"]) * Pc[:, 0] * invz + f32(K["cx"])).astype(f32)
-            v = (f32(K["fy"]) * Pc[:, 1] * invz + f32(K["cy"])).astype(f32)
-            PO = self.pos - F.Ow
-            dist = np.linalg.norm(PO, axis=1).astype(f32)
-            view_cos = (np.sum(PO * self.normal, 1) / dist).astype(f32)
-            ratio = self.max_d / dist
-            lvl = np.ceil(np.log(ratio) / np.log(F.sf[1] / F.sf[0])).astype(np.int64)
-        ok = (z > 0) & (u >= F.bounds[0]) & (u <= F.bounds[2]) & (v >= F.bounds[1]) & (v <= F.bounds[3])
-        ok &= (dist >= self.min_d) & (dist <= self.max_d) & (view_cos >= cos_limit)
-        lvl = np.clip(np.nan_to_num(lvl), 0, len(F.sf) - 1).astype(np.int32)
+            u = (f32(K["fx"]) * Pc[..., 0] * invz + f32(K["cx"])).astype(f32)
+            v = (f32(K["fy"]) * Pc[..., 1] * invz + f32(K["cy"])).astype(f32)
+            PO = self.pos[None, :, :] - Ow[:, None, :]
+            dist = np.sqrt(np.einsum("kmi,kmi->km", PO, PO)).astype(f32)
+            view_cos = (np.einsum("kmi,mi->km", PO, self.normal) / dist).astype(f32)
+            ratio = self.max_d[None] / dist
+            lvl = np.ceil(np.log(ratio) / np.log(sf[1] / sf[0]))
+        b = Fs[0].bounds
+        ok = (z > 0) & (u >= b[0]) & (u <= b[2]) & (v >= b[1]) & (v <= b[3])
+        ok &= (dist >= self.min_d[None]) & (dist <= self.max_d[None]) & (view_cos >= cos_limit)
+        lvl = np.clip(np.nan_to_num(lvl), 0, len(sf) - 1).astype(np.int32)
         xr = (u - f32(K["bf"]) * invz).astype(f32)
-        return ok.astype(np.uint8), np.nan_to_num(u), np.nan_to_num(v), np.nan_to_num(xr), lvl, np.nan_to_num(view_cos)
+        ok8, u, v, xr, vc = ok.astype(np.uint8), np.nan_to_num(u), np.nan_to_num(v), np.nan_to_num(xr), np.nan_to_num(view_cos)
+        return [(ok8[i], u[i], v[i], xr[i], lvl[i], vc[i]) for i in range(len(Fs))]
+
+    def frustum(self, F: FrameLite, cos_limit=0.5):
+        return self.frustum_group([F], cos_limit)[0]
 
 
 class TrackingFrontEnd:
@@ -152,6 +176,9 @@ class TrackingFrontEnd:
         return int(np.sum((m.astype(np.int64) + 1) * (np.arange(len(m)) + 1)))
 
     def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True, batch=True):
+        """features = (orb, lines); `lines` may be a concurrent.futures.Future: the point side (Frame-lite, C3, C2) does not
+        need the lines, so it proceeds while the line extractor is still running — the reference runs its two extractors
+        in two threads for the same reason (Frame.cc:152-155)."""
         n = len(gray)
         if features is None:
             orb = self.b.extract_orb(gray)
@@ -160,7 +187,7 @@ class TrackingFrontEnd:
             orb, lines = features
         rng = np.random.Generator(np.random.PCG64(424242))
         keep = self.keepalive = []
-        # ---- caller state of every frame (Frame-lite, local-map snapshots) ----
+        # ---- point side of the caller state (Frame-lite, local-map snapshots) ----
         frames, maps = [], []
         lm = LocalMap()
         for t in range(n):
@@ -168,13 +195,12 @@ class TrackingFrontEnd:
             if prior_noise:  # pose prior = ground truth + small noise (stand-in for the motion model)
                 T[:3, 3] += rng.normal(0, 0.002, 3)
             kps, desc = orb[t]
-            kls, ldesc, _ = lines[t]
-            F = FrameLite(kps, desc, kls, ldesc, depth[t], T.astype(f32), self.K, scale_factors)
+            F = FrameLite(kps, desc, None, None, depth[t], T.astype(f32), self.K, scale_factors)
             frames.append(F)
-            maps.append((lm.pos, lm.desc, lm.normal, lm.max_d, lm.min_d, lm.ls, lm.le, lm.lkl, lm.ldesc))
+            maps.append((lm.pos, lm.desc, lm.normal, lm.max_d, lm.min_d))
             if t % self.kf_every == 0:
-                lm.add_keyframe(F)
-        summary = [dict(frame=t, n_kp=len(frames[t].kps), n_kl=len(frames[t].kls)) for t in range(n)]
+                lm.add_keyframe_points(F)
+        summary = [dict(frame=t, n_kp=len(frames[t].kps)) for t in range(n)]
         # ---- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ----
         c3_t = list(range(1, n))
         cvs = [frames[t].view(None, keep) for t in c3_t]
@@ -183,11 +209,45 @@ class TrackingFrontEnd:
             last = frames[t - 1]
             lvs.append(N.make_lastframe_view(last.depth > 0, last.unproject_points(), last.desc, last.kps["octave"], last.kps["angle"],
                                              (np.arange(len(last.kps)) % 3 != 0), last.Tcw[:3].reshape(-1), keep))
+        # C2 inputs that do not depend on the C3 result (Frame::IsInFrustum of the local map): prepared before the first
+        # matcher call, so that all of this host work overlaps the line extraction still running on the device
+        c2_t = [t for t in range(n) if len(maps[t][0])]
+        fr = []
+        tmp = LocalMap()
+        k = 0
+        while k < len(c2_t):  # consecutive frames that see the same map snapshot are projected together
+            k1 = k
+            while k1 < len(c2_t) and maps[c2_t[k1]][0] is maps[c2_t[k]][0]:
+                k1 += 1
+            tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[c2_t[k]][:5]
+            fr += [(tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]])]
+            k = k1
         r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
         claimed = [None] * n
         for t, (m3, n3) in zip(c3_t, r3):
             summary[t].update(c3_matches=n3, c3_sum=self._chk(m3))
             claimed[t] = (m3 >= 0).astype(np.int32)
+        # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
+        fvs, mvs, inview = [], [], []
+        for t, (mdesc, inv, u, v, xr, lvl, vc) in zip(c2_t, fr):
+            fvs.append(frames[t].view(claimed[t], keep))
+            mvs.append(N.make_mappoint_view(mdesc, inv, u, v, xr, lvl, vc, None, keep))
+            inview.append(int(inv.sum()))
+        r2 = self.b.search_local_points_batch(fvs, mvs, 3.0, 0.8) if batch else [self.b.search_local_points(f, m, 3.0, 0.8) for f, m in zip(fvs, mvs)]
+        for t, iv, (m2, n2) in zip(c2_t, inview, r2):
+            summary[t].update(c2_in_view=iv, c2_matches=n2, c2_sum=self._chk(m2))
+        # ---- line side of the caller state ----
+        if hasattr(lines, "result"):
+            lines = lines.result()
+        lmaps = []
+        lm = LocalMap()
+        for t in range(n):
+            kls, ldesc, _ = lines[t]
+            frames[t].set_lines(kls, ldesc)
+            summary[t].update(n_kl=len(kls))
+            lmaps.append((lm.ls, lm.le, lm.lkl, lm.ldesc))
+            if t % self.kf_every == 0:
+                lm.add_keyframe_lines(frames[t])
         # ---- D3: LineMatcher(0.9).SearchByProjection(Cur, Last) (Tracking.cc:1247) ----
         d3_t = [t for t in c3_t if len(frames[t - 1].kls) and len(frames[t].kls)]
         lcv, llv = [], []
@@ -199,26 +259,12 @@ class TrackingFrontEnd:
         rd3 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
         for t, (ml, nl, rel, npj) in zip(d3_t, rd3):
             summary[t].update(d3_proj=npj, d3_matches=nl, d3_relaxed=rel, d3_sum=self._chk(ml))
-        # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
-        c2_t = [t for t in range(n) if len(maps[t][0])]
-        fvs, mvs, inview = [], [], []
-        tmp = LocalMap()
-        for t in c2_t:
-            F = frames[t]
-            tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[t][:5]
-            inv, u, v, xr, lvl, vc = tmp.frustum(F)
-            fvs.append(F.view(claimed[t], keep))
-            mvs.append(N.make_mappoint_view(tmp.desc, inv, u, v, xr, lvl, vc, None, keep))
-            inview.append(int(inv.sum()))
-        r2 = self.b.search_local_points_batch(fvs, mvs, 3.0, 0.8) if batch else [self.b.search_local_points(f, m, 3.0, 0.8) for f, m in zip(fvs, mvs)]
-        for t, iv, (m2, n2) in zip(c2_t, inview, r2):
-            summary[t].update(c2_in_view=iv, c2_matches=n2, c2_sum=self._chk(m2))
         # ---- D5: LineMatcher(0.8).SearchByProjection(F, localLines) (Tracking.cc:1863) ----
-        d5_t = [t for t in c2_t if len(maps[t][7]) and len(frames[t].kls)]
+        d5_t = [t for t in c2_t if len(lmaps[t][2]) and len(frames[t].kls)]
         lcv, llv = [], []
         for t in d5_t:
             F = frames[t]
-            ls, le, lkl, ldesc = maps[t][5:9]
+            ls, le, lkl, ldesc = lmaps[t]
             lcv.append(N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep))
             llv.append(N.make_mapline_view(ls, le, lkl, ldesc, np.ones(len(lkl), np.uint8), keep))
         rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
