@@ -583,7 +583,7 @@ __device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double 
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);  // lanes beyond n hold zeros: adding +0.0 changes nothing
         const double pxw = __dmul_rn(pt.x, pt.w), pyw = __dmul_rn(pt.y, pt.w);
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < 32; j++) {
             x = __dadd_rn(x, __shfl_sync(FULL, pxw, j));
             y = __dadd_rn(y, __shfl_sync(FULL, pyw, j));
@@ -603,7 +603,7 @@ __device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double 
             tyy = __dmul_rn(__dmul_rn(dx, dx), pt.w);
             txy = __dmul_rn(__dmul_rn(dx, dy), pt.w);
         }
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < 32; j++) {
             Ixx = __dadd_rn(Ixx, __shfl_sync(FULL, txx, j));
             Iyy = __dadd_rn(Iyy, __shfl_sync(FULL, tyy, j));
@@ -616,8 +616,10 @@ __device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double 
                                            : (double)fast_atan2_deg((float)Ixy, (float)__dsub_rn(lambda, Iyy));
     theta *= kDegToRad;
     if (fabs(lsd_angle_diff_signed(theta, reg_angle)) > prec) theta += kPiD;
-    const double dx = cos(theta), dy = sin(theta);
+    double dx, dy;
+    sincos(theta, &dy, &dx);
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+#pragma unroll 1
     for (int idx = lane; idx < n; idx += 32) {
         const unsigned pp = F.reg[idx];
         const double rdx = __dsub_rn((double)(int)(pp & 0xffffu), x), rdy = __dsub_rn((double)(int)(pp >> 16), y);
@@ -704,7 +706,7 @@ __device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double p
             }
         }
         cnt_in += __popc(__ballot_sync(FULL, inside));
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < 32; j++) {  // points outside contribute +0.0
             sum = __dadd_rn(sum, __shfl_sync(FULL, ang_d, j));
             s_sum = __dadd_rn(s_sum, __shfl_sync(FULL, ang_d2, j));
@@ -733,7 +735,7 @@ struct NfaTabs {
     const double* lgam;  // lgam[m] = log_gamma(m + 1)
     double logp[kPMax], log1mp[kPMax], log10p[kPMax];
 };
-__device__ double lsd_log_gamma_direct(double x) {
+__device__ __noinline__ double lsd_log_gamma_direct(double x) {
     if (x > 15.0) {  // Windschitl
         return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
     }
@@ -757,7 +759,7 @@ __device__ __forceinline__ bool lsd_double_equal(double a, double b) {
     return (abs_diff / abs_max) <= (100.0 * 2.2204460492503131e-16);
 }
 // nfa(): pj indexes p = 0.125 * 2^-pj
-__device__ double lsd_nfa(const NfaTabs& T, int n, int k, double p, int pj, double log_nt) {
+__device__ __noinline__ double lsd_nfa(const NfaTabs& T, int n, int k, double p, int pj, double log_nt) {
     if (n == 0 || k == 0) return -log_nt;
     const double lp = pj < kPMax ? T.logp[pj] : log(p), l1p = pj < kPMax ? T.log1mp[pj] : log(1.0 - p);
     if (n == k) return -log_nt - (double)n * (pj < kPMax ? T.log10p[pj] : log10(p));
@@ -791,7 +793,8 @@ __device__ __forceinline__ double lsd_slope(double px, double py, double qx, dou
 // rectangle (rows round-robin over the group); every lane returns its partial counts: total points and, for each
 // of the `np` precisions, aligned points.
 struct ScanCounts { int total; int alg[5]; };
-__device__ __forceinline__ ScanCounts lsd_rect_scan(const LsdFrame& F, const LsdRect& rec, const double* precs, int np, int sub, int grp) {
+// (not inlined: rect_improve calls it from six places, and the kernel is bound by instruction fetch)
+__device__ __noinline__ ScanCounts lsd_rect_scan(const LsdFrame& F, const LsdRect& rec, const double* precs, int np, int sub, int grp) {
     ScanCounts c;
     c.total = 0;
 #pragma unroll
@@ -862,118 +865,113 @@ __device__ double lsd_rect_nfa(const LsdFrame& F, const NfaTabs& T, const LsdRec
 // rect_improve().  The five trials of a stage are known up front (the trial rectangle evolves regardless of
 // acceptance), so a stage evaluates them concurrently — precision stages with one scan counting all five
 // tolerances, geometry stages with five lane groups — and then replays the reference's sequential acceptance.
-__device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect& rec, double log_nt, double log_eps) {
+// The stages are separate, non-inlined functions: the kernel is bound by instruction fetch, not by call overhead.
+struct ImproveState {
+    LsdRect rec;
+    int pj;  // rec.p == 0.125 * 2^-pj
+    double log_nfa;
+};
+// precision stage (used twice): r.p halves five times
+__device__ __noinline__ void lsd_improve_precision(const LsdFrame& F, const NfaTabs& T, ImproveState& S, double log_nt, bool need_width) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const double delta = 0.5;
+    LsdRect r = S.rec;
+    const int rj = S.pj;
+    if (need_width && !((r.width - delta) >= 0.5)) return;  // the last stage tries only while the width allows it
+    double ps[5], precs[5];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) {
+        r.p /= 2;
+        ps[n] = r.p;
+        precs[n] = r.p * kPiD;
+    }
+    ScanCounts c = lsd_rect_scan(F, S.rec, precs, 5, lane, 32);
+    const int total = warp_sum(c.total);
+    int alg[5];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) alg[n] = warp_sum(c.alg[n]);
+    // lanes 0..4 evaluate the five NFAs concurrently
+    double v = 0;
+    {
+        int myk = 0;
+        double myp = 0;
+#pragma unroll
+        for (int n = 0; n < 5; ++n)
+            if (lane == n) { myk = alg[n]; myp = ps[n]; }
+        if (lane < 5) v = lsd_nfa(T, total, myk, myp, rj + lane + 1, log_nt);
+    }
+    for (int n = 0; n < 5; ++n) {
+        const double vn = __shfl_sync(FULL, v, n);
+        if (vn > S.log_nfa) {
+            S.log_nfa = vn;
+            S.rec.p = ps[n];
+            S.rec.prec = precs[n];
+            S.pj = rj + n + 1;
+        }
+    }
+}
+// geometry stage: mode 0 = reduce width, 1 = reduce one side, 2 = reduce the other side
+__device__ __noinline__ void lsd_improve_geometry(const LsdFrame& F, const NfaTabs& T, ImproveState& S, double log_nt, int mode) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const double delta = 0.5, delta_2 = delta / 2.0;
-    int pj = 0;  // rec.p == 0.125 * 2^-pj
-    double log_nfa = lsd_rect_nfa(F, T, rec, pj, log_nt);
-    if (log_nfa > log_eps) return log_nfa;
-
-    // precision stage (used twice): r.p halves five times
-    auto precision_stage = [&](bool need_width) {
-        LsdRect r = rec;
-        int rj = pj;
-        if (need_width && !((r.width - delta) >= 0.5)) return;  // the last stage tries only while the width allows it
-        double ps[5], precs[5];
-#pragma unroll
-        for (int n = 0; n < 5; ++n) {
-            r.p /= 2;
-            ps[n] = r.p;
-            precs[n] = r.p * kPiD;
-        }
-        ScanCounts c = lsd_rect_scan(F, rec, precs, 5, lane, 32);
-        const int total = warp_sum(c.total);
-        int alg[5];
-#pragma unroll
-        for (int n = 0; n < 5; ++n) alg[n] = warp_sum(c.alg[n]);
-        // lanes 0..4 evaluate the five NFAs concurrently
-        double v = 0;
-        {
-            int myk = 0;
-            double myp = 0;
-#pragma unroll
-            for (int n = 0; n < 5; ++n)
-                if (lane == n) { myk = alg[n]; myp = ps[n]; }
-            if (lane < 5) v = lsd_nfa(T, total, myk, myp, rj + lane + 1, log_nt);
-        }
-        for (int n = 0; n < 5; ++n) {
-            const double vn = __shfl_sync(FULL, v, n);
-            if (vn > log_nfa) {
-                log_nfa = vn;
-                rec.p = ps[n];
-                rec.prec = precs[n];
-                pj = rj + n + 1;
+    LsdRect r = S.rec;
+    LsdRect mine = S.rec;  // trial rectangle of this lane's group
+    const int grp = lane / 6, sub = lane - grp * 6;  // groups 0..4 (lanes 30,31 idle)
+    int ntrial = 0;
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            if (mode == 1) {
+                r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2;
+                r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
+            } else if (mode == 2) {
+                r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2;
+                r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
             }
+            r.width -= delta;
+            if (grp == ntrial) mine = r;
+            ntrial++;
         }
-    };
-    // geometry stage: mode 0 = reduce width, 1 = reduce one side, 2 = reduce the other side
-    auto geometry_stage = [&](int mode) {
-        LsdRect r = rec;
-        LsdRect mine = rec;  // trial rectangle of this lane's group
-        const int grp = lane / 6, sub = lane - grp * 6;  // groups 0..4 (lanes 30,31 idle)
-        int ntrial = 0;
-        for (int n = 0; n < 5; ++n) {
-            if ((r.width - delta) >= 0.5) {
-                if (mode == 1) {
-                    r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2;
-                    r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
-                } else if (mode == 2) {
-                    r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2;
-                    r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
-                }
-                r.width -= delta;
-                if (grp == ntrial) mine = r;
-                ntrial++;
-            }
+    }
+    if (ntrial == 0) return;
+    const double pr[1] = {S.rec.prec};
+    ScanCounts c;
+    c.total = 0;
+    c.alg[0] = 0;
+    if (grp < ntrial) c = lsd_rect_scan(F, mine, pr, 1, sub, 6);
+    // reduce inside each 6-lane group (groups are not power-of-two wide: gather through shuffles)
+    int myn = 0, myk = 0;
+#pragma unroll 1
+    for (int l = 0; l < 30; ++l) {
+        const int ct = __shfl_sync(FULL, c.total, l), ca = __shfl_sync(FULL, c.alg[0], l);
+        if (lane == l / 6) { myn += ct; myk += ca; }
+    }
+    double v = 0;
+    if (lane < ntrial) v = lsd_nfa(T, myn, myk, S.rec.p, S.pj, log_nt);
+    // replay: trial t's rectangle lives in group t
+    for (int t = 0; t < ntrial; ++t) {
+        const double vt = __shfl_sync(FULL, v, t);
+        if (vt > S.log_nfa) {
+            S.log_nfa = vt;
+            const int src = t * 6;
+            S.rec.x1 = __shfl_sync(FULL, mine.x1, src); S.rec.y1 = __shfl_sync(FULL, mine.y1, src);
+            S.rec.x2 = __shfl_sync(FULL, mine.x2, src); S.rec.y2 = __shfl_sync(FULL, mine.y2, src);
+            S.rec.width = __shfl_sync(FULL, mine.width, src);
         }
-        if (ntrial == 0) return;
-        const double pr[1] = {rec.prec};
-        ScanCounts c;
-        c.total = 0;
-        c.alg[0] = 0;
-        if (grp < ntrial) c = lsd_rect_scan(F, mine, pr, 1, sub, 6);
-        // reduce inside each 6-lane group (groups are not power-of-two wide: gather through shuffles)
-        int tot[5], al[5];
-#pragma unroll
-        for (int t = 0; t < 5; ++t) { tot[t] = 0; al[t] = 0; }
-#pragma unroll
-        for (int l = 0; l < 30; ++l) {
-            const int ct = __shfl_sync(FULL, c.total, l), ca = __shfl_sync(FULL, c.alg[0], l);
-            tot[l / 6] += ct;
-            al[l / 6] += ca;
-        }
-        double v = 0;
-        {
-            int myn = 0, myk = 0;
-#pragma unroll
-            for (int t = 0; t < 5; ++t)
-                if (lane == t) { myn = tot[t]; myk = al[t]; }
-            if (lane < ntrial) v = lsd_nfa(T, myn, myk, rec.p, pj, log_nt);
-        }
-        // replay: trial t's rectangle lives in group t
-        for (int t = 0; t < ntrial; ++t) {
-            const double vt = __shfl_sync(FULL, v, t);
-            if (vt > log_nfa) {
-                log_nfa = vt;
-                const int src = t * 6;
-                rec.x1 = __shfl_sync(FULL, mine.x1, src); rec.y1 = __shfl_sync(FULL, mine.y1, src);
-                rec.x2 = __shfl_sync(FULL, mine.x2, src); rec.y2 = __shfl_sync(FULL, mine.y2, src);
-                rec.width = __shfl_sync(FULL, mine.width, src);
-            }
-        }
-    };
-
-    precision_stage(false);
-    if (log_nfa > log_eps) return log_nfa;
-    geometry_stage(0);
-    if (log_nfa > log_eps) return log_nfa;
-    geometry_stage(1);
-    if (log_nfa > log_eps) return log_nfa;
-    geometry_stage(2);
-    if (log_nfa > log_eps) return log_nfa;
-    precision_stage(true);
-    return log_nfa;
+    }
+}
+__device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect& rec, double log_nt, double log_eps) {
+    ImproveState S;
+    S.rec = rec;
+    S.pj = 0;
+    S.log_nfa = lsd_rect_nfa(F, T, rec, 0, log_nt);
+    if (S.log_nfa > log_eps) return S.log_nfa;
+    lsd_improve_precision(F, T, S, log_nt, false);
+    for (int mode = 0; mode < 3 && !(S.log_nfa > log_eps); mode++) lsd_improve_geometry(F, T, S, log_nt, mode);
+    if (!(S.log_nfa > log_eps)) lsd_improve_precision(F, T, S, log_nt, true);
+    rec = S.rec;
+    return S.log_nfa;
 }
 
 // flsd() main loop.  Persistent CTAs take frames from a counter; the G warps of a CTA are region growers.
