@@ -320,11 +320,8 @@ __device__ __forceinline__ void lsd_unmark(const LsdFrame& F, int x, int y, unsi
     else atomicAnd(&F.pool[(unsigned)F.dir[(y >> 5) * F.tw + (x >> 5)] * 32 + (y & 31)], ~(1u << (x & 31)));
 }
 // warp-collective: makes sure the tiles of the lanes with `want` exist; false when the pool is exhausted
-__device__ __forceinline__ bool lsd_priv_alloc(const LsdFrame& F, bool want, int x, int y) {
-    if (!F.sparse) return true;
+__device__ __noinline__ bool lsd_priv_alloc_tiles(const LsdFrame& F, int t, unsigned need) {
     const int lane = threadIdx.x & 31;
-    const int t = want ? (y >> 5) * F.tw + (x >> 5) : -1;
-    unsigned need = __ballot_sync(0xffffffffu, want && F.dir[max(t, 0)] == 0xffu);
     while (need) {
         const int tj = __shfl_sync(0xffffffffu, t, __ffs(need) - 1);
         const int k = *(volatile int*)F.ntiles;
@@ -341,16 +338,25 @@ __device__ __forceinline__ bool lsd_priv_alloc(const LsdFrame& F, bool want, int
     }
     return true;
 }
+__device__ __forceinline__ bool lsd_priv_alloc(const LsdFrame& F, bool want, int x, int y) {
+    if (!F.sparse) return true;
+    const int t = want ? (y >> 5) * F.tw + (x >> 5) : -1;
+    const unsigned need = __ballot_sync(0xffffffffu, want && F.dir[max(t, 0)] == 0xffu);
+    if (!need) return true;
+    return lsd_priv_alloc_tiles(F, t, need);
+}
 // back to "nothing marked"; nt = entries of the touched log (every pixel ever marked is in it)
 __device__ __forceinline__ void lsd_priv_reset(const LsdFrame& F, int nt) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
     if (F.sparse) {
         const int k = *(volatile int*)F.ntiles;
+        #pragma unroll 1
         for (int s2 = lane; s2 < k; s2 += 32) F.dir[F.rev[s2]] = 0xffu;
         __syncwarp();
         if (lane == 0) *(volatile int*)F.ntiles = 0;
     } else {
+        #pragma unroll 1
         for (int i = lane; i < nt; i += 32) {
             const unsigned pp = F.touched[i];
             const unsigned o = (pp >> 16) * (unsigned)F.W + (pp & 0xffffu);
@@ -380,13 +386,17 @@ __device__ __forceinline__ double lsd_dist_sq(double x1, double y1, double x2, d
     return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
 }
 
+// (rare path, kept out of line: the grower is bound by instruction fetch)
+__device__ __noinline__ bool lsd_aligned_cold(float th, float adeg, double prec) {
+    return lsd_aligned((double)th * kDegToRad, (double)adeg * kDegToRad, prec);
+}
 // isAligned() on the float degree values the reference converts to double radians: decided in float when the
 // distance is not within 2e-3 degrees of the tolerance or of the fold point, else with the reference's own formula.
 __device__ __forceinline__ bool lsd_aligned_deg(float th, float adeg, float precdeg, double prec) {
     const float t = fabsf(th - adeg);
     const float tf = t > 270.f ? fabsf(t - 360.f) : t;
     if (fabsf(tf - precdeg) > 2e-3f && fabsf(t - 270.f) > 2e-3f) return tf <= precdeg;
-    return lsd_aligned((double)th * kDegToRad, (double)adeg * kDegToRad, prec);
+    return lsd_aligned_cold(th, adeg, prec);
 }
 
 // region_grow(): returns the region size; reg_angle (radians) is returned through *out_angle.
@@ -628,7 +638,7 @@ __device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double 
         l_max = fmax(l_max, l); l_min = fmin(l_min, l);
         w_max = fmax(w_max, w); w_min = fmin(w_min, w);
     }
-#pragma unroll
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
         l_max = fmax(l_max, __shfl_xor_sync(FULL, l_max, o));
         l_min = fmin(l_min, __shfl_xor_sync(FULL, l_min, o));
@@ -647,7 +657,7 @@ __device__ __forceinline__ double lsd_density(int n, const LsdRect& rec) {
 }
 
 // reduce_region_radius(): sequential swap-with-last removal keeps the reference's point order
-__device__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n, double reg_angle, double prec, double p, LsdRect& rec,
+__device__ __noinline__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n, double reg_angle, double prec, double p, LsdRect& rec,
                                          double density, double density_th) {
     const int lane = threadIdx.x & 31;
     const unsigned p0 = F.reg[0];
@@ -1155,6 +1165,7 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, Gr
     F.reg = nullptr;
     F.touched = nullptr;
     F.reg_cap = F.touched_cap = 0;
+    #pragma unroll 1
     for (int i = lane; i < gs.tiles; i += 32) F.dir[i] = 0xffu;
     if (lane == 0) *F.ntiles = 0;
     if (threadIdx.x < kMaxFrameSlots) s_ctl[threadIdx.x].active = threadIdx.x < FS ? kFrameEmpty : kFrameNoMore;
@@ -1246,7 +1257,9 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, Gr
             if (lane == 0) f = atomicAdd(B.frame_counter, 1);
             f = __shfl_sync(FULL, f, 0);
             if (f < nf) {
+                #pragma unroll 1
                 for (int i = lane; i < kSlots; i += 32) s_slot[i].w = slot_pack(kSlotFree, 0, -1);
+                #pragma unroll 1
                 for (int i = lane; i < gs.bits_words; i += 32) s_used[i] = 0;
                 if (lane == 0) {
                     ctl->next_pos = ctl->ticket_next = ctl->grow_next = ctl->commit_head = 0;
@@ -1300,6 +1313,7 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, Gr
                     if (!redo) {
                         const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
                         bool conflict = false;
+                        #pragma unroll 1
                         for (int i = lane; i < nt; i += 32) {
                             const unsigned pp = tk[i];
                             const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
@@ -1332,6 +1346,7 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, Gr
                         rec = buf >= 0 ? my_pool_rect[buf] : my_small_rect[h % kSlots];
                     }
                     if (status >= 0) {
+                        #pragma unroll 1
                         for (int i = lane; i < n; i += 32) {
                             const unsigned pp = rg[i];
                             const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
@@ -1460,7 +1475,9 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, Gr
             const bool keep = res.status >= 0 && !small;
             if (small) {
                 unsigned int* dst = B.small_buf + ((cta_fs + fsi) * kSlots + (size_t)(my_ticket % kSlots)) * 2 * kSmall;
+                #pragma unroll 1
                 for (int i = lane; i < res.n; i += 32) dst[i] = FS2.reg[i];
+                #pragma unroll 1
                 for (int i = lane; i < res.nt; i += 32) dst[kSmall + i] = FS2.touched[i];
                 if (lane == 0 && res.status == kStRect) B.small_rect[(cta_fs + fsi) * kSlots + (my_ticket % kSlots)] = res.rec;
                 __syncwarp();
