@@ -1185,7 +1185,12 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, Gr
                     volatile int4* sl = reinterpret_cast<volatile int4*>(s_raw + (size_t)cand * gs.per_frame());
                     const int st = c->active;
                     if (st == kFrameNoMore) { nomore++; continue; }
-                    if (st == kFrameEmpty) { action = kActInit; fsi = cand; break; }
+                    if (st == kFrameEmpty) {
+                        // fair start: a CTA fills its k-th frame slot only after every CTA had the chance to fill k - 1
+                        // slots, so that the frames spread evenly over the SMs instead of going to the CTAs that start first
+                        if (cand == 0 || *(volatile int*)B.frame_counter >= cand * (int)gridDim.x) { action = kActInit; fsi = cand; break; }
+                        continue;
+                    }
                     if (st != kFrameRunning) continue;
                     const int h = c->commit_head, tn = c->ticket_next, gn = c->grow_next, ai = c->all_issued;
                     if (ai && h == tn) action = kActFinish;
@@ -2178,7 +2183,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                         }
                     }
             };
-            int g_few = 8, g_many = kMaxGrowers, fs_many = 2;
+            int g_few = 8, g_many = kMaxGrowers, fs_many = 3;
             if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<few>,<many>,<frame slots>"
                 int a = 0, b2 = 0, c2 = 0;
                 if (sscanf(ev, "%d,%d,%d", &a, &b2, &c2) == 3) {
