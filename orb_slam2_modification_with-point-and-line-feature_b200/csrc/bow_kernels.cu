@@ -326,7 +326,7 @@ PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, con
     }
     const BowDev* d_bd = h->in.put(bd.data(), (size_t)n);
     cudaStream_t st = h->stream;
-    PL_CUDA_TRY(cudaMemcpyAsync(h->in.d, h->in.h, h->in.cur, cudaMemcpyHostToDevice, st));
+    { int urc = h->in.upload(st); if (urc != PL_OK) return urc; }
     if (max_nq > 0) {
         k_bow_dist<<<dim3((max_nq * 32 + 255) / 256, n), 256, 0, st>>>(d_bd);
         h->last_launches++;

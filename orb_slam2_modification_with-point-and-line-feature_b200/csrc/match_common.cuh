@@ -2,6 +2,7 @@
 // line matching): the 256-bit Hamming distance, the pl_match handle and its scratch / staging buffers.
 #pragma once
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "pl_common.cuh"
@@ -22,6 +23,7 @@ struct PlStage {
     size_t cap = 0, cur = 0;
     int reserve(size_t bytes) {
         cur = 0;
+        jobs.clear();
         if (bytes <= cap) return PL_OK;
         if (h) cudaFreeHost(h);
         if (d) cudaFree(d);
@@ -35,12 +37,45 @@ struct PlStage {
     }
     static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
     // copies n elements into the pinned buffer; returns the DEVICE address they will have after upload()
+    // Large arrays are not copied at once: the copy is recorded and executed by a few host threads in upload(), so the
+    // source must stay alive until then (it always is: every put() happens inside the API call that uploads).
+    struct Job { size_t off; const void* src; size_t bytes; };
+    std::vector<Job> jobs;
     template <typename T>
     const T* put(const T* src, size_t n) {
-        const size_t off = cur;
-        if (n && src) memcpy(h + off, src, n * sizeof(T));
-        cur += pad(n * sizeof(T));
+        const size_t off = cur, bytes = n * sizeof(T);
+        if (n && src) {
+            if (bytes >= (size_t)8 << 10) jobs.push_back(Job{off, src, bytes});
+            else memcpy(h + off, src, bytes);
+        }
+        cur += pad(bytes);
         return (const T*)(d + off);
+    }
+    // executes the recorded copies (up to 4 threads when there is enough to copy) and sends the packed buffer to the device
+    int upload(cudaStream_t st) {
+        size_t total = 0;
+        for (const Job& j : jobs) total += j.bytes;
+        const int nt = total >= ((size_t)4 << 20) ? 4 : 1;
+        auto work = [&](int t) {
+            // thread t takes the jobs whose cumulative start falls into its share of the bytes
+            const size_t lo = total * t / nt, hi = total * (t + 1) / nt;
+            size_t acc = 0;
+            for (const Job& j : jobs) {
+                if (acc >= lo && acc < hi) memcpy(h + j.off, j.src, j.bytes);
+                acc += j.bytes;
+            }
+        };
+        if (nt == 1) {
+            work(0);
+        } else {
+            std::thread th[3];
+            for (int t = 1; t < nt; t++) th[t - 1] = std::thread(work, t);
+            work(0);
+            for (int t = 1; t < nt; t++) th[t - 1].join();
+        }
+        jobs.clear();
+        PL_CUDA_TRY(cudaMemcpyAsync(d, h, cur, cudaMemcpyHostToDevice, st));
+        return PL_OK;
     }
     // space that only exists on the device side (outputs / scratch): returns device address, and host mirror address
     template <typename T>

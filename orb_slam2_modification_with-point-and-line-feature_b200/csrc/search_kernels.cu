@@ -953,7 +953,7 @@ PL_API int pl_orb_search_last_frame_batch(pl_match* h, int n, const pl_frame_vie
         max_n2 = std::max(max_n2, n2); max_np = std::max(max_np, L.n); max_feat = std::max(max_feat, cur[i].n);
     }
     const SearchDev* d_sd = h->in.put(sd.data(), (size_t)n);
-    PL_CUDA_TRY(cudaMemcpyAsync(h->in.d, h->in.h, h->in.cur, cudaMemcpyHostToDevice, h->stream));
+    { int urc = h->in.upload(h->stream); if (urc != PL_OK) return urc; }
     return run_search<0>(h, sd, d_sd, n, total_feats, total_pts, total_n2, max_n2, max_np, max_feat, th, 0.f, check_orientation, match_of_feature,
                          n_matches);
 }
@@ -1000,7 +1000,7 @@ PL_API int pl_orb_search_local_points_batch(pl_match* h, int n, const pl_frame_v
         max_n2 = std::max(max_n2, n2); max_np = std::max(max_np, M.n); max_feat = std::max(max_feat, F[i].n);
     }
     const SearchDev* d_sd = h->in.put(sd.data(), (size_t)n);
-    PL_CUDA_TRY(cudaMemcpyAsync(h->in.d, h->in.h, h->in.cur, cudaMemcpyHostToDevice, h->stream));
+    { int urc = h->in.upload(h->stream); if (urc != PL_OK) return urc; }
     return run_search<1>(h, sd, d_sd, n, total_feats, total_pts, total_n2, max_n2, max_np, max_feat, th, nn_ratio, 0, match_of_feature, n_matches);
 }
 
@@ -1069,7 +1069,7 @@ int pose_points_search(pl_match* h, int n, const pl_frame_view* fr, const pl_pos
         max_n2 = std::max(max_n2, n2); max_np = std::max(max_np, P.n); max_feat = std::max(max_feat, fr[i].n);
     }
     const SearchDev* d_sd = h->in.put(sd.data(), (size_t)n);
-    PL_CUDA_TRY(cudaMemcpyAsync(h->in.d, h->in.h, h->in.cur, cudaMemcpyHostToDevice, h->stream));
+    { int urc = h->in.upload(h->stream); if (urc != PL_OK) return urc; }
     return run_search<MODE>(h, sd, d_sd, n, total_feats, total_pts, total_n2, max_n2, max_np, max_feat, th, 0.f, check_orientation,
                             match_of_feature, n_matches, th_dist);
 }
@@ -1136,7 +1136,7 @@ PL_API int pl_line_search_by_projection_batch(pl_match* h, int n, const pl_linef
     }
     const LineSearchDev* d_ld = h->in.put(ld.data(), (size_t)n);
     cudaStream_t st = h->stream;
-    PL_CUDA_TRY(cudaMemcpyAsync(h->in.d, h->in.h, h->in.cur, cudaMemcpyHostToDevice, st));
+    { int urc = h->in.upload(st); if (urc != PL_OK) return urc; }
     void* p;
     if ((rc = match_scratch(h, 6, (size_t)std::max(total_lines, 1) * sizeof(pl_keyline), &p)) != PL_OK) return rc;
     pl_keyline* d_pk = (pl_keyline*)p;
@@ -1246,7 +1246,7 @@ PL_API int pl_line_match_pairs(pl_match* h, const pl_keyline* proj, const uint8_
     D.cur_claimed = cur_claimed ? h->in.put(cur_claimed, (size_t)n_cur) : nullptr;
     const LineSearchDev* d_ld = h->in.put(&D, 1);
     cudaStream_t st = h->stream;
-    PL_CUDA_TRY(cudaMemcpyAsync(h->in.d, h->in.h, h->in.cur, cudaMemcpyHostToDevice, st));
+    { int urc = h->in.upload(st); if (urc != PL_OK) return urc; }
     void* p;
     if ((rc = match_scratch(h, 7, (size_t)std::max(n_proj, 1) * 4, &p)) != PL_OK) return rc;
     int* d_pi = (int*)p;
