@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "pl_common.cuh"
@@ -24,6 +25,7 @@ struct PlStage {
     int reserve(size_t bytes) {
         cur = 0;
         jobs.clear();
+        seen.clear();
         if (bytes <= cap) return PL_OK;
         if (h) cudaFreeHost(h);
         if (d) cudaFree(d);
@@ -41,12 +43,21 @@ struct PlStage {
     // source must stay alive until then (it always is: every put() happens inside the API call that uploads).
     struct Job { size_t off; const void* src; size_t bytes; };
     std::vector<Job> jobs;
+    // a large array that several instances of a batch share (the same local-map snapshot for consecutive frames, a frame that
+    // is "current" in one instance and "last" in the next) travels once: same host pointer and size -> same device copy
+    std::unordered_map<const void*, std::pair<size_t, size_t>> seen;  // src -> (bytes, offset)
     template <typename T>
     const T* put(const T* src, size_t n) {
         const size_t off = cur, bytes = n * sizeof(T);
         if (n && src) {
-            if (bytes >= (size_t)8 << 10) jobs.push_back(Job{off, src, bytes});
-            else memcpy(h + off, src, bytes);
+            if (bytes >= (size_t)8 << 10) {
+                auto it = seen.find((const void*)src);
+                if (it != seen.end() && it->second.first == bytes) return (const T*)(d + it->second.second);
+                seen[(const void*)src] = std::make_pair(bytes, off);
+                jobs.push_back(Job{off, src, bytes});
+            } else {
+                memcpy(h + off, src, bytes);
+            }
         }
         cur += pad(bytes);
         return (const T*)(d + off);
