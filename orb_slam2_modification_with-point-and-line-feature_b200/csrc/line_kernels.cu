@@ -342,7 +342,7 @@ __device__ __forceinline__ bool lsd_priv_alloc(const LsdFrame& F, bool want, int
     if (!F.sparse) return true;
     const int t = want ? (y >> 5) * F.tw + (x >> 5) : -1;
     const unsigned need = __ballot_sync(0xffffffffu, want && F.dir[max(t, 0)] == 0xffu);
-    if (!need) return true;
+    if (__builtin_expect(!need, 1)) return true;
     return lsd_priv_alloc_tiles(F, t, need);
 }
 // back to "nothing marked"; nt = entries of the touched log (every pixel ever marked is in it)
@@ -395,7 +395,7 @@ __device__ __noinline__ bool lsd_aligned_cold(float th, float adeg, double prec)
 __device__ __forceinline__ bool lsd_aligned_deg(float th, float adeg, float precdeg, double prec) {
     const float t = fabsf(th - adeg);
     const float tf = t > 270.f ? fabsf(t - 360.f) : t;
-    if (fabsf(tf - precdeg) > 2e-3f && fabsf(t - 270.f) > 2e-3f) return tf <= precdeg;
+    if (__builtin_expect(fabsf(tf - precdeg) > 2e-3f && fabsf(t - 270.f) > 2e-3f, 1)) return tf <= precdeg;
     return lsd_aligned_cold(th, adeg, prec);
 }
 
@@ -523,7 +523,7 @@ __device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy,
                 const unsigned M = __ballot_sync(FULL, inrem && v != inH);
                 unsigned T = H2, resolved = FULL;
                 int hl = 31 - __clz(rem);
-                if (M) {
+                if (__builtin_expect(M != 0, 0)) {
                     const int ls = __ffs(M) - 1;
                     const unsigned below = (1u << ls) - 1u;
                     T = (H2 & below) | (((H2 >> ls) & 1u) ? 0u : (1u << ls));
@@ -533,9 +533,9 @@ __device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy,
                 hint = __shfl_sync(FULL, th, hl);
                 const int cnt = __popc(T);
                 if (cnt) {
-                    if (n + cnt > F.reg_cap || nt + cnt > F.touched_cap) return -1;
-                    if (__any_sync(FULL, ((T >> lane) & 1u) && lsd_claim_hit(F, cur.claim))) return -2;
-                    if (!lsd_priv_alloc(F, (T >> lane) & 1u, cur.xx, cur.yy)) return -1;
+                    if (__builtin_expect(n + cnt > F.reg_cap || nt + cnt > F.touched_cap, 0)) return -1;
+                    if (__builtin_expect(__any_sync(FULL, ((T >> lane) & 1u) && lsd_claim_hit(F, cur.claim)), 0)) return -2;
+                    if (__builtin_expect(!lsd_priv_alloc(F, (T >> lane) & 1u, cur.xx, cur.yy), 0)) return -1;
                     if ((T >> lane) & 1u) {
                         F.claims[cur.o] = (unsigned short)F.ticket;
                         const int r = __popc(T & lt);
@@ -1505,7 +1505,7 @@ __global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, Gr
 // NFA validation of the fitted rectangles (rect_improve): it only reads the angle map and does not influence any
 // other region, so every rectangle of every frame is independent — one warp per rectangle, grid-strided.
 constexpr int kNfaBlocksPerFrame = 32, kNfaThreads = 256;
-__global__ void __launch_bounds__(kNfaThreads) k_lsd_nfa(LineGeom g, const float* __restrict__ angdeg, size_t plane,
+__global__ void __launch_bounds__(kNfaThreads, 4) k_lsd_nfa(LineGeom g, const float* __restrict__ angdeg, size_t plane,
                                                          const LsdQueueItem* __restrict__ queue, const int* __restrict__ n_rects,
                                                          LsdSeg* __restrict__ qres, uint8_t* __restrict__ qvalid, NfaTabs T) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
