@@ -2194,6 +2194,13 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             }
             choose(1, g_few, &h->cfg_few);
             for (int fs = fs_many; fs >= 1 && h->cfg_many.growers < std::min(g_many, 4); fs--) choose(fs, g_many, &h->cfg_many);
+            if (const char* ev = getenv("PLSLAM_LSD_POOL_TILES")) {  // test hook: a tiny pool forces the overflow -> re-growth path
+                const int pt = atoi(ev);
+                if (pt >= 1 && pt <= kMaxPoolTiles) {
+                    h->cfg_few.pool_tiles = std::min(h->cfg_few.pool_tiles, pt);
+                    h->cfg_many.pool_tiles = std::min(h->cfg_many.pool_tiles, pt);
+                }
+            }
             h->grow_tiles = tiles;
             h->grow_window = 128;
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));

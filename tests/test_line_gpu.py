@@ -83,3 +83,26 @@ def test_max_lines_parameter(api, synth, oracle):
         okl, odesc, oco = oracle.line_extract(img, m)
         assert len(kls) == len(okl) == m
         assert np.array_equal(kls["class_id"], okl["class_id"]) and np.array_equal(desc, odesc)
+
+
+@pytest.mark.parametrize("env", [{"PLSLAM_LSD_POOL_TILES": "2"}, {"PLSLAM_LSD_POOL_TILES": "1", "PLSLAM_LSD_WINDOW": "1"},
+                                 {"PLSLAM_LSD_GROWERS": "1,1,1"}, {"PLSLAM_LSD_GROWERS": "12,12,4", "PLSLAM_LSD_WINDOW": "256"},
+                                 {"PLSLAM_LSD_GROWERS": "3,5,2", "PLSLAM_LSD_WINDOW": "7"}])
+def test_grower_configuration_does_not_change_the_result(env, api, synth, monkeypatch):
+    """The speculative region grower must give the sequential result whatever its shape: number of grower
+    warps, frames per CTA, window of uncommitted tickets, and a private tile pool so small that most regions overflow and
+    are re-grown at commit time.  (The knobs are read when the extractor is created.)"""
+    frames = synth.frames(4242, 5)
+    ref = api.LineExtractor(max_batch=5)
+    k0, d0, c0, n0 = ref.extract_batch(frames)
+    s0 = ref.lsd_segments(frame=4)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ex = api.LineExtractor(max_batch=5)
+    k1, d1, c1, n1 = ex.extract_batch(frames)
+    s1 = ex.lsd_segments(frame=4)
+    assert np.array_equal(n0, n1) and np.array_equal(k0, k1) and np.array_equal(d0, d1) and np.array_equal(c0, c1)
+    for a, b in zip(s0, s1):
+        assert np.array_equal(a, b)
+    ex.close()
+    ref.close()
