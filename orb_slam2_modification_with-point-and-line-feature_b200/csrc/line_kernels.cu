@@ -1005,7 +1005,7 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
 // earlier tickets in the map, so the result is the sequential one whatever the stamps say.  rect_improve only reads
 // the angle map and does not influence later regions: it runs afterwards in k_lsd_nfa, and accepted segments are
 // compacted in seed order.
-constexpr int kMaxGrowers = 12;    // grower warps per CTA
+constexpr int kMaxGrowers = 16;    // grower warps per CTA
 constexpr int kMaxFrameSlots = 4;  // frames a CTA works on at once
 constexpr int kSlots = 256;        // ticket slots per frame (the window of uncommitted tickets is at most this)
 constexpr int kPool = 64;          // region buffers per CTA
@@ -1135,7 +1135,10 @@ struct GrowBufs {
 // A CTA works on up to gs.frame_slots frames at once and its warps take whatever work any of them offers, so a warp
 // that would wait (the window of a frame is full, nothing is ready, the head region is still growing) works on
 // another frame instead.  Frames are handed out through a global counter.
-__global__ void __launch_bounds__(kMaxGrowers * 32, 1) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, GrowBufs B) {
+// Two instantiations: kBound = 256 (up to 8 growers, all the registers they want: single-frame latency) and kBound = 512
+// (up to 16 growers at 128 registers: throughput over many frames).
+template <int kBound>
+__global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, GrowBufs B) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ GrowCtl s_ctl[kMaxFrameSlots];
     __shared__ unsigned long long s_free_mask;  // free buffers of the pool
@@ -2059,7 +2062,8 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         gb.pool_reg = h->d_spec_reg; gb.pool_touched = h->d_spec_touched; gb.pool_rect = h->d_pool_rect;
         gb.small_buf = h->d_small_buf; gb.small_rect = h->d_small_rect; gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
         gb.flags = h->d_flags; gb.phase_cycles = prof ? h->d_phase : nullptr; gb.frame_counter = h->d_frame_counter; gb.plane = plane;
-        k_lsd_grow<<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
+        if (cf.growers <= 8) k_lsd_grow<256><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
+        else k_lsd_grow<512><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
     }
     k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
     launches += 2;
@@ -2183,7 +2187,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                         }
                     }
             };
-            int g_few = 8, g_many = kMaxGrowers, fs_many = 3;
+            int g_few = 8, g_many = kMaxGrowers, fs_many = 3;  // (g_few <= 8: the 256-thread instantiation)
             if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<few>,<many>,<frame slots>"
                 int a = 0, b2 = 0, c2 = 0;
                 if (sscanf(ev, "%d,%d,%d", &a, &b2, &c2) == 3) {
@@ -2210,7 +2214,8 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
-            e = cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            e = cudaFuncSetAttribute(k_lsd_grow<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lsd_grow<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
         }
     }
     const size_t max_ctas = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1));
