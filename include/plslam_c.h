@@ -109,6 +109,8 @@ PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, in
 PL_API int pl_orb_extract_batch_dev(pl_orb* h, const uint8_t* d_gray, int n_frames, int rows, int cols,
                                     size_t step, size_t frame_stride, pl_keypoint* d_kps, uint8_t* d_desc, int cap,
                                     int* d_n_out);
+/* waits for the handle's stream; returns PL_ERR_CAPACITY when a frame extracted through the device-pointer API since the
+ * previous call exceeded a capacity (the host-pointer calls report it themselves). */
 PL_API int pl_orb_sync(pl_orb* h);
 /* the CUDA stream of the handle as an opaque pointer (cudaStream_t) — for event timing by the caller */
 PL_API void* pl_orb_stream(pl_orb* h);
@@ -157,6 +159,8 @@ PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, 
 PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols,
                                      size_t step, size_t frame_stride, int max_lines, pl_keyline* d_kls,
                                      uint8_t* d_desc, double* d_coeffs, int* d_n_out);
+/* waits for the handle's stream; returns PL_ERR_CAPACITY when a frame extracted through the device-pointer API since the
+ * previous call exceeded a capacity (the host-pointer calls report it themselves). */
 PL_API int pl_line_sync(pl_line* h);
 PL_API void* pl_line_stream(pl_line* h);
 PL_API int pl_line_last_launches(const pl_line* h);

@@ -1922,6 +1922,7 @@ struct pl_line {
     unsigned int* d_small_buf = nullptr;
     unsigned short* d_claims = nullptr;
     int* d_frame_counter = nullptr;
+    int* d_sticky = nullptr;  // capacity flags of the device-pointer API since the last pl_line_sync
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
     unsigned int* d_big_bits = nullptr;
@@ -2098,6 +2099,13 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     return PL_OK;
 }
 
+__global__ void __launch_bounds__(32) k_line_or_flags(const int* __restrict__ flags, int n, int* __restrict__ sticky) {
+    int v = 0;
+    for (int i = threadIdx.x; i < n; i += 32) v |= flags[i];
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0 && v) atomicOr(sticky, v);
+}
+
 int line_check_flags(pl_line* h, int nf) {
     PL_CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -2230,6 +2238,8 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_big_bits, max_fs * (size_t)h->bits_words);
     if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_fs * (size_t)h->bits_words * sizeof(unsigned int));
     A(&h->d_frame_counter, 1);
+    A(&h->d_sticky, 1);
+    if (e == cudaSuccess) e = cudaMemset(h->d_sticky, 0, sizeof(int));
     A(&h->d_resp, B * seg_cap);
     A(&h->d_dx, B * align_up((size_t)max_cols, 8) * max_rows);
     A(&h->d_dy, B * align_up((size_t)max_cols, 8) * max_rows);
@@ -2285,7 +2295,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_cs, h->d_cs0, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_sticky, h->d_cs, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -2298,7 +2308,14 @@ PL_API void pl_line_destroy(pl_line* h) {
 PL_API int pl_line_sync(pl_line* h) {
     PL_CHECK_ARG(h);
     PL_CUDA_TRY(cudaSetDevice(h->device));
+    int sticky = 0;
+    PL_CUDA_TRY(cudaMemcpyAsync(&sticky, h->d_sticky, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (sticky) {
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_sticky, 0, sizeof(int), h->stream));
+        set_error("a frame extracted through the device-pointer API exceeded an LSD capacity (flags=%d: 1=segments, 2=region size)", sticky);
+        return PL_ERR_CAPACITY;
+    }
     return PL_OK;
 }
 PL_API void* pl_line_stream(pl_line* h) { return h ? (void*)h->stream : nullptr; }
@@ -2346,6 +2363,7 @@ PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_fr
         rc = line_launch_chunk(h, d_gray + (size_t)f0 * frame_stride, nf, step, frame_stride, d_kls + (size_t)f0 * max_lines,
                                d_desc + (size_t)f0 * max_lines * 32, d_coeffs + (size_t)f0 * max_lines * 3, max_lines, d_n_out + f0);
         if (rc != PL_OK) return rc;
+        k_line_or_flags<<<1, 32, 0, h->stream>>>(h->d_flags, nf, h->d_sticky);
     }
     return PL_OK;
 }

@@ -839,6 +839,7 @@ struct pl_orb {
     size_t in_alloc = 0, pyr_alloc = 0, blur_alloc = 0, cand_alloc = 0, cell_alloc = 0, lvlkp_alloc = 0;
     size_t cells_alloc = 0, tabs_alloc = 0, tiles_alloc = 0;
     int* h_flags = nullptr;  // pinned
+    int* d_sticky = nullptr; // capacity flags of the device-pointer API since the last pl_orb_sync
     int last_batch = 0;      // frames of the last chunk (for debug reads)
     int last_launches = 0;
     size_t oct_smem = 0;
@@ -1099,6 +1100,14 @@ int launch_chunk(pl_orb* h, const uint8_t* d_gray, int nf, size_t step, size_t f
     return PL_OK;
 }
 
+// device-pointer API: the per-frame capacity flags of a chunk are folded into one sticky word that pl_orb_sync reports
+__global__ void __launch_bounds__(32) k_or_flags(const int* __restrict__ flags, int n, int* __restrict__ sticky) {
+    int v = 0;
+    for (int i = threadIdx.x; i < n; i += 32) v |= flags[i];
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0 && v) atomicOr(sticky, v);
+}
+
 int check_flags(pl_orb* h, int nf) {
     PL_CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1173,6 +1182,8 @@ PL_API int pl_orb_create(pl_orb** out, int nfeatures, float scale_factor, int nl
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_lvl_count, sizeof(int) * (size_t)max_batch * kMaxLevels);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_lvl_n, sizeof(int) * (size_t)max_batch * kMaxLevels);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_flags, sizeof(int) * (size_t)max_batch);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_sticky, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_sticky, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_nout, sizeof(int) * (size_t)max_batch);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_flags, sizeof(int) * (size_t)max_batch);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern));
@@ -1195,7 +1206,7 @@ PL_API void pl_orb_destroy(pl_orb* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_geom, h->d_cells, h->d_tabs, h->d_tiles, h->d_in, h->d_pyr, h->d_blur, h->d_cand, h->d_ord, h->d_lvl_kp,
-                    h->d_node, h->d_cell_off, h->d_cell_cnt, h->d_lvl_count, h->d_lvl_n, h->d_flags, h->d_kps, h->d_desc, h->d_nout};
+                    h->d_node, h->d_cell_off, h->d_cell_cnt, h->d_lvl_count, h->d_lvl_n, h->d_flags, h->d_sticky, h->d_kps, h->d_desc, h->d_nout};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -1258,7 +1269,15 @@ PL_API int pl_orb_bytes_per_frame(const pl_orb* h, long long* pyr, long long* bl
 PL_API int pl_orb_sync(pl_orb* h) {
     PL_CHECK_ARG(h);
     PL_CUDA_TRY(cudaSetDevice(h->device));
+    int sticky = 0;
+    PL_CUDA_TRY(cudaMemcpyAsync(&sticky, h->d_sticky, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (sticky) {
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_sticky, 0, sizeof(int), h->stream));
+        set_error("a frame extracted through the device-pointer API exceeded a capacity (flags=%d: 1=FAST candidates, 2=quadtree nodes, "
+                  "4=caller cap); it produced no keypoints", sticky);
+        return PL_ERR_CAPACITY;
+    }
     return PL_OK;
 }
 
@@ -1279,6 +1298,7 @@ PL_API int pl_orb_extract_batch_dev(pl_orb* h, const uint8_t* d_gray, int n_fram
         rc = launch_chunk(h, d_gray + (size_t)f0 * frame_stride, nf, step, frame_stride, d_kps + (size_t)f0 * cap,
                           d_desc + (size_t)f0 * cap * 32, cap, d_n_out + f0);
         if (rc != PL_OK) return rc;
+        k_or_flags<<<1, 32, 0, h->stream>>>(h->d_flags, nf, h->d_sticky);
     }
     return PL_OK;
 }
