@@ -12,8 +12,9 @@ Extraction of different frames is independent, so it is batched; matching runs f
 
   value : frames/s with the images already resident in HBM (device pointers into the C ABI); wall clock between
           device synchronisations, max over ranks.
-  e2e   : the same pass through the host-pointer C ABI: images in pinned host memory, H2D copies, D2H of features,
-          the caller glue (Frame-lite, numpy) and the matcher calls — everything a user of the API pays.
+  e2e   : the same pass from HOST buffers: images in pinned host memory uploaded once per step, both extractors through
+          the device-pointer C ABI, D2H of all features into pinned memory, the caller glue (Frame-lite, numpy) and the
+          matcher calls with host arrays — everything a user of the API pays.
   --impl reference : the CPU oracle (oracle/, the restatement of the reference's CPU path pinned to OpenCV 4.13) on all
           host cores, frame-parallel extraction + the same glue and matchers, on a bounded sample of the sequence.
 
@@ -188,14 +189,47 @@ def run_ours(a, rank, world, local_rank, dist):
         gb.m.sync()
 
     e2e_fe = fe.TrackingFrontEnd(gb)
-    pool = concurrent.futures.ThreadPoolExecutor(1)
+
+    # e2e staging: pinned host mirrors of the outputs (the step's D2H reads) and a device image buffer (the step's H2D write)
+    e_gray = torch.empty_like(d_gray)
+    p_kps, p_desc, p_n = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (d_kps, d_desc, d_n))
+    p_kls, p_ldesc, p_lco, p_ln = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (d_kls, d_ldesc, d_lco, d_ln))
+
+    s_orb, s_line = torch.cuda.ExternalStream(gb.orb.stream()), torch.cuda.ExternalStream(gb.line.stream())
+    ev_orb = torch.cuda.Event()
+
+    class LinesLater:
+        """result() waits for the line extractor's stream and reads its outputs back (the line side of the glue asks for it)."""
+
+        def result(self):
+            gb.line.sync()
+            for dst, src in ((p_kls, d_kls), (p_ldesc, d_ldesc), (p_lco, d_lco), (p_ln, d_ln)):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            kl = p_kls.numpy().view(N.KL_DTYPE).reshape(F, MAXL)
+            ld, lc, ln = p_ldesc.numpy(), p_lco.numpy(), p_ln.numpy()
+            return [(kl[i, :ln[i]], ld[i, :ln[i]], lc[i, :ln[i]]) for i in range(F)]
 
     def step_e2e():
-        # the point side goes first (ORB extraction is short); the line extraction then runs in a second host thread, as the
-        # reference's second extractor thread does (Frame.cc:152-155), while the caller glue of the point side proceeds
-        orb = gb.extract_orb(h_gray.numpy())
-        lines = pool.submit(gb.extract_lines, h_gray.numpy())
-        return e2e_fe.run(h_gray.numpy(), depth, Tcw, sf, features=(orb, lines))
+        # host images -> device ONCE (both extractors read the same upload), ORB first (short), the line extractor right behind
+        # it on its own stream; the ORB results come back and the point side of the caller glue proceeds while the line
+        # extractor is still running (the reference runs its two extractors in two threads for the same reason, Frame.cc:152-155)
+        e_gray.copy_(h_gray, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        gb.orb.extract_batch_dev(e_gray.data_ptr(), F, H, W, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+        # the region grower of the line path fills every SM for tens of ms and no other kernel can share an SM with it: the
+        # line stream waits for the (short) ORB work, otherwise ORB's later kernels would queue behind it
+        ev_orb.record(s_orb)
+        s_line.wait_event(ev_orb)
+        gb.line.extract_batch_dev(e_gray.data_ptr(), F, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
+        gb.orb.sync()
+        for dst, src in ((p_kps, d_kps), (p_desc, d_desc), (p_n, d_n)):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        kp = p_kps.numpy().view(N.KP_DTYPE).reshape(F, cap)
+        dd, nn = p_desc.numpy(), p_n.numpy()
+        orb = [(kp[i, :nn[i]], dd[i, :nn[i]]) for i in range(F)]
+        return e2e_fe.run(h_gray.numpy(), depth, Tcw, sf, features=(orb, LinesLater()))
 
     def barrier():
         torch.cuda.synchronize()
@@ -333,7 +367,7 @@ def run_ours(a, rank, world, local_rank, dist):
         "step_breakdown_ms": {"extract": round(t_ext * 1e3, 2), "match": round(t_match * 1e3, 2), "matcher_calls": len(plan.calls)},
         "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(F * W * H),
                 "d2h_bytes_per_step": int(F * (cap * 60 + MAXL * (68 + 32 + 24) + 8)), "steps": e2e_steps,
-                "note": "host-pointer C ABI (line extraction in a second host thread) + numpy caller glue (Frame-lite) + per-call matcher copies"},
+                "note": "host images uploaded once, both extractors through the device-pointer C ABI on their own streams, results read back to pinned host memory; numpy caller glue (Frame-lite) overlapping the line extractor; matcher calls with host arrays"},
         "gpu_launches": int(launches_per_step * a.steps),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "matches_per_frame": {"c3": round(float(np.mean([r.get("c3_matches", 0) for r in summary])), 1),
