@@ -1005,6 +1005,37 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
 // earlier tickets in the map, so the result is the sequential one whatever the stamps say.  rect_improve only reads
 // the angle map and does not influence later regions: it runs afterwards in k_lsd_nfa, and accepted segments are
 // compacted in seed order.
+struct LsdQueueItem { LsdRect rec; };
+constexpr int kNfaChunk = 16;         // rectangles per work item of the tail helpers
+constexpr int kNfaChunksPerFrame = 2048;  // item = frame * kNfaChunksPerFrame + chunk
+constexpr uint8_t kNfaTodo = 0xff;    // qvalid: rectangle not validated yet
+// rect_improve of rectangle t of frame f -> qres / qvalid (one warp)
+__device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restrict__ ang, const LsdQueueItem* __restrict__ queue,
+                                         LsdSeg* __restrict__ qres, uint8_t* __restrict__ qvalid, const NfaTabs& T, int f, int t) {
+    const int lane = threadIdx.x & 31;
+    LsdFrame F;
+    F.ang = ang;
+    F.g2 = nullptr; F.cs = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
+    F.W = g.W; F.H = g.H;
+    F.sparse = false; F.dir = nullptr; F.rev = nullptr; F.pool = nullptr; F.ntiles = nullptr; F.tw = 0; F.pool_tiles = 0;
+    F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
+    F.claims = nullptr; F.ticket = 0; F.commit_head = nullptr;
+    const double log_eps = 0.0;
+    LsdRect rec = queue[(size_t)f * g.seg_cap + t].rec;
+    const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
+    if (lane == 0) {
+        LsdSeg sg;
+        sg.x1 = (float)((rec.x1 + 0.5) / 0.8); sg.y1 = (float)((rec.y1 + 0.5) / 0.8);
+        sg.x2 = (float)((rec.x2 + 0.5) / 0.8); sg.y2 = (float)((rec.y2 + 0.5) / 0.8);
+        sg.width = rec.width / 0.8;
+        sg.p = rec.p;
+        sg.nfa = log_nfa;
+        qres[(size_t)f * g.seg_cap + t] = sg;
+        qvalid[(size_t)f * g.seg_cap + t] = log_nfa > log_eps;
+    }
+    __syncwarp();
+}
+
 constexpr int kMaxGrowers = 16;    // grower warps per CTA
 constexpr int kMaxFrameSlots = 4;  // frames a CTA works on at once
 constexpr int kSlots = 256;        // ticket slots per frame (the window of uncommitted tickets is at most this)
@@ -1012,13 +1043,13 @@ constexpr int kPool = 64;          // region buffers per CTA
 constexpr int kSmall = 64;         // regions up to this size (and log length) are parked in their slot's small buffer instead
 constexpr int kSvalEntries = 36;
 constexpr int kMaxPoolTiles = 64, kMinPoolTiles = 24;
-struct LsdQueueItem { LsdRect rec; };
 // shared memory of a grower warp: sval | ring | tile pool | rev | dir | ntiles, each part 16-byte aligned
 struct GrowSmem {
     int tiles, pool_tiles;
     int window;       // tickets that may be uncommitted at once (<= kSlots): deeper speculation wastes more growth
     int frame_slots;  // frames per CTA
     int bits_words;   // words of a W*H bitmap
+    int tail_nfa;     // CTAs without frames validate rectangles of finished frames
     __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
     __host__ __device__ size_t off_pool() const { return off_ring() + kRegRing * sizeof(unsigned int); }
     __host__ __device__ size_t off_rev() const { return off_pool() + (size_t)pool_tiles * 32 * sizeof(unsigned int); }
@@ -1130,6 +1161,12 @@ struct GrowBufs {
     long long* phase_cycles;
     int* frame_counter;
     size_t plane;
+    // tail helpers: finished frames publish chunks of their rectangles; CTAs without frames validate them
+    LsdSeg* qres;
+    uint8_t* qvalid;
+    unsigned int* nfa_items;  // [nf * kNfaChunksPerFrame] 0xffffffff = not published yet
+    int* nfa_ctl;             // [0] items published (tail), [1] items taken (cursor), [2] frames finished
+    NfaTabs nfa_tabs;
 };
 
 // A CTA works on up to gs.frame_slots frames at once and its warps take whatever work any of them offers, so a warp
@@ -1211,7 +1248,33 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
             if (action != kActNone) break;
             __nanosleep(400);
         }
-        if (action == kActExit) break;
+        if (action == kActExit) {
+            // no frame left for this CTA: validate rectangles of finished frames while other CTAs are still growing.  Once every
+            // frame is finished the kernel should end: k_lsd_nfa then validates what is left with the whole GPU.
+            bool quit = nf <= (int)gridDim.x || !gs.tail_nfa;  // one frame per CTA at most: there is no tail worth filling
+            while (!quit) {
+                int it = 0;
+                if (lane == 0) it = atomicAdd(B.nfa_ctl + 1, 1);
+                it = __shfl_sync(FULL, it, 0);
+                unsigned item = 0xffffffffu;
+                while (true) {  // the item may not be published yet
+                    if (lane == 0) {
+                        if (*(volatile int*)(B.nfa_ctl + 2) >= nf) item = 0xfffffffeu;  // every frame finished: stop helping
+                        else if (it < *(volatile int*)(B.nfa_ctl + 0)) item = *(volatile unsigned int*)(B.nfa_items + it);
+                    }
+                    item = __shfl_sync(FULL, item, 0);
+                    if (item != 0xffffffffu) break;
+                    __nanosleep(1000);
+                }
+                if (item == 0xfffffffeu) break;
+                __threadfence();
+                const int fi = (int)(item / kNfaChunksPerFrame), ch = (int)(item % kNfaChunksPerFrame);
+                const int nr = min(B.n_rects[fi], g.seg_cap);
+                for (int t = ch * kNfaChunk; t < min(nr, (ch + 1) * kNfaChunk); t++)
+                    lsd_nfa_one(g, B.angdeg + (size_t)fi * plane, B.queue, B.qres, B.qvalid, B.nfa_tabs, fi, t);
+            }
+            break;
+        }
         fsi = __shfl_sync(FULL, fsi, 0);
         rr = fsi + 1 < FS ? fsi + 1 : 0;
         if (action == kActBuffer) {
@@ -1246,6 +1309,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                     ctl->active = kFrameBusy;
                     const int f = ctl->frame;
                     B.n_rects[f] = ctl->head;
+                    __threadfence();
                     if (B.phase_cycles) {
                         long long* pc = B.phase_cycles + (size_t)f * 8;
                         pc[0] = (long long)((ctl->stat[4] / 1000) + ((ctl->stat[7] / 1000) << 20) + ((ctl->stat[5] / 1000) << 40));
@@ -1259,6 +1323,19 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                     }
                 }
                 __syncwarp();
+                if (mine) {  // publish the frame's rectangles for the tail helpers, then count the frame as finished
+                    const int fdone = __shfl_sync(FULL, ctl->frame, 0), nr = min(__shfl_sync(FULL, ctl->head, 0), g.seg_cap);
+                    const int nchunks = (nr + kNfaChunk - 1) / kNfaChunk;
+                    if (nchunks > 0 && nchunks <= kNfaChunksPerFrame) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(B.nfa_ctl + 0, nchunks);
+                        base = __shfl_sync(FULL, base, 0);
+                        for (int i = lane; i < nchunks; i += 32) B.nfa_items[base + i] = (unsigned)fdone * kNfaChunksPerFrame + (unsigned)i;
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(B.nfa_ctl + 2, 1);
+                }
             }
             if (!mine) continue;
             int f = 0;
@@ -1506,36 +1583,19 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
 }
 
 // NFA validation of the fitted rectangles (rect_improve): it only reads the angle map and does not influence any
-// other region, so every rectangle of every frame is independent — one warp per rectangle, grid-strided.
+// other region, so every rectangle of every frame is independent — one warp per rectangle.  Rectangles are validated
+// in two places: grower CTAs that have run out of frames take chunks of kNfaChunk rectangles of finished frames from a
+// queue while the last frames are still being grown (the tail of k_lsd_grow would otherwise leave most SMs idle), and
+// k_lsd_nfa afterwards does whatever is left (qvalid == kNfaTodo).
 constexpr int kNfaBlocksPerFrame = 32, kNfaThreads = 256;
 __global__ void __launch_bounds__(kNfaThreads, 4) k_lsd_nfa(LineGeom g, const float* __restrict__ angdeg, size_t plane,
                                                          const LsdQueueItem* __restrict__ queue, const int* __restrict__ n_rects,
                                                          LsdSeg* __restrict__ qres, uint8_t* __restrict__ qvalid, NfaTabs T) {
-    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int f = blockIdx.y;
     const int wid = blockIdx.x * (kNfaThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kNfaThreads / 32);
-    LsdFrame F;
-    F.ang = angdeg + (size_t)f * plane;
-    F.g2 = nullptr; F.cs = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
-    F.W = g.W; F.H = g.H;
-    F.sparse = false; F.dir = nullptr; F.rev = nullptr; F.pool = nullptr; F.ntiles = nullptr; F.tw = 0; F.pool_tiles = 0;
-    F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
-    F.claims = nullptr; F.ticket = 0; F.commit_head = nullptr;
     const int n = min(n_rects[f], g.seg_cap);
-    const double log_eps = 0.0;
-    for (int t = wid; t < n; t += nw) {
-        LsdRect rec = queue[(size_t)f * g.seg_cap + t].rec;
-        const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
-        if (lane == 0) {
-            LsdSeg sg;
-            sg.x1 = (float)((rec.x1 + 0.5) / 0.8); sg.y1 = (float)((rec.y1 + 0.5) / 0.8);
-            sg.x2 = (float)((rec.x2 + 0.5) / 0.8); sg.y2 = (float)((rec.y2 + 0.5) / 0.8);
-            sg.width = rec.width / 0.8;
-            sg.p = rec.p;
-            sg.nfa = log_nfa;
-            qres[(size_t)f * g.seg_cap + t] = sg;
-            qvalid[(size_t)f * g.seg_cap + t] = log_nfa > log_eps;
-        }
-    }
+    for (int t = wid; t < n; t += nw)
+        if (qvalid[(size_t)f * g.seg_cap + t] == kNfaTodo) lsd_nfa_one(g, angdeg + (size_t)f * plane, queue, qres, qvalid, T, f, t);
 }
 
 }  // namespace pl
@@ -1922,8 +1982,11 @@ struct pl_line {
     unsigned int* d_small_buf = nullptr;
     unsigned short* d_claims = nullptr;
     int* d_frame_counter = nullptr;
+    int* d_nfa_ctl = nullptr;
+    unsigned int* d_nfa_items = nullptr;
     int* d_sticky = nullptr;  // capacity flags of the device-pointer API since the last pl_line_sync
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
+    int tail_nfa = 1;
     GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
     unsigned int* d_big_bits = nullptr;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
@@ -2053,7 +2116,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         // one CTA per SM; a CTA works on several frames at once when there are more frames than SMs
         const bool many = nf > h->num_sms && h->cfg_many.growers > 0;
         const GrowConfig& cf = many ? h->cfg_many : h->cfg_few;
-        GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words};
+        GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words, h->tail_nfa};
         const int ctas = std::min(nf, h->num_sms);
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_claims, 0xff, sizeof(unsigned short) * plane * nf, st));
@@ -2063,6 +2126,10 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         gb.pool_reg = h->d_spec_reg; gb.pool_touched = h->d_spec_touched; gb.pool_rect = h->d_pool_rect;
         gb.small_buf = h->d_small_buf; gb.small_rect = h->d_small_rect; gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
         gb.flags = h->d_flags; gb.phase_cycles = prof ? h->d_phase : nullptr; gb.frame_counter = h->d_frame_counter; gb.plane = plane;
+        gb.qres = h->d_qres; gb.qvalid = h->d_qvalid; gb.nfa_items = h->d_nfa_items; gb.nfa_ctl = h->d_nfa_ctl; gb.nfa_tabs = h->nfa_tabs;
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_ctl, 0, 4 * sizeof(int), st));
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
         if (cf.growers <= 8) k_lsd_grow<256><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
         else k_lsd_grow<512><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
     }
@@ -2187,7 +2254,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                 *c = GrowConfig{0, 0, fs};
                 for (int gN = max_g; gN >= 1 && c->growers == 0; gN--)
                     for (int pN = kMaxPoolTiles; pN >= kMinPoolTiles; pN -= 8) {
-                        GrowSmem gs{tiles, pN, 0, fs, h->bits_words};
+                        GrowSmem gs{tiles, pN, 0, fs, h->bits_words, 0};
                         if (gs.total(gN) <= budget) {
                             c->growers = gN;
                             c->pool_tiles = pN;
@@ -2214,11 +2281,12 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                 }
             }
             h->grow_tiles = tiles;
+            if (const char* ev = getenv("PLSLAM_LSD_TAIL_NFA")) h->tail_nfa = atoi(ev) != 0;
             h->grow_window = 128;
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));
             if (h->cfg_few.growers < 1) {
                 set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region growers, the device offers %zu",
-                          max_cols, max_rows, GrowSmem{tiles, kMinPoolTiles, 0, 1, h->bits_words}.total(1), budget);
+                          max_cols, max_rows, GrowSmem{tiles, kMinPoolTiles, 0, 1, h->bits_words, 0}.total(1), budget);
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
@@ -2238,6 +2306,8 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_big_bits, max_fs * (size_t)h->bits_words);
     if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_fs * (size_t)h->bits_words * sizeof(unsigned int));
     A(&h->d_frame_counter, 1);
+    A(&h->d_nfa_ctl, 4);
+    A(&h->d_nfa_items, B * kNfaChunksPerFrame);
     A(&h->d_sticky, 1);
     if (e == cudaSuccess) e = cudaMemset(h->d_sticky, 0, sizeof(int));
     A(&h->d_resp, B * seg_cap);
@@ -2295,7 +2365,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_sticky, h->d_cs, h->d_cs0, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_sticky, h->d_cs, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
