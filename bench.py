@@ -55,6 +55,29 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic_bytes(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full summary
+    (profiles/*_ncu_set_full_selected.csv, newest tag), or None."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_set_full_selected.csv")))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in reversed(files):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            units = None
+            for r in rows[1:]:
+                if r[0].endswith("(units)"):
+                    units = r
+                elif kernel in r[1] and units is not None:
+                    return int(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+        except (OSError, ValueError, KeyError, IndexError):
+            continue
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -357,7 +380,7 @@ def run_ours(a, rank, world, local_rank, dist):
             rl[k] = {"ms_per_pass": round(ms, 4)}
     ach = alg_bytes.get(dom, 0) * F / (stage[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": ncu_traffic_bytes("k_lsd_grow<512>"), "peak_source": peak_src,
                 "note": "k_lsd_grow is the ordered (sequential-semantics) region grower, run as speculative transactions with in-order commit (DESIGN.md 4.1): latency-bound, not a streaming kernel; the HBM fraction is printed for completeness only",
                 "per_kernel": rl}
 

@@ -320,18 +320,19 @@ __device__ __forceinline__ void lsd_unmark(const LsdFrame& F, int x, int y, unsi
     else atomicAnd(&F.pool[(unsigned)F.dir[(y >> 5) * F.tw + (x >> 5)] * 32 + (y & 31)], ~(1u << (x & 31)));
 }
 // warp-collective: makes sure the tiles of the lanes with `want` exist; false when the pool is exhausted
-__device__ __noinline__ bool lsd_priv_alloc_tiles(const LsdFrame& F, int t, unsigned need) {
+__device__ __noinline__ bool lsd_priv_alloc_tiles(unsigned int* pool, unsigned char* dir, unsigned short* rev, int* ntiles, int pool_tiles,
+                                                  int t, unsigned need) {
     const int lane = threadIdx.x & 31;
     while (need) {
         const int tj = __shfl_sync(0xffffffffu, t, __ffs(need) - 1);
-        const int k = *(volatile int*)F.ntiles;
-        if (k >= F.pool_tiles) return false;
-        F.pool[k * 32 + lane] = 0;
+        const int k = *(volatile int*)ntiles;
+        if (k >= pool_tiles) return false;
+        pool[k * 32 + lane] = 0;
         __syncwarp();
         if (lane == 0) {
-            F.dir[tj] = (unsigned char)k;
-            F.rev[k] = (unsigned short)tj;
-            *(volatile int*)F.ntiles = k + 1;
+            dir[tj] = (unsigned char)k;
+            rev[k] = (unsigned short)tj;
+            *(volatile int*)ntiles = k + 1;
         }
         __syncwarp();
         need &= ~__ballot_sync(0xffffffffu, t == tj);
@@ -343,7 +344,7 @@ __device__ __forceinline__ bool lsd_priv_alloc(const LsdFrame& F, bool want, int
     const int t = want ? (y >> 5) * F.tw + (x >> 5) : -1;
     const unsigned need = __ballot_sync(0xffffffffu, want && F.dir[max(t, 0)] == 0xffu);
     if (__builtin_expect(!need, 1)) return true;
-    return lsd_priv_alloc_tiles(F, t, need);
+    return lsd_priv_alloc_tiles(F.pool, F.dir, F.rev, F.ntiles, F.pool_tiles, t, need);
 }
 // back to "nothing marked"; nt = entries of the touched log (every pixel ever marked is in it)
 __device__ __forceinline__ void lsd_priv_reset(const LsdFrame& F, int nt) {
@@ -657,8 +658,9 @@ __device__ __forceinline__ double lsd_density(int n, const LsdRect& rec) {
 }
 
 // reduce_region_radius(): sequential swap-with-last removal keeps the reference's point order
-__device__ __noinline__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n, double reg_angle, double prec, double p, LsdRect& rec,
+__device__ __noinline__ bool lsd_reduce_region_radius(const LsdFrame& Fin, int& n, double reg_angle, double prec, double p, LsdRect& rec,
                                          double density, double density_th) {
+    const LsdFrame F = Fin;
     const int lane = threadIdx.x & 31;
     const unsigned p0 = F.reg[0];
     const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
@@ -684,7 +686,7 @@ __device__ __noinline__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n,
         n = __shfl_sync(0xffffffffu, n, 0);
         __syncwarp();
         if (n < 2) return false;
-        lsd_region2rect(F, n, reg_angle, prec, p, rec);
+        lsd_region2rect(Fin, n, reg_angle, prec, p, rec);
         density = lsd_density(n, rec);
     }
     return true;
@@ -692,7 +694,8 @@ __device__ __noinline__ bool lsd_reduce_region_radius(const LsdFrame& F, int& n,
 
 // refine()
 // returns 1 = refined, 0 = rejected, -1 = capacity exceeded (speculative growers)
-__device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double prec, double p, LsdRect& rec, double density_th, int& nt) {
+// F: register copy for the inlined loops; Fm: the same view in (shared) memory, handed to the out-of-line callees
+__device__ int lsd_refine(const LsdFrame& F, const LsdFrame& Fm, int& n, double& reg_angle, double prec, double p, LsdRect& rec, double density_th, int& nt) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     double density = lsd_density(n, rec);
@@ -726,12 +729,12 @@ __device__ int lsd_refine(const LsdFrame& F, int& n, double& reg_angle, double p
     const double mean_angle = sum / (double)cnt_in;
     const double tau = 2.0 * sqrt(__dadd_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)) / (double)cnt_in,
                                             __dmul_rn(mean_angle, mean_angle)));
-    n = lsd_region_grow(F, sx, sy, tau, &reg_angle, nt);
+    n = lsd_region_grow(Fm, sx, sy, tau, &reg_angle, nt);
     if (n < 0) return n;
     if (n < 2) return 0;
-    lsd_region2rect(F, n, reg_angle, prec, p, rec);
+    lsd_region2rect(Fm, n, reg_angle, prec, p, rec);
     density = lsd_density(n, rec);
-    if (density < density_th) return lsd_reduce_region_radius(F, n, reg_angle, prec, p, rec, density, density_th) ? 1 : 0;
+    if (density < density_th) return lsd_reduce_region_radius(Fm, n, reg_angle, prec, p, rec, density, density_th) ? 1 : 0;
     return 1;
 }
 
@@ -1115,26 +1118,31 @@ __device__ __forceinline__ int pool_pop(unsigned long long* mask, int lane) {
     return __shfl_sync(0xffffffffu, b, 0);
 }
 // grow + fit + refine one seed into the buffers of F; leaves the private marks clean
+// Fin and out live in shared memory (one per warp): the out-of-line callees read the view from there instead of
+// every thread keeping (and spilling) its own copy in local memory.
 __device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min_reg_size, GrowResult* out) {
-    const LsdFrame F = Fin;  // a private copy the compiler keeps in registers (the caller's lives in local memory)
+    const LsdFrame F = Fin;  // register copy for the inlined code
+    const int lane = threadIdx.x & 31;
     const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
     const double density_th = 0.7;
     const int sx = pix % F.W, sy = pix / F.W;
     double reg_angle;
     int nt = 0, status = kStNoRect;
     LsdRect rec;
-    int n = lsd_region_grow(F, sx, sy, prec, &reg_angle, nt);
+    int n = lsd_region_grow(Fin, sx, sy, prec, &reg_angle, nt);
     if (n < 0) {
         status = n;
     } else if (n >= min_reg_size) {
-        lsd_region2rect(F, n, reg_angle, prec, p, rec);
-        status = lsd_refine(F, n, reg_angle, prec, p, rec, density_th, nt);
+        lsd_region2rect(Fin, n, reg_angle, prec, p, rec);
+        status = lsd_refine(F, Fin, n, reg_angle, prec, p, rec, density_th, nt);
     }
     lsd_priv_reset(F, nt);
-    out->status = status;
-    out->n = n;
-    out->nt = nt;
-    if (status == kStRect) out->rec = rec;
+    if (lane == 0) {
+        out->status = status;
+        out->n = n;
+        out->nt = nt;
+        if (status == kStRect) out->rec = rec;
+    }
     __syncwarp();
 }
 
@@ -1178,6 +1186,8 @@ template <int kBound>
 __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, GrowBufs B) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ GrowCtl s_ctl[kMaxFrameSlots];
+    __shared__ LsdFrame s_view[kMaxGrowers];    // the frame view a warp hands to lsd_grow_seed
+    __shared__ GrowResult s_res[kMaxGrowers];
     __shared__ unsigned long long s_free_mask;  // free buffers of the pool
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -1417,7 +1427,11 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                         FS2.reg_cap = (int)plane;
                         FS2.touched_cap = (int)(2 * plane);
                         FS2.ticket = h;
-                        lsd_grow_seed(FS2, pix, g.min_reg_size, &res);
+                        __syncwarp();
+                        if (lane == 0) s_view[warp] = FS2;
+                        __syncwarp();
+                        lsd_grow_seed(s_view[warp], pix, g.min_reg_size, &s_res[warp]);
+                        res = s_res[warp];
                         status = res.status;
                         n = res.n;
                         rec = res.rec;
@@ -1554,7 +1568,11 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
             FS2.reg_cap = FS2.touched_cap = kSpecCap;
             FS2.ticket = my_ticket;
             const long long g0 = clock64();
-            lsd_grow_seed(FS2, my_pix, g.min_reg_size, &res);
+            __syncwarp();
+            if (lane == 0) s_view[warp] = FS2;
+            __syncwarp();
+            lsd_grow_seed(s_view[warp], my_pix, g.min_reg_size, &s_res[warp]);
+            res = s_res[warp];
             // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer
             const bool small = res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
             const bool keep = res.status >= 0 && !small;
@@ -2249,7 +2267,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             // shared memory: per frame slot the ticket slots + committed bitmap, per grower the ring, the staging area
             // and the sparse private bitmap (a pool of 32x32-pixel tiles: the more, the fewer regions overflow)
             const int tiles = ((W + 31) / 32) * ((H + 31) / 32);
-            const size_t budget = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;  // static control blocks
+            const size_t budget = prop.sharedMemPerBlockOptin > 8192 ? prop.sharedMemPerBlockOptin - 8192 : 0;  // static: control blocks, views, results
             auto choose = [&](int fs, int max_g, GrowConfig* c) {
                 *c = GrowConfig{0, 0, fs};
                 for (int gN = max_g; gN >= 1 && c->growers == 0; gN--)
