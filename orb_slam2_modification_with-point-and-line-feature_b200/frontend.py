@@ -49,6 +49,7 @@ class FrameLite:
     def set_lines(self, kls, ldesc):
         """Attaches the line features (they may arrive later than the points: the two extractors run concurrently)."""
         self.kls, self.ldesc = kls, ldesc
+        self._ul = None
         depth = self._depth_img
         h, w = depth.shape
         # line endpoints: depth at the rounded endpoint
@@ -70,6 +71,8 @@ class FrameLite:
         return (pc @ self.Rwc.T + self.Ow).astype(f32)
 
     def unproject_lines(self):
+        if getattr(self, "_ul", None) is not None:
+            return self._ul
         K = self.K
         Rwc, Ow = self.Rwc.astype(np.float64), self.Ow.astype(np.float64)
 
@@ -79,7 +82,45 @@ class FrameLite:
 
         s3 = lift(self.kls["sx"].astype(np.float64), self.kls["sy"].astype(np.float64), self.ds)
         e3 = lift(self.kls["ex"].astype(np.float64), self.kls["ey"].astype(np.float64), self.de)
-        return s3, e3, (self.ds > 0) & (self.de > 0)
+        self._ul = (s3, e3, (self.ds > 0) & (self.de > 0))
+        return self._ul
+
+    @staticmethod
+    def attach_lines_batch(frames, lines, depth):
+        """set_lines + unproject_lines of a whole sequence in one vectorised pass (depth: the (n, h, w) array the frames were
+        built from).  Same arithmetic as the per-frame methods."""
+        n = len(frames)
+        counts = np.array([len(l[0]) for l in lines], np.int64)
+        if counts.sum() == 0 or not isinstance(depth, np.ndarray) or depth.ndim != 3:
+            for F, (kls, ldesc, _) in zip(frames, lines):
+                F.set_lines(kls, ldesc)
+            return
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        kl = np.concatenate([l[0] for l in lines])
+        fidx = np.repeat(np.arange(n), counts)
+        h, w = depth.shape[1:]
+        sx = np.clip(np.rint(kl["sx"]).astype(np.int64), 0, w - 1)
+        sy = np.clip(np.rint(kl["sy"]).astype(np.int64), 0, h - 1)
+        ex = np.clip(np.rint(kl["ex"]).astype(np.int64), 0, w - 1)
+        ey = np.clip(np.rint(kl["ey"]).astype(np.int64), 0, h - 1)
+        ds = depth[fidx, sy, sx].astype(np.float64)
+        de = depth[fidx, ey, ex].astype(np.float64)
+        K = frames[0].K
+        Rwc = np.stack([F.Rwc for F in frames]).astype(np.float64)[fidx]
+        Ow = np.stack([F.Ow for F in frames]).astype(np.float64)[fidx]
+
+        def lift(px, py, z):
+            pc = np.stack([(px - K["cx"]) * z / K["fx"], (py - K["cy"]) * z / K["fy"], z], 1)
+            return np.einsum("nij,nj->ni", Rwc, pc) + Ow
+
+        s3 = lift(kl["sx"].astype(np.float64), kl["sy"].astype(np.float64), ds)
+        e3 = lift(kl["ex"].astype(np.float64), kl["ey"].astype(np.float64), de)
+        ok = (ds > 0) & (de > 0)
+        for t, F in enumerate(frames):
+            a, b = offs[t], offs[t + 1]
+            F.kls, F.ldesc = lines[t][0], lines[t][1]
+            F.ds, F.de = ds[a:b], de[a:b]
+            F._ul = (s3[a:b], e3[a:b], ok[a:b])
 
     def view(self, claimed, keep):
         return N.make_frame_view(self.kps, self.desc, self.u_right, claimed, self.bounds, self.K, self.Tcw[:3].reshape(-1), self.sf, keep)
@@ -241,10 +282,9 @@ class TrackingFrontEnd:
             lines = lines.result()
         lmaps = []
         lm = LocalMap()
+        FrameLite.attach_lines_batch(frames, lines, depth)
         for t in range(n):
-            kls, ldesc, _ = lines[t]
-            frames[t].set_lines(kls, ldesc)
-            summary[t].update(n_kl=len(kls))
+            summary[t].update(n_kl=len(lines[t][0]))
             lmaps.append((lm.ls, lm.le, lm.lkl, lm.ldesc))
             if t % self.kf_every == 0:
                 lm.add_keyframe_lines(frames[t])
