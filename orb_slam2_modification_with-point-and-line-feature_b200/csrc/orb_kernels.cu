@@ -675,43 +675,64 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const OrbGeom* __restric
 // ---------------------------------------------------------------------------------------------------------------
 // GaussianBlur 7x7 sigma 2, 8U fixed point (OpenCV >= 4): kernel {18,34,48,56,48,34,18}/256
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 64, kBlurTH = 32;
+constexpr int kBlurTW = 128, kBlurTH = 28;  // one warp blurs a 128-wide, 28-tall strip: 4 pixels per lane, rows streamed
 struct BlurTile { short level, tx, ty, pad; };
 
-__global__ void __launch_bounds__(256) k_blur7(const OrbGeom* __restrict__ g, const BlurTile* __restrict__ tiles,
+// horizontal pass of four neighbouring pixels x..x+3: p points at image column x - 3 (plane column x + 16, word aligned
+// because the image starts at plane column kEdge = 19), so the 12 bytes b0..b11 hold columns x-3..x+8 and pixel x+j reads
+// b[j..j+6].  Two pixels are evaluated per 32-bit operation: P(k) = b[k] | b[k+1] << 16, and the weighted sum of a 16-bit
+// half is at most 256 * 255, so nothing carries into the other half.
+__device__ __forceinline__ void blur7_hrow(const uint8_t* __restrict__ p, unsigned (&out)[4]) {
+    const unsigned w0 = __ldg((const unsigned*)p), w1 = __ldg((const unsigned*)(p + 4)), w2 = __ldg((const unsigned*)(p + 8));
+    const unsigned v1 = __funnelshift_r(w0, w1, 8), v5 = __funnelshift_r(w1, w2, 8);  // bytes b1..b4, b5..b8
+    const unsigned P0 = __byte_perm(w0, 0, 0x4140), P2 = __byte_perm(w0, 0, 0x4342);
+    const unsigned P1 = __byte_perm(v1, 0, 0x4140), P3 = __byte_perm(v1, 0, 0x4342);
+    const unsigned P4 = __byte_perm(w1, 0, 0x4140), P6 = __byte_perm(w1, 0, 0x4342);
+    const unsigned P5 = __byte_perm(v5, 0, 0x4140), P7 = __byte_perm(v5, 0, 0x4342);
+    const unsigned P8 = __byte_perm(w2, 0, 0x4140);
+    const unsigned A = 18u * (P0 + P6) + 34u * (P1 + P5) + 48u * (P2 + P4) + 56u * P3;  // pixels x, x+1
+    const unsigned B = 18u * (P2 + P8) + 34u * (P3 + P7) + 48u * (P4 + P6) + 56u * P5;  // pixels x+2, x+3
+    out[0] = A & 0xffffu;
+    out[1] = A >> 16;
+    out[2] = B & 0xffffu;
+    out[3] = B >> 16;
+}
+
+// GaussianBlur 7x7 sigma 2 of OpenCV's 8-bit path: separable 8.8 fixed point {18,34,48,56,48,34,18}, horizontal pass exact,
+// vertical pass (sum + 0x8000) >> 16.  One warp per strip; a lane owns 4 columns and keeps the horizontal sums of the last
+// seven rows in registers, so every input byte is loaded once per strip (plus the halo) and there is no shared memory.
+__global__ void __launch_bounds__(256) k_blur7(const OrbGeom* __restrict__ g, const BlurTile* __restrict__ tiles, int n_items,
                                                const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
-    __shared__ uint8_t s_in[(kBlurTH + 6) * (kBlurTW + 8)];
-    __shared__ uint16_t s_h[(kBlurTH + 6) * kBlurTW];
-    const BlurTile t = tiles[blockIdx.x];
-    const int f = blockIdx.y, tid = threadIdx.x;
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= n_items) return;
+    const BlurTile t = tiles[item];
+    const int f = blockIdx.y;
     const LevelGeom& L = g->lv[t.level];
-    const int x0 = t.tx * kBlurTW, y0 = t.ty * kBlurTH;
+    const int x = t.tx * kBlurTW + lane * 4, y0 = t.ty * kBlurTH;
+    if (x >= L.w) return;
+    const int rows = min(kBlurTH, L.h - y0);
     // the bordered plane already holds BORDER_REFLECT_101 of the image itself (19 >= 3), which is exactly the
-    // border GaussianBlur applies to the un-bordered clone (:1085-1086)
-    const uint8_t* src = pyr + L.plane_off + (size_t)f * L.plane_size + (size_t)(y0 - 3 + kEdge) * L.pitch + (x0 - 3 + kEdge);
-    constexpr int IW = kBlurTW + 6, IP = kBlurTW + 8;
-    const int rows_avail = min(kBlurTH + 6, L.h - y0 + 6);   // stay inside the bordered plane
-    const int cols_avail = min(IW, L.w - x0 + 6);
-    for (int i = tid; i < (kBlurTH + 6) * IW; i += 256) {
-        int r = i / IW, c = i - r * IW;
-        s_in[r * IP + c] = (r < rows_avail && c < cols_avail) ? __ldg(src + (size_t)r * L.pitch + c) : 0;
-    }
-    __syncthreads();
-    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-        int r = i / kBlurTW, c = i - r * kBlurTW;
-        const uint8_t* p = s_in + r * IP + c;
-        s_h[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    uint8_t* dst = blur + L.blur_off + (size_t)f * L.blur_size;
-    for (int i = tid; i < kBlurTH * kBlurTW; i += 256) {
-        int r = i / kBlurTW, c = i - r * kBlurTW;
-        int x = x0 + c, y = y0 + r;
-        if (x < L.w && y < L.h) {
-            const uint16_t* p = s_h + r * kBlurTW + c;
-            uint32_t acc = 18u * (p[0] + p[6 * kBlurTW]) + 34u * (p[kBlurTW] + p[5 * kBlurTW]) +
-                           48u * (p[2 * kBlurTW] + p[4 * kBlurTW]) + 56u * p[3 * kBlurTW];
-            dst[(size_t)y * L.bpitch + x] = (uint8_t)((acc + 0x8000u) >> 16);
+    // border GaussianBlur applies to the un-bordered clone (:1085-1086); image column x - 3 is plane column x + 16
+    const uint8_t* src = pyr + L.plane_off + (size_t)f * L.plane_size + (size_t)(y0 - 3 + kEdge) * L.pitch + (x + kEdge - 3);
+    uint8_t* dst = blur + L.blur_off + (size_t)f * L.blur_size + (size_t)y0 * L.bpitch + x;
+    unsigned ring[7][4];
+#pragma unroll
+    for (int k = 0; k < 6; k++) blur7_hrow(src + (size_t)k * L.pitch, ring[k]);
+    for (int r0 = 0; r0 < rows; r0 += 7) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const int r = r0 + k;
+            if (r < rows) {
+                blur7_hrow(src + (size_t)(r + 6) * L.pitch, ring[(k + 6) % 7]);
+                unsigned o = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const unsigned acc = 18u * (ring[k % 7][j] + ring[(k + 6) % 7][j]) + 34u * (ring[(k + 1) % 7][j] + ring[(k + 5) % 7][j]) +
+                                         48u * (ring[(k + 2) % 7][j] + ring[(k + 4) % 7][j]) + 56u * ring[(k + 3) % 7][j];
+                    o |= ((acc + 0x8000u) >> 16) << (8 * j);
+                }
+                *(unsigned*)(dst + (size_t)r * L.bpitch) = o;
+            }
         }
     }
 }
@@ -1078,7 +1099,7 @@ int launch_chunk(pl_orb* h, const uint8_t* d_gray, int nf, size_t step, size_t f
                                                                    h->d_flags);
     launches++;
     if (prof) cudaEventRecord(h->ev[3], st);
-    k_blur7<<<dim3(G.total_tiles, nf), 256, 0, st>>>(h->d_geom, h->d_tiles, h->d_pyr, h->d_blur);
+    k_blur7<<<dim3((G.total_tiles + 7) / 8, nf), 256, 0, st>>>(h->d_geom, h->d_tiles, G.total_tiles, h->d_pyr, h->d_blur);
     launches++;
     if (prof) cudaEventRecord(h->ev[4], st);
     k_orient_brief<<<dim3((G.out_per_frame + 7) / 8, nf), 256, 0, st>>>(h->d_geom, h->d_pyr, h->d_blur, h->d_lvl_kp, h->d_lvl_n,
