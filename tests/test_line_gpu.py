@@ -106,3 +106,20 @@ def test_grower_configuration_does_not_change_the_result(env, api, synth, monkey
         assert np.array_equal(a, b)
     ex.close()
     ref.close()
+
+
+def test_full_hd_frame(api, synth, oracle):
+    """1920x1080: the committed bitmap of a frame takes most of the shared memory, so the grower runs one frame per CTA
+    with fewer warps and a smaller tile pool — same result."""
+    img = synth.frame(77, 1920, 1080)
+    ex = api.LineExtractor(max_cols=1920, max_rows=1080)
+    kls, desc, co = ex.ExtractLineSegment(img)
+    okl, odesc, oco = oracle.line_extract(img, 80)
+    assert len(kls) == len(okl) and np.array_equal(kls["class_id"], okl["class_id"])
+    for f in ("sx", "sy", "ex", "ey"):
+        assert np.abs(kls[f] - okl[f]).max() <= ENDPOINT_TOL_PX
+    assert np.array_equal(desc, odesc)
+    frames = np.stack([img, synth.frame(78, 1920, 1080), img])
+    exb = api.LineExtractor(max_cols=1920, max_rows=1080, max_batch=3)
+    k2, d2, c2, n2 = exb.extract_batch(frames)
+    assert n2[0] == len(okl) and np.array_equal(d2[0, :n2[0]], odesc) and np.array_equal(d2[2, :n2[2]], odesc)
