@@ -390,6 +390,61 @@ PL_API int pl_line_search_for_triangulation(pl_match* h, const uint8_t* desc1, i
 PL_API int pl_line_fuse_candidates(pl_match* h, const uint8_t* ml_desc, const uint8_t* valid, int n, const uint8_t* kf_desc,
                                    int n_kf, int* tdx, int* n_fused);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * E: the remaining ORBmatcher entry points — the LocalMapping / LoopClosing / Initializer callers.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* E1: ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) — ORBmatcher.cc:1107-1277 (variant 0) and
+ * ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) — :1290-1427 (variant 1): the projection search
+ * of every map point into the key frame.  The points do not interact (no claims), so every one is searched at once.
+ * kf[i] = the key frame (tcw = Rcw | tcw; for variant 1 after the scale was divided out by the caller, :1299-1302);
+ * pts[i].valid = pMP && !isBad() && !IsInKeyFrame(pKF) (:1128-1133) / !isBad() && !spAlreadyFound.count(pMP) (:1317-1320);
+ * ow = camera centre; inv_level_sigma2 = pKF->mvInvLevelSigma2 (kf[i].n_levels floats per call, used by the chi-square
+ * gates :1217-1235 of variant 0; may be NULL for variant 1).
+ * best_idx[i][k] = key-frame feature the point k fuses with (bestDist <= TH_LOW, :1249 / :1404) or -1;
+ * best_dist[i][k] = its distance (256 when no candidate survived).  n_fused[i] = number of hits == the reference's return
+ * value when vpMapPoints holds no duplicates.  The Replace / AddObservation bookkeeping (:1251-1272, :1406-1418) stays
+ * with the caller, which walks best_idx in order. */
+PL_API int pl_orb_fuse_candidates_batch(pl_match* h, int n, const pl_frame_view* kf, const pl_posepoint_view* pts, const float* ow /* n x 3 */,
+                                        const float* log_scale_factor /* n */, const float* const* inv_level_sigma2 /* n pointers or NULL */,
+                                        float th, int variant, int* const* best_idx, int* const* best_dist /* may be NULL */, int* n_fused);
+
+/* E2: ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) — ORBmatcher.cc:1441-1692.
+ * kf1 / kf2: the key frames (tcw = R1w | t1w and R2w | t2w; intrinsics of kf1 are used for both projections as in :1445-1448).
+ * pts1 / pts2 = GetMapPointMatches() of each; valid = pMP && !vbAlreadyMatched && !isBad() (:1477-1484, :1551-1557).
+ * t21 = sR21 | t21 and t12 = sR12 | t12 as 3x4 row-major, evaluated by the caller with the reference's cv::Mat
+ * expressions (:1457-1460).  match12[i1] = feature of kf2 whose map point is written to vpMatches12[i1] (:1632-1647), or -1. */
+PL_API int pl_orb_search_by_sim3(pl_match* h, const pl_frame_view* kf1, const pl_frame_view* kf2, const pl_posepoint_view* pts1,
+                                 const pl_posepoint_view* pts2, const float t21[12], const float t12[12], float log_scale_factor1,
+                                 float log_scale_factor2, float th, int* match12, int* n_found);
+
+/* E3: ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — ORBmatcher.cc:573-717.
+ * Only claimed / tcw-independent fields of the views are read.  prev_matched (F1.n x 2 floats, in/out) = vbPrevMatched;
+ * matches12 (F1.n) = vnMatches12.  F2.n <= 20000 (the replay keeps vMatchedDistance / vnMatches21 in shared memory). */
+PL_API int pl_orb_search_for_initialization(pl_match* h, const pl_frame_view* F1, const pl_frame_view* F2, float* prev_matched,
+                                            int window_size, float nn_ratio, int check_orientation, int* matches12, int* n_matches);
+
+/* E4: ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) — ORBmatcher.cc:884-1095 with
+ * CheckDistEpipolarLine (:205-232).  a / b: bow.valid[i] = (GetMapPoint(i) == NULL) (:938-940, :964-966), bow.angle =
+ * mvKeysUn[i].angle; keys_un / u_right = mvKeysUn / mvuRight.  cw1 = pKF1->GetCameraCenter(); kf2_tcw = R2w | t2w; the
+ * epipole (:897-903) is evaluated here like the reference's cv::Mat expression.  pairs receives n_matches (idx1, idx2)
+ * pairs in ascending idx1 (:1085-1091); capacity a.bow.n pairs. */
+typedef struct {
+    pl_bow_view bow;
+    const pl_keypoint* keys_un;
+    const float* u_right;
+} pl_triang_view;
+PL_API int pl_orb_search_for_triangulation(pl_match* h, const pl_triang_view* a, const pl_triang_view* b, const float f12[9],
+                                           const float cw1[3], const float kf2_tcw[12], float fx2, float fy2, float cx2, float cy2,
+                                           const float* scale_factors2, const float* level_sigma2_2, int n_levels2, int only_stereo,
+                                           int check_orientation, int* pairs, int* n_matches);
+
+/* E5: MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:256-321) == MapLine::ComputeDistinctiveDescriptors
+ * (MapLine.cpp:269-330) for n_groups map points / lines at once: group g owns the descriptor rows
+ * [group_off[g], group_off[g+1]) (the observations whose key frame is not bad, in map order).  best_row[g] = row (relative to
+ * the group) with the least median distance to the others (median = sorted[int(0.5*(N-1))], first minimum wins), or -1 for
+ * an empty group. */
+PL_API int pl_distinctive_descriptors(pl_match* h, const uint8_t* desc, const int* group_off, int n_groups, int* best_row);
+
 #ifdef __cplusplus
 }
 #endif

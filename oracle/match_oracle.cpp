@@ -68,6 +68,7 @@ extern "C" void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* 
 // =================================================================================================================
 // Projection searches (ORBmatcher) and line matching (LineMatcher) over the POD views of include/plslam_c.h
 // =================================================================================================================
+#include <climits>
 #include <cmath>
 #include <utility>
 
@@ -736,5 +737,307 @@ extern "C" int orc_line_fuse_candidates(const uint8_t* ml_desc, const uint8_t* v
         }
     }
     *n_fused = fused;
+    return 0;
+}
+
+// =================================================================================================================
+// E rows: the remaining ORBmatcher entry points and ComputeDistinctiveDescriptors
+// =================================================================================================================
+namespace {
+// KeyFrame::IsInImage — KeyFrame.cc:683-686
+inline bool kf_in_image(const pl_frame_view& K, float x, float y) { return x >= K.min_x && x < K.max_x && y >= K.min_y && y < K.max_y; }
+
+// the window search shared by Fuse / SearchBySim3: KeyFrame::GetFeaturesInArea(u, v, radius) + the level gate
+// [lvl-1, lvl]; chi2 != nullptr adds the reprojection gates of ORBmatcher.cc:1217-1235
+inline void best_in_window(const pl_frame_view& K, const Grid& grid, float u, float v, float ur, float radius, int lvl, const uint8_t* dMP,
+                           const float* chi2_inv_sigma2, std::vector<int>& scratch, int& bestDist, int& bestIdx) {
+    bestDist = 256;  // the reference starts from 256 (:1199) or INT_MAX (:1377, :1520): the same for a <= TH test
+    bestIdx = -1;
+    grid.in_area(K, u, v, radius, -1, -1, scratch);
+    for (int idx : scratch) {
+        const pl_keypoint& kp = K.keys_un[idx];
+        const int kpLevel = kp.octave;
+        if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+        if (chi2_inv_sigma2) {
+            if (K.u_right[idx] >= 0) {
+                const float ex = u - kp.x, ey = v - kp.y, er = ur - K.u_right[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * chi2_inv_sigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float ex = u - kp.x, ey = v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * chi2_inv_sigma2[kpLevel] > 5.99) continue;
+            }
+        }
+        const int dist = descriptor_distance(dMP, K.desc + 32 * (size_t)idx);
+        if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+}
+}  // namespace
+
+// ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) — ORBmatcher.cc:1107-1277 (variant 0)
+// ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) — ORBmatcher.cc:1290-1427 (variant 1)
+extern "C" int orc_orb_fuse_candidates(const pl_frame_view* Kp, const pl_posepoint_view* P, const float* ow, float log_scale_factor,
+                                       const float* inv_level_sigma2, float th, int variant, int* best_idx, int* best_dist, int* n_fused) {
+    const pl_frame_view& K = *Kp;
+    Grid grid(K);
+    std::vector<int> scratch;
+    int nFused = 0;
+    for (int i = 0; i < P->n; i++) {
+        best_idx[i] = -1;
+        if (best_dist) best_dist[i] = 256;
+        if (!P->valid[i]) continue;
+        const float* p3Dw = P->world_pos + 3 * (size_t)i;
+        float p3Dc[3];
+        mat_rx_plus_t(K.tcw, p3Dw, p3Dc);
+        if (p3Dc[2] < 0.0f) continue;
+        const float invz = variant == 0 ? 1 / p3Dc[2] : (float)(1.0 / p3Dc[2]);  // :1145 `1/z` (float) vs :1335 `1.0/z` (double, rounded)
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = K.fx * x + K.cx, v = K.fy * y + K.cy;
+        if (!kf_in_image(K, u, v)) continue;
+        const float ur = u - K.bf * invz;
+        const float maxDistance = P->max_dist_inv[i], minDistance = P->min_dist_inv[i];
+        const float PO[3] = {p3Dw[0] - ow[0], p3Dw[1] - ow[1], p3Dw[2] - ow[2]};
+        const float dist3D = norm3(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float* Pn = P->normal + 3 * (size_t)i;
+        double dot = 0;
+        for (int k = 0; k < 3; k++) dot += (double)PO[k] * Pn[k];
+        if (dot < 0.5 * dist3D) continue;
+        const int lvl = predict_scale(P->max_dist[i], dist3D, log_scale_factor, K.n_levels);
+        const float radius = th * K.scale_factors[lvl];
+        int bd, bi;
+        best_in_window(K, grid, u, v, ur, radius, lvl, P->desc + 32 * (size_t)i, variant == 0 ? inv_level_sigma2 : nullptr, scratch, bd, bi);
+        if (best_dist) best_dist[i] = bd;
+        if (bd <= TH_LOW) {
+            best_idx[i] = bi;
+            nFused++;
+        }
+    }
+    *n_fused = nFused;
+    return 0;
+}
+
+// ORBmatcher::SearchBySim3 — ORBmatcher.cc:1441-1692
+namespace {
+void sim3_half(const pl_frame_view& Ka, const pl_frame_view& Kb, const pl_posepoint_view& P, const float* Tba, float log_sf_b, float th,
+               const pl_frame_view& Kintr, std::vector<int>& out) {
+    // points of key frame a (world -> camera a with Ka.tcw, -> camera b with Tba = sRba | tba), searched in key frame b
+    Grid grid(Kb);
+    std::vector<int> scratch;
+    out.assign(P.n, -1);
+    for (int i = 0; i < P.n; i++) {
+        if (!P.valid[i]) continue;
+        float pa[3], pb[3];
+        mat_rx_plus_t(Ka.tcw, P.world_pos + 3 * (size_t)i, pa);
+        mat_rx_plus_t(Tba, pa, pb);
+        if (pb[2] < 0.0) continue;
+        const float invz = (float)(1.0 / pb[2]);
+        const float x = pb[0] * invz, y = pb[1] * invz;
+        const float u = Kintr.fx * x + Kintr.cx, v = Kintr.fy * y + Kintr.cy;
+        if (!kf_in_image(Kb, u, v)) continue;
+        const float dist3D = norm3(pb);
+        if (dist3D < P.min_dist_inv[i] || dist3D > P.max_dist_inv[i]) continue;
+        const int lvl = predict_scale(P.max_dist[i], dist3D, log_sf_b, Kb.n_levels);
+        const float radius = th * Kb.scale_factors[lvl];
+        int bd, bi;
+        best_in_window(Kb, grid, u, v, 0.f, radius, lvl, P.desc + 32 * (size_t)i, nullptr, scratch, bd, bi);
+        if (bd <= TH_HIGH) out[i] = bi;
+    }
+}
+}  // namespace
+extern "C" int orc_orb_search_by_sim3(const pl_frame_view* K1, const pl_frame_view* K2, const pl_posepoint_view* P1, const pl_posepoint_view* P2,
+                                      const float* t21, const float* t12, float log_sf1, float log_sf2, float th, int* match12, int* n_found) {
+    std::vector<int> vnMatch1, vnMatch2;
+    sim3_half(*K1, *K2, *P1, t21, log_sf2, th, *K1, vnMatch1);
+    sim3_half(*K2, *K1, *P2, t12, log_sf1, th, *K1, vnMatch2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < P1->n; i1++) {
+        match12[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && idx2 < P2->n) {
+            if (vnMatch2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+        }
+    }
+    *n_found = nFound;
+    return 0;
+}
+
+// ORBmatcher::SearchForInitialization — ORBmatcher.cc:573-717
+extern "C" int orc_orb_search_for_initialization(const pl_frame_view* F1p, const pl_frame_view* F2p, float* prev_matched, int window_size,
+                                                 float nn_ratio, int check_orientation, int* matches12, int* n_matches) {
+    const pl_frame_view &F1 = *F1p, &F2 = *F2p;
+    Grid grid(F2);
+    int nmatches = 0;
+    for (int i = 0; i < F1.n; i++) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    std::vector<int> vMatchedDistance(F2.n, INT_MAX), vnMatches21(F2.n, -1), vIndices2;
+    for (int i1 = 0; i1 < F1.n; i1++) {
+        const pl_keypoint& kp1 = F1.keys_un[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        grid.in_area(F2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window_size, level1, level1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* d1 = F1.desc + 32 * (size_t)i1;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = descriptor_distance(d1, F2.desc + 32 * (size_t)i2);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nn_ratio) {
+                if (vnMatches21[bestIdx2] >= 0) {
+                    matches12[vnMatches21[bestIdx2]] = -1;
+                    nmatches--;
+                }
+                matches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_orientation) {
+                    float rot = F1.keys_un[i1].angle - F2.keys_un[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                const int idx1 = rotHist[i][j];
+                if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+            }
+        }
+    }
+    for (int i1 = 0; i1 < F1.n; i1++)
+        if (matches12[i1] >= 0) {
+            prev_matched[2 * i1] = F2.keys_un[matches12[i1]].x;
+            prev_matched[2 * i1 + 1] = F2.keys_un[matches12[i1]].y;
+        }
+    *n_matches = nmatches;
+    return 0;
+}
+
+// ORBmatcher::SearchForTriangulation — ORBmatcher.cc:884-1095, CheckDistEpipolarLine — :205-232
+extern "C" int orc_orb_search_for_triangulation(const pl_triang_view* A, const pl_triang_view* B, const float* F12, const float* cw1,
+                                                const float* kf2_tcw, float fx2, float fy2, float cx2, float cy2, const float* scale_factors2,
+                                                const float* level_sigma2_2, int n_levels2, int only_stereo, int check_orientation, int* pairs,
+                                                int* n_matches) {
+    (void)n_levels2;
+    float C2[3];
+    mat_rx_plus_t(kf2_tcw, cw1, C2);
+    const float invz = 1.0f / C2[2];
+    const float ex = fx2 * C2[0] * invz + cx2;
+    const float ey = fy2 * C2[1] * invz + cy2;
+    int nmatches = 0;
+    const pl_bow_view &a = A->bow, &b = B->bow;
+    std::vector<uint8_t> vbMatched2(b.n, 0);
+    std::vector<int> vMatches12(a.n, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;
+    int ka = 0, kb = 0;
+    while (ka < a.n_nodes && kb < b.n_nodes) {
+        if (a.node_id[ka] == b.node_id[kb]) {
+            for (int pa = a.node_off[ka]; pa < a.node_off[ka + 1]; pa++) {
+                const int idx1 = (int)a.feat_idx[pa];
+                if (a.valid && !a.valid[idx1]) continue;  // pMP1 exists
+                const bool bStereo1 = A->u_right[idx1] >= 0;
+                if (only_stereo && !bStereo1) continue;
+                const pl_keypoint& kp1 = A->keys_un[idx1];
+                const uint8_t* d1 = a.desc + 32 * (size_t)idx1;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int pb = b.node_off[kb]; pb < b.node_off[kb + 1]; pb++) {
+                    const int idx2 = (int)b.feat_idx[pb];
+                    if (vbMatched2[idx2] || (b.valid && !b.valid[idx2])) continue;
+                    const bool bStereo2 = B->u_right[idx2] >= 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = descriptor_distance(d1, b.desc + 32 * (size_t)idx2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const pl_keypoint& kp2 = B->keys_un[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * scale_factors2[kp2.octave]) continue;
+                    }
+                    // CheckDistEpipolarLine
+                    const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                    const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                    const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                    const float num = la * kp2.x + lb * kp2.y + lc;
+                    const float den = la * la + lb * lb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * level_sigma2_2[kp2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    vMatches12[idx1] = bestIdx2;
+                    vbMatched2[bestIdx2] = 1;
+                    nmatches++;
+                    if (check_orientation) {
+                        float rot = kp1.angle - B->keys_un[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+            ka++;
+            kb++;
+        } else if (a.node_id[ka] < b.node_id[kb]) {
+            while (ka < a.n_nodes && a.node_id[ka] < b.node_id[kb]) ka++;
+        } else {
+            while (kb < b.n_nodes && b.node_id[kb] < a.node_id[ka]) kb++;
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                vMatches12[rotHist[i][j]] = -1;
+                nmatches--;
+            }
+        }
+    }
+    int np = 0;
+    for (int i = 0; i < a.n; i++)
+        if (vMatches12[i] >= 0) { pairs[2 * np] = i; pairs[2 * np + 1] = vMatches12[i]; np++; }
+    *n_matches = nmatches;
+    return 0;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors — MapPoint.cc:256-321 (== MapLine.cpp:269-330)
+extern "C" int orc_distinctive_descriptors(const uint8_t* desc, const int* group_off, int n_groups, int* best_row) {
+    for (int g = 0; g < n_groups; g++) {
+        const int N = group_off[g + 1] - group_off[g];
+        best_row[g] = -1;
+        if (N <= 0) continue;
+        const uint8_t* d = desc + 32 * (size_t)group_off[g];
+        std::vector<float> Distances((size_t)N * N, 0.f);
+        for (int i = 0; i < N; i++)
+            for (int j = i + 1; j < N; j++) {
+                const int distij = descriptor_distance(d + 32 * (size_t)i, d + 32 * (size_t)j);
+                Distances[(size_t)i * N + j] = (float)distij;
+                Distances[(size_t)j * N + i] = (float)distij;
+            }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            std::vector<int> vDists(Distances.begin() + (size_t)i * N, Distances.begin() + (size_t)(i + 1) * N);
+            std::sort(vDists.begin(), vDists.end());
+            const int median = vDists[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best_row[g] = BestIdx;
+    }
     return 0;
 }

@@ -49,6 +49,11 @@ ORC_API int orc_orb_search_bow(const pl_bow_view* A, const pl_bow_view* B, int m
 ORC_API int orc_line_match_knn_ratio(const uint8_t* ref_desc, int n_ref, const uint8_t* cur_desc, int n_cur, int* match_of_line, int* n_matches);
 ORC_API int orc_line_search_for_triangulation(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, int* pairs, int* n_matches, double* nn_mad, double* nn12_mad);
 ORC_API int orc_line_fuse_candidates(const uint8_t* ml_desc, const uint8_t* valid, int n, const uint8_t* kf_desc, int n_kf, int* tdx, int* n_fused);
+ORC_API int orc_orb_fuse_candidates(const pl_frame_view* K, const pl_posepoint_view* P, const float* ow, float log_scale_factor, const float* inv_level_sigma2, float th, int variant, int* best_idx, int* best_dist, int* n_fused);
+ORC_API int orc_orb_search_by_sim3(const pl_frame_view* K1, const pl_frame_view* K2, const pl_posepoint_view* P1, const pl_posepoint_view* P2, const float* t21, const float* t12, float log_sf1, float log_sf2, float th, int* match12, int* n_found);
+ORC_API int orc_orb_search_for_initialization(const pl_frame_view* F1, const pl_frame_view* F2, float* prev_matched, int window_size, float nn_ratio, int check_orientation, int* matches12, int* n_matches);
+ORC_API int orc_orb_search_for_triangulation(const pl_triang_view* A, const pl_triang_view* B, const float* F12, const float* cw1, const float* kf2_tcw, float fx2, float fy2, float cx2, float cy2, const float* scale_factors2, const float* level_sigma2_2, int n_levels2, int only_stereo, int check_orientation, int* pairs, int* n_matches);
+ORC_API int orc_distinctive_descriptors(const uint8_t* desc, const int* group_off, int n_groups, int* best_row);
 
 /* ---- line extraction (line_oracle.cpp) ---- */
 ORC_API int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t step, int order_mode, float* xyxy, double* width, double* prec, double* nfa, int cap);

@@ -402,6 +402,58 @@ def line_fuse_candidates(ml_desc, valid, kf_desc):
     return tdx[:a.shape[0]], n.value
 
 
+def fuse_candidates(kf_view, pt_view, ow, log_sf, inv_level_sigma2, th, variant=0):
+    bi = np.empty(max(pt_view.n, 1), np.int32)
+    bd = np.empty(max(pt_view.n, 1), np.int32)
+    n = C.c_int(0)
+    o = np.ascontiguousarray(ow, np.float32)
+    sg = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+    lib().orc_orb_fuse_candidates(C.byref(kf_view), C.byref(pt_view), _p(o), C.c_float(log_sf), _p(sg) if sg is not None else None, C.c_float(th),
+                                  C.c_int(variant), _p(bi), _p(bd), C.byref(n))
+    return bi[:pt_view.n], bd[:pt_view.n], n.value
+
+
+def search_by_sim3(kf1, kf2, pts1, pts2, t21, t12, log_sf1, log_sf2, th):
+    t21 = np.ascontiguousarray(t21, np.float32).reshape(-1)[:12].copy()
+    t12 = np.ascontiguousarray(t12, np.float32).reshape(-1)[:12].copy()
+    m = np.empty(max(kf1.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().orc_orb_search_by_sim3(C.byref(kf1), C.byref(kf2), C.byref(pts1), C.byref(pts2), _p(t21), _p(t12), C.c_float(log_sf1), C.c_float(log_sf2),
+                                 C.c_float(th), _p(m), C.byref(n))
+    return m[:kf1.n], n.value
+
+
+def search_for_initialization(f1, f2, prev_matched, window_size, nn_ratio=0.9, check_orientation=True):
+    pm = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m = np.empty(max(f1.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().orc_orb_search_for_initialization(C.byref(f1), C.byref(f2), _p(pm), C.c_int(int(window_size)), C.c_float(nn_ratio),
+                                            C.c_int(int(check_orientation)), _p(m), C.byref(n))
+    return m[:f1.n], n.value, pm
+
+
+def search_for_triangulation(a, b, f12, cw1, kf2_tcw, K2, scale_factors2, level_sigma2_2, only_stereo=False, check_orientation=True):
+    f12 = np.ascontiguousarray(f12, np.float32).reshape(-1)[:9].copy()
+    cw = np.ascontiguousarray(cw1, np.float32).reshape(-1)[:3].copy()
+    t2 = np.ascontiguousarray(kf2_tcw, np.float32).reshape(-1)[:12].copy()
+    sf = np.ascontiguousarray(scale_factors2, np.float32)
+    sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+    pairs = np.empty((max(a.bow.n, 1), 2), np.int32)
+    n = C.c_int(0)
+    lib().orc_orb_search_for_triangulation(C.byref(a), C.byref(b), _p(f12), _p(cw), _p(t2), C.c_float(K2["fx"]), C.c_float(K2["fy"]),
+                                           C.c_float(K2["cx"]), C.c_float(K2["cy"]), _p(sf), _p(sg), C.c_int(len(sf)), C.c_int(int(only_stereo)),
+                                           C.c_int(int(check_orientation)), _p(pairs), C.byref(n))
+    return pairs[:max(n.value, 0)], n.value
+
+
+def distinctive_descriptors(desc, group_off):
+    d = _rows(desc)
+    off = np.ascontiguousarray(group_off, np.int32)
+    best = np.empty(max(len(off) - 1, 1), np.int32)
+    lib().orc_distinctive_descriptors(_p(d), _p(off), C.c_int(len(off) - 1), _p(best))
+    return best[:len(off) - 1]
+
+
 class OracleBackend:
     """CPU-oracle backend for frontend.TrackingFrontEnd (same interface as frontend.GpuBackend)."""
 

@@ -229,3 +229,20 @@ def make_bow_view(angle, desc, valid, feat_vec, keep):
     v.n_nodes = len(ids)
     v.node_id, v.node_off, v.feat_idx = _addr(node_id), _addr(off), _addr(feat_idx)
     return v
+
+
+class TriangView(C.Structure):
+    """pl_triang_view: one key frame of ORBmatcher::SearchForTriangulation (bow view + undistorted keys + mvuRight)."""
+    _fields_ = [("bow", BowView), ("keys_un", C.c_void_p), ("u_right", C.c_void_p)]
+
+
+def make_triang_view(keys_un, desc, u_right, no_mappoint, feat_vec, keep):
+    """no_mappoint[i] = 1 when the key frame holds no map point for feature i (the features offered for triangulation)."""
+    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+    ur = np.ascontiguousarray(u_right, np.float32)
+    ang = np.ascontiguousarray(keys_un["angle"], np.float32)
+    keep += [keys_un, ur]
+    v = TriangView()
+    v.bow = make_bow_view(ang, desc, no_mappoint, feat_vec, keep)
+    v.keys_un, v.u_right = _addr(keys_un), _addr(ur)
+    return v

@@ -463,3 +463,66 @@ class DescriptorMatcher:
         n = C.c_int(0)
         check(N.lib().pl_line_fuse_candidates(self._h, ptr(a), ptr(va), C.c_int(a.shape[0]), ptr(b), C.c_int(b.shape[0]), ptr(tdx), C.byref(n)))
         return tdx[:a.shape[0]], n.value
+
+    # ---- E rows: the remaining ORBmatcher entry points (Fuse, SearchBySim3, SearchForInitialization,
+    #      SearchForTriangulation) and ComputeDistinctiveDescriptors ----
+    def FuseCandidatesBatch(self, kf_views, pt_views, ow, log_scale_factor, inv_level_sigma2, th, variant=0):
+        """ORBmatcher::Fuse(pKF, vpMapPoints, th) (variant 0) / Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (variant 1) for n
+        calls -> [(best_idx per map point (-1 = no fusion), best_dist, n_fused)]."""
+        n = len(kf_views)
+        fa = self._view_array(kf_views, N.FrameView)
+        pa = self._view_array(pt_views, N.PosePointView)
+        ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+        ls = np.ascontiguousarray(log_scale_factor, np.float32).reshape(-1)
+        sig = None if inv_level_sigma2 is None else [np.ascontiguousarray(s_, np.float32) for s_ in inv_level_sigma2]
+        sp = (C.c_void_p * n)(*[s_.ctypes.data for s_ in sig]) if sig is not None else None
+        bi = [np.empty(max(v.n, 1), np.int32) for v in pt_views]
+        bd = [np.empty(max(v.n, 1), np.int32) for v in pt_views]
+        pi = (C.c_void_p * n)(*[o.ctypes.data for o in bi])
+        pd = (C.c_void_p * n)(*[o.ctypes.data for o in bd])
+        cnt = np.zeros(max(n, 1), np.int32)
+        check(N.lib().pl_orb_fuse_candidates_batch(self._h, C.c_int(n), fa, pa, ptr(ow), ptr(ls), sp, C.c_float(th), C.c_int(variant), pi, pd,
+                                                   ptr(cnt)))
+        return [(bi[i][:pt_views[i].n], bd[i][:pt_views[i].n], int(cnt[i])) for i in range(n)]
+
+    def SearchBySim3(self, kf1, kf2, pts1, pts2, t21, t12, log_sf1, log_sf2, th):
+        """ORBmatcher::SearchBySim3 -> (match12 over KF1 features -> KF2 feature or -1, nFound)."""
+        t21 = np.ascontiguousarray(t21, np.float32).reshape(-1)[:12].copy()
+        t12 = np.ascontiguousarray(t12, np.float32).reshape(-1)[:12].copy()
+        m = np.empty(max(kf1.n, 1), np.int32)
+        nf = C.c_int(0)
+        check(N.lib().pl_orb_search_by_sim3(self._h, C.byref(kf1), C.byref(kf2), C.byref(pts1), C.byref(pts2), ptr(t21), ptr(t12),
+                                            C.c_float(log_sf1), C.c_float(log_sf2), C.c_float(th), ptr(m), C.byref(nf)))
+        return m[:kf1.n], nf.value
+
+    def SearchForInitialization(self, f1, f2, prev_matched, window_size, nn_ratio=0.9, check_orientation=True):
+        """ORBmatcher::SearchForInitialization -> (vnMatches12, nmatches, updated vbPrevMatched)."""
+        pm = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+        m = np.empty(max(f1.n, 1), np.int32)
+        nm = C.c_int(0)
+        check(N.lib().pl_orb_search_for_initialization(self._h, C.byref(f1), C.byref(f2), ptr(pm), C.c_int(int(window_size)), C.c_float(nn_ratio),
+                                                       C.c_int(int(check_orientation)), ptr(m), C.byref(nm)))
+        return m[:f1.n], nm.value, pm
+
+    def SearchForTriangulation(self, a, b, f12, cw1, kf2_tcw, K2, scale_factors2, level_sigma2_2, only_stereo=False, check_orientation=True):
+        """ORBmatcher::SearchForTriangulation -> (vMatchedPairs as an (n, 2) array, nmatches)."""
+        f12 = np.ascontiguousarray(f12, np.float32).reshape(-1)[:9].copy()
+        cw = np.ascontiguousarray(cw1, np.float32).reshape(-1)[:3].copy()
+        t2 = np.ascontiguousarray(kf2_tcw, np.float32).reshape(-1)[:12].copy()
+        sf = np.ascontiguousarray(scale_factors2, np.float32)
+        sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+        pairs = np.empty((max(a.bow.n, 1), 2), np.int32)
+        nm = C.c_int(0)
+        check(N.lib().pl_orb_search_for_triangulation(self._h, C.byref(a), C.byref(b), ptr(f12), ptr(cw), ptr(t2), C.c_float(K2["fx"]),
+                                                      C.c_float(K2["fy"]), C.c_float(K2["cx"]), C.c_float(K2["cy"]), ptr(sf), ptr(sg),
+                                                      C.c_int(len(sf)), C.c_int(int(only_stereo)), C.c_int(int(check_orientation)), ptr(pairs),
+                                                      C.byref(nm)))
+        return pairs[:max(nm.value, 0)], nm.value
+
+    def DistinctiveDescriptors(self, desc, group_off):
+        """MapPoint / MapLine::ComputeDistinctiveDescriptors for many map points at once -> best row per group (-1 = empty)."""
+        d = self._rows(desc)
+        off = np.ascontiguousarray(group_off, np.int32)
+        best = np.empty(max(len(off) - 1, 1), np.int32)
+        check(N.lib().pl_distinctive_descriptors(self._h, ptr(d), ptr(off), C.c_int(len(off) - 1), ptr(best)))
+        return best[:len(off) - 1]

@@ -8,6 +8,8 @@
 //   LineMatcher::SearchByProjection(Frame&, KeyFrame*, vector<MapLine*>&) src/LineMatcher.cpp:489-525
 //   LineMatcher::SearchForTriangulation + KeyFrame::lineDescriptorMAD    src/LineMatcher.cpp:1174-1204, src/KeyFrame.cc:773-797
 //   LineMatcher::Fuse (descriptor half of the active branch)            src/LineMatcher.cpp:1296-1330
+//   ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine          src/ORBmatcher.cc:884-1095, :205-232 (E4)
+//   MapPoint / MapLine::ComputeDistinctiveDescriptors                   src/MapPoint.cc:256-321, src/MapLine.cpp:269-330 (E5)
 //
 // SearchByBoW: the merge-join of the two FeatureVectors (<= ~100 level-4 nodes per image) is done on the host while the
 // inputs are packed; it yields, in the reference's processing order, one query per valid feature of side A inside a
@@ -239,6 +241,190 @@ __global__ void __launch_bounds__(256) k_fuse_rule(const int* __restrict__ idx, 
     if (t >= 0) atomicAdd(n_fused, 1);
 }
 
+
+// ---- E4: SearchForTriangulation ----
+struct TriDev {
+    BowDev B;                       // queries / candidates of the merge-join (q_idx = idx1, cand = idx2)
+    const pl_keypoint *keysA, *keysB;
+    const float *urA, *urB;
+    float f12[9], ex, ey;
+    float sf2[kMaxLevels], sigma2[kMaxLevels];
+};
+
+// distances + the gates that do not depend on earlier matches (ORBmatcher.cc:978-1013): TH_LOW, the epipole distance for
+// monocular pairs, CheckDistEpipolarLine.  A candidate that fails is given the distance 511.
+__global__ void __launch_bounds__(256) k_triang_dist(const TriDev* __restrict__ TD) {
+    const TriDev& T = TD[0];
+    const BowDev& D = T.B;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= D.nq) return;
+    const int a = D.q_idx[q];
+    const uint4 a0 = D.descA[2 * (size_t)a], a1 = D.descA[2 * (size_t)a + 1];
+    const pl_keypoint kp1 = T.keysA[a];
+    const bool stereo1 = T.urA[a] >= 0;
+    // CheckDistEpipolarLine (:209-211): line l = x1' F12
+    const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.f12[0]), __fmul_rn(kp1.y, T.f12[3])), T.f12[6]);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.f12[1]), __fmul_rn(kp1.y, T.f12[4])), T.f12[7]);
+    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.f12[2]), __fmul_rn(kp1.y, T.f12[5])), T.f12[8]);
+    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    for (int k = D.q_off[q] + lane; k < D.q_off[q + 1]; k += 32) {
+        const unsigned b = D.cand[k];
+        int dist = hamming256(a0, a1, D.descB[2 * (size_t)b], D.descB[2 * (size_t)b + 1]);
+        if (dist <= kBowThLow) {
+            const pl_keypoint kp2 = T.keysB[b];
+            bool ok = true;
+            if (!stereo1 && !(T.urB[b] >= 0)) {
+                const float distex = __fsub_rn(T.ex, kp2.x), distey = __fsub_rn(T.ey, kp2.y);
+                if (__fadd_rn(__fmul_rn(distex, distex), __fmul_rn(distey, distey)) < __fmul_rn(100.f, T.sf2[kp2.octave])) ok = false;
+            }
+            if (ok) {
+                const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+                if (den == 0) ok = false;
+                else {
+                    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                    ok = (double)dsqr < __dmul_rn(3.84, (double)T.sigma2[kp2.octave]);
+                }
+            }
+            if (!ok) dist = 511;
+        } else {
+            dist = 511;
+        }
+        D.cand[k] = b | ((unsigned)dist << 16);
+    }
+}
+
+// the ordered part (:956-1046): per query the LAST candidate of minimum distance among those that passed the gates and are
+// not matched yet (`dist > bestDist` skips, so an equal distance replaces); vbMatched2 in query order; rotation histogram
+__global__ void __launch_bounds__(32) k_triang_resolve(const TriDev* __restrict__ TD, int check_orientation) {
+    extern __shared__ uint8_t s_matched[];
+    __shared__ int s_hist[kBowHisto];
+    const BowDev& D = TD[0].B;
+    const int lane = threadIdx.x;
+    for (int i = lane; i < D.nB; i += 32) s_matched[i] = 0;
+    for (int i = lane; i < D.n_out; i += 32) D.match[i] = -1;
+    if (lane < kBowHisto) s_hist[lane] = 0;
+    __syncwarp();
+    const float factor = kBowHisto / 360.0f;
+    int nmatches = 0, nrec = 0;
+    for (int q = 0; q < D.nq; q++) {
+        const int o0 = D.q_off[q], c = D.q_off[q + 1] - o0;
+        if (c == 0) continue;
+        const unsigned int* cd = D.cand + o0;
+        unsigned best = 0xFFFFFFFFu;
+        for (int base = 0; base < c; base += 32) {
+            unsigned key = 0xFFFFFFFFu;
+            const int pos = base + lane;
+            if (pos < c) {
+                const unsigned e = cd[pos];
+                if ((e >> 16) <= (unsigned)kBowThLow && !s_matched[e & 0xFFFFu]) key = ((e >> 16) << 16) | (unsigned)(0xFFFF - pos);
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
+            best = min(best, key);
+        }
+        if (best == 0xFFFFFFFFu) continue;
+        const int pb = 0xFFFF - (int)(best & 0xFFFFu);
+        const int idxB = (int)(cd[pb] & 0xFFFFu), idxA = D.q_idx[q];
+        if (lane == 0) {
+            s_matched[idxB] = 1;
+            D.match[idxA] = idxB;
+        }
+        if (check_orientation) {
+            float rot = __fsub_rn(D.angA[idxA], D.angB[idxB]);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == kBowHisto) bin = 0;
+            if (lane == 0) {
+                D.rec[2 * nrec] = idxA;
+                D.rec[2 * nrec + 1] = bin;
+                s_hist[bin]++;
+            }
+            nrec++;
+        }
+        nmatches++;
+        __syncwarp();
+    }
+    if (check_orientation) {
+        __syncwarp();
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < kBowHisto; i++) {
+            const int sz = s_hist[i];
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+        int removed = 0;
+        for (int k = lane; k < nrec; k += 32) {
+            const int bin = D.rec[2 * k + 1];
+            if (bin != ind1 && bin != ind2 && bin != ind3) {
+                D.match[D.rec[2 * k]] = -1;
+                removed++;
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, sft);
+        nmatches -= removed;
+    }
+    if (lane == 0) D.out[0] = nmatches;
+}
+
+// ---- E5: ComputeDistinctiveDescriptors ----
+// one CTA per map point / map line; a warp per row: the N distances of the row go into a 257-bin histogram, the median
+// (sorted[int(0.5*(N-1))]) is read off its prefix sums; the row with the least median wins, first one on ties
+constexpr int kDistWarps = 4, kDistBins = 288;  // 257 bins rounded up to 9 per lane
+__global__ void __launch_bounds__(kDistWarps * 32) k_distinctive(const uint4* __restrict__ desc, const int* __restrict__ group_off,
+                                                                 int* __restrict__ best_row) {
+    __shared__ int s_hist[kDistWarps][kDistBins];
+    __shared__ unsigned s_best[kDistWarps];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int o = group_off[g], N = group_off[g + 1] - o;
+    const int kth = (int)(0.5 * (double)(N - 1));
+    unsigned best = 0xFFFFFFFFu;
+    for (int i = warp; i < N; i += kDistWarps) {
+        for (int b = lane; b < kDistBins; b += 32) s_hist[warp][b] = 0;
+        __syncwarp();
+        const uint4 a0 = desc[2 * (size_t)(o + i)], a1 = desc[2 * (size_t)(o + i) + 1];
+        for (int j = lane; j < N; j += 32) {
+            const int d = j == i ? 0 : hamming256(a0, a1, desc[2 * (size_t)(o + j)], desc[2 * (size_t)(o + j) + 1]);
+            atomicAdd(&s_hist[warp][d], 1);
+        }
+        __syncwarp();
+        // lane owns bins [9*lane, 9*lane+9)
+        int local = 0;
+#pragma unroll
+        for (int b = 0; b < 9; b++) local += s_hist[warp][9 * lane + b];
+        int incl = local;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, sft);
+            if (lane >= sft) incl += t;
+        }
+        const int excl = incl - local;
+        int median = -1;
+        if (kth >= excl && kth < incl) {
+            int acc = excl;
+#pragma unroll
+            for (int b = 0; b < 9; b++) {
+                acc += s_hist[warp][9 * lane + b];
+                if (median < 0 && kth < acc) median = 9 * lane + b;
+            }
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, median >= 0);
+        median = __shfl_sync(0xffffffffu, median, __ffs(who) - 1);
+        best = min(best, ((unsigned)median << 16) | (unsigned)i);
+        __syncwarp();
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned b = s_best[0];
+        for (int w = 1; w < kDistWarps; w++) b = min(b, s_best[w]);
+        best_row[g] = N > 0 ? (int)(b & 0xFFFFu) : -1;
+    }
+}
+
 }  // namespace pl
 
 using namespace pl;
@@ -446,6 +632,144 @@ PL_API int pl_line_fuse_candidates(pl_match* h, const uint8_t* ml_desc, const ui
     PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
     memcpy(tdx, tmp.data(), (size_t)n * 4);
     *n_fused = tmp[n];
+    return PL_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+PL_API int pl_orb_search_for_triangulation(pl_match* h, const pl_triang_view* a, const pl_triang_view* b, const float f12[9], const float cw1[3],
+                                           const float kf2_tcw[12], float fx2, float fy2, float cx2, float cy2, const float* scale_factors2,
+                                           const float* level_sigma2_2, int n_levels2, int only_stereo, int check_orientation, int* pairs,
+                                           int* n_matches) {
+    PL_CHECK_ARG(h && a && b && f12 && cw1 && kf2_tcw && scale_factors2 && level_sigma2_2 && n_matches && n_levels2 >= 1 && n_levels2 <= kMaxLevels);
+    const pl_bow_view &A = a->bow, &B = b->bow;
+    PL_CHECK_ARG(A.n >= 0 && B.n >= 0 && A.n <= 65535 && B.n <= 65535 && A.n_nodes >= 0 && B.n_nodes >= 0);
+    PL_CHECK_ARG((A.n == 0 || (A.desc && A.angle && a->keys_un && a->u_right && pairs)) && (B.n == 0 || (B.desc && B.angle && b->keys_un && b->u_right)));
+    PL_CHECK_ARG((A.n_nodes == 0 || (A.node_id && A.node_off && A.feat_idx)) && (B.n_nodes == 0 || (B.node_id && B.node_off && B.feat_idx)));
+    for (int k = 0; k + 1 < A.n_nodes; k++) PL_CHECK_ARG(A.node_id[k] < A.node_id[k + 1]);
+    for (int k = 0; k + 1 < B.n_nodes; k++) PL_CHECK_ARG(B.node_id[k] < B.node_id[k + 1]);
+    for (int i = 0; i < B.n; i++) PL_CHECK_ARG(b->keys_un[i].octave >= 0 && b->keys_un[i].octave < n_levels2);
+    *n_matches = 0;
+    // merge-join (:925-1061) with the gates that only depend on one side: pMP1 / pMP2, bOnlyStereo
+    std::vector<int> q_idx, q_off(1, 0);
+    std::vector<unsigned> cand;
+    int ka = 0, kb = 0;
+    while (ka < A.n_nodes && kb < B.n_nodes) {
+        if (A.node_id[ka] == B.node_id[kb]) {
+            for (int pa = A.node_off[ka]; pa < A.node_off[ka + 1]; pa++) {
+                const unsigned ia = A.feat_idx[pa];
+                PL_CHECK_ARG(ia < (unsigned)A.n);
+                if (A.valid && !A.valid[ia]) continue;
+                if (only_stereo && !(a->u_right[ia] >= 0)) continue;
+                for (int pb = B.node_off[kb]; pb < B.node_off[kb + 1]; pb++) {
+                    const unsigned ib = B.feat_idx[pb];
+                    PL_CHECK_ARG(ib < (unsigned)B.n);
+                    if (B.valid && !B.valid[ib]) continue;
+                    if (only_stereo && !(b->u_right[ib] >= 0)) continue;
+                    cand.push_back(ib);
+                }
+                q_idx.push_back((int)ia);
+                q_off.push_back((int)cand.size());
+            }
+            ka++;
+            kb++;
+        } else if (A.node_id[ka] < B.node_id[kb]) {
+            ka = (int)(std::lower_bound(A.node_id + ka, A.node_id + A.n_nodes, B.node_id[kb]) - A.node_id);
+        } else {
+            kb = (int)(std::lower_bound(B.node_id + kb, B.node_id + B.n_nodes, A.node_id[ka]) - B.node_id);
+        }
+    }
+    const size_t nq = q_idx.size();
+    if (A.n == 0) return PL_OK;
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    const size_t bytes = padb(sizeof(TriDev)) + padb(nq * 4) + padb((nq + 1) * 4) + padb(cand.size() * 4) + padb((size_t)A.n * 32) + padb((size_t)B.n * 32) +
+                         (padb((size_t)A.n * 4) + padb((size_t)B.n * 4)) * 2 + padb((size_t)A.n * sizeof(pl_keypoint)) +
+                         padb((size_t)B.n * sizeof(pl_keypoint)) + padb((size_t)A.n * 4) + padb(nq * 8 + 8) + padb(8);
+    int rc = h->in.reserve(bytes);
+    if (rc != PL_OK) return rc;
+    TriDev T;
+    memset(&T, 0, sizeof(T));
+    BowDev& D = T.B;
+    int *h_match, *h_out;
+    D.nq = (int)nq; D.nA = A.n; D.nB = B.n; D.n_out = A.n;
+    D.q_idx = h->in.put(q_idx.data(), nq);
+    D.q_off = h->in.put(q_off.data(), q_off.size());
+    D.cand = const_cast<unsigned int*>(h->in.put(cand.data(), cand.size()));
+    D.descA = (const uint4*)h->in.put(A.desc, (size_t)A.n * 32);
+    D.descB = (const uint4*)h->in.put(B.desc, (size_t)B.n * 32);
+    D.angA = h->in.put(A.angle, (size_t)A.n);
+    D.angB = h->in.put(B.angle, (size_t)B.n);
+    T.keysA = h->in.put(a->keys_un, (size_t)A.n);
+    T.keysB = h->in.put(b->keys_un, (size_t)B.n);
+    T.urA = h->in.put(a->u_right, (size_t)A.n);
+    T.urB = h->in.put(b->u_right, (size_t)B.n);
+    D.match = h->in.out<int>((size_t)A.n, &h_match);
+    D.rec = h->in.out<int>(nq * 2 + 2);
+    D.out = h->in.out<int>(2, &h_out);
+    for (int k = 0; k < 9; k++) T.f12[k] = f12[k];
+    for (int k = 0; k < n_levels2; k++) { T.sf2[k] = scale_factors2[k]; T.sigma2[k] = level_sigma2_2[k]; }
+    // the epipole (:897-903): C2 = R2w*Cw + t2w as one cv::Mat gemm (double accumulation, rounded once); the float
+    // expressions that follow are kept un-contracted (volatile: the host compiler must not fuse them)
+    float C2[3];
+    for (int r = 0; r < 3; r++) {
+        double sacc = 0;
+        for (int k = 0; k < 3; k++) sacc += (double)kf2_tcw[4 * r + k] * (double)cw1[k];
+        C2[r] = (float)(sacc * 1.0 + (double)kf2_tcw[4 * r + 3] * 1.0);
+    }
+    {
+        volatile float invz = 1.0f / C2[2];
+        volatile float tx = fx2 * C2[0], ty = fy2 * C2[1];
+        volatile float txz = tx * invz, tyz = ty * invz;
+        T.ex = txz + cx2;
+        T.ey = tyz + cy2;
+    }
+    const TriDev* d_t = h->in.put(&T, 1);
+    cudaStream_t st = h->stream;
+    if ((rc = h->in.upload(st)) != PL_OK) return rc;
+    if (nq > 0) {
+        k_triang_dist<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(d_t);
+        h->last_launches++;
+    }
+    const size_t sm = (size_t)std::max(B.n, 1);
+    if (sm > 48 * 1024) PL_CUDA_TRY(cudaFuncSetAttribute(k_triang_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_triang_resolve<<<1, 32, sm, st>>>(d_t, check_orientation);
+    h->last_launches++;
+    PL_CUDA_TRY(cudaGetLastError());
+    PL_CUDA_TRY(cudaMemcpyAsync(h->in.h, h->in.d, h->in.cur, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    int np = 0;
+    for (int i = 0; i < A.n; i++)
+        if (h_match[i] >= 0) { pairs[2 * np] = i; pairs[2 * np + 1] = h_match[i]; np++; }
+    *n_matches = h_out[0];
+    return PL_OK;
+}
+
+PL_API int pl_distinctive_descriptors(pl_match* h, const uint8_t* desc, const int* group_off, int n_groups, int* best_row) {
+    PL_CHECK_ARG(h && n_groups >= 0 && (n_groups == 0 || (group_off && best_row)));
+    if (n_groups == 0) return PL_OK;
+    PL_CHECK_ARG(group_off[0] == 0);
+    for (int g = 0; g < n_groups; g++) PL_CHECK_ARG(group_off[g + 1] >= group_off[g] && group_off[g + 1] - group_off[g] <= 65535);
+    const size_t rows = (size_t)group_off[n_groups];
+    PL_CHECK_ARG(rows == 0 || desc);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    int rc = h->in.reserve(padb(rows * 32) + padb((size_t)(n_groups + 1) * 4) + padb((size_t)n_groups * 4));
+    if (rc != PL_OK) return rc;
+    const uint4* d_desc = (const uint4*)h->in.put(desc, rows * 32);
+    const int* d_off = h->in.put(group_off, (size_t)n_groups + 1);
+    int* h_best;
+    int* d_best = h->in.out<int>((size_t)n_groups, &h_best);
+    cudaStream_t st = h->stream;
+    if ((rc = h->in.upload(st)) != PL_OK) return rc;
+    k_distinctive<<<n_groups, kDistWarps * 32, 0, st>>>(d_desc, d_off, d_best);
+    h->last_launches++;
+    PL_CUDA_TRY(cudaGetLastError());
+    PL_CUDA_TRY(cudaMemcpyAsync(h_best, d_best, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(best_row, h_best, (size_t)n_groups * 4);
     return PL_OK;
 }
 

@@ -48,6 +48,10 @@ struct SearchDev {
     const float *min_inv, *max_inv, *max_raw, *normal;  // C4 / C5: distance invariance, mfMaxDistance, viewing normal (C5)
     float ow[3], log_sf;                                  // C4 / C5: camera centre, mfLogScaleFactor
     int pt_base, feat_base, sort_base, n2;  // offsets into the batch-wide scratch arrays
+    // E rows (Fuse / SearchBySim3): second transform applied after F.tcw (sR21 | t21), chi-square gates of Fuse
+    float t2[12];
+    float inv_sigma2[kMaxLevels];
+    int use_t2, use_chi2;
 };
 
 // Frame::AssignFeaturesToGrid (Frame.cc:265-287): features sorted by (cell, index); cell = posX*48 + posY with
@@ -158,7 +162,7 @@ __device__ __forceinline__ float mat_row(const float* T, int r, float X, float Y
 
 // phase A, run twice: FILL == false counts the candidates of every point (cand_n), FILL == true writes them at the
 // CSR offsets.  MODE 0 = C3 (ORBmatcher.cc:1746-1830 without the claim check), 1 = C2 (ORBmatcher.cc:84-149),
-// 2 = C4 (ORBmatcher.cc:1909-1960), 3 = C5 (ORBmatcher.cc:451-531).
+// 2 = C4 (ORBmatcher.cc:1909-1960), 3 = C5 (ORBmatcher.cc:451-531), 4 = SearchForInitialization (ORBmatcher.cc:598-606).
 template <int MODE, bool FILL>
 __global__ void __launch_bounds__(256) k_candidates(const SearchDev* __restrict__ SD, float th, const int* __restrict__ sorted_idx,
                                                     const int* __restrict__ cell_start, int* __restrict__ cand_n,
@@ -239,6 +243,9 @@ __global__ void __launch_bounds__(256) k_candidates(const SearchDev* __restrict_
                     count = gather_candidates(F, sidx, cst, u, v, radius, lvl - 1, MODE == 2 ? lvl + 1 : lvl, 0.f, __int_as_float(0x7f800000), q0, q1, out);
                 }
             }
+        } else if (MODE == 4) {
+            // SearchForInitialization (ORBmatcher.cc:598-606): window around vbPrevMatched[i1], level 0 only; th = windowSize
+            count = gather_candidates(F, sidx, cst, S.proj_x[i], S.proj_y[i], th, 0, 0, 0.f, __int_as_float(0x7f800000), q0, q1, out);
         } else {
             const int lvl = S.level[i];
             float r = S.view_cos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos (ORBmatcher.cc:186-193)
@@ -532,6 +539,267 @@ __global__ void __launch_bounds__(kResThreads) k_local_points_resolve(const Sear
     }
     __syncthreads();
     if (tid == 0) { out[2 * blockIdx.x] = s_nm; out[2 * blockIdx.x + 1] = s_overflow; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// E rows: searches without claims between points (Fuse, SearchBySim3) and SearchForInitialization's replay
+// ---------------------------------------------------------------------------------------------------------------
+// KeyFrame::GetFeaturesInArea (KeyFrame.cc:642-681) + the level gate [lvl-1, lvl] + (optionally) the chi-square gates of
+// ORBmatcher.cc:1217-1235, reduced to the first minimum distance in visiting order.  One warp.
+// Returns dist << 36 | ordinal << 16 | idx  (all ones = no candidate).
+__device__ unsigned long long gather_best(const FrameDev& F, const int* __restrict__ sorted_idx, const int* __restrict__ cell_start, float x,
+                                          float y, float r, int lvl, float ur, const float* inv_sigma2, uint4 q0, uint4 q1) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long none = ~0ull;
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, F.min_x), r), F.inv_w)));
+    if (nMinCellX >= kGridCols) return none;
+    const int nMaxCellX = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, F.min_x), r), F.inv_w)));
+    if (nMaxCellX < 0) return none;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, F.min_y), r), F.inv_h)));
+    if (nMinCellY >= kGridRows) return none;
+    const int nMaxCellY = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, F.min_y), r), F.inv_h)));
+    if (nMaxCellY < 0) return none;
+    unsigned long long best = none;
+    unsigned ordinal = 0;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        const int beg = cell_start[ix * kGridRows + nMinCellY], end = cell_start[ix * kGridRows + nMaxCellY + 1];
+        for (int base = beg; base < end; base += 32, ordinal += 32) {
+            const int k = base + lane;
+            if (k >= end) continue;
+            const int idx = sorted_idx[k];
+            const pl_keypoint kp = F.keys[idx];
+            const float distx = __fsub_rn(kp.x, x), disty = __fsub_rn(kp.y, y);
+            if (!(fabsf(distx) < r && fabsf(disty) < r)) continue;
+            if (kp.octave < lvl - 1 || kp.octave > lvl) continue;
+            if (inv_sigma2) {
+                const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                const float kpr = F.u_right[idx];
+                double lim = 5.99;
+                if (kpr >= 0) {
+                    const float er = __fsub_rn(ur, kpr);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    lim = 7.8;
+                }
+                if ((double)__fmul_rn(e2, inv_sigma2[kp.octave]) > lim) continue;
+            }
+            const unsigned dist = (unsigned)hamming256(q0, q1, F.desc[2 * (size_t)idx], F.desc[2 * (size_t)idx + 1]);
+            const unsigned long long key = ((unsigned long long)dist << 36) | ((unsigned long long)(ordinal + lane) << 16) | (unsigned)idx;
+            best = key < best ? key : best;
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, sft);
+        best = o < best ? o : best;
+    }
+    return best;
+}
+
+// VARIANT 0 = Fuse(pKF, vpMapPoints, th) ORBmatcher.cc:1124-1249; 1 = Fuse(pKF, Scw, ...) :1314-1404;
+// 2 = one direction of SearchBySim3 :1472-1546 / :1549-1617.  One warp per point, no interaction between points.
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_point_best(const SearchDev* __restrict__ SD, float th, int th_dist, const int* __restrict__ sorted_idx,
+                                                    const int* __restrict__ cell_start, int* __restrict__ best_idx, int* __restrict__ best_dist,
+                                                    int* __restrict__ hits) {
+    const SearchDev& S = SD[blockIdx.y];
+    const FrameDev& F = S.F;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= S.np) return;
+    const int* sidx = sorted_idx + S.sort_base;
+    const int* cst = cell_start + (size_t)blockIdx.y * (kGridCells + 1);
+    unsigned long long best = ~0ull;
+    if (S.valid[i]) {
+        const float X = S.world_pos[3 * (size_t)i], Y = S.world_pos[3 * (size_t)i + 1], Z = S.world_pos[3 * (size_t)i + 2];
+        float xc = mat_row(F.tcw, 0, X, Y, Z), yc = mat_row(F.tcw, 1, X, Y, Z), zc = mat_row(F.tcw, 2, X, Y, Z);
+        if (VARIANT == 2) {
+            const float x2 = mat_row(S.t2, 0, xc, yc, zc), y2 = mat_row(S.t2, 1, xc, yc, zc), z2 = mat_row(S.t2, 2, xc, yc, zc);
+            xc = x2; yc = y2; zc = z2;
+        }
+        if (!(zc < 0.0f)) {
+            const float invz = VARIANT == 0 ? __fdiv_rn(1.0f, zc) : (float)(1.0 / (double)zc);
+            const float u = __fadd_rn(__fmul_rn(F.fx, __fmul_rn(xc, invz)), F.cx);
+            const float v = __fadd_rn(__fmul_rn(F.fy, __fmul_rn(yc, invz)), F.cy);
+            if (u >= F.min_x && u < F.max_x && v >= F.min_y && v < F.max_y) {  // KeyFrame::IsInImage
+                const float ur = __fsub_rn(u, __fmul_rn(F.bf, invz));
+                float px, py, pz;
+                if (VARIANT == 2) { px = xc; py = yc; pz = zc; }  // cv::norm(p3Dc2) (:1503)
+                else { px = __fsub_rn(X, S.ow[0]); py = __fsub_rn(Y, S.ow[1]); pz = __fsub_rn(Z, S.ow[2]); }
+                double ss = __dmul_rn((double)px, (double)px);
+                ss = __dadd_rn(ss, __dmul_rn((double)py, (double)py));
+                ss = __dadd_rn(ss, __dmul_rn((double)pz, (double)pz));
+                const float dist3D = (float)sqrt(ss);
+                bool ok = !(dist3D < S.min_inv[i] || dist3D > S.max_inv[i]);
+                if (ok && VARIANT != 2) {
+                    const float* nrm = S.normal + 3 * (size_t)i;
+                    double dot = __dmul_rn((double)px, (double)nrm[0]);
+                    dot = __dadd_rn(dot, __dmul_rn((double)py, (double)nrm[1]));
+                    dot = __dadd_rn(dot, __dmul_rn((double)pz, (double)nrm[2]));
+                    ok = !(dot < __dmul_rn(0.5, (double)dist3D));
+                }
+                if (ok) {
+                    const float ratio = __fdiv_rn(S.max_raw[i], dist3D);  // MapPoint::PredictScale (MapPoint.cc:397-431)
+                    int lvl = (int)ceilf(__fdiv_rn(glibc_logf(ratio), S.log_sf));
+                    if (lvl < 0) lvl = 0;
+                    else if (lvl >= F.n_levels) lvl = F.n_levels - 1;
+                    const float radius = __fmul_rn(th, F.sf[lvl]);
+                    const uint4 q0 = S.pdesc[2 * (size_t)i], q1 = S.pdesc[2 * (size_t)i + 1];
+                    best = gather_best(F, sidx, cst, u, v, radius, lvl, ur, (VARIANT == 0 && S.use_chi2) ? S.inv_sigma2 : nullptr, q0, q1);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        const int bd = best == ~0ull ? 256 : (int)(best >> 36);
+        const bool hit = bd <= th_dist;
+        best_idx[S.pt_base + i] = hit ? (int)(best & 0xFFFFu) : -1;
+        best_dist[S.pt_base + i] = bd;
+        if (hit) atomicAdd(&hits[blockIdx.y], 1);
+    }
+}
+
+// SearchBySim3's agreement step (ORBmatcher.cc:1620-1647): vnMatch1 / vnMatch2 are the two k_point_best results
+__global__ void __launch_bounds__(256) k_sim3_agree(const int* __restrict__ m1, int n1, const int* __restrict__ m2, int n2, int* __restrict__ match12,
+                                                    int* __restrict__ n_found) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (i1 < n1) {
+        const int idx2 = m1[i1];
+        hit = idx2 >= 0 && idx2 < n2 && m2[idx2] == i1;
+        match12[i1] = hit ? idx2 : -1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_found, __popc(m));
+}
+
+// SearchForInitialization, phase B (ORBmatcher.cc:609-708): points (features of F1) in order; a feature of F2 that already
+// has a match is only offered at a strictly smaller distance (vMatchedDistance, :626), taking it un-matches its previous
+// owner (:650-654).  Best / second best in closed form as in k_local_points_resolve.
+constexpr int kInitMaxFeat = 20000;
+__global__ void __launch_bounds__(kResThreads) k_init_resolve(const SearchDev* __restrict__ SD, float nn_ratio, int check_orientation,
+                                                              const unsigned int* __restrict__ cand, const int* __restrict__ cand_n,
+                                                              const int* __restrict__ cand_off, const int* __restrict__ totals,
+                                                              const pl_keypoint* __restrict__ keys1, int* __restrict__ match12,
+                                                              int* __restrict__ rec, float* __restrict__ prev_matched, int* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ int s_hist[kHistoLen];
+    __shared__ int s_p1, s_overflow, s_nm, s_nrec;
+    const SearchDev& S = SD[0];
+    const FrameDev& F2 = S.F;
+    unsigned int* s_cand = (unsigned int*)s_raw;
+    int* s_m21 = (int*)(s_raw + (size_t)kResChunkCand * 4);
+    unsigned short* s_mdist = (unsigned short*)(s_m21 + F2.n);
+    const int* off = cand_off;
+    const int* cnt = cand_n;
+    const int total = totals[0];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < F2.n; i += kResThreads) { s_m21[i] = -1; s_mdist[i] = 0xFFFFu; }
+    for (int i = tid; i < S.np; i += kResThreads) match12[i] = -1;
+    if (tid < kHistoLen) s_hist[tid] = 0;
+    if (tid == 0) { s_overflow = 0; s_nm = 0; s_nrec = 0; }
+    const float factor = kHistoLen / 360.0f;
+    int p0 = 0;
+    while (p0 < S.np) {
+        int p1 = resolve_load_chunk(s_cand, cand, off, cnt, p0, S.np, total, &s_p1, &s_overflow);
+        if (p1 & (1 << 30)) { p0 = p1 & ~(1 << 30); continue; }
+        if (warp == 0) {
+            int nmatches = s_nm, nrec = s_nrec;
+            const int o0 = off[p0];
+            for (int i1 = p0; i1 < p1; i1++) {
+                const int c = cnt[i1];
+                if (c == 0) continue;
+                const unsigned int* cd = s_cand + (off[i1] - o0);
+                unsigned best = 0xFFFFFFFFu;
+                for (int base = 0; base < c; base += 32) {
+                    unsigned key = 0xFFFFFFFFu;
+                    if (base + lane < c) {
+                        const unsigned e = cd[base + lane];
+                        if ((unsigned)s_mdist[e & 0xFFFFu] > (e >> 16)) key = ((e >> 16) << 16) | (unsigned)(base + lane);
+                    }
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
+                    best = min(best, key);
+                }
+                if (best == 0xFFFFFFFFu) continue;
+                const int pb = (int)(best & 0xFFFFu), bestDist = (int)(best >> 16);
+                if (bestDist > kThLow) continue;
+                unsigned second = 0xFFFFFFFFu;
+                for (int base = 0; base < c; base += 32) {
+                    unsigned key = 0xFFFFFFFFu;
+                    const int pos = base + lane;
+                    if (pos < c && pos != pb) {
+                        const unsigned e = cd[pos];
+                        if ((unsigned)s_mdist[e & 0xFFFFu] > (e >> 16)) key = e >> 16;
+                    }
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
+                    second = min(second, key);
+                }
+                const float d2 = second == 0xFFFFFFFFu ? 2147483648.0f : (float)second;  // (float)INT_MAX
+                if (!((float)bestDist < __fmul_rn(d2, nn_ratio))) continue;
+                const int bestIdx2 = (int)(cd[pb] & 0xFFFFu);
+                const int prev = s_m21[bestIdx2];
+                if (prev >= 0) nmatches--;
+                __syncwarp();
+                if (lane == 0) {
+                    if (prev >= 0) match12[prev] = -1;
+                    match12[i1] = bestIdx2;
+                    s_m21[bestIdx2] = i1;
+                    s_mdist[bestIdx2] = (unsigned short)bestDist;
+                }
+                nmatches++;
+                if (check_orientation) {
+                    float rot = __fsub_rn(keys1[i1].angle, F2.keys[bestIdx2].angle);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, factor));
+                    if (bin == kHistoLen) bin = 0;
+                    if (lane == 0) {
+                        rec[2 * nrec] = i1;
+                        rec[2 * nrec + 1] = bin;
+                        s_hist[bin]++;
+                    }
+                    nrec++;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { s_nm = nmatches; s_nrec = nrec; }
+        }
+        p0 = p1;
+    }
+    __threadfence_block();
+    __syncthreads();
+    int nmatches = s_nm;
+    const int nrec = s_nrec;
+    if (warp == 0 && check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < kHistoLen; i++) {
+            const int sz = s_hist[i];
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+        int removed = 0;
+        for (int k = lane; k < nrec; k += 32) {
+            const int bin = rec[2 * k + 1], idx1 = rec[2 * k];
+            if (bin != ind1 && bin != ind2 && bin != ind3 && match12[idx1] >= 0) {  // a point is recorded at most once
+                match12[idx1] = -1;
+                removed++;
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, sft);
+        nmatches -= removed;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // :711-714 — vbPrevMatched follows the surviving matches
+    for (int i = tid; i < S.np; i += kResThreads) {
+        const int m = match12[i];
+        if (m >= 0) { prev_matched[2 * i] = F2.keys[m].x; prev_matched[2 * i + 1] = F2.keys[m].y; }
+    }
+    if (tid == 0) { out[0] = nmatches; out[1] = s_overflow; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1269,4 +1537,267 @@ PL_API int pl_line_match_pairs(pl_match* h, const pl_keyline* proj, const uint8_
     *used_relaxed = res[1];
     return PL_OK;
 }
+}  // extern "C"
+
+// ---- E rows: Fuse / SearchBySim3 / SearchForInitialization ----
+namespace {
+int check_posepoints(const pl_posepoint_view& P, bool need_normal) {
+    PL_CHECK_ARG(P.n >= 0 && (P.n == 0 || (P.valid && P.world_pos && P.desc && P.min_dist_inv && P.max_dist_inv && P.max_dist)));
+    PL_CHECK_ARG(P.n == 0 || !need_normal || P.normal != nullptr);
+    return PL_OK;
+}
+size_t posepoint_bytes(const pl_posepoint_view& P) {
+    return padb((size_t)P.n) + padb((size_t)P.n * 12) * 2 + padb((size_t)P.n * 32) + padb((size_t)P.n * 4) * 3;
+}
+void put_posepoints(PlStage& st, const pl_posepoint_view& P, SearchDev& S, bool with_normal) {
+    S.np = P.n;
+    S.valid = st.put(P.valid, (size_t)P.n);
+    S.world_pos = st.put(P.world_pos, (size_t)P.n * 3);
+    S.pdesc = (const uint4*)st.put(P.desc, (size_t)P.n * 32);
+    S.min_inv = st.put(P.min_dist_inv, (size_t)P.n);
+    S.max_inv = st.put(P.max_dist_inv, (size_t)P.n);
+    S.max_raw = st.put(P.max_dist, (size_t)P.n);
+    S.normal = with_normal ? st.put(P.normal, (size_t)P.n * 3) : nullptr;
+}
+struct IndepLayout { int total_pts = 0, total_n2 = 0, max_n2 = 1, max_np = 0; };
+void place(SearchDev& S, int nfeat, IndepLayout& L) {
+    int n2 = 1;
+    while (n2 < std::max(nfeat, 1)) n2 <<= 1;
+    S.n2 = n2;
+    S.pt_base = L.total_pts; S.feat_base = 0; S.sort_base = L.total_n2;
+    L.total_pts += S.np; L.total_n2 += n2;
+    L.max_n2 = std::max(L.max_n2, n2); L.max_np = std::max(L.max_np, S.np);
+}
+// grid + k_point_best for n packed instances; results stay on the device (best_idx / best_dist / hits in scratch 12 / 13 / 14)
+template <int VARIANT>
+int run_point_best(pl_match* h, const SearchDev* d_sd, int n, const IndepLayout& L, float th, int th_dist, int** d_idx, int** d_dist, int** d_hits) {
+    cudaStream_t st = h->stream;
+    int rc;
+    void* p;
+    int *sorted_idx, *cell_start;
+    if ((rc = match_scratch(h, 6, (size_t)std::max(L.total_n2, 1) * 4, &p)) != PL_OK) return rc; sorted_idx = (int*)p;
+    if ((rc = match_scratch(h, 7, (size_t)n * (kGridCells + 1) * 4, &p)) != PL_OK) return rc; cell_start = (int*)p;
+    if ((rc = match_scratch(h, 12, (size_t)std::max(L.total_pts, 1) * 4, &p)) != PL_OK) return rc; *d_idx = (int*)p;
+    if ((rc = match_scratch(h, 13, (size_t)std::max(L.total_pts, 1) * 8, &p)) != PL_OK) return rc; *d_dist = (int*)p;
+    if ((rc = match_scratch(h, 14, (size_t)n * 8, &p)) != PL_OK) return rc; *d_hits = (int*)p;
+    PL_CUDA_TRY(cudaMemsetAsync(*d_hits, 0, (size_t)n * 8, st));
+    if ((size_t)L.max_n2 * 4 > 48 * 1024) PL_CUDA_TRY(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, L.max_n2 * 4));
+    k_frame_grid<<<n, 1024, (size_t)L.max_n2 * 4, st>>>(d_sd, sorted_idx, cell_start);
+    h->last_launches++;
+    if (L.max_np > 0) {
+        const dim3 grid((L.max_np * 32 + 255) / 256, n);
+        k_point_best<VARIANT><<<grid, 256, 0, st>>>(d_sd, th, th_dist, sorted_idx, cell_start, *d_idx, *d_dist, *d_hits);
+        h->last_launches++;
+    }
+    PL_CUDA_TRY(cudaGetLastError());
+    return PL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+PL_API int pl_orb_fuse_candidates_batch(pl_match* h, int n, const pl_frame_view* kf, const pl_posepoint_view* pts, const float* ow,
+                                        const float* log_scale_factor, const float* const* inv_level_sigma2, float th, int variant,
+                                        int* const* best_idx, int* const* best_dist, int* n_fused) {
+    PL_CHECK_ARG(h && n >= 0 && (variant == 0 || variant == 1) && (n == 0 || (kf && pts && ow && log_scale_factor && best_idx && n_fused)));
+    PL_CHECK_ARG(n == 0 || variant == 1 || inv_level_sigma2);
+    if (n == 0) return PL_OK;
+    size_t bytes = padb(sizeof(SearchDev) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        int rc = check_frame(&kf[i]);
+        if (rc != PL_OK) return rc;
+        if ((rc = check_posepoints(pts[i], true)) != PL_OK) return rc;
+        PL_CHECK_ARG(log_scale_factor[i] > 0.f && (best_idx[i] != nullptr || pts[i].n == 0));
+        PL_CHECK_ARG(variant == 1 || inv_level_sigma2[i] != nullptr);
+        bytes += frame_bytes(kf[i]) + posepoint_bytes(pts[i]);
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    int rc = h->in.reserve(bytes);
+    if (rc != PL_OK) return rc;
+    std::vector<SearchDev> sd(n);
+    IndepLayout L;
+    for (int i = 0; i < n; i++) {
+        SearchDev& S = sd[i];
+        memset(&S, 0, sizeof(S));
+        put_frame(h->in, kf[i], S.F);
+        put_posepoints(h->in, pts[i], S, true);
+        for (int k = 0; k < 3; k++) S.ow[k] = ow[3 * (size_t)i + k];
+        S.log_sf = log_scale_factor[i];
+        if (variant == 0) {
+            S.use_chi2 = 1;
+            for (int k = 0; k < kf[i].n_levels; k++) S.inv_sigma2[k] = inv_level_sigma2[i][k];
+        }
+        place(S, kf[i].n, L);
+    }
+    const SearchDev* d_sd = h->in.put(sd.data(), (size_t)n);
+    if ((rc = h->in.upload(h->stream)) != PL_OK) return rc;
+    int *d_idx, *d_dist, *d_hits;
+    rc = variant == 0 ? run_point_best<0>(h, d_sd, n, L, th, kThLow, &d_idx, &d_dist, &d_hits)
+                      : run_point_best<1>(h, d_sd, n, L, th, kThLow, &d_idx, &d_dist, &d_hits);
+    if (rc != PL_OK) return rc;
+    const size_t np = (size_t)std::max(L.total_pts, 1);
+    if ((rc = h->res.reserve(padb(np * 4) * 2 + padb((size_t)n * 4))) != PL_OK) return rc;
+    int *h_idx, *h_dist, *h_hits;
+    h->res.out<int>(np, &h_idx);
+    h->res.out<int>(np, &h_dist);
+    h->res.out<int>((size_t)n, &h_hits);
+    cudaStream_t st = h->stream;
+    if (L.total_pts) {
+        PL_CUDA_TRY(cudaMemcpyAsync(h_idx, d_idx, (size_t)L.total_pts * 4, cudaMemcpyDeviceToHost, st));
+        PL_CUDA_TRY(cudaMemcpyAsync(h_dist, d_dist, (size_t)L.total_pts * 4, cudaMemcpyDeviceToHost, st));
+    }
+    PL_CUDA_TRY(cudaMemcpyAsync(h_hits, d_hits, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) {
+        if (pts[i].n) {
+            memcpy(best_idx[i], h_idx + sd[i].pt_base, (size_t)pts[i].n * 4);
+            if (best_dist && best_dist[i]) memcpy(best_dist[i], h_dist + sd[i].pt_base, (size_t)pts[i].n * 4);
+        }
+        n_fused[i] = h_hits[i];
+    }
+    return PL_OK;
+}
+
+PL_API int pl_orb_search_by_sim3(pl_match* h, const pl_frame_view* kf1, const pl_frame_view* kf2, const pl_posepoint_view* pts1,
+                                 const pl_posepoint_view* pts2, const float t21[12], const float t12[12], float log_scale_factor1,
+                                 float log_scale_factor2, float th, int* match12, int* n_found) {
+    PL_CHECK_ARG(h && kf1 && kf2 && pts1 && pts2 && t21 && t12 && n_found && log_scale_factor1 > 0.f && log_scale_factor2 > 0.f);
+    int rc;
+    if ((rc = check_frame(kf1)) != PL_OK || (rc = check_frame(kf2)) != PL_OK) return rc;
+    if ((rc = check_posepoints(*pts1, false)) != PL_OK || (rc = check_posepoints(*pts2, false)) != PL_OK) return rc;
+    PL_CHECK_ARG(pts1->n == kf1->n && pts2->n == kf2->n && (match12 || kf1->n == 0));  // GetMapPointMatches(): one slot per feature
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    if ((rc = h->in.reserve(padb(sizeof(SearchDev) * 2) + frame_bytes(*kf1) + frame_bytes(*kf2) + posepoint_bytes(*pts1) + posepoint_bytes(*pts2))) != PL_OK)
+        return rc;
+    SearchDev sd[2];
+    IndepLayout L;
+    for (int d = 0; d < 2; d++) {
+        SearchDev& S = sd[d];
+        memset(&S, 0, sizeof(S));
+        const pl_frame_view& from = d == 0 ? *kf1 : *kf2;  // owner of the points
+        const pl_frame_view& into = d == 0 ? *kf2 : *kf1;  // searched key frame
+        put_frame(h->in, into, S.F);
+        put_posepoints(h->in, d == 0 ? *pts1 : *pts2, S, false);
+        for (int k = 0; k < 12; k++) { S.F.tcw[k] = from.tcw[k]; S.t2[k] = (d == 0 ? t21 : t12)[k]; }
+        S.F.fx = kf1->fx; S.F.fy = kf1->fy; S.F.cx = kf1->cx; S.F.cy = kf1->cy;  // :1445-1448: pKF1's intrinsics both ways
+        S.use_t2 = 1;
+        S.log_sf = d == 0 ? log_scale_factor2 : log_scale_factor1;
+        place(S, into.n, L);
+    }
+    const SearchDev* d_sd = h->in.put(sd, 2);
+    if ((rc = h->in.upload(h->stream)) != PL_OK) return rc;
+    int *d_idx, *d_dist, *d_hits;
+    if ((rc = run_point_best<2>(h, d_sd, 2, L, th, kThHigh, &d_idx, &d_dist, &d_hits)) != PL_OK) return rc;
+    cudaStream_t st = h->stream;
+    // d_dist (scratch 13, 8 bytes per point) is reused: the first half holds distances, the second half receives match12
+    int* d_m12 = d_dist + std::max(L.total_pts, 1);
+    int* d_found = d_hits + 2;
+    if (kf1->n) {
+        k_sim3_agree<<<(kf1->n + 255) / 256, 256, 0, st>>>(d_idx + sd[0].pt_base, kf1->n, d_idx + sd[1].pt_base, kf2->n, d_m12, d_found);
+        h->last_launches++;
+        PL_CUDA_TRY(cudaGetLastError());
+    }
+    if ((rc = h->res.reserve(padb((size_t)std::max(kf1->n, 1) * 4) + padb(16))) != PL_OK) return rc;
+    int *h_m12, *h_found;
+    h->res.out<int>((size_t)std::max(kf1->n, 1), &h_m12);
+    h->res.out<int>(4, &h_found);
+    if (kf1->n) PL_CUDA_TRY(cudaMemcpyAsync(h_m12, d_m12, (size_t)kf1->n * 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaMemcpyAsync(h_found, d_found, 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    if (kf1->n) memcpy(match12, h_m12, (size_t)kf1->n * 4);
+    *n_found = h_found[0];
+    return PL_OK;
+}
+
+PL_API int pl_orb_search_for_initialization(pl_match* h, const pl_frame_view* F1, const pl_frame_view* F2, float* prev_matched, int window_size,
+                                            float nn_ratio, int check_orientation, int* matches12, int* n_matches) {
+    PL_CHECK_ARG(h && F1 && F2 && n_matches && window_size > 0);
+    int rc;
+    if ((rc = check_frame(F1)) != PL_OK || (rc = check_frame(F2)) != PL_OK) return rc;
+    PL_CHECK_ARG(F1->n == 0 || (prev_matched && matches12));
+    if (F2->n > kInitMaxFeat) { set_error("SearchForInitialization: F2 has %d features, the limit is %d", F2->n, kInitMaxFeat); return PL_ERR_CAPACITY; }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    *n_matches = 0;
+    if (F1->n == 0) return PL_OK;
+    const size_t n1 = (size_t)F1->n;
+    if ((rc = h->in.reserve(padb(sizeof(SearchDev)) + frame_bytes(*F2) + padb(n1 * sizeof(pl_keypoint)) + padb(n1 * 32) + padb(n1) + padb(n1 * 4) * 2 +
+                            padb(n1 * 8))) != PL_OK)
+        return rc;
+    SearchDev S;
+    memset(&S, 0, sizeof(S));
+    put_frame(h->in, *F2, S.F);
+    // the points are the level-0 features of F1 (:592-596), searched around vbPrevMatched
+    std::vector<uint8_t> valid(n1);
+    std::vector<float> px(n1), py(n1);
+    for (size_t i = 0; i < n1; i++) {
+        valid[i] = F1->keys_un[i].octave > 0 ? 0 : 1;
+        px[i] = prev_matched[2 * i];
+        py[i] = prev_matched[2 * i + 1];
+    }
+    S.np = F1->n;
+    S.valid = h->in.put(valid.data(), n1);
+    S.pdesc = (const uint4*)h->in.put(F1->desc, n1 * 32);
+    S.proj_x = h->in.put(px.data(), n1);
+    S.proj_y = h->in.put(py.data(), n1);
+    const pl_keypoint* d_keys1 = h->in.put(F1->keys_un, n1);
+    float* d_prev = const_cast<float*>(h->in.put(prev_matched, n1 * 2));
+    IndepLayout L;
+    place(S, F2->n, L);
+    const SearchDev* d_sd = h->in.put(&S, 1);
+    if ((rc = h->in.upload(h->stream)) != PL_OK) return rc;
+    cudaStream_t st = h->stream;
+    void* p;
+    int *sorted_idx, *cell_start, *cand_n, *cand_off, *totals, *match, *rec, *out;
+    if ((rc = match_scratch(h, 6, (size_t)S.n2 * 4, &p)) != PL_OK) return rc; sorted_idx = (int*)p;
+    if ((rc = match_scratch(h, 7, (size_t)(kGridCells + 1) * 4, &p)) != PL_OK) return rc; cell_start = (int*)p;
+    if ((rc = match_scratch(h, 8, n1 * 4, &p)) != PL_OK) return rc; cand_n = (int*)p;
+    if ((rc = match_scratch(h, 9, n1 * 4, &p)) != PL_OK) return rc; cand_off = (int*)p;
+    if ((rc = match_scratch(h, 10, 4, &p)) != PL_OK) return rc; totals = (int*)p;
+    if ((rc = match_scratch(h, 12, n1 * 4, &p)) != PL_OK) return rc; match = (int*)p;
+    if ((rc = match_scratch(h, 13, n1 * 8, &p)) != PL_OK) return rc; rec = (int*)p;
+    if ((rc = match_scratch(h, 14, 8, &p)) != PL_OK) return rc; out = (int*)p;
+    if ((size_t)S.n2 * 4 > 48 * 1024) PL_CUDA_TRY(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, S.n2 * 4));
+    k_frame_grid<<<1, 1024, (size_t)S.n2 * 4, st>>>(d_sd, sorted_idx, cell_start);
+    const dim3 cgrid((F1->n * 32 + 255) / 256, 1);
+    const float thw = (float)window_size;
+    k_candidates<4, false><<<cgrid, 256, 0, st>>>(d_sd, thw, sorted_idx, cell_start, cand_n, nullptr, nullptr, nullptr);
+    k_cand_scan<<<1, 1024, 0, st>>>(d_sd, cand_n, cand_off, totals);
+    h->last_launches += 3;
+    int h_tot = 0;
+    PL_CUDA_TRY(cudaMemcpyAsync(&h_tot, totals, 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    if ((rc = match_scratch(h, 15, (size_t)std::max(h_tot, 1) * 4, &p)) != PL_OK) return rc;
+    unsigned int* cand = (unsigned int*)p;
+    if ((rc = match_scratch(h, 11, 4, &p)) != PL_OK) return rc;
+    int* inst_base = (int*)p;
+    PL_CUDA_TRY(cudaMemsetAsync(inst_base, 0, 4, st));
+    k_candidates<4, true><<<cgrid, 256, 0, st>>>(d_sd, thw, sorted_idx, cell_start, cand_n, cand_off, inst_base, cand);
+    const size_t rsm = (size_t)kResChunkCand * 4 + (size_t)std::max(F2->n, 1) * 6 + 16;
+    PL_CUDA_TRY(cudaFuncSetAttribute(k_init_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+    k_init_resolve<<<1, kResThreads, rsm, st>>>(d_sd, nn_ratio, check_orientation, cand, cand_n, cand_off, totals, d_keys1, match, rec, d_prev, out);
+    h->last_launches += 2;
+    PL_CUDA_TRY(cudaGetLastError());
+    if ((rc = h->res.reserve(padb(n1 * 4) + padb(n1 * 8) + padb(8))) != PL_OK) return rc;
+    int *h_match, *h_out;
+    float* h_prev;
+    h->res.out<int>(n1, &h_match);
+    h->res.out<float>(n1 * 2, &h_prev);
+    h->res.out<int>(2, &h_out);
+    PL_CUDA_TRY(cudaMemcpyAsync(h_match, match, n1 * 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaMemcpyAsync(h_prev, d_prev, n1 * 8, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaMemcpyAsync(h_out, out, 8, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(matches12, h_match, n1 * 4);
+    memcpy(prev_matched, h_prev, n1 * 8);
+    *n_matches = h_out[0];
+    if (h_out[1]) {
+        set_error("a feature had more than %d candidates in its search window", kResChunkCand);
+        return PL_ERR_CAPACITY;
+    }
+    return PL_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,272 @@
+"""CPU tests (-m "not gpu") of the oracle's E rows (remaining ORBmatcher entry points, ComputeDistinctiveDescriptors):
+each C++ restatement is compared with a second, deliberately naive Python restatement of the reference text, or checked
+through the invariants the reference guarantees.  The reference cannot be run here (OpenCV C++ is not in the image)."""
+import importlib
+
+import numpy as np
+import pytest
+
+import matchgen
+
+PKG = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200")
+N = PKG._native if hasattr(PKG, "_native") else importlib.import_module(PKG.__name__ + "._native")
+TH_LOW, HISTO = 50, 30
+
+
+def _popcnt(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def _view_arrays(v, n_field="n"):
+    import ctypes as C
+    n = v.n
+    kp = np.frombuffer((C.c_char * (n * 28)).from_address(v.keys_un), N.KP_DTYPE) if n else np.zeros(0, N.KP_DTYPE)
+    d = np.frombuffer((C.c_char * (n * 32)).from_address(v.desc), np.uint8).reshape(n, 32) if n else np.zeros((0, 32), np.uint8)
+    return kp, d
+
+
+def _three_maxima(h):
+    m1 = m2 = m3 = 0
+    i1 = i2 = i3 = -1
+    for i, s in enumerate(h):
+        if s > m1:
+            m3, m2, m1, i3, i2, i1 = m2, m1, s, i2, i1, i
+        elif s > m2:
+            m3, m2, i3, i2 = m2, s, i2, i
+        elif s > m3:
+            m3, i3 = s, i
+    if m2 < np.float32(0.1) * np.float32(m1):
+        i2 = i3 = -1
+    elif m3 < np.float32(0.1) * np.float32(m1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def naive_distinctive(desc, off):
+    out = []
+    for g in range(len(off) - 1):
+        d = desc[off[g]:off[g + 1]]
+        n = len(d)
+        if n == 0:
+            out.append(-1)
+            continue
+        D = np.array([[0 if i == j else _popcnt(d[i], d[j]) for j in range(n)] for i in range(n)])
+        best, bi = 2 ** 31 - 1, 0
+        for i in range(n):
+            med = sorted(D[i])[int(0.5 * (n - 1))]
+            if med < best:
+                best, bi = med, i
+        out.append(bi)
+    return np.asarray(out, np.int32)
+
+
+@pytest.mark.parametrize("seed,sizes", [(1, [1, 2, 3, 5, 8, 0, 13, 40]), (2, [64, 33, 32, 31, 7]), (3, [150]), (4, [])])
+def test_distinctive_descriptors_vs_naive(seed, sizes, oracle):
+    rng = np.random.default_rng(seed)
+    desc, off = matchgen.distinctive_case(rng, sizes)
+    if len(sizes) == 0:
+        assert len(oracle.distinctive_descriptors(np.zeros((0, 32), np.uint8), np.zeros(1, np.int32))) == 0
+        return
+    assert np.array_equal(oracle.distinctive_descriptors(desc, off), naive_distinctive(desc, off))
+
+
+def naive_init(f1, f2, prev, window, ratio, check_ori):
+    kp1, d1 = _view_arrays(f1)
+    kp2, d2 = _view_arrays(f2)
+    prev = prev.copy()
+    m12 = np.full(len(kp1), -1, np.int32)
+    mdist = np.full(len(kp2), 2 ** 31 - 1, np.int64)
+    m21 = np.full(len(kp2), -1, np.int64)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    r = np.float32(window)
+    invw, invh = np.float32(64) / np.float32(640), np.float32(48) / np.float32(480)
+    cells = {}
+    for i, k in enumerate(kp2):
+        cx, cy = int(np.round(np.float32(k["x"] * invw))), int(np.round(np.float32(k["y"] * invh)))
+        if 0 <= cx < 64 and 0 <= cy < 48:
+            cells.setdefault((cx, cy), []).append(i)
+    for i1, k1 in enumerate(kp1):
+        if k1["octave"] > 0:
+            continue
+        x, y = prev[i1]
+        x0 = max(0, int(np.floor(np.float32(np.float32(x - r) * invw)))); x1 = min(63, int(np.ceil(np.float32(np.float32(x + r) * invw))))
+        y0 = max(0, int(np.floor(np.float32(np.float32(y - r) * invh)))); y1 = min(47, int(np.ceil(np.float32(np.float32(y + r) * invh))))
+        if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+            continue
+        best = best2 = 2 ** 31 - 1
+        bi = -1
+        for cx in range(x0, x1 + 1):
+            for cy in range(y0, y1 + 1):
+                for i2 in cells.get((cx, cy), []):
+                    k2 = kp2[i2]
+                    if k2["octave"] > 0:
+                        continue
+                    if not (abs(np.float32(k2["x"] - x)) < r and abs(np.float32(k2["y"] - y)) < r):
+                        continue
+                    dist = _popcnt(d1[i1], d2[i2])
+                    if mdist[i2] <= dist:
+                        continue
+                    if dist < best:
+                        best2, best, bi = best, dist, i2
+                    elif dist < best2:
+                        best2 = dist
+        if best <= TH_LOW and np.float32(best) < np.float32(np.float32(best2) * np.float32(ratio)):
+            if m21[bi] >= 0:
+                m12[m21[bi]] = -1
+                nm -= 1
+            m12[i1], m21[bi], mdist[bi] = bi, i1, best
+            nm += 1
+            if check_ori:
+                rot = np.float32(k1["angle"] - kp2[bi]["angle"])
+                if rot < 0:
+                    rot = np.float32(rot + np.float32(360))
+                b = int(np.round(np.float32(rot * (np.float32(HISTO) / np.float32(360)))))
+                hist[0 if b == HISTO else b].append(i1)
+    if check_ori:
+        keep = _three_maxima([len(h) for h in hist])
+        for b in range(HISTO):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                if m12[i1] >= 0:
+                    m12[i1] = -1
+                    nm -= 1
+    for i1 in range(len(kp1)):
+        if m12[i1] >= 0:
+            prev[i1] = (kp2[m12[i1]]["x"], kp2[m12[i1]]["y"])
+    return m12, nm, prev
+
+
+@pytest.mark.parametrize("seed,n1,n2,window", [(1, 300, 350, 100), (2, 200, 150, 30), (3, 0, 20, 100), (4, 20, 0, 100)])
+def test_search_for_initialization_vs_naive(seed, n1, n2, window, oracle, synth):
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    rng = np.random.default_rng(seed)
+    f1, f2, prev, keep = matchgen.init_case(rng, n1, n2, N, synth.TUM1, sf)
+    for ori in (True, False):
+        o = oracle.search_for_initialization(f1, f2, prev, window, 0.9, ori)
+        m, nm, pm = naive_init(f1, f2, prev, window, 0.9, ori)
+        assert np.array_equal(o[0], m) and o[1] == nm and np.array_equal(o[2], pm)
+        assert o[1] == int((o[0] >= 0).sum())
+    if n1 >= 300:
+        assert o[1] > 40
+
+
+def test_fuse_and_sim3_invariants(oracle, synth):
+    """Every reported fusion / Sim3 match satisfies the gates of the reference text; hits are counted consistently."""
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    rng = np.random.default_rng(7)
+    fv, pv, ow, log_sf, inv_s2, keep = matchgen.fuse_case(rng, 600, 300, N, synth.TUM1, sf)
+    kp, desc = _view_arrays(fv)
+    for variant in (0, 1):
+        bi, bd, nf = oracle.fuse_candidates(fv, pv, ow, log_sf, inv_s2, 3.0, variant)
+        assert nf == int((bi >= 0).sum()) and nf > 100
+        assert np.all(bd[bi >= 0] <= TH_LOW) and np.all((bd[bi < 0] > TH_LOW))
+        import ctypes as C
+        pd = np.frombuffer((C.c_char * (pv.n * 32)).from_address(pv.desc), np.uint8).reshape(pv.n, 32)
+        for k in np.nonzero(bi >= 0)[0][:50]:
+            assert _popcnt(pd[k], desc[bi[k]]) == bd[k]
+    # the chi-square gates of variant 0 can only remove candidates
+    b0 = oracle.fuse_candidates(fv, pv, ow, log_sf, inv_s2, 3.0, 0)
+    b1 = oracle.fuse_candidates(fv, pv, ow, log_sf, inv_s2, 3.0, 1)
+    assert b0[2] <= b1[2]
+    kf1, kf2, p1, p2, t21, t12, lsf, keep2 = matchgen.sim3_case(rng, 500, 100, 150, N, synth.TUM1, sf)
+    m12, nf = oracle.search_by_sim3(kf1, kf2, p1, p2, t21, t12, lsf, lsf, 7.5)
+    assert nf == int((m12 >= 0).sum()) and nf > 100
+    hit = m12[m12 >= 0]
+    assert len(np.unique(hit)) == len(hit)      # mutual agreement makes the assignment one-to-one
+
+
+def naive_triangulation(a, b, f12, cw1, tcw2, K2, sf2, sigma2, only_stereo, check_ori):
+    import ctypes as C
+
+    def arrs(v):
+        n = v.bow.n
+        kp = np.frombuffer((C.c_char * (n * 28)).from_address(v.keys_un), N.KP_DTYPE)
+        d = np.frombuffer((C.c_char * (n * 32)).from_address(v.bow.desc), np.uint8).reshape(n, 32)
+        ur = np.frombuffer((C.c_char * (n * 4)).from_address(v.u_right), np.float32)
+        va = np.frombuffer((C.c_char * n).from_address(v.bow.valid), np.uint8)
+        ids = np.frombuffer((C.c_char * (v.bow.n_nodes * 4)).from_address(v.bow.node_id), np.uint32)
+        off = np.frombuffer((C.c_char * ((v.bow.n_nodes + 1) * 4)).from_address(v.bow.node_off), np.int32)
+        fi = np.frombuffer((C.c_char * (int(off[-1]) * 4)).from_address(v.bow.feat_idx), np.uint32)
+        return kp, d, ur, va, {int(ids[k]): [int(x) for x in fi[off[k]:off[k + 1]]] for k in range(len(ids))}
+    kp1, d1, ur1, va1, fv1 = arrs(a)
+    kp2, d2, ur2, va2, fv2 = arrs(b)
+    f = np.float32
+    T = np.asarray(tcw2, np.float32).reshape(3, 4)
+    C2 = [f(sum(np.float64(T[r, k]) * np.float64(cw1[k]) for k in range(3)) + np.float64(T[r, 3])) for r in range(3)]
+    invz = f(f(1) / C2[2])
+    ex = f(f(f(f(K2["fx"]) * C2[0]) * invz) + f(K2["cx"]))
+    ey = f(f(f(f(K2["fy"]) * C2[1]) * invz) + f(K2["cy"]))
+    F = np.asarray(f12, np.float32).reshape(3, 3)
+    matched2 = np.zeros(len(kp2), bool)
+    m12 = np.full(len(kp1), -1, np.int64)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for node in sorted(set(fv1) & set(fv2)):
+        for idx1 in fv1[node]:
+            if not va1[idx1]:
+                continue
+            st1 = ur1[idx1] >= 0
+            if only_stereo and not st1:
+                continue
+            k1 = kp1[idx1]
+            best, bi = TH_LOW, -1
+            for idx2 in fv2[node]:
+                if matched2[idx2] or not va2[idx2]:
+                    continue
+                st2 = ur2[idx2] >= 0
+                if only_stereo and not st2:
+                    continue
+                dist = _popcnt(d1[idx1], d2[idx2])
+                if dist > TH_LOW or dist > best:
+                    continue
+                k2 = kp2[idx2]
+                if not st1 and not st2:
+                    dx, dy = f(ex - k2["x"]), f(ey - k2["y"])
+                    if f(f(dx * dx) + f(dy * dy)) < f(f(100) * sf2[k2["octave"]]):
+                        continue
+                la = f(f(f(k1["x"] * F[0, 0]) + f(k1["y"] * F[1, 0])) + F[2, 0])
+                lb = f(f(f(k1["x"] * F[0, 1]) + f(k1["y"] * F[1, 1])) + F[2, 1])
+                lc = f(f(f(k1["x"] * F[0, 2]) + f(k1["y"] * F[1, 2])) + F[2, 2])
+                num = f(f(f(la * k2["x"]) + f(lb * k2["y"])) + lc)
+                den = f(f(la * la) + f(lb * lb))
+                if den == 0:
+                    continue
+                dsqr = f(f(num * num) / den)
+                if np.float64(dsqr) < 3.84 * np.float64(sigma2[k2["octave"]]):
+                    bi, best = idx2, dist
+            if bi >= 0:
+                m12[idx1] = bi
+                matched2[bi] = True
+                nm += 1
+                if check_ori:
+                    rot = f(k1["angle"] - kp2[bi]["angle"])
+                    if rot < 0:
+                        rot = f(rot + f(360))
+                    bn = int(np.round(f(rot * (f(HISTO) / f(360)))))
+                    hist[0 if bn == HISTO else bn].append(idx1)
+    if check_ori:
+        keep = _three_maxima([len(h) for h in hist])
+        for bn in range(HISTO):
+            if bn in keep:
+                continue
+            for i in hist[bn]:
+                m12[i] = -1
+                nm -= 1
+    pairs = np.asarray([(i, m12[i]) for i in range(len(kp1)) if m12[i] >= 0], np.int32).reshape(-1, 2)
+    return pairs, nm
+
+
+@pytest.mark.parametrize("seed,m,e1,e2,nodes,only_stereo", [(1, 250, 60, 80, 20, False), (2, 200, 30, 30, 6, True), (3, 0, 10, 10, 3, False)])
+def test_search_for_triangulation_vs_naive(seed, m, e1, e2, nodes, only_stereo, oracle, synth):
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    rng = np.random.default_rng(seed)
+    with np.errstate(over="ignore", invalid="ignore"):
+        a, b, f12, cw1, tcw2, sigma2, keep = matchgen.triang_case(rng, m, e1, e2, nodes, N, synth.TUM1, sf)
+        for ori in (True, False):
+            o = oracle.search_for_triangulation(a, b, f12, cw1, tcw2, synth.TUM1, sf, sigma2, only_stereo, ori)
+            p, nm = naive_triangulation(a, b, f12, cw1, tcw2, synth.TUM1, np.asarray(sf, np.float32), sigma2, only_stereo, ori)
+            assert o[1] == nm and np.array_equal(o[0], p)
+    if m >= 200 and not only_stereo:
+        assert o[1] > 30
