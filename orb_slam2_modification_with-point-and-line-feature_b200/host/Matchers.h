@@ -86,6 +86,68 @@ public:
         match12.resize(KF1.n);
         return n;
     }
+    // Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th) (ORBmatcher.cc:1107-1277): best_idx[i] = key-frame feature the map point i
+    // fuses with, or -1; the caller walks it in order for the Replace / AddObservation bookkeeping (:1251-1272)
+    int Fuse(const pl_frame_view& KF, const pl_posepoint_view& vpMapPoints, const float Ow[3], float logScaleFactor, const float* invLevelSigma2,
+             float th, std::vector<int>& best_idx) {
+        int n = 0;
+        best_idx.assign(vpMapPoints.n > 0 ? vpMapPoints.n : 1, -1);
+        int* bi[1] = {best_idx.data()};
+        const float* sg[1] = {invLevelSigma2};
+        check(pl_orb_fuse_candidates_batch(h_, 1, &KF, &vpMapPoints, Ow, &logScaleFactor, sg, th, 0, bi, nullptr, &n));
+        best_idx.resize(vpMapPoints.n);
+        return n;
+    }
+    // Fuse(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, float th, vector<MapPoint*> &vpReplacePoint) (ORBmatcher.cc:1290-1427);
+    // KF.tcw = Rcw | tcw with the scale divided out, Ow = -Rcw^T tcw (:1299-1303)
+    int Fuse(const pl_frame_view& KF, const float Ow[3], float logScaleFactor, const pl_posepoint_view& vpPoints, float th, std::vector<int>& best_idx) {
+        int n = 0;
+        best_idx.assign(vpPoints.n > 0 ? vpPoints.n : 1, -1);
+        int* bi[1] = {best_idx.data()};
+        check(pl_orb_fuse_candidates_batch(h_, 1, &KF, &vpPoints, Ow, &logScaleFactor, nullptr, th, 1, bi, nullptr, &n));
+        best_idx.resize(vpPoints.n);
+        return n;
+    }
+    // SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, s12, R12, t12, th) (ORBmatcher.cc:1441-1692):
+    // T21 = sR21 | t21 and T12 = sR12 | t12 (:1457-1460); match12[i1] = KF2 feature whose map point goes to vpMatches12[i1], or -1
+    int SearchBySim3(const pl_frame_view& KF1, const pl_frame_view& KF2, const pl_posepoint_view& vpMapPoints1, const pl_posepoint_view& vpMapPoints2,
+                     const float T21[12], const float T12[12], float logScaleFactor1, float logScaleFactor2, float th, std::vector<int>& match12) {
+        int n = 0;
+        match12.assign(KF1.n > 0 ? KF1.n : 1, -1);
+        check(pl_orb_search_by_sim3(h_, &KF1, &KF2, &vpMapPoints1, &vpMapPoints2, T21, T12, logScaleFactor1, logScaleFactor2, th, match12.data(), &n));
+        match12.resize(KF1.n);
+        return n;
+    }
+    // SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize) (ORBmatcher.cc:573-717)
+    int SearchForInitialization(const pl_frame_view& F1, const pl_frame_view& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                int windowSize = 10) {
+        int n = 0;
+        vnMatches12.assign(F1.n > 0 ? F1.n : 1, -1);
+        static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f is two floats");
+        check(pl_orb_search_for_initialization(h_, &F1, &F2, (float*)vbPrevMatched.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0,
+                                               vnMatches12.data(), &n));
+        vnMatches12.resize(F1.n);
+        return n;
+    }
+    // SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vector<pair<size_t,size_t>> &vMatchedPairs, bOnlyStereo) (ORBmatcher.cc:884-1095)
+    int SearchForTriangulation(const pl_triang_view& KF1, const pl_triang_view& KF2, const float F12[9], const float Cw1[3], const float Tcw2[12],
+                               float fx2, float fy2, float cx2, float cy2, const float* scaleFactors2, const float* levelSigma2_2, int nLevels2,
+                               std::vector<std::pair<size_t, size_t>>& vMatchedPairs, bool bOnlyStereo) {
+        int n = 0;
+        std::vector<int> pairs(2 * (size_t)(KF1.bow.n > 0 ? KF1.bow.n : 1));
+        check(pl_orb_search_for_triangulation(h_, &KF1, &KF2, F12, Cw1, Tcw2, fx2, fy2, cx2, cy2, scaleFactors2, levelSigma2_2, nLevels2,
+                                              bOnlyStereo ? 1 : 0, mbCheckOrientation ? 1 : 0, pairs.data(), &n));
+        vMatchedPairs.clear();
+        for (int i = 0; i < n; i++) vMatchedPairs.push_back(std::make_pair((size_t)pairs[2 * i], (size_t)pairs[2 * i + 1]));
+        return n;
+    }
+    // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:256-321) / MapLine twin (MapLine.cpp:269-330) for many map points at once
+    void ComputeDistinctiveDescriptors(const uint8_t* vDescriptors, const std::vector<int>& group_off, std::vector<int>& best_row) {
+        const int g = (int)group_off.size() - 1;
+        best_row.assign(g > 0 ? g : 1, -1);
+        if (g > 0) check(pl_distinctive_descriptors(h_, vDescriptors, group_off.data(), g, best_row.data()));
+        best_row.resize(g > 0 ? g : 0);
+    }
     pl_match* handle() { return h_; }
 
 protected:
