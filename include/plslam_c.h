@@ -445,6 +445,42 @@ PL_API int pl_orb_search_for_triangulation(pl_match* h, const pl_triang_view* a,
  * an empty group. */
 PL_API int pl_distinctive_descriptors(pl_match* h, const uint8_t* desc, const int* group_off, int n_groups, int* best_row);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * F: per-feature maps of Frame that sit between the extractors and the matchers.  Pure
+ *    element-wise work; batched over the frames of a sequence so that one call covers what the reference does in
+ *    N Frame constructors / N SearchLocalPoints passes.  Frame f owns the features [off[f], off[f+1]).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* F1: Frame::UndistortKeyPoints (Frame.cc:737-765) / UndistortKeyLines endpoints (:767-800) ==
+ * cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) for n (x, y) pairs; dist_coef = k1 k2 p1 p2 k3
+ * (Tracking.cc:79-91).  k1 == 0 copies the input, as the reference does (:739-743). */
+PL_API int pl_frame_undistort_points(pl_match* h, const float* xy, int n, float fx, float fy, float cx, float cy, const float dist_coef[5],
+                                     float* xy_out);
+/* F2: Frame::ComputeStereoFromRGBD (Frame.cc:1065-1117): d = imDepth.at<float>(v, u) at the truncated DISTORTED position
+ * xy (mvKeys[i].pt, or a KeyLine end point), depth_out = d and u_right_out = x_un - bf / d when d > 0, else -1 / -1.
+ * depth = n_frames float images (rows x cols, row stride step_bytes, frame f at depth + f * frame_stride_bytes).
+ * depth_is_device != 0: `depth` is a device pointer (images already resident in HBM), everything else stays host. */
+PL_API int pl_frame_stereo_from_rgbd_batch(pl_match* h, int n_frames, const float* depth, int depth_is_device, int rows, int cols, size_t step_bytes,
+                                           size_t frame_stride_bytes, const int* off, const float* xy, const float* x_un, float bf, float* depth_out,
+                                           float* u_right_out);
+/* F3: Frame::UnprojectStereo (Frame.cc:1120-1134) == UnprojectStereoLine{,Start,End} (:1140-1205) per end point:
+ * x = (u-cx)*z*invfx, y = (v-cy)*z*invfy, world = mRwc * (x, y, z) + mOw for z > 0 (world is left 0 and valid = 0 otherwise).
+ * rwc = n_frames x 9 (row-major mRwc), ow = n_frames x 3; invfx = 1.0f / fx as Frame.cc computes it. */
+PL_API int pl_frame_unproject_batch(pl_match* h, int n_frames, const int* off, const float* xy_un, const float* z, const float* rwc, const float* ow,
+                                    float fx, float fy, float cx, float cy, float* world /* total x 3 */, uint8_t* valid /* total */);
+/* F4: Frame::IsInFrustum(MapPoint*, viewingCosLimit) (Frame.cc:345-401) with MapPoint::PredictScale (MapPoint.cc:416-431) for
+ * n_frames frames against one snapshot of m map points: the fields it leaves on the map point, as [n_frames x m] planes —
+ * exactly the inputs of pl_orb_search_local_points (C2).  tcw = n_frames x 12 (mRcw | mtcw), ow = n_frames x 3,
+ * bounds = mnMinX, mnMinY, mnMaxX, mnMaxY.  Planes other than in_view are only defined where in_view = 1. */
+PL_API int pl_frame_is_in_frustum_batch(pl_match* h, int n_frames, const float* tcw, const float* ow, float fx, float fy, float cx, float cy, float bf,
+                                        const float bounds[4], int n_levels, float log_scale_factor, int m, const float* world_pos,
+                                        const float* normal, const float* min_dist_inv, const float* max_dist_inv, const float* max_dist,
+                                        float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* scale_level,
+                                        float* view_cos);
+/* Frame::IsInFrustum(MapLine*, viewingCosLimit) (Frame.cc:403-430): a map line is in view unless both end points are behind
+ * the camera.  start3d / end3d = m x 3 doubles (MapLine::mStart3d / mEnd3d), converted to float as the reference does. */
+PL_API int pl_frame_lines_in_frustum_batch(pl_match* h, int n_frames, const float* tcw, int m, const double* start3d, const double* end3d,
+                                           uint8_t* in_view /* n_frames x m */);
+
 #ifdef __cplusplus
 }
 #endif

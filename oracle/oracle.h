@@ -55,6 +55,13 @@ ORC_API int orc_orb_search_for_initialization(const pl_frame_view* F1, const pl_
 ORC_API int orc_orb_search_for_triangulation(const pl_triang_view* A, const pl_triang_view* B, const float* F12, const float* cw1, const float* kf2_tcw, float fx2, float fy2, float cx2, float cy2, const float* scale_factors2, const float* level_sigma2_2, int n_levels2, int only_stereo, int check_orientation, int* pairs, int* n_matches);
 ORC_API int orc_distinctive_descriptors(const uint8_t* desc, const int* group_off, int n_groups, int* best_row);
 
+/* ---- Frame glue (frame_oracle.cpp) ---- */
+ORC_API int orc_frame_undistort_points(const float* xy, int n, float fx, float fy, float cx, float cy, const float* dist_coef, float* xy_out);
+ORC_API int orc_frame_stereo_from_rgbd_batch(int n_frames, const float* depth, int rows, int cols, size_t step_bytes, size_t frame_stride_bytes, const int* off, const float* xy, const float* x_un, float bf, float* depth_out, float* u_right_out);
+ORC_API int orc_frame_unproject_batch(int n_frames, const int* off, const float* xy_un, const float* z, const float* rwc, const float* ow, float fx, float fy, float cx, float cy, float* world, uint8_t* valid);
+ORC_API int orc_frame_is_in_frustum_batch(int n_frames, const float* tcw, const float* ow, float fx, float fy, float cx, float cy, float bf, const float* bounds, int n_levels, float log_scale_factor, int m, const float* world_pos, const float* normal, const float* min_dist_inv, const float* max_dist_inv, const float* max_dist, float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* scale_level, float* view_cos);
+ORC_API int orc_frame_lines_in_frustum_batch(int n_frames, const float* tcw, int m, const double* start3d, const double* end3d, uint8_t* in_view);
+
 /* ---- line extraction (line_oracle.cpp) ---- */
 ORC_API int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t step, int order_mode, float* xyxy, double* width, double* prec, double* nfa, int cap);
 ORC_API int orc_lsd_angles(const uint8_t* img, int rows, int cols, size_t step, double* out, int* ow, int* oh);

@@ -454,6 +454,67 @@ def distinctive_descriptors(desc, group_off):
     return best[:len(off) - 1]
 
 
+def frame_undistort_points(xy, K, dist_coef):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    dc = np.ascontiguousarray(dist_coef, np.float32).reshape(-1)[:5].copy()
+    out = np.empty_like(xy)
+    lib().orc_frame_undistort_points(_p(xy), C.c_int(len(xy)), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]), C.c_float(K["cy"]), _p(dc),
+                                     _p(out))
+    return out
+
+
+def frame_stereo_from_rgbd_batch(depth, off, xy, x_un, bf):
+    depth = np.ascontiguousarray(depth, np.float32)
+    nf, rows, cols = depth.shape
+    off = np.ascontiguousarray(off, np.int32)
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    xu = np.ascontiguousarray(x_un, np.float32)
+    d = np.empty(max(len(xu), 1), np.float32)
+    ur = np.empty(max(len(xu), 1), np.float32)
+    lib().orc_frame_stereo_from_rgbd_batch(C.c_int(nf), _p(depth), C.c_int(rows), C.c_int(cols), C.c_size_t(cols * 4), C.c_size_t(rows * cols * 4),
+                                           _p(off), _p(xy), _p(xu), C.c_float(bf), _p(d), _p(ur))
+    return d[:len(xu)], ur[:len(xu)]
+
+
+def frame_unproject_batch(off, xy_un, z, rwc, ow, K):
+    off = np.ascontiguousarray(off, np.int32)
+    xy = np.ascontiguousarray(xy_un, np.float32).reshape(-1, 2)
+    z = np.ascontiguousarray(z, np.float32)
+    rwc = np.ascontiguousarray(rwc, np.float32).reshape(-1, 9)
+    ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+    w = np.empty((max(len(z), 1), 3), np.float32)
+    v = np.empty(max(len(z), 1), np.uint8)
+    lib().orc_frame_unproject_batch(C.c_int(len(off) - 1), _p(off), _p(xy), _p(z), _p(rwc), _p(ow), C.c_float(K["fx"]), C.c_float(K["fy"]),
+                                    C.c_float(K["cx"]), C.c_float(K["cy"]), _p(w), _p(v))
+    return w[:len(z)], v[:len(z)]
+
+
+def frame_is_in_frustum_batch(tcw, ow, K, bounds, n_levels, log_sf, world_pos, normal, min_inv, max_inv, max_raw, cos_limit=0.5):
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(-1, 12)
+    ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+    wp = np.ascontiguousarray(world_pos, np.float32).reshape(-1, 3)
+    no = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    mi, ma, mr = (np.ascontiguousarray(a, np.float32) for a in (min_inv, max_inv, max_raw))
+    n, m = len(tcw), len(wp)
+    b = np.asarray(bounds, np.float32)
+    iv = np.zeros((n, m), np.uint8)
+    px, py, pxr, vc = (np.zeros((n, m), np.float32) for _ in range(4))
+    lv = np.zeros((n, m), np.int32)
+    lib().orc_frame_is_in_frustum_batch(C.c_int(n), _p(tcw), _p(ow), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]), C.c_float(K["cy"]),
+                                        C.c_float(K["bf"]), _p(b), C.c_int(n_levels), C.c_float(log_sf), C.c_int(m), _p(wp), _p(no), _p(mi), _p(ma),
+                                        _p(mr), C.c_float(cos_limit), _p(iv), _p(px), _p(py), _p(pxr), _p(lv), _p(vc))
+    return iv, px, py, pxr, lv, vc
+
+
+def frame_lines_in_frustum_batch(tcw, start3d, end3d):
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(-1, 12)
+    s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)
+    e3 = np.ascontiguousarray(end3d, np.float64).reshape(-1, 3)
+    iv = np.zeros((len(tcw), len(s3)), np.uint8)
+    lib().orc_frame_lines_in_frustum_batch(C.c_int(len(tcw)), _p(tcw), C.c_int(len(s3)), _p(s3), _p(e3), _p(iv))
+    return iv
+
+
 class OracleBackend:
     """CPU-oracle backend for frontend.TrackingFrontEnd (same interface as frontend.GpuBackend)."""
 

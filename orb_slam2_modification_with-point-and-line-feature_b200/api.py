@@ -526,3 +526,72 @@ class DescriptorMatcher:
         best = np.empty(max(len(off) - 1, 1), np.int32)
         check(N.lib().pl_distinctive_descriptors(self._h, ptr(d), ptr(off), C.c_int(len(off) - 1), ptr(best)))
         return best[:len(off) - 1]
+
+    # ---- F rows: per-feature maps of Frame between the extractors and the matchers ----
+    def UndistortPoints(self, xy, K, dist_coef):
+        """Frame::UndistortKeyPoints: cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) for (n, 2) float points."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        dc = np.ascontiguousarray(dist_coef, np.float32).reshape(-1)[:5].copy()
+        out = np.empty_like(xy)
+        check(N.lib().pl_frame_undistort_points(self._h, ptr(xy), C.c_int(len(xy)), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]),
+                                                C.c_float(K["cy"]), ptr(dc), ptr(out)))
+        return out
+
+    def StereoFromRGBDBatch(self, depth, off, xy, x_un, bf, depth_dev_ptr=None):
+        """Frame::ComputeStereoFromRGBD for the frames of a sequence -> (mvDepth, mvuRight) over the concatenated features.
+        depth: (n_frames, rows, cols) float32 host array, or its shape when depth_dev_ptr gives a device copy."""
+        off = np.ascontiguousarray(off, np.int32)
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        xu = np.ascontiguousarray(x_un, np.float32)
+        if depth_dev_ptr is None:
+            depth = np.ascontiguousarray(depth, np.float32)
+            nf, rows, cols = depth.shape
+            dp, isdev = ptr(depth), 0
+        else:
+            nf, rows, cols = depth
+            dp, isdev = C.c_void_p(depth_dev_ptr), 1
+        d = np.empty(max(len(xu), 1), np.float32)
+        ur = np.empty(max(len(xu), 1), np.float32)
+        check(N.lib().pl_frame_stereo_from_rgbd_batch(self._h, C.c_int(nf), dp, C.c_int(isdev), C.c_int(rows), C.c_int(cols), C.c_size_t(cols * 4),
+                                                      C.c_size_t(rows * cols * 4), ptr(off), ptr(xy), ptr(xu), C.c_float(bf), ptr(d), ptr(ur)))
+        return d[:len(xu)], ur[:len(xu)]
+
+    def UnprojectBatch(self, off, xy_un, z, rwc, ow, K):
+        """Frame::UnprojectStereo for the frames of a sequence -> (world (total, 3), valid (total,))."""
+        off = np.ascontiguousarray(off, np.int32)
+        xy = np.ascontiguousarray(xy_un, np.float32).reshape(-1, 2)
+        z = np.ascontiguousarray(z, np.float32)
+        rwc = np.ascontiguousarray(rwc, np.float32).reshape(-1, 9)
+        ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+        w = np.empty((max(len(z), 1), 3), np.float32)
+        v = np.empty(max(len(z), 1), np.uint8)
+        check(N.lib().pl_frame_unproject_batch(self._h, C.c_int(len(off) - 1), ptr(off), ptr(xy), ptr(z), ptr(rwc), ptr(ow), C.c_float(K["fx"]),
+                                               C.c_float(K["fy"]), C.c_float(K["cx"]), C.c_float(K["cy"]), ptr(w), ptr(v)))
+        return w[:len(z)], v[:len(z)]
+
+    def IsInFrustumBatch(self, tcw, ow, K, bounds, n_levels, log_sf, world_pos, normal, min_inv, max_inv, max_raw, cos_limit=0.5):
+        """Frame::IsInFrustum of n frames against one snapshot of m map points -> (in_view, proj_x, proj_y, proj_xr, level, view_cos),
+        each (n, m)."""
+        tcw = np.ascontiguousarray(tcw, np.float32).reshape(-1, 12)
+        ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+        wp = np.ascontiguousarray(world_pos, np.float32).reshape(-1, 3)
+        no = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+        mi, ma, mr = (np.ascontiguousarray(a, np.float32) for a in (min_inv, max_inv, max_raw))
+        n, m = len(tcw), len(wp)
+        b = np.asarray(bounds, np.float32)
+        iv = np.zeros((n, m), np.uint8)
+        px, py, pxr, vc = (np.zeros((n, m), np.float32) for _ in range(4))
+        lv = np.zeros((n, m), np.int32)
+        check(N.lib().pl_frame_is_in_frustum_batch(self._h, C.c_int(n), ptr(tcw), ptr(ow), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]),
+                                                   C.c_float(K["cy"]), C.c_float(K["bf"]), ptr(b), C.c_int(n_levels), C.c_float(log_sf), C.c_int(m),
+                                                   ptr(wp), ptr(no), ptr(mi), ptr(ma), ptr(mr), C.c_float(cos_limit), ptr(iv), ptr(px), ptr(py),
+                                                   ptr(pxr), ptr(lv), ptr(vc)))
+        return iv, px, py, pxr, lv, vc
+
+    def LinesInFrustumBatch(self, tcw, start3d, end3d):
+        tcw = np.ascontiguousarray(tcw, np.float32).reshape(-1, 12)
+        s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)
+        e3 = np.ascontiguousarray(end3d, np.float64).reshape(-1, 3)
+        iv = np.zeros((len(tcw), len(s3)), np.uint8)
+        check(N.lib().pl_frame_lines_in_frustum_batch(self._h, C.c_int(len(tcw)), ptr(tcw), C.c_int(len(s3)), ptr(s3), ptr(e3), ptr(iv)))
+        return iv

@@ -265,3 +265,29 @@ def distinctive_case(rng, sizes):
         rows.append(d)
         off.append(off[-1] + n)
     return np.concatenate(rows) if rows else np.zeros((0, 32), np.uint8), np.asarray(off, np.int32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# F rows: Frame glue
+# ---------------------------------------------------------------------------------------------------------------
+TUM1_DIST = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)   # Examples/RGB-D/TUM1.yaml:14-18
+
+
+def frustum_case(rng, n_frames, m, K):
+    """n_frames nearby poses and m map points around their common field of view."""
+    T = np.stack([_pose(rng, 0.05, 0.1)[:3] for _ in range(n_frames)]) if n_frames else np.zeros((0, 3, 4), np.float32)
+    ow = np.stack([_centre(np.vstack([t, [0, 0, 0, 1]]).astype(np.float32)) for t in T]) if n_frames else np.zeros((0, 3), np.float32)
+    Xw = _world_points(rng, m, K)
+    centre = ow.mean(0) if n_frames else np.zeros(3, np.float32)
+    d = np.linalg.norm(Xw.astype(np.float64) - centre, axis=1)
+    lvl = rng.integers(0, 8, m)
+    max_raw = (d * np.float32(1.2) ** (lvl + rng.uniform(-0.5, 0.5, m))).astype(np.float32)
+    max_inv = (np.float32(1.2) * max_raw).astype(np.float32)
+    min_inv = (np.float32(0.8) * max_raw / np.float32(1.2) ** 7).astype(np.float32)
+    if m:
+        min_inv[:: 19] = max_inv[:: 19]
+    normal = Xw.astype(np.float64) - centre
+    normal /= np.maximum(np.linalg.norm(normal, axis=1, keepdims=True), 1e-9)
+    normal += rng.normal(0, 0.6, normal.shape)
+    normal /= np.maximum(np.linalg.norm(normal, axis=1, keepdims=True), 1e-9)
+    return T.reshape(n_frames, 12).astype(np.float32), ow.astype(np.float32), Xw, normal.astype(np.float32), min_inv, max_inv, max_raw
