@@ -552,3 +552,9 @@ class OracleBackend:
 
     def line_search_batch(self, cvs, lvs):
         return [line_search_by_projection(c, l) for c, l in zip(cvs, lvs)]
+
+    def unproject_batch(self, off, xy, z, rwc, ow, K):
+        return frame_unproject_batch(off, xy, z, rwc, ow, K)
+
+    def is_in_frustum_batch(self, *a):
+        return frame_is_in_frustum_batch(*a)

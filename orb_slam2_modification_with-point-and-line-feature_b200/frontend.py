@@ -24,7 +24,7 @@ f32 = np.float32
 class FrameLite:
     """The subset of ORB_SLAM2::Frame the matchers read."""
 
-    def __init__(self, kps, desc, kls, ldesc, depth, Tcw, K, scale_factors):
+    def __init__(self, kps, desc, kls, ldesc, depth, Tcw, K, scale_factors, stereo=None):
         self.kps, self.desc, self.kls, self.ldesc = kps, desc, kls, ldesc
         self.Tcw = np.asarray(Tcw, f32)
         self.K = K
@@ -32,19 +32,51 @@ class FrameLite:
         h, w = depth.shape
         self.bounds = (0.0, 0.0, float(w), float(h))  # ComputeImageBounds without distortion (Frame.cc:852-887)
         self.size = (w, h)
-        # ComputeStereoFromRGBD (Frame.cc:1065-1117): depth at the (truncated) keypoint position
-        u = kps["x"].astype(np.int64)
-        v = kps["y"].astype(np.int64)
-        d = depth[np.clip(v, 0, h - 1), np.clip(u, 0, w - 1)].astype(f32)
-        ok = d > 0
-        self.depth = np.where(ok, d, f32(-1)).astype(f32)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            self.u_right = np.where(ok, kps["x"] - f32(K["bf"]) / d, f32(-1)).astype(f32)
+        self._world = None
+        if stereo is not None:  # (mvDepth, mvuRight) already computed for the whole sequence (build_batch)
+            self.depth, self.u_right = stereo
+        else:
+            # ComputeStereoFromRGBD (Frame.cc:1065-1117): depth at the (truncated) keypoint position
+            u = kps["x"].astype(np.int64)
+            v = kps["y"].astype(np.int64)
+            d = depth[np.clip(v, 0, h - 1), np.clip(u, 0, w - 1)].astype(f32)
+            ok = d > 0
+            self.depth = np.where(ok, d, f32(-1)).astype(f32)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                self.u_right = np.where(ok, kps["x"] - f32(K["bf"]) / d, f32(-1)).astype(f32)
         Rcw, tcw = self.Tcw[:3, :3], self.Tcw[:3, 3]
         self.Rwc = Rcw.T.copy()
         self.Ow = (-self.Rwc @ tcw).astype(f32)
         self._depth_img = depth
         self.set_lines(kls, ldesc)
+
+    @staticmethod
+    def build_batch(orb, depth, Tcw, K, scale_factors, backend):
+        """The Frame constructors of a whole sequence: ComputeStereoFromRGBD as one gather over all key points, UnprojectStereo
+        of every frame through the backend's batched F3 call (pl_frame_unproject_batch / its oracle twin) — the same arithmetic
+        for both arms."""
+        n = len(orb)
+        counts = np.array([len(o[0]) for o in orb], np.int64)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        if n == 0 or not isinstance(depth, np.ndarray) or depth.ndim != 3 or not hasattr(backend, "unproject_batch"):
+            return [FrameLite(orb[t][0], orb[t][1], None, None, depth[t], Tcw[t], K, scale_factors) for t in range(n)]
+        x = np.concatenate([o[0]["x"] for o in orb])
+        y = np.concatenate([o[0]["y"] for o in orb])
+        fidx = np.repeat(np.arange(n), counts)
+        h, w = depth.shape[1:]
+        d = depth[fidx, np.clip(y.astype(np.int64), 0, h - 1), np.clip(x.astype(np.int64), 0, w - 1)].astype(f32)
+        ok = d > 0
+        dd = np.where(ok, d, f32(-1)).astype(f32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ur = np.where(ok, x - f32(K["bf"]) / d, f32(-1)).astype(f32)
+        frames = [FrameLite(orb[t][0], orb[t][1], None, None, depth[t], Tcw[t], K, scale_factors, stereo=(dd[off[t]:off[t + 1]], ur[off[t]:off[t + 1]]))
+                  for t in range(n)]
+        rwc = np.stack([F.Rwc for F in frames])
+        ow = np.stack([F.Ow for F in frames])
+        world, _ = backend.unproject_batch(off, np.stack([x, y], 1), dd, rwc, ow, K)
+        for t, F in enumerate(frames):
+            F._world = world[off[t]:off[t + 1]]
+        return frames
 
     def set_lines(self, kls, ldesc):
         """Attaches the line features (they may arrive later than the points: the two extractors run concurrently)."""
@@ -64,6 +96,8 @@ class FrameLite:
 
     # Frame::UnprojectStereo (Frame.cc:1120-1134), vectorised
     def unproject_points(self):
+        if self._world is not None:
+            return self._world
         z = self.depth
         x = (self.kps["x"] - f32(self.K["cx"])) * z * f32(1.0 / self.K["fx"])
         y = (self.kps["y"] - f32(self.K["cy"])) * z * f32(1.0 / self.K["fy"])
@@ -169,9 +203,17 @@ class LocalMap:
 
     # Frame::IsInFrustum (Frame.cc:345-401) + MapPoint::PredictScale (MapPoint.cc:416-431), vectorised float32 over the
     # frames that see the same snapshot of the map
-    def frustum_group(self, Fs, cos_limit=0.5):
+    def frustum_group(self, Fs, cos_limit=0.5, backend=None):
         K = Fs[0].K
         sf = Fs[0].sf
+        if backend is not None and hasattr(backend, "is_in_frustum_batch"):
+            # F4: pl_frame_is_in_frustum_batch / its oracle twin — Frame::IsInFrustum with the reference's own rounding
+            tcw = np.stack([F.Tcw[:3].reshape(-1) for F in Fs])
+            ow = np.stack([F.Ow for F in Fs])
+            log_sf = float(f32(np.log(f32(sf[1] / sf[0]))))
+            iv, u, v, xr, lvl, vc = backend.is_in_frustum_batch(tcw, ow, K, Fs[0].bounds, len(sf), log_sf, self.pos, self.normal, self.min_d, self.max_d,
+                                                                 self.max_d, cos_limit)
+            return [(iv[i], u[i], v[i], xr[i], lvl[i], vc[i]) for i in range(len(Fs))]
         R = np.stack([F.Tcw[:3, :3] for F in Fs]).astype(f32)
         t = np.stack([F.Tcw[:3, 3] for F in Fs]).astype(f32)
         Ow = np.stack([F.Ow for F in Fs]).astype(f32)
@@ -229,18 +271,19 @@ class TrackingFrontEnd:
         rng = np.random.Generator(np.random.PCG64(424242))
         keep = self.keepalive = []
         # ---- point side of the caller state (Frame-lite, local-map snapshots) ----
-        frames, maps = [], []
+        maps = []
         lm = LocalMap()
+        Tn = []
         for t in range(n):
             T = np.array(Tcw[t], np.float64)
             if prior_noise:  # pose prior = ground truth + small noise (stand-in for the motion model)
                 T[:3, 3] += rng.normal(0, 0.002, 3)
-            kps, desc = orb[t]
-            F = FrameLite(kps, desc, None, None, depth[t], T.astype(f32), self.K, scale_factors)
-            frames.append(F)
+            Tn.append(T.astype(f32))
+        frames = FrameLite.build_batch(orb, depth, Tn, self.K, scale_factors, self.b)
+        for t in range(n):
             maps.append((lm.pos, lm.desc, lm.normal, lm.max_d, lm.min_d))
             if t % self.kf_every == 0:
-                lm.add_keyframe_points(F)
+                lm.add_keyframe_points(frames[t])
         summary = [dict(frame=t, n_kp=len(frames[t].kps)) for t in range(n)]
         # ---- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ----
         c3_t = list(range(1, n))
@@ -261,7 +304,7 @@ class TrackingFrontEnd:
             while k1 < len(c2_t) and maps[c2_t[k1]][0] is maps[c2_t[k]][0]:
                 k1 += 1
             tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[c2_t[k]][:5]
-            fr += [(tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]])]
+            fr += [(tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]], backend=self.b)]
             k = k1
         r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
         claimed = [None] * n
@@ -353,3 +396,10 @@ class GpuBackend:
 
     def line_search_batch(self, cvs, lvs):
         return self.m.SearchLinesByProjectionBatch(cvs, lvs)
+
+    # F rows (Frame glue): UnprojectStereo / IsInFrustum of many frames in one call
+    def unproject_batch(self, off, xy, z, rwc, ow, K):
+        return self.m.UnprojectBatch(off, xy, z, rwc, ow, K)
+
+    def is_in_frustum_batch(self, *a):
+        return self.m.IsInFrustumBatch(*a)
