@@ -481,6 +481,32 @@ PL_API int pl_frame_is_in_frustum_batch(pl_match* h, int n_frames, const float* 
 PL_API int pl_frame_lines_in_frustum_batch(pl_match* h, int n_frames, const float* tcw, int m, const double* start3d, const double* end3d,
                                            uint8_t* in_view /* n_frames x m */);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * G: Frame::ComputeBoW (Frame.cc:721-735) — DBoW2 TemplatedVocabulary<FORB>::transform(features, mBowVec, mFeatVec, 4)
+ *    (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1194, :1218-1259; FORB::distance FORB.cpp:85-110).  SURVEY.md §8(f)
+ *    rank 1: the same Hamming kernel walks the vocabulary tree (k children per level, first minimum wins) and produces the
+ *    FeatureVector that SearchByBoW consumes, flattened exactly like pl_bow_view.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pl_voc pl_voc;
+/* The tree as loadFromTextFile builds it (TemplatedVocabulary.h:1338-1422): node ids 1..n_nodes in file order (0 = root),
+ * parent[i] < i+1, is_leaf / 32 descriptor bytes / weight per node; word ids are assigned to leaves in file order.
+ * scoring / weighting = the DBoW2 enums (BowVector.h:36-53; ORBvoc.txt: 0 0 = L1_NORM, TF_IDF).  A node has <= 32 children. */
+PL_API int pl_voc_create(pl_voc** out, int device, int k, int L, int scoring, int weighting, int n_nodes, const int* parent,
+                         const uint8_t* is_leaf, const uint8_t* desc, const double* weight);
+/* ORBVocabulary::loadFromTextFile(strVocFile) (System.cc:67).  Blank lines are skipped (the reference turns a trailing blank
+ * line into a node with an uninitialised descriptor). */
+PL_API int pl_voc_load_text(pl_voc** out, int device, const char* filename);
+PL_API void pl_voc_destroy(pl_voc* v);
+PL_API int pl_voc_info(const pl_voc* v, int* k, int* L, int* n_nodes /* incl. root */, int* n_words);
+/* transform() for n_frames frames: frame f owns the descriptor rows [off[f], off[f+1]) (<= 8192 per frame).  All outputs are
+ * segmented like the input: the BowVector of frame f is word_id / word_value[off[f] .. off[f] + n_words[f]) in ascending word
+ * id; its FeatureVector is node_id[off[f] .. off[f] + n_fv_nodes[f]) ascending, node k owning
+ * feat_idx[off[f] + node_off[off[f] + f + k] .. off[f] + node_off[off[f] + f + k + 1]) (frame-relative feature indices,
+ * ascending) — node_off has total + n_frames entries.  A leaf shallower than L - levelsup leaves the reference's nid
+ * uninitialised; here such a feature is filed under node 0. */
+PL_API int pl_voc_transform_batch(pl_voc* v, int n_frames, const int* off, const uint8_t* desc, int levelsup, int* n_words, unsigned int* word_id,
+                                  double* word_value, int* n_fv_nodes, unsigned int* node_id, int* node_off, unsigned int* feat_idx);
+
 #ifdef __cplusplus
 }
 #endif

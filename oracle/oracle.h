@@ -62,6 +62,14 @@ ORC_API int orc_frame_unproject_batch(int n_frames, const int* off, const float*
 ORC_API int orc_frame_is_in_frustum_batch(int n_frames, const float* tcw, const float* ow, float fx, float fy, float cx, float cy, float bf, const float* bounds, int n_levels, float log_scale_factor, int m, const float* world_pos, const float* normal, const float* min_dist_inv, const float* max_dist_inv, const float* max_dist, float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* scale_level, float* view_cos);
 ORC_API int orc_frame_lines_in_frustum_batch(int n_frames, const float* tcw, int m, const double* start3d, const double* end3d, uint8_t* in_view);
 
+/* ---- DBoW2 vocabulary transform (bow_oracle.cpp) ---- */
+typedef struct orc_voc orc_voc;
+ORC_API orc_voc* orc_voc_create(int k, int L, int scoring, int weighting, int n_nodes, const int* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weight);
+ORC_API orc_voc* orc_voc_load_text(const char* filename);
+ORC_API void orc_voc_destroy(orc_voc* v);
+ORC_API int orc_voc_info(const orc_voc* v, int* k, int* L, int* n_nodes, int* n_words);
+ORC_API int orc_voc_transform(const orc_voc* v, const uint8_t* desc, int n, int levelsup, int* n_words, unsigned* word_id, double* word_value, int* n_fv_nodes, unsigned* node_id, int* node_off, unsigned* feat_idx);
+
 /* ---- line extraction (line_oracle.cpp) ---- */
 ORC_API int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t step, int order_mode, float* xyxy, double* width, double* prec, double* nfa, int cap);
 ORC_API int orc_lsd_angles(const uint8_t* img, int rows, int cols, size_t step, double* out, int* ow, int* oh);

@@ -515,6 +515,53 @@ def frame_lines_in_frustum_batch(tcw, start3d, end3d):
     return iv
 
 
+class VocOracle:
+    """CPU restatement of DBoW2's vocabulary transform (bow_oracle.cpp)."""
+
+    def __init__(self):
+        self._h = None
+        lib().orc_voc_create.restype = C.c_void_p
+        lib().orc_voc_load_text.restype = C.c_void_p
+        lib().orc_voc_destroy.argtypes = [C.c_void_p]
+
+    def __del__(self):
+        if self._h:
+            lib().orc_voc_destroy(self._h)
+            self._h = None
+
+    def create(self, k, L, scoring, weighting, parent, is_leaf, desc, weight):
+        parent = np.ascontiguousarray(parent, np.int32)
+        leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        weight = np.ascontiguousarray(weight, np.float64)
+        self._h = C.c_void_p(lib().orc_voc_create(C.c_int(k), C.c_int(L), C.c_int(scoring), C.c_int(weighting), C.c_int(len(parent)), _p(parent), _p(leaf),
+                                                  _p(desc), _p(weight)))
+        assert self._h
+        return self
+
+    def loadFromTextFile(self, filename):
+        h = lib().orc_voc_load_text(str(filename).encode())
+        self._h = C.c_void_p(h) if h else None
+        return bool(h)
+
+    def info(self):
+        k, L, nn, nw = (C.c_int() for _ in range(4))
+        lib().orc_voc_info(self._h, C.byref(k), C.byref(L), C.byref(nn), C.byref(nw))
+        return dict(k=k.value, L=L.value, n_nodes=nn.value, n_words=nw.value)
+
+    def transform(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        cap = max(n, 1)
+        wid, nid, fi = (np.zeros(cap, np.uint32) for _ in range(3))
+        wv = np.zeros(cap, np.float64)
+        noff = np.zeros(cap + 1, np.int32)
+        nw, nn = C.c_int(), C.c_int()
+        lib().orc_voc_transform(self._h, _p(d), C.c_int(n), C.c_int(levelsup), C.byref(nw), _p(wid), _p(wv), C.byref(nn), _p(nid), _p(noff), _p(fi))
+        fv = {int(nid[k]): [int(x) for x in fi[noff[k]:noff[k + 1]]] for k in range(nn.value)}
+        return (wid[:nw.value].copy(), wv[:nw.value].copy()), fv
+
+
 class OracleBackend:
     """CPU-oracle backend for frontend.TrackingFrontEnd (same interface as frontend.GpuBackend)."""
 

@@ -595,3 +595,71 @@ class DescriptorMatcher:
         iv = np.zeros((len(tcw), len(s3)), np.uint8)
         check(N.lib().pl_frame_lines_in_frustum_batch(self._h, C.c_int(len(tcw)), ptr(tcw), C.c_int(len(s3)), ptr(s3), ptr(e3), ptr(iv)))
         return iv
+
+
+class ORBVocabulary:
+    """Mirror of ORB_SLAM2::ORBVocabulary (DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) for the one call on the hot path:
+    transform(features, BowVector, FeatureVector, levelsup) — Frame::ComputeBoW (Frame.cc:721-735)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib().pl_voc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def create(self, k, L, scoring, weighting, parent, is_leaf, desc, weight):
+        """The tree as loadFromTextFile builds it: node i+1 has parent[i] (0 = root), in file order."""
+        self.close()
+        parent = np.ascontiguousarray(parent, np.int32)
+        leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        weight = np.ascontiguousarray(weight, np.float64)
+        check(N.lib().pl_voc_create(C.byref(self._h), C.c_int(self._device), C.c_int(k), C.c_int(L), C.c_int(scoring), C.c_int(weighting),
+                                    C.c_int(len(parent)), ptr(parent), ptr(leaf), ptr(desc), ptr(weight)))
+        return self
+
+    def loadFromTextFile(self, filename):
+        self.close()
+        rc = N.lib().pl_voc_load_text(C.byref(self._h), C.c_int(self._device), str(filename).encode())
+        if rc == N.PL_ERR_ARG:
+            return False          # the reference returns false on a file it cannot parse
+        check(rc)
+        return True
+
+    def info(self):
+        k, L, nn, nw = (C.c_int() for _ in range(4))
+        check(N.lib().pl_voc_info(self._h, C.byref(k), C.byref(L), C.byref(nn), C.byref(nw)))
+        return dict(k=k.value, L=L.value, n_nodes=nn.value, n_words=nw.value)
+
+    def transform_batch(self, descs, levelsup=4):
+        """descs: list of (n_i, 32) uint8 arrays -> list of (BowVector as (word_id, word_value), FeatureVector as dict node -> [features])."""
+        counts = [len(d) for d in descs]
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        tot, nf = int(off[-1]), len(descs)
+        allv = np.concatenate([np.ascontiguousarray(d, np.uint8).reshape(-1, 32) for d in descs]) if tot else np.zeros((0, 32), np.uint8)
+        cap = max(tot, 1)
+        nw, nn = np.zeros(max(nf, 1), np.int32), np.zeros(max(nf, 1), np.int32)
+        wid, nid, fi = (np.zeros(cap, np.uint32) for _ in range(3))
+        wv = np.zeros(cap, np.float64)
+        noff = np.zeros(cap + nf, np.int32)
+        check(N.lib().pl_voc_transform_batch(self._h, C.c_int(nf), ptr(off), ptr(allv), C.c_int(levelsup), ptr(nw), ptr(wid), ptr(wv), ptr(nn), ptr(nid),
+                                             ptr(noff), ptr(fi)))
+        out = []
+        for f in range(nf):
+            o = int(off[f])
+            no = noff[o + f:o + f + nn[f] + 1]
+            fv = {int(nid[o + k]): [int(x) for x in fi[o + no[k]:o + no[k + 1]]] for k in range(nn[f])}
+            out.append(((wid[o:o + nw[f]].copy(), wv[o:o + nw[f]].copy()), fv))
+        return out
+
+    def transform(self, desc, levelsup=4):
+        return self.transform_batch([desc], levelsup)[0]

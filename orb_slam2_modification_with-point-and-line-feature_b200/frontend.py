@@ -51,14 +51,14 @@ class FrameLite:
         self.set_lines(kls, ldesc)
 
     @staticmethod
-    def build_batch(orb, depth, Tcw, K, scale_factors, backend):
-        """The Frame constructors of a whole sequence: ComputeStereoFromRGBD as one gather over all key points, UnprojectStereo
-        of every frame through the backend's batched F3 call (pl_frame_unproject_batch / its oracle twin) — the same arithmetic
-        for both arms."""
+    def build_batch(orb, depth, Tcw, K, scale_factors, backend=None):
+        """The Frame constructors of a whole sequence: ComputeStereoFromRGBD as one gather over all key points and UnprojectStereo
+        of every frame in one pass — through the backend's batched F3 call (pl_frame_unproject_batch / its oracle twin) when a
+        backend is given, else in numpy (same formula; used while the device is saturated by the line extractor)."""
         n = len(orb)
         counts = np.array([len(o[0]) for o in orb], np.int64)
         off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-        if n == 0 or not isinstance(depth, np.ndarray) or depth.ndim != 3 or not hasattr(backend, "unproject_batch"):
+        if n == 0 or not isinstance(depth, np.ndarray) or depth.ndim != 3:
             return [FrameLite(orb[t][0], orb[t][1], None, None, depth[t], Tcw[t], K, scale_factors) for t in range(n)]
         x = np.concatenate([o[0]["x"] for o in orb])
         y = np.concatenate([o[0]["y"] for o in orb])
@@ -73,7 +73,11 @@ class FrameLite:
                   for t in range(n)]
         rwc = np.stack([F.Rwc for F in frames])
         ow = np.stack([F.Ow for F in frames])
-        world, _ = backend.unproject_batch(off, np.stack([x, y], 1), dd, rwc, ow, K)
+        if backend is not None and hasattr(backend, "unproject_batch"):
+            world, _ = backend.unproject_batch(off, np.stack([x, y], 1), dd, rwc, ow, K)
+        else:
+            pc = np.stack([(x - f32(K["cx"])) * dd * f32(1.0 / K["fx"]), (y - f32(K["cy"])) * dd * f32(1.0 / K["fy"]), dd], 1).astype(f32)
+            world = (np.einsum("nij,nj->ni", rwc[fidx], pc) + ow[fidx]).astype(f32)
         for t, F in enumerate(frames):
             F._world = world[off[t]:off[t + 1]]
         return frames
@@ -248,10 +252,15 @@ class TrackingFrontEnd:
     (`batch=True`, the offline / throughput mode) or frame by frame (`batch=False`, the streaming mode).  Both modes
     run the same searches on the same inputs and return the same summary."""
 
-    def __init__(self, backend, K=TUM1, keyframe_every=10):
+    def __init__(self, backend, K=TUM1, keyframe_every=10, device_glue=False):
+        """device_glue: run the Frame glue (UnprojectStereo, IsInFrustum) through the backend's batched F-row calls instead of
+        numpy.  Off by default for the throughput runs: while the ordered LSD stage owns every SM, work queued on the device
+        waits for it, whereas the host cores are idle — the numpy path overlaps the line extraction, the device path queues
+        behind it (tools/prof_e2e.py shows both timelines)."""
         self.b = backend
         self.K = K
         self.kf_every = keyframe_every
+        self.device_glue = device_glue
         self.keepalive = []  # arrays referenced by the views handed to the backend (views hold raw addresses)
 
     @staticmethod
@@ -279,7 +288,7 @@ class TrackingFrontEnd:
             if prior_noise:  # pose prior = ground truth + small noise (stand-in for the motion model)
                 T[:3, 3] += rng.normal(0, 0.002, 3)
             Tn.append(T.astype(f32))
-        frames = FrameLite.build_batch(orb, depth, Tn, self.K, scale_factors, self.b)
+        frames = FrameLite.build_batch(orb, depth, Tn, self.K, scale_factors, self.b if self.device_glue else None)
         for t in range(n):
             maps.append((lm.pos, lm.desc, lm.normal, lm.max_d, lm.min_d))
             if t % self.kf_every == 0:
@@ -304,7 +313,7 @@ class TrackingFrontEnd:
             while k1 < len(c2_t) and maps[c2_t[k1]][0] is maps[c2_t[k]][0]:
                 k1 += 1
             tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[c2_t[k]][:5]
-            fr += [(tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]], backend=self.b)]
+            fr += [(tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]], backend=self.b if self.device_glue else None)]
             k = k1
         r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
         claimed = [None] * n

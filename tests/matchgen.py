@@ -291,3 +291,45 @@ def frustum_case(rng, n_frames, m, K):
     normal += rng.normal(0, 0.6, normal.shape)
     normal /= np.maximum(np.linalg.norm(normal, axis=1, keepdims=True), 1e-9)
     return T.reshape(n_frames, 12).astype(np.float32), ow.astype(np.float32), Xw, normal.astype(np.float32), min_inv, max_inv, max_raw
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# G row: a synthetic DBoW2 vocabulary (hierarchical clusters of binary descriptors) in loadFromTextFile's node order
+# ---------------------------------------------------------------------------------------------------------------
+def make_vocabulary(rng, k, L, leaf_depth_jitter=True, stop_frac=0.05):
+    """Returns (parent, is_leaf, desc, weight) for nodes 1..n in breadth-first file order; children are noisy copies of the parent."""
+    parent, leaf, desc, weight = [], [], [], []
+    level = [(0, rng.integers(0, 256, 32, dtype=np.uint8))]
+    for depth in range(1, L + 1):
+        nxt = []
+        for pid, pdesc in level:
+            for _ in range(k):
+                d = noisy(pdesc[None, :], rng, 0.18 / depth)[0]
+                parent.append(pid)
+                is_leaf = depth == L or (leaf_depth_jitter and depth >= 2 and rng.random() < 0.04)
+                leaf.append(is_leaf)
+                desc.append(d)
+                weight.append(0.0 if (is_leaf and rng.random() < stop_frac) else float(rng.uniform(0.5, 9.0)) if is_leaf else 0.0)
+                nid = len(parent)
+                if not is_leaf:
+                    nxt.append((nid, d))
+        level = nxt
+    return np.asarray(parent, np.int32), np.asarray(leaf, np.uint8), np.stack(desc), np.asarray(weight, np.float64)
+
+
+def write_vocabulary_text(path, k, L, scoring, weighting, parent, leaf, desc, weight):
+    """TemplatedVocabulary::saveToTextFile (TemplatedVocabulary.h:1426-1452) format."""
+    with open(path, "w") as f:
+        f.write(f"{k} {L}  {scoring} {weighting}\n")
+        for i in range(len(parent)):
+            f.write(f"{parent[i]} {int(leaf[i])} " + " ".join(str(int(b)) for b in desc[i]) + f" {float(weight[i])!r}\n")
+
+
+def vocabulary_features(rng, desc, leaf, n):
+    """n query descriptors: noisy copies of random leaves (so that several features share a word) + a few random rows."""
+    leaves = np.nonzero(leaf)[0]
+    src = leaves[rng.integers(0, len(leaves), n) % max(len(leaves) // 3, 1)]
+    q = noisy(desc[src], rng, 0.03)
+    if n > 4:
+        q[:: 7] = rng.integers(0, 256, q[:: 7].shape, dtype=np.uint8)
+    return q

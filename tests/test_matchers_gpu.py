@@ -77,6 +77,25 @@ def test_sequence_matchers_bit_exact(seq, feats, api, oracle, pkg):
     assert any(r.get("d5_matches", 0) > 5 for r in so)
 
 
+def test_sequence_with_device_glue_bit_exact(seq, feats, api, oracle, pkg):
+    """The same schedule with the Frame glue (UnprojectStereo, IsInFrustum) on the device (F rows): both arms still agree
+    bit for bit, and the searches still match."""
+    fe = importlib.import_module(PKG + ".frontend")
+    gray, depth, T = seq
+    ob = Recorder(oracle.OracleBackend())
+    sf = ob.b.scale_factors()
+    so = fe.TrackingFrontEnd(ob, device_glue=True).run(gray, depth, T, sf, features=feats, batch=False)
+    ref = _flatten([x for x in ob.log if x[0].startswith(("search", "line_search"))])
+    gb = Recorder(fe.GpuBackend(api, 480, 640))
+    sg = fe.TrackingFrontEnd(gb, device_glue=True).run(gray, depth, T, sf, features=feats, batch=True)
+    assert sg == so
+    got = _flatten([x for x in gb.log if x[0].startswith(("search", "line_search"))])
+    assert len(got) == len(ref) > 30
+    for (kg, rg), (ko, ro) in zip(got, ref):
+        assert kg == ko and np.array_equal(rg[0], ro[0]) and tuple(rg[1:]) == tuple(ro[1:]), kg
+    assert sum(r.get("c2_matches", 0) for r in so) > 200 and sum(r.get("c3_matches", 0) for r in so) > 1000
+
+
 def test_batch_with_ragged_and_empty_instances(api, oracle, synth):
     """Batched searches with instances of different sizes, including empty frames / empty point sets."""
     N = api.N
