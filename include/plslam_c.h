@@ -122,6 +122,11 @@ PL_API void* pl_orb_stream(pl_orb* h);
 PL_API int pl_orb_pyramid_dims(const pl_orb* h, int level, int* rows, int* cols);
 PL_API int pl_orb_pyramid_read(pl_orb* h, int frame, int level, uint8_t* out, size_t out_step);
 
+/* The same level as a DEVICE pointer to the un-bordered image (pixel (0,0) of mvImagePyramid[level]; the 19-pixel border lies
+ * around it in the same allocation, row pitch `pitch` bytes) — for consumers that stay on the device (pl_frame_compute_stereo_matches).
+ * Valid until the next extract call on the handle; after the device-pointer extract call pl_orb_sync first. */
+PL_API int pl_orb_pyramid_dev(pl_orb* h, int frame, int level, const uint8_t** d_image, size_t* pitch, int* rows, int* cols);
+
 /* Debug / test hook: the ordered FAST candidate list handed to DistributeOctTree for (frame, level) of the last
  * extract call (ORBextractor.cc:779-829: vToDistributeKeys), coordinates relative to minBorder. */
 PL_API int pl_orb_candidates_read(pl_orb* h, int frame, int level, float* xs, float* ys, float* responses, int cap,
@@ -480,6 +485,15 @@ PL_API int pl_frame_is_in_frustum_batch(pl_match* h, int n_frames, const float* 
  * the camera.  start3d / end3d = m x 3 doubles (MapLine::mStart3d / mEnd3d), converted to float as the reference does. */
 PL_API int pl_frame_lines_in_frustum_batch(pl_match* h, int n_frames, const float* tcw, int m, const double* start3d, const double* end3d,
                                            uint8_t* in_view /* n_frames x m */);
+
+/* F5: Frame::ComputeStereoMatches (Frame.cc:888-1062): per left key point the best right key point in
+ * its row band (Hamming, level +-1, disparity range), the 11x11 SAD sub-pixel refinement over 11 shifts read from BOTH
+ * extractors' mvImagePyramid (which never leaves the device), and the final 1.5*1.4*median outlier rule.  left / right = the two
+ * extractors after operator() on the rectified pair (frame `frame` of their last call); keys = mvKeys / mvKeysRight (image
+ * coordinates), bf = mbf, b = mb.  u_right / depth = mvuRight / mvDepth (-1 = no match).  n_left, n_right <= 16384. */
+PL_API int pl_frame_compute_stereo_matches(pl_match* h, pl_orb* left, pl_orb* right, int frame, const pl_keypoint* keys_left,
+                                           const uint8_t* desc_left, int n_left, const pl_keypoint* keys_right, const uint8_t* desc_right,
+                                           int n_right, float bf, float b, float* u_right, float* depth);
 
 /* ------------------------------------------------------------------------------------------------------------
  * G: Frame::ComputeBoW (Frame.cc:721-735) — DBoW2 TemplatedVocabulary<FORB>::transform(features, mBowVec, mFeatVec, 4)

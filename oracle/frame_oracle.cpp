@@ -162,3 +162,116 @@ extern "C" int orc_frame_lines_in_frustum_batch(int n_frames, const float* tcw, 
     }
     return 0;
 }
+
+// Frame::ComputeStereoMatches — src/Frame.cc:888-1062.  left / right = the two extractors after
+// operator() on the rectified pair (their mvImagePyramid is read, Frame.cc:895,985,997,1002).
+#include <algorithm>
+#include <climits>
+#include <utility>
+#include <vector>
+extern "C" int orc_frame_compute_stereo_matches(const orc_orb* left, const orc_orb* right, const pl_keypoint* keysL, const uint8_t* descL, int N,
+                                                const pl_keypoint* keysR, const uint8_t* descR, int Nr, float mbf, float mb, float* mvuRight,
+                                                float* mvDepth) {
+    float sf[32], invsf[32], s2[32], is2[32];
+    int perLevel[32], umax[32];
+    orc_orb_tables(left, sf, invsf, s2, is2, perLevel, umax);
+    struct Lvl { int w, h; std::vector<uint8_t> px; };  // bordered plane, the image is the ROI at (19, 19)
+    std::vector<Lvl> pl, pr;
+    for (int side = 0; side < 2; side++) {
+        const orc_orb* o = side ? right : left;
+        std::vector<Lvl>& v = side ? pr : pl;
+        for (int l = 0;; l++) {
+            int w, h;
+            if (orc_orb_level_dims(o, l, &w, &h) != 0) break;
+            Lvl L{w, h, std::vector<uint8_t>((size_t)(w + 38) * (h + 38))};
+            orc_orb_level_bordered(o, l, L.px.data());
+            v.push_back(std::move(L));
+        }
+    }
+    auto at = [](const Lvl& L, int r, int c) -> float { return (float)L.px[(size_t)(r + 19) * (L.w + 38) + (c + 19)]; };
+    for (int i = 0; i < N; i++) { mvuRight[i] = -1.0f; mvDepth[i] = -1.0f; }
+    if (pl.empty() || pr.empty()) return 0;
+    const int thOrbDist = (100 + 50) / 2;
+    const int nRows = pl[0].h;
+    std::vector<std::vector<size_t>> vRowIndices(nRows);
+    for (int iR = 0; iR < Nr; iR++) {
+        const float kpY = keysR[iR].y;
+        const float r = 2.0f * sf[keysR[iR].octave];
+        const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++)
+            if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);  // the reference writes out of bounds otherwise
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < N; iL++) {
+        const pl_keypoint& kpL = keysL[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y, uL = kpL.x;
+        if (!(vL >= 0 && (int)vL < nRows)) continue;
+        const std::vector<size_t>& vCandidates = vRowIndices[(size_t)vL];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = 100;
+        size_t bestIdxR = 0;
+        const uint8_t* dL = descL + 32 * (size_t)iL;
+        for (size_t iR : vCandidates) {
+            const pl_keypoint& kpR = keysR[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = orc_descriptor_distance(dL, descR + 32 * iR);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = keysR[bestIdxR].x;
+            const float scaleFactor = invsf[kpL.octave];
+            const float scaleduL = std::round(kpL.x * scaleFactor);
+            const float scaledvL = std::round(kpL.y * scaleFactor);
+            const float scaleduR0 = std::round(uR0 * scaleFactor);
+            const int w = 5;
+            const Lvl& IL = pl[kpL.octave];
+            const Lvl& IRl = pr[kpL.octave];
+            const int r0 = (int)(scaledvL - w), c0 = (int)(scaleduL - w);
+            const float cL = at(IL, r0 + w, c0 + w);
+            int bestDistS = INT_MAX, bestincR = 0;
+            const int L = 5;
+            float vDists[2 * 5 + 1];
+            const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= IRl.w) continue;
+            for (int incR = -L; incR <= +L; incR++) {
+                const int cr0 = (int)(scaleduR0 + incR - w);
+                const float cR = at(IRl, r0 + w, cr0 + w);
+                double acc = 0;  // cv::norm(IL, IR, NORM_L1) of CV_32F: double accumulation of |a - b|
+                for (int y = 0; y < 2 * w + 1; y++)
+                    for (int x = 0; x < 2 * w + 1; x++) acc += std::fabs((at(IL, r0 + y, c0 + x) - cL) - (at(IRl, r0 + y, cr0 + x) - cR));
+                const float dist = (float)acc;
+                if (dist < bestDistS) { bestDistS = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = sf[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                mvDepth[iL] = mbf / disparity;
+                mvuRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return 0;  // the reference indexes an empty vector here
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+        if (vDistIdx[i].first < thDist) break;
+        mvuRight[vDistIdx[i].second] = -1;
+        mvDepth[vDistIdx[i].second] = -1;
+    }
+    return 0;
+}

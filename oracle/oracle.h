@@ -60,6 +60,7 @@ ORC_API int orc_frame_undistort_points(const float* xy, int n, float fx, float f
 ORC_API int orc_frame_stereo_from_rgbd_batch(int n_frames, const float* depth, int rows, int cols, size_t step_bytes, size_t frame_stride_bytes, const int* off, const float* xy, const float* x_un, float bf, float* depth_out, float* u_right_out);
 ORC_API int orc_frame_unproject_batch(int n_frames, const int* off, const float* xy_un, const float* z, const float* rwc, const float* ow, float fx, float fy, float cx, float cy, float* world, uint8_t* valid);
 ORC_API int orc_frame_is_in_frustum_batch(int n_frames, const float* tcw, const float* ow, float fx, float fy, float cx, float cy, float bf, const float* bounds, int n_levels, float log_scale_factor, int m, const float* world_pos, const float* normal, const float* min_dist_inv, const float* max_dist_inv, const float* max_dist, float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* scale_level, float* view_cos);
+ORC_API int orc_frame_compute_stereo_matches(const orc_orb* left, const orc_orb* right, const pl_keypoint* keysL, const uint8_t* descL, int N, const pl_keypoint* keysR, const uint8_t* descR, int Nr, float mbf, float mb, float* mvuRight, float* mvDepth);
 ORC_API int orc_frame_lines_in_frustum_batch(int n_frames, const float* tcw, int m, const double* start3d, const double* end3d, uint8_t* in_view);
 
 /* ---- DBoW2 vocabulary transform (bow_oracle.cpp) ---- */

@@ -515,6 +515,18 @@ def frame_lines_in_frustum_batch(tcw, start3d, end3d):
     return iv
 
 
+def frame_compute_stereo_matches(left, right, keys_left, desc_left, keys_right, desc_right, bf, b):
+    """left / right: OrbOracle objects after extract() on the rectified pair."""
+    kl = np.ascontiguousarray(keys_left, KP_DTYPE)
+    kr = np.ascontiguousarray(keys_right, KP_DTYPE)
+    dl, dr = _rows(desc_left), _rows(desc_right)
+    ur = np.empty(max(len(kl), 1), np.float32)
+    d = np.empty(max(len(kl), 1), np.float32)
+    lib().orc_frame_compute_stereo_matches(left._h, right._h, _p(kl), _p(dl), C.c_int(len(kl)), _p(kr), _p(dr), C.c_int(len(kr)),
+                                           C.c_float(bf), C.c_float(b), _p(ur), _p(d))
+    return ur[:len(kl)], d[:len(kl)]
+
+
 class VocOracle:
     """CPU restatement of DBoW2's vocabulary transform (bow_oracle.cpp)."""
 

@@ -588,6 +588,18 @@ class DescriptorMatcher:
                                                    ptr(pxr), ptr(lv), ptr(vc)))
         return iv, px, py, pxr, lv, vc
 
+    def ComputeStereoMatches(self, left, right, keys_left, desc_left, keys_right, desc_right, bf, b, frame=0):
+        """Frame::ComputeStereoMatches: left / right = the two ORBextractor objects after their extract call on the rectified pair
+        -> (mvuRight, mvDepth)."""
+        kl = np.ascontiguousarray(keys_left, N.KP_DTYPE)
+        kr = np.ascontiguousarray(keys_right, N.KP_DTYPE)
+        dl, dr = self._rows(desc_left), self._rows(desc_right)
+        ur = np.empty(max(len(kl), 1), np.float32)
+        d = np.empty(max(len(kl), 1), np.float32)
+        check(N.lib().pl_frame_compute_stereo_matches(self._h, left._h, right._h, C.c_int(frame), ptr(kl), ptr(dl), C.c_int(len(kl)), ptr(kr), ptr(dr),
+                                                      C.c_int(len(kr)), C.c_float(bf), C.c_float(b), ptr(ur), ptr(d)))
+        return ur[:len(kl)], d[:len(kl)]
+
     def LinesInFrustumBatch(self, tcw, start3d, end3d):
         tcw = np.ascontiguousarray(tcw, np.float32).reshape(-1, 12)
         s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)

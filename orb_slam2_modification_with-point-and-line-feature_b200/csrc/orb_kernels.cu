@@ -1404,6 +1404,20 @@ PL_API int pl_orb_pyramid_read(pl_orb* h, int frame, int level, uint8_t* out, si
     return PL_OK;
 }
 
+PL_API int pl_orb_pyramid_dev(pl_orb* h, int frame, int level, const uint8_t** d_image, size_t* pitch, int* rows, int* cols) {
+    PL_CHECK_ARG(h && d_image && pitch && level >= 0 && level < h->nlevels);
+    if (frame < 0 || frame >= h->last_batch) {
+        set_error("no extract result for frame %d", frame);
+        return PL_ERR_STATE;
+    }
+    const LevelGeom& L = h->geom.lv[level];
+    *d_image = h->d_pyr + L.plane_off + (size_t)frame * L.plane_size + (size_t)kEdge * L.pitch + kEdge;
+    *pitch = L.pitch;
+    if (rows) *rows = L.h;
+    if (cols) *cols = L.w;
+    return PL_OK;
+}
+
 PL_API int pl_orb_blurred_read(pl_orb* h, int frame, int level, uint8_t* out, size_t out_step) {
     PL_CHECK_ARG(h && out && level >= 0 && level < h->nlevels);
     if (frame < 0 || frame >= h->last_batch) {

@@ -333,3 +333,18 @@ def vocabulary_features(rng, desc, leaf, n):
     if n > 4:
         q[:: 7] = rng.integers(0, 256, q[:: 7].shape, dtype=np.uint8)
     return q
+
+
+def stereo_pair(synth, seed, w=640, h=480):
+    """A rectified pair: the right image is the left one seen with a disparity that grows towards the bottom of the image
+    (8 .. 40 px, piecewise constant in bands of rows, sub-pixel by linear interpolation) + independent sensor noise."""
+    left = synth.frame(seed, w, h)
+    rng = np.random.default_rng(seed)
+    right = np.empty_like(left)
+    xs = np.arange(w, dtype=np.float64)
+    for y0 in range(0, h, 40):
+        d = 8.0 + 32.0 * y0 / h + 0.37
+        for y in range(y0, min(y0 + 40, h)):
+            right[y] = np.clip(np.rint(np.interp(xs + d, xs, left[y].astype(np.float64))), 0, 255).astype(np.uint8)
+    right = np.clip(right.astype(np.int16) + rng.integers(-2, 3, right.shape), 0, 255).astype(np.uint8)
+    return left, right

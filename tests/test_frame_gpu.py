@@ -103,3 +103,43 @@ def test_frustum_feeds_local_point_search(api, oracle, synth):
     g = dm.SearchByProjectionLocalPoints(fv, mv, 3.0, 0.8)
     o = oracle.search_local_points(fv, mv, 3.0, 0.8)
     assert np.array_equal(g[0], o[0]) and g[1] == o[1] and o[1] > 200
+
+
+@pytest.mark.parametrize("seed,nfeat,size", [(1000, 1000, (640, 480)), (1001, 2000, (640, 480)), (3000, 2000, (1241, 376))])
+def test_compute_stereo_matches(seed, nfeat, size, api, oracle, synth):
+    """F5: row-band Hamming search + SAD refinement on the device-resident pyramids of both extractors, vs the oracle."""
+    w, h = size
+    left, right = matchgen.stereo_pair(synth, seed, w, h)
+    el = api.ORBextractor(nfeat, 1.2, 8, 20, 7, max_cols=w, max_rows=h)
+    er = api.ORBextractor(nfeat, 1.2, 8, 20, 7, max_cols=w, max_rows=h)
+    kl, dl = el(left)
+    kr, dr = er(right)
+    ol, orr = oracle.OrbOracle(nfeat), oracle.OrbOracle(nfeat)
+    okl, odl = ol.extract(left)
+    okr, odr = orr.extract(right)
+    assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
+    K = synth.TUM1
+    b = float(f32(K["bf"]) / f32(K["fx"]))
+    g = api.DescriptorMatcher().ComputeStereoMatches(el, er, kl, dl, kr, dr, K["bf"], b)
+    o = oracle.frame_compute_stereo_matches(ol, orr, okl, odl, okr, odr, K["bf"], b)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1])
+    assert (o[0] >= 0).sum() > 150
+
+
+def test_compute_stereo_matches_degenerate(api, oracle, synth):
+    """No right key points / identical images (zero disparity -> the 0.01 clamp of Frame.cc:1045-1049)."""
+    img = synth.frame(1000, 640, 480)
+    el, er = api.ORBextractor(1000, 1.2, 8, 20, 7), api.ORBextractor(1000, 1.2, 8, 20, 7)
+    kl, dl = el(img)
+    kr, dr = er(img)
+    ol, orr = oracle.OrbOracle(1000), oracle.OrbOracle(1000)
+    ol.extract(img)
+    orr.extract(img)
+    dm = api.DescriptorMatcher()
+    K = synth.TUM1
+    b = float(f32(K["bf"]) / f32(K["fx"]))
+    g = dm.ComputeStereoMatches(el, er, kl, dl, kr, dr, K["bf"], b)
+    o = oracle.frame_compute_stereo_matches(ol, orr, kl, dl, kr, dr, K["bf"], b)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and (o[0] >= 0).sum() > 500
+    g = dm.ComputeStereoMatches(el, er, kl, dl, kr[:0], dr[:0], K["bf"], b)
+    assert np.all(g[0] == -1) and np.all(g[1] == -1)

@@ -83,3 +83,22 @@ def test_is_in_frustum_vs_numpy(oracle, synth):
         zs = (s3.astype(f32).astype(np.float64) @ T[f, 2, :3].astype(np.float64) + np.float64(T[f, 2, 3])).astype(f32)
         ze = (e3.astype(f32).astype(np.float64) @ T[f, 2, :3].astype(np.float64) + np.float64(T[f, 2, 3])).astype(f32)
         assert np.array_equal(li[f].astype(bool), ~((zs < 0) & (ze < 0)))
+
+
+def test_compute_stereo_matches_recovers_the_disparity(oracle, synth):
+    """Frame::ComputeStereoMatches on a synthetic rectified pair with known disparity bands: the oracle's sub-pixel uRight must
+    sit on the true disparity for the bulk of the matches, depth = bf / disparity, and the outlier rule must have run."""
+    left, right = matchgen.stereo_pair(synth, 1000)
+    ol, orr = oracle.OrbOracle(1000), oracle.OrbOracle(1000)
+    kl, dl = ol.extract(left)
+    kr, dr = orr.extract(right)
+    K = synth.TUM1
+    b = float(f32(K["bf"]) / f32(K["fx"]))
+    ur, dep = oracle.frame_compute_stereo_matches(ol, orr, kl, dl, kr, dr, K["bf"], b)
+    ok = ur >= 0
+    assert ok.sum() > 150 and (~ok).sum() > 50
+    true_d = 8.0 + 32.0 * (np.floor(kl["y"][ok] / 40) * 40) / 480 + 0.37
+    err = np.abs((kl["x"][ok] - ur[ok]) - true_d)
+    assert np.median(err) < 0.6 and (err < 2.0).mean() > 0.85
+    assert np.array_equal(dep[ok], (f32(K["bf"]) / (kl["x"][ok] - ur[ok])).astype(f32))
+    assert np.all(dep[~ok] == -1)
