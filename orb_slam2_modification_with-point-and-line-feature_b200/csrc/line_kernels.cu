@@ -1405,17 +1405,30 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                 } else {
                     const unsigned int* rg = buf >= 0 ? my_pool_reg + (size_t)buf * kSpecCap : my_small + (size_t)(h % kSlots) * 2 * kSmall;
                     bool redo = status < 0;
+                    // This section is serial per frame, and a region's points, log and rectangle live in global memory: the three
+                    // reads are issued together (one round trip instead of three dependent ones); the first 32 entries of the two
+                    // lists — all of them for most regions — and the rectangle (24 words, one per lane) stay in registers.
+                    unsigned rg0 = 0, tk0 = 0, rc0 = 0;
                     if (!redo) {
                         const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
+                        if (lane < nt) tk0 = tk[lane];
+                        if (lane < n) rg0 = rg[lane];
+                        if (status == kStRect && lane < (int)(sizeof(LsdRect) / 4))
+                            rc0 = reinterpret_cast<const unsigned int*>(buf >= 0 ? &my_pool_rect[buf] : &my_small_rect[h % kSlots])[lane];
                         bool conflict = false;
+                        if (lane < nt) {
+                            const unsigned o = (tk0 >> 16) * (unsigned)g.W + (tk0 & 0xffffu);
+                            conflict = ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
+                        }
                         #pragma unroll 1
-                        for (int i = lane; i < nt; i += 32) {
+                        for (int i = lane + 32; i < nt; i += 32) {
                             const unsigned pp = tk[i];
                             const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
                             conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
                         }
                         redo = __any_sync(FULL, conflict);
                     }
+                    const bool regrown = redo;
                     LsdRect rec;
                     if (redo) {  // everything before this ticket is committed: this growth is the sequential one
                         const long long g0 = clock64();
@@ -1441,12 +1454,14 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                             ctl->stat[2]++;
                             ctl->stat[7] += (unsigned long long)(clock64() - g0);
                         }
-                    } else if (status == kStRect) {
-                        rec = buf >= 0 ? my_pool_rect[buf] : my_small_rect[h % kSlots];
                     }
                     if (status >= 0) {
+                        if (!regrown && lane < n) {
+                            const unsigned o = (rg0 >> 16) * (unsigned)g.W + (rg0 & 0xffffu);
+                            atomicOr(&s_used[o >> 5], 1u << (o & 31));
+                        }
                         #pragma unroll 1
-                        for (int i = lane; i < n; i += 32) {
+                        for (int i = regrown ? lane : lane + 32; i < n; i += 32) {
                             const unsigned pp = rg[i];
                             const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
                             atomicOr(&s_used[o >> 5], 1u << (o & 31));
@@ -1454,10 +1469,12 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                         if (status == kStRect) {
                             const int head = __shfl_sync(FULL, ctl->head, 0);
                             if (head < g.seg_cap) {
-                                if (lane == 0) {
-                                    q[head].rec = rec;
-                                    ctl->head = head + 1;
+                                if (regrown) {
+                                    if (lane == 0) q[head].rec = rec;
+                                } else if (lane < (int)(sizeof(LsdRect) / 4)) {
+                                    reinterpret_cast<unsigned int*>(&q[head].rec)[lane] = rc0;
                                 }
+                                if (lane == 0) ctl->head = head + 1;
                             } else if (lane == 0) {
                                 atomicOr(B.flags + f, 1);
                             }
