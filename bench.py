@@ -131,7 +131,7 @@ class MatchPlan:
     def record(self, name, *args):
         self.calls.append((name, args))
         r = getattr(self.gb, name)(*args)
-        self.launches += self.gb.m.last_launches()
+        self.launches += (self.gb.ml if name.startswith("line_") else self.gb.m).last_launches()
         return r
 
     def replay(self, which=None):
@@ -224,6 +224,7 @@ def run_ours(a, rank, world, local_rank, dist):
         gb.line.sync()
         plan.replay("lines")
         gb.m.sync()
+        gb.ml.sync()
 
     e2e_fe = fe.TrackingFrontEnd(gb)
 
@@ -295,6 +296,7 @@ def run_ours(a, rank, world, local_rank, dist):
     t1 = time.perf_counter()
     plan.replay()
     gb.m.sync()
+    gb.ml.sync()
     t_match = time.perf_counter() - t1
     # ---- dominant-kernel timing (CUDA events on the launching stream, inside the same process) ----
     N.check(N.lib().pl_line_set_profiling(gb.line._h, 1))
@@ -401,7 +403,7 @@ def run_ours(a, rank, world, local_rank, dist):
         "step_breakdown_ms": {"extract": round(t_ext * 1e3, 2), "match": round(t_match * 1e3, 2), "matcher_calls": len(plan.calls)},
         "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(F * W * H),
                 "d2h_bytes_per_step": int(F * (cap * 60 + MAXL * (68 + 32 + 24) + 8)), "steps": e2e_steps,
-                "note": "host images uploaded once, both extractors through the device-pointer C ABI on their own streams, results read back to pinned host memory; numpy caller glue (Frame-lite) overlapping the line extractor; matcher calls with host arrays"},
+                "note": "host images uploaded once, both extractors through the device-pointer C ABI on their own streams, results read back to pinned host memory; numpy caller glue (Frame-lite) overlapping the line extractor; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
         "gpu_launches": int(launches_per_step * a.steps),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "matches_per_frame": {"c3": round(float(np.mean([r.get("c3_matches", 0) for r in summary])), 1),

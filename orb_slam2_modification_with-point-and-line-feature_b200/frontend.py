@@ -315,20 +315,40 @@ class TrackingFrontEnd:
             tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[c2_t[k]][:5]
             fr += [(tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]], backend=self.b if self.device_glue else None)]
             k = k1
-        r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
-        claimed = [None] * n
-        for t, (m3, n3) in zip(c3_t, r3):
-            summary[t].update(c3_matches=n3, c3_sum=self._chk(m3))
-            claimed[t] = (m3 >= 0).astype(np.int32)
-        # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
-        fvs, mvs, inview = [], [], []
-        for t, (mdesc, inv, u, v, xr, lvl, vc) in zip(c2_t, fr):
-            fvs.append(frames[t].view(claimed[t], keep))
-            mvs.append(N.make_mappoint_view(mdesc, inv, u, v, xr, lvl, vc, None, keep))
-            inview.append(int(inv.sum()))
-        r2 = self.b.search_local_points_batch(fvs, mvs, 3.0, 0.8) if batch else [self.b.search_local_points(f, m, 3.0, 0.8) for f, m in zip(fvs, mvs)]
-        for t, iv, (m2, n2) in zip(c2_t, inview, r2):
-            summary[t].update(c2_in_view=iv, c2_matches=n2, c2_sum=self._chk(m2))
+        def point_searches():
+            r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
+            claimed = [None] * n
+            for t, (m3, n3) in zip(c3_t, r3):
+                summary[t].update(c3_matches=n3, c3_sum=self._chk(m3))
+                claimed[t] = (m3 >= 0).astype(np.int32)
+            # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
+            fvs, mvs, inview = [], [], []
+            for t, (mdesc, inv, u, v, xr, lvl, vc) in zip(c2_t, fr):
+                fvs.append(frames[t].view(claimed[t], keep))
+                mvs.append(N.make_mappoint_view(mdesc, inv, u, v, xr, lvl, vc, None, keep))
+                inview.append(int(inv.sum()))
+            r2 = self.b.search_local_points_batch(fvs, mvs, 3.0, 0.8) if batch else [self.b.search_local_points(f, m, 3.0, 0.8) for f, m in zip(fvs, mvs)]
+            for t, iv, (m2, n2) in zip(c2_t, inview, r2):
+                summary[t].update(c2_in_view=iv, c2_matches=n2, c2_sum=self._chk(m2))
+
+        # The point searches and the line side do not depend on each other.  A backend whose line matcher has its own handle
+        # (its own stream and staging buffers) lets the point searches run on a second host thread while this one prepares and
+        # issues the line searches: the matcher calls block in native code (no GIL), so their device time overlaps the numpy glue
+        # of the other side.  Same calls, same inputs, same results — only the order in wall-clock time changes.
+        worker = None
+        if batch and getattr(self.b, "concurrent_sides", False):
+            import threading
+            err = []
+
+            def guarded():
+                try:
+                    point_searches()
+                except BaseException as e:  # re-raised on the caller's thread
+                    err.append(e)
+            worker = threading.Thread(target=guarded)
+            worker.start()
+        else:
+            point_searches()
         # ---- line side of the caller state ----
         if hasattr(lines, "result"):
             lines = lines.result()
@@ -362,6 +382,10 @@ class TrackingFrontEnd:
         rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
         for t, (ml, nl, rel, npj) in zip(d5_t, rd5):
             summary[t].update(d5_proj=npj, d5_matches=nl, d5_relaxed=rel, d5_sum=self._chk(ml))
+        if worker is not None:
+            worker.join()
+            if err:
+                raise err[0]
         return summary
 
 
@@ -373,6 +397,8 @@ class GpuBackend:
         self.orb = api.ORBextractor(nfeatures, 1.2, 8, 20, 7, device=device, max_cols=cols, max_rows=rows, max_batch=chunk)
         self.line = api.LineExtractor(device=device, max_cols=cols, max_rows=rows, max_batch=chunk)
         self.m = api.DescriptorMatcher(device=device)
+        self.ml = api.DescriptorMatcher(device=device)   # the line side's own handle: stream + staging buffers
+        self.concurrent_sides = True
 
     def scale_factors(self):
         return self.orb.GetScaleFactors()
@@ -404,7 +430,7 @@ class GpuBackend:
         return self.m.SearchByProjectionLocalPointsBatch(fvs, mvs, th, nn)
 
     def line_search_batch(self, cvs, lvs):
-        return self.m.SearchLinesByProjectionBatch(cvs, lvs)
+        return self.ml.SearchLinesByProjectionBatch(cvs, lvs)
 
     # F rows (Frame glue): UnprojectStereo / IsInFrustum of many frames in one call
     def unproject_batch(self, off, xy, z, rwc, ow, K):
