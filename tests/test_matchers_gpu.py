@@ -44,13 +44,15 @@ class Recorder:
 
 
 def _flatten(log):
+    """Calls of the log as (kind, result), grouped by kind (call order inside a kind is kept): the point searches and the line
+    searches may run on two host threads, so their relative order in the log is not defined."""
     out = []
     for k, r in log:
         if k.endswith("_batch"):
             out += [(k[:-6], x) for x in r]
         else:
             out.append((k, r))
-    return out
+    return sorted(out, key=lambda e: e[0])
 
 
 def test_sequence_matchers_bit_exact(seq, feats, api, oracle, pkg):
