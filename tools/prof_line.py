@@ -19,8 +19,9 @@ ap.add_argument("--chunk", type=int, default=64)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--w", type=int, default=640)
 ap.add_argument("--h", type=int, default=480)
+ap.add_argument("--room", action="store_true", help="frames of the bench's room sequence instead of the textured test frames")
 a = ap.parse_args()
-fr = pkg.synth.frames(6000, a.frames, a.w, a.h)
+fr = pkg.synth.room_sequence(a.frames, a.w, a.h, workers=min(32, os.cpu_count() or 1))[0] if a.room else pkg.synth.frames(6000, a.frames, a.w, a.h)
 d_in = torch.from_numpy(fr).cuda()
 ex = api.LineExtractor(max_cols=a.w, max_rows=a.h, max_batch=a.chunk)
 ML = 80
