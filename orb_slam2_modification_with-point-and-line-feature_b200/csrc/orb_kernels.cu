@@ -149,6 +149,8 @@ constexpr int kMaxWin = 66;   // wCell = ceil(width/floor(width/30)) < 60, windo
 constexpr int kWinPitch = 68;
 constexpr int kMaxInt = kMaxWin - 6;
 constexpr int kMaxSurv = ((kMaxInt + 1) / 2) * ((kMaxInt + 1) / 2);
+constexpr int kFastBitWords = 128;  // >= kMaxInt * kMaxInt / 32 (one bit per interior pixel of a cell), a multiple of 32
+static_assert(kFastBitWords * 32 >= kMaxInt * kMaxInt && kFastBitWords % 32 == 0 && kWinPitch % 4 == 0, "FAST cell bitmap");
 
 // Packed ring differences: for ring value r and centre constant A = (v+256) + ((256-v)<<16),
 // r*0xFFFF + A = (v-r+256) | ((r-v+256)<<16): both 16-bit halves are biased by +256 and positive, so one
@@ -182,13 +184,15 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const OrbGeom* __re
                                                              const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
                                                              int* __restrict__ cell_off, int* __restrict__ cell_cnt,
                                                              int* __restrict__ lvl_count, int* __restrict__ flags) {
-    __shared__ __align__(16) uint8_t s_win[kMaxWin * kWinPitch];
-    __shared__ uint8_t s_score[(kMaxInt + 2) * (kMaxInt + 2)];
-    __shared__ uint16_t s_queue[kMaxInt * kMaxInt];
-    __shared__ uint32_t s_list[kMaxSurv];
+    __shared__ __align__(16) uint8_t s_win[kMaxWin * kWinPitch + 16];
+    __shared__ __align__(16) uint8_t s_score[((kMaxInt + 2) * (kMaxInt + 2) + 15) & ~15];
+    __shared__ uint16_t s_queue[kMaxInt * kMaxInt];   // survivors of the high-speed test, packed py << 8 | px
+    __shared__ uint32_t s_list[kMaxSurv];             // local maxima: (py * iw + px) << 8 | score
+    __shared__ uint32_t s_bits[kFastBitWords];        // kept maxima, one bit per interior pixel (raster order)
+    __shared__ int s_pref[kFastBitWords];             // kept maxima before each word
     __shared__ int s_qn, s_ln, s_has_ini, s_base, s_keep;
 
-    const int cid = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int cid = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const Cell c = cells[cid];
     const LevelGeom& L = g->lv[c.level];
     const int ww = c.x1 - c.x0, wh = c.y1 - c.y0;
@@ -202,37 +206,67 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const OrbGeom* __re
     const int ini_th = g->ini_th, min_th = g->min_th;
     const int low_th = min(ini_th, min_th);
     if (tid == 0) { s_qn = 0; s_ln = 0; s_has_ini = 0; }
+    // window -> shared memory, four pixels per thread and step: two aligned 32-bit loads + a funnel shift per word (the window
+    // starts at an arbitrary byte of the plane); the (row, word) of a thread advances without divisions
+    const int nw = (ww + 3) >> 2;  // words per window row (<= kWinPitch / 4)
+    const int dq = kFastThreads / nw, dr = kFastThreads - dq * nw;
     const uint8_t* src = pyr + L.plane_off + (size_t)f * L.plane_size + (size_t)(c.y0 + kEdge) * L.pitch + c.x0 + kEdge;
-    for (int i = tid; i < wh * ww; i += kFastThreads) {
-        int r = i / ww, x = i - r * ww;
-        s_win[r * kWinPitch + x] = __ldg(src + (size_t)r * L.pitch + x);
+    uint32_t* s_win32 = reinterpret_cast<uint32_t*>(s_win);
+    {
+        int r = tid / nw, k = tid - r * nw;
+        while (r < wh) {
+            const uint8_t* a = src + (size_t)r * L.pitch + 4 * k;
+            const uint32_t* b = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+            const unsigned sh = ((unsigned)reinterpret_cast<uintptr_t>(a) & 3u) * 8u;
+            const uint32_t w0 = __ldg(b), w1 = sh ? __ldg(b + 1) : 0u;
+            s_win32[r * (kWinPitch / 4) + k] = __funnelshift_r(w0, w1, sh);
+            k += dr; r += dq;
+            if (k >= nw) { k -= nw; r++; }
+        }
     }
     const int sp = iw + 2;
-    for (int i = tid; i < (ih + 2) * sp; i += kFastThreads) s_score[i] = 0;
+    {
+        uint32_t* sc32 = reinterpret_cast<uint32_t*>(s_score);
+        for (int i = tid; i < ((ih + 2) * sp + 3) >> 2; i += kFastThreads) sc32[i] = 0;
+    }
+    if (tid < kFastBitWords) s_bits[tid] = 0;
     __syncthreads();
 
-    // phase 1: high-speed test on the two opposite pairs (0,8) and (4,12): any arc of 9 contains one pixel of each
-    const uint32_t thr2 = (uint32_t)(low_th + 256) * 0x10001u;
-    for (int i = tid; i < iw * ih; i += kFastThreads) {
-        int py = i / iw, px = i - py * iw;
-        const uint8_t* cp = s_win + (py + 3) * kWinPitch + px + 3;
-        uint32_t v = cp[0];
-        uint32_t A = (v + 256u) + ((256u - v) << 16);
-        uint32_t d0 = ring_d2(cp, 3 * kWinPitch, A), d8 = ring_d2(cp, -3 * kWinPitch, A);
-        uint32_t d4 = ring_d2(cp, 3, A), d12 = ring_d2(cp, -3, A);
-        uint32_t r = __vmins2(__vmaxs2(d0, d8), __vmaxs2(d4, d12));
-        // pass if either half exceeds low_th+256
-        if (__vcmpgts2(r, thr2)) {
-            int q = atomicAdd(&s_qn, 1);
-            s_queue[q] = (uint16_t)i;
+    // phase 1: high-speed test on the two opposite pairs (0,8) and (4,12) — any arc of 9 contains one pixel of each pair —
+    // for four horizontally adjacent pixels per step with byte-wise SIMD: saturating c +- t, unsigned per-byte compares.
+    // Word k of window row py + 3 holds the centres at window columns 4k .. 4k+3; the interior is columns 3 .. 3 + iw - 1.
+    {
+        const uint32_t T4 = (uint32_t)low_th * 0x01010101u;
+        int py = tid / nw, k = tid - py * nw;
+        while (py < ih) {
+            const uint32_t* row = s_win32 + (py + 3) * (kWinPitch / 4);
+            const uint32_t cw = row[k];
+            const uint32_t up = row[k - 3 * (kWinPitch / 4)], dn = row[k + 3 * (kWinPitch / 4)];
+            const uint32_t wl = k > 0 ? row[k - 1] : 0u, wr = row[k + 1];
+            const uint32_t le = __funnelshift_r(wl, cw, 8);    // window columns 4k+j-3
+            const uint32_t ri = __funnelshift_r(cw, wr, 24);   // window columns 4k+j+3
+            const uint32_t hi = __vaddus4(cw, T4), lo = __vsubus4(cw, T4);
+            const uint32_t bright = (__vcmpgtu4(up, hi) | __vcmpgtu4(dn, hi)) & (__vcmpgtu4(le, hi) | __vcmpgtu4(ri, hi));
+            const uint32_t dark = (__vcmpltu4(up, lo) | __vcmpltu4(dn, lo)) & (__vcmpltu4(le, lo) | __vcmpltu4(ri, lo));
+            uint32_t m = bright | dark;
+            while (m) {
+                const int j = (__ffs(m) - 1) >> 3;
+                m &= ~(0xFFu << (8 * j));
+                const int px = 4 * k + j - 3;
+                if (px >= 0 && px < iw) {
+                    const int q = atomicAdd(&s_qn, 1);
+                    s_queue[q] = (uint16_t)((py << 8) | px);
+                }
+            }
+            k += dr; py += dq;
+            if (k >= nw) { k -= nw; py++; }
         }
     }
     __syncthreads();
     const int qn = s_qn;
     // phase 2: full score for the surviving pixels (dense over the queue)
     for (int q = tid; q < qn; q += kFastThreads) {
-        int i = s_queue[q];
-        int py = i / iw, px = i - py * iw;
+        const int e = s_queue[q], py = e >> 8, px = e & 0xff;
         const uint8_t* cp = s_win + (py + 3) * kWinPitch + px + 3;
         uint32_t v = cp[0];
         uint32_t A = (v + 256u) + ((256u - v) << 16);
@@ -242,27 +276,43 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const OrbGeom* __re
     __syncthreads();
     // phase 3: 3x3 non-max suppression inside the cell (strict >, everything outside the cell interior counts 0)
     for (int q = tid; q < qn; q += kFastThreads) {
-        int i = s_queue[q];
-        int py = i / iw, px = i - py * iw;
+        const int e = s_queue[q], py = e >> 8, px = e & 0xff;
         const uint8_t* sc = s_score + (py + 1) * sp + px + 1;
         int s = sc[0];
         if (s == 0) continue;
         if (s > sc[-1] && s > sc[1] && s > sc[-sp - 1] && s > sc[-sp] && s > sc[-sp + 1] && s > sc[sp - 1] && s > sc[sp] &&
             s > sc[sp + 1]) {
             int k = atomicAdd(&s_ln, 1);
-            s_list[k] = ((uint32_t)i << 8) | (uint32_t)s;
+            s_list[k] = ((uint32_t)(py * iw + px) << 8) | (uint32_t)s;
             if (s >= ini_th) s_has_ini = 1;
         }
     }
     __syncthreads();
-    // phase 4: threshold fallback (:809-816) and ordered emission (raster order inside the cell)
+    // phase 4: threshold fallback (:809-816) and ordered emission (raster order inside the cell): the kept maxima set their
+    // bit in a raster bitmap; a maximum's rank is the number of bits before its own (word prefix + popc)
     const int ln = s_ln;
     const int keep_th = s_has_ini ? ini_th : min_th;
-    if (tid == 0) s_keep = 0;
+    for (int k = tid; k < ln; k += kFastThreads) {
+        const uint32_t e = s_list[k];
+        if ((int)(e & 0xffu) >= keep_th) atomicOr(&s_bits[e >> 13], 1u << ((e >> 8) & 31u));
+    }
     __syncthreads();
-    int my_keep = 0;
-    for (int k = tid; k < ln; k += kFastThreads) my_keep += ((int)(s_list[k] & 0xffu) >= keep_th);
-    if (my_keep) atomicAdd(&s_keep, my_keep);
+    if (tid < 32) {  // exclusive prefix of the word popcounts: kFastBitWords / 32 words per lane
+        constexpr int kPer = kFastBitWords / 32;
+        int cnt[kPer], local = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) { cnt[j] = __popc(s_bits[lane * kPer + j]); local += cnt[j]; }
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int run = incl - local;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) { s_pref[lane * kPer + j] = run; run += cnt[j]; }
+        if (lane == 31) s_keep = incl;
+    }
     __syncthreads();
     const int n_keep = s_keep;
     if (tid == 0) {
@@ -285,13 +335,9 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const OrbGeom* __re
     for (int k = tid; k < ln; k += kFastThreads) {
         uint32_t e = s_list[k];
         if ((int)(e & 0xffu) < keep_th) continue;
-        int rank = 0;
-        for (int j = 0; j < ln; j++) {
-            uint32_t o = s_list[j];
-            rank += ((int)(o & 0xffu) >= keep_th) && (o >> 8) < (e >> 8);
-        }
-        int i = (int)(e >> 8);
-        int py = i / iw, px = i - py * iw;
+        const int i = (int)(e >> 8);
+        const int rank = s_pref[i >> 5] + __popc(s_bits[i >> 5] & ((1u << (i & 31)) - 1u));
+        const int py = i / iw, px = i - py * iw;
         // coordinates relative to minBorder (=16): cell-relative FAST coordinate + j*wCell (:822-823)
         uint32_t x = (uint32_t)(c.x0 + 3 + px - 16), y = (uint32_t)(c.y0 + 3 + py - 16);
         out[rank] = x | (y << 12) | ((e & 0xffu) << 24);
