@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--chunk", type=int, default=0, help="frames per extraction chunk (0 = whole sequence)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="frames of the cpu_baseline sample")
+    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the persistent LSD region grower leaves to the matcher kernels of the other streams")
+    ap.add_argument("--device-glue", type=int, default=1, help="e2e leg: Frame glue (UnprojectStereo, IsInFrustum) through the batched F-row calls instead of numpy")
     return ap.parse_args()
 
 
@@ -182,6 +184,7 @@ def run_ours(a, rank, world, local_rank, dist):
     t_gen = time.time() - t0
 
     gb = fe.GpuBackend(api, H, W, NFEAT, chunk=chunk, device=dev)
+    gb.line.set_reserved_sms(a.reserve_sms)
     sf = gb.scale_factors()
     cap = gb.orb.max_keypoints()
     d_gray = torch.from_numpy(gray).cuda()
@@ -226,7 +229,7 @@ def run_ours(a, rank, world, local_rank, dist):
         gb.m.sync()
         gb.ml.sync()
 
-    e2e_fe = fe.TrackingFrontEnd(gb)
+    e2e_fe = fe.TrackingFrontEnd(gb, device_glue=bool(a.device_glue))
 
     # e2e staging: pinned host mirrors of the outputs (the step's D2H reads) and a device image buffer (the step's H2D write)
     e_gray = torch.empty_like(d_gray)
@@ -395,7 +398,7 @@ def run_ours(a, rank, world, local_rank, dist):
         "ms_per_step": round(t_total / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"seq{F}-640x480-rgbd: ORB(1000,1.2,8,20,7) + LSD/LBD(80) extract, C3+D3+C2+D5 match", "frames_per_step": F,
-                   "frames_per_rank": F, "extract_chunk": chunk, "l2_flush": "256 MiB device fill between steps, outside the timed spans",
+                   "frames_per_rank": F, "extract_chunk": chunk, "lsd_reserved_sms": a.reserve_sms, "l2_flush": "256 MiB device fill between steps, outside the timed spans",
                    "timing": "wall clock between device synchronisations around each step (3 CUDA streams; the point searches overlap the line extraction, so the step is shorter than extract + match of step_breakdown_ms, which are timed one after the other), max over ranks",
                    "sequence_render_s": round(t_gen, 1)},
         "p50_ms_per_frame": round(p50, 3),
@@ -403,7 +406,7 @@ def run_ours(a, rank, world, local_rank, dist):
         "step_breakdown_ms": {"extract": round(t_ext * 1e3, 2), "match": round(t_match * 1e3, 2), "matcher_calls": len(plan.calls)},
         "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(F * W * H),
                 "d2h_bytes_per_step": int(F * (cap * 60 + MAXL * (68 + 32 + 24) + 8)), "steps": e2e_steps,
-                "note": "host images uploaded once, both extractors through the device-pointer C ABI on their own streams, results read back to pinned host memory; numpy caller glue (Frame-lite) overlapping the line extractor; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
+                "note": "host images uploaded once, both extractors through the device-pointer C ABI on their own streams, results read back to pinned host memory; caller glue (Frame-lite: numpy + the batched F-row calls of the library) and the point searches run on the SMs the line extractor's region grower leaves free while it is still working; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
         "gpu_launches": int(launches_per_step * a.steps),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "matches_per_frame": {"c3": round(float(np.mean([r.get("c3_matches", 0) for r in summary])), 1),

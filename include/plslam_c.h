@@ -169,6 +169,10 @@ PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_fr
 PL_API int pl_line_sync(pl_line* h);
 PL_API void* pl_line_stream(pl_line* h);
 PL_API int pl_line_last_launches(const pl_line* h);
+/* The ordered region grower runs as persistent CTAs that own their SM, so kernels of other streams (the matchers, the Frame
+ * glue) wait for it unless some SMs are left free: n SMs are kept out of the grower's grid whenever a batch has more frames
+ * than the remaining SMs (default 0).  Results do not depend on it. */
+PL_API int pl_line_set_reserved_sms(pl_line* h, int n);
 
 /* Measurement hooks: stages {0 blur+scale+gradient, 1 seed sort, 2 region growing/NFA, 3 KeyLines+blur5+Sobel, 4 LBD} */
 PL_API int pl_line_set_profiling(pl_line* h, int on);

@@ -218,6 +218,10 @@ class LineExtractor:
     def last_launches(self):
         return N.lib().pl_line_last_launches(self._h)
 
+    def set_reserved_sms(self, n):
+        """SMs the persistent region grower leaves to the kernels of other streams (matchers, Frame glue) in large batches."""
+        check(N.lib().pl_line_set_reserved_sms(self._h, C.c_int(int(n))))
+
     # ---- test hooks ----
     def lsd_segments(self, frame=0, cap=30000):
         xy = np.empty((cap, 4), np.float32)

@@ -524,7 +524,7 @@ PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, con
     PL_CUDA_TRY(cudaGetLastError());
     // results live in the same packed buffer: one copy back
     PL_CUDA_TRY(cudaMemcpyAsync(h->in.h, h->in.d, h->in.cur, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     for (int i = 0; i < n; i++) {
         if (bd[i].n_out) memcpy(match_out[i], h_match[i], (size_t)bd[i].n_out * 4);
         n_matches[i] = h_out[i][0];
@@ -568,7 +568,7 @@ PL_API int pl_line_match_knn_ratio(pl_match* h, const uint8_t* ref_desc, int n_r
     PL_CUDA_TRY(cudaGetLastError());
     std::vector<int> tmp((size_t)n_cur + 1);
     PL_CUDA_TRY(cudaMemcpyAsync(tmp.data(), dm, (size_t)(n_cur + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     memcpy(match_of_line, tmp.data(), (size_t)n_cur * 4);
     *n_matches = tmp[n_cur];
     return PL_OK;
@@ -597,7 +597,7 @@ PL_API int pl_line_search_for_triangulation(pl_match* h, const uint8_t* desc1, i
     uint8_t misc[24];
     PL_CUDA_TRY(cudaMemcpyAsync(misc, dmisc, 24, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(cudaMemcpyAsync(pairs, dp, (size_t)n1 * 8, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     double m[2];
     memcpy(m, misc, 16);
     memcpy(n_matches, misc + 16, 4);
@@ -629,7 +629,7 @@ PL_API int pl_line_fuse_candidates(pl_match* h, const uint8_t* ml_desc, const ui
     PL_CUDA_TRY(cudaGetLastError());
     std::vector<int> tmp((size_t)n + 1);
     PL_CUDA_TRY(cudaMemcpyAsync(tmp.data(), dt, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     memcpy(tdx, tmp.data(), (size_t)n * 4);
     *n_fused = tmp[n];
     return PL_OK;
@@ -739,7 +739,7 @@ PL_API int pl_orb_search_for_triangulation(pl_match* h, const pl_triang_view* a,
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h->in.h, h->in.d, h->in.cur, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     int np = 0;
     for (int i = 0; i < A.n; i++)
         if (h_match[i] >= 0) { pairs[2 * np] = i; pairs[2 * np + 1] = h_match[i]; np++; }
@@ -768,7 +768,7 @@ PL_API int pl_distinctive_descriptors(pl_match* h, const uint8_t* desc, const in
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h_best, d_best, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(best_row, h_best, (size_t)n_groups * 4);
     return PL_OK;
 }

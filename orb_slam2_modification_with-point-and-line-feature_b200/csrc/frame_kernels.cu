@@ -206,7 +206,7 @@ PL_API int pl_frame_undistort_points(pl_match* h, const float* xy, int n, float 
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(xy_out, h_out, (size_t)n * 8);
     return PL_OK;
 }
@@ -242,7 +242,7 @@ PL_API int pl_frame_stereo_from_rgbd_batch(pl_match* h, int n_frames, const floa
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h_d, d_d, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_ur, d_ur, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(depth_out, h_d, (size_t)total * 4);
     memcpy(u_right_out, h_ur, (size_t)total * 4);
     return PL_OK;
@@ -279,7 +279,7 @@ PL_API int pl_frame_unproject_batch(pl_match* h, int n_frames, const int* off, c
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h_w, d_w, (size_t)total * 12, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_v, d_v, (size_t)total, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(world, h_w, (size_t)total * 12);
     memcpy(valid, h_v, (size_t)total);
     return PL_OK;
@@ -323,7 +323,7 @@ PL_API int pl_frame_is_in_frustum_batch(pl_match* h, int n_frames, const float* 
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h->res.h, h->res.d, h->res.cur, cudaMemcpyDeviceToHost, st));  // the six planes: one copy
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(in_view, h_iv, nm);
     memcpy(proj_x, h_x, nm * 4);
     memcpy(proj_y, h_y, nm * 4);
@@ -354,7 +354,7 @@ PL_API int pl_frame_lines_in_frustum_batch(pl_match* h, int n_frames, const floa
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h_iv, d_iv, nm, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(in_view, h_iv, nm);
     return PL_OK;
 }

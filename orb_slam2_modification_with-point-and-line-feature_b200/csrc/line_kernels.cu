@@ -2023,6 +2023,7 @@ struct pl_line {
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     int tail_nfa = 1;
     GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
+    int reserved_sms = 0;          // SMs the region grower leaves to the kernels of other streams (pl_line_set_reserved_sms)
     unsigned int* d_big_bits = nullptr;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
     short *d_dx = nullptr, *d_dy = nullptr;
@@ -2101,7 +2102,7 @@ int line_geometry(pl_line* h, int rows, int cols, int max_lines) {
     build_exact_axis(yt, G.H, rows, 0.8);
     PL_CUDA_TRY(cudaMemcpyAsync(h->d_xtab, xt.data(), xt.size() * sizeof(ExactTab), cudaMemcpyHostToDevice, h->stream));
     PL_CUDA_TRY(cudaMemcpyAsync(h->d_ytab, yt.data(), yt.size() * sizeof(ExactTab), cudaMemcpyHostToDevice, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     h->rows = rows; h->cols = cols; h->max_lines = max_lines;
     return PL_OK;
 }
@@ -2149,10 +2150,13 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     if (prof) cudaEventRecord(h->ev[2], st);
     {
         // one CTA per SM; a CTA works on several frames at once when there are more frames than SMs
-        const bool many = nf > h->num_sms && h->cfg_many.growers > 0;
+        // The grower's CTAs are persistent and own their SM (all registers, almost all shared memory): a kernel of another stream
+        // only runs where no grower CTA sits.  reserved_sms keeps that many SMs free while there are more frames than SMs.
+        const int sms = std::max(1, h->num_sms - (nf > h->num_sms - h->reserved_sms ? h->reserved_sms : 0));
+        const bool many = nf > sms && h->cfg_many.growers > 0;
         const GrowConfig& cf = many ? h->cfg_many : h->cfg_few;
         GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words, h->tail_nfa};
-        const int ctas = std::min(nf, h->num_sms);
+        const int ctas = std::min(nf, sms);
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_claims, 0xff, sizeof(unsigned short) * plane * nf, st));
         GrowBufs gb;
@@ -2210,7 +2214,7 @@ __global__ void __launch_bounds__(32) k_line_or_flags(const int* __restrict__ fl
 
 int line_check_flags(pl_line* h, int nf) {
     PL_CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     for (int i = 0; i < nf; i++)
         if (h->h_flags[i]) {
             set_error("frame %d of the chunk exceeded an LSD capacity (flags=%d: 1=segments, 2=region size)", i, h->h_flags[i]);
@@ -2317,6 +2321,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             }
             h->grow_tiles = tiles;
             if (const char* ev = getenv("PLSLAM_LSD_TAIL_NFA")) h->tail_nfa = atoi(ev) != 0;
+            if (const char* ev = getenv("PLSLAM_LSD_RESERVE_SMS")) h->reserved_sms = std::max(0, std::min(h->num_sms - 1, atoi(ev)));
             h->grow_window = 128;
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));
             if (h->cfg_few.growers < 1) {
@@ -2397,7 +2402,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
 PL_API void pl_line_destroy(pl_line* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) pl::stream_sync(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
                     h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_sticky, h->d_cs, h->d_cs0, h->d_nrects};
@@ -2414,8 +2419,9 @@ PL_API int pl_line_sync(pl_line* h) {
     PL_CHECK_ARG(h);
     PL_CUDA_TRY(cudaSetDevice(h->device));
     int sticky = 0;
+    PL_CUDA_TRY(pl::stream_sync(h->stream));  // a copy into pageable memory blocks inside the runtime until the stream gets there
     PL_CUDA_TRY(cudaMemcpyAsync(&sticky, h->d_sticky, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     if (sticky) {
         PL_CUDA_TRY(cudaMemsetAsync(h->d_sticky, 0, sizeof(int), h->stream));
         set_error("a frame extracted through the device-pointer API exceeded an LSD capacity (flags=%d: 1=segments, 2=region size)", sticky);
@@ -2424,6 +2430,11 @@ PL_API int pl_line_sync(pl_line* h) {
     return PL_OK;
 }
 PL_API void* pl_line_stream(pl_line* h) { return h ? (void*)h->stream : nullptr; }
+PL_API int pl_line_set_reserved_sms(pl_line* h, int n) {
+    PL_CHECK_ARG(h && n >= 0 && n < std::max(h->num_sms, 1));
+    h->reserved_sms = n;
+    return PL_OK;
+}
 PL_API int pl_line_last_launches(const pl_line* h) { return h ? h->last_launches : 0; }
 
 PL_API int pl_line_set_profiling(pl_line* h, int on) {
@@ -2498,7 +2509,7 @@ PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, 
                                     h->stream));
         PL_CUDA_TRY(cudaMemcpyAsync(coeffs + (size_t)f0 * max_lines * 3, h->d_coef, sizeof(double) * (size_t)nf * max_lines * 3,
                                     cudaMemcpyDeviceToHost, h->stream));
-        PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        PL_CUDA_TRY(pl::stream_sync(h->stream));
     }
     return PL_OK;
 }
@@ -2516,14 +2527,15 @@ PL_API int pl_line_lsd_read(pl_line* h, int frame, float* xyxy, double* width, d
     }
     PL_CUDA_TRY(cudaSetDevice(h->device));
     int n = 0;
+    PL_CUDA_TRY(pl::stream_sync(h->stream));  // a copy into pageable memory blocks inside the runtime until the stream gets there
     PL_CUDA_TRY(cudaMemcpyAsync(&n, h->d_nsegs + frame, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     *n_out = n;
     if (n > cap) return PL_ERR_CAPACITY;
     std::vector<LsdSeg> tmp(n);
     if (n) {
         PL_CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_segs + (size_t)frame * h->geom.seg_cap, sizeof(LsdSeg) * n, cudaMemcpyDeviceToHost, h->stream));
-        PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        PL_CUDA_TRY(pl::stream_sync(h->stream));
     }
     for (int i = 0; i < n; i++) {
         xyxy[4 * i] = tmp[i].x1; xyxy[4 * i + 1] = tmp[i].y1; xyxy[4 * i + 2] = tmp[i].x2; xyxy[4 * i + 3] = tmp[i].y2;
@@ -2541,7 +2553,7 @@ PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out7) {
     // out7 receives 8 values, see plslam_c.h
     PL_CUDA_TRY(cudaSetDevice(h->device));
     PL_CUDA_TRY(cudaMemcpyAsync(out7, h->d_phase + (size_t)frame * 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 
@@ -2558,21 +2570,21 @@ PL_API int pl_line_scaled_read(pl_line* h, int frame, uint8_t* out, size_t out_s
     PL_CUDA_TRY(cudaSetDevice(h->device));
     PL_CUDA_TRY(cudaMemcpy2DAsync(out, out_step, h->d_scaled + (size_t)frame * h->scaled_stride, h->geom.spitch, h->geom.W, h->geom.H,
                                   cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 PL_API int pl_line_angles_read(pl_line* h, int frame, float* out) {
     PL_CHECK_ARG(h && out && frame >= 0 && frame < h->last_batch);
     PL_CUDA_TRY(cudaSetDevice(h->device));
     PL_CUDA_TRY(cudaMemcpyAsync(out, h->d_ang + (size_t)frame * h->plane, sizeof(float) * h->plane, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 PL_API int pl_line_fdesc_read(pl_line* h, int frame, float* out, int n) {
     PL_CHECK_ARG(h && out && frame >= 0 && frame < h->last_batch && n >= 0 && n <= h->out_cap);
     PL_CUDA_TRY(cudaSetDevice(h->device));
     PL_CUDA_TRY(cudaMemcpyAsync(out, h->d_fdesc + (size_t)frame * h->max_lines * 72, sizeof(float) * 72 * n, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 

@@ -153,7 +153,7 @@ PL_API int pl_match_create(pl_match** out, int device) {
 PL_API void pl_match_destroy(pl_match* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) pl::stream_sync(h->stream);
     for (int i = 0; i < 24; i++)
         if (h->d_buf[i]) cudaFree(h->d_buf[i]);
     h->in.release();
@@ -165,7 +165,7 @@ PL_API void pl_match_destroy(pl_match* h) {
 PL_API int pl_match_sync(pl_match* h) {
     PL_CHECK_ARG(h);
     PL_CUDA_TRY(cudaSetDevice(h->device));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 PL_API void* pl_match_stream(pl_match* h) { return h ? (void*)h->stream : nullptr; }
@@ -187,7 +187,7 @@ PL_API int pl_hamming_pairs(pl_match* h, const uint8_t* a, const uint8_t* b, int
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 
@@ -217,7 +217,7 @@ PL_API int pl_hamming_knn2(pl_match* h, const uint8_t* q, int nq, const uint8_t*
     if (rc != PL_OK) return rc;
     PL_CUDA_TRY(cudaMemcpyAsync(idx, di, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(cudaMemcpyAsync(dist, dd, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 
@@ -247,7 +247,7 @@ PL_API int pl_hamming_candidates(pl_match* h, const uint8_t* q, int nq, const ui
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(dist_out, dd, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 

@@ -1106,7 +1106,7 @@ int build_geometry(pl_orb* h, int rows, int cols) {
     PL_CUDA_TRY(cudaMemcpyAsync(h->d_cells, h->cells.data(), h->cells.size() * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
     PL_CUDA_TRY(cudaMemcpyAsync(h->d_tabs, h->tabs.data(), h->tabs.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, h->stream));
     PL_CUDA_TRY(cudaMemcpyAsync(h->d_tiles, h->tiles.data(), h->tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     h->rows = rows;
     h->cols = cols;
     return PL_OK;
@@ -1177,7 +1177,7 @@ __global__ void __launch_bounds__(32) k_or_flags(const int* __restrict__ flags, 
 
 int check_flags(pl_orb* h, int nf) {
     PL_CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     for (int i = 0; i < nf; i++)
         if (h->h_flags[i]) {
             set_error("frame %d of the chunk exceeded a capacity (flags=%d: 1=FAST candidates, 2=quadtree nodes, 4=caller cap)", i,
@@ -1271,7 +1271,7 @@ PL_API int pl_orb_create(pl_orb** out, int nfeatures, float scale_factor, int nl
 PL_API void pl_orb_destroy(pl_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) pl::stream_sync(h->stream);
     void* bufs[] = {h->d_geom, h->d_cells, h->d_tabs, h->d_tiles, h->d_in, h->d_pyr, h->d_blur, h->d_cand, h->d_ord, h->d_lvl_kp,
                     h->d_node, h->d_cell_off, h->d_cell_cnt, h->d_lvl_count, h->d_lvl_n, h->d_flags, h->d_sticky, h->d_kps, h->d_desc, h->d_nout};
     for (void* b : bufs)
@@ -1337,8 +1337,9 @@ PL_API int pl_orb_sync(pl_orb* h) {
     PL_CHECK_ARG(h);
     PL_CUDA_TRY(cudaSetDevice(h->device));
     int sticky = 0;
+    PL_CUDA_TRY(pl::stream_sync(h->stream));  // a copy into pageable memory blocks inside the runtime until the stream gets there
     PL_CUDA_TRY(cudaMemcpyAsync(&sticky, h->d_sticky, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     if (sticky) {
         PL_CUDA_TRY(cudaMemsetAsync(h->d_sticky, 0, sizeof(int), h->stream));
         set_error("a frame extracted through the device-pointer API exceeded a capacity (flags=%d: 1=FAST candidates, 2=quadtree nodes, "
@@ -1418,7 +1419,7 @@ PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, in
             PL_CUDA_TRY(cudaMemcpyAsync(desc + (size_t)(f0 + f) * cap * 32, h->d_desc + (size_t)f * cap * 32, (size_t)n * 32,
                                         cudaMemcpyDeviceToHost, h->stream));
         }
-        PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        PL_CUDA_TRY(pl::stream_sync(h->stream));
     }
     return PL_OK;
 }
@@ -1446,7 +1447,7 @@ PL_API int pl_orb_pyramid_read(pl_orb* h, int frame, int level, uint8_t* out, si
     PL_CUDA_TRY(cudaSetDevice(h->device));
     PL_CUDA_TRY(cudaMemcpy2DAsync(out, out_step, h->d_pyr + L.plane_off + (size_t)frame * L.plane_size, L.pitch, L.w + 2 * kEdge,
                                   L.h + 2 * kEdge, cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 
@@ -1475,7 +1476,7 @@ PL_API int pl_orb_blurred_read(pl_orb* h, int frame, int level, uint8_t* out, si
     PL_CUDA_TRY(cudaSetDevice(h->device));
     PL_CUDA_TRY(cudaMemcpy2DAsync(out, out_step, h->d_blur + L.blur_off + (size_t)frame * L.blur_size, L.bpitch, L.w, L.h,
                                   cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }
 
@@ -1488,15 +1489,16 @@ PL_API int pl_orb_candidates_read(pl_orb* h, int frame, int level, float* xs, fl
     PL_CUDA_TRY(cudaSetDevice(h->device));
     const LevelGeom& L = h->geom.lv[level];
     int n = 0;
+    PL_CUDA_TRY(pl::stream_sync(h->stream));  // a copy into pageable memory blocks inside the runtime until the stream gets there
     PL_CUDA_TRY(cudaMemcpyAsync(&n, h->d_lvl_count + (size_t)frame * h->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PL_CUDA_TRY(pl::stream_sync(h->stream));
     *n_out = n;
     if (n > cap || n > L.cand_cap) return PL_ERR_CAPACITY;
     std::vector<uint32_t> tmp(n);
     if (n) {
         PL_CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_ord + (size_t)frame * h->geom.cand_per_frame + L.cand_base, sizeof(uint32_t) * n,
                                     cudaMemcpyDeviceToHost, h->stream));
-        PL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        PL_CUDA_TRY(pl::stream_sync(h->stream));
     }
     for (int i = 0; i < n; i++) {
         xs[i] = (float)(tmp[i] & 0xfffu);

@@ -44,6 +44,13 @@ constexpr int kMaxLevels = 16;
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Waits for a stream.  NB for every caller: an asynchronous D2H copy into PAGEABLE host memory is not asynchronous — the call
+// blocks inside the runtime until the stream reaches the copy, and while it does the other host threads of the process get
+// no work through the runtime either (measured: pl_line_sync used to read its capacity flag into a stack variable; a matcher
+// call issued from a second thread then did not start until the line extractor had finished, 35 ms later).  So: wait for the
+// stream first, copy into pageable memory afterwards (or copy into pinned memory).
+inline cudaError_t stream_sync(cudaStream_t st) { return cudaStreamSynchronize(st); }
+
 #ifdef __CUDACC__
 // BORDER_REFLECT_101 index (one reflection is enough for |overshoot| < len; loop kept for tiny images)
 __host__ __device__ __forceinline__ int reflect101(int p, int len) {

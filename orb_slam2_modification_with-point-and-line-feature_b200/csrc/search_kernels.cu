@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(1024) k_cand_scan(const SearchDev* __restrict_
 
 // ---- phase B: ordered replay out of shared memory ----
 constexpr int kResThreads = 256;
-constexpr int kResChunkCand = 24 * 1024;  // packed candidates per chunk (96 KB)
+constexpr int kResChunkCand = 8 * 1024;  // packed candidates per chunk (32 KB: six replay CTAs fit on an SM, which matters when the LSD grower leaves only a few SMs free)
 
 // finds the end p1 of the chunk starting at p0 (largest p1 with off[p1]-off[p0] <= kResChunkCand) and copies its
 // candidates into shared memory.  A point with more than kResChunkCand candidates is flagged and skipped.
@@ -1126,7 +1126,7 @@ int run_search(pl_match* h, const std::vector<SearchDev>& host_sd, const SearchD
     int* h_base;
     h->res.out<int>((size_t)n, &h_base);
     PL_CUDA_TRY(cudaMemcpyAsync(h_tot, B.totals, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     long long grand = 0;
     for (int i = 0; i < n; i++) { h_base[i] = (int)grand; grand += h_tot[i]; }
     if (grand > 0x7fffffffLL) { set_error("too many candidates in one batch"); return PL_ERR_CAPACITY; }
@@ -1149,7 +1149,7 @@ int run_search(pl_match* h, const std::vector<SearchDev>& host_sd, const SearchD
     h->res.out<int>((size_t)n * 2, &h_out);
     if (total_feats) PL_CUDA_TRY(cudaMemcpyAsync(h_match, B.match, (size_t)total_feats * 4, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_out, B.out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     bool overflow = false;
     for (int i = 0; i < n; i++) {
         if (host_sd[i].F.n) memcpy(match_out[i], h_match + host_sd[i].feat_base, (size_t)host_sd[i].F.n * 4);
@@ -1436,7 +1436,7 @@ PL_API int pl_line_search_by_projection_batch(pl_match* h, int n, const pl_linef
     PL_CUDA_TRY(cudaMemcpyAsync(h_np, d_np, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_pi, d_pi, (size_t)std::max(total_lines, 1) * 4, cudaMemcpyDeviceToHost, st));
     if (want_proj && total_lines) PL_CUDA_TRY(cudaMemcpyAsync(h_pk, d_pk, (size_t)total_lines * sizeof(pl_keyline), cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     for (int i = 0; i < n; i++) {
         const LineSearchDev& D = ld[i];
         // match index: position in new_KeyLines -> index of the original map line (new_kl_index), as the reference
@@ -1532,7 +1532,7 @@ PL_API int pl_line_match_pairs(pl_match* h, const pl_keyline* proj, const uint8_
     int res[2] = {0, 0};
     PL_CUDA_TRY(cudaMemcpyAsync(match_of_line, d_match, (size_t)n_cur * 4, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(res, d_out, 8, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     *n_matches = res[0];
     *used_relaxed = res[1];
     return PL_OK;
@@ -1648,7 +1648,7 @@ PL_API int pl_orb_fuse_candidates_batch(pl_match* h, int n, const pl_frame_view*
         PL_CUDA_TRY(cudaMemcpyAsync(h_dist, d_dist, (size_t)L.total_pts * 4, cudaMemcpyDeviceToHost, st));
     }
     PL_CUDA_TRY(cudaMemcpyAsync(h_hits, d_hits, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     for (int i = 0; i < n; i++) {
         if (pts[i].n) {
             memcpy(best_idx[i], h_idx + sd[i].pt_base, (size_t)pts[i].n * 4);
@@ -1705,7 +1705,7 @@ PL_API int pl_orb_search_by_sim3(pl_match* h, const pl_frame_view* kf1, const pl
     h->res.out<int>(4, &h_found);
     if (kf1->n) PL_CUDA_TRY(cudaMemcpyAsync(h_m12, d_m12, (size_t)kf1->n * 4, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_found, d_found, 4, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     if (kf1->n) memcpy(match12, h_m12, (size_t)kf1->n * 4);
     *n_found = h_found[0];
     return PL_OK;
@@ -1767,8 +1767,9 @@ PL_API int pl_orb_search_for_initialization(pl_match* h, const pl_frame_view* F1
     k_cand_scan<<<1, 1024, 0, st>>>(d_sd, cand_n, cand_off, totals);
     h->last_launches += 3;
     int h_tot = 0;
+    PL_CUDA_TRY(pl::stream_sync(st));  // a copy into pageable memory blocks inside the runtime until the stream gets there
     PL_CUDA_TRY(cudaMemcpyAsync(&h_tot, totals, 4, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     if ((rc = match_scratch(h, 15, (size_t)std::max(h_tot, 1) * 4, &p)) != PL_OK) return rc;
     unsigned int* cand = (unsigned int*)p;
     if ((rc = match_scratch(h, 11, 4, &p)) != PL_OK) return rc;
@@ -1789,7 +1790,7 @@ PL_API int pl_orb_search_for_initialization(pl_match* h, const pl_frame_view* F1
     PL_CUDA_TRY(cudaMemcpyAsync(h_match, match, n1 * 4, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_prev, d_prev, n1 * 8, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_out, out, 8, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(matches12, h_match, n1 * 4);
     memcpy(prev_matched, h_prev, n1 * 8);
     *n_matches = h_out[0];

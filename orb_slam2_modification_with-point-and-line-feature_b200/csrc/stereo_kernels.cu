@@ -217,7 +217,7 @@ PL_API int pl_frame_compute_stereo_matches(pl_match* h, pl_orb* left, pl_orb* ri
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(h_ur, d_ur, nl * 4, cudaMemcpyDeviceToHost, st));
     PL_CUDA_TRY(cudaMemcpyAsync(h_d, d_d, nl * 4, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(u_right, h_ur, nl * 4);
     memcpy(depth, h_d, nl * 4);
     return PL_OK;

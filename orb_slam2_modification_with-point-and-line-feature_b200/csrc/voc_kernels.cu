@@ -406,7 +406,7 @@ PL_API int pl_voc_transform_batch(pl_voc* v, int n_frames, const int* off, const
     k_voc_assemble<<<n_frames, kVocThreads, sm, st>>>(d_off, f_word, f_weight, f_nid, v->scoring, v->weighting, d_nw, d_wid, d_wv, d_nn, d_nid, d_noff, d_fi);
     PL_CUDA_TRY(cudaGetLastError());
     PL_CUDA_TRY(cudaMemcpyAsync(v->in.h + out_begin, v->in.d + out_begin, v->in.cur - out_begin, cudaMemcpyDeviceToHost, st));
-    PL_CUDA_TRY(cudaStreamSynchronize(st));
+    PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(n_words, h_nw, (size_t)n_frames * 4);
     memcpy(n_fv_nodes, h_nn, (size_t)n_frames * 4);
     for (int f = 0; f < n_frames; f++) {

@@ -18,6 +18,9 @@ F = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 H, W, MAXL = 480, 640, 80
 gray, depth, Tcw = pkg.synth.room_sequence(F, W, H, workers=min(32, os.cpu_count() or 1))
 gb = fe.GpuBackend(api, H, W, 1000, chunk=F, device=0)
+RES = int(os.environ.get("RESERVE_SMS", "16"))
+DG = int(os.environ.get("DEVICE_GLUE", "1"))
+gb.line.set_reserved_sms(RES)
 sf = gb.scale_factors()
 cap = gb.orb.max_keypoints()
 h_gray = torch.from_numpy(gray).pin_memory()
@@ -33,6 +36,7 @@ p_kps, p_desc, p_n = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in 
 p_kls, p_ldesc, p_lco, p_ln = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (d_kls, d_ldesc, d_lco, d_ln))
 s_orb, s_line = torch.cuda.ExternalStream(gb.orb.stream()), torch.cuda.ExternalStream(gb.line.stream())
 ev_orb = torch.cuda.Event()
+ev_line = torch.cuda.Event()
 marks = []
 
 
@@ -59,6 +63,9 @@ class Timed:
 class LinesLater:
     def result(self):
         mark("lines wait >")
+        if os.environ.get("POLL", "0") == "1":  # poll instead of blocking in cudaStreamSynchronize while the other host thread launches work
+            while not ev_line.query():
+                time.sleep(0.0003)
         gb.line.sync()
         mark("lines ready")
         for dst, src in ((p_kls, d_kls), (p_ldesc, d_ldesc), (p_lco, d_lco), (p_ln, d_ln)):
@@ -71,7 +78,7 @@ class LinesLater:
         return r
 
 
-tfe = fe.TrackingFrontEnd(Timed(gb))
+tfe = fe.TrackingFrontEnd(Timed(gb), device_glue=bool(DG))
 
 
 def step():
@@ -84,6 +91,7 @@ def step():
     ev_orb.record(s_orb)
     s_line.wait_event(ev_orb)
     gb.line.extract_batch_dev(e_gray.data_ptr(), F, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
+    ev_line.record(s_line)
     gb.orb.sync()
     mark("ORB done")
     for dst, src in ((p_kps, d_kps), (p_desc, d_desc), (p_n, d_n)):
