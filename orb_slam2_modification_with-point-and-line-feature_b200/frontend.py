@@ -363,10 +363,12 @@ class TrackingFrontEnd:
         # ---- D3: LineMatcher(0.9).SearchByProjection(Cur, Last) (Tracking.cc:1247) ----
         d3_t = [t for t in c3_t if len(frames[t - 1].kls) and len(frames[t].kls)]
         lcv, llv = [], []
+        cur_view = {}  # the current-frame side of D3 and D5 is the same view
         for t in d3_t:
             F, last = frames[t], frames[t - 1]
             s3, e3, okl = last.unproject_lines()
-            lcv.append(N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep))
+            cur_view[t] = N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep)
+            lcv.append(cur_view[t])
             llv.append(N.make_mapline_view(s3, e3, last.kls, last.ldesc, okl, keep))
         rd3 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
         for t, (ml, nl, rel, npj) in zip(d3_t, rd3):
@@ -374,11 +376,14 @@ class TrackingFrontEnd:
         # ---- D5: LineMatcher(0.8).SearchByProjection(F, localLines) (Tracking.cc:1863) ----
         d5_t = [t for t in c2_t if len(lmaps[t][2]) and len(frames[t].kls)]
         lcv, llv = [], []
+        snap_view = {}  # frames between two key frames see the same snapshot of the local line map
         for t in d5_t:
             F = frames[t]
             ls, le, lkl, ldesc = lmaps[t]
-            lcv.append(N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep))
-            llv.append(N.make_mapline_view(ls, le, lkl, ldesc, np.ones(len(lkl), np.uint8), keep))
+            lcv.append(cur_view[t] if t in cur_view else N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep))
+            if id(lkl) not in snap_view:
+                snap_view[id(lkl)] = N.make_mapline_view(ls, le, lkl, ldesc, np.ones(len(lkl), np.uint8), keep)
+            llv.append(snap_view[id(lkl)])
         rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
         for t, (ml, nl, rel, npj) in zip(d5_t, rd5):
             summary[t].update(d5_proj=npj, d5_matches=nl, d5_relaxed=rel, d5_sum=self._chk(ml))
