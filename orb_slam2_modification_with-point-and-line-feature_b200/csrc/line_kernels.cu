@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineGeom g, const uint8_t* __
 // rounded to float (what a seed starts its sums from), so the ordered grower only loads them
 __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __restrict__ scaled, size_t scaled_frame_stride,
                                                   float* __restrict__ angdeg, int* __restrict__ g2, float2* __restrict__ cs,
-                                                  size_t plane, double rho, int* __restrict__ max_g2) {
+                                                  float2* __restrict__ cs0, size_t plane, double rho, int* __restrict__ max_g2) {
     const int f = blockIdx.z;
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     int my = -1;
@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __r
                 // cos(float(angle)) / sin(float(angle)) of the reference's region_grow resolve to cosf / sinf
                 const float af = (float)((double)a * kDegToRad);
                 cs[(size_t)f * plane + (size_t)y * g.W + x] = make_float2(glibc_sincosf(af, 1), glibc_sincosf(af, 0));
+                // a seed starts its sums from float(std::cos(double angle)), float(std::sin(double angle))
+                const double ad = (double)a * kDegToRad;
+                cs0[(size_t)f * plane + (size_t)y * g.W + x] = make_float2((float)cos(ad), (float)sin(ad));
             }
         }
         angdeg[(size_t)f * plane + (size_t)y * g.W + x] = a;
@@ -274,6 +277,7 @@ struct LsdFrame {  // per-frame (and per-grower) device views
     const float* ang;   // level-line angle in degrees or kNotDefDeg
     const int* g2;      // gx^2 + gy^2
     const float2* cs;   // (cosf, sinf) of the angle
+    const float2* cs0;  // (float(cos(double angle)), float(sin(double angle))): a seed's initial sums
     float2* sval;       // shared-memory staging of one warp, 36 entries
     const unsigned int* used_bits;  // the committed USED map: one bit per pixel, shared memory
     unsigned int* reg;  // region points, packed y<<16 | x
@@ -446,10 +450,8 @@ __device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy,
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
     const unsigned so = (unsigned)sy * (unsigned)F.W + (unsigned)sx;
     const float seed_deg = F.ang[so];
-    // a seed starts its sums from float(std::cos(double angle)), float(std::sin(double angle)): computed here, once per ticket,
-    // instead of as a plane for every pixel (8 bytes per pixel less to produce, keep in flight and miss)
-    const double seed_rad = (double)seed_deg * kDegToRad;
-    float sumdx = (float)cos(seed_rad), sumdy = (float)sin(seed_rad);
+    const float2 c0 = F.cs0[so];
+    float sumdx = c0.x, sumdy = c0.y;
     float hint = seed_deg;
     const float precdeg = (float)(prec * (180.0 / kPiD));
     if (nt >= F.touched_cap) return -1;
@@ -1016,7 +1018,7 @@ __device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restr
     const int lane = threadIdx.x & 31;
     LsdFrame F;
     F.ang = ang;
-    F.g2 = nullptr; F.cs = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
+    F.g2 = nullptr; F.cs = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
     F.W = g.W; F.H = g.H;
     F.sparse = false; F.dir = nullptr; F.rev = nullptr; F.pool = nullptr; F.ntiles = nullptr; F.tw = 0; F.pool_tiles = 0;
     F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
@@ -1149,6 +1151,7 @@ struct GrowBufs {
     const float* angdeg;
     const int* g2;
     const float2* cs;
+    const float2* cs0;
     const unsigned int* seeds;
     const int* n_seeds;
     unsigned short* claims;      // [frame][plane]
@@ -1381,6 +1384,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
             F.ang = B.angdeg + (size_t)f * plane;
             F.g2 = B.g2 + (size_t)f * plane;
             F.cs = B.cs + (size_t)f * plane;
+            F.cs0 = B.cs0 + (size_t)f * plane;
             F.claims = B.claims + (size_t)f * plane;
             F.used_bits = s_used;
             F.commit_head = &ctlp->commit_head;
@@ -1572,6 +1576,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
             F.ang = B.angdeg + (size_t)f * plane;
             F.g2 = B.g2 + (size_t)f * plane;
             F.cs = B.cs + (size_t)f * plane;
+            F.cs0 = B.cs0 + (size_t)f * plane;
             F.used_bits = s_used;
             F.commit_head = &ctlp->commit_head;
             LsdFrame FS2 = F;
@@ -1997,7 +2002,7 @@ struct pl_line {
     // device buffers (sized for max_cols x max_rows x max_batch at creation)
     uint8_t *d_in = nullptr, *d_scaled = nullptr, *d_blur5 = nullptr;
     float* d_ang = nullptr;
-    float2* d_cs = nullptr;
+    float2 *d_cs = nullptr, *d_cs0 = nullptr;
     int* d_nrects = nullptr;
     int* d_g2 = nullptr;
     unsigned int *d_reg = nullptr, *d_seeds = nullptr;
@@ -2134,7 +2139,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     {
         const double rho = 2.0 / sin(kPiD * 22.5 / 180);
         dim3 grid((G.W + 63) / 64, (G.H + 3) / 4, nf);
-        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, h->d_cs, plane, rho, h->d_maxg2);
+        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, h->d_cs, h->d_cs0, plane, rho, h->d_maxg2);
         launches++;
     }
     if (prof) cudaEventRecord(h->ev[1], st);
@@ -2155,7 +2160,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_claims, 0xff, sizeof(unsigned short) * plane * nf, st));
         GrowBufs gb;
-        gb.angdeg = h->d_ang; gb.g2 = h->d_g2; gb.cs = h->d_cs; gb.seeds = h->d_seeds; gb.n_seeds = h->d_nseeds;
+        gb.angdeg = h->d_ang; gb.g2 = h->d_g2; gb.cs = h->d_cs; gb.cs0 = h->d_cs0; gb.seeds = h->d_seeds; gb.n_seeds = h->d_nseeds;
         gb.claims = h->d_claims; gb.big_reg = h->d_reg; gb.big_touched = h->d_big_touched; gb.big_bits = h->d_big_bits;
         gb.pool_reg = h->d_spec_reg; gb.pool_touched = h->d_spec_touched; gb.pool_rect = h->d_pool_rect;
         gb.small_buf = h->d_small_buf; gb.small_rect = h->d_small_rect; gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
@@ -2258,6 +2263,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_scaled, B * align_up((size_t)W, 16) * H);
     A(&h->d_ang, B * plane);
     A(&h->d_cs, B * plane);
+    A(&h->d_cs0, B * plane);
     A(&h->d_nrects, B);
     A(&h->d_g2, B * plane);
     A(&h->d_reg, B * plane);
@@ -2399,7 +2405,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) pl::stream_sync(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_sticky, h->d_cs, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_claims, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_sticky, h->d_cs, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
