@@ -108,6 +108,21 @@ def test_grower_configuration_does_not_change_the_result(env, api, synth, monkey
     ref.close()
 
 
+def test_reserved_sms_do_not_change_the_result(api, synth):
+    """pl_line_set_reserved_sms only changes how many persistent grower CTAs are launched when a batch has more frames than SMs
+    (frames come from a counter); the segments must be the same, and a matcher call must be able to run next to the grower."""
+    frames = synth.frames(777, 160, 320, 240)   # more frames than SMs: the reservation applies
+    ex = api.LineExtractor(max_cols=320, max_rows=240, max_batch=160)
+    k0, d0, c0, n0 = ex.extract_batch(frames)
+    for r in (16, 100, 147):
+        ex.set_reserved_sms(r)
+        k1, d1, c1, n1 = ex.extract_batch(frames)
+        assert np.array_equal(n0, n1) and np.array_equal(k0, k1) and np.array_equal(d0, d1) and np.array_equal(c0, c1), r
+    with pytest.raises(api.N.PlError):
+        ex.set_reserved_sms(100000)
+    ex.close()
+
+
 def test_full_hd_frame(api, synth, oracle):
     """1920x1080: the committed bitmap of a frame takes most of the shared memory, so the grower runs one frame per CTA
     with fewer warps and a smaller tile pool — same result."""
