@@ -1044,6 +1044,7 @@ constexpr int kMaxFrameSlots = 4;  // frames a CTA works on at once
 constexpr int kSlots = 256;        // ticket slots per frame (the window of uncommitted tickets is at most this)
 constexpr int kPool = 64;          // region buffers per CTA
 constexpr int kSmall = 64;         // regions up to this size (and log length) are parked in their slot's small buffer instead
+constexpr int kTiny = 16;          // regions without a rectangle up to this size never leave shared memory: the points sit in their ticket slot
 constexpr int kSvalEntries = 36;
 constexpr int kMaxPoolTiles = 64, kMinPoolTiles = 24;
 // shared memory of a grower warp: sval | ring | tile pool | rev | dir | ntiles, each part 16-byte aligned
@@ -1059,8 +1060,9 @@ struct GrowSmem {
     __host__ __device__ size_t off_dir() const { return off_rev() + (((size_t)pool_tiles * sizeof(unsigned short) + 15) & ~(size_t)15); }
     __host__ __device__ size_t off_ntiles() const { return off_dir() + (((size_t)tiles + 15) & ~(size_t)15); }
     __host__ __device__ size_t per_grower() const { return off_ntiles() + 16; }
-    // per frame slot: ticket slots | committed bitmap
-    __host__ __device__ size_t per_frame() const { return kSlots * sizeof(int4) + (((size_t)bits_words * sizeof(unsigned int) + 15) & ~(size_t)15); }
+    // per frame slot: ticket slots | committed bitmap | tiny regions (kTiny points per ticket slot)
+    __host__ __device__ size_t off_tiny() const { return kSlots * sizeof(int4) + (((size_t)bits_words * sizeof(unsigned int) + 15) & ~(size_t)15); }
+    __host__ __device__ size_t per_frame() const { return off_tiny() + (size_t)kSlots * kTiny * sizeof(unsigned int); }
     __host__ __device__ size_t total(int growers) const { return (size_t)frame_slots * per_frame() + (size_t)growers * per_grower(); }
 };
 // ticket slot (shared memory, int4): x = seed pixel, y = region size, z = touched-log size,
@@ -1295,6 +1297,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
         volatile GrowCtl* ctl = ctlp;
         volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_raw + (size_t)fsi * gs.per_frame());
         unsigned int* s_used = reinterpret_cast<unsigned int*>(s_raw + (size_t)fsi * gs.per_frame() + kSlots * sizeof(int4));
+        unsigned int* s_tiny = reinterpret_cast<unsigned int*>(s_raw + (size_t)fsi * gs.per_frame() + gs.off_tiny());
         const volatile unsigned int* vused = s_used;
         if (action == kActInit || action == kActFinish) {
             // a finished frame is closed, and the slot gets the next frame, by one warp that holds both locks
@@ -1409,7 +1412,19 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                     // reads are issued together (one round trip instead of three dependent ones); the first 32 entries of the two
                     // lists — all of them for most regions — and the rectangle (24 words, one per lane) stay in registers.
                     unsigned rg0 = 0, tk0 = 0, rc0 = 0;
-                    if (!redo) {
+                    // Most tickets are regions of a few pixels that get no rectangle (85 % of the commits): their points never left
+                    // shared memory (the grower parked them in the ticket slot), so this serial section does not touch global memory
+                    // for them; the accept log of such a region is its point list.
+                    const bool tiny = !redo && status == kStNoRect && buf < 0 && n <= kTiny && nt == n;
+                    if (tiny) {
+                        if (lane < n) rg0 = s_tiny[(h % kSlots) * kTiny + lane];
+                        bool conflict = false;
+                        if (lane < n) {
+                            const unsigned o = (rg0 >> 16) * (unsigned)g.W + (rg0 & 0xffffu);
+                            conflict = ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
+                        }
+                        redo = __any_sync(FULL, conflict);
+                    } else if (!redo) {
                         const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
                         if (lane < nt) tk0 = tk[lane];
                         if (lane < n) rg0 = rg[lane];
@@ -1591,8 +1606,13 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
             lsd_grow_seed(s_view[warp], my_pix, g.min_reg_size, &s_res[warp]);
             res = s_res[warp];
             // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer
-            const bool small = res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
-            const bool keep = res.status >= 0 && !small;
+            const bool tiny = res.status == kStNoRect && res.n <= kTiny && res.nt == res.n;
+            if (tiny) {  // the ring still holds every point of such a region
+                if (lane < res.n) s_tiny[(my_ticket % kSlots) * kTiny + lane] = F.ring[lane];
+                __syncwarp();
+            }
+            const bool small = !tiny && res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
+            const bool keep = res.status >= 0 && !small && !tiny;
             if (small) {
                 unsigned int* dst = B.small_buf + ((cta_fs + fsi) * kSlots + (size_t)(my_ticket % kSlots)) * 2 * kSmall;
                 #pragma unroll 1
