@@ -36,7 +36,6 @@ p_kps, p_desc, p_n = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in 
 p_kls, p_ldesc, p_lco, p_ln = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (d_kls, d_ldesc, d_lco, d_ln))
 s_orb, s_line = torch.cuda.ExternalStream(gb.orb.stream()), torch.cuda.ExternalStream(gb.line.stream())
 ev_orb = torch.cuda.Event()
-ev_line = torch.cuda.Event()
 marks = []
 
 
@@ -63,9 +62,6 @@ class Timed:
 class LinesLater:
     def result(self):
         mark("lines wait >")
-        if os.environ.get("POLL", "0") == "1":  # poll instead of blocking in cudaStreamSynchronize while the other host thread launches work
-            while not ev_line.query():
-                time.sleep(0.0003)
         gb.line.sync()
         mark("lines ready")
         for dst, src in ((p_kls, d_kls), (p_ldesc, d_ldesc), (p_lco, d_lco), (p_ln, d_ln)):
@@ -91,7 +87,6 @@ def step():
     ev_orb.record(s_orb)
     s_line.wait_event(ev_orb)
     gb.line.extract_batch_dev(e_gray.data_ptr(), F, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
-    ev_line.record(s_line)
     gb.orb.sync()
     mark("ORB done")
     for dst, src in ((p_kps, d_kps), (p_desc, d_desc), (p_n, d_n)):
