@@ -1054,6 +1054,7 @@ struct GrowSmem {
     int frame_slots;  // frames per CTA
     int bits_words;   // words of a W*H bitmap
     int tail_nfa;     // CTAs without frames validate rectangles of finished frames
+    int poll_ns;      // sleep of a warp that found nothing to do before it looks again
     __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
     __host__ __device__ size_t off_pool() const { return off_ring() + kRegRing * sizeof(unsigned int); }
     __host__ __device__ size_t off_rev() const { return off_pool() + (size_t)pool_tiles * 32 * sizeof(unsigned int); }
@@ -1258,7 +1259,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
             }
             action = __shfl_sync(FULL, action, 0);
             if (action != kActNone) break;
-            __nanosleep(400);
+            __nanosleep(gs.poll_ns);
         }
         if (action == kActExit) {
             // no frame left for this CTA: validate rectangles of finished frames while other CTAs are still growing.  Once every
@@ -2043,6 +2044,7 @@ struct pl_line {
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     int tail_nfa = 1;
     GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
+    int poll_ns = 400;
     int reserved_sms = 0;          // SMs the region grower leaves to the kernels of other streams (pl_line_set_reserved_sms)
     unsigned int* d_big_bits = nullptr;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
@@ -2175,7 +2177,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         const int sms = std::max(1, h->num_sms - (nf > h->num_sms - h->reserved_sms ? h->reserved_sms : 0));
         const bool many = nf > sms && h->cfg_many.growers > 0;
         const GrowConfig& cf = many ? h->cfg_many : h->cfg_few;
-        GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words, h->tail_nfa};
+        GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words, h->tail_nfa, h->poll_ns};
         const int ctas = std::min(nf, sms);
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_claims, 0xff, sizeof(unsigned short) * plane * nf, st));
@@ -2313,7 +2315,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                 *c = GrowConfig{0, 0, fs};
                 for (int gN = max_g; gN >= 1 && c->growers == 0; gN--)
                     for (int pN = kMaxPoolTiles; pN >= kMinPoolTiles; pN -= 8) {
-                        GrowSmem gs{tiles, pN, 0, fs, h->bits_words, 0};
+                        GrowSmem gs{tiles, pN, 0, fs, h->bits_words, 0, 400};
                         if (gs.total(gN) <= budget) {
                             c->growers = gN;
                             c->pool_tiles = pN;
@@ -2341,12 +2343,13 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             }
             h->grow_tiles = tiles;
             if (const char* ev = getenv("PLSLAM_LSD_TAIL_NFA")) h->tail_nfa = atoi(ev) != 0;
+            if (const char* ev = getenv("PLSLAM_LSD_POLL_NS")) h->poll_ns = std::max(20, std::min(100000, atoi(ev)));
             if (const char* ev = getenv("PLSLAM_LSD_RESERVE_SMS")) h->reserved_sms = std::max(0, std::min(h->num_sms - 1, atoi(ev)));
             h->grow_window = 128;
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));
             if (h->cfg_few.growers < 1) {
                 set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region growers, the device offers %zu",
-                          max_cols, max_rows, GrowSmem{tiles, kMinPoolTiles, 0, 1, h->bits_words, 0}.total(1), budget);
+                          max_cols, max_rows, GrowSmem{tiles, kMinPoolTiles, 0, 1, h->bits_words, 0, 400}.total(1), budget);
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
