@@ -464,6 +464,15 @@ PL_API int pl_distinctive_descriptors(pl_match* h, const uint8_t* desc, const in
  * (Tracking.cc:79-91).  k1 == 0 copies the input, as the reference does (:739-743). */
 PL_API int pl_frame_undistort_points(pl_match* h, const float* xy, int n, float fx, float fy, float cx, float cy, const float dist_coef[5],
                                      float* xy_out);
+/* Frame::UndistortKeyLines (Frame.cc:767-845): both end points through cv::undistortPoints, then the derived KeyLine fields
+ * (pt, lineLength, numOfPixels = cv::LineIterator(...).count on the img_cols x img_rows image, angle, size, response) are
+ * recomputed from them; every other field is copied.  k1 == 0 copies the key lines (:768-771). */
+PL_API int pl_frame_undistort_keylines(pl_match* h, const pl_keyline* kls, int n, float fx, float fy, float cx, float cy, const float dist_coef[5],
+                                       int img_cols, int img_rows, pl_keyline* out);
+/* Frame::AssignFeaturesToGrid (Frame.cc:265-287) with PosInGrid (:527-538): mGrid flattened — cell c = x * 48 + y (64 x 48
+ * cells over bounds = mnMinX, mnMinY, mnMaxX, mnMaxY) owns sorted_idx[cell_start[c] .. cell_start[c + 1]) in ascending
+ * feature index; features outside the grid are dropped.  cell_start has 64 * 48 + 1 entries, sorted_idx n. */
+PL_API int pl_frame_assign_features_to_grid(pl_match* h, const pl_keypoint* keys_un, int n, const float bounds[4], int* cell_start, int* sorted_idx);
 /* F2: Frame::ComputeStereoFromRGBD (Frame.cc:1065-1117): d = imDepth.at<float>(v, u) at the truncated DISTORTED position
  * xy (mvKeys[i].pt, or a KeyLine end point), depth_out = d and u_right_out = x_un - bf / d when d > 0, else -1 / -1.
  * depth = n_frames float images (rows x cols, row stride step_bytes, frame f at depth + f * frame_stride_bytes).

@@ -1041,3 +1041,39 @@ extern "C" int orc_distinctive_descriptors(const uint8_t* desc, const int* group
     }
     return 0;
 }
+
+// Frame::UndistortKeyLines — src/Frame.cc:767-845 (end points through cv::undistortPoints, then the same field updates as
+// LineMatcher::UpdateKeyLineData) and Frame::AssignFeaturesToGrid — src/Frame.cc:265-287
+extern "C" int orc_frame_undistort_keylines(const pl_keyline* kls, int n, float fx, float fy, float cx, float cy, const float* dist_coef, int img_cols,
+                                            int img_rows, pl_keyline* out) {
+    if (dist_coef[0] == 0.0f) {
+        for (int i = 0; i < n; i++) out[i] = kls[i];
+        return 0;
+    }
+    for (int i = 0; i < n; i++) {
+        pl_keyline k = kls[i];
+        const float in[4] = {k.sx, k.sy, k.ex, k.ey};
+        float un[4];
+        orc_frame_undistort_points(in, 2, fx, fy, cx, cy, dist_coef, un);
+        const double nl[4] = {un[0], un[1], un[2], un[3]};
+        update_keyline(nl, k, img_cols, img_rows);
+        out[i] = k;
+    }
+    return 0;
+}
+extern "C" int orc_frame_assign_features_to_grid(const pl_keypoint* keys_un, int n, const float* bounds, int* cell_start, int* sorted_idx) {
+    pl_frame_view F;
+    memset(&F, 0, sizeof(F));
+    F.n = n;
+    F.keys_un = keys_un;
+    F.min_x = bounds[0]; F.min_y = bounds[1]; F.max_x = bounds[2]; F.max_y = bounds[3];
+    Grid grid(F);
+    int k = 0;
+    for (int x = 0; x < FRAME_GRID_COLS; x++)
+        for (int y = 0; y < FRAME_GRID_ROWS; y++) {
+            cell_start[x * FRAME_GRID_ROWS + y] = k;
+            for (int idx : grid.cell[x][y]) sorted_idx[k++] = idx;
+        }
+    cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = k;
+    return 0;
+}

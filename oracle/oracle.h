@@ -61,6 +61,8 @@ ORC_API int orc_frame_stereo_from_rgbd_batch(int n_frames, const float* depth, i
 ORC_API int orc_frame_unproject_batch(int n_frames, const int* off, const float* xy_un, const float* z, const float* rwc, const float* ow, float fx, float fy, float cx, float cy, float* world, uint8_t* valid);
 ORC_API int orc_frame_is_in_frustum_batch(int n_frames, const float* tcw, const float* ow, float fx, float fy, float cx, float cy, float bf, const float* bounds, int n_levels, float log_scale_factor, int m, const float* world_pos, const float* normal, const float* min_dist_inv, const float* max_dist_inv, const float* max_dist, float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* scale_level, float* view_cos);
 ORC_API int orc_frame_compute_stereo_matches(const orc_orb* left, const orc_orb* right, const pl_keypoint* keysL, const uint8_t* descL, int N, const pl_keypoint* keysR, const uint8_t* descR, int Nr, float mbf, float mb, float* mvuRight, float* mvDepth);
+ORC_API int orc_frame_undistort_keylines(const pl_keyline* kls, int n, float fx, float fy, float cx, float cy, const float* dist_coef, int img_cols, int img_rows, pl_keyline* out);
+ORC_API int orc_frame_assign_features_to_grid(const pl_keypoint* keys_un, int n, const float* bounds, int* cell_start, int* sorted_idx);
 ORC_API int orc_frame_lines_in_frustum_batch(int n_frames, const float* tcw, int m, const double* start3d, const double* end3d, uint8_t* in_view);
 
 /* ---- DBoW2 vocabulary transform (bow_oracle.cpp) ---- */

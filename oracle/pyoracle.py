@@ -527,6 +527,24 @@ def frame_compute_stereo_matches(left, right, keys_left, desc_left, keys_right, 
     return ur[:len(kl)], d[:len(kl)]
 
 
+def frame_undistort_keylines(kls, K, dist_coef, img_size):
+    kls = np.ascontiguousarray(kls, KL_DTYPE)
+    dc = np.ascontiguousarray(dist_coef, np.float32).reshape(-1)[:5].copy()
+    out = np.empty_like(kls)
+    lib().orc_frame_undistort_keylines(_p(kls), C.c_int(len(kls)), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]), C.c_float(K["cy"]), _p(dc),
+                                       C.c_int(int(img_size[0])), C.c_int(int(img_size[1])), _p(out))
+    return out
+
+
+def frame_assign_features_to_grid(keys_un, bounds):
+    k = np.ascontiguousarray(keys_un, KP_DTYPE)
+    b = np.asarray(bounds, np.float32)
+    cst = np.zeros(64 * 48 + 1, np.int32)
+    idx = np.zeros(max(len(k), 1), np.int32)
+    lib().orc_frame_assign_features_to_grid(_p(k), C.c_int(len(k)), _p(b), _p(cst), _p(idx))
+    return cst, idx[:cst[-1]]
+
+
 class VocOracle:
     """CPU restatement of DBoW2's vocabulary transform (bow_oracle.cpp)."""
 

@@ -541,6 +541,24 @@ class DescriptorMatcher:
                                                 C.c_float(K["cy"]), ptr(dc), ptr(out)))
         return out
 
+    def UndistortKeyLines(self, kls, K, dist_coef, img_size):
+        """Frame::UndistortKeyLines: end points through cv::undistortPoints, derived KeyLine fields recomputed."""
+        kls = np.ascontiguousarray(kls, N.KL_DTYPE)
+        dc = np.ascontiguousarray(dist_coef, np.float32).reshape(-1)[:5].copy()
+        out = np.empty_like(kls)
+        check(N.lib().pl_frame_undistort_keylines(self._h, ptr(kls), C.c_int(len(kls)), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]),
+                                                  C.c_float(K["cy"]), ptr(dc), C.c_int(int(img_size[0])), C.c_int(int(img_size[1])), ptr(out)))
+        return out
+
+    def AssignFeaturesToGrid(self, keys_un, bounds):
+        """Frame::AssignFeaturesToGrid -> (cell_start (64 * 48 + 1,), sorted_idx): cell x * 48 + y owns sorted_idx[cell_start[c]:cell_start[c + 1]]."""
+        k = np.ascontiguousarray(keys_un, N.KP_DTYPE)
+        b = np.asarray(bounds, np.float32)
+        cst = np.zeros(64 * 48 + 1, np.int32)
+        idx = np.zeros(max(len(k), 1), np.int32)
+        check(N.lib().pl_frame_assign_features_to_grid(self._h, ptr(k), C.c_int(len(k)), ptr(b), ptr(cst), ptr(idx)))
+        return cst, idx[:cst[-1]]
+
     def StereoFromRGBDBatch(self, depth, off, xy, x_un, bf, depth_dev_ptr=None):
         """Frame::ComputeStereoFromRGBD for the frames of a sequence -> (mvDepth, mvuRight) over the concatenated features.
         depth: (n_frames, rows, cols) float32 host array, or its shape when depth_dev_ptr gives a device copy."""

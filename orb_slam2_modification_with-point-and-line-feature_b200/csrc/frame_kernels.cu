@@ -20,25 +20,7 @@ __global__ void __launch_bounds__(256) k_undistort(const float2* __restrict__ xy
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float2 p = xy[i];
-    const double ifx = 1. / fx, ify = 1. / fy;
-    const double u = p.x, v = p.y;
-    double x = (u - cx) * ifx, y = (v - cy) * ify;
-    const double x0 = x, y0 = y;
-    for (int j = 0; j < 5; j++) {  // TermCriteria(MAX_ITER, 5, 0.01)
-        const double r2 = x * x + y * y;
-        const double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
-        if (icdist < 0) {
-            x = (u - cx) * ifx;
-            y = (v - cy) * ify;
-            break;
-        }
-        const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
-        const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y + 0. * r2 + 0. * r2 * r2;
-        x = (x0 - deltaX) * icdist;
-        y = (y0 - deltaY) * icdist;
-    }
-    const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
-    out[i] = make_float2((float)(xx * ww), (float)(yy * ww));
+    out[i] = undistort_point(p.x, p.y, fx, fy, cx, cy, k0, k1, k2, k3, k4);
 }
 
 // frame of feature i: binary search in the offsets (n_frames + 1 entries)

@@ -15,6 +15,33 @@ __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, cons
     return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
            __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
+
+#ifdef __CUDACC__
+// cv::undistortPoints(src, dst, K, D = (k1 k2 p1 p2 k3), noArray(), P = K) for one point: five fixed-point iterations of the inverse
+// Brown model in double (TermCriteria(MAX_ITER, 5, 0.01)), re-projection with P.  Pinned bit-exactly against cv2 4.13.
+__device__ __forceinline__ float2 undistort_point(float px, float py, double fx, double fy, double cx, double cy, double k0, double k1, double k2,
+                                                  double k3, double k4) {
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double u = px, v = py;
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+        if (icdist < 0) {
+            x = (u - cx) * ifx;
+            y = (v - cy) * ify;
+            break;
+        }
+        const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+        const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y + 0. * r2 + 0. * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+    return make_float2((float)(xx * ww), (float)(yy * ww));
+}
+#endif
 }  // namespace pl
 
 // one pinned host buffer + one device buffer: every input of a call is packed into it and uploaded with ONE copy

@@ -1802,3 +1802,89 @@ PL_API int pl_orb_search_for_initialization(pl_match* h, const pl_frame_view* F1
 }
 
 }  // extern "C"
+
+// ---- Frame::UndistortKeyLines / Frame::AssignFeaturesToGrid ----
+namespace pl {
+__global__ void __launch_bounds__(256) k_undistort_keylines(const pl_keyline* __restrict__ kls, int n, double fx, double fy, double cx, double cy,
+                                                            double k0, double k1, double k2, double k3, double k4, int cols, int rows,
+                                                            pl_keyline* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pl_keyline k = kls[i];
+    const float2 s = undistort_point(k.sx, k.sy, fx, fy, cx, cy, k0, k1, k2, k3, k4);
+    const float2 e = undistort_point(k.ex, k.ey, fx, fy, cx, cy, k0, k1, k2, k3, k4);
+    const double nl[4] = {(double)s.x, (double)s.y, (double)e.x, (double)e.y};
+    update_keyline(nl, k, cols, rows);  // the same field updates as LineMatcher::UpdateKeyLineData (Frame.cc:823-842 == LineMatcher.cpp:1601-1624)
+    out[i] = k;
+}
+}  // namespace pl
+
+extern "C" {
+
+PL_API int pl_frame_undistort_keylines(pl_match* h, const pl_keyline* kls, int n, float fx, float fy, float cx, float cy, const float dist_coef[5],
+                                       int img_cols, int img_rows, pl_keyline* out) {
+    PL_CHECK_ARG(h && n >= 0 && dist_coef && (n == 0 || (kls && out)) && fx != 0.f && fy != 0.f && img_cols > 0 && img_rows > 0);
+    if (n == 0) return PL_OK;
+    if (dist_coef[0] == 0.0f) {  // Frame.cc:768-771: mvKeyLinesUn = mvKeyLines
+        memmove(out, kls, (size_t)n * sizeof(pl_keyline));
+        return PL_OK;
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    int rc = h->in.reserve(padb((size_t)n * sizeof(pl_keyline)) * 2);
+    if (rc != PL_OK) return rc;
+    const pl_keyline* d_in = h->in.put(kls, (size_t)n);
+    pl_keyline* h_out;
+    pl_keyline* d_out = h->in.out<pl_keyline>((size_t)n, &h_out);
+    cudaStream_t st = h->stream;
+    if ((rc = h->in.upload(st)) != PL_OK) return rc;
+    k_undistort_keylines<<<(n + 255) / 256, 256, 0, st>>>(d_in, n, (double)fx, (double)fy, (double)cx, (double)cy, (double)dist_coef[0],
+                                                          (double)dist_coef[1], (double)dist_coef[2], (double)dist_coef[3], (double)dist_coef[4],
+                                                          img_cols, img_rows, d_out);
+    h->last_launches++;
+    PL_CUDA_TRY(cudaGetLastError());
+    PL_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, (size_t)n * sizeof(pl_keyline), cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(pl::stream_sync(st));
+    memcpy(out, h_out, (size_t)n * sizeof(pl_keyline));
+    return PL_OK;
+}
+
+PL_API int pl_frame_assign_features_to_grid(pl_match* h, const pl_keypoint* keys_un, int n, const float bounds[4], int* cell_start, int* sorted_idx) {
+    PL_CHECK_ARG(h && n >= 0 && n <= 65535 && bounds && cell_start && (n == 0 || (keys_un && sorted_idx)) && bounds[2] > bounds[0] && bounds[3] > bounds[1]);
+    if (n == 0) {
+        for (int c = 0; c <= kGridCells; c++) cell_start[c] = 0;
+        return PL_OK;
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    int rc = h->in.reserve(padb(sizeof(SearchDev)) + padb((size_t)n * sizeof(pl_keypoint)) + padb((size_t)n2 * 4) + padb((size_t)(kGridCells + 1) * 4));
+    if (rc != PL_OK) return rc;
+    SearchDev S;
+    memset(&S, 0, sizeof(S));
+    S.F.n = n;
+    S.F.keys = h->in.put(keys_un, (size_t)n);
+    S.F.min_x = bounds[0]; S.F.min_y = bounds[1]; S.F.max_x = bounds[2]; S.F.max_y = bounds[3];
+    S.F.inv_w = (float)kGridCols / (bounds[2] - bounds[0]);  // mfGridElementWidthInv (Frame.cc:184)
+    S.F.inv_h = (float)kGridRows / (bounds[3] - bounds[1]);
+    S.n2 = n2;
+    int *h_sorted, *h_cst;
+    int* d_sorted = h->in.out<int>((size_t)n2, &h_sorted);
+    int* d_cst = h->in.out<int>((size_t)kGridCells + 1, &h_cst);
+    const SearchDev* d_sd = h->in.put(&S, 1);
+    cudaStream_t st = h->stream;
+    if ((rc = h->in.upload(st)) != PL_OK) return rc;
+    if ((size_t)n2 * 4 > 48 * 1024) PL_CUDA_TRY(cudaFuncSetAttribute(k_frame_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, n2 * 4));
+    k_frame_grid<<<1, 1024, (size_t)n2 * 4, st>>>(d_sd, d_sorted, d_cst);
+    h->last_launches++;
+    PL_CUDA_TRY(cudaGetLastError());
+    PL_CUDA_TRY(cudaMemcpyAsync(h_sorted, d_sorted, (size_t)n2 * 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(cudaMemcpyAsync(h_cst, d_cst, (size_t)(kGridCells + 1) * 4, cudaMemcpyDeviceToHost, st));
+    PL_CUDA_TRY(pl::stream_sync(st));
+    memcpy(cell_start, h_cst, (size_t)(kGridCells + 1) * 4);
+    memcpy(sorted_idx, h_sorted, (size_t)h_cst[kGridCells] * 4);
+    return PL_OK;
+}
+
+}  // extern "C"

@@ -144,3 +144,34 @@ def test_compute_stereo_matches_degenerate(api, oracle, synth):
     assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.all(o[0] == -1)
     g = dm.ComputeStereoMatches(el, er, kl, dl, kr[:0], dr[:0], K["bf"], b)
     assert np.all(g[0] == -1) and np.all(g[1] == -1)
+
+
+@pytest.mark.parametrize("n", [0, 1, 80, 5000])
+def test_undistort_keylines(n, api, oracle, synth):
+    rng = np.random.default_rng(n)
+    kls = np.zeros(n, api.N.KL_DTYPE)
+    for f_ in ("sx", "ex"):
+        kls[f_] = rng.uniform(0, 640, n).astype(f32)
+    for f_ in ("sy", "ey"):
+        kls[f_] = rng.uniform(0, 480, n).astype(f32)
+    kls["class_id"] = np.arange(n)
+    kls["octave"] = rng.integers(0, 2, n)
+    dm = api.DescriptorMatcher()
+    for D in (matchgen.TUM1_DIST, np.zeros(5, f32)):
+        g = dm.UndistortKeyLines(kls, synth.TUM1, D, (640, 480))
+        o = oracle.frame_undistort_keylines(kls, synth.TUM1, D, (640, 480))
+        for name in api.N.KL_DTYPE.names:
+            if name == "angle":     # atan2f: CUDA libm vs glibc, tolerance of the line path
+                assert np.allclose(g[name], o[name], rtol=1e-4, atol=1e-6)
+            else:
+                assert np.array_equal(g[name], o[name]), name
+
+
+@pytest.mark.parametrize("n,bounds", [(0, (0, 0, 640, 480)), (1, (0, 0, 640, 480)), (1000, (0, 0, 640, 480)), (3000, (-12.5, -9.25, 655.0, 490.5)),
+                                      (2000, (100, 100, 300, 200))])
+def test_assign_features_to_grid(n, bounds, api, oracle):
+    rng = np.random.default_rng(n)
+    kp, _, _ = matchgen.rand_frame(rng, n, api.N)
+    g = api.DescriptorMatcher().AssignFeaturesToGrid(kp, bounds)
+    o = oracle.frame_assign_features_to_grid(kp, bounds)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1])

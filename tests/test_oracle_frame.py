@@ -102,3 +102,32 @@ def test_compute_stereo_matches_recovers_the_disparity(oracle, synth):
     assert np.median(err) < 0.6 and (err < 2.0).mean() > 0.85
     assert np.array_equal(dep[ok], (f32(K["bf"]) / (kl["x"][ok] - ur[ok])).astype(f32))
     assert np.all(dep[~ok] == -1)
+
+
+def test_undistort_keylines_and_grid_vs_numpy(oracle, synth):
+    cv2 = pytest.importorskip("cv2")
+    K = synth.TUM1
+    img = synth.frame(1000, 640, 480)
+    kls, _, _ = oracle.line_extract(img, 80)
+    out = oracle.frame_undistort_keylines(kls, K, matchgen.TUM1_DIST, (640, 480))
+    Km = np.array([[K["fx"], 0, K["cx"]], [0, K["fy"], K["cy"]], [0, 0, 1]], np.float32)
+    for a, b in (("sx", "sy"), ("ex", "ey")):
+        ref = cv2.undistortPoints(np.stack([kls[a], kls[b]], 1).reshape(-1, 1, 2), Km, matchgen.TUM1_DIST, None, Km).reshape(-1, 2)
+        assert np.array_equal(out[a], ref[:, 0]) and np.array_equal(out[b], ref[:, 1])
+    assert np.array_equal(out["sx_oct"], out["sx"]) and np.array_equal(out["class_id"], kls["class_id"]) and np.array_equal(out["octave"], kls["octave"])
+    assert np.array_equal(out["pt_x"], (out["ex"] + out["sx"]) / f32(2))
+    ln = np.sqrt((out["sx"] - out["ex"]).astype(np.float64) ** 2 + (out["sy"] - out["ey"]).astype(np.float64) ** 2).astype(f32)
+    assert np.array_equal(out["length"], ln) and np.array_equal(out["response"], ln / f32(640))
+    assert np.array_equal(oracle.frame_undistort_keylines(kls, K, np.zeros(5, f32), (640, 480)), kls)
+    # grid: every feature inside the bounds sits in the cell PosInGrid gives it, ascending inside a cell
+    kp, _ = oracle.OrbOracle(1000).extract(img)
+    cst, idx = oracle.frame_assign_features_to_grid(kp, (0, 0, 640, 480))
+    c_round = lambda v: np.where(v >= 0, np.floor(v.astype(np.float64) + 0.5), -np.floor(-v.astype(np.float64) + 0.5)).astype(np.int64)  # round(): half away from zero
+    px = c_round((kp["x"] - f32(0)) * (f32(64) / f32(640)))
+    py = c_round((kp["y"] - f32(0)) * (f32(48) / f32(480)))
+    inside = (px >= 0) & (px < 64) & (py >= 0) & (py < 48)
+    assert cst[-1] == inside.sum() and sorted(idx.tolist()) == np.nonzero(inside)[0].tolist()
+    cell_of = px * 48 + py
+    for c in np.unique(cell_of[inside])[:200]:
+        got = idx[cst[c]:cst[c + 1]]
+        assert np.array_equal(got, np.nonzero(inside & (cell_of == c))[0])
