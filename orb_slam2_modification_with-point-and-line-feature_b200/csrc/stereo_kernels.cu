@@ -184,12 +184,17 @@ PL_API int pl_frame_compute_stereo_matches(pl_match* h, pl_orb* left, pl_orb* ri
     int rc;
     if ((rc = pl_orb_scale_factors(left, S.sf)) != PL_OK || (rc = pl_orb_inv_scale_factors(left, S.invsf)) != PL_OK) return rc;
     for (int l = 0; l < S.n_levels; l++) {
-        int rows = 0, cols = 0;
+        int rows = 0, cols = 0, rrows = 0;
         if ((rc = pl_orb_pyramid_dev(left, frame, l, &S.l[l], &S.lp[l], &rows, &cols)) != PL_OK) return rc;
         if (l == 0) S.n_rows0 = rows;
-        if ((rc = pl_orb_pyramid_dev(right, frame, l, &S.r[l], &S.rp[l], &rows, &S.rcols[l])) != PL_OK) return rc;
+        if ((rc = pl_orb_pyramid_dev(right, frame, l, &S.r[l], &S.rp[l], &rrows, &S.rcols[l])) != PL_OK) return rc;
+        PL_CHECK_ARG(rrows == rows && S.rcols[l] == cols);  // a rectified pair: the SAD windows index both pyramids with the same rows
     }
-    for (int i = 0; i < n_left; i++) PL_CHECK_ARG(keys_left[i].octave >= 0 && keys_left[i].octave < S.n_levels);
+    int w0 = 0, h0 = 0;
+    pl_orb_pyramid_dims(left, 0, &h0, &w0);
+    for (int i = 0; i < n_left; i++)  // inside the image: the SAD window around the scaled position then stays inside the bordered plane
+        PL_CHECK_ARG(keys_left[i].octave >= 0 && keys_left[i].octave < S.n_levels && keys_left[i].x >= 0.f && keys_left[i].x < (float)w0 &&
+                     keys_left[i].y >= 0.f && keys_left[i].y < (float)h0);
     for (int i = 0; i < n_right; i++) PL_CHECK_ARG(keys_right[i].octave >= 0 && keys_right[i].octave < S.n_levels);
     PL_CUDA_TRY(cudaSetDevice(h->device));
     h->last_launches = 0;
