@@ -60,3 +60,27 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
         raise AssertionError("expected ImportError")
     except ImportError as e:
         assert "no CPU or PyTorch fallback" in str(e)
+
+
+def test_cpp_host_mirrors_compile_and_link(tmp_path):
+    """Every header-only C++ mirror (ORBextractor, LineExtractor, ORBmatcher / LineMatcher incl. the E rows, ORBVocabulary,
+    FrameGlue) compiles as C++14 against the OpenCV-free stand-ins and links against the C-ABI library: each method's call into
+    the ABI has the declared signature.  (Nothing is executed: no GPU here.)"""
+    build = importlib.import_module(PKG + ".build")
+    build.build()
+    host = os.path.join(ROOT, PKG, "host")
+    src = tmp_path / "mirrors.cpp"
+    src.write_text('#include "ORBextractor.h"\n#include "LineExtractor.h"\n#include "Matchers.h"\n#include "FrameGlue.h"\n'
+                   "int use(ORB_SLAM2::ORBmatcher& m, ORB_SLAM2::ORBVocabulary& v, ORB_SLAM2::FrameGlue& g) {\n"
+                   "  std::vector<int> out; std::vector<std::pair<size_t, size_t>> pairs; std::vector<cv::Point2f> prev;\n"
+                   "  pl_frame_view f{}; pl_posepoint_view p{}; pl_triang_view t{}; float z[12] = {0};\n"
+                   "  DBoW2::BowVector bv; DBoW2::FeatureVector fv; std::vector<cv::KeyPoint> k, ku; std::vector<float> a, b;\n"
+                   "  int n = m.Fuse(f, p, z, 0.18f, z, 3.f, out) + m.Fuse(f, z, 0.18f, p, 3.f, out) + m.SearchBySim3(f, f, p, p, z, z, 0.18f, 0.18f, 7.5f, out);\n"
+                   "  n += m.SearchForInitialization(f, f, prev, out, 100) + m.SearchForTriangulation(t, t, z, z, z, 1, 1, 0, 0, z, z, 8, pairs, false);\n"
+                   "  m.ComputeDistinctiveDescriptors(nullptr, std::vector<int>{0}, out);\n"
+                   "  v.transform(nullptr, 0, bv, fv, 4); g.UndistortKeyPoints(k, 1, 1, 0, 0, z, ku); g.ComputeStereoFromRGBD(z, 1, 1, 4, k, ku, 40.f, a, b);\n"
+                   "  return n + (v.empty() ? 1 : 0);\n}\nint main() { return 0; }\n")
+    exe = tmp_path / "mirrors"
+    r = subprocess.run(["g++", "-std=c++14", "-Wall", "-I", host, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L" + os.path.join(ROOT, PKG), "-lplslam", "-Wl,-rpath," + os.path.join(ROOT, PKG)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
