@@ -163,6 +163,14 @@ class RecordingBackend:
     def line_search_batch(self, *a):
         return self.plan.record("line_search_batch", *a)
 
+    # the Frame glue of the plan pass goes through the same F-row calls as the end-to-end pass (not recorded: the device-resident
+    # step replays the matcher calls only)
+    def unproject_batch(self, *a):
+        return self.gb.unproject_batch(*a)
+
+    def is_in_frustum_batch(self, *a):
+        return self.gb.is_in_frustum_batch(*a)
+
 
 def run_ours(a, rank, world, local_rank, dist):
     import torch
@@ -207,7 +215,7 @@ def run_ours(a, rank, world, local_rank, dist):
     # one untimed pass through the public API: features + the matching plan (caller state) of the sequence
     feats = (gb.extract_orb(gray), gb.extract_lines(gray))
     plan = MatchPlan(gb)
-    plan_fe = fe.TrackingFrontEnd(RecordingBackend(gb, feats, plan))   # keeps the arrays behind the recorded views alive
+    plan_fe = fe.TrackingFrontEnd(RecordingBackend(gb, feats, plan), device_glue=bool(a.device_glue))   # keeps the arrays behind the recorded views alive
     summary = plan_fe.run(gray, depth, Tcw, sf, features=feats)
     extract_dev()
     launches_per_step = gb.orb.last_launches() + gb.line.last_launches() + plan.launches
@@ -444,7 +452,7 @@ def cpu_pass(gray, depth, Tcw, threads):
             fo = [ex.submit(orb_job, i) for i in range(n)]
             fl = [ex.submit(pyoracle.line_extract, gray[i], 80) for i in range(n)]
             feats = ([f.result() for f in fo], [f.result() for f in fl])
-    summary = fe.TrackingFrontEnd(ob).run(gray, depth, Tcw[:n], sf, features=feats)
+    summary = fe.TrackingFrontEnd(ob, device_glue=True).run(gray, depth, Tcw[:n], sf, features=feats)  # the same glue as the GPU arm's default
     return time.perf_counter() - t0, summary
 
 
