@@ -137,11 +137,26 @@ class MatchPlan:
         return r
 
     def replay(self, which=None):
-        """which = None: every call; "points" / "lines": the ORBmatcher / LineMatcher calls only."""
+        """which = None: every call; "points" / "lines": the ORBmatcher / LineMatcher calls only.  The line searches of the plan
+        (D3 against the last frame, D5 against the local map) are independent calls: they run side by side on two host threads,
+        each on its own matcher handle."""
+        line_calls = []
         for name, args in self.calls:
             is_line = name.startswith("line_")
             if which is None or (which == "lines") == is_line:
-                getattr(self.gb, name)(*args)
+                if is_line:
+                    line_calls.append(args)
+                else:
+                    getattr(self.gb, name)(*args)
+        if len(line_calls) == 2:
+            import threading
+            th = threading.Thread(target=lambda: self.gb.line_search_batch(*line_calls[0]))
+            th.start()
+            self.gb.line_search_batch(*line_calls[1][:2], True)
+            th.join()
+        else:
+            for args in line_calls:
+                self.gb.line_search_batch(*args)
 
 
 class RecordingBackend:
@@ -236,6 +251,7 @@ def run_ours(a, rank, world, local_rank, dist):
         plan.replay("lines")
         gb.m.sync()
         gb.ml.sync()
+        gb.ml2.sync()
 
     e2e_fe = fe.TrackingFrontEnd(gb, device_glue=bool(a.device_glue))
 
@@ -308,6 +324,7 @@ def run_ours(a, rank, world, local_rank, dist):
     plan.replay()
     gb.m.sync()
     gb.ml.sync()
+    gb.ml2.sync()
     t_match = time.perf_counter() - t1
     # ---- dominant-kernel timing (CUDA events on the launching stream, inside the same process) ----
     N.check(N.lib().pl_line_set_profiling(gb.line._h, 1))

@@ -370,9 +370,26 @@ class TrackingFrontEnd:
             cur_view[t] = N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep)
             lcv.append(cur_view[t])
             llv.append(N.make_mapline_view(s3, e3, last.kls, last.ldesc, okl, keep))
-        rd3 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
-        for t, (ml, nl, rel, npj) in zip(d3_t, rd3):
-            summary[t].update(d3_proj=npj, d3_matches=nl, d3_relaxed=rel, d3_sum=self._chk(ml))
+        def d3_search(lcv=lcv, llv=llv):
+            rd3 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
+            for t, (ml, nl, rel, npj) in zip(d3_t, rd3):
+                summary[t].update(d3_proj=npj, d3_matches=nl, d3_relaxed=rel, d3_sum=self._chk(ml))
+
+        d3_worker = None
+        two_handles = batch and getattr(self.b, "concurrent_sides", False)
+        if two_handles:  # D3 and D5 are independent: D3 runs on its own thread / handle while D5 is prepared and issued
+            import threading
+            d3_err = []
+
+            def d3_guarded():
+                try:
+                    d3_search()
+                except BaseException as e:
+                    d3_err.append(e)
+            d3_worker = threading.Thread(target=d3_guarded)
+            d3_worker.start()
+        else:
+            d3_search()
         # ---- D5: LineMatcher(0.8).SearchByProjection(F, localLines) (Tracking.cc:1863) ----
         d5_t = [t for t in c2_t if len(lmaps[t][2]) and len(frames[t].kls)]
         lcv, llv = [], []
@@ -384,9 +401,16 @@ class TrackingFrontEnd:
             if id(lkl) not in snap_view:
                 snap_view[id(lkl)] = N.make_mapline_view(ls, le, lkl, ldesc, np.ones(len(lkl), np.uint8), keep)
             llv.append(snap_view[id(lkl)])
-        rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
+        if two_handles:
+            rd5 = self.b.line_search_batch(lcv, llv, True)
+        else:
+            rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
         for t, (ml, nl, rel, npj) in zip(d5_t, rd5):
             summary[t].update(d5_proj=npj, d5_matches=nl, d5_relaxed=rel, d5_sum=self._chk(ml))
+        if d3_worker is not None:
+            d3_worker.join()
+            if d3_err:
+                raise d3_err[0]
         if worker is not None:
             worker.join()
             if err:
@@ -403,6 +427,7 @@ class GpuBackend:
         self.line = api.LineExtractor(device=device, max_cols=cols, max_rows=rows, max_batch=chunk)
         self.m = api.DescriptorMatcher(device=device)
         self.ml = api.DescriptorMatcher(device=device)   # the line side's own handle: stream + staging buffers
+        self.ml2 = api.DescriptorMatcher(device=device)  # D3 and D5 are independent calls: a handle each lets them run side by side
         self.concurrent_sides = True
 
     def scale_factors(self):
@@ -434,8 +459,8 @@ class GpuBackend:
     def search_local_points_batch(self, fvs, mvs, th, nn):
         return self.m.SearchByProjectionLocalPointsBatch(fvs, mvs, th, nn)
 
-    def line_search_batch(self, cvs, lvs):
-        return self.ml.SearchLinesByProjectionBatch(cvs, lvs)
+    def line_search_batch(self, cvs, lvs, second=False):
+        return (self.ml2 if second else self.ml).SearchLinesByProjectionBatch(cvs, lvs)
 
     # F rows (Frame glue): UnprojectStereo / IsInFrustum of many frames in one call
     def unproject_batch(self, off, xy, z, rwc, ow, K):

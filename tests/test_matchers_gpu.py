@@ -44,15 +44,17 @@ class Recorder:
 
 
 def _flatten(log):
-    """Calls of the log as (kind, result), grouped by kind (call order inside a kind is kept): the point searches and the line
-    searches may run on two host threads, so their relative order in the log is not defined."""
+    """Calls of the log as (kind, result), grouped by kind: the point searches and the line searches may run on several host
+    threads, so their relative order in the log is not defined."""
     out = []
     for k, r in log:
         if k.endswith("_batch"):
             out += [(k[:-6], x) for x in r]
         else:
             out.append((k, r))
-    return sorted(out, key=lambda e: e[0])
+    # the two line searches of a frame (D3, D5) may also run side by side: inside a kind the results are ordered by content,
+    # so both arms are compared as multisets of (kind, result)
+    return sorted(out, key=lambda e: (e[0], len(e[1][0]), e[1][0].tobytes(), tuple(int(x) for x in e[1][1:])))
 
 
 def test_sequence_matchers_bit_exact(seq, feats, api, oracle, pkg):
