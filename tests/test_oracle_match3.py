@@ -270,3 +270,92 @@ def test_search_for_triangulation_vs_naive(seed, m, e1, e2, nodes, only_stereo, 
             assert o[1] == nm and np.array_equal(o[0], p)
     if m >= 200 and not only_stereo:
         assert o[1] > 30
+
+
+def naive_fuse(fv, pv, ow, log_sf, inv_s2, th, variant):
+    """ORBmatcher::Fuse (both overloads) restated with numpy float32 scalars, point by point (ORBmatcher.cc:1124-1249 / 1314-1404)."""
+    import ctypes as C
+    f = np.float32
+    kp, desc = _view_arrays(fv)
+    n, m = fv.n, pv.n
+    arr = lambda addr, dt, cnt: np.frombuffer((C.c_char * (cnt * np.dtype(dt).itemsize)).from_address(addr), dt)
+    ur = arr(fv.u_right, np.float32, n)
+    sfs = arr(fv.scale_factors, np.float32, fv.n_levels)
+    valid, Xw = arr(pv.valid, np.uint8, m), arr(pv.world_pos, np.float32, 3 * m).reshape(m, 3)
+    pdesc = arr(pv.desc, np.uint8, 32 * m).reshape(m, 32)
+    mi, ma, mr = arr(pv.min_dist_inv, np.float32, m), arr(pv.max_dist_inv, np.float32, m), arr(pv.max_dist, np.float32, m)
+    nrm = arr(pv.normal, np.float32, 3 * m).reshape(m, 3)
+    T = np.array(list(fv.tcw), np.float32).reshape(3, 4)
+    invw, invh = f(64) / f(fv.max_x - fv.min_x), f(48) / f(fv.max_y - fv.min_y)
+    cells = {}
+    for i, k in enumerate(kp):
+        cx = int(np.floor(np.float64(f((k["x"] - f(fv.min_x)) * invw)) + 0.5)); cy = int(np.floor(np.float64(f((k["y"] - f(fv.min_y)) * invh)) + 0.5))
+        if 0 <= cx < 64 and 0 <= cy < 48:
+            cells.setdefault((cx, cy), []).append(i)
+    best_idx = np.full(m, -1, np.int32)
+    best_dist = np.full(m, 256, np.int32)
+    for i in range(m):
+        if not valid[i]:
+            continue
+        pc = [f(sum(np.float64(T[r, k]) * np.float64(Xw[i, k]) for k in range(3)) + np.float64(T[r, 3])) for r in range(3)]
+        if pc[2] < 0:
+            continue
+        invz = f(f(1) / pc[2]) if variant == 0 else f(1.0 / np.float64(pc[2]))
+        u = f(f(f(fv.fx) * f(pc[0] * invz)) + f(fv.cx)); v = f(f(f(fv.fy) * f(pc[1] * invz)) + f(fv.cy))
+        if not (u >= f(fv.min_x) and u < f(fv.max_x) and v >= f(fv.min_y) and v < f(fv.max_y)):
+            continue
+        urp = f(u - f(f(fv.bf) * invz))
+        PO = [f(Xw[i, k] - ow[k]) for k in range(3)]
+        dist3 = f(np.sqrt(sum(np.float64(x) * np.float64(x) for x in PO)))
+        if dist3 < mi[i] or dist3 > ma[i]:
+            continue
+        if sum(np.float64(PO[k]) * np.float64(nrm[i, k]) for k in range(3)) < 0.5 * np.float64(dist3):
+            continue
+        ratio = f(mr[i] / dist3)
+        lvl = int(np.ceil(f(f(np.log(ratio)) / f(log_sf))))
+        lvl = min(max(lvl, 0), fv.n_levels - 1)
+        r = f(f(th) * sfs[lvl])
+        x0 = max(0, int(np.floor(f(f(f(u - f(fv.min_x)) - r) * invw)))); x1 = min(63, int(np.ceil(f(f(f(u - f(fv.min_x)) + r) * invw))))
+        y0 = max(0, int(np.floor(f(f(f(v - f(fv.min_y)) - r) * invh)))); y1 = min(47, int(np.ceil(f(f(f(v - f(fv.min_y)) + r) * invh))))
+        if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+            continue
+        bd, bi = 256, -1
+        for cx in range(x0, x1 + 1):
+            for cy in range(y0, y1 + 1):
+                for j in cells.get((cx, cy), []):
+                    k = kp[j]
+                    if not (abs(f(k["x"] - u)) < r and abs(f(k["y"] - v)) < r):
+                        continue
+                    if k["octave"] < lvl - 1 or k["octave"] > lvl:
+                        continue
+                    if variant == 0:
+                        ex, ey = f(u - k["x"]), f(v - k["y"])
+                        if ur[j] >= 0:
+                            er = f(urp - ur[j])
+                            e2 = f(f(f(ex * ex) + f(ey * ey)) + f(er * er))
+                            if np.float64(f(e2 * inv_s2[k["octave"]])) > 7.8:
+                                continue
+                        else:
+                            e2 = f(f(ex * ex) + f(ey * ey))
+                            if np.float64(f(e2 * inv_s2[k["octave"]])) > 5.99:
+                                continue
+                    d = _popcnt(pdesc[i], desc[j])
+                    if d < bd:
+                        bd, bi = d, j
+        best_dist[i] = bd
+        if bd <= TH_LOW:
+            best_idx[i] = bi
+    return best_idx, best_dist
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fuse_vs_naive(variant, oracle, synth):
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    rng = np.random.default_rng(31 + variant)
+    fv, pv, ow, log_sf, inv_s2, keep = matchgen.fuse_case(rng, 350, 120, N, synth.TUM1, sf)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        bi, bd = naive_fuse(fv, pv, ow, log_sf, inv_s2, 3.0, variant)
+    oi, od, nf = oracle.fuse_candidates(fv, pv, ow, log_sf, inv_s2, 3.0, variant)
+    # numpy's float32 log may differ from glibc's logf in the last ulp at a ceil() edge of PredictScale: allow a stray point
+    assert (bi != oi).sum() <= 1 and (bd != od).sum() <= 1
+    assert nf == int((oi >= 0).sum()) and nf > 60
