@@ -430,6 +430,8 @@ struct Lsd {
 
     struct Seg { float x1, y1, x2, y2; double width, p, nfa; };
 
+    std::vector<int>* trace = nullptr;  // lab hook: per grown region {seed pixel, size of the first growth, final size, outcome}
+
     void detect(const uint8_t* img, int w, int h, size_t step, std::vector<Seg>& out) {
         out.clear();
         const double prec = kPi * ANG_TH / 180;
@@ -454,10 +456,16 @@ struct Lsd {
             if (used[(size_t)py * W + px] == 0 && ang(px, py) != NOTDEF) {
                 double reg_angle;
                 region_grow(px, py, reg, reg_angle, prec);
-                if (reg.size() < min_reg_size) continue;
+                const int n_first = (int)reg.size();
+                if (reg.size() < min_reg_size) {
+                    if (trace) trace->insert(trace->end(), {py * W + px, n_first, n_first, 0});
+                    continue;
+                }
                 Rect rec;
                 region2rect(reg, reg_angle, prec, p, rec);
-                if (!refine(reg, reg_angle, prec, p, rec, DENSITY_TH)) continue;
+                const bool refined = refine(reg, reg_angle, prec, p, rec, DENSITY_TH);
+                if (trace) trace->insert(trace->end(), {py * W + px, n_first, (int)reg.size(), refined ? 1 : 0});
+                if (!refined) continue;
                 double log_nfa = rect_improve(rec);
                 if (log_nfa <= LOG_EPS) continue;
                 rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
@@ -665,6 +673,20 @@ extern "C" int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t ste
         if (nfa) nfa[i] = segs[i].nfa;
     }
     return (int)segs.size();
+}
+
+// lab hook: the regions flsd() grows, in order: {seed pixel (y * W + x of the scaled image), size of the first growth, final size
+// (after refine), 1 = got a rectangle}; returns the number of regions
+extern "C" int orc_lsd_trace(const uint8_t* img, int rows, int cols, size_t step, int* out4, int cap) {
+    Lsd lsd;
+    std::vector<int> tr;
+    lsd.trace = &tr;
+    std::vector<Lsd::Seg> segs;
+    lsd.detect(img, cols, rows, step, segs);
+    const int n = (int)(tr.size() / 4);
+    for (int i = 0; i < n && i < cap; i++)
+        for (int k = 0; k < 4; k++) out4[4 * i + k] = tr[4 * i + k];
+    return n;
 }
 
 // lab hook: level-line angle map (radians, NOTDEF=-1024) of the scaled image

@@ -74,6 +74,7 @@ ORC_API int orc_voc_info(const orc_voc* v, int* k, int* L, int* n_nodes, int* n_
 ORC_API int orc_voc_transform(const orc_voc* v, const uint8_t* desc, int n, int levelsup, int* n_words, unsigned* word_id, double* word_value, int* n_fv_nodes, unsigned* node_id, int* node_off, unsigned* feat_idx);
 
 /* ---- line extraction (line_oracle.cpp) ---- */
+ORC_API int orc_lsd_trace(const uint8_t* img, int rows, int cols, size_t step, int* out4, int cap);
 ORC_API int orc_lsd_detect(const uint8_t* img, int rows, int cols, size_t step, int order_mode, float* xyxy, double* width, double* prec, double* nfa, int cap);
 ORC_API int orc_lsd_angles(const uint8_t* img, int rows, int cols, size_t step, double* out, int* ow, int* oh);
 ORC_API int orc_lsd_scaled(const uint8_t* img, int rows, int cols, size_t step, uint8_t* out, int* ow, int* oh);

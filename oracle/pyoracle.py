@@ -236,6 +236,15 @@ def lsd_detect(img, order_mode=0, cap=20000):
     return xy[:n].copy(), w[:n].copy(), p[:n].copy(), nf[:n].copy()
 
 
+def lsd_trace(img, cap=60000):
+    """The regions flsd() grows, in order: rows of (seed pixel of the scaled image, first growth size, final size, got a rectangle)."""
+    img = _u8(img)
+    out = np.empty((cap, 4), np.int32)
+    n = lib().orc_lsd_trace(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]), _p(out), C.c_int(cap))
+    assert n <= cap
+    return out[:n].copy()
+
+
 def lsd_scaled(img):
     img = _u8(img)
     ow, oh = C.c_int(), C.c_int()
