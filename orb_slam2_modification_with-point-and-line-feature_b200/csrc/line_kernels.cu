@@ -999,7 +999,8 @@ struct pl_line {
     LsdSeg* d_qres = nullptr;
     LsdQueueItem* d_queue = nullptr;
     uint8_t* d_qvalid = nullptr;
-    unsigned int *d_spec_reg = nullptr, *d_big_touched = nullptr, *d_dbg_bits = nullptr;
+    unsigned int *d_spec_reg = nullptr, *d_big_touched = nullptr, *d_dbg_bits = nullptr, *d_gfinal = nullptr;
+    TicketRec* d_trec = nullptr;
     int* d_dbg_out = nullptr;
     int4* d_dbg_log = nullptr;
     unsigned int* d_dbg_scratch = nullptr;
@@ -1152,6 +1153,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         GrowBufs gb;
         gb.angdeg = h->d_ang; gb.g2 = h->d_g2; gb.rec = h->d_rec; gb.cs0 = h->d_cs0; gb.seeds = h->d_seeds; gb.n_seeds = h->d_nseeds;
         gb.big_reg = h->d_big_touched; gb.pool_reg = h->d_spec_reg; gb.pool_rect = h->d_pool_rect;
+        gb.trec = h->d_trec; gb.gfinal = h->d_gfinal;
         gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
         gb.flags = h->d_flags; gb.phase_cycles = prof ? h->d_phase : nullptr; gb.frame_counter = h->d_frame_counter; gb.plane = plane;
         gb.watchdog_cycles = h->watchdog_cycles;
@@ -1272,8 +1274,8 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
         if (e == cudaSuccess) {
             h->num_sms = prop.multiProcessorCount;
             // shared memory of a grower CTA: the ticket slots with their point rings and the committed bitmap
-            int want_slots = 512, want_window = 0, want_stall = 16, want_restarts = 3;
-            if (const char* ev = getenv("PLSLAM_LSD_SLOTS")) want_slots = std::max(32, std::min(1024, atoi(ev)));
+            int want_slots = kMaxSlots, want_window = 0, want_stall = 16, want_restarts = 3;
+            if (const char* ev = getenv("PLSLAM_LSD_SLOTS")) want_slots = std::max(32, std::min(kMaxSlots, atoi(ev)));
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) want_window = std::max(1, atoi(ev));
             if (const char* ev = getenv("PLSLAM_LSD_STALL")) want_stall = std::max(0, std::min(100000, atoi(ev)));
             if (const char* ev = getenv("PLSLAM_LSD_RESTARTS")) want_restarts = std::max(0, std::min(8, atoi(ev)));
@@ -1281,9 +1283,9 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             if (const char* ev = getenv("PLSLAM_LSD_DEBUG")) want_debug = atoi(ev);
             h->grow_debug = want_debug;
             while (want_slots & (want_slots - 1)) want_slots &= want_slots - 1;  // power of two
-            auto choose = [&](size_t budget, int slots, GrowLayout* out) -> bool {
+            auto choose = [&](size_t budget, int threads, int slots, GrowLayout* out) -> bool {
                 for (int wN = slots; wN >= 32; wN >>= 1) {
-                    GrowLayout L{wN, want_window > 0 ? std::min(want_window, wN) : wN, h->bits_words, want_stall, want_restarts, 200, want_debug};
+                    GrowLayout L{wN, want_window > 0 ? std::min(want_window, wN) : wN, h->bits_words, want_stall, want_restarts, 200, want_debug, threads - 63};
                     if (L.total() <= budget) {
                         *out = L;
                         return true;
@@ -1294,9 +1296,9 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             const size_t static_smem = 2048;  // control block (static shared memory of k_lsd_grow)
             const size_t optin = prop.sharedMemPerBlockOptin, per_sm = prop.sharedMemPerMultiprocessor;
             const size_t budget1 = optin > static_smem ? optin - static_smem : 0;
-            if (!choose(budget1, want_slots, &h->lay_few)) {
+            if (!choose(budget1, 512, want_slots, &h->lay_few)) {
                 set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region grower, the device offers %zu",
-                          max_cols, max_rows, GrowLayout{32, 32, h->bits_words, 0, 0, 200, 0}.total(), budget1);
+                          max_cols, max_rows, GrowLayout{32, 32, h->bits_words, 0, 0, 200, 0, 512 - 63}.total(), budget1);
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
@@ -1304,7 +1306,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             // two CTAs per SM: each gets half of the SM's shared memory (1 KB per CTA is reserved by the system)
             const size_t half = per_sm / 2 > 1024 + static_smem ? per_sm / 2 - 1024 - static_smem : 0;
             GrowLayout two;
-            if (choose(half, std::min(want_slots, 256), &two) && two.W >= std::min(128, want_slots)) {
+            if (choose(half, 256, want_slots, &two) && two.W >= std::min(512, want_slots)) {
                 h->lay_many = two;
                 h->threads_many = 256;
                 h->ctas_per_sm_many = 2;
@@ -1330,6 +1332,8 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_spec_reg, max_ctas * kPoolBufs * 2 * (size_t)kSpecCap);
     A(&h->d_pool_rect, max_ctas * kPoolBufs);
     A(&h->d_big_touched, max_ctas * 2 * plane);
+    A(&h->d_trec, max_ctas * (size_t)kMaxSlots);
+    A(&h->d_gfinal, max_ctas * 2 * (size_t)kMaxSlots);
     A(&h->d_dbg_bits, max_ctas * (size_t)h->bits_words);
     if (e == cudaSuccess) e = cudaMemset(h->d_dbg_bits, 0, max_ctas * (size_t)h->bits_words * sizeof(unsigned int));
     if (h->grow_debug & 512) A(&h->d_dbg_scratch, max_ctas * plane);
@@ -1397,7 +1401,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) pl::stream_sync(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_blur5, h->d_ang, h->d_g2, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_big_touched, h->d_dbg_bits, h->d_dbg_out, h->d_dbg_log, h->d_dbg_log_n, h->d_dbg_scratch, h->d_pool_rect, h->d_frame_counter, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_big_touched, h->d_trec, h->d_gfinal, h->d_dbg_bits, h->d_dbg_out, h->d_dbg_log, h->d_dbg_log_n, h->d_dbg_scratch, h->d_pool_rect, h->d_frame_counter, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);

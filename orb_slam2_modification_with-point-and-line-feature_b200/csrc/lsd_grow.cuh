@@ -40,23 +40,28 @@ namespace pl {
 struct LsdQueueItem { LsdRect rec; };
 
 constexpr int kRing = 32;        // region points a ticket slot keeps in shared memory (>= min_reg_size of any supported image)
-constexpr int kPoolBufs = 128;   // region buffers per CTA (2 x kSpecCap words each: first growth | refine's re-growth)
-constexpr int kSpecCap = 16384;  // capacity of a buffer half; larger regions are grown by the committer with frame-sized buffers
+constexpr int kPoolBufs = 512;   // region buffers per CTA (2 x kSpecCap words each: first growth | refine's re-growth); a finished region keeps
+                                 // its buffer until it is committed, so the pool has to match the window of uncommitted tickets
+constexpr int kSpecCap = 4096;   // capacity of a buffer half; larger regions are grown by the committer with frame-sized buffers
 constexpr int kMaxDeps = 4;
+constexpr int kMaxSlots = 2048;
 constexpr unsigned kTicketMask = 0xffffffu;  // stamp = attempt << 24 | ticket + 1  (0 = never stamped)
 
 enum { kSlotFree = 0, kSlotReady = 1, kSlotGrowing = 2, kSlotDone = 4 };
 enum { kStDeferred = -2, kStCapacity = -1, kStNoRect = 0, kStRect = 1 };
 __device__ __forceinline__ int slot_pack(int state, int status, int buf) { return state | ((status + 2) << 8) | ((buf + 1) << 16); }
 
-// Dynamic shared memory of a CTA.
-//   slot[W]  int4: x = seed pixel | adjacency hint << 31, y = region size, z = size of the first growth when refine grew the
-//                  region again (0: it did not), w = state | (status + 2) << 8 | (buffer + 1) << 16
-//   dep[W]   uint4: the stamps of earlier tickets this growth deferred to (0 = empty)
-//   fin[W]   the stamp a finished ticket's region carries (0 while it is not final or when it failed)
-//   aux[W]   size of refine's re-growth before reduce_region_radius removed points (they stay in the log)
-//   poison[W] bit a: an earlier ticket took a pixel that carried this ticket's stamp of attempt a;  thief[W] who (ticket + 1, max)
-//   fring[2W] (what each recently committed ticket committed: its final stamp, or 0), ring[W][kRing], used bitmap
+// A ticket slot, in shared memory (60 bytes):
+//   state[W]  state | (status + 2) << 8 | (buffer + 1) << 16
+//   fin[W]    the stamp the finished region carries (0 while it is not final or when it failed)
+//   poison[W] bit a: an earlier ticket took a pixel that carried this ticket's stamp of attempt a
+//   hdr[W]    int4 {seed pixel | adjacency hint << 31, region size, size of the first growth when refine grew the region again (0: it
+//             did not), size of that re-growth before reduce_region_radius removed points (they stay in the log)}
+//   dep[W]    uint4: the stamps of earlier tickets this growth deferred to (0 = empty)
+//   pts4[W]   uint4: the first four points of a region without a buffer; the others are in global memory (TicketRec)
+struct TicketRec {
+    unsigned int pts[kRing];
+};
 struct GrowLayout {
     int W;           // ticket slots, a power of two
     int window;      // tickets that may be uncommitted at once (<= W)
@@ -64,19 +69,19 @@ struct GrowLayout {
     int stall;       // iterations a thread waits for an earlier ticket to become final before it assumes the stamp stays
     int restarts;    // speculative attempts a ticket gets after it lost a pixel to an earlier ticket (or a compare-and-swap)
     int poll_ns;
-    int debug;       // test hook (PLSLAM_LSD_DEBUG): bit 0 a growth with dependencies is not trusted, 1 nor one that started again,
-                     // 2 a dropped pixel of a finished region is not taken, 3 nor is a refined region trusted
+    int debug;       // test hook (PLSLAM_LSD_DEBUG): bits 4 / 7 shadow growth of every / every large committed region, 5 no batched commit,
+                     // 8 commit log, 9 shadow growth after a re-growth at the commit head
+    int rings;       // point rings: one per grower thread + one for the committer
     __host__ __device__ static size_t a16(size_t v) { return (v + 15) & ~(size_t)15; }
-    __host__ __device__ size_t off_slot() const { return 0; }
+    __host__ __device__ size_t off_hdr() const { return 0; }
     __host__ __device__ size_t off_dep() const { return (size_t)W * 16; }
-    __host__ __device__ size_t off_fin() const { return off_dep() + (size_t)W * 16; }
-    __host__ __device__ size_t off_aux() const { return off_fin() + (size_t)W * 4; }
-    __host__ __device__ size_t off_poison() const { return off_aux() + (size_t)W * 4; }
-    __host__ __device__ size_t off_thief() const { return off_poison() + (size_t)W * 4; }
-    __host__ __device__ size_t off_fring() const { return off_thief() + (size_t)W * 4; }
-    __host__ __device__ size_t off_ring() const { return off_fring() + (size_t)W * 8; }
-    __host__ __device__ size_t off_used() const { return off_ring() + (size_t)W * kRing * 4; }
-    __host__ __device__ size_t total() const { return off_used() + a16((size_t)bits_words * 4); }
+    __host__ __device__ size_t off_pts4() const { return (size_t)W * 32; }
+    __host__ __device__ size_t off_state() const { return (size_t)W * 48; }
+    __host__ __device__ size_t off_fin() const { return off_state() + (size_t)W * 4; }
+    __host__ __device__ size_t off_poison() const { return off_fin() + (size_t)W * 4; }
+    __host__ __device__ size_t off_ring() const { return off_poison() + (size_t)W * 4; }
+    __host__ __device__ size_t off_used() const { return off_ring() + (size_t)rings * kRing * 4; }
+    __host__ __device__ size_t total() const { return off_used() + a16((size_t)bits_words * 4 + 4); }
 };
 
 struct GrowCtl {
@@ -86,6 +91,7 @@ struct GrowCtl {
     int all_issued;   // the seed list is exhausted
     int done;         // the frame is finished
     int abort_;       // watchdog
+    int active;       // tickets held by grower threads
     unsigned long long free_mask[kPoolBufs / 64];
     unsigned long long stat[8];  // committed, void, regrown, committer asleep, grower-thread cycles, fit cycles, commit cycles, regrow cycles
     unsigned int why[16];        // profiling: 0 seed swallowed at take, 1 seed held by an earlier ticket, 2 too many dependencies, 3 CAS lost,
@@ -101,6 +107,8 @@ struct GrowBufs {
     const unsigned int* seeds;
     const int* n_seeds;
     unsigned int* big_reg;       // [cta][2 * plane]: the committer's own growth (first growth | refine's re-growth)
+    TicketRec* trec;             // [cta][kMaxSlots]
+    unsigned int* gfinal;        // [cta][2 * kMaxSlots] what each recently committed ticket committed: its final stamp, or 0
     unsigned int* pool_reg;      // [cta][kPoolBufs][2][kSpecCap]
     LsdRect* pool_rect;          // [cta][kPoolBufs]
     LsdQueueItem* queue;         // [frame][seg_cap]
@@ -135,15 +143,16 @@ __device__ __forceinline__ void pool_push(unsigned long long* masks, int b) { at
 // everything a region's thread needs of its frame and CTA
 struct TEnv {
     GrowCtl* ctl;
-    volatile int4* slot;
-    unsigned int* dep;     // [W][4]
-    unsigned int* fin;
-    unsigned int* aux;
-    unsigned int* poison;
-    unsigned int* thief;
-    unsigned int* fring;   // [2W]
-    unsigned int* ring;    // [W][kRing]
+    int4* hdr;             // [W] shared memory
+    uint4* dep;            // [W]
+    uint4* pts4;           // [W]
+    unsigned int* state;   // [W]
+    unsigned int* fin;     // [W]
+    unsigned int* poison;  // [W]
+    unsigned int* ring;    // [rings][kRing]
     unsigned int* used;
+    TicketRec* trec;       // [W] global memory
+    unsigned int* gfinal;  // [2W] global memory
     int wm;
     int W, H, min_reg, stall, restarts, debug;
     LsdPix* rec;
@@ -175,6 +184,7 @@ struct TState {
     int attempt;         // even: a first growth, odd: refine's re-growth of it (0, 1; 2, 3 after a restart ...; 62, 63 at the commit head)
     int restarts_left;
     int kstart;          // neighbour to resume the current point from
+    int pix;             // the seed
     int wait_u;          // >= 0: waiting for this earlier ticket to become final
     bool wait_hard;      // ... until it is committed, however long it takes (the ticket at the commit head)
     int stall_left;
@@ -315,7 +325,7 @@ __device__ __noinline__ bool lsd_reduce_thread(const TEnv& E, unsigned int* reg,
 //   2 final, and the region dropped the pixel (refine),  3 the ticket was committed meanwhile
 __device__ __forceinline__ int lsd_owner_state(const TEnv& E, unsigned st) {
     const int u = (int)(st & kTicketMask) - 1;
-    const int w = E.slot[u & E.wm].w;
+    const unsigned w = *(volatile unsigned int*)&E.state[u & E.wm];
     const unsigned f = *(volatile unsigned int*)&E.fin[u & E.wm];
     if (*(volatile int*)&E.ctl->commit_head > u) return 3;  // (read last: the slot was still the ticket's when w and f were read)
     // a stamp of the committer's own growth (attempts 62, 63): the ticket at the commit head is being grown again right now — its
@@ -326,7 +336,7 @@ __device__ __forceinline__ int lsd_owner_state(const TEnv& E, unsigned st) {
     return f == st ? 1 : 2;
 }
 __device__ __forceinline__ bool lsd_add_dep(const TEnv& E, int ticket, unsigned st) {
-    unsigned int* d = E.dep + (size_t)(ticket & E.wm) * kMaxDeps;
+    unsigned int* d = reinterpret_cast<unsigned int*>(&E.dep[ticket & E.wm]);
 #pragma unroll
     for (int k = 0; k < kMaxDeps; k++) {
         const unsigned v = d[k];
@@ -348,10 +358,7 @@ __device__ __forceinline__ bool lsd_stamp(const TEnv& E, const TState& T, int o,
     if (T.nonspec) old = atomicExch(&E.rec[o].stamp, T.mine);
     else ok = atomicCAS(&E.rec[o].stamp, obs, T.mine) == obs;
     const unsigned tk = old & kTicketMask;
-    if (ok && tk > (T.mine & kTicketMask) && (int)(tk - 1) >= head) {
-        atomicMax(&E.thief[(tk - 1) & E.wm], T.mine & kTicketMask);
-        atomicOr(&E.poison[(tk - 1) & E.wm], 1u << ((old >> 24) & 31u));
-    }
+    if (ok && tk > (T.mine & kTicketMask) && (int)(tk - 1) >= head) atomicOr(&E.poison[(tk - 1) & E.wm], 1u << ((old >> 24) & 31u));
     return ok;
 }
 
@@ -412,6 +419,19 @@ __device__ __forceinline__ bool lsd_thread_start(const TEnv& E, TState& T, int p
     return true;
 }
 
+// The committed-map bits of (x - 1, x, x + 1) in row yy as bits 0..2 (1 = committed); pixels outside the image count as committed.
+// (The bitmap has a spare word at its end.)
+__device__ __forceinline__ unsigned lsd_used3(const volatile unsigned int* vused, int W, int H, int x, int yy) {
+    if (yy < 0 || yy >= H) return 7u;
+    const int o = yy * W + max(x - 1, 0);
+    const unsigned s = (unsigned)o & 31u;
+    unsigned bits = vused[o >> 5] >> s;
+    if (s > 29u) bits |= vused[(o >> 5) + 1] << (32u - s);
+    if (x == 0) bits = (bits << 1) | 1u;
+    if (x + 1 >= W) bits |= 4u;
+    return bits & 7u;
+}
+
 // One region point: its 8 neighbours in the reference's order (row-major, the centre skipped).
 __device__ __forceinline__ void lsd_thread_step(const TEnv& E, TState& T) {
     const volatile unsigned int* vused = E.used;
@@ -436,14 +456,14 @@ __device__ __forceinline__ void lsd_thread_step(const TEnv& E, TState& T) {
     T.kstart = 0;
     float4 r[8];
     bool c[8];
+    // committed bits of the 3 x 3 neighbourhood: bit 3 * (dy + 1) + (dx + 1)
+    const unsigned ub = lsd_used3(vused, W, H, x, y - 1) | (lsd_used3(vused, W, H, x, y) << 3) | (lsd_used3(vused, W, H, x, y + 1) << 6);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int kk = k + (k >= 4 ? 1 : 0);
         const int dy = kk / 3 - 1, dx = kk - (kk / 3) * 3 - 1;
-        const int xx = x + dx, yy = y + dy;
         const int o = o0 + dy * W + dx;
-        c[k] = k >= ks && xx >= 0 && yy >= 0 && xx < W && yy < H;
-        if (c[k]) c[k] = ((vused[o >> 5] >> (o & 31)) & 1u) == 0;
+        c[k] = k >= ks && ((ub >> kk) & 1u) == 0;
         r[k] = make_float4(kNotDefDeg, 0.f, 0.f, 0.f);
         if (c[k]) r[k] = lsd_ld_rec(E.rec + o);
     }
@@ -517,7 +537,7 @@ __device__ __noinline__ bool lsd_thread_growth_end(const TEnv& E, TState& T, int
         __threadfence_block();
         if ((*(volatile unsigned int*)&E.poison[T.ticket & E.wm] >> (T.attempt & 31)) & 1u) {  // an earlier ticket took one of its pixels
             T.bad = 1;
-            T.other = (int)*(volatile unsigned int*)&E.thief[T.ticket & E.wm] - 1;
+            T.other = -1;
         }
     }
     if (T.bad) {
@@ -576,6 +596,7 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
     GrowCtl* ctl = E.ctl;
     volatile GrowCtl* vc = ctl;
     const int wm = E.wm;
+    const int gw = (int)(threadIdx.x >> 5) - 2;  // grower warp number
     const double prec0 = kPiD * 22.5 / 180;
     TState T;
     T.ticket = -1;
@@ -595,7 +616,8 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
     T.mine = T.pnext = 0;
     T.sumdx = T.sumdy = T.th = T.precdeg = 0.f;
     T.prec = prec0;
-    T.ring = E.ring;
+    T.ring = E.ring + (size_t)((int)threadIdx.x - 63) * kRing;  // (warps 0 and 1 are the committer and the issuer; ring 0 is the committer's)
+    T.pix = 0;
     T.greg = T.areg = nullptr;
     long long busy = 0, t_take = 0, fit_cyc = 0;
     while (true) {
@@ -606,7 +628,9 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
         const unsigned idle = __ballot_sync(FULL, T.ticket < 0);
         if (idle) {
             int base = 0, cnt = 0;
-            if (lane == 0) {
+            // Tickets are packed into the lower warps: a warp only takes new ones when the warps below it are three quarters busy,
+            // so that a lightly loaded frame keeps few warps awake (a warp with one busy lane costs the SM as much as a full one).
+            if (lane == 0 && (gw == 0 || vc->active >= 24 * gw)) {
                 int gn = vc->grow_next;
                 while (true) {
                     const int avail = vc->ticket_next - gn;
@@ -616,6 +640,7 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
                     if (old == gn) { base = gn; cnt = want; break; }
                     gn = old;
                 }
+                if (cnt) atomicAdd(&ctl->active, cnt);
             }
             base = __shfl_sync(FULL, base, 0);
             cnt = __shfl_sync(FULL, cnt, 0);
@@ -628,7 +653,6 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
                 T.ticket = base + __popc(idle & lt);
                 t_take = clock64();
                 T.mine = (unsigned)T.ticket + 1u;
-                T.ring = E.ring + (size_t)(T.ticket & wm) * kRing;
                 T.n = T.i = T.n0 = 0;
                 T.buf = -1;
                 T.bad = 0;
@@ -643,20 +667,22 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
                 T.restarts_left = E.restarts;
                 // a seed right next to the previous ticket's seed most likely belongs to the same region: let that one go first
                 T.phase = 1;
-                T.kstart = (E.slot[T.ticket & wm].x < 0) ? 2 : 0;  // (in phase 1: iterations to wait)
+                const int sx = *(volatile int*)&E.hdr[T.ticket & wm].x;
+                T.pix = sx & 0x7fffffff;
+                T.kstart = sx < 0 ? 2 : 0;  // (in phase 1: iterations to wait)
             }
         }
         bool progress = false;
         if (T.ticket >= 0) {
-            const int pix = E.slot[T.ticket & wm].x & 0x7fffffff;
+            const int pix = T.pix;
             // ---- an earlier ticket took a pixel of this growth: it cannot be trusted ----
             if (!T.bad && T.phase == 2 && ((*(volatile unsigned int*)&E.poison[T.ticket & wm] >> (T.attempt & 31)) & 1u)) {
                 T.bad = 1;
-                T.other = (int)*(volatile unsigned int*)&E.thief[T.ticket & wm] - 1;
+                T.other = -1;
             }
             // ---- waiting for an earlier ticket to become final ----
             if (T.wait_u >= 0) {
-                const int w = E.slot[T.wait_u & wm].w;
+                const unsigned w = *(volatile unsigned int*)&E.state[T.wait_u & wm];
                 if (vc->commit_head > T.wait_u || (!T.wait_hard && ((w & 0xff) == kSlotDone || --T.stall_left <= 0))) T.wait_u = -1;
             }
             if (T.wait_u < 0 && !T.bad) {
@@ -686,17 +712,17 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
                     T.restarts_left--;
                     T.attempt = (T.attempt & ~1) + 2;
                     T.mine = ((unsigned)T.attempt << 24) | ((unsigned)T.ticket + 1u);
-                    reinterpret_cast<uint4*>(E.dep)[T.ticket & wm] = make_uint4(0u, 0u, 0u, 0u);
+                    E.dep[T.ticket & wm] = make_uint4(0u, 0u, 0u, 0u);
                     T.n = T.i = T.n0 = 0;
                     T.greg = T.buf >= 0 ? T.areg : nullptr;
                     T.bad = 0;
                     T.phase = 1;
-                    T.kstart = 0;
                     T.prec = prec0;
                     T.precdeg = (float)(prec0 * (180.0 / kPiD));
-                    T.wait_u = (T.other >= 0 && T.other < T.ticket) ? T.other : -1;
+                    T.wait_u = -1;
                     T.wait_hard = false;
-                    T.stall_left = 8 * E.stall;
+                    T.stall_left = E.stall;
+                    T.kstart = 4;  // (a few iterations for whoever got in the way to get on)
                     finished = false;
                 } else {
                     status = kStDeferred;
@@ -704,26 +730,27 @@ __device__ __noinline__ void lsd_grower_threads(const TEnv& E, int poll_ns) {
                 }
             }
             if (finished) {
-                volatile int4* sl = &E.slot[T.ticket & wm];
-                if (E.debug && status >= 0) {
-                    if ((E.debug & 1) && E.dep[(size_t)(T.ticket & wm) * kMaxDeps] != 0u) status = kStDeferred;
-                    if ((E.debug & 2) && (T.attempt & 31) >= 2) status = kStDeferred;
-                    if ((E.debug & 8) && T.n0 > 0) status = kStDeferred;
-                }
                 if (status < 0 && T.buf >= 0) {
                     pool_push(ctl->free_mask, T.buf);
                     T.buf = -1;
                 }
                 if (status == kStCapacity && E.prof) atomicAdd(&ctl->why[5], 1u);
                 if (status == kStRect) E.pool_rect[T.buf] = rec;
-                sl->y = T.n;
-                sl->z = T.n0;
-                E.aux[T.ticket & wm] = (unsigned)n1;
+                E.hdr[T.ticket & wm] = make_int4(pix, T.n, T.n0, n1);
+                if (status >= 0 && T.buf < 0) {  // a small region: its points go with the ticket
+                    E.pts4[T.ticket & wm] = make_uint4(T.ring[0], T.ring[1], T.ring[2], T.ring[3]);
+                    if (T.n > 4) {
+                        unsigned int* gp = E.trec[T.ticket & wm].pts;
+#pragma unroll 1
+                        for (int k = 0; k < T.n; k++) gp[k] = T.ring[k];
+                    }
+                }
                 *(volatile unsigned int*)&E.fin[T.ticket & wm] = status >= 0 ? T.mine : 0u;
                 __threadfence_block();
-                sl->w = slot_pack(kSlotDone, status, T.buf);
+                *(volatile unsigned int*)&E.state[T.ticket & wm] = (unsigned)slot_pack(kSlotDone, status, T.buf);
                 busy += clock64() - t_take;
                 T.ticket = -1;
+                atomicSub(&ctl->active, 1);
             }
         }
         if (!__any_sync(FULL, progress)) __nanosleep(poll_ns);
@@ -770,14 +797,10 @@ __device__ __noinline__ void lsd_issuer_warp(const TEnv& E, const GrowBufs& B, i
             if (mine) {
                 const int tk = t + __popc(m & lt);
                 E.poison[tk & wm] = 0u;
-                E.thief[tk & wm] = 0u;
                 E.fin[tk & wm] = 0u;
-                reinterpret_cast<uint4*>(E.dep)[tk & wm] = make_uint4(0u, 0u, 0u, 0u);
-                volatile int4* sl = &E.slot[tk & wm];
-                sl->x = (int)(pix | (adj ? 0x80000000u : 0u));
-                sl->y = 0;
-                sl->z = 0;
-                sl->w = slot_pack(kSlotReady, 0, -1);
+                E.hdr[tk & wm] = make_int4((int)(pix | (adj ? 0x80000000u : 0u)), 0, 0, 0);
+                E.dep[tk & wm] = make_uint4(0u, 0u, 0u, 0u);
+                E.state[tk & wm] = (unsigned)slot_pack(kSlotReady, 0, -1);
             }
             __syncwarp();
             __threadfence_block();
@@ -834,8 +857,8 @@ __device__ __noinline__ void lsd_shadow_check(const TEnv& E, const GrowBufs& B, 
     if (diff >= 0 && atomicCAS(B.dbg_out + (size_t)f * 16, 0, 1) == 0) {
         int* d = B.dbg_out + (size_t)f * 16;
         d[1] = h; d[2] = pix; d[3] = n_spec; d[4] = n; d[5] = diff; d[6] = (int)fin_stamp; d[7] = n0;
-        d[8] = (int)E.poison[h & E.wm]; d[9] = (int)E.thief[h & E.wm];
-        for (int k = 0; k < kMaxDeps; k++) d[10 + k] = (int)E.dep[(size_t)(h & E.wm) * kMaxDeps + k];
+        d[8] = (int)E.poison[h & E.wm]; d[9] = 0;
+        for (int k = 0; k < kMaxDeps; k++) d[10 + k] = (int)reinterpret_cast<const unsigned int*>(&E.dep[h & E.wm])[k];
         d[14] = diff < n_spec ? (int)spec[diff] : -1;
         d[15] = diff < n ? (int)shadow[diff] : -1;
     }
@@ -846,14 +869,15 @@ __device__ __noinline__ void lsd_shadow_check(const TEnv& E, const GrowBufs& B, 
 // ---------------------------------------------------------------------------------------------------------------
 // were the stamps ticket `t` deferred to committed as they were seen?  (tickets below `h` are committed)
 __device__ __forceinline__ bool lsd_deps_hold(const TEnv& E, int t, int h, const int* s_kind) {
-    const unsigned int* d = E.dep + (size_t)(t & E.wm) * kMaxDeps;
+    const uint4 dv = E.dep[t & E.wm];
+    const unsigned int d[kMaxDeps] = {dv.x, dv.y, dv.z, dv.w};
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < kMaxDeps; k++) {
         const unsigned st = d[k];
         if (st != 0u) {
             const int u = (int)(st & kTicketMask) - 1;
-            if (u < h) ok &= *(volatile unsigned int*)&E.fring[u & (2 * E.wm + 1)] == st;
+            if (u < h) ok &= *(volatile unsigned int*)&E.gfinal[u & (2 * E.wm + 1)] == st;
             else ok &= !(E.debug & 64) && *(volatile int*)&s_kind[u - h] == 1 && st == *(volatile unsigned int*)&E.fin[u & E.wm];  // a small region of the same batch
         }
     }
@@ -898,9 +922,8 @@ __device__ __noinline__ void lsd_committer_warp(const LineGeom& g, const TEnv& E
         }
         // ---- the run of finished tickets at the head, one per lane ----
         const int t = h + lane;
-        volatile int4* sl = &E.slot[t & wm];
-        int w = 0;
-        if (t < tn) w = sl->w;
+        unsigned w = 0;
+        if (t < tn) w = *(volatile unsigned int*)&E.state[t & wm];
         const unsigned dm = __ballot_sync(FULL, t < tn && (w & 0xff) == kSlotDone);
         const int run = dm == FULL ? 32 : __ffs(~dm) - 1;
         if (run == 0) {
@@ -911,66 +934,151 @@ __device__ __noinline__ void lsd_committer_warp(const LineGeom& g, const TEnv& E
         }
         __threadfence_block();
         const long long b0 = clock64();
-        int kind = 2, n = 0;  // 0 void, 1 small region without a rectangle, 2 everything else
-        const unsigned int* pts = E.ring + (size_t)(t & wm) * kRing;
+        // kind: 0 void, 1 small region (no rectangle, no buffer), 3 region with a buffer, 4 failed speculation (void if an earlier region
+        // swallows its seed, else grown again), 2 needs the ticket-alone path
+        int kind = 2, n = 0, n0 = 0, nb = 0, buf = -1, status = 0, seed = 0;
+        unsigned f1 = 0u;
+        uint4 pv[kRing / 4];  // the points of a small region
         if (lane < run) {
-            const int pix = sl->x & 0x7fffffff, status = ((w >> 8) & 0xff) - 2, buf = ((w >> 16) & 0xff) - 1;
-            n = sl->y;
+            const int4 sv = E.hdr[t & wm];  // (stable once the ticket is done)
+            seed = sv.x & 0x7fffffff;
+            status = (int)((w >> 8) & 0xff) - 2;
+            buf = (int)((w >> 16) & 0xffff) - 1;
+            n = sv.y;
+            n0 = sv.z;
+            nb = sv.w;
             PL_LSD_CHECK(n >= 0 && (n <= kRing || buf >= 0 || status < 0), 6);
-            const unsigned f1 = *(volatile unsigned int*)&E.fin[t & wm];
-            if ((vused[pix >> 5] >> (pix & 31)) & 1u) kind = 0;
-            else if (status == kStNoRect && buf < 0 && ((*(volatile unsigned int*)&E.poison[t & wm] >> ((f1 >> 24) & 31u)) & 1u) == 0u && !(E.debug & 48)) kind = 1;
-        }
-        s_kind[lane] = kind;
-        __syncwarp();
-        if (lane < run && kind == 1) {
-            bool conflict = !lsd_deps_hold(E, t, h, s_kind);
-#pragma unroll 1
-            for (int k = 0; k < n; k++) {
-                const unsigned pp = pts[k];
-                const unsigned o = (pp >> 16) * (unsigned)W + (pp & 0xffffu);
-                conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
+            f1 = *(volatile unsigned int*)&E.fin[t & wm];
+            const bool poisoned = ((*(volatile unsigned int*)&E.poison[t & wm] >> ((f1 >> 24) & 31u)) & 1u) != 0u;
+            if ((vused[seed >> 5] >> (seed & 31)) & 1u) kind = 0;
+            else if (status < 0) kind = 4;
+            else if (!poisoned && !(E.debug & 48)) {
+                kind = buf < 0 ? 1 : 3;
+                if (buf >= 0 && n + n0 + nb > 4096) kind = 2;  // (a long list: the ticket-alone path has nothing else to wait for it)
             }
-            if (conflict) kind = 2;
         }
-        // (a lane whose dependency inside the batch turns out not to commit here lies behind that lane: it is cut off with it)
-        const unsigned other = __ballot_sync(FULL, lane < run && kind == 2);
-        const int k = other ? __ffs(other) - 1 : run;
-        if (lane < k) {
-            if (kind == 1) {
-#pragma unroll 1
-                for (int j = 0; j < n; j++) {
-                    const unsigned pp = pts[j];
-                    const unsigned o = (pp >> 16) * (unsigned)W + (pp & 0xffffu);
-                    const unsigned old = atomicOr(&E.used[o >> 5], 1u << (o & 31));
-                    if ((old >> (o & 31)) & 1u) {  // two small regions of the batch share a pixel: must not happen
-                        atomicAdd(&ctl->why[14], 1u);
-                        if (B.dbg_out && atomicCAS(B.dbg_out + (size_t)f * 16, 0, 2) == 0) {
-                            int* d = B.dbg_out + (size_t)f * 16;
-                            d[1] = t; d[2] = sl->x & 0x7fffffff; d[3] = n; d[4] = h; d[5] = j; d[6] = (int)E.fin[t & wm]; d[7] = k;
-                            d[8] = (int)E.poison[t & wm]; d[9] = (int)E.thief[t & wm];
-                            for (int q2 = 0; q2 < kMaxDeps; q2++) d[10 + q2] = (int)E.dep[(size_t)(t & wm) * kMaxDeps + q2];
-                            d[14] = (int)pp;
-                            d[15] = (int)__float_as_uint(lsd_ld_rec(E.rec + o).y);
-                        }
+        s_kind[lane] = kind == 3 ? 1 : kind;  // (for a dependency inside the batch both commit the speculation they finished with)
+        // the points of the small regions: four from the slot, the rest with vector loads from global memory, all issued together
+        if (lane < run && kind == 1) {
+            pv[0] = E.pts4[t & wm];
+            const uint4* gp = reinterpret_cast<const uint4*>(E.trec[t & wm].pts);
+#pragma unroll
+            for (int j = 1; j < kRing / 4; j++)
+                if (n > 4 * j) pv[j] = gp[j];
+        }
+        __syncwarp();
+        // every pixel the growth ever accepted must still be uncommitted (the regions of one batch cannot share a pixel: a ticket that
+        // lost one to an earlier ticket is poisoned), and the stamps it deferred to must have committed
+        bool ok = true;
+        if (lane < run && (kind == 1 || kind == 3)) ok = lsd_deps_hold(E, t, h, s_kind);
+        if (lane < run && kind == 1 && ok) {
+#pragma unroll
+            for (int j = 0; j < kRing / 4; j++) {
+                const unsigned q4[4] = {pv[j].x, pv[j].y, pv[j].z, pv[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (4 * j + e < n) {
+                        const unsigned o = (q4[e] >> 16) * (unsigned)W + (q4[e] & 0xffffu);
+                        ok &= ((vused[o >> 5] >> (o & 31)) & 1u) == 0;
                     }
+            }
+        }
+        {   // the lists of the regions with buffers, one region after the other with the whole warp
+            unsigned bigm = __ballot_sync(FULL, lane < run && kind == 3 && ok);
+            const unsigned stop_at = __ballot_sync(FULL, lane < run && (kind == 2 || ((kind == 1 || kind == 3) && !ok)));
+            if (stop_at) bigm &= (1u << (__ffs(stop_at) - 1)) - 1u;  // (nothing behind the first failure commits now)
+            while (bigm) {
+                const int bl = __ffs(bigm) - 1;
+                bigm &= bigm - 1;
+                const int bbuf = __shfl_sync(FULL, buf, bl), bn = __shfl_sync(FULL, n, bl), bn0 = __shfl_sync(FULL, n0, bl), bnb = __shfl_sync(FULL, nb, bl);
+                const unsigned int* rega = E.pool_reg + (size_t)bbuf * 2 * kSpecCap;
+                const int la = bn0 > 0 ? bn0 : bn, lb = bn0 > 0 ? bnb : 0;
+                bool conflict = false;
+#pragma unroll 2
+                for (int j = lane; j < la + lb; j += 32) {
+                    const unsigned pp = j < la ? rega[j] : rega[kSpecCap + (j - la)];
+                    const unsigned o = (pp >> 16) * (unsigned)W + (pp & 0xffffu);
+                    PL_LSD_CHECK(o < (unsigned)(W * E.H), 4);
+                    if (o < (unsigned)(W * E.H)) conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
+                }
+                if (__any_sync(FULL, conflict)) {
+                    if (lane == bl) ok = false;
+                    break;  // (what lies behind it does not commit in this batch)
                 }
             }
-            E.fring[t & fm] = kind == 1 ? *(volatile unsigned int*)&E.fin[t & wm] : 0u;
-            sl->w = slot_pack(kSlotFree, 0, -1);
         }
-        {
-            const unsigned voids = __ballot_sync(FULL, lane < k && kind == 0);
-            if (B.dbg_log) {  // {seed, first growth size, final size, stamp | batch flag}
-                const unsigned reg = __ballot_sync(FULL, lane < k && kind == 1);
-                const int at = (int)n_commit + __popc(reg & ((1u << lane) - 1u));
-                if (lane < k && kind == 1 && at < kDbgLogCap)
-                    B.dbg_log[(size_t)f * kDbgLogCap + at] = make_int4(sl->x & 0x7fffffff, n, n, (int)(E.fring[t & fm] | 0x80000000u));
+        if (lane < run && (kind == 1 || kind == 3) && !ok) kind = 2;
+        // ---- commit: up to the first ticket that needs the ticket-alone path.  A failed speculation whose seed one of the regions
+        //      committed here swallows is void and does not stop the batch ----
+        int lo = 0, k = 0;
+        while (true) {
+            const unsigned stopm = __ballot_sync(FULL, lane >= lo && lane < run && (kind == 2 || kind == 4));
+            k = stopm ? __ffs(stopm) - 1 : run;
+            const bool mine = lane >= lo && lane < k;
+            if (mine && kind == 1) {
+#pragma unroll
+                for (int j = 0; j < kRing / 4; j++) {
+                    const unsigned q4[4] = {pv[j].x, pv[j].y, pv[j].z, pv[j].w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (4 * j + e < n) {
+                            const unsigned o = (q4[e] >> 16) * (unsigned)W + (q4[e] & 0xffffu);
+                            const unsigned old = atomicOr(&E.used[o >> 5], 1u << (o & 31));
+                            if (__builtin_expect((old >> (o & 31)) & 1u, 0)) atomicOr(B.flags + f, 8 | (8 << 4));  // two regions of a batch share a pixel: must not happen
+                        }
+                }
             }
-            n_void += __popc(voids);
-            n_commit += k - __popc(voids);
+            unsigned bigm = __ballot_sync(FULL, mine && kind == 3);
+            while (bigm) {
+                const int bl = __ffs(bigm) - 1;
+                bigm &= bigm - 1;
+                const int bbuf = __shfl_sync(FULL, buf, bl), bn = __shfl_sync(FULL, n, bl), bn0 = __shfl_sync(FULL, n0, bl), bst = __shfl_sync(FULL, status, bl);
+                const unsigned int* rg = E.pool_reg + (size_t)bbuf * 2 * kSpecCap + (bn0 > 0 ? kSpecCap : 0);  // the final list
+#pragma unroll 2
+                for (int j = lane; j < bn; j += 32) {
+                    const unsigned pp = rg[j];
+                    const unsigned o = (pp >> 16) * (unsigned)W + (pp & 0xffffu);
+                    PL_LSD_CHECK(o < (unsigned)(W * E.H), 5);
+                    if (o < (unsigned)(W * E.H)) {
+                        const unsigned old = atomicOr(&E.used[o >> 5], 1u << (o & 31));
+                        if (__builtin_expect((old >> (o & 31)) & 1u, 0)) atomicOr(B.flags + f, 8 | (8 << 4));
+                    }
+                }
+                if (bst == kStRect) {
+                    if (rects < g.seg_cap) {
+                        if (lane < (int)(sizeof(LsdRect) / 4))
+                            reinterpret_cast<unsigned int*>(&q[rects].rec)[lane] = reinterpret_cast<const unsigned int*>(&E.pool_rect[bbuf])[lane];
+                        rects++;
+                    } else if (lane == 0) {
+                        atomicOr(B.flags + f, 1);
+                    }
+                }
+                if (lane == 0) pool_push(ctl->free_mask, bbuf);
+            }
+            if (mine) {
+                E.gfinal[t & fm] = kind != 0 ? f1 : 0u;
+                E.state[t & wm] = (unsigned)slot_pack(kSlotFree, 0, -1);
+            }
+            {
+                const unsigned voids = __ballot_sync(FULL, mine && kind == 0);
+                const unsigned regs = __ballot_sync(FULL, mine && kind != 0);
+                if (B.dbg_log) {  // {seed, first growth size, final size, stamp | batch flag}
+                    const int at = (int)n_commit + __popc(regs & ((1u << lane) - 1u));
+                    if (mine && kind != 0 && at < kDbgLogCap)
+                        B.dbg_log[(size_t)f * kDbgLogCap + at] = make_int4(seed, n0 > 0 ? n0 : n, n, (int)(f1 | 0x80000000u));
+                }
+                n_void += __popc(voids);
+                n_commit += __popc(regs);
+            }
+            __syncwarp();
+            if (k == run) break;
+            // the ticket that stopped the batch: a failed speculation that the regions committed just now made void?
+            bool now_void = false;
+            if (lane == k && kind == 4) now_void = ((vused[seed >> 5] >> (seed & 31)) & 1u) != 0;
+            if (!__any_sync(FULL, now_void)) break;
+            if (lane == k) kind = 0;
+            lo = k;
         }
-        __syncwarp();
         __threadfence_block();
         h += k;
         if (lane == 0) vc->commit_head = h;
@@ -982,12 +1090,14 @@ __device__ __noinline__ void lsd_committer_warp(const LineGeom& g, const TEnv& E
         const long long s0 = clock64();
         // ---- the ticket that ended the batch, alone ----
         {
-            volatile int4* s1 = &E.slot[h & wm];
-            const int pix = s1->x & 0x7fffffff, w1 = s1->w;
-            int n1 = s1->y, status = ((w1 >> 8) & 0xff) - 2;
-            const int n0 = s1->z, nb = (int)E.aux[h & wm];
-            const int buf = ((w1 >> 16) & 0xff) - 1;
-            const unsigned int* rega = buf >= 0 ? E.pool_reg + (size_t)buf * 2 * kSpecCap : E.ring + (size_t)(h & wm) * kRing;
+            const int4 sv1 = E.hdr[h & wm];
+            const unsigned w1 = *(volatile unsigned int*)&E.state[h & wm];
+            const int pix = sv1.x & 0x7fffffff;
+            int n1 = sv1.y, status = (int)((w1 >> 8) & 0xff) - 2;
+            const int n0 = sv1.z, nb = sv1.w;
+            const int buf = (int)((w1 >> 16) & 0xffff) - 1;
+            const unsigned int* rega = buf >= 0 ? E.pool_reg + (size_t)buf * 2 * kSpecCap
+                                                : (n1 > 4 ? E.trec[h & wm].pts : reinterpret_cast<const unsigned int*>(&E.pts4[h & wm]));
             const unsigned int* rg = n0 > 0 ? rega + kSpecCap : rega;  // the final list
             unsigned final_stamp = 0u;
             bool is_void = false;
@@ -1034,7 +1144,8 @@ __device__ __noinline__ void lsd_committer_warp(const LineGeom& g, const TEnv& E
                         T.pnext = 0;
                         T.prec = kPiD * 22.5 / 180;
                         T.precdeg = (float)(T.prec * (180.0 / kPiD));
-                        T.ring = E.ring + (size_t)(h & wm) * kRing;
+                        T.ring = E.ring;  // (ring 0 is the committer's)
+                        T.pix = pix;
                         T.greg = T.areg = my_big;
                         T.sumdx = T.sumdy = T.th = 0.f;
                         LsdRect rec;
@@ -1098,9 +1209,9 @@ __device__ __noinline__ void lsd_committer_warp(const LineGeom& g, const TEnv& E
             __syncwarp();
             __threadfence_block();
             if (lane == 0) {
-                E.fring[h & fm] = final_stamp;
+                E.gfinal[h & fm] = final_stamp;
                 if (buf >= 0) pool_push(ctl->free_mask, buf);
-                s1->w = slot_pack(kSlotFree, 0, -1);
+                E.state[h & wm] = (unsigned)slot_pack(kSlotFree, 0, -1);
                 __threadfence_block();
                 vc->commit_head = h + 1;
             }
@@ -1142,14 +1253,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow(LineGeom g, G
     const int tid = threadIdx.x, warp = tid >> 5;
     TEnv E;
     E.ctl = &s_ctl;
-    E.slot = reinterpret_cast<volatile int4*>(s_raw + L.off_slot());
-    E.dep = reinterpret_cast<unsigned int*>(s_raw + L.off_dep());
+    E.hdr = reinterpret_cast<int4*>(s_raw + L.off_hdr());
+    E.dep = reinterpret_cast<uint4*>(s_raw + L.off_dep());
+    E.pts4 = reinterpret_cast<uint4*>(s_raw + L.off_pts4());
+    E.state = reinterpret_cast<unsigned int*>(s_raw + L.off_state());
     E.fin = reinterpret_cast<unsigned int*>(s_raw + L.off_fin());
-    E.aux = reinterpret_cast<unsigned int*>(s_raw + L.off_aux());
     E.poison = reinterpret_cast<unsigned int*>(s_raw + L.off_poison());
-    E.thief = reinterpret_cast<unsigned int*>(s_raw + L.off_thief());
-    E.fring = reinterpret_cast<unsigned int*>(s_raw + L.off_fring());
     E.ring = reinterpret_cast<unsigned int*>(s_raw + L.off_ring());
+    E.trec = B.trec + (size_t)blockIdx.x * kMaxSlots;
+    E.gfinal = B.gfinal + (size_t)blockIdx.x * 2 * kMaxSlots;
     E.used = reinterpret_cast<unsigned int*>(s_raw + L.off_used());
     E.wm = L.W - 1;
     E.W = g.W;
@@ -1172,17 +1284,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow(LineGeom g, G
         E.g2 = B.g2 + (size_t)f * B.plane;
         E.flag = B.flags + f;
         for (int k = tid; k < L.W; k += kThreads) {
-            E.slot[k].w = slot_pack(kSlotFree, 0, -1);
+            E.state[k] = (unsigned)slot_pack(kSlotFree, 0, -1);
             E.poison[k] = 0u;
-            E.thief[k] = 0u;
             E.fin[k] = 0u;
-            E.fring[k] = 0u;
-            E.fring[k + L.W] = 0u;
+            E.gfinal[k] = 0u;
+            E.gfinal[k + L.W] = 0u;
         }
-        for (int k = tid; k < L.bits_words; k += kThreads) E.used[k] = 0u;
+        for (int k = tid; k < L.bits_words + 1; k += kThreads) E.used[k] = 0u;
         if (tid == 0) {
             s_ctl.ticket_next = s_ctl.grow_next = s_ctl.commit_head = 0;
             s_ctl.all_issued = s_ctl.done = s_ctl.abort_ = 0;
+            s_ctl.active = 0;
             for (int k = 0; k < kPoolBufs / 64; k++) s_ctl.free_mask[k] = ~0ull;
             for (int k = 0; k < 8; k++) s_ctl.stat[k] = 0;
             for (int k = 0; k < 16; k++) s_ctl.why[k] = 0;
@@ -1209,7 +1321,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow(LineGeom g, G
             pc[20] = s_ctl.why[11];             // tickets committed alone
             pc[22] = s_ctl.why[12];             // kcycles of the batch iterations
             pc[23] = s_ctl.why[13];             // kcycles of the tickets committed alone
-            if (s_ctl.why[14]) pc[19] = -(long long)s_ctl.why[14];  // (must not happen: small regions of one batch sharing a pixel)
             pc[21] = (long long)s_ctl.stat[3];  // cycles the committer slept waiting for the head ticket
         }
         __syncthreads();
