@@ -182,14 +182,6 @@ PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
  *  active, 2 cycles inside commit sections, 3 tickets issued, 4 regions re-grown at commit, 5 regions committed,
  *  6 tickets deferred, 7 tickets void} */
 PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out8);
-/* test hook: with PLSLAM_LSD_DEBUG bit 4 set when the extractor was created, k_lsd_grow re-grows every speculative region it is
- * about to commit sequentially from the committed map and records, per frame of the last chunk, the first one that differs
- * (16 ints: found, ticket, seed pixel, speculative size, sequential size, first differing index, stamp, size before refine,
- * poison word, thief, 4 dependencies, the two differing points).  Reading clears the record. */
-PL_API int pl_line_debug_read(pl_line* h, int n_frames, int* out16);
-/* test hook: with PLSLAM_LSD_DEBUG bit 8, the regions frame `frame` of the last chunk committed, in commit order: rows of
- * {seed pixel of the scaled image, size of the first growth (-1: grown at the commit head), final size, stamp | flags} */
-PL_API int pl_line_debug_log(pl_line* h, int frame, int* out4, int cap, int* n_out);
 /* Test hooks: the 0.8-scaled 8-bit image LSD works on, its level-line angle map (float degrees, -1024 = undefined,
  * rows x cols of the scaled image) and the float LBD descriptors (n x 72) of frame `frame` of the last call. */
 PL_API int pl_line_scaled_dims(const pl_line* h, int* rows, int* cols);

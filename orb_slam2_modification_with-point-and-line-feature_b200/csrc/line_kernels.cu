@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __r
         }
         angdeg[(size_t)f * plane + (size_t)y * g.W + x] = a;
         g2[(size_t)f * plane + (size_t)y * g.W + x] = q;
-        // the grower's record of the pixel: angle | stamp (0 = never accepted by anyone) | cosf | sinf
-        rec[(size_t)f * plane + (size_t)y * g.W + x] = make_float4(a, 0.f, ca, sa);
+        // the grower's record of the pixel, one 16-byte load: angle | claim stamp (0xffff = none) | cosf | sinf
+        rec[(size_t)f * plane + (size_t)y * g.W + x] = make_float4(a, __uint_as_float(0xffffu), ca, sa);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my = max(my, __shfl_xor_sync(0xffffffffu, my, o));
@@ -275,24 +275,108 @@ struct LsdSeg {  // one detected segment, in detection order (== cv::LineSegment
 struct LsdRect {
     double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
 };
-// What the grower reads of a pixel, in one 16-byte load: the level-line angle (degrees, or kNotDefDeg), the stamp of the
-// region that accepted the pixel last (attempt << 24 | ticket + 1, 0 = nobody yet), and cosf / sinf of the angle (what an
-// accepted pixel adds to the region's running sums).
+constexpr int kRegRing = 256;    // most recent region points kept in shared memory (the BFS frontier reads them)
+constexpr int kSpecCap = 16384;  // region / touched-list capacity of a speculative grower (larger regions run exclusively)
+// What the grower reads of a pixel, in ONE 16-byte load (the three separate planes it used to read cost three sectors per
+// neighbour): the level-line angle (degrees, or kNotDefDeg), the claim stamp (low 16 bits of the ticket that accepted the pixel
+// last, 0xffff = none; a hint only), and cosf / sinf of the angle (what an accepted pixel adds to the region's running sums).
 struct LsdPix {
     float ang;
-    unsigned int stamp;
+    unsigned int claim;
     float ca, sa;
 };
-// Stamps change under the growers' feet (atomicCAS at L2): records are always read past L1.
-__device__ __forceinline__ float4 lsd_ld_rec(const LsdPix* p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-struct LsdFrame {  // what rect_improve reads of a frame
-    const float* ang;  // level-line angle in degrees or kNotDefDeg
+struct LsdFrame {  // per-frame (and per-grower) device views
+    const float* ang;   // level-line angle in degrees or kNotDefDeg
+    const int* g2;      // gx^2 + gy^2
+    LsdPix* rec;        // per-pixel records
+    const float2* cs0;  // (float(cos(double angle)), float(sin(double angle))): a seed's initial sums
+    float2* sval;       // shared-memory staging of one warp, 36 entries
+    const unsigned int* used_bits;  // the committed USED map: one bit per pixel, shared memory
+    unsigned int* reg;  // region points, packed y<<16 | x
+    unsigned int* ring; // shared-memory copy of reg[n - kRegRing .. n)
     int W, H;
+    // The pixels a grower marks stay private until its region is committed.  Speculative growers keep them in a
+    // sparse bitmap in shared memory (a directory of 32x32-pixel tiles and a small pool of tile bitmaps); the
+    // commit-time re-growth, which has no size limit, uses a full bitmap in global memory.
+    bool sparse;
+    unsigned char* dir;   // [tiles] pool slot of the tile, 0xff = no pixel marked in it
+    unsigned short* rev;  // [pool_tiles] tile of a pool slot
+    unsigned int* pool;   // [pool_tiles][32] one word per tile row
+    int* ntiles;          // pool slots in use
+    int tw, pool_tiles;
+    unsigned int* bits;   // full private bitmap (W*H bits)
+    unsigned int* touched;  // log of accepted pixels (packed), capacity touched_cap
+    int reg_cap;            // capacity of reg
+    int touched_cap;        // capacity of touched
+    // in-flight claims (a hint that saves wasted growth, never needed for correctness): every accepted pixel is
+    // stamped with the low 16 bits of the grower's ticket; a grower that is about to accept a pixel stamped by an
+    // earlier ticket that is still uncommitted gives up (the seed is re-grown when its turn to commit comes).
+    int ticket;
+    const volatile int* commit_head;
 };
+__device__ __forceinline__ bool lsd_committed(const LsdFrame& F, unsigned o) { return (F.used_bits[o >> 5] >> (o & 31)) & 1u; }
+__device__ __forceinline__ bool lsd_priv_test(const LsdFrame& F, int x, int y, unsigned o) {
+    if (!F.sparse) return (F.bits[o >> 5] >> (o & 31)) & 1u;
+    const unsigned d = F.dir[(y >> 5) * F.tw + (x >> 5)];
+    return d != 0xffu && ((F.pool[d * 32 + (y & 31)] >> (x & 31)) & 1u);
+}
+// the tile must exist (lsd_priv_alloc)
+__device__ __forceinline__ void lsd_mark(const LsdFrame& F, int x, int y, unsigned o) {
+    if (!F.sparse) atomicOr(&F.bits[o >> 5], 1u << (o & 31));
+    else atomicOr(&F.pool[(unsigned)F.dir[(y >> 5) * F.tw + (x >> 5)] * 32 + (y & 31)], 1u << (x & 31));
+}
+// only called for pixels that are marked
+__device__ __forceinline__ void lsd_unmark(const LsdFrame& F, int x, int y, unsigned o) {
+    if (!F.sparse) atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
+    else atomicAnd(&F.pool[(unsigned)F.dir[(y >> 5) * F.tw + (x >> 5)] * 32 + (y & 31)], ~(1u << (x & 31)));
+}
+// warp-collective: makes sure the tiles of the lanes with `want` exist; false when the pool is exhausted
+__device__ __noinline__ bool lsd_priv_alloc_tiles(unsigned int* pool, unsigned char* dir, unsigned short* rev, int* ntiles, int pool_tiles,
+                                                  int t, unsigned need) {
+    const int lane = threadIdx.x & 31;
+    while (need) {
+        const int tj = __shfl_sync(0xffffffffu, t, __ffs(need) - 1);
+        const int k = *(volatile int*)ntiles;
+        if (k >= pool_tiles) return false;
+        pool[k * 32 + lane] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            dir[tj] = (unsigned char)k;
+            rev[k] = (unsigned short)tj;
+            *(volatile int*)ntiles = k + 1;
+        }
+        __syncwarp();
+        need &= ~__ballot_sync(0xffffffffu, t == tj);
+    }
+    return true;
+}
+__device__ __forceinline__ bool lsd_priv_alloc(const LsdFrame& F, bool want, int x, int y) {
+    if (!F.sparse) return true;
+    const int t = want ? (y >> 5) * F.tw + (x >> 5) : -1;
+    const unsigned need = __ballot_sync(0xffffffffu, want && F.dir[max(t, 0)] == 0xffu);
+    if (__builtin_expect(!need, 1)) return true;
+    return lsd_priv_alloc_tiles(F.pool, F.dir, F.rev, F.ntiles, F.pool_tiles, t, need);
+}
+// back to "nothing marked"; nt = entries of the touched log (every pixel ever marked is in it)
+__device__ __forceinline__ void lsd_priv_reset(const LsdFrame& F, int nt) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (F.sparse) {
+        const int k = *(volatile int*)F.ntiles;
+        #pragma unroll 1
+        for (int s2 = lane; s2 < k; s2 += 32) F.dir[F.rev[s2]] = 0xffu;
+        __syncwarp();
+        if (lane == 0) *(volatile int*)F.ntiles = 0;
+    } else {
+        #pragma unroll 1
+        for (int i = lane; i < nt; i += 32) {
+            const unsigned pp = F.touched[i];
+            const unsigned o = (pp >> 16) * (unsigned)F.W + (pp & 0xffffu);
+            atomicAnd(&F.bits[o >> 5], ~(1u << (o & 31)));
+        }
+    }
+    __syncwarp();
+}
 
 __device__ __forceinline__ double lsd_angle_diff_signed(double a, double b) {
     double diff = a - b;
@@ -325,6 +409,344 @@ __device__ __forceinline__ bool lsd_aligned_deg(float th, float adeg, float prec
     const float tf = t > 270.f ? fabsf(t - 360.f) : t;
     if (__builtin_expect(fabsf(tf - precdeg) > 2e-3f && fabsf(t - 270.f) > 2e-3f, 1)) return tf <= precdeg;
     return lsd_aligned_cold(th, adeg, prec);
+}
+
+// region_grow(): returns the region size; reg_angle (radians) is returned through *out_angle.
+//
+// The 32 lanes hold the 8-neighbourhoods of up to four consecutive region points in the reference's visiting order
+// (point, then row, then column; the centre is always USED and is skipped).  Acceptances must be resolved in that
+// order with the RUNNING region angle, which changes after every accepted pixel.  A batch is resolved by
+// hypothesis and verification:
+//   1. hypothesis H: the lanes that pass with a hint angle (the most recent angle known);
+//   2. every lane forms, in parallel, the float sums the reference would hold when it reaches that lane IF H is what
+//      happened before it (the accepted lanes' cos/sin are staged in shared memory and added in lane order), takes
+//      fastAtan2 of them and evaluates its own exact test;
+//   3. up to and including the first lane whose exact verdict differs from H, every verdict is the sequential one
+//      (induction over the lanes); those lanes are committed, the rest goes through another pass.
+// Most batches take one pass, whose serial chain is one fastAtan2.  The global loads of the next batch are issued
+// before the current one is resolved.
+// `nt` counts the entries of the touched log (speculative mode); returns -1 when a capacity is exceeded.
+struct GrowCand {
+    int xx, yy;
+    unsigned o;
+    float adeg, ca, sa;
+    unsigned short claim;
+    bool inb;
+};
+__device__ __forceinline__ bool lsd_claim_hit(const LsdFrame& F, unsigned short claim) {
+    const unsigned d = (unsigned)(F.ticket - (int)claim) & 0xffffu;  // tickets between the stamp and this grower
+    return d != 0 && d <= (unsigned)(F.ticket - *F.commit_head);
+}
+__device__ __forceinline__ void lsd_issue_cand(const LsdFrame& F, int ri, int n, int ddx, int ddy, GrowCand& c) {
+    const unsigned p = (n - ri <= kRegRing) ? F.ring[ri & (kRegRing - 1)] : F.reg[ri];
+    c.xx = (int)(p & 0xffffu) + ddx;
+    c.yy = (int)(p >> 16) + ddy;
+    c.inb = c.xx >= 0 && c.yy >= 0 && c.xx < F.W && c.yy < F.H;
+    c.o = 0;
+    c.adeg = kNotDefDeg;
+    c.ca = c.sa = 0.f;
+    c.claim = 0xffffu;
+    if (c.inb) {
+        c.o = (unsigned)c.yy * (unsigned)F.W + (unsigned)c.xx;
+        const float4 r = *reinterpret_cast<const float4*>(F.rec + c.o);
+        c.adeg = r.x;
+        c.claim = (unsigned short)__float_as_uint(r.y);
+        c.ca = r.z;
+        c.sa = r.w;
+    }
+}
+__device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy, double prec, double* out_angle, int& nt) {
+    const LsdFrame F = Fin;  // in registers (the caller's copy may live in local memory)
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    const unsigned so = (unsigned)sy * (unsigned)F.W + (unsigned)sx;
+    const float seed_deg = F.ang[so];
+    const float2 c0 = F.cs0[so];
+    float sumdx = c0.x, sumdy = c0.y;
+    float hint = seed_deg;
+    const float precdeg = (float)(prec * (180.0 / kPiD));
+    if (nt >= F.touched_cap) return -1;
+    if (!lsd_priv_alloc(F, lane == 0, sx, sy)) return -1;
+    if (lane == 0) {
+        F.reg[0] = ((unsigned)sy << 16) | (unsigned)sx;
+        F.ring[0] = ((unsigned)sy << 16) | (unsigned)sx;
+        lsd_mark(F, sx, sy, so);
+        F.touched[nt] = ((unsigned)sy << 16) | (unsigned)sx;
+        F.rec[so].claim = (unsigned)F.ticket & 0xffffu;
+    }
+    nt++;
+    __syncwarp();
+    int n = 1, i = 0, have = 0;
+    bool any = false;
+    const int b = lane >> 3, k8 = lane & 7, kk = k8 + (k8 >= 4 ? 1 : 0);
+    const int ddy = kk / 3 - 1, ddx = kk - (kk / 3) * 3 - 1;
+    GrowCand cur, nxt;
+    nxt.inb = false;
+    while (i < n) {
+        const int nb = min(4, n - i);
+        // the next batch's frontier points that exist already have their loads issued now (phase 1), so that they
+        // overlap the resolution of this batch; phase 0 loads what this batch did not get that way
+        const int have_next = max(0, min(4, n - (i + 4)));
+#pragma unroll 1
+        for (int phase = 0; phase < 2; phase++) {
+            GrowCand tmp;
+            tmp.inb = false;
+            const bool act = phase == 0 ? (b >= have && b < nb) : (b < have_next);
+            if (act) lsd_issue_cand(F, i + 4 * phase + b, n, ddx, ddy, tmp);
+            if (phase == 0) {
+                if (b < have) cur = nxt;
+                else cur = tmp;
+            } else {
+                nxt = tmp;
+            }
+        }
+        bool cand = false;
+        if (cur.inb) cand = cur.adeg != kNotDefDeg && !lsd_committed(F, cur.o) && !lsd_priv_test(F, cur.xx, cur.yy, cur.o);
+        unsigned rem = __ballot_sync(FULL, cand);
+        if (rem) {
+            const unsigned grp = __match_any_sync(FULL, cand ? cur.o : (0x80000000u | (unsigned)lane));  // lanes on the same pixel
+            while (rem) {
+                const bool inrem = (rem >> lane) & 1u;
+                // 1. hypothesis
+                float t = fabsf(hint - cur.adeg);
+                if (t > 270.f) t = fabsf(t - 360.f);
+                const bool hyp = inrem && t <= precdeg;
+                const unsigned H = __ballot_sync(FULL, hyp);
+                const bool inH = hyp && !(grp & H & lt);  // a pixel seen by several lanes is accepted by the first
+                const unsigned H2 = __ballot_sync(FULL, inH);
+                const int c = __popc(H2 & lt), cmax = __popc(H2);
+                if (inH) F.sval[c] = make_float2(cur.ca, cur.sa);
+                __syncwarp();
+                // 2. the sums the reference holds on reaching this lane, if H2 happened
+                float px = sumdx, py = sumdy;
+                for (int k0 = 0; k0 < cmax; k0 += 4) {
+                    const float2 v0 = F.sval[k0], v1 = F.sval[k0 + 1], v2 = F.sval[k0 + 2], v3 = F.sval[k0 + 3];
+                    if (k0 < c) { px = __fadd_rn(px, v0.x); py = __fadd_rn(py, v0.y); }
+                    if (k0 + 1 < c) { px = __fadd_rn(px, v1.x); py = __fadd_rn(py, v1.y); }
+                    if (k0 + 2 < c) { px = __fadd_rn(px, v2.x); py = __fadd_rn(py, v2.y); }
+                    if (k0 + 3 < c) { px = __fadd_rn(px, v3.x); py = __fadd_rn(py, v3.y); }
+                }
+                __syncwarp();
+                // the region angle is only defined by the sums after the first acceptance; before it, it is the seed's
+                const float th = (any || c > 0) ? fast_atan2_deg(py, px) : seed_deg;
+                bool v = false;
+                if (inrem && !(grp & H2 & lt)) v = lsd_aligned_deg(th, cur.adeg, precdeg, prec);
+                // 3. first lane whose verdict contradicts the hypothesis
+                const unsigned M = __ballot_sync(FULL, inrem && v != inH);
+                unsigned T = H2, resolved = FULL;
+                int hl = 31 - __clz(rem);
+                if (__builtin_expect(M != 0, 0)) {
+                    const int ls = __ffs(M) - 1;
+                    const unsigned below = (1u << ls) - 1u;
+                    T = (H2 & below) | (((H2 >> ls) & 1u) ? 0u : (1u << ls));
+                    resolved = (2u << ls) - 1u;
+                    hl = ls;
+                }
+                hint = __shfl_sync(FULL, th, hl);
+                const int cnt = __popc(T);
+                if (cnt) {
+                    if (__builtin_expect(n + cnt > F.reg_cap || nt + cnt > F.touched_cap, 0)) return -1;
+                    if (__builtin_expect(__any_sync(FULL, ((T >> lane) & 1u) && lsd_claim_hit(F, cur.claim)), 0)) return -2;
+                    if (__builtin_expect(!lsd_priv_alloc(F, (T >> lane) & 1u, cur.xx, cur.yy), 0)) return -1;
+                    if ((T >> lane) & 1u) {
+                        F.rec[cur.o].claim = (unsigned)F.ticket & 0xffffu;
+                        const int r = __popc(T & lt);
+                        const unsigned pk = ((unsigned)cur.yy << 16) | (unsigned)cur.xx;
+                        F.reg[n + r] = pk;
+                        F.ring[(n + r) & (kRegRing - 1)] = pk;
+                        lsd_mark(F, cur.xx, cur.yy, cur.o);
+                        F.touched[nt + r] = pk;
+                    }
+                    // sums after the last accepted lane: its own prefix plus its own pixel
+                    const int L = 31 - __clz(T);
+                    sumdx = __shfl_sync(FULL, __fadd_rn(px, cur.ca), L);
+                    sumdy = __shfl_sync(FULL, __fadd_rn(py, cur.sa), L);
+                    n += cnt;
+                    nt += cnt;
+                    any = true;
+                    rem &= ~__ballot_sync(FULL, (grp & T) != 0);
+                }
+                rem &= ~resolved;
+            }
+        }
+        __syncwarp();
+        i += nb;
+        have = have_next;
+    }
+    *out_angle = any ? (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad : (double)seed_deg * kDegToRad;
+    return n;
+}
+
+// sequential (reference-order) accumulation helper: every lane loads one region point, then all lanes replay the
+// 32 points in order through shuffles, so floating-point sums are formed exactly as the scalar loop forms them.
+struct RegPt { double x, y, w; float adeg; };
+__device__ __forceinline__ RegPt lsd_load_pt(const LsdFrame& F, int idx, int n) {
+    RegPt r;
+    r.x = r.y = r.w = 0;
+    r.adeg = 0;
+    if (idx < n) {
+        const unsigned p = F.reg[idx];
+        const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
+        r.x = (double)x;
+        r.y = (double)y;
+        const size_t o = (size_t)y * F.W + x;
+        r.w = sqrt((double)F.g2[o] / 4.0);  // modgrad
+        r.adeg = F.ang[o];
+    }
+    return r;
+}
+
+// region2rect() + get_theta()
+__device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double reg_angle, double prec, double p, LsdRect& rec) {
+    const LsdFrame F = Fin;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double x = 0, y = 0, sum = 0;
+    for (int base = 0; base < n; base += 32) {
+        const RegPt pt = lsd_load_pt(F, base + lane, n);  // lanes beyond n hold zeros: adding +0.0 changes nothing
+        const double pxw = __dmul_rn(pt.x, pt.w), pyw = __dmul_rn(pt.y, pt.w);
+#pragma unroll 2
+        for (int j = 0; j < 32; j++) {
+            x = __dadd_rn(x, __shfl_sync(FULL, pxw, j));
+            y = __dadd_rn(y, __shfl_sync(FULL, pyw, j));
+            sum = __dadd_rn(sum, __shfl_sync(FULL, pt.w, j));
+        }
+    }
+    x = x / sum;
+    y = y / sum;
+    // get_theta
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int base = 0; base < n; base += 32) {
+        const RegPt pt = lsd_load_pt(F, base + lane, n);
+        double txx = 0, tyy = 0, txy = 0;
+        if (base + lane < n) {
+            const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
+            txx = __dmul_rn(__dmul_rn(dy, dy), pt.w);
+            tyy = __dmul_rn(__dmul_rn(dx, dx), pt.w);
+            txy = __dmul_rn(__dmul_rn(dx, dy), pt.w);
+        }
+#pragma unroll 2
+        for (int j = 0; j < 32; j++) {
+            Ixx = __dadd_rn(Ixx, __shfl_sync(FULL, txx, j));
+            Iyy = __dadd_rn(Iyy, __shfl_sync(FULL, tyy, j));
+            Ixy = __dsub_rn(Ixy, __shfl_sync(FULL, txy, j));
+        }
+    }
+    const double dI = __dsub_rn(Ixx, Iyy);
+    const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy), sqrt(__dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy)))));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)__dsub_rn(lambda, Ixx), (float)Ixy)
+                                           : (double)fast_atan2_deg((float)Ixy, (float)__dsub_rn(lambda, Iyy));
+    theta *= kDegToRad;
+    if (fabs(lsd_angle_diff_signed(theta, reg_angle)) > prec) theta += kPiD;
+    double dx, dy;
+    sincos(theta, &dy, &dx);
+    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+#pragma unroll 1
+    for (int idx = lane; idx < n; idx += 32) {
+        const unsigned pp = F.reg[idx];
+        const double rdx = __dsub_rn((double)(int)(pp & 0xffffu), x), rdy = __dsub_rn((double)(int)(pp >> 16), y);
+        const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
+        const double w = __dadd_rn(__dmul_rn(-rdx, dy), __dmul_rn(rdy, dx));
+        l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+        w_max = fmax(w_max, w); w_min = fmin(w_min, w);
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        l_max = fmax(l_max, __shfl_xor_sync(FULL, l_max, o));
+        l_min = fmin(l_min, __shfl_xor_sync(FULL, l_min, o));
+        w_max = fmax(w_max, __shfl_xor_sync(FULL, w_max, o));
+        w_min = fmin(w_min, __shfl_xor_sync(FULL, w_min, o));
+    }
+    rec.x1 = __dadd_rn(x, __dmul_rn(l_min, dx)); rec.y1 = __dadd_rn(y, __dmul_rn(l_min, dy));
+    rec.x2 = __dadd_rn(x, __dmul_rn(l_max, dx)); rec.y2 = __dadd_rn(y, __dmul_rn(l_max, dy));
+    rec.width = __dsub_rn(w_max, w_min);
+    rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
+    if (rec.width < 1.0) rec.width = 1.0;
+}
+
+__device__ __forceinline__ double lsd_density(int n, const LsdRect& rec) {
+    return (double)n / (sqrt(lsd_dist_sq(rec.x1, rec.y1, rec.x2, rec.y2)) * rec.width);
+}
+
+// reduce_region_radius(): sequential swap-with-last removal keeps the reference's point order
+__device__ __noinline__ bool lsd_reduce_region_radius(const LsdFrame& Fin, int& n, double reg_angle, double prec, double p, LsdRect& rec,
+                                         double density, double density_th) {
+    const LsdFrame F = Fin;
+    const int lane = threadIdx.x & 31;
+    const unsigned p0 = F.reg[0];
+    const double xc = (double)(int)(p0 & 0xffffu), yc = (double)(int)(p0 >> 16);
+    const double r1 = lsd_dist_sq(xc, yc, rec.x1, rec.y1), r2 = lsd_dist_sq(xc, yc, rec.x2, rec.y2);
+    double radSq = r1 > r2 ? r1 : r2;
+    while (density < density_th) {
+        radSq *= 0.75 * 0.75;
+        if (lane == 0) {
+            int m = n;
+            for (int i = 0; i < m; ++i) {
+                const unsigned q = F.reg[i];
+                const int qx = (int)(q & 0xffffu), qy = (int)(q >> 16);
+                if (lsd_dist_sq(xc, yc, (double)qx, (double)qy) > radSq) {
+                    lsd_unmark(F, qx, qy, (unsigned)qy * (unsigned)F.W + (unsigned)qx);
+                    F.reg[i] = F.reg[m - 1];
+                    F.reg[m - 1] = q;
+                    --m;
+                    --i;
+                }
+            }
+            n = m;
+        }
+        n = __shfl_sync(0xffffffffu, n, 0);
+        __syncwarp();
+        if (n < 2) return false;
+        lsd_region2rect(Fin, n, reg_angle, prec, p, rec);
+        density = lsd_density(n, rec);
+    }
+    return true;
+}
+
+// refine()
+// returns 1 = refined, 0 = rejected, -1 = capacity exceeded (speculative growers)
+// F: register copy for the inlined loops; Fm: the same view in (shared) memory, handed to the out-of-line callees
+__device__ int lsd_refine(const LsdFrame& F, const LsdFrame& Fm, int& n, double& reg_angle, double prec, double p, LsdRect& rec, double density_th, int& nt) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double density = lsd_density(n, rec);
+    if (density >= density_th) return 1;
+    const unsigned p0 = F.reg[0];
+    const int sx = (int)(p0 & 0xffffu), sy = (int)(p0 >> 16);
+    const double xc = (double)sx, yc = (double)sy;
+    const double ang_c = (double)F.ang[(size_t)sy * F.W + sx] * kDegToRad;
+    double sum = 0, s_sum = 0;
+    int cnt_in = 0;
+    for (int base = 0; base < n; base += 32) {
+        const RegPt pt = lsd_load_pt(F, base + lane, n);
+        bool inside = false;
+        double ang_d = 0, ang_d2 = 0;
+        if (base + lane < n) {
+            lsd_unmark(F, (int)pt.x, (int)pt.y, (unsigned)(int)pt.y * (unsigned)F.W + (unsigned)(int)pt.x);
+            inside = sqrt(lsd_dist_sq(xc, yc, pt.x, pt.y)) < rec.width;
+            if (inside) {
+                ang_d = lsd_angle_diff_signed((double)pt.adeg * kDegToRad, ang_c);
+                ang_d2 = __dmul_rn(ang_d, ang_d);
+            }
+        }
+        cnt_in += __popc(__ballot_sync(FULL, inside));
+#pragma unroll 2
+        for (int j = 0; j < 32; j++) {  // points outside contribute +0.0
+            sum = __dadd_rn(sum, __shfl_sync(FULL, ang_d, j));
+            s_sum = __dadd_rn(s_sum, __shfl_sync(FULL, ang_d2, j));
+        }
+    }
+    __syncwarp();
+    const double mean_angle = sum / (double)cnt_in;
+    const double tau = 2.0 * sqrt(__dadd_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)) / (double)cnt_in,
+                                            __dmul_rn(mean_angle, mean_angle)));
+    n = lsd_region_grow(Fm, sx, sy, tau, &reg_angle, nt);
+    if (n < 0) return n;
+    if (n < 2) return 0;
+    lsd_region2rect(Fm, n, reg_angle, prec, p, rec);
+    density = lsd_density(n, rec);
+    if (density < density_th) return lsd_reduce_region_radius(Fm, n, reg_angle, prec, p, rec, density, density_th) ? 1 : 0;
+    return 1;
 }
 
 // ---- NFA ----
@@ -576,20 +998,42 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
     return S.log_nfa;
 }
 
-}  // namespace pl
-
-#include "lsd_grow.cuh"
-
-namespace pl {
-
+// flsd() main loop.  Persistent CTAs take frames from a counter; the G warps of a CTA are region growers.
+//
+// Region growing is ordered (seeds by gradient bin, shared USED map), but regions that do not touch the same pixels
+// commute.  The kernel runs the ordered loop as a window of speculative transactions with in-order commit:
+//   * select (one warp at a time): the next seed that is unused in the committed map gets the next ticket and a
+//     slot of the window (kSlots tickets may be uncommitted at once).  A seed stamped by an uncommitted ticket is
+//     most likely being swallowed by that region: it gets its ticket but is not grown ("deferred");
+//   * grow (any number of warps at once): the warp grows its seed reading the committed USED map (global bytes),
+//     keeps the pixels it marks in its private bitmap in shared memory and logs every pixel it ever accepts (initial
+//     growth and refine re-growth) in the touched list of a buffer from the CTA's pool; the final region, the fitted
+//     rectangle and the log stay in the buffer, the private bitmap is cleared, and the warp goes for the next seed.
+//     A grower that runs into a pixel stamped by an earlier uncommitted ticket gives up (deferred);
+//   * commit (one warp at a time, strictly in ticket order): seed already committed -> the seed is void (an earlier
+//     region swallowed it);  deferred, or a logged pixel already committed (the growth depended on a region that
+//     was committed after it read the map) -> the committing warp grows the seed now, when everything before it is
+//     committed, with the frame-sized buffers;  otherwise the growth is exactly what the sequential algorithm would
+//     have done.  The region is written to the USED map and its rectangle is queued.
+// Committed pixels are never released, tickets follow the seed order, and a grower only ever sees pixels of
+// earlier tickets in the map, so the result is the sequential one whatever the stamps say.  rect_improve only reads
+// the angle map and does not influence later regions: it runs afterwards in k_lsd_nfa, and accepted segments are
+// compacted in seed order.
+struct LsdQueueItem { LsdRect rec; };
+constexpr int kNfaChunk = 16;         // rectangles per work item of the tail helpers
+constexpr int kNfaChunksPerFrame = 2048;  // item = frame * kNfaChunksPerFrame + chunk
+constexpr uint8_t kNfaTodo = 0xff;    // qvalid: rectangle not validated yet
 // rect_improve of rectangle t of frame f -> qres / qvalid (one warp)
 __device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restrict__ ang, const LsdQueueItem* __restrict__ queue,
                                          LsdSeg* __restrict__ qres, uint8_t* __restrict__ qvalid, const NfaTabs& T, int f, int t) {
     const int lane = threadIdx.x & 31;
     LsdFrame F;
     F.ang = ang;
-    F.W = g.W;
-    F.H = g.H;
+    F.g2 = nullptr; F.rec = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
+    F.W = g.W; F.H = g.H;
+    F.sparse = false; F.dir = nullptr; F.rev = nullptr; F.pool = nullptr; F.ntiles = nullptr; F.tw = 0; F.pool_tiles = 0;
+    F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
+    F.ticket = 0; F.commit_head = nullptr;
     const double log_eps = 0.0;
     LsdRect rec = queue[(size_t)f * g.seg_cap + t].rec;
     const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
@@ -606,8 +1050,607 @@ __device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restr
     __syncwarp();
 }
 
+constexpr int kMaxGrowers = 16;    // grower warps per CTA
+constexpr int kMaxFrameSlots = 4;  // frames a CTA works on at once
+constexpr int kSlots = 256;        // ticket slots per frame (the window of uncommitted tickets is at most this)
+constexpr int kPool = 64;          // region buffers per CTA
+constexpr int kSmall = 64;         // regions up to this size (and log length) are parked in their slot's small buffer instead
+constexpr int kTiny = 16;          // regions without a rectangle up to this size never leave shared memory: the points sit in their ticket slot
+constexpr int kSvalEntries = 36;
+constexpr int kMaxPoolTiles = 64, kMinPoolTiles = 24;
+// shared memory of a grower warp: sval | ring | tile pool | rev | dir | ntiles, each part 16-byte aligned
+struct GrowSmem {
+    int tiles, pool_tiles;
+    int window;       // tickets that may be uncommitted at once (<= kSlots): deeper speculation wastes more growth
+    int frame_slots;  // frames per CTA
+    int bits_words;   // words of a W*H bitmap
+    int tail_nfa;     // CTAs without frames validate rectangles of finished frames
+    int poll_ns;      // sleep of a warp that found nothing to do before it looks again
+    __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
+    __host__ __device__ size_t off_pool() const { return off_ring() + kRegRing * sizeof(unsigned int); }
+    __host__ __device__ size_t off_rev() const { return off_pool() + (size_t)pool_tiles * 32 * sizeof(unsigned int); }
+    __host__ __device__ size_t off_dir() const { return off_rev() + (((size_t)pool_tiles * sizeof(unsigned short) + 15) & ~(size_t)15); }
+    __host__ __device__ size_t off_ntiles() const { return off_dir() + (((size_t)tiles + 15) & ~(size_t)15); }
+    __host__ __device__ size_t per_grower() const { return off_ntiles() + 16; }
+    // per frame slot: ticket slots | committed bitmap | tiny regions (kTiny points per ticket slot)
+    __host__ __device__ size_t off_tiny() const { return kSlots * sizeof(int4) + (((size_t)bits_words * sizeof(unsigned int) + 15) & ~(size_t)15); }
+    __host__ __device__ size_t per_frame() const { return off_tiny() + (size_t)kSlots * kTiny * sizeof(unsigned int); }
+    __host__ __device__ size_t total(int growers) const { return (size_t)frame_slots * per_frame() + (size_t)growers * per_grower(); }
+};
+// ticket slot (shared memory, int4): x = seed pixel, y = region size, z = touched-log size,
+// w = state | (status + 2) << 8 | (buffer + 1) << 16   (buffer -1 with status >= 0: the slot's small buffer)
+enum { kSlotFree = 0, kSlotReady = 1, kSlotGrowing = 2, kSlotDone = 3 };
+enum { kActNone = 0, kActCommit, kActIssue, kActTake, kActBuffer, kActInit, kActFinish, kActExit };
+enum { kStDeferred = -2, kStCapacity = -1, kStNoRect = 0, kStRect = 1 };
+enum { kFrameEmpty = 0, kFrameBusy = 1, kFrameRunning = 2, kFrameNoMore = 3 };
+__device__ __forceinline__ int slot_pack(int state, int status, int buf) { return state | ((status + 2) << 8) | ((buf + 1) << 16); }
+struct GrowCtl {  // one per frame slot
+    int active;       // kFrame*
+    int sel_lock, com_lock;
+    int next_pos;     // next position of the seed list to look at
+    int ticket_next;  // tickets issued
+    int grow_next;    // tickets handed to a grower
+    int commit_head;  // tickets committed
+    int head;         // rectangles queued
+    int all_issued;   // the seed list is exhausted
+    int frame, ns;
+    long long t_start;
+    unsigned long long stat[8];  // committed, void, regrown, deferred, growth cycles, given-up cycles, commit cycles, regrow cycles
+};
+struct GrowConfig {
+    int growers = 0, pool_tiles = 0, frame_slots = 1;
+};
+struct GrowResult {
+    int status, n, nt;
+    LsdRect rec;
+};
+__device__ __forceinline__ bool warp_try_lock(int* lock, int lane) {
+    int got = 0;
+    if (lane == 0) got = atomicCAS(lock, 0, 1) == 0;
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got) __threadfence_block();
+    return got != 0;
+}
+// a warp-uniform decision from a condition that reads state other warps change: lane 0 decides
+#define WARP_UNIFORM(cond) (__shfl_sync(0xffffffffu, (lane == 0) ? (int)(cond) : 0, 0) != 0)
+__device__ __forceinline__ void warp_unlock(int* lock, int lane) {
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) atomicExch(lock, 0);
+    __syncwarp();
+}
+__device__ __forceinline__ int pool_pop(unsigned long long* mask, int lane) {
+    int b = -1;
+    if (lane == 0) {
+        while (true) {
+            const unsigned long long m = *(volatile unsigned long long*)mask;
+            if (!m) break;
+            const int c = __ffsll((long long)m) - 1;
+            if (atomicCAS(mask, m, m & ~(1ull << c)) == m) { b = c; break; }
+        }
+    }
+    return __shfl_sync(0xffffffffu, b, 0);
+}
+// grow + fit + refine one seed into the buffers of F; leaves the private marks clean
+// Fin and out live in shared memory (one per warp): the out-of-line callees read the view from there instead of
+// every thread keeping (and spilling) its own copy in local memory.
+__device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min_reg_size, GrowResult* out) {
+    const LsdFrame F = Fin;  // register copy for the inlined code
+    const int lane = threadIdx.x & 31;
+    const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
+    const double density_th = 0.7;
+    const int sx = pix % F.W, sy = pix / F.W;
+    double reg_angle;
+    int nt = 0, status = kStNoRect;
+    LsdRect rec;
+    int n = lsd_region_grow(Fin, sx, sy, prec, &reg_angle, nt);
+    if (n < 0) {
+        status = n;
+    } else if (n >= min_reg_size) {
+        lsd_region2rect(Fin, n, reg_angle, prec, p, rec);
+        status = lsd_refine(F, Fin, n, reg_angle, prec, p, rec, density_th, nt);
+    }
+    lsd_priv_reset(F, nt);
+    if (lane == 0) {
+        out->status = status;
+        out->n = n;
+        out->nt = nt;
+        if (status == kStRect) out->rec = rec;
+    }
+    __syncwarp();
+}
+
+// device buffers of k_lsd_grow
+struct GrowBufs {
+    const float* angdeg;
+    const int* g2;
+    LsdPix* rec;
+    const float2* cs0;
+    const unsigned int* seeds;
+    const int* n_seeds;
+    unsigned int* big_reg;       // [frame][plane]
+    unsigned int* big_touched;   // [cta][frame slot][2 * plane]
+    unsigned int* big_bits;      // [cta][frame slot][bits_words], all-zero between uses
+    unsigned int* pool_reg;      // [cta][kPool][kSpecCap]
+    unsigned int* pool_touched;  // [cta][kPool][kSpecCap]
+    LsdRect* pool_rect;          // [cta][kPool]
+    unsigned int* small_buf;     // [cta][frame slot][kSlots][reg kSmall | touched kSmall]
+    LsdRect* small_rect;         // [cta][frame slot][kSlots]
+    LsdQueueItem* queue;         // [frame][seg_cap]
+    int* n_rects;
+    int* flags;
+    long long* phase_cycles;
+    int* frame_counter;
+    size_t plane;
+    // tail helpers: finished frames publish chunks of their rectangles; CTAs without frames validate them
+    LsdSeg* qres;
+    uint8_t* qvalid;
+    unsigned int* nfa_items;  // [nf * kNfaChunksPerFrame] 0xffffffff = not published yet
+    int* nfa_ctl;             // [0] items published (tail), [1] items taken (cursor), [2] frames finished
+    NfaTabs nfa_tabs;
+};
+
+// A CTA works on up to gs.frame_slots frames at once and its warps take whatever work any of them offers, so a warp
+// that would wait (the window of a frame is full, nothing is ready, the head region is still growing) works on
+// another frame instead.  Frames are handed out through a global counter.
+// Two instantiations: kBound = 256 (up to 8 growers, all the registers they want: single-frame latency) and kBound = 512
+// (up to 16 growers at 128 registers: throughput over many frames).
+template <int kBound>
+__global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, GrowBufs B) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ GrowCtl s_ctl[kMaxFrameSlots];
+    __shared__ LsdFrame s_view[kMaxGrowers];    // the frame view a warp hands to lsd_grow_seed
+    __shared__ GrowResult s_res[kMaxGrowers];
+    __shared__ unsigned long long s_free_mask;  // free buffers of the pool
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const int FS = gs.frame_slots;
+    const size_t plane = B.plane;
+    unsigned char* s_mine = s_raw + (size_t)FS * gs.per_frame() + (size_t)warp * gs.per_grower();
+    const size_t cta_fs = (size_t)blockIdx.x * FS;
+    unsigned int* my_pool_reg = B.pool_reg + (size_t)blockIdx.x * kPool * kSpecCap;
+    unsigned int* my_pool_touched = B.pool_touched + (size_t)blockIdx.x * kPool * kSpecCap;
+    LsdRect* my_pool_rect = B.pool_rect + (size_t)blockIdx.x * kPool;
+    LsdFrame F;
+    F.sval = reinterpret_cast<float2*>(s_mine);
+    F.ring = reinterpret_cast<unsigned int*>(s_mine + gs.off_ring());
+    F.pool = reinterpret_cast<unsigned int*>(s_mine + gs.off_pool());
+    F.rev = reinterpret_cast<unsigned short*>(s_mine + gs.off_rev());
+    F.dir = s_mine + gs.off_dir();
+    F.ntiles = reinterpret_cast<int*>(s_mine + gs.off_ntiles());
+    F.tw = (g.W + 31) >> 5;
+    F.pool_tiles = gs.pool_tiles;
+    F.sparse = true;
+    F.bits = nullptr;
+    F.ticket = 0;
+    F.W = g.W;
+    F.H = g.H;
+    F.reg = nullptr;
+    F.touched = nullptr;
+    F.reg_cap = F.touched_cap = 0;
+    #pragma unroll 1
+    for (int i = lane; i < gs.tiles; i += 32) F.dir[i] = 0xffu;
+    if (lane == 0) *F.ntiles = 0;
+    if (threadIdx.x < kMaxFrameSlots) s_ctl[threadIdx.x].active = threadIdx.x < FS ? kFrameEmpty : kFrameNoMore;
+    if (threadIdx.x == 0) s_free_mask = ~0ull << G;  // buffer w starts with warp w
+    __syncthreads();
+    int mybuf = warp, rr = warp % FS;
+    GrowResult res;
+    while (true) {
+        // ---------------- what to do next (a tight loop: idle warps must not thrash the instruction cache) ----------------
+        int action = kActNone, fsi = 0;
+        while (true) {
+            if (lane == 0) {
+                int nomore = 0;
+                for (int k = 0; k < FS && action == kActNone; k++) {
+                    const int cand = rr + k < FS ? rr + k : rr + k - FS;
+                    volatile GrowCtl* c = &s_ctl[cand];
+                    volatile int4* sl = reinterpret_cast<volatile int4*>(s_raw + (size_t)cand * gs.per_frame());
+                    const int st = c->active;
+                    if (st == kFrameNoMore) { nomore++; continue; }
+                    if (st == kFrameEmpty) {
+                        // fair start: a CTA fills its k-th frame slot only after every CTA had the chance to fill k - 1
+                        // slots, so that the frames spread evenly over the SMs instead of going to the CTAs that start first
+                        if (cand == 0 || *(volatile int*)B.frame_counter >= cand * (int)gridDim.x) { action = kActInit; fsi = cand; break; }
+                        continue;
+                    }
+                    if (st != kFrameRunning) continue;
+                    const int h = c->commit_head, tn = c->ticket_next, gn = c->grow_next, ai = c->all_issued;
+                    if (ai && h == tn) action = kActFinish;
+                    else if (h < tn && (sl[h % kSlots].w & 0xff) == kSlotDone && c->com_lock == 0) action = kActCommit;
+                    else if (mybuf >= 0 && gn < tn) action = kActTake;
+                    else if (!ai && tn - gn < G && tn - h < gs.window && c->sel_lock == 0) action = kActIssue;
+                    if (action != kActNone) fsi = cand;
+                }
+                if (action == kActNone) {
+                    if (nomore == FS) action = kActExit;
+                    else if (mybuf < 0 && *(volatile unsigned long long*)&s_free_mask != 0) action = kActBuffer;
+                }
+            }
+            action = __shfl_sync(FULL, action, 0);
+            if (action != kActNone) break;
+            __nanosleep(gs.poll_ns);
+        }
+        if (action == kActExit) {
+            // no frame left for this CTA: validate rectangles of finished frames while other CTAs are still growing.  Once every
+            // frame is finished the kernel should end: k_lsd_nfa then validates what is left with the whole GPU.
+            bool quit = nf <= (int)gridDim.x || !gs.tail_nfa;  // one frame per CTA at most: there is no tail worth filling
+            while (!quit) {
+                int it = 0;
+                if (lane == 0) it = atomicAdd(B.nfa_ctl + 1, 1);
+                it = __shfl_sync(FULL, it, 0);
+                unsigned item = 0xffffffffu;
+                while (true) {  // the item may not be published yet
+                    if (lane == 0) {
+                        if (*(volatile int*)(B.nfa_ctl + 2) >= nf) item = 0xfffffffeu;  // every frame finished: stop helping
+                        else if (it < *(volatile int*)(B.nfa_ctl + 0)) item = *(volatile unsigned int*)(B.nfa_items + it);
+                    }
+                    item = __shfl_sync(FULL, item, 0);
+                    if (item != 0xffffffffu) break;
+                    __nanosleep(1000);
+                }
+                if (item == 0xfffffffeu) break;
+                __threadfence();
+                const int fi = (int)(item / kNfaChunksPerFrame), ch = (int)(item % kNfaChunksPerFrame);
+                const int nr = min(B.n_rects[fi], g.seg_cap);
+                for (int t = ch * kNfaChunk; t < min(nr, (ch + 1) * kNfaChunk); t++)
+                    lsd_nfa_one(g, B.angdeg + (size_t)fi * plane, B.queue, B.qres, B.qvalid, B.nfa_tabs, fi, t);
+            }
+            break;
+        }
+        fsi = __shfl_sync(FULL, fsi, 0);
+        rr = fsi + 1 < FS ? fsi + 1 : 0;
+        if (action == kActBuffer) {
+            mybuf = pool_pop(&s_free_mask, lane);
+            continue;
+        }
+        GrowCtl* ctlp = &s_ctl[fsi];
+        volatile GrowCtl* ctl = ctlp;
+        volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_raw + (size_t)fsi * gs.per_frame());
+        unsigned int* s_used = reinterpret_cast<unsigned int*>(s_raw + (size_t)fsi * gs.per_frame() + kSlots * sizeof(int4));
+        unsigned int* s_tiny = reinterpret_cast<unsigned int*>(s_raw + (size_t)fsi * gs.per_frame() + gs.off_tiny());
+        const volatile unsigned int* vused = s_used;
+        if (action == kActInit || action == kActFinish) {
+            // a finished frame is closed, and the slot gets the next frame, by one warp that holds both locks
+            bool mine;
+            if (action == kActInit) {
+                mine = WARP_UNIFORM(atomicCAS(&ctlp->active, kFrameEmpty, kFrameBusy) == kFrameEmpty);
+            } else {
+                mine = warp_try_lock(&ctlp->com_lock, lane);
+                if (mine && !warp_try_lock(&ctlp->sel_lock, lane)) {
+                    warp_unlock(&ctlp->com_lock, lane);
+                    mine = false;
+                }
+                if (mine) {
+                    const bool done = WARP_UNIFORM(ctl->active == kFrameRunning && ctl->all_issued && ctl->commit_head == ctl->ticket_next);
+                    if (!done) {
+                        warp_unlock(&ctlp->sel_lock, lane);
+                        warp_unlock(&ctlp->com_lock, lane);
+                        mine = false;
+                    }
+                }
+                if (mine && lane == 0) {
+                    ctl->active = kFrameBusy;
+                    const int f = ctl->frame;
+                    B.n_rects[f] = ctl->head;
+                    __threadfence();
+                    if (B.phase_cycles) {
+                        long long* pc = B.phase_cycles + (size_t)f * 8;
+                        pc[0] = (long long)((ctl->stat[4] / 1000) + ((ctl->stat[7] / 1000) << 20) + ((ctl->stat[5] / 1000) << 40));
+                        pc[1] = clock64() - ctl->t_start;
+                        pc[2] = (long long)ctl->stat[6];
+                        pc[3] = ctl->ticket_next;
+                        pc[4] = (long long)ctl->stat[2];
+                        pc[5] = (long long)ctl->stat[0];
+                        pc[6] = (long long)ctl->stat[3];
+                        pc[7] = (long long)ctl->stat[1];
+                    }
+                }
+                __syncwarp();
+                if (mine) {  // publish the frame's rectangles for the tail helpers, then count the frame as finished
+                    const int fdone = __shfl_sync(FULL, ctl->frame, 0), nr = min(__shfl_sync(FULL, ctl->head, 0), g.seg_cap);
+                    const int nchunks = (nr + kNfaChunk - 1) / kNfaChunk;
+                    if (nchunks > 0 && nchunks <= kNfaChunksPerFrame) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(B.nfa_ctl + 0, nchunks);
+                        base = __shfl_sync(FULL, base, 0);
+                        for (int i = lane; i < nchunks; i += 32) B.nfa_items[base + i] = (unsigned)fdone * kNfaChunksPerFrame + (unsigned)i;
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(B.nfa_ctl + 2, 1);
+                }
+            }
+            if (!mine) continue;
+            int f = 0;
+            if (lane == 0) f = atomicAdd(B.frame_counter, 1);
+            f = __shfl_sync(FULL, f, 0);
+            if (f < nf) {
+                #pragma unroll 1
+                for (int i = lane; i < kSlots; i += 32) s_slot[i].w = slot_pack(kSlotFree, 0, -1);
+                #pragma unroll 1
+                for (int i = lane; i < gs.bits_words; i += 32) s_used[i] = 0;
+                if (lane == 0) {
+                    ctl->next_pos = ctl->ticket_next = ctl->grow_next = ctl->commit_head = 0;
+                    ctl->head = 0;
+                    ctl->all_issued = 0;
+                    ctl->frame = f;
+                    ctl->ns = B.n_seeds[f];
+                    ctl->t_start = clock64();
+                    for (int k = 0; k < 8; k++) ctl->stat[k] = 0;
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) {
+                ctl->sel_lock = 0;
+                ctl->com_lock = 0;
+                __threadfence_block();
+                ctl->active = f < nf ? kFrameRunning : kFrameNoMore;
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---------------- commit duty: strictly in ticket order ----------------
+        if (action == kActCommit && warp_try_lock(&ctlp->com_lock, lane)) {
+            const long long t0 = clock64();
+            const int f = __shfl_sync(FULL, ctl->frame, 0);
+            F.ang = B.angdeg + (size_t)f * plane;
+            F.g2 = B.g2 + (size_t)f * plane;
+            F.rec = B.rec + (size_t)f * plane;
+            F.cs0 = B.cs0 + (size_t)f * plane;
+            F.used_bits = s_used;
+            F.commit_head = &ctlp->commit_head;
+            LsdQueueItem* q = B.queue + (size_t)f * g.seg_cap;
+            const unsigned int* my_small = B.small_buf + (cta_fs + fsi) * kSlots * 2 * kSmall;
+            const LsdRect* my_small_rect = B.small_rect + (cta_fs + fsi) * kSlots;
+            while (true) {
+                const int h = __shfl_sync(FULL, ctl->commit_head, 0);
+                volatile int4* sl = &s_slot[h % kSlots];
+                if (!WARP_UNIFORM(ctl->active == kFrameRunning && h < ctl->ticket_next && (sl->w & 0xff) == kSlotDone)) break;
+                __threadfence_block();
+                const int pix = sl->x, w = sl->w;
+                int n = sl->y, nt = sl->z, status = ((w >> 8) & 0xff) - 2;
+                const int buf = ((w >> 16) & 0xff) - 1;
+                int kind = 0;  // 0 committed, 1 void
+                if ((vused[pix >> 5] >> (pix & 31)) & 1u) {
+                    kind = 1;  // swallowed by an earlier region
+                } else {
+                    const unsigned int* rg = buf >= 0 ? my_pool_reg + (size_t)buf * kSpecCap : my_small + (size_t)(h % kSlots) * 2 * kSmall;
+                    bool redo = status < 0;
+                    // This section is serial per frame, and a region's points, log and rectangle live in global memory: the three
+                    // reads are issued together (one round trip instead of three dependent ones); the first 32 entries of the two
+                    // lists — all of them for most regions — and the rectangle (24 words, one per lane) stay in registers.
+                    unsigned rg0 = 0, tk0 = 0, rc0 = 0;
+                    // Most tickets are regions of a few pixels that get no rectangle (85 % of the commits): their points never left
+                    // shared memory (the grower parked them in the ticket slot), so this serial section does not touch global memory
+                    // for them; the accept log of such a region is its point list.
+                    const bool tiny = !redo && status == kStNoRect && buf < 0 && n <= kTiny && nt == n;
+                    if (tiny) {
+                        if (lane < n) rg0 = s_tiny[(h % kSlots) * kTiny + lane];
+                        bool conflict = false;
+                        if (lane < n) {
+                            const unsigned o = (rg0 >> 16) * (unsigned)g.W + (rg0 & 0xffffu);
+                            conflict = ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
+                        }
+                        redo = __any_sync(FULL, conflict);
+                    } else if (!redo) {
+                        const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
+                        if (lane < nt) tk0 = tk[lane];
+                        if (lane < n) rg0 = rg[lane];
+                        if (status == kStRect && lane < (int)(sizeof(LsdRect) / 4))
+                            rc0 = reinterpret_cast<const unsigned int*>(buf >= 0 ? &my_pool_rect[buf] : &my_small_rect[h % kSlots])[lane];
+                        bool conflict = false;
+                        if (lane < nt) {
+                            const unsigned o = (tk0 >> 16) * (unsigned)g.W + (tk0 & 0xffffu);
+                            conflict = ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
+                        }
+                        #pragma unroll 1
+                        for (int i = lane + 32; i < nt; i += 32) {
+                            const unsigned pp = tk[i];
+                            const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
+                            conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
+                        }
+                        redo = __any_sync(FULL, conflict);
+                    }
+                    const bool regrown = redo;
+                    LsdRect rec;
+                    if (redo) {  // everything before this ticket is committed: this growth is the sequential one
+                        const long long g0 = clock64();
+                        LsdFrame FS2 = F;
+                        FS2.sparse = false;
+                        FS2.bits = B.big_bits + (cta_fs + fsi) * gs.bits_words;
+                        FS2.reg = B.big_reg + (size_t)f * plane;
+                        FS2.touched = B.big_touched + (cta_fs + fsi) * 2 * plane;
+                        FS2.reg_cap = (int)plane;
+                        FS2.touched_cap = (int)(2 * plane);
+                        FS2.ticket = h;
+                        __syncwarp();
+                        if (lane == 0) s_view[warp] = FS2;
+                        __syncwarp();
+                        lsd_grow_seed(s_view[warp], pix, g.min_reg_size, &s_res[warp]);
+                        res = s_res[warp];
+                        status = res.status;
+                        n = res.n;
+                        rec = res.rec;
+                        rg = FS2.reg;
+                        if (status < 0 && lane == 0) atomicOr(B.flags + f, 2);
+                        if (lane == 0) {
+                            ctl->stat[2]++;
+                            ctl->stat[7] += (unsigned long long)(clock64() - g0);
+                        }
+                    }
+                    if (status >= 0) {
+                        if (!regrown && lane < n) {
+                            const unsigned o = (rg0 >> 16) * (unsigned)g.W + (rg0 & 0xffffu);
+                            atomicOr(&s_used[o >> 5], 1u << (o & 31));
+                        }
+                        #pragma unroll 1
+                        for (int i = regrown ? lane : lane + 32; i < n; i += 32) {
+                            const unsigned pp = rg[i];
+                            const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
+                            atomicOr(&s_used[o >> 5], 1u << (o & 31));
+                        }
+                        if (status == kStRect) {
+                            const int head = __shfl_sync(FULL, ctl->head, 0);
+                            if (head < g.seg_cap) {
+                                if (regrown) {
+                                    if (lane == 0) q[head].rec = rec;
+                                } else if (lane < (int)(sizeof(LsdRect) / 4)) {
+                                    reinterpret_cast<unsigned int*>(&q[head].rec)[lane] = rc0;
+                                }
+                                if (lane == 0) ctl->head = head + 1;
+                            } else if (lane == 0) {
+                                atomicOr(B.flags + f, 1);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) {
+                    ctl->stat[kind]++;
+                    if (buf >= 0) atomicOr(&s_free_mask, 1ull << buf);
+                    sl->w = slot_pack(kSlotFree, 0, -1);
+                    __threadfence_block();
+                    ctl->commit_head = h + 1;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) ctl->stat[6] += (unsigned long long)(clock64() - t0);
+            warp_unlock(&ctlp->com_lock, lane);
+            continue;
+        }
+        // ---------------- issue tickets: one chunk of the seed list at a time ----------------
+        if (action == kActIssue && warp_try_lock(&ctlp->sel_lock, lane)) {
+            if (WARP_UNIFORM(ctl->active == kFrameRunning && !ctl->all_issued)) {
+                const int f = __shfl_sync(FULL, ctl->frame, 0), ns = __shfl_sync(FULL, ctl->ns, 0);
+                const unsigned int* sd = B.seeds + (size_t)f * plane;
+                int t = __shfl_sync(FULL, ctl->ticket_next, 0);
+                int pos = __shfl_sync(FULL, ctl->next_pos, 0);
+                bool full = false;
+                while (!full && pos < ns && t - __shfl_sync(FULL, ctl->grow_next, 0) < G) {
+                    const int idx = pos + lane;
+                    unsigned pix = 0;
+                    bool free_ = false;
+                    if (idx < ns) {
+                        pix = sd[idx];
+                        free_ = ((vused[pix >> 5] >> (pix & 31)) & 1u) == 0;
+                    }
+                    unsigned m = __ballot_sync(FULL, free_);
+                    int consumed = 32;  // seeds of this chunk that are dealt with
+                    while (m) {
+                        const int room = __shfl_sync(FULL, gs.window - (t - ctl->commit_head), 0);
+                        const int j = __ffs(m) - 1;
+                        if (room <= 0) { consumed = j; full = true; break; }
+                        m &= m - 1;
+                        const unsigned pj = __shfl_sync(FULL, pix, j);
+                        if (lane == 0) {
+                            volatile int4* sl = &s_slot[t % kSlots];
+                            sl->x = (int)pj;
+                            sl->y = 0;
+                            sl->z = 0;
+                            sl->w = slot_pack(kSlotReady, 0, -1);
+                            __threadfence_block();
+                            ctl->ticket_next = t + 1;
+                        }
+                        t++;
+                    }
+                    pos += consumed;
+                }
+                if (lane == 0) {
+                    ctl->next_pos = min(pos, ns);
+                    if (pos >= ns && !full) ctl->all_issued = 1;
+                }
+            }
+            warp_unlock(&ctlp->sel_lock, lane);
+            continue;
+        }
+        // ---------------- take the next ticket and grow it speculatively ----------------
+        if (action == kActTake) {
+            int my_ticket = -1;
+            if (lane == 0) {
+                while (true) {
+                    const int t = ctl->grow_next;
+                    if (ctl->active != kFrameRunning || t >= ctl->ticket_next) break;
+                    if (atomicCAS(&ctlp->grow_next, t, t + 1) == t) { my_ticket = t; break; }
+                }
+            }
+            my_ticket = __shfl_sync(FULL, my_ticket, 0);
+            if (my_ticket < 0) continue;
+            // the frame cannot finish before this ticket is committed: its identity is stable from here on
+            const int f = __shfl_sync(FULL, ctl->frame, 0);
+            volatile int4* sl = &s_slot[my_ticket % kSlots];
+            const int my_pix = sl->x;
+            // already swallowed, or stamped by an uncommitted earlier ticket (most likely being swallowed):
+            // not grown now; the committer decides when its turn comes
+            const unsigned short cl = (unsigned short)*(const volatile unsigned int*)&(B.rec + (size_t)f * plane)[my_pix].claim;
+            const unsigned d = (unsigned)(my_ticket - (int)cl) & 0xffffu;
+            const bool defer = WARP_UNIFORM((((vused[my_pix >> 5] >> (my_pix & 31)) & 1u) != 0) ||
+                                            (d != 0 && d <= (unsigned)(my_ticket - ctl->commit_head)));
+            if (defer) {
+                if (lane == 0) {
+                    atomicAdd(&ctlp->stat[3], 1ull);
+                    __threadfence_block();
+                    sl->w = slot_pack(kSlotDone, kStDeferred, -1);
+                }
+                __syncwarp();
+                continue;
+            }
+            F.ang = B.angdeg + (size_t)f * plane;
+            F.g2 = B.g2 + (size_t)f * plane;
+            F.rec = B.rec + (size_t)f * plane;
+            F.cs0 = B.cs0 + (size_t)f * plane;
+            F.used_bits = s_used;
+            F.commit_head = &ctlp->commit_head;
+            LsdFrame FS2 = F;
+            FS2.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
+            FS2.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
+            FS2.reg_cap = FS2.touched_cap = kSpecCap;
+            FS2.ticket = my_ticket;
+            const long long g0 = clock64();
+            __syncwarp();
+            if (lane == 0) s_view[warp] = FS2;
+            __syncwarp();
+            lsd_grow_seed(s_view[warp], my_pix, g.min_reg_size, &s_res[warp]);
+            res = s_res[warp];
+            // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer
+            const bool tiny = res.status == kStNoRect && res.n <= kTiny && res.nt == res.n;
+            if (tiny) {  // the ring still holds every point of such a region
+                if (lane < res.n) s_tiny[(my_ticket % kSlots) * kTiny + lane] = F.ring[lane];
+                __syncwarp();
+            }
+            const bool small = !tiny && res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
+            const bool keep = res.status >= 0 && !small && !tiny;
+            if (small) {
+                unsigned int* dst = B.small_buf + ((cta_fs + fsi) * kSlots + (size_t)(my_ticket % kSlots)) * 2 * kSmall;
+                #pragma unroll 1
+                for (int i = lane; i < res.n; i += 32) dst[i] = FS2.reg[i];
+                #pragma unroll 1
+                for (int i = lane; i < res.nt; i += 32) dst[kSmall + i] = FS2.touched[i];
+                if (lane == 0 && res.status == kStRect) B.small_rect[(cta_fs + fsi) * kSlots + (my_ticket % kSlots)] = res.rec;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                atomicAdd(&ctlp->stat[4], (unsigned long long)(clock64() - g0));
+                if (res.status < 0) atomicAdd(&ctlp->stat[5], (unsigned long long)(clock64() - g0));
+                if (keep && res.status == kStRect) my_pool_rect[mybuf] = res.rec;
+                sl->y = res.n;
+                sl->z = res.nt;
+                __threadfence_block();
+                sl->w = slot_pack(kSlotDone, res.status, keep ? mybuf : -1);
+            }
+            __syncwarp();
+            if (keep) mybuf = pool_pop(&s_free_mask, lane);
+        }
+    }
+}
+
 // NFA validation of the fitted rectangles (rect_improve): it only reads the angle map and does not influence any
-// other region, so every rectangle of every frame is independent — one warp per rectangle.
+// other region, so every rectangle of every frame is independent — one warp per rectangle.  Rectangles are validated
+// in two places: grower CTAs that have run out of frames take chunks of kNfaChunk rectangles of finished frames from a
+// queue while the last frames are still being grown (the tail of k_lsd_grow would otherwise leave most SMs idle), and
+// k_lsd_nfa afterwards does whatever is left (qvalid == kNfaTodo).
 constexpr int kNfaBlocksPerFrame = 32, kNfaThreads = 256;
 __global__ void __launch_bounds__(kNfaThreads, 4) k_lsd_nfa(LineGeom g, const float* __restrict__ angdeg, size_t plane,
                                                          const LsdQueueItem* __restrict__ queue, const int* __restrict__ n_rects,
@@ -616,7 +1659,7 @@ __global__ void __launch_bounds__(kNfaThreads, 4) k_lsd_nfa(LineGeom g, const fl
     const int wid = blockIdx.x * (kNfaThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kNfaThreads / 32);
     const int n = min(n_rects[f], g.seg_cap);
     for (int t = wid; t < n; t += nw)
-        lsd_nfa_one(g, angdeg + (size_t)f * plane, queue, qres, qvalid, T, f, t);
+        if (qvalid[(size_t)f * g.seg_cap + t] == kNfaTodo) lsd_nfa_one(g, angdeg + (size_t)f * plane, queue, qres, qvalid, T, f, t);
 }
 
 }  // namespace pl
@@ -992,30 +2035,26 @@ struct pl_line {
     float2* d_cs0 = nullptr;
     int* d_nrects = nullptr;
     int* d_g2 = nullptr;
-    unsigned int* d_seeds = nullptr;
+    unsigned int *d_reg = nullptr, *d_seeds = nullptr;
     int *d_maxg2 = nullptr, *d_tile_off = nullptr, *d_nseeds = nullptr, *d_nsegs = nullptr, *d_flags = nullptr, *d_nout = nullptr;
     unsigned short* d_tile_hist = nullptr;
     LsdSeg* d_segs = nullptr;
     LsdSeg* d_qres = nullptr;
     LsdQueueItem* d_queue = nullptr;
     uint8_t* d_qvalid = nullptr;
-    unsigned int *d_spec_reg = nullptr, *d_big_touched = nullptr, *d_dbg_bits = nullptr, *d_gfinal = nullptr;
-    TicketRec* d_trec = nullptr;
-    int* d_dbg_out = nullptr;
-    int4* d_dbg_log = nullptr;
-    unsigned int* d_dbg_scratch = nullptr;
-    int* d_dbg_log_n = nullptr;
-    int grow_debug = 0;
-    LsdRect* d_pool_rect = nullptr;
+    unsigned int *d_spec_reg = nullptr, *d_spec_touched = nullptr, *d_big_touched = nullptr;
+    LsdRect *d_pool_rect = nullptr, *d_small_rect = nullptr;
+    unsigned int* d_small_buf = nullptr;
     int* d_frame_counter = nullptr;
+    int* d_nfa_ctl = nullptr;
+    unsigned int* d_nfa_items = nullptr;
     int* d_sticky = nullptr;  // capacity flags of the device-pointer API since the last pl_line_sync
-    int bits_words = 0, num_sms = 0;
-    // two shapes of the grower: up to one frame per SM (one big CTA per SM: latency of a frame) and more frames than SMs
-    // (two smaller CTAs per SM, each with its own frame: the serial parts of one frame overlap the other's growth)
-    GrowLayout lay_few, lay_many;
-    int threads_few = 0, threads_many = 0, ctas_per_sm_many = 1;
-    long long watchdog_cycles = 0;
+    int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
+    int tail_nfa = 1;
+    GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
+    int poll_ns = 400;
     int reserved_sms = 0;          // SMs the region grower leaves to the kernels of other streams (pl_line_set_reserved_sms)
+    unsigned int* d_big_bits = nullptr;
     float *d_resp = nullptr, *d_rowsum = nullptr, *d_fdesc = nullptr;
     short *d_dx = nullptr, *d_dy = nullptr;
     ExactTab *d_xtab = nullptr, *d_ytab = nullptr;
@@ -1130,8 +2169,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     {
         const double rho = 2.0 / sin(kPiD * 22.5 / 180);
         dim3 grid((G.W + 63) / 64, (G.H + 3) / 4, nf);
-        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, reinterpret_cast<float4*>(h->d_rec), h->d_cs0, plane,
-                                         rho, h->d_maxg2);
+        k_lsd_grad<<<grid, 256, 0, st>>>(G, h->d_scaled, h->scaled_stride, h->d_ang, h->d_g2, reinterpret_cast<float4*>(h->d_rec), h->d_cs0, plane, rho, h->d_maxg2);
         launches++;
     }
     if (prof) cudaEventRecord(h->ev[1], st);
@@ -1141,25 +2179,27 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
     {
-        // Persistent CTAs take frames from a counter.  Up to one frame per SM: one 512-thread CTA per SM; more frames than
-        // SMs: two 256-thread CTAs per SM when the shared memory allows it.  The grower's CTAs own their SMs for milliseconds:
-        // a kernel of another stream only runs where no grower CTA sits, so reserved_sms keeps that many SMs free while there
-        // are more frames than SMs.
+        // one CTA per SM; a CTA works on several frames at once when there are more frames than SMs
+        // The grower's CTAs are persistent and own their SM (all registers, almost all shared memory): a kernel of another stream
+        // only runs where no grower CTA sits.  reserved_sms keeps that many SMs free while there are more frames than SMs.
         const int sms = std::max(1, h->num_sms - (nf > h->num_sms - h->reserved_sms ? h->reserved_sms : 0));
-        const bool many = nf > sms && h->threads_many > 0;
-        const GrowLayout& lay = many ? h->lay_many : h->lay_few;
-        const int ctas = std::min(nf, sms * (many ? h->ctas_per_sm_many : 1));
+        const bool many = nf > sms && h->cfg_many.growers > 0;
+        const GrowConfig& cf = many ? h->cfg_many : h->cfg_few;
+        GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words, h->tail_nfa, h->poll_ns};
+        const int ctas = std::min(nf, sms);
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         GrowBufs gb;
         gb.angdeg = h->d_ang; gb.g2 = h->d_g2; gb.rec = h->d_rec; gb.cs0 = h->d_cs0; gb.seeds = h->d_seeds; gb.n_seeds = h->d_nseeds;
-        gb.big_reg = h->d_big_touched; gb.pool_reg = h->d_spec_reg; gb.pool_rect = h->d_pool_rect;
-        gb.trec = h->d_trec; gb.gfinal = h->d_gfinal;
-        gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
+        gb.big_reg = h->d_reg; gb.big_touched = h->d_big_touched; gb.big_bits = h->d_big_bits;
+        gb.pool_reg = h->d_spec_reg; gb.pool_touched = h->d_spec_touched; gb.pool_rect = h->d_pool_rect;
+        gb.small_buf = h->d_small_buf; gb.small_rect = h->d_small_rect; gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
         gb.flags = h->d_flags; gb.phase_cycles = prof ? h->d_phase : nullptr; gb.frame_counter = h->d_frame_counter; gb.plane = plane;
-        gb.watchdog_cycles = h->watchdog_cycles;
-        gb.dbg_bits = h->d_dbg_bits; gb.dbg_out = h->d_dbg_out; gb.dbg_log = h->d_dbg_log; gb.dbg_log_n = h->d_dbg_log_n; gb.dbg_scratch = h->d_dbg_scratch;
-        if (many) k_lsd_grow<256, 2><<<ctas, 256, lay.total(), st>>>(G, lay, nf, gb);
-        else k_lsd_grow<512, 1><<<ctas, 512, lay.total(), st>>>(G, lay, nf, gb);
+        gb.qres = h->d_qres; gb.qvalid = h->d_qvalid; gb.nfa_items = h->d_nfa_items; gb.nfa_ctl = h->d_nfa_ctl; gb.nfa_tabs = h->nfa_tabs;
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_ctl, 0, 4 * sizeof(int), st));
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
+        if (cf.growers <= 8) k_lsd_grow<256><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
+        else k_lsd_grow<512><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
     }
     k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
     launches += 2;
@@ -1206,7 +2246,7 @@ int line_check_flags(pl_line* h, int nf) {
     PL_CUDA_TRY(pl::stream_sync(h->stream));
     for (int i = 0; i < nf; i++)
         if (h->h_flags[i]) {
-            set_error("frame %d of the chunk exceeded an LSD capacity (flags=%d: 1=segments, 2=region size, 4=watchdog, 8=internal check, code in bits 4..)", i, h->h_flags[i]);
+            set_error("frame %d of the chunk exceeded an LSD capacity (flags=%d: 1=segments, 2=region size)", i, h->h_flags[i]);
             return PL_ERR_CAPACITY;
         }
     return PL_OK;
@@ -1255,6 +2295,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_cs0, B * plane);
     A(&h->d_nrects, B);
     A(&h->d_g2, B * plane);
+    A(&h->d_reg, B * plane);
     A(&h->d_seeds, B * plane);
     A(&h->d_maxg2, B);
     A(&h->d_nseeds, B);
@@ -1273,77 +2314,69 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
         if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
         if (e == cudaSuccess) {
             h->num_sms = prop.multiProcessorCount;
-            // shared memory of a grower CTA: the ticket slots with their point rings and the committed bitmap
-            int want_slots = kMaxSlots, want_window = 0, want_stall = 16, want_restarts = 3;
-            if (const char* ev = getenv("PLSLAM_LSD_SLOTS")) want_slots = std::max(32, std::min(kMaxSlots, atoi(ev)));
-            if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) want_window = std::max(1, atoi(ev));
-            if (const char* ev = getenv("PLSLAM_LSD_STALL")) want_stall = std::max(0, std::min(100000, atoi(ev)));
-            if (const char* ev = getenv("PLSLAM_LSD_RESTARTS")) want_restarts = std::max(0, std::min(8, atoi(ev)));
-            int want_debug = 0;
-            if (const char* ev = getenv("PLSLAM_LSD_DEBUG")) want_debug = atoi(ev);
-            h->grow_debug = want_debug;
-            while (want_slots & (want_slots - 1)) want_slots &= want_slots - 1;  // power of two
-            auto choose = [&](size_t budget, int threads, int slots, GrowLayout* out) -> bool {
-                for (int wN = slots; wN >= 32; wN >>= 1) {
-                    GrowLayout L{wN, want_window > 0 ? std::min(want_window, wN) : wN, h->bits_words, want_stall, want_restarts, 200, want_debug, threads - 63};
-                    if (L.total() <= budget) {
-                        *out = L;
-                        return true;
+            // shared memory: per frame slot the ticket slots + committed bitmap, per grower the ring, the staging area
+            // and the sparse private bitmap (a pool of 32x32-pixel tiles: the more, the fewer regions overflow)
+            const int tiles = ((W + 31) / 32) * ((H + 31) / 32);
+            const size_t budget = prop.sharedMemPerBlockOptin > 8192 ? prop.sharedMemPerBlockOptin - 8192 : 0;  // static: control blocks, views, results
+            auto choose = [&](int fs, int max_g, GrowConfig* c) {
+                *c = GrowConfig{0, 0, fs};
+                for (int gN = max_g; gN >= 1 && c->growers == 0; gN--)
+                    for (int pN = kMaxPoolTiles; pN >= kMinPoolTiles; pN -= 8) {
+                        GrowSmem gs{tiles, pN, 0, fs, h->bits_words, 0, 400};
+                        if (gs.total(gN) <= budget) {
+                            c->growers = gN;
+                            c->pool_tiles = pN;
+                            break;
+                        }
                     }
-                }
-                return false;
             };
-            const size_t static_smem = 2048;  // control block (static shared memory of k_lsd_grow)
-            const size_t optin = prop.sharedMemPerBlockOptin, per_sm = prop.sharedMemPerMultiprocessor;
-            const size_t budget1 = optin > static_smem ? optin - static_smem : 0;
-            if (!choose(budget1, 512, want_slots, &h->lay_few)) {
-                set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region grower, the device offers %zu",
-                          max_cols, max_rows, GrowLayout{32, 32, h->bits_words, 0, 0, 200, 0, 512 - 63}.total(), budget1);
+            int g_few = 8, g_many = kMaxGrowers, fs_many = 3;  // (g_few <= 8: the 256-thread instantiation)
+            if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<few>,<many>,<frame slots>"
+                int a = 0, b2 = 0, c2 = 0;
+                if (sscanf(ev, "%d,%d,%d", &a, &b2, &c2) == 3) {
+                    if (a >= 1 && a <= kMaxGrowers) g_few = a;
+                    if (b2 >= 1 && b2 <= kMaxGrowers) g_many = b2;
+                    if (c2 >= 1 && c2 <= kMaxFrameSlots) fs_many = c2;
+                }
+            }
+            choose(1, g_few, &h->cfg_few);
+            for (int fs = fs_many; fs >= 1 && h->cfg_many.growers < std::min(g_many, 4); fs--) choose(fs, g_many, &h->cfg_many);
+            if (const char* ev = getenv("PLSLAM_LSD_POOL_TILES")) {  // test hook: a tiny pool forces the overflow -> re-growth path
+                const int pt = atoi(ev);
+                if (pt >= 1 && pt <= kMaxPoolTiles) {
+                    h->cfg_few.pool_tiles = std::min(h->cfg_few.pool_tiles, pt);
+                    h->cfg_many.pool_tiles = std::min(h->cfg_many.pool_tiles, pt);
+                }
+            }
+            h->grow_tiles = tiles;
+            if (const char* ev = getenv("PLSLAM_LSD_TAIL_NFA")) h->tail_nfa = atoi(ev) != 0;
+            if (const char* ev = getenv("PLSLAM_LSD_POLL_NS")) h->poll_ns = std::max(20, std::min(100000, atoi(ev)));
+            if (const char* ev = getenv("PLSLAM_LSD_RESERVE_SMS")) h->reserved_sms = std::max(0, std::min(h->num_sms - 1, atoi(ev)));
+            h->grow_window = 128;
+            if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));
+            if (h->cfg_few.growers < 1) {
+                set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region growers, the device offers %zu",
+                          max_cols, max_rows, GrowSmem{tiles, kMinPoolTiles, 0, 1, h->bits_words, 0, 400}.total(1), budget);
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
-            h->threads_few = 512;
-            // two CTAs per SM: each gets half of the SM's shared memory (1 KB per CTA is reserved by the system)
-            const size_t half = per_sm / 2 > 1024 + static_smem ? per_sm / 2 - 1024 - static_smem : 0;
-            GrowLayout two;
-            if (choose(half, 256, want_slots, &two) && two.W >= std::min(512, want_slots)) {
-                h->lay_many = two;
-                h->threads_many = 256;
-                h->ctas_per_sm_many = 2;
-            } else {
-                h->lay_many = h->lay_few;
-                h->threads_many = 0;  // the 512-thread shape for everything
-                h->ctas_per_sm_many = 1;
-            }
-            if (const char* ev = getenv("PLSLAM_LSD_SHAPE")) {  // test hook: "few" forces the one-CTA-per-SM shape for every batch size
-                if (!strcmp(ev, "few")) { h->threads_many = 0; h->ctas_per_sm_many = 1; h->lay_many = h->lay_few; }
-            }
-            if (const char* ev = getenv("PLSLAM_LSD_POLL_NS")) h->lay_few.poll_ns = h->lay_many.poll_ns = std::max(20, std::min(100000, atoi(ev)));
-            if (const char* ev = getenv("PLSLAM_LSD_RESERVE_SMS")) h->reserved_sms = std::max(0, std::min(h->num_sms - 1, atoi(ev)));
-            // watchdog: a frame that takes longer than this many cycles is abandoned with PL_ERR_CAPACITY flag 4 (never seen; it
-            // turns a would-be hang of the persistent kernel into an error)
-            h->watchdog_cycles = 20000000000ll;
-            if (const char* ev = getenv("PLSLAM_LSD_WATCHDOG_MS")) h->watchdog_cycles = (long long)atof(ev) * 1900000ll;
-            e = cudaFuncSetAttribute(k_lsd_grow<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget1);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lsd_grow<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(half, 1024));
+            e = cudaFuncSetAttribute(k_lsd_grow<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lsd_grow<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
         }
     }
-    const size_t max_ctas = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1) * 2);
-    A(&h->d_spec_reg, max_ctas * kPoolBufs * 2 * (size_t)kSpecCap);
-    A(&h->d_pool_rect, max_ctas * kPoolBufs);
-    A(&h->d_big_touched, max_ctas * 2 * plane);
-    A(&h->d_trec, max_ctas * (size_t)kMaxSlots);
-    A(&h->d_gfinal, max_ctas * 2 * (size_t)kMaxSlots);
-    A(&h->d_dbg_bits, max_ctas * (size_t)h->bits_words);
-    if (e == cudaSuccess) e = cudaMemset(h->d_dbg_bits, 0, max_ctas * (size_t)h->bits_words * sizeof(unsigned int));
-    if (h->grow_debug & 512) A(&h->d_dbg_scratch, max_ctas * plane);
-    if (h->grow_debug & 256) {
-        A(&h->d_dbg_log, B * (size_t)kDbgLogCap);
-        A(&h->d_dbg_log_n, B);
-    }
-    A(&h->d_dbg_out, B * 16);
-    if (e == cudaSuccess) e = cudaMemset(h->d_dbg_out, 0, B * 16 * sizeof(int));
+    const size_t max_ctas = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1));
+    const size_t max_fs = max_ctas * kMaxFrameSlots;
+    A(&h->d_spec_reg, max_ctas * kPool * (size_t)kSpecCap);
+    A(&h->d_spec_touched, max_ctas * kPool * (size_t)kSpecCap);
+    A(&h->d_pool_rect, max_ctas * kPool);
+    A(&h->d_small_buf, max_fs * kSlots * 2 * (size_t)kSmall);
+    A(&h->d_small_rect, max_fs * kSlots);
+    A(&h->d_big_touched, max_fs * 2 * plane);
+    A(&h->d_big_bits, max_fs * (size_t)h->bits_words);
+    if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_fs * (size_t)h->bits_words * sizeof(unsigned int));
     A(&h->d_frame_counter, 1);
+    A(&h->d_nfa_ctl, 4);
+    A(&h->d_nfa_items, B * kNfaChunksPerFrame);
     A(&h->d_sticky, 1);
     if (e == cudaSuccess) e = cudaMemset(h->d_sticky, 0, sizeof(int));
     A(&h->d_resp, B * seg_cap);
@@ -1352,7 +2385,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_xtab, (size_t)W);
     A(&h->d_ytab, (size_t)H);
     A(&h->d_lgam, (size_t)kLgMax);
-    A(&h->d_phase, B * 24);
+    A(&h->d_phase, B * 8);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_flags, sizeof(int) * B);
     if (e != cudaSuccess) {
         set_error("pl_line_create: %s", cudaGetErrorString(e));
@@ -1399,9 +2432,9 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) pl::stream_sync(h->stream);
-    void* bufs[] = {h->d_in, h->d_scaled, h->d_blur5, h->d_ang, h->d_g2, h->d_seeds, h->d_maxg2, h->d_tile_off,
+    void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_big_touched, h->d_trec, h->d_gfinal, h->d_dbg_bits, h->d_dbg_out, h->d_dbg_log, h->d_dbg_log_n, h->d_dbg_scratch, h->d_pool_rect, h->d_frame_counter, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -1548,32 +2581,8 @@ PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out7) {
     PL_CHECK_ARG(h && out7 && frame >= 0 && frame < h->last_batch);
     // out7 receives 8 values, see plslam_c.h
     PL_CUDA_TRY(cudaSetDevice(h->device));
-    PL_CUDA_TRY(cudaMemcpyAsync(out7, h->d_phase + (size_t)frame * 24, sizeof(long long) * 24, cudaMemcpyDeviceToHost, h->stream));
+    PL_CUDA_TRY(cudaMemcpyAsync(out7, h->d_phase + (size_t)frame * 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(pl::stream_sync(h->stream));
-    return PL_OK;
-}
-
-/* test hook (PLSLAM_LSD_DEBUG bit 4): 16 ints per frame of the last chunk, see lsd_shadow_check; clears them */
-PL_API int pl_line_debug_read(pl_line* h, int n_frames, int* out16) {
-    PL_CHECK_ARG(h && out16 && n_frames >= 1 && n_frames <= h->max_batch);
-    PL_CUDA_TRY(cudaSetDevice(h->device));
-    PL_CUDA_TRY(pl::stream_sync(h->stream));
-    PL_CUDA_TRY(cudaMemcpy(out16, h->d_dbg_out, sizeof(int) * 16 * n_frames, cudaMemcpyDeviceToHost));
-    PL_CUDA_TRY(cudaMemset(h->d_dbg_out, 0, sizeof(int) * 16 * n_frames));
-    return PL_OK;
-}
-
-/* test hook (PLSLAM_LSD_DEBUG bit 8): the regions frame `frame` of the last chunk committed, in order: rows of {seed pixel,
- * first growth size (-1: grown at the commit head), final size, stamp | flags} */
-PL_API int pl_line_debug_log(pl_line* h, int frame, int* out4, int cap, int* n_out) {
-    PL_CHECK_ARG(h && out4 && n_out && frame >= 0 && frame < h->last_batch && h->d_dbg_log);
-    PL_CUDA_TRY(cudaSetDevice(h->device));
-    PL_CUDA_TRY(pl::stream_sync(h->stream));
-    int n = 0;
-    PL_CUDA_TRY(cudaMemcpy(&n, h->d_dbg_log_n + frame, sizeof(int), cudaMemcpyDeviceToHost));
-    *n_out = n;
-    n = std::min(std::min(n, cap), kDbgLogCap);
-    PL_CUDA_TRY(cudaMemcpy(out4, h->d_dbg_log + (size_t)frame * kDbgLogCap, sizeof(int4) * n, cudaMemcpyDeviceToHost));
     return PL_OK;
 }
 

@@ -59,17 +59,16 @@ names = ["scale+grad", "seed_sort", "grow+nfa", "keylines+sobel", "lbd"]
 for i in range(5):
     print(f"  {names[i]:15s} {out[i]*1000/(a.frames*a.iters):9.2f} us/frame  ({out[i]/a.iters:.3f} ms per pass)")
 print("lines/frame", float(d_n.float().mean().item()), "launches", ex.last_launches())
-ph = np.zeros(24, np.int64)
+ph = np.zeros(8, np.int64)
 N.check(N.lib().pl_line_grow_phases(ex._h, C.c_int(0), N.ptr(ph)))
-nfr = min(a.frames, a.chunk)
-tot = np.zeros(24, np.int64)
-for fi in range(nfr):
-    N.check(N.lib().pl_line_grow_phases(ex._h, C.c_int(fi), N.ptr(ph)))
-    tot += ph
-m = tot / nfr
-print(f"grow kernel (mean of {nfr} frames of the last chunk): frame {m[1]/1e6:.2f} Mcycles; grower threads held tickets for {m[0]/1e6:.1f} Mcycles "
-      f"(sum over threads), of which fitting {m[6]/1e6:.2f}; committer {m[2]/1e6:.2f} (asleep {m[21]/1e6:.2f}); tickets {m[3]:.0f}, committed {m[5]:.0f}, "
-      f"void {m[7]:.0f}, regrown at commit {m[4]:.0f} ({m[8]/1e6:.2f} Mcycles)")
-print("  seed swallowed at take %.0f, seed held by earlier %.0f, too many deps %.0f, CAS lost %.0f, poisoned %.0f, capacity %.0f, stalls %.0f, "
-      "conflict at commit %.0f, dep failed at commit %.0f, deps taken %.0f" % tuple(m[9:19]))
-print(f"  committer: {m[19]:.0f} batch iterations ({m[22]*1024/1e6:.2f} Mcycles), {m[20]:.0f} tickets alone ({m[23]*1024/1e6:.2f} Mcycles)")
+if os.environ.get("PLSLAM_NVCC_EXTRA", "").find("PL_LSD_PROF3") >= 0:
+    print(f"PROF3 region_grow (frame 0, all calls, Mcycles): loads {ph[7]/1e6:.1f} | pass: hypothesis {ph[0]/1e6:.1f} prefix {ph[1]/1e6:.1f} "
+          f"atan2+verdict {ph[2]/1e6:.1f} commit {ph[3]/1e6:.1f}; batches {ph[4]} passes {ph[5]} pixels {ph[6]}")
+elif os.environ.get("PLSLAM_NVCC_EXTRA", "").find("PL_LSD_PROF2") >= 0:
+    print(f"PROF2 (frame 0): total {ph[1]/1e6:.1f} Mcycles x8 warps, rounds {ph[3]}, accepted pixels {ph[4]}, busy: grow {ph[5]/1e6:.1f} "
+          f"rect {ph[6]/1e6:.1f} refine {ph[7]/1e6:.1f} Mcycles (sum over warps)")
+else:
+    busy, regrow, aborted = ph[0] & 0xfffff, (ph[0] >> 20) & 0xfffff, ph[0] >> 40
+    print(f"grow kernel (frame 0): total {ph[1]/1e6:.1f} Mcycles; speculative growth {busy/1e3:.1f} Mcycles over all warps (given up: {aborted/1e3:.1f}), "
+          f"re-growth at commit {regrow/1e3:.1f}; commit sections {ph[2]/1e6:.1f}; tickets {ph[3]}, committed {ph[5]}, "
+          f"void {ph[7]}, deferred {ph[6]}, regrown {ph[4]}")
