@@ -28,6 +28,14 @@ static inline int descriptor_distance(const uint8_t* a, const uint8_t* b) {
 }
 
 extern "C" int orc_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+namespace { void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3); }
+// lab hook: ComputeThreeMaxima on bins of the given sizes (tests/test_oracle_ref.py compares it with the reference's own)
+extern "C" void orc_compute_three_maxima(const int* counts, int L, int* ind) {
+    std::vector<std::vector<int>> histo(L);
+    for (int i = 0; i < L; i++) histo[i].assign(counts[i], 0);
+    ind[0] = ind[1] = ind[2] = -1;
+    three_maxima(histo.data(), L, ind[0], ind[1], ind[2]);
+}
 
 extern "C" void orc_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int* dist) {
     for (int i = 0; i < n; i++) dist[i] = descriptor_distance(a + 32 * (size_t)i, b + 32 * (size_t)i);

@@ -33,6 +33,7 @@ ORC_API int orc_orb_level_candidates(const orc_orb* o, int level, float* xs, flo
 
 /* ---- descriptor search (match_oracle.cpp) ---- */
 ORC_API int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+ORC_API void orc_compute_three_maxima(const int* counts, int L, int* ind);
 ORC_API void orc_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int* dist);
 ORC_API void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist, int threads);
 ORC_API void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* t, const int* off, const int* cidx, int* dist);

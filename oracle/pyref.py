@@ -1,0 +1,117 @@
+"""ctypes binding of oracle/_ref/libplref.so: the REFERENCE'S OWN hot-path code (src/ORBextractor.cc as a whole, DescriptorDistance
+and ComputeThreeMaxima cut out of src/ORBmatcher.cc / src/LineMatcher.cpp, the vendored DBoW2 vocabulary), compiled from the sources
+where they lie under /root/reference against the OpenCV stand-in of oracle/ref_shim/cv_standin.hpp (see oracle/ref_shim/Makefile).
+
+TEST INFRASTRUCTURE: tests/test_oracle_ref.py checks the oracle's restatements against it.  The library can only be BUILT where
+/root/reference exists; it is git-ignored but travels to the GPU box with the snapshot."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import pyoracle
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libplref.so")
+REFERENCE = os.environ.get("PLSLAM_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH) or os.path.isdir(os.path.join(REFERENCE, "src"))
+
+
+def build(force: bool = False) -> str:
+    """Builds libplref.so when the reference sources are present (no-op otherwise: the prebuilt file is used)."""
+    if os.path.isdir(os.path.join(REFERENCE, "src")):
+        pyoracle.build()
+        args = ["make", "-C", os.path.join(_HERE, "ref_shim"), "-s", f"REF={REFERENCE}"]
+        if force:
+            args.append("-B")
+        subprocess.check_call(args)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        pyoracle.lib()  # libplref.so resolves the image-processing primitives in libploracle.so
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ref_voc_load_text.restype = C.c_void_p
+        _lib.ref_voc_load_text.argtypes = [C.c_char_p]
+        _lib.ref_voc_destroy.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, cap=20000, monotone=True):
+    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)(img) -> (keypoints[KP_DTYPE], descriptors (n,32)).
+    monotone: the reference's allocations come from a bump arena (a later node has the higher address), which makes the order
+    DistributeOctTree gives nodes with equally many key points — the address, ORBextractor.cc:684 — the creation order."""
+    img = np.ascontiguousarray(img, np.uint8)
+    kps = np.zeros(cap, pyoracle.KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = C.c_int()
+    rc = lib().ref_orb_extract(_p(img), C.c_int(img.shape[0]), C.c_int(img.shape[1]), C.c_size_t(img.strides[0]), C.c_int(nfeatures),
+                               C.c_float(scale_factor), C.c_int(nlevels), C.c_int(ini_th), C.c_int(min_th), C.c_int(int(monotone)), _p(kps), _p(desc), C.c_int(cap),
+                               C.byref(n))
+    assert rc == 0
+    return kps[:n.value].copy(), desc[:n.value].copy()
+
+
+def distribute_octtree(xs, ys, resp, minX, maxX, minY, maxY, N, monotone=True):
+    xs, ys, resp = (np.ascontiguousarray(a, np.float32) for a in (xs, ys, resp))
+    cap = len(xs) + 8
+    ox, oy, orr = (np.empty(cap, np.float32) for _ in range(3))
+    n = lib().ref_distribute_octtree(_p(xs), _p(ys), _p(resp), C.c_int(len(xs)), C.c_int(minX), C.c_int(maxX), C.c_int(minY), C.c_int(maxY),
+                                     C.c_int(N), C.c_int(int(monotone)), _p(ox), _p(oy), _p(orr), C.c_int(cap))
+    return ox[:n].copy(), oy[:n].copy(), orr[:n].copy()
+
+
+def orb_descriptor_distance(a, b):
+    return lib().ref_orb_descriptor_distance(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))
+
+
+def line_descriptor_distance(a, b):
+    return lib().ref_line_descriptor_distance(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))
+
+
+def compute_three_maxima(counts):
+    counts = np.ascontiguousarray(counts, np.int32)
+    ind = np.zeros(3, np.int32)
+    lib().ref_compute_three_maxima(_p(counts), C.c_int(len(counts)), _p(ind))
+    return tuple(int(v) for v in ind)
+
+
+class Vocabulary:
+    """ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>, loaded with loadFromTextFile."""
+
+    def __init__(self, filename):
+        self._h = lib().ref_voc_load_text(str(filename).encode())
+        if not self._h:
+            raise ValueError("loadFromTextFile failed: " + str(filename))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_voc_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def transform(self, desc, levelsup=4):
+        """Frame::ComputeBoW: ((word ids, word values), {node id: feature indices})."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        wid, wv = np.empty(n + 1, np.uint32), np.empty(n + 1, np.float64)
+        nid, noff, fidx = np.empty(n + 1, np.uint32), np.empty(n + 2, np.int32), np.empty(n + 1, np.uint32)
+        nw, nn = C.c_int(), C.c_int()
+        lib().ref_voc_transform(C.c_void_p(self._h), _p(desc), C.c_int(n), C.c_int(levelsup), C.byref(nw), _p(wid), _p(wv), C.byref(nn), _p(nid),
+                                _p(noff), _p(fidx))
+        fv = {int(nid[i]): fidx[noff[i]:noff[i + 1]].copy() for i in range(nn.value)}
+        return (wid[:nw.value].copy(), wv[:nw.value].copy()), fv
