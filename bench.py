@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="frames of the cpu_baseline sample")
     ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the persistent LSD region grower leaves to the matcher kernels of the other streams")
     ap.add_argument("--device-glue", type=int, default=1, help="e2e leg: Frame glue (UnprojectStereo, IsInFrustum) through the batched F-row calls instead of numpy")
+    ap.add_argument("--c5-frames", type=int, default=4096, help="frames of the config-5 leg (batched offline extraction sharded frame-wise over the ranks); 0 = skip")
+    ap.add_argument("--c5-chunk", type=int, default=512, help="frames per device-resident chunk of the config-5 leg")
+    ap.add_argument("--kitti-frames", type=int, default=24, help="frames of the config-3 leg (1241x376, ORB(2000) + lines, one frame at a time); 0 = skip")
     return ap.parse_args()
 
 
@@ -78,6 +81,12 @@ def ncu_traffic_bytes(kernel):
         except (OSError, ValueError, KeyError, IndexError):
             continue
     return None
+
+
+# the kernel whose ncu capture gives roofline.traffic for a stage of *_stage_ms
+KERNEL_OF_STAGE = {"lsd_grow": "k_lsd_grow", "lsd_scale_grad": "k_lsd_grad", "lsd_seed_sort": "k_lsd_scatter", "keylines_sobel": "k_sobel3",
+                   "lbd": "k_lbd_rows", "orb_pyramid": "k_pyr_resize", "orb_fast": "k_fast_cells", "orb_octree": "k_octree", "orb_blur": "k_blur7",
+                   "orb_orient_brief": "k_orient_brief"}
 
 
 def load_peaks():
@@ -368,6 +377,11 @@ def run_ours(a, rank, world, local_rank, dist):
         lat.append((time.perf_counter() - t1) * 1e3)
     p50 = float(np.median(lat[3:])) if len(lat) > 3 else float(np.median(lat))
 
+    # ---- config 3 (KITTI-size frames, one at a time) and config 5 (batched offline extraction, sharded frame-wise) ----
+    del gb1
+    kitti = run_kitti(a, api, fe, dev) if (a.kitti_frames > 0 and rank == 0) else None
+    c5 = run_config5(a, rank, world, dev, dist, api, pkg) if a.c5_frames > 0 else None
+
     tt = torch.tensor([t_total, t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -410,12 +424,16 @@ def run_ours(a, rank, world, local_rank, dist):
             rl[k] = {"ms_per_pass": round(ms, 4)}
     ach = alg_bytes.get(dom, 0) * F / (stage[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6),
-                "traffic": ncu_traffic_bytes("k_lsd_grow<512>"), "peak_source": peak_src,
+                "traffic": ncu_traffic_bytes(KERNEL_OF_STAGE.get(dom, dom)), "traffic_kernel": KERNEL_OF_STAGE.get(dom, dom), "peak_source": peak_src,
                 "note": "k_lsd_grow is the ordered (sequential-semantics) region grower, run as speculative transactions with in-order commit (DESIGN.md 4.1): latency-bound, not a streaming kernel; the HBM fraction is printed for completeness only",
                 "per_kernel": rl}
 
     # ---- cpu_baseline: the oracle on one host core, bounded sample ----
-    cpu = cpu_sample(a.cpu_sample, gray, depth, Tcw, threads=1)
+    cpu, cpu_summary = cpu_sample(a.cpu_sample, gray, depth, Tcw, threads=1)
+    # parity at the benchmarked workload: the CPU oracle's matches of the sample frames are the GPU's, frame by frame
+    assert cpu_summary == summary[:len(cpu_summary)], "the CPU oracle and the CUDA path disagree on the sample frames of the timed workload"
+    cpu["parity"] = f"match summary of the {len(cpu_summary)} sample frames identical to the CUDA path's"
+    cpu.update(cpu_latency(gray, threads=2))
     frames_total = F * a.steps * world
     value = frames_total / t_total
     out = {
@@ -434,12 +452,140 @@ def run_ours(a, rank, world, local_rank, dist):
                 "note": "host images uploaded once, both extractors through the device-pointer C ABI on their own streams, results read back to pinned host memory; caller glue (Frame-lite: numpy + the batched F-row calls of the library) and the point searches run on the SMs the line extractor's region grower leaves free while it is still working; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
         "gpu_launches": int(launches_per_step * a.steps),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+        "config3_kitti": kitti, "config5_sharded": c5,
         "matches_per_frame": {"c3": round(float(np.mean([r.get("c3_matches", 0) for r in summary])), 1),
                               "c2": round(float(np.mean([r.get("c2_matches", 0) for r in summary])), 1),
                               "d3": round(float(np.mean([r.get("d3_matches", 0) for r in summary])), 1),
                               "d5": round(float(np.mean([r.get("d5_matches", 0) for r in summary])), 1)},
     }
     return out
+
+
+def run_kitti(a, api, fe, dev):
+    """BASELINE.json config 3: 1241x376 frames, ORBextractor(2000) + LineExtractor, one frame at a time on one GPU (images resident in
+    HBM), with the CPU oracle's two-thread single-frame latency beside it."""
+    import torch
+    pkg = importlib.import_module(PKG)
+    KW, KH, KF = 1241, 376, 2000
+    n = a.kitti_frames
+    fr = pkg.synth.frames_range(3000, 0, n, KW, KH, workers=min(16, os.cpu_count() or 1))
+    gbk = fe.GpuBackend(api, KH, KW, KF, chunk=1, device=dev)
+    cap = gbk.orb.max_keypoints()
+    d_fr = torch.from_numpy(fr).cuda()
+    d_kps = torch.empty((1, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.empty((1, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.empty(1, dtype=torch.int32, device="cuda")
+    d_kls = torch.empty((1, MAXL, 17), dtype=torch.float32, device="cuda")
+    d_ldesc = torch.empty((1, MAXL, 32), dtype=torch.uint8, device="cuda")
+    d_lco = torch.empty((1, MAXL, 3), dtype=torch.float64, device="cuda")
+    d_ln = torch.empty(1, dtype=torch.int32, device="cuda")
+    lat = []
+    for t in range(n):
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        gbk.orb.extract_batch_dev(d_fr[t].data_ptr(), 1, KH, KW, KW, KW * KH, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+        gbk.line.extract_batch_dev(d_fr[t].data_ptr(), 1, KH, KW, KW, KW * KH, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
+        gbk.orb.sync()
+        gbk.line.sync()
+        lat.append((time.perf_counter() - t1) * 1e3)
+    lat = lat[2:] if len(lat) > 4 else lat
+    cpu = cpu_latency(fr, threads=2, n=4, nfeat=KF)
+    return {"workload": f"{n} frames 1241x376: ORB(2000,1.2,8,20,7) + LSD/LBD(80), one frame at a time, images resident in HBM",
+            "p50_ms_per_frame": round(float(np.percentile(lat, 50)), 3), "p95_ms_per_frame": round(float(np.percentile(lat, 95)), 3),
+            "cpu_baseline": dict(cpu, cores=2, kind="port")}
+
+
+def run_config5(a, rank, world, dev, dist, api, pkg):
+    """BASELINE.json config 5: batched offline extraction of --c5-frames synthetic frames frame(seed = 6000 + i), sharded frame-wise:
+    rank r takes the contiguous range [r F / G, (r + 1) F / G) (frames are independent units, ORBextractor.cc:1053-1073), the shard is
+    extracted in device-resident chunks, and the only cross-rank step is the final gather of the RESULTS (key points, ORB descriptors,
+    key lines, LBD descriptors, line coefficients) to rank 0.  Strong scaling: the total work is fixed."""
+    import torch
+    sh = importlib.import_module(PKG + ".sharding")
+    Ft = a.c5_frames
+    b, e = sh.shard_range(Ft, world, rank)
+    Fr = e - b
+    workers = max(1, min(32, (os.cpu_count() or 1) // max(1, min(world, 8))))
+    t0 = time.time()
+    fr = pkg.synth.frames_range(6000, b, e, W, H, workers=workers)
+    t_gen = time.time() - t0
+    chunk = max(1, min(a.c5_chunk, Fr))
+    orb = api.ORBextractor(NFEAT, 1.2, 8, 20, 7, device=dev, max_cols=W, max_rows=H, max_batch=chunk)
+    line = api.LineExtractor(device=dev, max_cols=W, max_rows=H, max_batch=chunk)
+    cap = orb.max_keypoints()
+    d_fr = torch.from_numpy(fr).cuda()
+    d_kps = torch.empty((Fr, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.empty((Fr, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.empty(Fr, dtype=torch.int32, device="cuda")
+    d_kls = torch.empty((Fr, MAXL, 17), dtype=torch.float32, device="cuda")
+    d_ldesc = torch.empty((Fr, MAXL, 32), dtype=torch.uint8, device="cuda")
+    d_lco = torch.empty((Fr, MAXL, 3), dtype=torch.float64, device="cuda")
+    d_ln = torch.empty(Fr, dtype=torch.int32, device="cuda")
+    s_orb, s_line = torch.cuda.ExternalStream(orb.stream()), torch.cuda.ExternalStream(line.stream())
+    ev = torch.cuda.Event()
+
+    def one_pass():
+        if Fr == 0:
+            return
+        orb.extract_batch_dev(d_fr.data_ptr(), Fr, H, W, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+        ev.record(s_orb)
+        s_line.wait_event(ev)
+        line.extract_batch_dev(d_fr.data_ptr(), Fr, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
+        orb.sync()
+        line.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    one_pass()
+    reps = 2
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    torch.cuda.synchronize()
+    t_ext = (time.perf_counter() - t1) / reps
+    barrier()
+    # ---- the final gather: counts first, then one buffer per rank ----
+    t1 = time.perf_counter()
+    parts = sh.pack_features(d_kps, d_desc, d_n, d_kls, d_ldesc, d_lco, d_ln)
+    got, nbytes = sh.gather_features(parts, world, rank, dist)
+    torch.cuda.synchronize()
+    t_gather = time.perf_counter() - t1
+    barrier()
+    tt = torch.tensor([t_ext, t_gather], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    chk = sh.features_checksum(got)
+    # a few frames of the gathered result against the CPU oracle (key points, descriptors, key lines, LBD bits)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    n_all, ln_all = got[0].cpu().numpy(), got[1].cpu().numpy()
+    kp_off, kl_off = np.concatenate([[0], np.cumsum(n_all)]), np.concatenate([[0], np.cumsum(ln_all)])
+    o = pyoracle.OrbOracle(NFEAT)
+    checked = []
+    for i in sorted({0, Ft // 2, Ft - 1}):
+        img = pkg.synth.frames_range(6000, i, i + 1, W, H)[0]
+        ok, od = o.extract(img)
+        okl, old_, _ = pyoracle.line_extract(img, MAXL)
+        gk = got[2][kp_off[i]:kp_off[i + 1]].cpu().numpy()
+        gd = got[3][kp_off[i]:kp_off[i + 1]].cpu().numpy()
+        gld = got[5][kl_off[i]:kl_off[i + 1]].cpu().numpy()
+        assert len(gk) == len(ok) and np.array_equal(gk[:, 0], ok["x"]) and np.array_equal(gk[:, 1], ok["y"]) and np.array_equal(gd, od), f"config 5: frame {i} differs from the oracle"
+        assert len(gld) == len(old_) and np.array_equal(gld, old_), f"config 5: key lines of frame {i} differ from the oracle"
+        checked.append(int(i))
+    t_ext, t_gather = float(tt[0]), float(tt[1])
+    return {"workload": f"{Ft} frames frame(seed=6000+i) 640x480, ORB(1000) + LSD/LBD(80), contiguous frame ranges per rank, device-resident chunks of {chunk}",
+            "n_gpus": world, "scaling": "strong", "frames_per_s": round(Ft / t_ext, 1), "extract_ms": round(t_ext * 1e3, 2),
+            "gather_ms": round(t_gather * 1e3, 2), "gathered_bytes": int(nbytes), "frames_per_s_with_gather": round(Ft / (t_ext + t_gather), 1),
+            "checksum": int(chk), "key_points": int(n_all.sum()), "key_lines": int(ln_all.sum()), "oracle_checked_frames": checked,
+            "frame_render_s": round(t_gen, 1),
+            "note": "times are the max over ranks; the checksum covers every gathered byte in frame order and does not depend on the sharding, so runs at different N must print the same value"}
 
 
 # -------------------------------------------------------------------------------------------------------------------
@@ -475,9 +621,31 @@ def cpu_pass(gray, depth, Tcw, threads):
 
 def cpu_sample(nframes, gray, depth, Tcw, threads):
     n = min(nframes, len(gray))
-    dt, _ = cpu_pass(gray[:n], depth[:n], Tcw, threads)
+    dt, summary = cpu_pass(gray[:n], depth[:n], Tcw, threads)
     return {"value": round(n / dt, 3), "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"first {n} frames of the sequence: oracle ORB + LSD/LBD extraction and the same C3/D3/C2/D5 schedule, {threads} thread(s)"}
+            "sample": f"first {n} frames of the sequence: oracle ORB + LSD/LBD extraction and the same C3/D3/C2/D5 schedule, {threads} thread(s)"}, summary
+
+
+def cpu_latency(frames, threads=2, n=6, nfeat=NFEAT):
+    """Single-frame latency of the CPU path the way the reference runs it: ORB and line extraction of ONE frame on two threads
+    (Frame.cc:152-155); median over a few frames."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    o = pyoracle.OrbOracle(nfeat)
+    lat = []
+    for i in range(min(n, len(frames))):
+        t1 = time.perf_counter()
+        if threads >= 2:
+            th = threading.Thread(target=pyoracle.line_extract, args=(frames[i], 80))
+            th.start()
+            o.extract(frames[i])
+            th.join()
+        else:
+            o.extract(frames[i])
+            pyoracle.line_extract(frames[i], 80)
+        lat.append((time.perf_counter() - t1) * 1e3)
+    return {"p50_ms_per_frame": round(float(np.median(lat)), 2),
+            "p50_note": f"one frame at a time, ORB || LSD+LBD on {threads} host threads as the reference's Frame constructor (extraction only), median of {len(lat)} frames"}
 
 
 def run_reference(a, rank, world):
@@ -485,7 +653,7 @@ def run_reference(a, rank, world):
         return None
     pkg = importlib.import_module(PKG)
     threads = os.cpu_count() or 1
-    n = min(a.frames, max(2 * threads, 16), 96)
+    n = a.frames   # the whole sequence: the local map (and with it the matching work) grows along it
     gray, depth, Tcw = pkg.synth.room_sequence(a.frames, W, H, workers=min(32, threads))
     gray, depth = gray[:n], depth[:n]
     for _ in range(min(a.warmup, 1)):
@@ -496,7 +664,7 @@ def run_reference(a, rank, world):
         t += dt
     v = n * a.steps / t
     cpu = {"value": round(v, 3), "unit": "frames/s", "cores": threads, "kind": "port",
-           "sample": f"first {n} frames of the {a.frames}-frame sequence per step; frame-parallel extraction on {threads} threads, sequential matching"}
+           "sample": f"all {n} frames of the sequence per step; frame-parallel extraction on {threads} threads, sequential matching"}
     return {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "frames/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(t / a.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",

@@ -52,3 +52,56 @@ def gather_results(local_counts, local_checksums, n_frames: int, world: int, ran
     counts = np.concatenate([out[r][:sizes[r], 0].cpu().numpy() for r in range(world)])
     sums = np.concatenate([out[r][:sizes[r], 1].cpu().numpy() for r in range(world)])
     return counts, sums
+
+
+def pack_features(kps, desc, n, kls, ldesc, lco, ln):
+    """Compacts the padded per-frame outputs of a shard (torch tensors: kps (F, cap, 7) f32, desc (F, cap, 32) u8, n (F) i32, kls
+    (F, L, 17) f32, ldesc (F, L, 32) u8, lco (F, L, 3) f64, ln (F) i32) into what travels in the final gather: the two count vectors
+    and the five row lists without padding.  Works on any device."""
+    import torch
+    cap, L = kps.shape[1], kls.shape[1]
+    pm = torch.arange(cap, device=kps.device)[None, :] < n[:, None].to(torch.int64)
+    lm = torch.arange(L, device=kls.device)[None, :] < ln[:, None].to(torch.int64)
+    return [n.to(torch.int32).contiguous(), ln.to(torch.int32).contiguous(), kps[pm].contiguous(), desc[pm].contiguous(), kls[lm].contiguous(),
+            ldesc[lm].contiguous(), lco[lm].contiguous()]
+
+
+def gather_features(parts, world: int, rank: int, dist, device=None):
+    """The final gather of a frame-wise sharded extraction: every rank's packed features (pack_features) go to rank 0,
+    which returns them concatenated in rank order == frame order (shards are contiguous frame ranges), and None elsewhere.
+    Variable-length: the byte counts are gathered first, then every rank sends ONE buffer (NCCL send / recv on GPUs, gloo on CPU)."""
+    import torch
+    flat = torch.cat([t.reshape(-1).view(torch.uint8) for t in parts])
+    sizes = torch.tensor([t.numel() * t.element_size() for t in parts], dtype=torch.int64, device=flat.device)
+    if world == 1:
+        return parts, int(flat.numel())
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)] if rank == 0 else None
+    dist.gather(sizes, all_sizes, dst=0)
+    if rank != 0:
+        dist.send(flat, dst=0)
+        return None, int(flat.numel())
+    bufs = [flat]
+    for r in range(1, world):
+        b = torch.empty(int(all_sizes[r].sum()), dtype=torch.uint8, device=flat.device)
+        dist.recv(b, src=r)
+        bufs.append(b)
+    out = []
+    for k, proto in enumerate(parts):
+        pieces = []
+        for r in range(world):
+            off = int(all_sizes[r][:k].sum())
+            pieces.append(bufs[r][off:off + int(all_sizes[r][k])].view(proto.dtype))
+        cat = torch.cat(pieces)
+        out.append(cat.reshape((-1,) + tuple(proto.shape[1:])) if proto.dim() > 1 else cat)
+    return out, int(sum(int(x.sum()) for x in all_sizes))
+
+
+def features_checksum(parts) -> int:
+    """Order-sensitive checksum of gathered features that does not depend on how the frames were sharded."""
+    import torch
+    h = 0
+    for k, t in enumerate(parts):
+        b = t.reshape(-1).view(torch.uint8).to(torch.int64)
+        w = (torch.arange(b.numel(), device=b.device, dtype=torch.int64) % 65521) + 1
+        h = (h * 1000003 + int((b * w).sum().item()) + 7919 * k + int(b.numel())) % ((1 << 61) - 1)
+    return h

@@ -111,6 +111,37 @@ def _rot(rx, ry, rz):
     return Rz @ Ry @ Rx
 
 
+def _frames_block_job(args):
+    seed0, blk, lo, hi, width, height = args
+    base = frame(seed0 + blk * 8, width, height)
+    out = []
+    for i in range(max(lo, blk * 8), min(hi, blk * 8 + 8)):
+        if i % 8 == 0:
+            out.append(base)
+        else:
+            rng = np.random.Generator(np.random.PCG64(seed0 + i))
+            sx, sy = int(rng.integers(-24, 25)), int(rng.integers(-24, 25))
+            v = np.roll(base, (sy, sx), axis=(0, 1)).astype(np.int16)
+            v += rng.integers(-3, 4, size=v.shape, dtype=np.int16)
+            out.append(np.clip(v, 0, 255).astype(np.uint8))
+    return np.stack(out)
+
+
+def frames_range(seed0: int, begin: int, end: int, width: int = 640, height: int = 480, workers: int = 1) -> np.ndarray:
+    """frames(seed0, N, ...)[begin:end] for any N >= end, without rendering the rest: frame i only depends on seed0 and i (its block of
+    eight), which is what lets every rank of a sharded run render its own contiguous range.  `workers` processes render the blocks."""
+    if end <= begin:
+        return np.empty((0, height, width), np.uint8)
+    jobs = [(seed0, blk, begin, end, width, height) for blk in range(begin // 8, (end + 7) // 8)]
+    if workers <= 1 or len(jobs) < 4:
+        res = [_frames_block_job(j) for j in jobs]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            res = pool.map(_frames_block_job, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+    return np.concatenate(res)
+
+
 def room_trajectory(n: int, seed: int = 2003) -> np.ndarray:
     """n world->camera poses Tcw (n,4,4) float64: smooth motion, <= 2 cm and <= 0.5 deg per frame."""
     rng = np.random.Generator(np.random.PCG64(seed))
