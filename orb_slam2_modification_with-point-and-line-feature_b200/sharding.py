@@ -71,29 +71,42 @@ def gather_features(parts, world: int, rank: int, dist, device=None):
     which returns them concatenated in rank order == frame order (shards are contiguous frame ranges), and None elsewhere.
     Variable-length: the byte counts are gathered first, then every rank sends ONE buffer (NCCL send / recv on GPUs, gloo on CPU)."""
     import torch
-    flat = torch.cat([t.reshape(-1).view(torch.uint8) for t in parts])
-    sizes = torch.tensor([t.numel() * t.element_size() for t in parts], dtype=torch.int64, device=flat.device)
+
+    def pad16(nbytes: int) -> int:
+        return (nbytes + 15) & ~15
+
+    # every part starts at a multiple of 16 bytes inside the buffer, so the receiver can view it with the part's own dtype
+    raw = [t.reshape(-1).view(torch.uint8) for t in parts]
+    chunks = []
+    for b in raw:
+        chunks.append(b)
+        extra = pad16(b.numel()) - b.numel()
+        if extra:
+            chunks.append(torch.zeros(extra, dtype=torch.uint8, device=b.device))
+    flat = torch.cat(chunks) if chunks else torch.zeros(0, dtype=torch.uint8, device=device)
+    sizes = torch.tensor([b.numel() for b in raw], dtype=torch.int64, device=flat.device)
     if world == 1:
-        return parts, int(flat.numel())
+        return parts, int(sizes.sum())
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)] if rank == 0 else None
     dist.gather(sizes, all_sizes, dst=0)
     if rank != 0:
         dist.send(flat, dst=0)
-        return None, int(flat.numel())
+        return None, int(sizes.sum())
+    all_sizes = [[int(v) for v in a.cpu().tolist()] for a in all_sizes]
     bufs = [flat]
     for r in range(1, world):
-        b = torch.empty(int(all_sizes[r].sum()), dtype=torch.uint8, device=flat.device)
+        b = torch.empty(sum(pad16(v) for v in all_sizes[r]), dtype=torch.uint8, device=flat.device)
         dist.recv(b, src=r)
         bufs.append(b)
     out = []
     for k, proto in enumerate(parts):
         pieces = []
         for r in range(world):
-            off = int(all_sizes[r][:k].sum())
-            pieces.append(bufs[r][off:off + int(all_sizes[r][k])].view(proto.dtype))
+            off = sum(pad16(v) for v in all_sizes[r][:k])
+            pieces.append(bufs[r][off:off + all_sizes[r][k]].view(proto.dtype))
         cat = torch.cat(pieces)
         out.append(cat.reshape((-1,) + tuple(proto.shape[1:])) if proto.dim() > 1 else cat)
-    return out, int(sum(int(x.sum()) for x in all_sizes))
+    return out, int(sum(sum(a) for a in all_sizes))
 
 
 def features_checksum(parts) -> int:

@@ -100,7 +100,8 @@ def _synthetic_outputs(n_frames, cap=40, L=9):
     return kps, desc, n, kls, ldesc, lco, ln
 
 
-def test_feature_gather_equals_the_unsharded_result(world=2):
+@pytest.mark.parametrize("world", [2, 3])
+def test_feature_gather_equals_the_unsharded_result(world):
     import torch.multiprocessing as mp
     sh = importlib.import_module(PKG + ".sharding")
     n = 7  # ragged shards
