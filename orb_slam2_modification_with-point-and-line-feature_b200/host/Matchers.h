@@ -12,7 +12,13 @@
 
 #include "plslam_cvlite.h"
 
-namespace ORB_SLAM2 {
+// The shims with the reference's own signatures (host/shim/ORBmatcher.h, LineMatcher.h) are the classes called
+// ORB_SLAM2::ORBmatcher / LineMatcher there; they include this header with PLSLAM_VIEW_NS set to another namespace.
+#ifndef PLSLAM_VIEW_NS
+#define PLSLAM_VIEW_NS ORB_SLAM2
+#endif
+
+namespace PLSLAM_VIEW_NS {
 
 class ORBmatcher {
 public:
@@ -232,4 +238,4 @@ protected:
     pl_match* h_ = nullptr;
 };
 
-}  // namespace ORB_SLAM2
+}  // namespace PLSLAM_VIEW_NS

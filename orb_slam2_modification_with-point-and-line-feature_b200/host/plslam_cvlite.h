@@ -25,34 +25,54 @@ struct KeyPoint {  // same field order and size as cv::KeyPoint
     int octave = 0, class_id = -1;
 };
 static_assert(sizeof(KeyPoint) == sizeof(pl_keypoint), "cv::KeyPoint layout");
-enum { CV_8U = 0, CV_8UC1 = 0 };
-class Mat {  // 8-bit single-channel matrix, shared ownership, optional ROI (data offset + step)
+enum { CV_8U = 0, CV_8UC1 = 0, CV_32F = 5, CV_32FC1 = 5, CV_64F = 6, CV_64FC1 = 6 };
+class Mat {  // single-channel matrix (8U, 32F or 64F), shared ownership, optional ROI (data offset + step in bytes)
 public:
     int rows = 0, cols = 0;
     size_t step = 0;
     uint8_t* data = nullptr;
     Mat() {}
-    Mat(int r, int c, int /*type*/) { create(r, c, CV_8UC1); }
-    Mat(int r, int c, int /*type*/, void* ext, size_t st) : rows(r), cols(c), step(st ? st : (size_t)c), data((uint8_t*)ext) {}
-    void create(int r, int c, int /*type*/) {
-        if (r == rows && c == cols && buf_ && step == (size_t)c) return;
-        rows = r; cols = c; step = (size_t)c;
-        buf_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * c > 0 ? (size_t)r * c : 1], std::default_delete<uint8_t[]>());
+    Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(int r, int c, int type, void* ext, size_t st = 0) : rows(r), cols(c), data((uint8_t*)ext), type_(type) { step = st ? st : (size_t)c * elemSize(); }
+    void create(int r, int c, int type) {
+        if (r == rows && c == cols && buf_ && type == type_ && step == (size_t)c * elemSize()) return;
+        rows = r; cols = c; type_ = type; step = (size_t)c * elemSize();
+        const size_t bytes = (size_t)r * step;
+        buf_ = std::shared_ptr<uint8_t>(new uint8_t[bytes > 0 ? bytes : 1](), std::default_delete<uint8_t[]>());
         data = buf_.get();
     }
     void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    int type() const { return CV_8UC1; }
+    int type() const { return type_; }
+    size_t elemSize() const { return type_ == CV_32F ? 4 : (type_ == CV_64F ? 8 : 1); }
     uint8_t* ptr(int r = 0) { return data + (size_t)r * step; }
     const uint8_t* ptr(int r = 0) const { return data + (size_t)r * step; }
+    template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
+    template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
+    template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
+    template <typename T> T& at(int i) { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i)[0]; }
+    template <typename T> const T& at(int i) const { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i)[0]; }
+    Mat row(int r) const {
+        Mat m = *this;
+        m.data = data + (size_t)r * step;
+        m.rows = 1;
+        return m;
+    }
+    Mat clone() const {
+        Mat m(rows, cols, type_);
+        for (int r = 0; r < rows; r++) memcpy(m.ptr(r), ptr(r), (size_t)cols * elemSize());
+        return m;
+    }
     Mat roi(int x, int y, int w, int h) const {
         Mat m = *this;
-        m.data = data + (size_t)y * step + x;
+        m.data = data + (size_t)y * step + (size_t)x * elemSize();
         m.rows = h; m.cols = w;
         return m;
     }
 private:
     std::shared_ptr<uint8_t> buf_;
+    int type_ = CV_8UC1;
 };
 typedef const Mat& InputArray;
 typedef Mat& OutputArray;
@@ -73,8 +93,13 @@ static_assert(sizeof(KeyLine) == sizeof(pl_keyline), "cv::line_descriptor::KeyLi
 namespace Eigen {
 struct Vector3d {
     double v[3] = {0, 0, 0};
+    Vector3d() {}
+    Vector3d(double x, double y, double z) { v[0] = x; v[1] = y; v[2] = z; }
     double& operator()(int i) { return v[i]; }
     double operator()(int i) const { return v[i]; }
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+    const double* data() const { return v; }
 };
 }  // namespace Eigen
 #endif

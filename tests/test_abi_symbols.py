@@ -84,3 +84,33 @@ def test_cpp_host_mirrors_compile_and_link(tmp_path):
     r = subprocess.run(["g++", "-std=c++14", "-Wall", "-I", host, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                         "-L" + os.path.join(ROOT, PKG), "-lplslam", "-Wl,-rpath," + os.path.join(ROOT, PKG)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_matcher_shims_with_reference_signatures_compile_and_link(tmp_path):
+    """host/shim/ORBmatcher.{h,cc} and LineMatcher.{h,cc} — the classes with exactly the reference's method signatures
+    (include/ORBmatcher.h:50-208, include/LineMatcher.h:35-86) — compile against the stand-in Frame / KeyFrame / MapPoint / MapLine
+    and link against the C-ABI library together with the driver the GPU test runs.  A call through every reference signature is
+    type-checked here (nothing is executed: no GPU)."""
+    build = importlib.import_module(PKG + ".build")
+    build.build()
+    shim = os.path.join(ROOT, PKG, "host", "shim")
+    src = tmp_path / "calls.cpp"
+    src.write_text('#include "ORBmatcher.h"\n#include "LineMatcher.h"\nusing namespace ORB_SLAM2;\n'
+                   "int calls(ORBmatcher& m, LineMatcher& l, Frame& F, Frame& G, KeyFrame* k1, KeyFrame* k2, cv::Mat S) {\n"
+                   "  std::vector<MapPoint*> pts, out; std::set<MapPoint*> found; std::vector<MapLine*> lines, lout;\n"
+                   "  std::vector<cv::Point2f> prev; std::vector<int> m12; std::vector<std::pair<size_t, size_t>> pairs;\n"
+                   "  std::vector<LineMatcher::KeyLine> kls; std::vector<std::pair<int, int>> idx; const float s12 = 1.f;\n"
+                   "  int n = m.SearchByProjection(F, pts) + m.SearchByProjection(F, pts, 3.f) + m.SearchByProjection(F, G, 15.f, false);\n"
+                   "  n += m.SearchByProjection(F, k1, found, 10.f, 100) + m.SearchByProjection(k1, S, pts, out, 10);\n"
+                   "  n += m.SearchByBoW(k1, F, out) + m.SearchByBoW(k1, k2, out) + m.SearchForInitialization(F, G, prev, m12, 100);\n"
+                   "  n += m.SearchForTriangulation(k1, k2, S, pairs, false) + m.SearchBySim3(k1, k2, out, s12, S, S, 7.5f);\n"
+                   "  n += m.Fuse(k1, pts) + m.Fuse(k1, S, pts, 4.f, out) + ORBmatcher::DescriptorDistance(S, S);\n"
+                   "  n += l.SearchByProjection(F, G) + l.SearchByProjection(F, G, kls, idx) + l.SearchByProjection(F, k1, lout) + l.SearchByProjection(F, k1);\n"
+                   "  n += l.SearchByProjection(F, k1, kls, idx) + l.SearchByProjection(F, lines) + l.SearchByProjection(F, lines, kls, idx);\n"
+                   "  n += l.SearchForTriangulation(k1, k2, pairs, false) + l.Fuse(k1, lines) + LineMatcher::DescriptorDistance(S, S);\n"
+                   "  return n + ORBmatcher::TH_LOW + ORBmatcher::TH_HIGH + ORBmatcher::HISTO_LENGTH;\n}\n")
+    exe = tmp_path / "shims"
+    r = subprocess.run(["g++", "-std=c++14", "-Wall", "-I", shim, str(src), os.path.join(shim, "ORBmatcher.cc"), os.path.join(shim, "LineMatcher.cc"),
+                        os.path.join(ROOT, "tests", "cpp", "matcher_shim_test.cpp"), "-o", str(exe),
+                        "-L" + os.path.join(ROOT, PKG), "-lplslam", "-Wl,-rpath," + os.path.join(ROOT, PKG)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
