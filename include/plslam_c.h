@@ -177,11 +177,12 @@ PL_API int pl_line_set_reserved_sms(pl_line* h, int n);
 /* Measurement hooks: stages {0 blur+scale+gradient, 1 seed sort, 2 region growing/NFA, 3 KeyLines+blur5+Sobel, 4 LBD} */
 PL_API int pl_line_set_profiling(pl_line* h, int on);
 PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
-/* with profiling on, 8 values of frame `frame` of the last chunk from k_lsd_grow's own clock64 accounting:
- * {0 packed kcycles: speculative growth | re-growth at commit << 20 | given-up growth << 40, 1 cycles the frame was
- *  active, 2 cycles inside commit sections, 3 tickets issued, 4 regions re-grown at commit, 5 regions committed,
- *  6 tickets deferred, 7 tickets void} */
-PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out8);
+/* with profiling on, 16 values of frame `frame` of the last chunk from k_lsd_grow2's own clock64 accounting:
+ * {0 sequencer cycles in commit-time re-growth, 1 cycles the frame was active, 2 sequencer cycles in commits (without the re-growth),
+ *  3 tickets issued, 4 regions re-grown at commit, 5 regions committed, 6 tickets deferred, 7 tickets void, 8 sequencer cycles
+ *  issuing tickets, 9 sequencer cycles idle, 10 / 11 / 12 grower cycles (summed over the grower warps) growing / waiting for a
+ *  ticket / parking results, 13 grower warps, 14 grower cycles in growth that was given up, 15 reserved} */
+PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out16);
 /* Test hooks: the 0.8-scaled 8-bit image LSD works on, its level-line angle map (float degrees, -1024 = undefined,
  * rows x cols of the scaled image) and the float LBD descriptors (n x 72) of frame `frame` of the last call. */
 PL_API int pl_line_scaled_dims(const pl_line* h, int* rows, int* cols);

@@ -411,6 +411,31 @@ __device__ __forceinline__ bool lsd_aligned_deg(float th, float adeg, float prec
     return lsd_aligned_cold(th, adeg, prec);
 }
 
+// ---- shared-memory accessors by 32-bit shared-space address ----
+// The views hold generic pointers; a generic load of shared memory is a long-scoreboard access with 64-bit address arithmetic.
+// The grower's hot loop converts them once and uses ld.shared / st.shared / atom.shared.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f2(unsigned a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void reds_or(unsigned a, unsigned v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // region_grow(): returns the region size; reg_angle (radians) is returned through *out_angle.
 //
 // The 32 lanes hold the 8-neighbourhoods of up to four consecutive region points in the reference's visiting order
@@ -425,54 +450,74 @@ __device__ __forceinline__ bool lsd_aligned_deg(float th, float adeg, float prec
 //      (induction over the lanes); those lanes are committed, the rest goes through another pass.
 // Most batches take one pass, whose serial chain is one fastAtan2.  The global loads of the next batch are issued
 // before the current one is resolved.
-// `nt` counts the entries of the touched log (speculative mode); returns -1 when a capacity is exceeded.
-struct GrowCand {
-    int xx, yy;
-    unsigned o;
-    float adeg, ca, sa;
-    unsigned short claim;
-    bool inb;
-};
-__device__ __forceinline__ bool lsd_claim_hit(const LsdFrame& F, unsigned short claim) {
-    const unsigned d = (unsigned)(F.ticket - (int)claim) & 0xffffu;  // tickets between the stamp and this grower
-    return d != 0 && d <= (unsigned)(F.ticket - *F.commit_head);
+// `nt` counts the entries of the touched log (speculative mode); returns -1 when a capacity is exceeded, -2 when the region
+// runs into a pixel stamped by an earlier uncommitted ticket.
+// This is the instruction stream the grower warps live in: it is written for a small footprint (the kernel was bound by
+// instruction fetch) — no unrolling, shared memory by 32-bit address, one call-free body; kSparse selects the private marks
+// (speculative growers: tile directory in shared memory; commit-time re-growth: full bitmap in global memory).
+__device__ __forceinline__ bool lsd_claim_hit(int ticket, int commit_head, unsigned claim) {
+    const unsigned d = (unsigned)(ticket - (int)claim) & 0xffffu;  // tickets between the stamp and this grower
+    return d != 0 && d <= (unsigned)(ticket - commit_head);
 }
-__device__ __forceinline__ void lsd_issue_cand(const LsdFrame& F, int ri, int n, int ddx, int ddy, GrowCand& c) {
-    const unsigned p = (n - ri <= kRegRing) ? F.ring[ri & (kRegRing - 1)] : F.reg[ri];
-    c.xx = (int)(p & 0xffffu) + ddx;
-    c.yy = (int)(p >> 16) + ddy;
-    c.inb = c.xx >= 0 && c.yy >= 0 && c.xx < F.W && c.yy < F.H;
-    c.o = 0;
-    c.adeg = kNotDefDeg;
-    c.ca = c.sa = 0.f;
-    c.claim = 0xffffu;
-    if (c.inb) {
-        c.o = (unsigned)c.yy * (unsigned)F.W + (unsigned)c.xx;
-        const float4 r = *reinterpret_cast<const float4*>(F.rec + c.o);
-        c.adeg = r.x;
-        c.claim = (unsigned short)__float_as_uint(r.y);
-        c.ca = r.z;
-        c.sa = r.w;
-    }
-}
-__device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy, double prec, double* out_angle, int& nt) {
-    const LsdFrame F = Fin;  // in registers (the caller's copy may live in local memory)
+__device__ __noinline__ float fast_atan2_deg_ool(float y, float x) { return fast_atan2_deg(y, x); }
+
+template <bool kSparse>
+__device__ __noinline__ int lsd_region_grow_t(const LsdFrame& Fin, int sx, int sy, double prec, double* out_angle, int& nt_io) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
-    const unsigned so = (unsigned)sy * (unsigned)F.W + (unsigned)sx;
-    const float seed_deg = F.ang[so];
-    const float2 c0 = F.cs0[so];
+    const unsigned a_used = smem_u32(Fin.used_bits), a_sval = smem_u32(Fin.sval), a_ring = smem_u32(Fin.ring);
+    const unsigned a_head = smem_u32((const void*)Fin.commit_head);
+    const unsigned a_dir = kSparse ? smem_u32(Fin.dir) : 0u, a_pool = kSparse ? smem_u32(Fin.pool) : 0u;
+    LsdPix* const rec = Fin.rec;
+    unsigned int* const reg = Fin.reg;
+    unsigned int* const touched = Fin.touched;
+    unsigned int* const bits = Fin.bits;
+    const int W = Fin.W, H = Fin.H, tw = Fin.tw, ticket = Fin.ticket;
+    const int reg_cap = Fin.reg_cap, touched_cap = Fin.touched_cap;
+    int nt = nt_io;
+    const unsigned so = (unsigned)sy * (unsigned)W + (unsigned)sx;
+    const float seed_deg = Fin.ang[so];
+    const float2 c0 = Fin.cs0[so];
     float sumdx = c0.x, sumdy = c0.y;
     float hint = seed_deg;
     const float precdeg = (float)(prec * (180.0 / kPiD));
-    if (nt >= F.touched_cap) return -1;
-    if (!lsd_priv_alloc(F, lane == 0, sx, sy)) return -1;
+    if (nt >= touched_cap) return -1;
+    // private mark of a pixel: the tile must exist first (sparse)
+    auto tile_alloc = [&](bool want, int x, int y) -> bool {  // warp-collective; false when the pool is exhausted
+        if (!kSparse) return true;
+        const int t = want ? (y >> 5) * tw + (x >> 5) : -1;
+        unsigned need = __ballot_sync(FULL, want && lds_u8(a_dir + (unsigned)max(t, 0)) == 0xffu);
+        if (__builtin_expect(need == 0, 1)) return true;
+        const unsigned a_rev = smem_u32(Fin.rev), a_nt = smem_u32(Fin.ntiles);
+        #pragma unroll 1
+        while (need) {
+            const int tj = __shfl_sync(FULL, t, __ffs(need) - 1);
+            const int k = (int)lds_u32(a_nt);
+            if (k >= Fin.pool_tiles) return false;
+            sts_u32(a_pool + (unsigned)(k * 32 + lane) * 4u, 0u);
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_dir + (unsigned)tj), "r"(k) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_rev + (unsigned)k * 2u), "r"(tj) : "memory");
+                sts_u32(a_nt, (unsigned)(k + 1));
+            }
+            __syncwarp();
+            need &= ~__ballot_sync(FULL, t == tj);
+        }
+        return true;
+    };
+    auto mark = [&](int x, int y, unsigned o) {
+        if (kSparse) reds_or(a_pool + (lds_u8(a_dir + (unsigned)((y >> 5) * tw + (x >> 5))) * 32u + (unsigned)(y & 31)) * 4u, 1u << (x & 31));
+        else atomicOr(&bits[o >> 5], 1u << (o & 31));
+    };
+    if (!tile_alloc(lane == 0, sx, sy)) return -1;
     if (lane == 0) {
-        F.reg[0] = ((unsigned)sy << 16) | (unsigned)sx;
-        F.ring[0] = ((unsigned)sy << 16) | (unsigned)sx;
-        lsd_mark(F, sx, sy, so);
-        F.touched[nt] = ((unsigned)sy << 16) | (unsigned)sx;
-        F.rec[so].claim = (unsigned)F.ticket & 0xffffu;
+        const unsigned pk = ((unsigned)sy << 16) | (unsigned)sx;
+        reg[0] = pk;
+        sts_u32(a_ring, pk);
+        mark(sx, sy, so);
+        touched[nt] = pk;
+        rec[so].claim = (unsigned)ticket & 0xffffu;
     }
     nt++;
     __syncwarp();
@@ -480,57 +525,86 @@ __device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy,
     bool any = false;
     const int b = lane >> 3, k8 = lane & 7, kk = k8 + (k8 >= 4 ? 1 : 0);
     const int ddy = kk / 3 - 1, ddx = kk - (kk / 3) * 3 - 1;
-    GrowCand cur, nxt;
-    nxt.inb = false;
+    // a candidate: packed position, pixel offset, and its record (angle | claim | cosf | sinf); angle kNotDefDeg = not a candidate
+    unsigned c_pk = 0, c_o = 0, n_pk = 0, n_o = 0;
+    float4 c_r = make_float4(kNotDefDeg, 0.f, 0.f, 0.f), n_r = c_r;
+#define PL_LOAD_CAND(ri, pk_, o_, r_)                                                                                          \
+    {                                                                                                                           \
+        const unsigned p_ = (n - (ri) <= kRegRing) ? lds_u32(a_ring + (unsigned)((ri) & (kRegRing - 1)) * 4u) : reg[ri];        \
+        const int xx_ = (int)(p_ & 0xffffu) + ddx, yy_ = (int)(p_ >> 16) + ddy;                                                 \
+        pk_ = ((unsigned)yy_ << 16) | ((unsigned)xx_ & 0xffffu);                                                                \
+        o_ = 0;                                                                                                                 \
+        r_.x = kNotDefDeg;                                                                                                      \
+        if ((unsigned)xx_ < (unsigned)W && (unsigned)yy_ < (unsigned)H) {                                                       \
+            o_ = (unsigned)yy_ * (unsigned)W + (unsigned)xx_;                                                                   \
+            r_ = *reinterpret_cast<const float4*>(rec + o_);                                                                    \
+        }                                                                                                                       \
+    }
+    #pragma unroll 1
     while (i < n) {
         const int nb = min(4, n - i);
-        // the next batch's frontier points that exist already have their loads issued now (phase 1), so that they
-        // overlap the resolution of this batch; phase 0 loads what this batch did not get that way
+        // the frontier points of this batch that were not loaded ahead, then those of the next batch that exist already (their loads
+        // overlap the resolution of this one)
+        if (b < have) { c_pk = n_pk; c_o = n_o; c_r = n_r; }
+        if (have < nb) {
+            if (b >= have && b < nb) PL_LOAD_CAND(i + b, c_pk, c_o, c_r)
+        }
+        if (b >= nb) c_r.x = kNotDefDeg;
         const int have_next = max(0, min(4, n - (i + 4)));
-#pragma unroll 1
-        for (int phase = 0; phase < 2; phase++) {
-            GrowCand tmp;
-            tmp.inb = false;
-            const bool act = phase == 0 ? (b >= have && b < nb) : (b < have_next);
-            if (act) lsd_issue_cand(F, i + 4 * phase + b, n, ddx, ddy, tmp);
-            if (phase == 0) {
-                if (b < have) cur = nxt;
-                else cur = tmp;
-            } else {
-                nxt = tmp;
+        if (have_next > 0) {
+            if (b < have_next) PL_LOAD_CAND(i + 4 + b, n_pk, n_o, n_r)
+        }
+        const int cx = (int)(c_pk & 0xffffu), cy = (int)(c_pk >> 16);
+        bool cand = false;
+        if (c_r.x != kNotDefDeg) {
+            cand = ((lds_u32(a_used + (c_o >> 5) * 4u) >> (c_o & 31)) & 1u) == 0;
+            if (cand) {
+                if (kSparse) {
+                    const unsigned d = lds_u8(a_dir + (unsigned)((cy >> 5) * tw + (cx >> 5)));
+                    if (d != 0xffu) cand = ((lds_u32(a_pool + (d * 32u + (unsigned)(cy & 31)) * 4u) >> (cx & 31)) & 1u) == 0;
+                } else {
+                    cand = ((bits[c_o >> 5] >> (c_o & 31)) & 1u) == 0;
+                }
             }
         }
-        bool cand = false;
-        if (cur.inb) cand = cur.adeg != kNotDefDeg && !lsd_committed(F, cur.o) && !lsd_priv_test(F, cur.xx, cur.yy, cur.o);
         unsigned rem = __ballot_sync(FULL, cand);
         if (rem) {
-            const unsigned grp = __match_any_sync(FULL, cand ? cur.o : (0x80000000u | (unsigned)lane));  // lanes on the same pixel
+            // lanes on the same pixel (two frontier points share a neighbour)
+            const unsigned grp = nb > 1 ? __match_any_sync(FULL, cand ? c_o : (0x80000000u | (unsigned)lane)) : (1u << lane);
+            const unsigned claim = __float_as_uint(c_r.y) & 0xffffu;
+            const int commit_head = (int)lds_u32(a_head);
+            #pragma unroll 1
             while (rem) {
                 const bool inrem = (rem >> lane) & 1u;
                 // 1. hypothesis
-                float t = fabsf(hint - cur.adeg);
+                float t = fabsf(hint - c_r.x);
                 if (t > 270.f) t = fabsf(t - 360.f);
-                const bool hyp = inrem && t <= precdeg;
-                const unsigned H = __ballot_sync(FULL, hyp);
-                const bool inH = hyp && !(grp & H & lt);  // a pixel seen by several lanes is accepted by the first
+                const unsigned H0 = __ballot_sync(FULL, inrem && t <= precdeg);
+                const bool inH = ((H0 >> lane) & 1u) && !(grp & H0 & lt);  // a pixel seen by several lanes is accepted by the first
                 const unsigned H2 = __ballot_sync(FULL, inH);
                 const int c = __popc(H2 & lt), cmax = __popc(H2);
-                if (inH) F.sval[c] = make_float2(cur.ca, cur.sa);
+                if (inH) sts_f2(a_sval + (unsigned)c * 8u, c_r.z, c_r.w);
                 __syncwarp();
                 // 2. the sums the reference holds on reaching this lane, if H2 happened
                 float px = sumdx, py = sumdy;
-                for (int k0 = 0; k0 < cmax; k0 += 4) {
-                    const float2 v0 = F.sval[k0], v1 = F.sval[k0 + 1], v2 = F.sval[k0 + 2], v3 = F.sval[k0 + 3];
+                #pragma unroll 1
+                for (int k0 = 0; k0 < cmax; k0 += 2) {
+                    const float2 v0 = lds_f2(a_sval + (unsigned)k0 * 8u), v1 = lds_f2(a_sval + (unsigned)k0 * 8u + 8u);
                     if (k0 < c) { px = __fadd_rn(px, v0.x); py = __fadd_rn(py, v0.y); }
                     if (k0 + 1 < c) { px = __fadd_rn(px, v1.x); py = __fadd_rn(py, v1.y); }
-                    if (k0 + 2 < c) { px = __fadd_rn(px, v2.x); py = __fadd_rn(py, v2.y); }
-                    if (k0 + 3 < c) { px = __fadd_rn(px, v3.x); py = __fadd_rn(py, v3.y); }
                 }
                 __syncwarp();
                 // the region angle is only defined by the sums after the first acceptance; before it, it is the seed's
                 const float th = (any || c > 0) ? fast_atan2_deg(py, px) : seed_deg;
                 bool v = false;
-                if (inrem && !(grp & H2 & lt)) v = lsd_aligned_deg(th, cur.adeg, precdeg, prec);
+                if (inrem && !(grp & H2 & lt)) {
+                    // isAligned() on the float degree values the reference converts to double radians: decided in float when the
+                    // distance is not within 2e-3 degrees of the tolerance or of the fold point, else with the reference's own formula
+                    const float t2 = fabsf(th - c_r.x);
+                    const float tf = t2 > 270.f ? fabsf(t2 - 360.f) : t2;
+                    if (__builtin_expect(fabsf(tf - precdeg) > 2e-3f && fabsf(t2 - 270.f) > 2e-3f, 1)) v = tf <= precdeg;
+                    else v = lsd_aligned((double)th * kDegToRad, (double)c_r.x * kDegToRad, prec);
+                }
                 // 3. first lane whose verdict contradicts the hypothesis
                 const unsigned M = __ballot_sync(FULL, inrem && v != inH);
                 unsigned T = H2, resolved = FULL;
@@ -545,22 +619,22 @@ __device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy,
                 hint = __shfl_sync(FULL, th, hl);
                 const int cnt = __popc(T);
                 if (cnt) {
-                    if (__builtin_expect(n + cnt > F.reg_cap || nt + cnt > F.touched_cap, 0)) return -1;
-                    if (__builtin_expect(__any_sync(FULL, ((T >> lane) & 1u) && lsd_claim_hit(F, cur.claim)), 0)) return -2;
-                    if (__builtin_expect(!lsd_priv_alloc(F, (T >> lane) & 1u, cur.xx, cur.yy), 0)) return -1;
-                    if ((T >> lane) & 1u) {
-                        F.rec[cur.o].claim = (unsigned)F.ticket & 0xffffu;
+                    const bool mine = (T >> lane) & 1u;
+                    if (__builtin_expect(n + cnt > reg_cap || nt + cnt > touched_cap, 0)) return -1;
+                    if (__builtin_expect(__any_sync(FULL, mine && lsd_claim_hit(ticket, commit_head, claim)), 0)) return -2;
+                    if (__builtin_expect(!tile_alloc(mine, cx, cy), 0)) return -1;
+                    if (mine) {
+                        rec[c_o].claim = (unsigned)ticket & 0xffffu;
                         const int r = __popc(T & lt);
-                        const unsigned pk = ((unsigned)cur.yy << 16) | (unsigned)cur.xx;
-                        F.reg[n + r] = pk;
-                        F.ring[(n + r) & (kRegRing - 1)] = pk;
-                        lsd_mark(F, cur.xx, cur.yy, cur.o);
-                        F.touched[nt + r] = pk;
+                        reg[n + r] = c_pk;
+                        sts_u32(a_ring + (unsigned)((n + r) & (kRegRing - 1)) * 4u, c_pk);
+                        mark(cx, cy, c_o);
+                        touched[nt + r] = c_pk;
                     }
                     // sums after the last accepted lane: its own prefix plus its own pixel
                     const int L = 31 - __clz(T);
-                    sumdx = __shfl_sync(FULL, __fadd_rn(px, cur.ca), L);
-                    sumdy = __shfl_sync(FULL, __fadd_rn(py, cur.sa), L);
+                    sumdx = __shfl_sync(FULL, __fadd_rn(px, c_r.z), L);
+                    sumdy = __shfl_sync(FULL, __fadd_rn(py, c_r.w), L);
                     n += cnt;
                     nt += cnt;
                     any = true;
@@ -573,8 +647,13 @@ __device__ __noinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy,
         i += nb;
         have = have_next;
     }
-    *out_angle = any ? (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad : (double)seed_deg * kDegToRad;
+#undef PL_LOAD_CAND
+    nt_io = nt;
+    *out_angle = any ? (double)fast_atan2_deg_ool(sumdy, sumdx) * kDegToRad : (double)seed_deg * kDegToRad;
     return n;
+}
+__device__ __forceinline__ int lsd_region_grow(const LsdFrame& Fin, int sx, int sy, double prec, double* out_angle, int& nt) {
+    return Fin.sparse ? lsd_region_grow_t<true>(Fin, sx, sy, prec, out_angle, nt) : lsd_region_grow_t<false>(Fin, sx, sy, prec, out_angle, nt);
 }
 
 // sequential (reference-order) accumulation helper: every lane loads one region point, then all lanes replay the
@@ -1646,6 +1725,10 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
     }
 }
 
+}  // namespace pl
+#include "lsd_grow2.cuh"
+namespace pl {
+
 // NFA validation of the fitted rectangles (rect_improve): it only reads the angle map and does not influence any
 // other region, so every rectangle of every frame is independent — one warp per rectangle.  Rectangles are validated
 // in two places: grower CTAs that have run out of frames take chunks of kNfaChunk rectangles of finished frames from a
@@ -2052,6 +2135,9 @@ struct pl_line {
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     int tail_nfa = 1;
     GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
+    // k_lsd_grow2 (role-specialised grower, one frame per CTA): shape for up to one frame per SM / for more frames than SMs
+    struct Grow2Cfg { int threads = 0, occ = 0, pool_tiles = 0, pool_n = 0; size_t smem = 0; } g2_few, g2_many;
+    int grow_impl = 2, lookahead = 4;
     int poll_ns = 400;
     int reserved_sms = 0;          // SMs the region grower leaves to the kernels of other streams (pl_line_set_reserved_sms)
     unsigned int* d_big_bits = nullptr;
@@ -2198,7 +2284,16 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_ctl, 0, 4 * sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
-        if (cf.growers <= 8) k_lsd_grow<256><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
+        if (h->grow_impl == 2) {
+            // role-specialised grower: one frame per CTA, several CTAs per SM when there are more frames than SMs
+            const bool many2 = nf > sms && h->g2_many.threads > 0;
+            const pl_line::Grow2Cfg& c2 = many2 ? h->g2_many : h->g2_few;
+            Grow2Smem g2{h->grow_tiles, c2.pool_tiles, std::min(h->grow_window, kSlots2), h->lookahead, h->bits_words, h->tail_nfa, h->poll_ns, c2.pool_n};
+            const int ctas2 = std::min(nf, sms * std::max(1, c2.occ));
+            if (c2.threads <= 256 && c2.occ >= 2) k_lsd_grow2<256, 3><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
+            else if (c2.threads <= 512) k_lsd_grow2<512, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
+            else k_lsd_grow2<1024, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
+        } else if (cf.growers <= 8) k_lsd_grow<256><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
         else k_lsd_grow<512><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
     }
     k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
@@ -2362,15 +2457,84 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             }
             e = cudaFuncSetAttribute(k_lsd_grow<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lsd_grow<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            // ---- k_lsd_grow2: warps per CTA, CTAs per SM, private tile pool ----
+            if (const char* ev = getenv("PLSLAM_LSD_IMPL")) h->grow_impl = atoi(ev) == 1 ? 1 : 2;
+            if (const char* ev = getenv("PLSLAM_LSD_LOOKAHEAD")) h->lookahead = std::max(1, std::min(kSlots2, atoi(ev)));
+            auto allow_smem = [&](const void* fn) {  // dynamic shared memory up to what the kernel's static part leaves
+                cudaFuncAttributes fa;
+                if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fn);
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes));
+            };
+            allow_smem((const void*)k_lsd_grow2<256, 3>);
+            allow_smem((const void*)k_lsd_grow2<512, 1>);
+            allow_smem((const void*)k_lsd_grow2<1024, 1>);
+            const size_t sm_smem = prop.sharedMemPerMultiprocessor;
+            // threads = 32 * (1 sequencer + growers); the largest tile pool that still gives the wanted CTAs per SM
+            auto choose2 = [&](int threads, int occ, pl_line::Grow2Cfg* c) {
+                const size_t fixed = sizeof(Grow2Shared) + 64;  // static shared memory
+                const size_t per_cta = std::min<size_t>(sm_smem / occ > 1024 + fixed ? sm_smem / occ - 1024 - fixed : 0, prop.sharedMemPerBlockOptin - fixed);
+                for (int pN = kMaxPoolTiles; pN >= 8; pN -= 4) {
+                    Grow2Smem g2{tiles, pN, 0, 0, h->bits_words, 0, 0, 0};
+                    if (g2.total(threads / 32) <= per_cta) {
+                        c->threads = threads;
+                        c->occ = occ;
+                        c->pool_tiles = pN;
+                        c->pool_n = std::min(kMaxPool2, threads / 32 - 1 + 17);
+                        c->smem = g2.total(threads / 32);
+                        return true;
+                    }
+                }
+                return false;
+            };
+            int t_few = 512, t_many = 256, occ_many = 3;
+            if (const char* ev = getenv("PLSLAM_LSD_GROW2")) {  // tuning override: "<threads few>,<threads many>,<CTAs per SM>"
+                int a = 0, b2 = 0, c2 = 0;
+                if (sscanf(ev, "%d,%d,%d", &a, &b2, &c2) == 3) {
+                    if (a >= 64 && a <= 1024 && a % 32 == 0) t_few = a;
+                    if (b2 >= 64 && b2 <= 1024 && b2 % 32 == 0) t_many = b2;
+                    if (c2 >= 1 && c2 <= 8) occ_many = c2;
+                }
+            }
+            for (int t = t_few; t >= 64 && !h->g2_few.threads; t -= 32) choose2(t, 1, &h->g2_few);
+            if (t_many > 256) occ_many = 1;
+            for (int oc = occ_many; oc >= 1 && !h->g2_many.threads; oc--)
+                for (int t = t_many; t >= 64 && !h->g2_many.threads; t -= 32) {
+                    if (!choose2(t, oc, &h->g2_many)) continue;
+                    int occ_real = 0;  // what the device really gives (registers count too)
+                    cudaError_t eo = oc >= 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k_lsd_grow2<256, 3>, t, h->g2_many.smem)
+                                             : cudaSuccess;
+                    if (oc >= 2 && (eo != cudaSuccess || occ_real < oc)) h->g2_many = pl_line::Grow2Cfg{};
+                }
+            if (const char* ev = getenv("PLSLAM_LSD_POOL_TILES")) {
+                const int pt = atoi(ev);
+                if (pt >= 1 && pt <= kMaxPoolTiles) {
+                    h->g2_few.pool_tiles = std::min(h->g2_few.pool_tiles, pt);
+                    h->g2_many.pool_tiles = std::min(h->g2_many.pool_tiles, pt);
+                }
+            }
+            if (h->grow_impl == 2 && h->g2_few.threads < 64) {
+                set_error("pl_line_create: a %dx%d image does not leave shared memory for a sequencer and a grower warp", max_cols, max_rows);
+                pl_line_destroy(h);
+                return PL_ERR_CAPACITY;
+            }
         }
     }
     const size_t max_ctas = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1));
-    const size_t max_fs = max_ctas * kMaxFrameSlots;
-    A(&h->d_spec_reg, max_ctas * kPool * (size_t)kSpecCap);
-    A(&h->d_spec_touched, max_ctas * kPool * (size_t)kSpecCap);
-    A(&h->d_pool_rect, max_ctas * kPool);
-    A(&h->d_small_buf, max_fs * kSlots * 2 * (size_t)kSmall);
-    A(&h->d_small_rect, max_fs * kSlots);
+    size_t max_fs = max_ctas * kMaxFrameSlots;
+    size_t pool_words = max_ctas * kPool * (size_t)kSpecCap, pool_rects = max_ctas * kPool, small_slots = max_fs * kSlots;
+    if (h->grow_impl == 2) {  // the buffers of k_lsd_grow2 are indexed by CTA
+        const size_t c_few = max_ctas, c_many = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1) * std::max(1, h->g2_many.occ));
+        pool_words = std::max(c_few * h->g2_few.pool_n, c_many * h->g2_many.pool_n) * (size_t)kSpecCap2;
+        pool_rects = std::max(c_few * h->g2_few.pool_n, c_many * h->g2_many.pool_n);
+        max_fs = std::max(c_few, c_many);
+        small_slots = max_fs * kSlots2;
+    }
+    A(&h->d_spec_reg, pool_words);
+    A(&h->d_spec_touched, pool_words);
+    A(&h->d_pool_rect, pool_rects);
+    A(&h->d_small_buf, small_slots * 2 * (size_t)kSmall);
+    A(&h->d_small_rect, small_slots);
     A(&h->d_big_touched, max_fs * 2 * plane);
     A(&h->d_big_bits, max_fs * (size_t)h->bits_words);
     if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_fs * (size_t)h->bits_words * sizeof(unsigned int));
@@ -2385,7 +2549,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_xtab, (size_t)W);
     A(&h->d_ytab, (size_t)H);
     A(&h->d_lgam, (size_t)kLgMax);
-    A(&h->d_phase, B * 8);
+    A(&h->d_phase, B * 16);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_flags, sizeof(int) * B);
     if (e != cudaSuccess) {
         set_error("pl_line_create: %s", cudaGetErrorString(e));
@@ -2577,11 +2741,13 @@ PL_API int pl_line_lsd_read(pl_line* h, int frame, float* xyxy, double* width, d
 
 /* with profiling on: cycles of frame `frame` of the last chunk spent in {seed scan, grow, rect fit, refine, NFA} and
  * the number of regions tried / regions that reached the minimum size (k_lsd_grow's own clock64 accounting) */
-PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out7) {
-    PL_CHECK_ARG(h && out7 && frame >= 0 && frame < h->last_batch);
-    // out7 receives 8 values, see plslam_c.h
+PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out16) {
+    PL_CHECK_ARG(h && out16 && frame >= 0 && frame < h->last_batch);
+    // out16 receives 16 values, see plslam_c.h
     PL_CUDA_TRY(cudaSetDevice(h->device));
-    PL_CUDA_TRY(cudaMemcpyAsync(out7, h->d_phase + (size_t)frame * 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost, h->stream));
+    const size_t stride = h->grow_impl == 2 ? 16 : 8;
+    for (int i = 8; i < 16; i++) out16[i] = 0;
+    PL_CUDA_TRY(cudaMemcpyAsync(out16, h->d_phase + (size_t)frame * stride, sizeof(long long) * stride, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(pl::stream_sync(h->stream));
     return PL_OK;
 }

@@ -59,16 +59,9 @@ names = ["scale+grad", "seed_sort", "grow+nfa", "keylines+sobel", "lbd"]
 for i in range(5):
     print(f"  {names[i]:15s} {out[i]*1000/(a.frames*a.iters):9.2f} us/frame  ({out[i]/a.iters:.3f} ms per pass)")
 print("lines/frame", float(d_n.float().mean().item()), "launches", ex.last_launches())
-ph = np.zeros(8, np.int64)
+ph = np.zeros(16, np.int64)
 N.check(N.lib().pl_line_grow_phases(ex._h, C.c_int(0), N.ptr(ph)))
-if os.environ.get("PLSLAM_NVCC_EXTRA", "").find("PL_LSD_PROF3") >= 0:
-    print(f"PROF3 region_grow (frame 0, all calls, Mcycles): loads {ph[7]/1e6:.1f} | pass: hypothesis {ph[0]/1e6:.1f} prefix {ph[1]/1e6:.1f} "
-          f"atan2+verdict {ph[2]/1e6:.1f} commit {ph[3]/1e6:.1f}; batches {ph[4]} passes {ph[5]} pixels {ph[6]}")
-elif os.environ.get("PLSLAM_NVCC_EXTRA", "").find("PL_LSD_PROF2") >= 0:
-    print(f"PROF2 (frame 0): total {ph[1]/1e6:.1f} Mcycles x8 warps, rounds {ph[3]}, accepted pixels {ph[4]}, busy: grow {ph[5]/1e6:.1f} "
-          f"rect {ph[6]/1e6:.1f} refine {ph[7]/1e6:.1f} Mcycles (sum over warps)")
-else:
-    busy, regrow, aborted = ph[0] & 0xfffff, (ph[0] >> 20) & 0xfffff, ph[0] >> 40
-    print(f"grow kernel (frame 0): total {ph[1]/1e6:.1f} Mcycles; speculative growth {busy/1e3:.1f} Mcycles over all warps (given up: {aborted/1e3:.1f}), "
-          f"re-growth at commit {regrow/1e3:.1f}; commit sections {ph[2]/1e6:.1f}; tickets {ph[3]}, committed {ph[5]}, "
-          f"void {ph[7]}, deferred {ph[6]}, regrown {ph[4]}")
+M = 1e6
+print(f"grow kernel (frame 0): frame active {ph[1]/M:.1f} Mcycles; sequencer: commit {ph[2]/M:.1f}, re-growth {ph[0]/M:.1f}, issue {ph[8]/M:.1f}, "
+      f"idle {ph[9]/M:.1f}; {ph[13]} growers: growing {ph[10]/M:.1f} (given up {ph[14]/M:.1f}), waiting {ph[11]/M:.1f}, parking {ph[12]/M:.1f} "
+      f"(summed over the warps); tickets {ph[3]}, committed {ph[5]}, void {ph[7]}, deferred {ph[6]}, regrown {ph[4]}")
