@@ -305,7 +305,8 @@ struct LsdFrame {  // per-frame (and per-grower) device views
     int* ntiles;          // pool slots in use
     int tw, pool_tiles;
     unsigned int* bits;   // full private bitmap (W*H bits)
-    unsigned int* touched;  // log of accepted pixels (packed), capacity touched_cap
+    unsigned int* touched;  // log of accepted pixels (packed), capacity touched_cap; nullptr = not logged (a first growth: the log is the region)
+    unsigned int* touched_buf;  // where the log goes once a re-growth (refine) starts
     int reg_cap;            // capacity of reg
     int touched_cap;        // capacity of touched
     // in-flight claims (a hint that saves wasted growth, never needed for correctness): every accepted pixel is
@@ -481,7 +482,7 @@ __device__ __noinline__ int lsd_region_grow_t(const LsdFrame& Fin, int sx, int s
     float sumdx = c0.x, sumdy = c0.y;
     float hint = seed_deg;
     const float precdeg = (float)(prec * (180.0 / kPiD));
-    if (nt >= touched_cap) return -1;
+    if (touched && nt >= touched_cap) return -1;
     // private mark of a pixel: the tile must exist first (sparse)
     auto tile_alloc = [&](bool want, int x, int y) -> bool {  // warp-collective; false when the pool is exhausted
         if (!kSparse) return true;
@@ -516,10 +517,10 @@ __device__ __noinline__ int lsd_region_grow_t(const LsdFrame& Fin, int sx, int s
         reg[0] = pk;
         sts_u32(a_ring, pk);
         mark(sx, sy, so);
-        touched[nt] = pk;
+        if (touched) touched[nt] = pk;
         rec[so].claim = (unsigned)ticket & 0xffffu;
     }
-    nt++;
+    if (touched) nt++;
     __syncwarp();
     int n = 1, i = 0, have = 0;
     bool any = false;
@@ -620,7 +621,7 @@ __device__ __noinline__ int lsd_region_grow_t(const LsdFrame& Fin, int sx, int s
                 const int cnt = __popc(T);
                 if (cnt) {
                     const bool mine = (T >> lane) & 1u;
-                    if (__builtin_expect(n + cnt > reg_cap || nt + cnt > touched_cap, 0)) return -1;
+                    if (__builtin_expect(n + cnt > reg_cap || (touched && nt + cnt > touched_cap), 0)) return -1;
                     if (__builtin_expect(__any_sync(FULL, mine && lsd_claim_hit(ticket, commit_head, claim)), 0)) return -2;
                     if (__builtin_expect(!tile_alloc(mine, cx, cy), 0)) return -1;
                     if (mine) {
@@ -629,14 +630,14 @@ __device__ __noinline__ int lsd_region_grow_t(const LsdFrame& Fin, int sx, int s
                         reg[n + r] = c_pk;
                         sts_u32(a_ring + (unsigned)((n + r) & (kRegRing - 1)) * 4u, c_pk);
                         mark(cx, cy, c_o);
-                        touched[nt + r] = c_pk;
+                        if (touched) touched[nt + r] = c_pk;
                     }
                     // sums after the last accepted lane: its own prefix plus its own pixel
                     const int L = 31 - __clz(T);
                     sumdx = __shfl_sync(FULL, __fadd_rn(px, c_r.z), L);
                     sumdy = __shfl_sync(FULL, __fadd_rn(py, c_r.w), L);
                     n += cnt;
-                    nt += cnt;
+                    if (touched) nt += cnt;
                     any = true;
                     rem &= ~__ballot_sync(FULL, (grp & T) != 0);
                 }
@@ -819,6 +820,16 @@ __device__ int lsd_refine(const LsdFrame& F, const LsdFrame& Fm, int& n, double&
     const double mean_angle = sum / (double)cnt_in;
     const double tau = 2.0 * sqrt(__dadd_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)) / (double)cnt_in,
                                             __dmul_rn(mean_angle, mean_angle)));
+    if (F.touched == nullptr) {
+        // the first growth was not logged (its log is the region): the region list is about to be overwritten, so the log starts
+        // now, with the region as its first n entries
+        if (n > F.touched_cap) return kStCapacity;
+        #pragma unroll 1
+        for (int i = lane; i < n; i += 32) F.touched_buf[i] = F.reg[i];
+        nt = n;
+        if (lane == 0) const_cast<LsdFrame&>(Fm).touched = F.touched_buf;
+        __syncwarp();
+    }
     n = lsd_region_grow(Fm, sx, sy, tau, &reg_angle, nt);
     if (n < 0) return n;
     if (n < 2) return 0;
@@ -1111,7 +1122,7 @@ __device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restr
     F.g2 = nullptr; F.rec = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
     F.W = g.W; F.H = g.H;
     F.sparse = false; F.dir = nullptr; F.rev = nullptr; F.pool = nullptr; F.ntiles = nullptr; F.tw = 0; F.pool_tiles = 0;
-    F.bits = nullptr; F.touched = nullptr; F.reg_cap = 0; F.touched_cap = 0;
+    F.bits = nullptr; F.touched = nullptr; F.touched_buf = nullptr; F.reg_cap = 0; F.touched_cap = 0;
     F.ticket = 0; F.commit_head = nullptr;
     const double log_eps = 0.0;
     LsdRect rec = queue[(size_t)f * g.seg_cap + t].rec;
@@ -1213,28 +1224,35 @@ __device__ __forceinline__ int pool_pop(unsigned long long* mask, int lane) {
 // grow + fit + refine one seed into the buffers of F; leaves the private marks clean
 // Fin and out live in shared memory (one per warp): the out-of-line callees read the view from there instead of
 // every thread keeping (and spilling) its own copy in local memory.
-__device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min_reg_size, GrowResult* out) {
+// region2rect + refine of a region of at least min_reg_size pixels (n, reg_angle, nt: in / out); returns the status and leaves
+// the rectangle in out->rec.  Out of line and apart from the growth: only one region in seven gets here.
+__device__ __noinline__ int lsd_fit_refine(const LsdFrame& Fin, int* n_io, double reg_angle, int* nt_io, GrowResult* out) {
     const LsdFrame F = Fin;  // register copy for the inlined code
-    const int lane = threadIdx.x & 31;
     const double prec = kPiD * 22.5 / 180, p = 22.5 / 180;
     const double density_th = 0.7;
-    const int sx = pix % F.W, sy = pix / F.W;
+    int n = *n_io, nt = *nt_io;
+    LsdRect rec;
+    lsd_region2rect(Fin, n, reg_angle, prec, p, rec);
+    const int status = lsd_refine(F, Fin, n, reg_angle, prec, p, rec, density_th, nt);
+    if ((threadIdx.x & 31) == 0 && status == kStRect) out->rec = rec;
+    *n_io = n;
+    *nt_io = nt;
+    return status;
+}
+__device__ __noinline__ void lsd_grow_seed(const LsdFrame& Fin, int pix, int min_reg_size, GrowResult* out) {
+    const int lane = threadIdx.x & 31;
+    const double prec = kPiD * 22.5 / 180;
+    const int sx = pix % Fin.W, sy = pix / Fin.W;
     double reg_angle;
     int nt = 0, status = kStNoRect;
-    LsdRect rec;
     int n = lsd_region_grow(Fin, sx, sy, prec, &reg_angle, nt);
-    if (n < 0) {
-        status = n;
-    } else if (n >= min_reg_size) {
-        lsd_region2rect(Fin, n, reg_angle, prec, p, rec);
-        status = lsd_refine(F, Fin, n, reg_angle, prec, p, rec, density_th, nt);
-    }
-    lsd_priv_reset(F, nt);
+    if (n < 0) status = n;
+    else if (n >= min_reg_size) status = lsd_fit_refine(Fin, &n, reg_angle, &nt, out);
+    lsd_priv_reset(Fin, nt);
     if (lane == 0) {
         out->status = status;
         out->n = n;
         out->nt = nt;
-        if (status == kStRect) out->rec = rec;
     }
     __syncwarp();
 }
@@ -1306,6 +1324,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
     F.H = g.H;
     F.reg = nullptr;
     F.touched = nullptr;
+    F.touched_buf = nullptr;
     F.reg_cap = F.touched_cap = 0;
     #pragma unroll 1
     for (int i = lane; i < gs.tiles; i += 32) F.dir[i] = 0xffu;
@@ -1541,6 +1560,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
                         FS2.bits = B.big_bits + (cta_fs + fsi) * gs.bits_words;
                         FS2.reg = B.big_reg + (size_t)f * plane;
                         FS2.touched = B.big_touched + (cta_fs + fsi) * 2 * plane;
+                        FS2.touched_buf = FS2.touched;
                         FS2.reg_cap = (int)plane;
                         FS2.touched_cap = (int)(2 * plane);
                         FS2.ticket = h;
@@ -1685,6 +1705,7 @@ __global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs,
             LsdFrame FS2 = F;
             FS2.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
             FS2.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
+            FS2.touched_buf = FS2.touched;
             FS2.reg_cap = FS2.touched_cap = kSpecCap;
             FS2.ticket = my_ticket;
             const long long g0 = clock64();

@@ -175,6 +175,7 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
         F.H = g.H;
         F.reg = B.big_reg + (size_t)f * plane;
         F.touched = B.big_touched + (size_t)blockIdx.x * 2 * plane;
+        F.touched_buf = F.touched;
         F.reg_cap = (int)plane;
         F.touched_cap = (int)(2 * plane);
         F.used_bits = s_used;
@@ -223,7 +224,7 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
                     unsigned rg0 = 0, tk0 = 0, rc0 = 0;
                     // Most tickets are regions of a few pixels without a rectangle: their points never left shared memory
                     // (the grower parked them in the ticket slot) and their accept log is their point list.
-                    const bool tiny = !redo && status == kStNoRect && buf < 0 && n <= kTiny && nt == n;
+                    const bool tiny = !redo && status == kStNoRect && buf < 0 && n <= kTiny && nt == 0;
                     if (tiny) {
                         bool conflict = false;
                         if (lane < n) {
@@ -235,6 +236,10 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
                     } else if (!redo) {
                         // points, log and rectangle live in global memory: the three reads are issued together
                         const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap2 : rg + kSmall;
+                        if (nt == 0) {  // a growth without re-growth: its accept log is its region
+                            tk = rg;
+                            nt = n;
+                        }
                         if (lane < nt) tk0 = tk[lane];
                         if (lane < n) rg0 = rg[lane];
                         if (status == kStRect && lane < (int)(sizeof(LsdRect) / 4))
@@ -409,7 +414,7 @@ __device__ __noinline__ int g2_grower(int f, int mybuf) {
     unsigned int* my_pool_touched = B.pool_touched + (size_t)blockIdx.x * gs.pool_n * kSpecCap2;
     const LsdPix* rec = B.rec + (size_t)f * B.plane;
     const unsigned int* ring = reinterpret_cast<unsigned int*>(s_raw + gs.off_growers() + (size_t)(warp - 1) * gs.per_grower() + gs.off_ring());
-    const int min_reg_size = g2s.g.min_reg_size, poll_ns = gs.poll_ns;
+    const int min_reg_size = g2s.g.min_reg_size, poll_ns = gs.poll_ns, W = g2s.g.W;
     const bool prof = B.phase_cycles != nullptr;
     if (lane == 0) {
         view->ang = B.angdeg + (size_t)f * B.plane;
@@ -449,23 +454,30 @@ __device__ __noinline__ int g2_grower(int f, int mybuf) {
         }
         if (lane == 0) {
             view->reg = my_pool_reg + (size_t)mybuf * kSpecCap2;
-            view->touched = my_pool_touched + (size_t)mybuf * kSpecCap2;
+            view->touched = nullptr;  // the first growth is not logged: its log is the region
+            view->touched_buf = my_pool_touched + (size_t)mybuf * kSpecCap2;
             view->ticket = t;
         }
         __syncwarp();
-        lsd_grow_seed(*view, pix, min_reg_size, res);
+        int r_n, r_nt = 0, r_status = kStNoRect;
+        {
+            double reg_angle;
+            r_n = lsd_region_grow_t<true>(*view, pix % W, pix / W, kPiD * 22.5 / 180, &reg_angle, r_nt);
+            if (r_n < 0) r_status = r_n;
+            else if (r_n >= min_reg_size) r_status = lsd_fit_refine(*view, &r_n, reg_angle, &r_nt, res);
+            lsd_priv_reset(*view, r_nt);
+        }
         const long long w2 = prof ? clock64() : 0;
-        const int r_status = res->status, r_n = res->n, r_nt = res->nt;
         // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer, a tiny one
         // (the ring still holds every point of it) into the slot itself
-        const bool tiny = r_status == kStNoRect && r_n <= kTiny && r_nt == r_n;
+        const bool tiny = r_status == kStNoRect && r_n <= kTiny && r_nt == 0;
         const bool small = !tiny && r_status >= 0 && r_n <= kSmall && r_nt <= kSmall;
         const bool keep = r_status >= 0 && !small && !tiny;
         const int slot = t & (kSlots2 - 1);
         if (tiny) {
             if (lane < r_n) s_tiny[slot * kTiny + lane] = ring[lane];
         } else if (small) {
-            const unsigned int* sr = my_pool_reg + (size_t)mybuf * kSpecCap2;
+            const unsigned int* sr = my_pool_reg + (size_t)mybuf * kSpecCap2;  // (reduce_region_radius reorders the list in place)
             const unsigned int* st = my_pool_touched + (size_t)mybuf * kSpecCap2;
             unsigned int* dst = B.small_buf + ((size_t)blockIdx.x * kSlots2 + slot) * 2 * kSmall;
             #pragma unroll 1
@@ -534,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
             F.H = g_.H;
             F.reg = nullptr;
             F.touched = nullptr;
+            F.touched_buf = nullptr;
             F.reg_cap = F.touched_cap = kSpecCap2;
             F.used_bits = reinterpret_cast<unsigned int*>(s_raw + gs_.off_used());
             F.commit_head = &g2s.ctl.commit_head;
