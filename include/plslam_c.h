@@ -183,6 +183,10 @@ PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
  *  issuing tickets, 9 sequencer cycles idle, 10 / 11 / 12 grower cycles (summed over the grower warps) growing / waiting for a
  *  ticket / parking results, 13 grower warps, 14 grower cycles in growth that was given up, 15 reserved} */
 PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out16);
+/* Test hook: the double-precision sin / cos the line path uses on the device where one ulp decides a discrete outcome
+ * (region2rect of lsd.cpp: rec.dx / rec.dy; the seeds' initial sums) — glibc's own arithmetic restated
+ * (csrc/pl_glibc_sincos.cuh), so that the results equal std::sin / std::cos of the reference's host. */
+PL_API int pl_test_sincos(const double* x, int n, double* s, double* c);
 /* Test hooks: the 0.8-scaled 8-bit image LSD works on, its level-line angle map (float degrees, -1024 = undefined,
  * rows x cols of the scaled image) and the float LBD descriptors (n x 72) of frame `frame` of the last call. */
 PL_API int pl_line_scaled_dims(const pl_line* h, int* rows, int* cols);

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "pl_common.cuh"
+#include "pl_glibc_sincos.cuh"
 
 namespace pl {
 
@@ -30,6 +31,10 @@ constexpr double k32Pi = (3 * kPiD) / 2;
 constexpr float kNotDefDeg = -1024.0f;  // stored angle of pixels with undefined gradient
 constexpr int kBins = 1024;
 constexpr int kTileRows = 8;  // rows per sort tile (one warp walks a tile in raster order)
+// sin / cos of k / 128 for the host-exact double sin / cos (pl_glibc_sincos.cuh)
+__device__ const double g_sincostab[440] = {
+#include "pl_sincostab.inc"
+};
 
 struct LineGeom {
     int cols, rows;        // input image
@@ -135,7 +140,8 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineGeom g, const uint8_t* __r
                 sa = glibc_sincosf(af, 0);
                 // a seed starts its sums from float(std::cos(double angle)), float(std::sin(double angle))
                 const double ad = (double)a * kDegToRad;
-                cs0[(size_t)f * plane + (size_t)y * g.W + x] = make_float2((float)cos(ad), (float)sin(ad));
+                const GlibcSinCos sc{g_sincostab};
+                cs0[(size_t)f * plane + (size_t)y * g.W + x] = make_float2((float)sc.cos(ad), (float)sc.sin(ad));
             }
         }
         angdeg[(size_t)f * plane + (size_t)y * g.W + x] = a;
@@ -719,7 +725,12 @@ __device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double 
     theta *= kDegToRad;
     if (fabs(lsd_angle_diff_signed(theta, reg_angle)) > prec) theta += kPiD;
     double dx, dy;
-    sincos(theta, &dy, &dx);
+    // the host libm's own arithmetic: the last bit of dx / dy decides which pixels the rectangle's edges include
+    {
+        const GlibcSinCos sc{g_sincostab};
+        dx = sc.cos(theta);
+        dy = sc.sin(theta);
+    }
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
 #pragma unroll 1
     for (int idx = lane; idx < n; idx += 32) {
@@ -823,7 +834,7 @@ __device__ int lsd_refine(const LsdFrame& F, const LsdFrame& Fm, int& n, double&
     if (F.touched == nullptr) {
         // the first growth was not logged (its log is the region): the region list is about to be overwritten, so the log starts
         // now, with the region as its first n entries
-        if (n > F.touched_cap) return kStCapacity;
+        if (n > F.touched_cap) return -1;  // (kStCapacity)
         #pragma unroll 1
         for (int i = lane; i < n; i += 32) F.touched_buf[i] = F.reg[i];
         nt = n;
@@ -2370,7 +2381,40 @@ int line_check_flags(pl_line* h, int nf) {
 
 }  // namespace
 
+__global__ void __launch_bounds__(256) k_test_sincos(const double* __restrict__ x, int n, double* __restrict__ s, double* __restrict__ c) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) {
+        const pl::GlibcSinCos sc{pl::g_sincostab};
+        s[i] = sc.sin(x[i]);
+        c[i] = sc.cos(x[i]);
+    }
+}
+
 extern "C" {
+
+PL_API int pl_test_sincos(const double* x, int n, double* s, double* c) {
+    PL_CHECK_ARG(x && s && c && n >= 0);
+    if (n == 0) return PL_OK;
+    double *dx = nullptr, *ds = nullptr, *dc = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dx, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ds, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_test_sincos<<<(n + 255) / 256, 256>>>(dx, n, ds, dc);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(s, ds, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(c, dc, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(ds);
+    cudaFree(dc);
+    if (e != cudaSuccess) {
+        set_error("pl_test_sincos: %s", cudaGetErrorString(e));
+        return PL_ERR_CUDA;
+    }
+    return PL_OK;
+}
 
 PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows, int max_batch) {
     PL_CHECK_ARG(out != nullptr);

@@ -6,6 +6,8 @@ its exhaustive sweep (2,130,706,432 floats, 0 mismatches, with and without FMA) 
 import os
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -15,3 +17,16 @@ def test_sincos_restatement_matches_libm(tmp_path):
     out = subprocess.run([exe, "211"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "mismatches 0" in out.stdout
+
+
+def test_double_sincos_restatement_equals_host_libm(tmp_path):
+    """csrc/pl_glibc_sincos.cuh (rec.dx / rec.dy of LSD's region2rect, the seeds' initial sums) against std::sin / std::cos of this
+    host, compiled without contraction.  The restatement follows the FMA build of glibc's s_sin.c, which is what an x86-64 host
+    with FMA3 runs; on another host the reference itself computes other last bits, and the test says so instead of failing."""
+    exe = str(tmp_path / "glibc_sincos_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "glibc_sincos_check.cpp"), "-lm"])
+    r = subprocess.run([exe, "20000000"], capture_output=True, text=True)
+    fma = "fma" in open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else False
+    if not fma:
+        pytest.skip("host without FMA3: its libm runs the non-FMA build of s_sin.c: " + r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0, r.stdout
