@@ -300,6 +300,7 @@ struct LsdFrame {  // per-frame (and per-grower) device views
     const unsigned int* used_bits;  // the committed USED map: one bit per pixel, shared memory
     unsigned int* reg;  // region points, packed y<<16 | x
     unsigned int* ring; // shared-memory copy of reg[n - kRegRing .. n)
+    double* scratch;    // shared memory of the warp, 3 x 32 doubles: the ordered sums of region2rect / refine
     int W, H;
     // The pixels a grower marks stay private until its region is committed.  Speculative growers keep them in a
     // sparse bitmap in shared memory (a directory of 32x32-pixel tiles and a small pool of tile bitmaps); the
@@ -682,26 +683,45 @@ __device__ __forceinline__ RegPt lsd_load_pt(const LsdFrame& F, int idx, int n) 
     return r;
 }
 
+// Ordered sums of region2rect / refine.  The reference adds the terms of a region point by point, so every sum is a serial chain of
+// rounded additions — but the (up to three) sums of a pass are independent chains.  The 32 lanes compute the terms of 32 points and
+// park them in shared memory (scratch[k][lane]); then lane k alone walks chain k: one shared-memory load and one addition per point
+// instead of a shuffle per term and lane.  `acc` is the running sum of chain `lane` (lanes >= 3 carry nothing).
+__device__ __forceinline__ void lsd_ordered_add32(unsigned a_scratch, int lane, double t0, double t1, double t2, double& acc) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_scratch + (unsigned)lane * 8u), "d"(t0) : "memory");
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_scratch + 256u + (unsigned)lane * 8u), "d"(t1) : "memory");
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_scratch + 512u + (unsigned)lane * 8u), "d"(t2) : "memory");
+    __syncwarp();
+    if (lane < 3) {
+        const unsigned a = a_scratch + (unsigned)lane * 256u;
+        #pragma unroll 1
+        for (int j = 0; j < 32; j += 4) {
+            double v0, v1, v2, v3;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a + (unsigned)j * 8u) : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(a + (unsigned)j * 8u + 16u) : "memory");
+            acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, v0), v1), v2), v3);
+        }
+    }
+    __syncwarp();
+}
+
 // region2rect() + get_theta()
 __device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double reg_angle, double prec, double p, LsdRect& rec) {
     const LsdFrame F = Fin;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    double x = 0, y = 0, sum = 0;
+    const unsigned a_scratch = smem_u32(F.scratch);
+    double acc = 0;  // lane 0: sum x * w, lane 1: sum y * w, lane 2: sum w
+    #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);  // lanes beyond n hold zeros: adding +0.0 changes nothing
-        const double pxw = __dmul_rn(pt.x, pt.w), pyw = __dmul_rn(pt.y, pt.w);
-#pragma unroll 2
-        for (int j = 0; j < 32; j++) {
-            x = __dadd_rn(x, __shfl_sync(FULL, pxw, j));
-            y = __dadd_rn(y, __shfl_sync(FULL, pyw, j));
-            sum = __dadd_rn(sum, __shfl_sync(FULL, pt.w, j));
-        }
+        lsd_ordered_add32(a_scratch, lane, __dmul_rn(pt.x, pt.w), __dmul_rn(pt.y, pt.w), pt.w, acc);
     }
-    x = x / sum;
-    y = y / sum;
+    const double sum = __shfl_sync(FULL, acc, 2);
+    const double x = __shfl_sync(FULL, acc, 0) / sum, y = __shfl_sync(FULL, acc, 1) / sum;
     // get_theta
-    double Ixx = 0, Iyy = 0, Ixy = 0;
+    acc = 0;  // lane 0: Ixx, lane 1: Iyy, lane 2: Ixy (the reference subtracts its terms: a - b == a + (-b))
+    #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);
         double txx = 0, tyy = 0, txy = 0;
@@ -709,15 +729,11 @@ __device__ __noinline__ void lsd_region2rect(const LsdFrame& Fin, int n, double 
             const double dx = __dsub_rn(pt.x, x), dy = __dsub_rn(pt.y, y);
             txx = __dmul_rn(__dmul_rn(dy, dy), pt.w);
             tyy = __dmul_rn(__dmul_rn(dx, dx), pt.w);
-            txy = __dmul_rn(__dmul_rn(dx, dy), pt.w);
+            txy = -__dmul_rn(__dmul_rn(dx, dy), pt.w);
         }
-#pragma unroll 2
-        for (int j = 0; j < 32; j++) {
-            Ixx = __dadd_rn(Ixx, __shfl_sync(FULL, txx, j));
-            Iyy = __dadd_rn(Iyy, __shfl_sync(FULL, tyy, j));
-            Ixy = __dsub_rn(Ixy, __shfl_sync(FULL, txy, j));
-        }
+        lsd_ordered_add32(a_scratch, lane, txx, tyy, txy, acc);
     }
+    const double Ixx = __shfl_sync(FULL, acc, 0), Iyy = __shfl_sync(FULL, acc, 1), Ixy = __shfl_sync(FULL, acc, 2);
     const double dI = __dsub_rn(Ixx, Iyy);
     const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy), sqrt(__dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy)))));
     double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)__dsub_rn(lambda, Ixx), (float)Ixy)
@@ -806,8 +822,10 @@ __device__ int lsd_refine(const LsdFrame& F, const LsdFrame& Fm, int& n, double&
     const int sx = (int)(p0 & 0xffffu), sy = (int)(p0 >> 16);
     const double xc = (double)sx, yc = (double)sy;
     const double ang_c = (double)F.ang[(size_t)sy * F.W + sx] * kDegToRad;
-    double sum = 0, s_sum = 0;
+    const unsigned a_scratch = smem_u32(F.scratch);
+    double acc = 0;  // lane 0: sum of the angle differences, lane 1: sum of their squares
     int cnt_in = 0;
+    #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         const RegPt pt = lsd_load_pt(F, base + lane, n);
         bool inside = false;
@@ -821,13 +839,10 @@ __device__ int lsd_refine(const LsdFrame& F, const LsdFrame& Fm, int& n, double&
             }
         }
         cnt_in += __popc(__ballot_sync(FULL, inside));
-#pragma unroll 2
-        for (int j = 0; j < 32; j++) {  // points outside contribute +0.0
-            sum = __dadd_rn(sum, __shfl_sync(FULL, ang_d, j));
-            s_sum = __dadd_rn(s_sum, __shfl_sync(FULL, ang_d2, j));
-        }
+        lsd_ordered_add32(a_scratch, lane, ang_d, ang_d2, 0.0, acc);  // points outside contribute +0.0
     }
     __syncwarp();
+    const double sum = __shfl_sync(FULL, acc, 0), s_sum = __shfl_sync(FULL, acc, 1);
     const double mean_angle = sum / (double)cnt_in;
     const double tau = 2.0 * sqrt(__dadd_rn(__dsub_rn(s_sum, __dmul_rn(__dmul_rn(2.0, mean_angle), sum)) / (double)cnt_in,
                                             __dmul_rn(mean_angle, mean_angle)));
@@ -1130,7 +1145,7 @@ __device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restr
     const int lane = threadIdx.x & 31;
     LsdFrame F;
     F.ang = ang;
-    F.g2 = nullptr; F.rec = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr;
+    F.g2 = nullptr; F.rec = nullptr; F.cs0 = nullptr; F.sval = nullptr; F.used_bits = nullptr; F.reg = nullptr; F.ring = nullptr; F.scratch = nullptr;
     F.W = g.W; F.H = g.H;
     F.sparse = false; F.dir = nullptr; F.rev = nullptr; F.pool = nullptr; F.ntiles = nullptr; F.tw = 0; F.pool_tiles = 0;
     F.bits = nullptr; F.touched = nullptr; F.touched_buf = nullptr; F.reg_cap = 0; F.touched_cap = 0;
@@ -1151,75 +1166,19 @@ __device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restr
     __syncwarp();
 }
 
-constexpr int kMaxGrowers = 16;    // grower warps per CTA
-constexpr int kMaxFrameSlots = 4;  // frames a CTA works on at once
-constexpr int kSlots = 256;        // ticket slots per frame (the window of uncommitted tickets is at most this)
-constexpr int kPool = 64;          // region buffers per CTA
 constexpr int kSmall = 64;         // regions up to this size (and log length) are parked in their slot's small buffer instead
 constexpr int kTiny = 16;          // regions without a rectangle up to this size never leave shared memory: the points sit in their ticket slot
 constexpr int kSvalEntries = 36;
 constexpr int kMaxPoolTiles = 64, kMinPoolTiles = 24;
-// shared memory of a grower warp: sval | ring | tile pool | rev | dir | ntiles, each part 16-byte aligned
-struct GrowSmem {
-    int tiles, pool_tiles;
-    int window;       // tickets that may be uncommitted at once (<= kSlots): deeper speculation wastes more growth
-    int frame_slots;  // frames per CTA
-    int bits_words;   // words of a W*H bitmap
-    int tail_nfa;     // CTAs without frames validate rectangles of finished frames
-    int poll_ns;      // sleep of a warp that found nothing to do before it looks again
-    __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
-    __host__ __device__ size_t off_pool() const { return off_ring() + kRegRing * sizeof(unsigned int); }
-    __host__ __device__ size_t off_rev() const { return off_pool() + (size_t)pool_tiles * 32 * sizeof(unsigned int); }
-    __host__ __device__ size_t off_dir() const { return off_rev() + (((size_t)pool_tiles * sizeof(unsigned short) + 15) & ~(size_t)15); }
-    __host__ __device__ size_t off_ntiles() const { return off_dir() + (((size_t)tiles + 15) & ~(size_t)15); }
-    __host__ __device__ size_t per_grower() const { return off_ntiles() + 16; }
-    // per frame slot: ticket slots | committed bitmap | tiny regions (kTiny points per ticket slot)
-    __host__ __device__ size_t off_tiny() const { return kSlots * sizeof(int4) + (((size_t)bits_words * sizeof(unsigned int) + 15) & ~(size_t)15); }
-    __host__ __device__ size_t per_frame() const { return off_tiny() + (size_t)kSlots * kTiny * sizeof(unsigned int); }
-    __host__ __device__ size_t total(int growers) const { return (size_t)frame_slots * per_frame() + (size_t)growers * per_grower(); }
-};
 // ticket slot (shared memory, int4): x = seed pixel, y = region size, z = touched-log size,
 // w = state | (status + 2) << 8 | (buffer + 1) << 16   (buffer -1 with status >= 0: the slot's small buffer)
 enum { kSlotFree = 0, kSlotReady = 1, kSlotGrowing = 2, kSlotDone = 3 };
-enum { kActNone = 0, kActCommit, kActIssue, kActTake, kActBuffer, kActInit, kActFinish, kActExit };
 enum { kStDeferred = -2, kStCapacity = -1, kStNoRect = 0, kStRect = 1 };
-enum { kFrameEmpty = 0, kFrameBusy = 1, kFrameRunning = 2, kFrameNoMore = 3 };
 __device__ __forceinline__ int slot_pack(int state, int status, int buf) { return state | ((status + 2) << 8) | ((buf + 1) << 16); }
-struct GrowCtl {  // one per frame slot
-    int active;       // kFrame*
-    int sel_lock, com_lock;
-    int next_pos;     // next position of the seed list to look at
-    int ticket_next;  // tickets issued
-    int grow_next;    // tickets handed to a grower
-    int commit_head;  // tickets committed
-    int head;         // rectangles queued
-    int all_issued;   // the seed list is exhausted
-    int frame, ns;
-    long long t_start;
-    unsigned long long stat[8];  // committed, void, regrown, deferred, growth cycles, given-up cycles, commit cycles, regrow cycles
-};
-struct GrowConfig {
-    int growers = 0, pool_tiles = 0, frame_slots = 1;
-};
 struct GrowResult {
     int status, n, nt;
     LsdRect rec;
 };
-__device__ __forceinline__ bool warp_try_lock(int* lock, int lane) {
-    int got = 0;
-    if (lane == 0) got = atomicCAS(lock, 0, 1) == 0;
-    got = __shfl_sync(0xffffffffu, got, 0);
-    if (got) __threadfence_block();
-    return got != 0;
-}
-// a warp-uniform decision from a condition that reads state other warps change: lane 0 decides
-#define WARP_UNIFORM(cond) (__shfl_sync(0xffffffffu, (lane == 0) ? (int)(cond) : 0, 0) != 0)
-__device__ __forceinline__ void warp_unlock(int* lock, int lane) {
-    __syncwarp();
-    __threadfence_block();
-    if (lane == 0) atomicExch(lock, 0);
-    __syncwarp();
-}
 __device__ __forceinline__ int pool_pop(unsigned long long* mask, int lane) {
     int b = -1;
     if (lane == 0) {
@@ -1297,465 +1256,6 @@ struct GrowBufs {
     int* nfa_ctl;             // [0] items published (tail), [1] items taken (cursor), [2] frames finished
     NfaTabs nfa_tabs;
 };
-
-// A CTA works on up to gs.frame_slots frames at once and its warps take whatever work any of them offers, so a warp
-// that would wait (the window of a frame is full, nothing is ready, the head region is still growing) works on
-// another frame instead.  Frames are handed out through a global counter.
-// Two instantiations: kBound = 256 (up to 8 growers, all the registers they want: single-frame latency) and kBound = 512
-// (up to 16 growers at 128 registers: throughput over many frames).
-template <int kBound>
-__global__ void __launch_bounds__(kBound, 1) k_lsd_grow(LineGeom g, GrowSmem gs, int nf, GrowBufs B) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ GrowCtl s_ctl[kMaxFrameSlots];
-    __shared__ LsdFrame s_view[kMaxGrowers];    // the frame view a warp hands to lsd_grow_seed
-    __shared__ GrowResult s_res[kMaxGrowers];
-    __shared__ unsigned long long s_free_mask;  // free buffers of the pool
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 5;
-    const unsigned FULL = 0xffffffffu;
-    const int FS = gs.frame_slots;
-    const size_t plane = B.plane;
-    unsigned char* s_mine = s_raw + (size_t)FS * gs.per_frame() + (size_t)warp * gs.per_grower();
-    const size_t cta_fs = (size_t)blockIdx.x * FS;
-    unsigned int* my_pool_reg = B.pool_reg + (size_t)blockIdx.x * kPool * kSpecCap;
-    unsigned int* my_pool_touched = B.pool_touched + (size_t)blockIdx.x * kPool * kSpecCap;
-    LsdRect* my_pool_rect = B.pool_rect + (size_t)blockIdx.x * kPool;
-    LsdFrame F;
-    F.sval = reinterpret_cast<float2*>(s_mine);
-    F.ring = reinterpret_cast<unsigned int*>(s_mine + gs.off_ring());
-    F.pool = reinterpret_cast<unsigned int*>(s_mine + gs.off_pool());
-    F.rev = reinterpret_cast<unsigned short*>(s_mine + gs.off_rev());
-    F.dir = s_mine + gs.off_dir();
-    F.ntiles = reinterpret_cast<int*>(s_mine + gs.off_ntiles());
-    F.tw = (g.W + 31) >> 5;
-    F.pool_tiles = gs.pool_tiles;
-    F.sparse = true;
-    F.bits = nullptr;
-    F.ticket = 0;
-    F.W = g.W;
-    F.H = g.H;
-    F.reg = nullptr;
-    F.touched = nullptr;
-    F.touched_buf = nullptr;
-    F.reg_cap = F.touched_cap = 0;
-    #pragma unroll 1
-    for (int i = lane; i < gs.tiles; i += 32) F.dir[i] = 0xffu;
-    if (lane == 0) *F.ntiles = 0;
-    if (threadIdx.x < kMaxFrameSlots) s_ctl[threadIdx.x].active = threadIdx.x < FS ? kFrameEmpty : kFrameNoMore;
-    if (threadIdx.x == 0) s_free_mask = ~0ull << G;  // buffer w starts with warp w
-    __syncthreads();
-    int mybuf = warp, rr = warp % FS;
-    GrowResult res;
-    while (true) {
-        // ---------------- what to do next (a tight loop: idle warps must not thrash the instruction cache) ----------------
-        int action = kActNone, fsi = 0;
-        while (true) {
-            if (lane == 0) {
-                int nomore = 0;
-                for (int k = 0; k < FS && action == kActNone; k++) {
-                    const int cand = rr + k < FS ? rr + k : rr + k - FS;
-                    volatile GrowCtl* c = &s_ctl[cand];
-                    volatile int4* sl = reinterpret_cast<volatile int4*>(s_raw + (size_t)cand * gs.per_frame());
-                    const int st = c->active;
-                    if (st == kFrameNoMore) { nomore++; continue; }
-                    if (st == kFrameEmpty) {
-                        // fair start: a CTA fills its k-th frame slot only after every CTA had the chance to fill k - 1
-                        // slots, so that the frames spread evenly over the SMs instead of going to the CTAs that start first
-                        if (cand == 0 || *(volatile int*)B.frame_counter >= cand * (int)gridDim.x) { action = kActInit; fsi = cand; break; }
-                        continue;
-                    }
-                    if (st != kFrameRunning) continue;
-                    const int h = c->commit_head, tn = c->ticket_next, gn = c->grow_next, ai = c->all_issued;
-                    if (ai && h == tn) action = kActFinish;
-                    else if (h < tn && (sl[h % kSlots].w & 0xff) == kSlotDone && c->com_lock == 0) action = kActCommit;
-                    else if (mybuf >= 0 && gn < tn) action = kActTake;
-                    else if (!ai && tn - gn < G && tn - h < gs.window && c->sel_lock == 0) action = kActIssue;
-                    if (action != kActNone) fsi = cand;
-                }
-                if (action == kActNone) {
-                    if (nomore == FS) action = kActExit;
-                    else if (mybuf < 0 && *(volatile unsigned long long*)&s_free_mask != 0) action = kActBuffer;
-                }
-            }
-            action = __shfl_sync(FULL, action, 0);
-            if (action != kActNone) break;
-            __nanosleep(gs.poll_ns);
-        }
-        if (action == kActExit) {
-            // no frame left for this CTA: validate rectangles of finished frames while other CTAs are still growing.  Once every
-            // frame is finished the kernel should end: k_lsd_nfa then validates what is left with the whole GPU.
-            bool quit = nf <= (int)gridDim.x || !gs.tail_nfa;  // one frame per CTA at most: there is no tail worth filling
-            while (!quit) {
-                int it = 0;
-                if (lane == 0) it = atomicAdd(B.nfa_ctl + 1, 1);
-                it = __shfl_sync(FULL, it, 0);
-                unsigned item = 0xffffffffu;
-                while (true) {  // the item may not be published yet
-                    if (lane == 0) {
-                        if (*(volatile int*)(B.nfa_ctl + 2) >= nf) item = 0xfffffffeu;  // every frame finished: stop helping
-                        else if (it < *(volatile int*)(B.nfa_ctl + 0)) item = *(volatile unsigned int*)(B.nfa_items + it);
-                    }
-                    item = __shfl_sync(FULL, item, 0);
-                    if (item != 0xffffffffu) break;
-                    __nanosleep(1000);
-                }
-                if (item == 0xfffffffeu) break;
-                __threadfence();
-                const int fi = (int)(item / kNfaChunksPerFrame), ch = (int)(item % kNfaChunksPerFrame);
-                const int nr = min(B.n_rects[fi], g.seg_cap);
-                for (int t = ch * kNfaChunk; t < min(nr, (ch + 1) * kNfaChunk); t++)
-                    lsd_nfa_one(g, B.angdeg + (size_t)fi * plane, B.queue, B.qres, B.qvalid, B.nfa_tabs, fi, t);
-            }
-            break;
-        }
-        fsi = __shfl_sync(FULL, fsi, 0);
-        rr = fsi + 1 < FS ? fsi + 1 : 0;
-        if (action == kActBuffer) {
-            mybuf = pool_pop(&s_free_mask, lane);
-            continue;
-        }
-        GrowCtl* ctlp = &s_ctl[fsi];
-        volatile GrowCtl* ctl = ctlp;
-        volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_raw + (size_t)fsi * gs.per_frame());
-        unsigned int* s_used = reinterpret_cast<unsigned int*>(s_raw + (size_t)fsi * gs.per_frame() + kSlots * sizeof(int4));
-        unsigned int* s_tiny = reinterpret_cast<unsigned int*>(s_raw + (size_t)fsi * gs.per_frame() + gs.off_tiny());
-        const volatile unsigned int* vused = s_used;
-        if (action == kActInit || action == kActFinish) {
-            // a finished frame is closed, and the slot gets the next frame, by one warp that holds both locks
-            bool mine;
-            if (action == kActInit) {
-                mine = WARP_UNIFORM(atomicCAS(&ctlp->active, kFrameEmpty, kFrameBusy) == kFrameEmpty);
-            } else {
-                mine = warp_try_lock(&ctlp->com_lock, lane);
-                if (mine && !warp_try_lock(&ctlp->sel_lock, lane)) {
-                    warp_unlock(&ctlp->com_lock, lane);
-                    mine = false;
-                }
-                if (mine) {
-                    const bool done = WARP_UNIFORM(ctl->active == kFrameRunning && ctl->all_issued && ctl->commit_head == ctl->ticket_next);
-                    if (!done) {
-                        warp_unlock(&ctlp->sel_lock, lane);
-                        warp_unlock(&ctlp->com_lock, lane);
-                        mine = false;
-                    }
-                }
-                if (mine && lane == 0) {
-                    ctl->active = kFrameBusy;
-                    const int f = ctl->frame;
-                    B.n_rects[f] = ctl->head;
-                    __threadfence();
-                    if (B.phase_cycles) {
-                        long long* pc = B.phase_cycles + (size_t)f * 8;
-                        pc[0] = (long long)((ctl->stat[4] / 1000) + ((ctl->stat[7] / 1000) << 20) + ((ctl->stat[5] / 1000) << 40));
-                        pc[1] = clock64() - ctl->t_start;
-                        pc[2] = (long long)ctl->stat[6];
-                        pc[3] = ctl->ticket_next;
-                        pc[4] = (long long)ctl->stat[2];
-                        pc[5] = (long long)ctl->stat[0];
-                        pc[6] = (long long)ctl->stat[3];
-                        pc[7] = (long long)ctl->stat[1];
-                    }
-                }
-                __syncwarp();
-                if (mine) {  // publish the frame's rectangles for the tail helpers, then count the frame as finished
-                    const int fdone = __shfl_sync(FULL, ctl->frame, 0), nr = min(__shfl_sync(FULL, ctl->head, 0), g.seg_cap);
-                    const int nchunks = (nr + kNfaChunk - 1) / kNfaChunk;
-                    if (nchunks > 0 && nchunks <= kNfaChunksPerFrame) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(B.nfa_ctl + 0, nchunks);
-                        base = __shfl_sync(FULL, base, 0);
-                        for (int i = lane; i < nchunks; i += 32) B.nfa_items[base + i] = (unsigned)fdone * kNfaChunksPerFrame + (unsigned)i;
-                    }
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) atomicAdd(B.nfa_ctl + 2, 1);
-                }
-            }
-            if (!mine) continue;
-            int f = 0;
-            if (lane == 0) f = atomicAdd(B.frame_counter, 1);
-            f = __shfl_sync(FULL, f, 0);
-            if (f < nf) {
-                #pragma unroll 1
-                for (int i = lane; i < kSlots; i += 32) s_slot[i].w = slot_pack(kSlotFree, 0, -1);
-                #pragma unroll 1
-                for (int i = lane; i < gs.bits_words; i += 32) s_used[i] = 0;
-                if (lane == 0) {
-                    ctl->next_pos = ctl->ticket_next = ctl->grow_next = ctl->commit_head = 0;
-                    ctl->head = 0;
-                    ctl->all_issued = 0;
-                    ctl->frame = f;
-                    ctl->ns = B.n_seeds[f];
-                    ctl->t_start = clock64();
-                    for (int k = 0; k < 8; k++) ctl->stat[k] = 0;
-                }
-            }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) {
-                ctl->sel_lock = 0;
-                ctl->com_lock = 0;
-                __threadfence_block();
-                ctl->active = f < nf ? kFrameRunning : kFrameNoMore;
-            }
-            __syncwarp();
-            continue;
-        }
-        // ---------------- commit duty: strictly in ticket order ----------------
-        if (action == kActCommit && warp_try_lock(&ctlp->com_lock, lane)) {
-            const long long t0 = clock64();
-            const int f = __shfl_sync(FULL, ctl->frame, 0);
-            F.ang = B.angdeg + (size_t)f * plane;
-            F.g2 = B.g2 + (size_t)f * plane;
-            F.rec = B.rec + (size_t)f * plane;
-            F.cs0 = B.cs0 + (size_t)f * plane;
-            F.used_bits = s_used;
-            F.commit_head = &ctlp->commit_head;
-            LsdQueueItem* q = B.queue + (size_t)f * g.seg_cap;
-            const unsigned int* my_small = B.small_buf + (cta_fs + fsi) * kSlots * 2 * kSmall;
-            const LsdRect* my_small_rect = B.small_rect + (cta_fs + fsi) * kSlots;
-            while (true) {
-                const int h = __shfl_sync(FULL, ctl->commit_head, 0);
-                volatile int4* sl = &s_slot[h % kSlots];
-                if (!WARP_UNIFORM(ctl->active == kFrameRunning && h < ctl->ticket_next && (sl->w & 0xff) == kSlotDone)) break;
-                __threadfence_block();
-                const int pix = sl->x, w = sl->w;
-                int n = sl->y, nt = sl->z, status = ((w >> 8) & 0xff) - 2;
-                const int buf = ((w >> 16) & 0xff) - 1;
-                int kind = 0;  // 0 committed, 1 void
-                if ((vused[pix >> 5] >> (pix & 31)) & 1u) {
-                    kind = 1;  // swallowed by an earlier region
-                } else {
-                    const unsigned int* rg = buf >= 0 ? my_pool_reg + (size_t)buf * kSpecCap : my_small + (size_t)(h % kSlots) * 2 * kSmall;
-                    bool redo = status < 0;
-                    // This section is serial per frame, and a region's points, log and rectangle live in global memory: the three
-                    // reads are issued together (one round trip instead of three dependent ones); the first 32 entries of the two
-                    // lists — all of them for most regions — and the rectangle (24 words, one per lane) stay in registers.
-                    unsigned rg0 = 0, tk0 = 0, rc0 = 0;
-                    // Most tickets are regions of a few pixels that get no rectangle (85 % of the commits): their points never left
-                    // shared memory (the grower parked them in the ticket slot), so this serial section does not touch global memory
-                    // for them; the accept log of such a region is its point list.
-                    const bool tiny = !redo && status == kStNoRect && buf < 0 && n <= kTiny && nt == n;
-                    if (tiny) {
-                        if (lane < n) rg0 = s_tiny[(h % kSlots) * kTiny + lane];
-                        bool conflict = false;
-                        if (lane < n) {
-                            const unsigned o = (rg0 >> 16) * (unsigned)g.W + (rg0 & 0xffffu);
-                            conflict = ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
-                        }
-                        redo = __any_sync(FULL, conflict);
-                    } else if (!redo) {
-                        const unsigned int* tk = buf >= 0 ? my_pool_touched + (size_t)buf * kSpecCap : rg + kSmall;
-                        if (lane < nt) tk0 = tk[lane];
-                        if (lane < n) rg0 = rg[lane];
-                        if (status == kStRect && lane < (int)(sizeof(LsdRect) / 4))
-                            rc0 = reinterpret_cast<const unsigned int*>(buf >= 0 ? &my_pool_rect[buf] : &my_small_rect[h % kSlots])[lane];
-                        bool conflict = false;
-                        if (lane < nt) {
-                            const unsigned o = (tk0 >> 16) * (unsigned)g.W + (tk0 & 0xffffu);
-                            conflict = ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
-                        }
-                        #pragma unroll 1
-                        for (int i = lane + 32; i < nt; i += 32) {
-                            const unsigned pp = tk[i];
-                            const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
-                            conflict |= ((vused[o >> 5] >> (o & 31)) & 1u) != 0;
-                        }
-                        redo = __any_sync(FULL, conflict);
-                    }
-                    const bool regrown = redo;
-                    LsdRect rec;
-                    if (redo) {  // everything before this ticket is committed: this growth is the sequential one
-                        const long long g0 = clock64();
-                        LsdFrame FS2 = F;
-                        FS2.sparse = false;
-                        FS2.bits = B.big_bits + (cta_fs + fsi) * gs.bits_words;
-                        FS2.reg = B.big_reg + (size_t)f * plane;
-                        FS2.touched = B.big_touched + (cta_fs + fsi) * 2 * plane;
-                        FS2.touched_buf = FS2.touched;
-                        FS2.reg_cap = (int)plane;
-                        FS2.touched_cap = (int)(2 * plane);
-                        FS2.ticket = h;
-                        __syncwarp();
-                        if (lane == 0) s_view[warp] = FS2;
-                        __syncwarp();
-                        lsd_grow_seed(s_view[warp], pix, g.min_reg_size, &s_res[warp]);
-                        res = s_res[warp];
-                        status = res.status;
-                        n = res.n;
-                        rec = res.rec;
-                        rg = FS2.reg;
-                        if (status < 0 && lane == 0) atomicOr(B.flags + f, 2);
-                        if (lane == 0) {
-                            ctl->stat[2]++;
-                            ctl->stat[7] += (unsigned long long)(clock64() - g0);
-                        }
-                    }
-                    if (status >= 0) {
-                        if (!regrown && lane < n) {
-                            const unsigned o = (rg0 >> 16) * (unsigned)g.W + (rg0 & 0xffffu);
-                            atomicOr(&s_used[o >> 5], 1u << (o & 31));
-                        }
-                        #pragma unroll 1
-                        for (int i = regrown ? lane : lane + 32; i < n; i += 32) {
-                            const unsigned pp = rg[i];
-                            const unsigned o = (pp >> 16) * (unsigned)g.W + (pp & 0xffffu);
-                            atomicOr(&s_used[o >> 5], 1u << (o & 31));
-                        }
-                        if (status == kStRect) {
-                            const int head = __shfl_sync(FULL, ctl->head, 0);
-                            if (head < g.seg_cap) {
-                                if (regrown) {
-                                    if (lane == 0) q[head].rec = rec;
-                                } else if (lane < (int)(sizeof(LsdRect) / 4)) {
-                                    reinterpret_cast<unsigned int*>(&q[head].rec)[lane] = rc0;
-                                }
-                                if (lane == 0) ctl->head = head + 1;
-                            } else if (lane == 0) {
-                                atomicOr(B.flags + f, 1);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) {
-                    ctl->stat[kind]++;
-                    if (buf >= 0) atomicOr(&s_free_mask, 1ull << buf);
-                    sl->w = slot_pack(kSlotFree, 0, -1);
-                    __threadfence_block();
-                    ctl->commit_head = h + 1;
-                }
-                __syncwarp();
-            }
-            if (lane == 0) ctl->stat[6] += (unsigned long long)(clock64() - t0);
-            warp_unlock(&ctlp->com_lock, lane);
-            continue;
-        }
-        // ---------------- issue tickets: one chunk of the seed list at a time ----------------
-        if (action == kActIssue && warp_try_lock(&ctlp->sel_lock, lane)) {
-            if (WARP_UNIFORM(ctl->active == kFrameRunning && !ctl->all_issued)) {
-                const int f = __shfl_sync(FULL, ctl->frame, 0), ns = __shfl_sync(FULL, ctl->ns, 0);
-                const unsigned int* sd = B.seeds + (size_t)f * plane;
-                int t = __shfl_sync(FULL, ctl->ticket_next, 0);
-                int pos = __shfl_sync(FULL, ctl->next_pos, 0);
-                bool full = false;
-                while (!full && pos < ns && t - __shfl_sync(FULL, ctl->grow_next, 0) < G) {
-                    const int idx = pos + lane;
-                    unsigned pix = 0;
-                    bool free_ = false;
-                    if (idx < ns) {
-                        pix = sd[idx];
-                        free_ = ((vused[pix >> 5] >> (pix & 31)) & 1u) == 0;
-                    }
-                    unsigned m = __ballot_sync(FULL, free_);
-                    int consumed = 32;  // seeds of this chunk that are dealt with
-                    while (m) {
-                        const int room = __shfl_sync(FULL, gs.window - (t - ctl->commit_head), 0);
-                        const int j = __ffs(m) - 1;
-                        if (room <= 0) { consumed = j; full = true; break; }
-                        m &= m - 1;
-                        const unsigned pj = __shfl_sync(FULL, pix, j);
-                        if (lane == 0) {
-                            volatile int4* sl = &s_slot[t % kSlots];
-                            sl->x = (int)pj;
-                            sl->y = 0;
-                            sl->z = 0;
-                            sl->w = slot_pack(kSlotReady, 0, -1);
-                            __threadfence_block();
-                            ctl->ticket_next = t + 1;
-                        }
-                        t++;
-                    }
-                    pos += consumed;
-                }
-                if (lane == 0) {
-                    ctl->next_pos = min(pos, ns);
-                    if (pos >= ns && !full) ctl->all_issued = 1;
-                }
-            }
-            warp_unlock(&ctlp->sel_lock, lane);
-            continue;
-        }
-        // ---------------- take the next ticket and grow it speculatively ----------------
-        if (action == kActTake) {
-            int my_ticket = -1;
-            if (lane == 0) {
-                while (true) {
-                    const int t = ctl->grow_next;
-                    if (ctl->active != kFrameRunning || t >= ctl->ticket_next) break;
-                    if (atomicCAS(&ctlp->grow_next, t, t + 1) == t) { my_ticket = t; break; }
-                }
-            }
-            my_ticket = __shfl_sync(FULL, my_ticket, 0);
-            if (my_ticket < 0) continue;
-            // the frame cannot finish before this ticket is committed: its identity is stable from here on
-            const int f = __shfl_sync(FULL, ctl->frame, 0);
-            volatile int4* sl = &s_slot[my_ticket % kSlots];
-            const int my_pix = sl->x;
-            // already swallowed, or stamped by an uncommitted earlier ticket (most likely being swallowed):
-            // not grown now; the committer decides when its turn comes
-            const unsigned short cl = (unsigned short)*(const volatile unsigned int*)&(B.rec + (size_t)f * plane)[my_pix].claim;
-            const unsigned d = (unsigned)(my_ticket - (int)cl) & 0xffffu;
-            const bool defer = WARP_UNIFORM((((vused[my_pix >> 5] >> (my_pix & 31)) & 1u) != 0) ||
-                                            (d != 0 && d <= (unsigned)(my_ticket - ctl->commit_head)));
-            if (defer) {
-                if (lane == 0) {
-                    atomicAdd(&ctlp->stat[3], 1ull);
-                    __threadfence_block();
-                    sl->w = slot_pack(kSlotDone, kStDeferred, -1);
-                }
-                __syncwarp();
-                continue;
-            }
-            F.ang = B.angdeg + (size_t)f * plane;
-            F.g2 = B.g2 + (size_t)f * plane;
-            F.rec = B.rec + (size_t)f * plane;
-            F.cs0 = B.cs0 + (size_t)f * plane;
-            F.used_bits = s_used;
-            F.commit_head = &ctlp->commit_head;
-            LsdFrame FS2 = F;
-            FS2.reg = my_pool_reg + (size_t)mybuf * kSpecCap;
-            FS2.touched = my_pool_touched + (size_t)mybuf * kSpecCap;
-            FS2.touched_buf = FS2.touched;
-            FS2.reg_cap = FS2.touched_cap = kSpecCap;
-            FS2.ticket = my_ticket;
-            const long long g0 = clock64();
-            __syncwarp();
-            if (lane == 0) s_view[warp] = FS2;
-            __syncwarp();
-            lsd_grow_seed(s_view[warp], my_pix, g.min_reg_size, &s_res[warp]);
-            res = s_res[warp];
-            // a large region keeps the buffer until it is committed; a small one moves to the slot's small buffer
-            const bool tiny = res.status == kStNoRect && res.n <= kTiny && res.nt == res.n;
-            if (tiny) {  // the ring still holds every point of such a region
-                if (lane < res.n) s_tiny[(my_ticket % kSlots) * kTiny + lane] = F.ring[lane];
-                __syncwarp();
-            }
-            const bool small = !tiny && res.status >= 0 && res.n <= kSmall && res.nt <= kSmall;
-            const bool keep = res.status >= 0 && !small && !tiny;
-            if (small) {
-                unsigned int* dst = B.small_buf + ((cta_fs + fsi) * kSlots + (size_t)(my_ticket % kSlots)) * 2 * kSmall;
-                #pragma unroll 1
-                for (int i = lane; i < res.n; i += 32) dst[i] = FS2.reg[i];
-                #pragma unroll 1
-                for (int i = lane; i < res.nt; i += 32) dst[kSmall + i] = FS2.touched[i];
-                if (lane == 0 && res.status == kStRect) B.small_rect[(cta_fs + fsi) * kSlots + (my_ticket % kSlots)] = res.rec;
-                __syncwarp();
-            }
-            if (lane == 0) {
-                atomicAdd(&ctlp->stat[4], (unsigned long long)(clock64() - g0));
-                if (res.status < 0) atomicAdd(&ctlp->stat[5], (unsigned long long)(clock64() - g0));
-                if (keep && res.status == kStRect) my_pool_rect[mybuf] = res.rec;
-                sl->y = res.n;
-                sl->z = res.nt;
-                __threadfence_block();
-                sl->w = slot_pack(kSlotDone, res.status, keep ? mybuf : -1);
-            }
-            __syncwarp();
-            if (keep) mybuf = pool_pop(&s_free_mask, lane);
-        }
-    }
-}
 
 }  // namespace pl
 #include "lsd_grow2.cuh"
@@ -2166,10 +1666,10 @@ struct pl_line {
     int* d_sticky = nullptr;  // capacity flags of the device-pointer API since the last pl_line_sync
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     int tail_nfa = 1;
-    GrowConfig cfg_few, cfg_many;  // up to one frame per SM / more frames than SMs
     // k_lsd_grow2 (role-specialised grower, one frame per CTA): shape for up to one frame per SM / for more frames than SMs
     struct Grow2Cfg { int threads = 0, occ = 0, pool_tiles = 0, pool_n = 0; size_t smem = 0; } g2_few, g2_many;
-    int grow_impl = 2, lookahead = 4;
+    int lookahead = 4;
+    bool force_many = false;  // test hook (PLSLAM_LSD_FORCE_MANY): the many-frames shape also for small batches
     int poll_ns = 400;
     int reserved_sms = 0;          // SMs the region grower leaves to the kernels of other streams (pl_line_set_reserved_sms)
     unsigned int* d_big_bits = nullptr;
@@ -2297,14 +1797,10 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
     {
-        // one CTA per SM; a CTA works on several frames at once when there are more frames than SMs
-        // The grower's CTAs are persistent and own their SM (all registers, almost all shared memory): a kernel of another stream
-        // only runs where no grower CTA sits.  reserved_sms keeps that many SMs free while there are more frames than SMs.
+        // One frame per CTA (k_lsd_grow2), several CTAs per SM when there are more frames than SMs.  The CTAs are persistent (frames
+        // come from a counter) but do not fill an SM: kernels of other streams run next to them on what is left.  reserved_sms only
+        // shrinks the grid.
         const int sms = std::max(1, h->num_sms - (nf > h->num_sms - h->reserved_sms ? h->reserved_sms : 0));
-        const bool many = nf > sms && h->cfg_many.growers > 0;
-        const GrowConfig& cf = many ? h->cfg_many : h->cfg_few;
-        GrowSmem gs{h->grow_tiles, cf.pool_tiles, std::min(h->grow_window, kSlots), cf.frame_slots, h->bits_words, h->tail_nfa, h->poll_ns};
-        const int ctas = std::min(nf, sms);
         PL_CUDA_TRY(cudaMemsetAsync(h->d_frame_counter, 0, sizeof(int), st));
         GrowBufs gb;
         gb.angdeg = h->d_ang; gb.g2 = h->d_g2; gb.rec = h->d_rec; gb.cs0 = h->d_cs0; gb.seeds = h->d_seeds; gb.n_seeds = h->d_nseeds;
@@ -2316,17 +1812,13 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_ctl, 0, 4 * sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
-        if (h->grow_impl == 2) {
-            // role-specialised grower: one frame per CTA, several CTAs per SM when there are more frames than SMs
-            const bool many2 = nf > sms && h->g2_many.threads > 0;
-            const pl_line::Grow2Cfg& c2 = many2 ? h->g2_many : h->g2_few;
-            Grow2Smem g2{h->grow_tiles, c2.pool_tiles, std::min(h->grow_window, kSlots2), h->lookahead, h->bits_words, h->tail_nfa, h->poll_ns, c2.pool_n};
-            const int ctas2 = std::min(nf, sms * std::max(1, c2.occ));
-            if (c2.threads <= 256 && c2.occ >= 2) k_lsd_grow2<256, 3><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
-            else if (c2.threads <= 512) k_lsd_grow2<512, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
-            else k_lsd_grow2<1024, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
-        } else if (cf.growers <= 8) k_lsd_grow<256><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
-        else k_lsd_grow<512><<<ctas, cf.growers * 32, gs.total(cf.growers), st>>>(G, gs, nf, gb);
+        const bool many2 = (nf > sms || h->force_many) && h->g2_many.threads > 0;
+        const pl_line::Grow2Cfg& c2 = many2 ? h->g2_many : h->g2_few;
+        Grow2Smem g2{h->grow_tiles, c2.pool_tiles, std::min(h->grow_window, kSlots2), h->lookahead, h->bits_words, h->tail_nfa, h->poll_ns, c2.pool_n};
+        const int ctas2 = std::min(nf, sms * std::max(1, c2.occ));
+        if (c2.threads <= 256 && c2.occ >= 2) k_lsd_grow2<256, 3><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
+        else if (c2.threads <= 512) k_lsd_grow2<512, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
+        else k_lsd_grow2<1024, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
     }
     k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
     launches += 2;
@@ -2477,53 +1969,14 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             // shared memory: per frame slot the ticket slots + committed bitmap, per grower the ring, the staging area
             // and the sparse private bitmap (a pool of 32x32-pixel tiles: the more, the fewer regions overflow)
             const int tiles = ((W + 31) / 32) * ((H + 31) / 32);
-            const size_t budget = prop.sharedMemPerBlockOptin > 8192 ? prop.sharedMemPerBlockOptin - 8192 : 0;  // static: control blocks, views, results
-            auto choose = [&](int fs, int max_g, GrowConfig* c) {
-                *c = GrowConfig{0, 0, fs};
-                for (int gN = max_g; gN >= 1 && c->growers == 0; gN--)
-                    for (int pN = kMaxPoolTiles; pN >= kMinPoolTiles; pN -= 8) {
-                        GrowSmem gs{tiles, pN, 0, fs, h->bits_words, 0, 400};
-                        if (gs.total(gN) <= budget) {
-                            c->growers = gN;
-                            c->pool_tiles = pN;
-                            break;
-                        }
-                    }
-            };
-            int g_few = 8, g_many = kMaxGrowers, fs_many = 3;  // (g_few <= 8: the 256-thread instantiation)
-            if (const char* ev = getenv("PLSLAM_LSD_GROWERS")) {  // tuning override: "<few>,<many>,<frame slots>"
-                int a = 0, b2 = 0, c2 = 0;
-                if (sscanf(ev, "%d,%d,%d", &a, &b2, &c2) == 3) {
-                    if (a >= 1 && a <= kMaxGrowers) g_few = a;
-                    if (b2 >= 1 && b2 <= kMaxGrowers) g_many = b2;
-                    if (c2 >= 1 && c2 <= kMaxFrameSlots) fs_many = c2;
-                }
-            }
-            choose(1, g_few, &h->cfg_few);
-            for (int fs = fs_many; fs >= 1 && h->cfg_many.growers < std::min(g_many, 4); fs--) choose(fs, g_many, &h->cfg_many);
-            if (const char* ev = getenv("PLSLAM_LSD_POOL_TILES")) {  // test hook: a tiny pool forces the overflow -> re-growth path
-                const int pt = atoi(ev);
-                if (pt >= 1 && pt <= kMaxPoolTiles) {
-                    h->cfg_few.pool_tiles = std::min(h->cfg_few.pool_tiles, pt);
-                    h->cfg_many.pool_tiles = std::min(h->cfg_many.pool_tiles, pt);
-                }
-            }
             h->grow_tiles = tiles;
             if (const char* ev = getenv("PLSLAM_LSD_TAIL_NFA")) h->tail_nfa = atoi(ev) != 0;
             if (const char* ev = getenv("PLSLAM_LSD_POLL_NS")) h->poll_ns = std::max(20, std::min(100000, atoi(ev)));
             if (const char* ev = getenv("PLSLAM_LSD_RESERVE_SMS")) h->reserved_sms = std::max(0, std::min(h->num_sms - 1, atoi(ev)));
             h->grow_window = 128;
-            if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots, atoi(ev)));
-            if (h->cfg_few.growers < 1) {
-                set_error("pl_line_create: a %dx%d image needs %zu bytes of shared memory for the region growers, the device offers %zu",
-                          max_cols, max_rows, GrowSmem{tiles, kMinPoolTiles, 0, 1, h->bits_words, 0, 400}.total(1), budget);
-                pl_line_destroy(h);
-                return PL_ERR_CAPACITY;
-            }
-            e = cudaFuncSetAttribute(k_lsd_grow<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lsd_grow<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots2, atoi(ev)));
             // ---- k_lsd_grow2: warps per CTA, CTAs per SM, private tile pool ----
-            if (const char* ev = getenv("PLSLAM_LSD_IMPL")) h->grow_impl = atoi(ev) == 1 ? 1 : 2;
+            if (const char* ev = getenv("PLSLAM_LSD_FORCE_MANY")) h->force_many = atoi(ev) != 0;
             if (const char* ev = getenv("PLSLAM_LSD_LOOKAHEAD")) h->lookahead = std::max(1, std::min(kSlots2, atoi(ev)));
             auto allow_smem = [&](const void* fn) {  // dynamic shared memory up to what the kernel's static part leaves
                 cudaFuncAttributes fa;
@@ -2578,23 +2031,18 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                     h->g2_many.pool_tiles = std::min(h->g2_many.pool_tiles, pt);
                 }
             }
-            if (h->grow_impl == 2 && h->g2_few.threads < 64) {
+            if (h->g2_few.threads < 64) {
                 set_error("pl_line_create: a %dx%d image does not leave shared memory for a sequencer and a grower warp", max_cols, max_rows);
                 pl_line_destroy(h);
                 return PL_ERR_CAPACITY;
             }
         }
     }
-    const size_t max_ctas = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1));
-    size_t max_fs = max_ctas * kMaxFrameSlots;
-    size_t pool_words = max_ctas * kPool * (size_t)kSpecCap, pool_rects = max_ctas * kPool, small_slots = max_fs * kSlots;
-    if (h->grow_impl == 2) {  // the buffers of k_lsd_grow2 are indexed by CTA
-        const size_t c_few = max_ctas, c_many = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1) * std::max(1, h->g2_many.occ));
-        pool_words = std::max(c_few * h->g2_few.pool_n, c_many * h->g2_many.pool_n) * (size_t)kSpecCap2;
-        pool_rects = std::max(c_few * h->g2_few.pool_n, c_many * h->g2_many.pool_n);
-        max_fs = std::max(c_few, c_many);
-        small_slots = max_fs * kSlots2;
-    }
+    // the buffers of k_lsd_grow2 are indexed by CTA
+    const size_t c_few = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1));
+    const size_t c_many = std::min<size_t>(B, (size_t)std::max(h->num_sms, 1) * std::max(1, h->g2_many.occ));
+    const size_t pool_rects = std::max(c_few * h->g2_few.pool_n, c_many * h->g2_many.pool_n), pool_words = pool_rects * (size_t)kSpecCap2;
+    const size_t max_fs = std::max(c_few, c_many), small_slots = max_fs * kSlots2;
     A(&h->d_spec_reg, pool_words);
     A(&h->d_spec_touched, pool_words);
     A(&h->d_pool_rect, pool_rects);
@@ -2810,7 +2258,7 @@ PL_API int pl_line_grow_phases(pl_line* h, int frame, long long* out16) {
     PL_CHECK_ARG(h && out16 && frame >= 0 && frame < h->last_batch);
     // out16 receives 16 values, see plslam_c.h
     PL_CUDA_TRY(cudaSetDevice(h->device));
-    const size_t stride = h->grow_impl == 2 ? 16 : 8;
+    const size_t stride = 16;
     for (int i = 8; i < 16; i++) out16[i] = 0;
     PL_CUDA_TRY(cudaMemcpyAsync(out16, h->d_phase + (size_t)frame * stride, sizeof(long long) * stride, cudaMemcpyDeviceToHost, h->stream));
     PL_CUDA_TRY(pl::stream_sync(h->stream));

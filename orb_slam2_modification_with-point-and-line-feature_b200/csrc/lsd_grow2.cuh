@@ -34,9 +34,13 @@ struct Grow2Smem {
     int bits_words;  // words of a W*H bitmap
     int tail_nfa, poll_ns;
     int pool_n;      // region buffers of this CTA
-    // per warp: sval | ring | tile pool | rev | dir | ntiles  (the sequencer re-grows with the full bitmap: no tile pool)
+    // per warp: sval | ring | scratch (3 x 32 doubles) | frame view | result | tile pool | rev | dir | ntiles
+    // (the sequencer re-grows with the full bitmap: no tile pool)
     __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
-    __host__ __device__ size_t off_pool() const { return off_ring() + kRegRing * sizeof(unsigned int); }
+    __host__ __device__ size_t off_scratch() const { return off_ring() + kRegRing * sizeof(unsigned int); }
+    __host__ __device__ size_t off_view() const { return off_scratch() + 96 * sizeof(double); }
+    __host__ __device__ size_t off_res() const { return off_view() + ((sizeof(LsdFrame) + 15) & ~(size_t)15); }
+    __host__ __device__ size_t off_pool() const { return off_res() + ((sizeof(GrowResult) + 15) & ~(size_t)15); }
     __host__ __device__ size_t off_rev() const { return off_pool() + (size_t)pool_tiles * 32 * sizeof(unsigned int); }
     __host__ __device__ size_t off_dir() const { return off_rev() + (((size_t)pool_tiles * sizeof(unsigned short) + 15) & ~(size_t)15); }
     __host__ __device__ size_t off_ntiles() const { return off_dir() + (((size_t)tiles + 15) & ~(size_t)15); }
@@ -69,13 +73,11 @@ struct Grow2Shared {
     GrowBufs B;
     int nf;
     unsigned long long stat[8];  // profiling: growers' cycles growing, waiting for a ticket, parking, given up | sequencer's
-    LsdFrame view[32];           // the frame view a warp hands to lsd_grow_seed
     struct Seq {                 // the sequencer's state while the kernel body runs a commit-time re-growth for it
         int t_next, head, base, n_rect, n_commit, n_void, n_regrow, n_defer, all_issued;
         unsigned done_mask;
         long long c_commit, c_regrow, c_issue, c_idle, t_start, g0;
     } seq;
-    GrowResult res[32];
 };
 __shared__ Grow2Shared g2s;
 
@@ -98,8 +100,8 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
     unsigned int* s_tiny = reinterpret_cast<unsigned int*>(s_raw + gs.off_tiny());
     volatile Grow2Ctl* ctl = &g2s.ctl;
     Grow2Ctl& s_ctl = g2s.ctl;
-    LsdFrame* s_view = g2s.view;
-    GrowResult* s_res = g2s.res;
+    LsdFrame* s_view = reinterpret_cast<LsdFrame*>(s_raw + gs.off_seq() + gs.off_view());   // [0]: the sequencer's own
+    GrowResult* s_res = reinterpret_cast<GrowResult*>(s_raw + gs.off_seq() + gs.off_res());
     unsigned int* my_pool_reg = B.pool_reg + (size_t)blockIdx.x * gs.pool_n * kSpecCap2;
     unsigned int* my_pool_touched = B.pool_touched + (size_t)blockIdx.x * gs.pool_n * kSpecCap2;
     LsdRect* my_pool_rect = B.pool_rect + (size_t)blockIdx.x * gs.pool_n;
@@ -165,6 +167,7 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
         LsdFrame F;
         F.sval = reinterpret_cast<float2*>(s_mine);
         F.ring = reinterpret_cast<unsigned int*>(s_mine + gs.off_ring());
+        F.scratch = reinterpret_cast<double*>(s_mine + gs.off_scratch());
         F.pool = nullptr; F.rev = nullptr; F.dir = nullptr; F.ntiles = nullptr;
         F.tw = (g.W + 31) >> 5;
         F.pool_tiles = 0;
@@ -408,12 +411,13 @@ __device__ __noinline__ int g2_grower(int f, int mybuf) {
     const volatile unsigned int* vused = reinterpret_cast<unsigned int*>(s_raw + gs.off_used());
     unsigned int* s_tiny = reinterpret_cast<unsigned int*>(s_raw + gs.off_tiny());
     volatile Grow2Ctl* ctl = &g2s.ctl;
-    LsdFrame* view = &g2s.view[warp];
-    GrowResult* res = &g2s.res[warp];
+    unsigned char* s_mine = s_raw + gs.off_growers() + (size_t)(warp - 1) * gs.per_grower();
+    LsdFrame* view = reinterpret_cast<LsdFrame*>(s_mine + gs.off_view());
+    GrowResult* res = reinterpret_cast<GrowResult*>(s_mine + gs.off_res());
     unsigned int* my_pool_reg = B.pool_reg + (size_t)blockIdx.x * gs.pool_n * kSpecCap2;
     unsigned int* my_pool_touched = B.pool_touched + (size_t)blockIdx.x * gs.pool_n * kSpecCap2;
     const LsdPix* rec = B.rec + (size_t)f * B.plane;
-    const unsigned int* ring = reinterpret_cast<unsigned int*>(s_raw + gs.off_growers() + (size_t)(warp - 1) * gs.per_grower() + gs.off_ring());
+    const unsigned int* ring = reinterpret_cast<unsigned int*>(s_mine + gs.off_ring());
     const int min_reg_size = g2s.g.min_reg_size, poll_ns = gs.poll_ns, W = g2s.g.W;
     const bool prof = B.phase_cycles != nullptr;
     if (lane == 0) {
@@ -532,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
             LsdFrame F;
             F.sval = reinterpret_cast<float2*>(s_mine);
             F.ring = reinterpret_cast<unsigned int*>(s_mine + gs_.off_ring());
+            F.scratch = reinterpret_cast<double*>(s_mine + gs_.off_scratch());
             F.pool = reinterpret_cast<unsigned int*>(s_mine + gs_.off_pool());
             F.rev = reinterpret_cast<unsigned short*>(s_mine + gs_.off_rev());
             F.dir = dir;
@@ -551,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
             F.used_bits = reinterpret_cast<unsigned int*>(s_raw + gs_.off_used());
             F.commit_head = &g2s.ctl.commit_head;
             F.ang = nullptr; F.g2 = nullptr; F.rec = nullptr; F.cs0 = nullptr;
-            g2s.view[warp] = F;
+            *reinterpret_cast<LsdFrame*>(s_mine + gs_.off_view()) = F;
         }
     }
     int mybuf = warp - 1;  // grower w starts with buffer w - 1
@@ -573,7 +578,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
         if (warp == 0) {
             int rq = g2_sequencer(f, 0);
             while (rq >= 0) {
-                lsd_grow_seed(g2s.view[0], rq, g_.min_reg_size, &g2s.res[0]);
+                lsd_grow_seed(*reinterpret_cast<LsdFrame*>(s_raw + gs_.off_seq() + gs_.off_view()), rq, g_.min_reg_size,
+                              reinterpret_cast<GrowResult*>(s_raw + gs_.off_seq() + gs_.off_res()));
                 rq = g2_sequencer(f, 1);
             }
         }
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
     }
     // no frame left for this CTA: validate rectangles of finished frames while other CTAs are still growing.  Once every frame is
     // finished the kernel ends: k_lsd_nfa then validates what is left with the whole GPU.
-    if (nf_ > (int)gridDim.x && gs_.tail_nfa) {
+    if (nf_ > 1 && gs_.tail_nfa) {
         while (true) {
             int it = 0;
             if (lane == 0) it = atomicAdd(B_.nfa_ctl + 1, 1);

@@ -86,12 +86,15 @@ def test_max_lines_parameter(api, synth, oracle):
 
 
 @pytest.mark.parametrize("env", [{"PLSLAM_LSD_POOL_TILES": "2"}, {"PLSLAM_LSD_POOL_TILES": "1", "PLSLAM_LSD_WINDOW": "1"},
-                                 {"PLSLAM_LSD_GROWERS": "1,1,1"}, {"PLSLAM_LSD_GROWERS": "12,12,4", "PLSLAM_LSD_WINDOW": "256"},
-                                 {"PLSLAM_LSD_GROWERS": "3,5,2", "PLSLAM_LSD_WINDOW": "7"}])
+                                 {"PLSLAM_LSD_GROW2": "64,64,1"}, {"PLSLAM_LSD_GROW2": "1024,384,2", "PLSLAM_LSD_WINDOW": "128", "PLSLAM_LSD_LOOKAHEAD": "32"},
+                                 {"PLSLAM_LSD_GROW2": "512,256,3", "PLSLAM_LSD_FORCE_MANY": "1"},
+                                 {"PLSLAM_LSD_GROW2": "128,160,4", "PLSLAM_LSD_WINDOW": "7", "PLSLAM_LSD_LOOKAHEAD": "1"},
+                                 {"PLSLAM_LSD_GROW2": "512,256,3", "PLSLAM_LSD_TAIL_NFA": "0", "PLSLAM_LSD_POLL_NS": "5000"}])
 def test_grower_configuration_does_not_change_the_result(env, api, synth, monkeypatch):
     """The speculative region grower must give the sequential result whatever its shape: number of grower
-    warps, frames per CTA, window of uncommitted tickets, and a private tile pool so small that most regions overflow and
-    are re-grown at commit time.  (The knobs are read when the extractor is created.)"""
+    warps per CTA (PLSLAM_LSD_GROW2 = threads for up to one frame per SM, threads and CTAs per SM for more), window of
+    uncommitted tickets, tickets issued ahead of the growers, and a private tile pool so small that most regions overflow
+    and are re-grown at commit time.  (The knobs are read when the extractor is created.)"""
     frames = synth.frames(4242, 5)
     ref = api.LineExtractor(max_batch=5)
     k0, d0, c0, n0 = ref.extract_batch(frames)
