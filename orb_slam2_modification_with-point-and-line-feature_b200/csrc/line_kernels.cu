@@ -1667,7 +1667,7 @@ struct pl_line {
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     int tail_nfa = 1;
     // k_lsd_grow2 (role-specialised grower, one frame per CTA): shape for up to one frame per SM / for more frames than SMs
-    struct Grow2Cfg { int threads = 0, occ = 0, pool_tiles = 0, pool_n = 0; size_t smem = 0; } g2_few, g2_many;
+    struct Grow2Cfg { int threads = 0, occ = 0, pool_tiles = 0, pool_n = 0, split = 0; size_t smem = 0; } g2_few, g2_many;
     int lookahead = 4;
     bool force_many = false;  // test hook (PLSLAM_LSD_FORCE_MANY): the many-frames shape also for small batches
     int poll_ns = 400;
@@ -1814,9 +1814,10 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
         const bool many2 = (nf > sms || h->force_many) && h->g2_many.threads > 0;
         const pl_line::Grow2Cfg& c2 = many2 ? h->g2_many : h->g2_few;
-        Grow2Smem g2{h->grow_tiles, c2.pool_tiles, std::min(h->grow_window, kSlots2), h->lookahead, h->bits_words, h->tail_nfa, h->poll_ns, c2.pool_n};
+        Grow2Smem g2{h->grow_tiles, c2.pool_tiles, std::min(h->grow_window, kSlots2), h->lookahead, h->bits_words, h->tail_nfa, h->poll_ns, c2.pool_n, c2.split};
         const int ctas2 = std::min(nf, sms * std::max(1, c2.occ));
         if (c2.threads <= 256 && c2.occ >= 2) k_lsd_grow2<256, 3><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
+        else if (c2.threads <= 384 && c2.occ >= 2) k_lsd_grow2<384, 2><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
         else if (c2.threads <= 512) k_lsd_grow2<512, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
         else k_lsd_grow2<1024, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
     }
@@ -1985,6 +1986,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes));
             };
             allow_smem((const void*)k_lsd_grow2<256, 3>);
+            allow_smem((const void*)k_lsd_grow2<384, 2>);
             allow_smem((const void*)k_lsd_grow2<512, 1>);
             allow_smem((const void*)k_lsd_grow2<1024, 1>);
             const size_t sm_smem = prop.sharedMemPerMultiprocessor;
@@ -2015,15 +2017,26 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
                 }
             }
             for (int t = t_few; t >= 64 && !h->g2_few.threads; t -= 32) choose2(t, 1, &h->g2_few);
-            if (t_many > 256) occ_many = 1;
+            if (t_many > 384) occ_many = 1;
+            else if (t_many > 256) occ_many = std::min(occ_many, 2);
             for (int oc = occ_many; oc >= 1 && !h->g2_many.threads; oc--)
                 for (int t = t_many; t >= 64 && !h->g2_many.threads; t -= 32) {
                     if (!choose2(t, oc, &h->g2_many)) continue;
                     int occ_real = 0;  // what the device really gives (registers count too)
-                    cudaError_t eo = oc >= 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k_lsd_grow2<256, 3>, t, h->g2_many.smem)
-                                             : cudaSuccess;
+                    cudaError_t eo = oc < 2 ? cudaSuccess
+                                     : t <= 256 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k_lsd_grow2<256, 3>, t, h->g2_many.smem)
+                                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k_lsd_grow2<384, 2>, t, h->g2_many.smem);
                     if (oc >= 2 && (eo != cudaSuccess || occ_real < oc)) h->g2_many = pl_line::Grow2Cfg{};
                 }
+            // a frame that is alone on its SM is bound by the sequencer: committing and issuing on a warp each
+            h->g2_few.split = h->g2_few.threads >= 128 ? 1 : 0;
+            if (const char* ev = getenv("PLSLAM_LSD_SPLIT")) {  // tuning override: "<few>,<many>"
+                int a = 0, b2 = 0;
+                if (sscanf(ev, "%d,%d", &a, &b2) == 2) {
+                    h->g2_few.split = a != 0 && h->g2_few.threads >= 96;
+                    h->g2_many.split = b2 != 0 && h->g2_many.threads >= 96;
+                }
+            }
             if (const char* ev = getenv("PLSLAM_LSD_POOL_TILES")) {
                 const int pt = atoi(ev);
                 if (pt >= 1 && pt <= kMaxPoolTiles) {

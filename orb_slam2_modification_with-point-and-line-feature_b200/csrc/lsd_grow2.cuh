@@ -34,6 +34,7 @@ struct Grow2Smem {
     int bits_words;  // words of a W*H bitmap
     int tail_nfa, poll_ns;
     int pool_n;      // region buffers of this CTA
+    int split;       // 1: warp 0 commits, warp 1 issues tickets, growers from warp 2 on; 0: warp 0 does both, growers from warp 1 on
     // per warp: sval | ring | scratch (3 x 32 doubles) | frame view | result | tile pool | rev | dir | ntiles
     // (the sequencer re-grows with the full bitmap: no tile pool)
     __host__ __device__ size_t off_ring() const { return kSvalEntries * sizeof(float2); }
@@ -59,6 +60,7 @@ struct Grow2Ctl {
     int grow_next;    // tickets claimed          (growers: atomicAdd)
     int commit_head;  // tickets committed        (sequencer writes)
     int frame_done;
+    int all_issued;   // the seed list is exhausted (the issuer, when it is a warp of its own)
     int frame, ns;
     unsigned long long free_mask;  // free region buffers
 };
@@ -86,6 +88,7 @@ __shared__ Grow2Shared g2s;
 // over a capacity, or in conflict with a region committed after its grower read the map): the kernel body calls lsd_grow_seed
 // with view[0] and comes back with resume = 1.  (The call is made there and not here so that this function contains no call:
 // with one, its loop state lived in local memory.)
+template <bool kProf, bool kIssue>
 __device__ __noinline__ int g2_sequencer(int f, int resume) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
@@ -115,9 +118,9 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
     int t_next = 0, head = 0, base = 0, n_rect = 0;
     int n_commit = 0, n_void = 0, n_regrow = 0, n_defer = 0;
     long long c_commit = 0, c_regrow = 0, c_issue = 0, c_idle = 0;
-    const bool prof = B.phase_cycles != nullptr;
+    constexpr bool prof = kProf;  // the clock64 accounting of pl_line_grow_phases is compiled into a copy of its own
     unsigned done_mask = 0;
-    bool all_issued = ns == 0;
+    bool all_issued = kIssue ? ns == 0 : false;
     if (resume) {
         t_next = Q.t_next; head = Q.head; base = Q.base; n_rect = Q.n_rect;
         n_commit = Q.n_commit; n_void = Q.n_void; n_regrow = Q.n_regrow; n_defer = Q.n_defer;
@@ -125,8 +128,13 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
         done_mask = Q.done_mask;
         all_issued = Q.all_issued != 0;
     }
-    unsigned pa = base + lane < ns ? sd[base + lane] : 0, pb = base + 32 + lane < ns ? sd[base + 32 + lane] : 0,
-             pc = base + 64 + lane < ns ? sd[base + 64 + lane] : 0, pd = base + 96 + lane < ns ? sd[base + 96 + lane] : 0;
+    unsigned pa = 0, pb = 0, pc = 0, pd = 0;
+    if (kIssue) {
+        pa = base + lane < ns ? sd[base + lane] : 0;
+        pb = base + 32 + lane < ns ? sd[base + 32 + lane] : 0;
+        pc = base + 64 + lane < ns ? sd[base + 64 + lane] : 0;
+        pd = base + 96 + lane < ns ? sd[base + 96 + lane] : 0;
+    }
     if (resume) {
         // the head ticket has just been grown by the kernel body (everything before it is committed: that growth is the sequential
         // one): write it to the map, queue its rectangle
@@ -192,6 +200,7 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
     __syncwarp();
     while (true) {
         bool progress = false;
+        if (!kIssue) t_next = ctl->ticket_next;  // (a slot read before its ticket's state is visible says Free: see the end of a run)
         // ---------------- commit the run of finished tickets at the head ----------------
         // The states of up to 32 slots are read at once and the fences are paid once per run: when the growers are ahead of the
         // sequencer (the case that matters) a ticket costs a few shared-memory round trips.
@@ -266,6 +275,9 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
                         if (buf >= 0 && lane == 0) atomicOr(&s_ctl.free_mask, 1ull << buf);
                         __syncwarp();
                         __threadfence_block();
+                        if (!kIssue && lane <= r) s_slot[(head + lane) & (kSlots2 - 1)].y = kSlotFree;
+                        __syncwarp();
+                        __threadfence_block();
                         head += r;
                         if (lane == 0) {
                             ctl->commit_head = head;  // (the claim rule of the grower compares stamps with it)
@@ -303,6 +315,9 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
                     if (buf >= 0 && lane == 0) atomicOr(&s_ctl.free_mask, 1ull << buf);
                     __syncwarp();  // the next ticket of the run reads the map this one wrote
                 }
+                // the slots go back to Free before the window moves on: a committer that is not the issuer must never take the Done of
+                // a slot's previous ticket for the state of its next one
+                if (!kIssue && lane < run) s_slot[(head + lane) & (kSlots2 - 1)].y = kSlotFree;
                 __syncwarp();
                 __threadfence_block();
                 head += run;
@@ -312,7 +327,7 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
             }
         }
         // ---------------- issue tickets: a burst of chunks of the seed list, published once ----------------
-        if (!all_issued) {
+        if (kIssue && !all_issued) {
             const long long i0 = prof ? clock64() : 0;
             int room = min(gs.window - (t_next - head), gs.lookahead - (t_next - ctl->grow_next));
             const int t0 = t_next;
@@ -352,7 +367,13 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
             if (t_next != t0 || chunks < 7) progress = true;
             if (prof) c_issue += clock64() - i0;
         }
-        if (all_issued && head == t_next) break;
+        if (kIssue) {
+            if (all_issued && head == t_next) break;
+        } else if (head == t_next && ctl->all_issued) {
+            __threadfence_block();
+            t_next = ctl->ticket_next;  // the final count: all_issued is written after it
+            if (head == t_next) break;
+        }
         if (!progress) {
             const long long i0 = prof ? clock64() : 0;
             __nanosleep(gs.poll_ns);
@@ -372,12 +393,12 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
             pc8[5] = n_commit;
             pc8[6] = n_defer;
             pc8[7] = n_void;
-            pc8[8] = c_issue;
+            pc8[8] = kIssue ? c_issue : (long long)g2s.stat[5];
             pc8[9] = c_idle;
             pc8[10] = (long long)g2s.stat[0];
             pc8[11] = (long long)g2s.stat[1];
             pc8[12] = (long long)g2s.stat[2];
-            pc8[13] = (blockDim.x >> 5) - 1;
+            pc8[13] = (blockDim.x >> 5) - 1 - gs.split;
             pc8[14] = (long long)g2s.stat[3];
             pc8[15] = (long long)g2s.stat[4];
         }
@@ -400,7 +421,78 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
     return -1;
 }
 
-// =============================== grower (warps 1 ..) ===============================
+// =============================== issuer (warp 1 when the sequencer's two duties are split) ===============================
+// Walks the seed list and gives every seed that is unused in the committed map the next ticket, as far as the window and the
+// growers' demand allow.  Committing and issuing are both serial per frame but independent of each other: on two warps a frame
+// that is alone on its SM (tracking mode) is no longer bound by their sum.
+template <bool kProf>
+__device__ __noinline__ void g2_issuer(int f) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    const Grow2Smem& gs = g2s.gs;
+    volatile int4* s_slot = reinterpret_cast<volatile int4*>(s_raw);
+    const volatile unsigned int* vused = reinterpret_cast<unsigned int*>(s_raw + gs.off_used());
+    volatile Grow2Ctl* ctl = &g2s.ctl;
+    const int ns = g2s.ctl.ns, window = gs.window, lookahead = gs.lookahead, poll_ns = gs.poll_ns;
+    const unsigned int* sd = g2s.B.seeds + (size_t)f * g2s.B.plane;
+    int t_next = 0, base = 0;
+    unsigned done_mask = 0;
+    long long c_issue = 0;
+    unsigned pa = lane < ns ? sd[lane] : 0, pb = 32 + lane < ns ? sd[32 + lane] : 0, pc = 64 + lane < ns ? sd[64 + lane] : 0,
+             pd = 96 + lane < ns ? sd[96 + lane] : 0;
+    bool all_issued = ns == 0;
+    while (!all_issued) {
+        const long long i0 = kProf ? clock64() : 0;
+        int room = min(window - (t_next - ctl->commit_head), lookahead - (t_next - ctl->grow_next));
+        const int t0 = t_next;
+        int chunks = 16;
+        while (room > 0 && chunks-- > 0) {
+            const bool isfree = base + lane < ns && !((done_mask >> lane) & 1u) && !((vused[pa >> 5] >> (pa & 31)) & 1u);
+            const unsigned m = __ballot_sync(FULL, isfree);
+            const int cnt = __popc(m);
+            const int take = min(cnt, room);
+            const int r = __popc(m & lt);
+            if (isfree && r < take) {
+                volatile int4* sl = &s_slot[(t_next + r) & (kSlots2 - 1)];
+                sl->x = (int)pa;
+                sl->y = kSlotReady;
+            }
+            t_next += take;
+            room -= take;
+            if (take < cnt) {  // the window / the look-ahead ends inside this chunk: the rest of it is looked at again later
+                const unsigned sel = __ballot_sync(FULL, isfree && r == take - 1);
+                done_mask |= (2u << (__ffs(sel) - 1)) - 1u;
+                break;
+            }
+            base += 32;
+            done_mask = 0;
+            pa = pb; pb = pc; pc = pd;
+            pd = base + 96 + lane < ns ? sd[base + 96 + lane] : 0;
+            if (base >= ns) {
+                all_issued = true;
+                break;
+            }
+        }
+        if (t_next != t0) {
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) ctl->ticket_next = t_next;
+        }
+        if (kProf) c_issue += clock64() - i0;
+        if (t_next == t0 && chunks >= 15 && !all_issued) __nanosleep(poll_ns);
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) {
+        if (kProf) g2s.stat[5] = (unsigned long long)c_issue;
+        ctl->all_issued = 1;
+    }
+    while (!ctl->frame_done) __nanosleep(1000);  // (the end-of-frame barrier is for every warp)
+}
+
+// =============================== grower ===============================
+template <bool kProf>
 __device__ __noinline__ int g2_grower(int f, int mybuf) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -411,7 +503,7 @@ __device__ __noinline__ int g2_grower(int f, int mybuf) {
     const volatile unsigned int* vused = reinterpret_cast<unsigned int*>(s_raw + gs.off_used());
     unsigned int* s_tiny = reinterpret_cast<unsigned int*>(s_raw + gs.off_tiny());
     volatile Grow2Ctl* ctl = &g2s.ctl;
-    unsigned char* s_mine = s_raw + gs.off_growers() + (size_t)(warp - 1) * gs.per_grower();
+    unsigned char* s_mine = s_raw + gs.off_growers() + (size_t)(warp - 1 - gs.split) * gs.per_grower();
     LsdFrame* view = reinterpret_cast<LsdFrame*>(s_mine + gs.off_view());
     GrowResult* res = reinterpret_cast<GrowResult*>(s_mine + gs.off_res());
     unsigned int* my_pool_reg = B.pool_reg + (size_t)blockIdx.x * gs.pool_n * kSpecCap2;
@@ -419,7 +511,7 @@ __device__ __noinline__ int g2_grower(int f, int mybuf) {
     const LsdPix* rec = B.rec + (size_t)f * B.plane;
     const unsigned int* ring = reinterpret_cast<unsigned int*>(s_mine + gs.off_ring());
     const int min_reg_size = g2s.g.min_reg_size, poll_ns = gs.poll_ns, W = g2s.g.W;
-    const bool prof = B.phase_cycles != nullptr;
+    constexpr bool prof = kProf;  // the clock64 accounting of pl_line_grow_phases is compiled into a copy of its own
     if (lane == 0) {
         view->ang = B.angdeg + (size_t)f * B.plane;
         view->g2 = B.g2 + (size_t)f * B.plane;
@@ -525,10 +617,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
         g2s.gs = gs_;
         g2s.B = B_;
         g2s.nf = nf_;
-        g2s.ctl.free_mask = (gs_.pool_n >= 64 ? ~0ull : ((1ull << gs_.pool_n) - 1ull)) & ~((1ull << (NW - 1)) - 1ull);
+        g2s.ctl.free_mask = (gs_.pool_n >= 64 ? ~0ull : ((1ull << gs_.pool_n) - 1ull)) & ~((1ull << (NW - 1 - gs_.split)) - 1ull);
     }
-    if (warp > 0) {  // the static part of a grower's frame view, and its empty private bitmap
-        unsigned char* s_mine = s_raw + gs_.off_growers() + (size_t)(warp - 1) * gs_.per_grower();
+    const int g0 = 1 + gs_.split;  // the first grower warp
+    if (warp >= g0) {  // the static part of a grower's frame view, and its empty private bitmap
+        unsigned char* s_mine = s_raw + gs_.off_growers() + (size_t)(warp - g0) * gs_.per_grower();
         unsigned char* dir = s_mine + gs_.off_dir();
         #pragma unroll 1
         for (int i = lane; i < gs_.tiles; i += 32) dir[i] = 0xffu;
@@ -559,31 +652,39 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
             *reinterpret_cast<LsdFrame*>(s_mine + gs_.off_view()) = F;
         }
     }
-    int mybuf = warp - 1;  // grower w starts with buffer w - 1
+    int mybuf = warp - g0;  // grower i starts with buffer i
     while (true) {
         __syncthreads();  // the previous frame is finished, every warp has left it
         if (threadIdx.x == 0) {
             const int fnext = atomicAdd(B_.frame_counter, 1);
             g2s.ctl.frame = fnext;
             g2s.ctl.ns = fnext < nf_ ? B_.n_seeds[fnext] : 0;
-            g2s.ctl.ticket_next = g2s.ctl.grow_next = g2s.ctl.commit_head = g2s.ctl.frame_done = 0;
+            g2s.ctl.ticket_next = g2s.ctl.grow_next = g2s.ctl.commit_head = g2s.ctl.frame_done = g2s.ctl.all_issued = 0;
             for (int k = 0; k < 8; k++) g2s.stat[k] = 0;
         }
         unsigned int* s_used = reinterpret_cast<unsigned int*>(s_raw + gs_.off_used());
         #pragma unroll 1
         for (int i = threadIdx.x; i < gs_.bits_words; i += blockDim.x) s_used[i] = 0;
+        if (threadIdx.x < kSlots2) reinterpret_cast<volatile int4*>(s_raw)[threadIdx.x].y = kSlotFree;
         __syncthreads();
         const int f = g2s.ctl.frame;
         if (f >= nf_) break;
+        const bool prof = B_.phase_cycles != nullptr;
         if (warp == 0) {
-            int rq = g2_sequencer(f, 0);
+            const bool sp = gs_.split != 0;
+            int rq = prof ? (sp ? g2_sequencer<true, false>(f, 0) : g2_sequencer<true, true>(f, 0))
+                          : (sp ? g2_sequencer<false, false>(f, 0) : g2_sequencer<false, true>(f, 0));
             while (rq >= 0) {
                 lsd_grow_seed(*reinterpret_cast<LsdFrame*>(s_raw + gs_.off_seq() + gs_.off_view()), rq, g_.min_reg_size,
                               reinterpret_cast<GrowResult*>(s_raw + gs_.off_seq() + gs_.off_res()));
-                rq = g2_sequencer(f, 1);
+                rq = prof ? (sp ? g2_sequencer<true, false>(f, 1) : g2_sequencer<true, true>(f, 1))
+                          : (sp ? g2_sequencer<false, false>(f, 1) : g2_sequencer<false, true>(f, 1));
             }
         }
-        else mybuf = g2_grower(f, mybuf);
+        else if (warp < g0) {
+            if (prof) g2_issuer<true>(f);
+            else g2_issuer<false>(f);
+        } else mybuf = prof ? g2_grower<true>(f, mybuf) : g2_grower<false>(f, mybuf);
     }
     // no frame left for this CTA: validate rectangles of finished frames while other CTAs are still growing.  Once every frame is
     // finished the kernel ends: k_lsd_nfa then validates what is left with the whole GPU.
