@@ -269,38 +269,47 @@ def run_ours(a, rank, world, local_rank, dist):
     p_kps, p_desc, p_n = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (d_kps, d_desc, d_n))
     p_kls, p_ldesc, p_lco, p_ln = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (d_kls, d_ldesc, d_lco, d_ln))
 
+    # e2e through the plugin's own host-buffer entry points (pl_orb_extract_batch / pl_line_extract_batch): pinned host images in,
+    # pinned host features out, the copies inside the calls.  The two extractors are called from two host threads, as the
+    # reference's Frame constructor does (Frame.cc:152-155).
+    import threading
+    hg = h_gray.numpy()
+    kp_np = p_kps.numpy().view(N.KP_DTYPE).reshape(F, cap)
+    dd_np, nn_np = p_desc.numpy(), p_n.numpy()
+    kl_np = p_kls.numpy().view(N.KL_DTYPE).reshape(F, MAXL)
+    ld_np, lc_np, ln_np = p_ldesc.numpy(), p_lco.numpy(), p_ln.numpy()
+
     class LinesLater:
-        """result() waits for the line extractor's stream and reads its outputs back (the line side of the glue asks for it)."""
+        """result() waits for the line extractor's thread (the line side of the glue asks for it)."""
+
+        def __init__(self):
+            self.err = []
+            self.th = threading.Thread(target=self.work)
+            self.th.start()
+
+        def work(self):
+            try:
+                gb.line.extract_batch_into(hg, MAXL, kl_np, ld_np, lc_np, ln_np)
+            except BaseException as e:
+                self.err.append(e)
 
         def result(self):
-            gb.line.sync()
-            for dst, src in ((p_kls, d_kls), (p_ldesc, d_ldesc), (p_lco, d_lco), (p_ln, d_ln)):
-                dst.copy_(src, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            kl = p_kls.numpy().view(N.KL_DTYPE).reshape(F, MAXL)
-            ld, lc, ln = p_ldesc.numpy(), p_lco.numpy(), p_ln.numpy()
-            return [(kl[i, :ln[i]], ld[i, :ln[i]], lc[i, :ln[i]]) for i in range(F)]
+            self.th.join()
+            if self.err:
+                raise self.err[0]
+            r = fe.FeatureList((kl_np[i, :ln_np[i]], ld_np[i, :ln_np[i]], lc_np[i, :ln_np[i]]) for i in range(F))
+            r.dense = (kl_np, ln_np)
+            return r
 
     def step_e2e():
-        # host images -> device ONCE (both extractors read the same upload), ORB first (short), the line extractor right behind
-        # it on its own stream; the ORB results come back and the point side of the caller glue proceeds while the line
-        # extractor is still running (the reference runs its two extractors in two threads for the same reason, Frame.cc:152-155)
-        e_gray.copy_(h_gray, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        gb.orb.extract_batch_dev(e_gray.data_ptr(), F, H, W, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
-        # the region grower of the line path fills every SM for tens of ms and no other kernel can share an SM with it: the
-        # line stream waits for the (short) ORB work, otherwise ORB's later kernels would queue behind it
-        ev_orb.record(s_orb)
-        s_line.wait_event(ev_orb)
-        gb.line.extract_batch_dev(e_gray.data_ptr(), F, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
-        gb.orb.sync()
-        for dst, src in ((p_kps, d_kps), (p_desc, d_desc), (p_n, d_n)):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        kp = p_kps.numpy().view(N.KP_DTYPE).reshape(F, cap)
-        dd, nn = p_desc.numpy(), p_n.numpy()
-        orb = [(kp[i, :nn[i]], dd[i, :nn[i]]) for i in range(F)]
-        return e2e_fe.run(h_gray.numpy(), depth, Tcw, sf, features=(orb, LinesLater()))
+        # ORB first (4-5 ms of device time), the line extractor right behind it on its own thread: next to the region grower's
+        # resident CTAs the ORB kernels would only get what is left of every SM and arrive later, and the point side of the glue
+        # needs them first
+        gb.orb.extract_batch_into(hg, kp_np, dd_np, nn_np)
+        lines_later = LinesLater()
+        orb = fe.FeatureList((kp_np[i, :nn_np[i]], dd_np[i, :nn_np[i]]) for i in range(F))
+        orb.dense = (kp_np, nn_np)
+        return e2e_fe.run(hg, depth, Tcw, sf, features=(orb, lines_later))
 
     def barrier():
         torch.cuda.synchronize()
@@ -447,9 +456,9 @@ def run_ours(a, rank, world, local_rank, dist):
         "p50_ms_per_frame": round(p50, 3),
         "p50_note": "streaming mode: one frame at a time, ORB || LSD+LBD extraction then SearchByProjection(Cur, Last); images resident in HBM",
         "step_breakdown_ms": {"extract": round(t_ext * 1e3, 2), "match": round(t_match * 1e3, 2), "matcher_calls": len(plan.calls)},
-        "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(F * W * H),
+        "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(2 * F * W * H),
                 "d2h_bytes_per_step": int(F * (cap * 60 + MAXL * (68 + 32 + 24) + 8)), "steps": e2e_steps,
-                "note": "host images uploaded once, both extractors through the device-pointer C ABI on their own streams, results read back to pinned host memory; caller glue (Frame-lite: numpy + the batched F-row calls of the library) and the point searches run on the SMs the line extractor's region grower leaves free while it is still working; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
+                "note": "through the plugin's host-buffer entry points: pl_orb_extract_batch and pl_line_extract_batch are called from two host threads (as the reference's Frame constructor calls its two extractors, Frame.cc:152-155) with pinned host images and pinned host outputs, each call doing its own upload (hence 2 x the image bytes) and read-back; caller glue (Frame-lite: numpy + the batched F-row calls of the library) and the point searches run while the line extractor is still working; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
         "gpu_launches": int(launches_per_step * a.steps),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "config3_kitti": kitti, "config5_sharded": c5,

@@ -86,16 +86,31 @@ class LastFrameView(C.Structure):
 
 
 def _addr(a):
-    return None if a is None else a.ctypes.data
+    if a is None:
+        return None
+    # (__array_interface__ is the cheap way to the address, except for structured dtypes, whose interface spells out the fields)
+    return a.ctypes.data if a.dtype.names else a.__array_interface__["data"][0]
+
+
+def _c(a, dt):
+    """np.ascontiguousarray(a, dt) without the call when `a` already is one (the glue builds hundreds of views per step)."""
+    if type(a) is np.ndarray and a.dtype == dt and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dt)
+
+
+def _tcw12(tcw):
+    t = _c(np.asarray(tcw).reshape(-1)[:12], np.float32)
+    return (C.c_float * 12).from_buffer_copy(t)
 
 
 def make_frame_view(keys_un, desc, u_right, claimed, bounds, K, tcw, scale_factors, keep):
     """keep: list that receives the arrays referenced by the view (lifetime)."""
-    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
-    desc = np.ascontiguousarray(desc, np.uint8)
-    u_right = np.ascontiguousarray(u_right, np.float32)
-    claimed = None if claimed is None else np.ascontiguousarray(claimed, np.int32)
-    sf = np.ascontiguousarray(scale_factors, np.float32)
+    keys_un = _c(keys_un, KP_DTYPE)
+    desc = _c(desc, np.uint8)
+    u_right = _c(u_right, np.float32)
+    claimed = None if claimed is None else _c(claimed, np.int32)
+    sf = _c(scale_factors, np.float32)
     keep += [keys_un, desc, u_right, claimed, sf]
     v = FrameView()
     v.n = len(keys_un)
@@ -103,20 +118,19 @@ def make_frame_view(keys_un, desc, u_right, claimed, bounds, K, tcw, scale_facto
     v.min_x, v.min_y, v.max_x, v.max_y = [float(b) for b in bounds]
     v.fx, v.fy, v.cx, v.cy, v.bf = float(K["fx"]), float(K["fy"]), float(K["cx"]), float(K["cy"]), float(K["bf"])
     v.b = float(np.float32(K["bf"]) / np.float32(K["fx"]))
-    t = np.asarray(tcw, np.float32).reshape(-1)[:12]
-    v.tcw = (C.c_float * 12)(*[float(x) for x in t])
+    v.tcw = _tcw12(tcw)
     v.n_levels = len(sf)
     v.scale_factors = _addr(sf)
     return v
 
 
 def make_mappoint_view(desc, in_view, proj_x, proj_y, proj_xr, level, view_cos, has_obs, keep):
-    desc = np.ascontiguousarray(desc, np.uint8)
-    in_view = np.ascontiguousarray(in_view, np.uint8)
-    px, py, pxr = (np.ascontiguousarray(a, np.float32) for a in (proj_x, proj_y, proj_xr))
-    level = np.ascontiguousarray(level, np.int32)
-    vc = np.ascontiguousarray(view_cos, np.float32)
-    ho = None if has_obs is None else np.ascontiguousarray(has_obs, np.uint8)
+    desc = _c(desc, np.uint8)
+    in_view = _c(in_view, np.uint8)
+    px, py, pxr = (_c(a, np.float32) for a in (proj_x, proj_y, proj_xr))
+    level = _c(level, np.int32)
+    vc = _c(view_cos, np.float32)
+    ho = None if has_obs is None else _c(has_obs, np.uint8)
     keep += [desc, in_view, px, py, pxr, level, vc, ho]
     v = MapPointView()
     v.n = len(in_view)
@@ -126,18 +140,17 @@ def make_mappoint_view(desc, in_view, proj_x, proj_y, proj_xr, level, view_cos, 
 
 
 def make_lastframe_view(valid, world_pos, desc, octave, angle, has_obs, tcw, keep):
-    valid = np.ascontiguousarray(valid, np.uint8)
-    wp = np.ascontiguousarray(world_pos, np.float32)
-    desc = np.ascontiguousarray(desc, np.uint8)
-    octave = np.ascontiguousarray(octave, np.int32)
-    angle = np.ascontiguousarray(angle, np.float32)
-    ho = None if has_obs is None else np.ascontiguousarray(has_obs, np.uint8)
+    valid = _c(valid, np.uint8)
+    wp = _c(world_pos, np.float32)
+    desc = _c(desc, np.uint8)
+    octave = _c(octave, np.int32)
+    angle = _c(angle, np.float32)
+    ho = None if has_obs is None else _c(has_obs, np.uint8)
     keep += [valid, wp, desc, octave, angle, ho]
     v = LastFrameView()
     v.n = len(valid)
     v.valid, v.world_pos, v.desc, v.octave, v.angle, v.has_observations = _addr(valid), _addr(wp), _addr(desc), _addr(octave), _addr(angle), _addr(ho)
-    t = np.asarray(tcw, np.float32).reshape(-1)[:12]
-    v.tcw = (C.c_float * 12)(*[float(x) for x in t])
+    v.tcw = _tcw12(tcw)
     return v
 
 
@@ -152,11 +165,11 @@ class LineFrameView(C.Structure):
 
 
 def make_mapline_view(start3d, end3d, kl, desc, valid, keep):
-    s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)
-    e3 = np.ascontiguousarray(end3d, np.float64).reshape(-1, 3)
-    kl = np.ascontiguousarray(kl, KL_DTYPE)
-    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
-    valid = np.ascontiguousarray(valid, np.uint8)
+    s3 = _c(start3d, np.float64).reshape(-1, 3)
+    e3 = _c(end3d, np.float64).reshape(-1, 3)
+    kl = _c(kl, KL_DTYPE)
+    desc = _c(desc, np.uint8).reshape(-1, 32)
+    valid = _c(valid, np.uint8)
     keep += [s3, e3, kl, desc, valid]
     v = MapLineView()
     v.n = len(kl)
@@ -165,15 +178,14 @@ def make_mapline_view(start3d, end3d, kl, desc, valid, keep):
 
 
 def make_lineframe_view(kl, desc, claimed, tcw, K, bounds, img_size, keep):
-    kl = np.ascontiguousarray(kl, KL_DTYPE)
-    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
-    claimed = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    kl = _c(kl, KL_DTYPE)
+    desc = _c(desc, np.uint8).reshape(-1, 32)
+    claimed = None if claimed is None else _c(claimed, np.uint8)
     keep += [kl, desc, claimed]
     v = LineFrameView()
     v.n = len(kl)
     v.kl, v.desc, v.claimed = _addr(kl), _addr(desc), _addr(claimed)
-    t = np.asarray(tcw, np.float32).reshape(-1)[:12]
-    v.tcw = (C.c_float * 12)(*[float(x) for x in t])
+    v.tcw = _tcw12(tcw)
     v.fx, v.fy, v.cx, v.cy = float(K["fx"]), float(K["fy"]), float(K["cx"]), float(K["cy"])
     v.min_x, v.min_y, v.max_x, v.max_y = [float(b) for b in bounds]
     v.cols, v.rows = int(img_size[0]), int(img_size[1])
@@ -187,14 +199,14 @@ class PosePointView(C.Structure):
 
 
 def make_posepoint_view(valid, world_pos, desc, min_dist_inv, max_dist_inv, max_dist, angle, normal, keep):
-    valid = np.ascontiguousarray(valid, np.uint8)
-    wp = np.ascontiguousarray(world_pos, np.float32).reshape(-1, 3)
-    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
-    mi = np.ascontiguousarray(min_dist_inv, np.float32)
-    ma = np.ascontiguousarray(max_dist_inv, np.float32)
-    mr = np.ascontiguousarray(max_dist, np.float32)
-    an = None if angle is None else np.ascontiguousarray(angle, np.float32)
-    no = None if normal is None else np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    valid = _c(valid, np.uint8)
+    wp = _c(world_pos, np.float32).reshape(-1, 3)
+    desc = _c(desc, np.uint8).reshape(-1, 32)
+    mi = _c(min_dist_inv, np.float32)
+    ma = _c(max_dist_inv, np.float32)
+    mr = _c(max_dist, np.float32)
+    an = None if angle is None else _c(angle, np.float32)
+    no = None if normal is None else _c(normal, np.float32).reshape(-1, 3)
     keep += [valid, wp, desc, mi, ma, mr, an, no]
     v = PosePointView()
     v.n = len(valid)
@@ -211,9 +223,9 @@ class BowView(C.Structure):
 
 def make_bow_view(angle, desc, valid, feat_vec, keep):
     """feat_vec: dict node id -> list of feature indices (DBoW2::FeatureVector); flattened in key order."""
-    angle = np.ascontiguousarray(angle, np.float32)
-    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
-    valid = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    angle = _c(angle, np.float32)
+    desc = _c(desc, np.uint8).reshape(-1, 32)
+    valid = None if valid is None else _c(valid, np.uint8)
     ids = sorted(feat_vec.keys())
     node_id = np.asarray(ids, np.uint32)
     off = np.zeros(len(ids) + 1, np.int32)
@@ -238,8 +250,8 @@ class TriangView(C.Structure):
 
 def make_triang_view(keys_un, desc, u_right, no_mappoint, feat_vec, keep):
     """no_mappoint[i] = 1 when the key frame holds no map point for feature i (the features offered for triangulation)."""
-    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
-    ur = np.ascontiguousarray(u_right, np.float32)
+    keys_un = _c(keys_un, KP_DTYPE)
+    ur = _c(u_right, np.float32)
     ang = np.ascontiguousarray(keys_un["angle"], np.float32)
     keep += [keys_un, ur]
     v = TriangView()

@@ -118,6 +118,19 @@ class ORBextractor:
         self._last = (min(n, self.max_batch) if n % self.max_batch == 0 else n % self.max_batch, rows, cols)
         return kps, desc, cnt
 
+    def extract_batch_into(self, frames, kps, desc, cnt):
+        """The host-pointer entry (pl_orb_extract_batch) with caller-owned outputs: kps (n, cap) KP_DTYPE, desc (n, cap, 32) uint8,
+        cnt (n,) int32 — e.g. views of pinned memory, so that the copies inside the call are asynchronous DMA."""
+        fr = np.asarray(frames)
+        assert fr.dtype == np.uint8 and fr.ndim == 3 and fr.strides[2] == 1
+        n, rows, cols = fr.shape
+        cap = kps.shape[1]
+        assert kps.shape[0] >= n and desc.shape[:2] == kps.shape[:2] and len(cnt) >= n
+        check(N.lib().pl_orb_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols),
+                                           C.c_size_t(fr.strides[1]), C.c_size_t(fr.strides[0]), ptr(kps), ptr(desc),
+                                           C.c_int(cap), ptr(cnt)))
+        self._last = (min(n, self.max_batch) if n % self.max_batch == 0 else n % self.max_batch, rows, cols)
+
     def extract_batch_dev(self, d_gray, n, rows, cols, step, frame_stride, d_kps, d_desc, cap, d_nout):
         """All pointers are raw device addresses (ints); asynchronous on the handle's stream."""
         check(N.lib().pl_orb_extract_batch_dev(self._h, ptr(d_gray), C.c_int(n), C.c_int(rows), C.c_int(cols),
@@ -203,6 +216,16 @@ class LineExtractor:
         check(N.lib().pl_line_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(fr.strides[1]),
                                             C.c_size_t(fr.strides[0]), C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), ptr(cnt)))
         return kls, desc, co, cnt
+
+    def extract_batch_into(self, frames, max_lines, kls, desc, co, cnt):
+        """pl_line_extract_batch with caller-owned outputs (kls (n, max_lines) KL_DTYPE, desc (n, max_lines, 32), co (n, max_lines, 3)
+        float64, cnt (n,) int32)."""
+        fr = np.asarray(frames)
+        assert fr.dtype == np.uint8 and fr.ndim == 3 and fr.strides[2] == 1
+        n, rows, cols = fr.shape
+        assert kls.shape == (n, max_lines) and desc.shape == (n, max_lines, 32) and co.shape == (n, max_lines, 3) and len(cnt) >= n
+        check(N.lib().pl_line_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(fr.strides[1]),
+                                            C.c_size_t(fr.strides[0]), C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), ptr(cnt)))
 
     def extract_batch_dev(self, d_gray, n, rows, cols, step, frame_stride, max_lines, d_kls, d_desc, d_coef, d_nout):
         check(N.lib().pl_line_extract_batch_dev(self._h, ptr(d_gray), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(step),

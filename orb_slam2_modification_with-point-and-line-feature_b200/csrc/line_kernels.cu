@@ -2215,9 +2215,13 @@ PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, 
     h->last_launches = 0;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
-        for (int f = 0; f < nf; f++)
-            PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride, step,
-                                          cols, rows, cudaMemcpyHostToDevice, h->stream));
+        // one copy per chunk when the caller's frames are dense and already have the staging pitch, else one strided copy per frame
+        if (step == in_pitch && frame_stride == in_pitch * (size_t)rows)
+            PL_CUDA_TRY(cudaMemcpyAsync(h->d_in, gray + (size_t)f0 * frame_stride, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->stream));
+        else
+            for (int f = 0; f < nf; f++)
+                PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride, step,
+                                              cols, rows, cudaMemcpyHostToDevice, h->stream));
         rc = line_launch_chunk(h, h->d_in, nf, in_pitch, in_pitch * rows, h->d_kls, h->d_desc, h->d_coef, max_lines, h->d_nout);
         if (rc != PL_OK) return rc;
         PL_CUDA_TRY(cudaMemcpyAsync(n_out + f0, h->d_nout, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));

@@ -13,6 +13,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -1402,24 +1404,39 @@ PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, in
     h->last_launches = 0;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
-        for (int f = 0; f < nf; f++)
-            PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride,
-                                          step, cols, rows, cudaMemcpyHostToDevice, h->stream));
+        // one copy per chunk when the caller's frames are dense and already have the staging pitch, else one strided copy per frame
+        if (step == in_pitch && frame_stride == in_pitch * (size_t)rows)
+            PL_CUDA_TRY(cudaMemcpyAsync(h->d_in, gray + (size_t)f0 * frame_stride, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->stream));
+        else
+            for (int f = 0; f < nf; f++)
+                PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride,
+                                              step, cols, rows, cudaMemcpyHostToDevice, h->stream));
         rc = launch_chunk(h, h->d_in, nf, in_pitch, in_pitch * rows, h->d_kps, h->d_desc, cap, h->d_nout);
         if (rc != PL_OK) return rc;
         PL_CUDA_TRY(cudaMemcpyAsync(n_out + f0, h->d_nout, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
+        if (nf > 1) {
+            // a batch: the chunk's key points and descriptors in one copy each (the rows of a frame beyond its count are whatever the
+            // device buffer held: the caller reads n_out[f] of them) instead of two small copies per frame
+            PL_CUDA_TRY(cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps, sizeof(pl_keypoint) * (size_t)nf * cap, cudaMemcpyDeviceToHost, h->stream));
+            PL_CUDA_TRY(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, h->d_desc, (size_t)nf * cap * 32, cudaMemcpyDeviceToHost, h->stream));
+        }
         rc = check_flags(h, nf);  // synchronises
         if (rc != PL_OK) return rc;
-        // copy only the filled prefix of every frame
-        for (int f = 0; f < nf; f++) {
-            const int n = n_out[f0 + f];
-            if (n <= 0) continue;
-            PL_CUDA_TRY(cudaMemcpyAsync(kps + (size_t)(f0 + f) * cap, h->d_kps + (size_t)f * cap, sizeof(pl_keypoint) * n,
-                                        cudaMemcpyDeviceToHost, h->stream));
-            PL_CUDA_TRY(cudaMemcpyAsync(desc + (size_t)(f0 + f) * cap * 32, h->d_desc + (size_t)f * cap * 32, (size_t)n * 32,
-                                        cudaMemcpyDeviceToHost, h->stream));
+        if (nf > 1) {  // rows beyond a frame's count stay zero, as the per-frame prefix copies left them
+            for (int f = 0; f < nf; f++) {
+                const int n = std::max(0, std::min(n_out[f0 + f], cap));
+                memset(kps + (size_t)(f0 + f) * cap + n, 0, sizeof(pl_keypoint) * (size_t)(cap - n));
+                memset(desc + ((size_t)(f0 + f) * cap + n) * 32, 0, (size_t)(cap - n) * 32);
+            }
         }
-        PL_CUDA_TRY(pl::stream_sync(h->stream));
+        if (nf == 1) {  // a single frame: only the filled prefix
+            const int n = n_out[f0];
+            if (n > 0) {
+                PL_CUDA_TRY(cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps, sizeof(pl_keypoint) * n, cudaMemcpyDeviceToHost, h->stream));
+                PL_CUDA_TRY(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, h->d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+                PL_CUDA_TRY(pl::stream_sync(h->stream));
+            }
+        }
     }
     return PL_OK;
 }

@@ -21,6 +21,13 @@ from .synth import TUM1
 f32 = np.float32
 
 
+class FeatureList(list):
+    """A list of per-frame feature tuples that also carries the dense arrays they are views of — `dense` = (array (n, cap) of the
+    structured key points / key lines, counts (n,)) — so that the sequence-wide parts of the glue gather from the dense array once
+    instead of concatenating n small views."""
+    dense = None
+
+
 class FrameLite:
     """The subset of ORB_SLAM2::Frame the matchers read."""
 
@@ -60,8 +67,13 @@ class FrameLite:
         off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
         if n == 0 or not isinstance(depth, np.ndarray) or depth.ndim != 3:
             return [FrameLite(orb[t][0], orb[t][1], None, None, depth[t], Tcw[t], K, scale_factors) for t in range(n)]
-        x = np.concatenate([o[0]["x"] for o in orb])
-        y = np.concatenate([o[0]["y"] for o in orb])
+        dense = getattr(orb, "dense", None)
+        if dense is not None:
+            mask = np.arange(dense[0].shape[1])[None, :] < counts[:, None]
+            x, y = dense[0]["x"][mask], dense[0]["y"][mask]
+        else:
+            x = np.concatenate([o[0]["x"] for o in orb])
+            y = np.concatenate([o[0]["y"] for o in orb])
         fidx = np.repeat(np.arange(n), counts)
         h, w = depth.shape[1:]
         d = depth[fidx, np.clip(y.astype(np.int64), 0, h - 1), np.clip(x.astype(np.int64), 0, w - 1)].astype(f32)
@@ -134,7 +146,8 @@ class FrameLite:
                 F.set_lines(kls, ldesc)
             return
         offs = np.concatenate([[0], np.cumsum(counts)])
-        kl = np.concatenate([l[0] for l in lines])
+        dense = getattr(lines, "dense", None)
+        kl = dense[0][np.arange(dense[0].shape[1])[None, :] < counts[:, None]] if dense is not None else np.concatenate([l[0] for l in lines])
         fidx = np.repeat(np.arange(n), counts)
         h, w = depth.shape[1:]
         sx = np.clip(np.rint(kl["sx"]).astype(np.int64), 0, w - 1)
@@ -263,9 +276,23 @@ class TrackingFrontEnd:
         self.device_glue = device_glue
         self.keepalive = []  # arrays referenced by the views handed to the backend (views hold raw addresses)
 
+    _chk_w = {}
+    _obs = {}
+
+    @staticmethod
+    def _has_obs(n):
+        """two of three key points of the last frame carry a map point with observations (the same pattern for every frame)"""
+        a = TrackingFrontEnd._obs.get(n)
+        if a is None:
+            a = TrackingFrontEnd._obs[n] = (np.arange(n) % 3 != 0).astype(np.uint8)
+        return a
+
     @staticmethod
     def _chk(m):
-        return int(np.sum((m.astype(np.int64) + 1) * (np.arange(len(m)) + 1)))
+        w = TrackingFrontEnd._chk_w.get(len(m))
+        if w is None:
+            w = TrackingFrontEnd._chk_w[len(m)] = np.arange(1, len(m) + 1, dtype=np.int64)
+        return int(np.dot(m.astype(np.int64), w) + (len(m) * (len(m) + 1)) // 2)   # sum((m + 1) * (i + 1))
 
     def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True, batch=True):
         """features = (orb, lines); `lines` may be a concurrent.futures.Future: the point side (Frame-lite, C3, C2) does not
@@ -297,11 +324,12 @@ class TrackingFrontEnd:
         # ---- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ----
         c3_t = list(range(1, n))
         cvs = [frames[t].view(None, keep) for t in c3_t]
+        cv_of = dict(zip(c3_t, cvs))
         lvs = []
         for t in c3_t:
             last = frames[t - 1]
             lvs.append(N.make_lastframe_view(last.depth > 0, last.unproject_points(), last.desc, last.kps["octave"], last.kps["angle"],
-                                             (np.arange(len(last.kps)) % 3 != 0), last.Tcw[:3].reshape(-1), keep))
+                                             self._has_obs(len(last.kps)), last.Tcw[:3].reshape(-1), keep))
         # C2 inputs that do not depend on the C3 result (Frame::IsInFrustum of the local map): prepared before the first
         # matcher call, so that all of this host work overlaps the line extraction still running on the device
         c2_t = [t for t in range(n) if len(maps[t][0])]
@@ -324,7 +352,13 @@ class TrackingFrontEnd:
             # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
             fvs, mvs, inview = [], [], []
             for t, (mdesc, inv, u, v, xr, lvl, vc) in zip(c2_t, fr):
-                fvs.append(frames[t].view(claimed[t], keep))
+                if t in cv_of:  # the same frame view as in C3, plus the claims
+                    fv = type(cv_of[t]).from_buffer_copy(cv_of[t])
+                    keep.append(claimed[t])
+                    fv.claimed = claimed[t].__array_interface__["data"][0]
+                    fvs.append(fv)
+                else:
+                    fvs.append(frames[t].view(claimed[t], keep))
                 mvs.append(N.make_mappoint_view(mdesc, inv, u, v, xr, lvl, vc, None, keep))
                 inview.append(int(inv.sum()))
             r2 = self.b.search_local_points_batch(fvs, mvs, 3.0, 0.8) if batch else [self.b.search_local_points(f, m, 3.0, 0.8) for f, m in zip(fvs, mvs)]
