@@ -31,6 +31,10 @@ struct BowDev {  // one SearchByBoW call
     int* match;              // n_out
     int* rec;                // 2 * nq: (slot in match, histogram bin) per accepted match
     int* out;                // [0] = matches
+    // groups of queries that share no feature with any other group (the common nodes of the two feature vectors when every
+    // feature sits in one node): the ordered replay is per group; n_groups == 0: one group with every query
+    const int* g_off;        // n_groups + 1 offsets into the queries
+    int n_groups;
 };
 
 __global__ void __launch_bounds__(256) k_bow_dist(const BowDev* __restrict__ BD) {
@@ -49,72 +53,85 @@ __global__ void __launch_bounds__(256) k_bow_dist(const BowDev* __restrict__ BD)
 // mode 0: C6 (:296-347), mode 1: C7 (:770-836).  The reference's sequential two-minimum update is evaluated in closed
 // form: with pb = first position of the minimum among the unmatched candidates, the second best is the smaller of the
 // minimum before pb and the minimum after pb (the update displaces the running best when pb arrives).
-__global__ void __launch_bounds__(32) k_bow_resolve(const BowDev* __restrict__ BD, int mode, float nn_ratio, int check_orientation) {
+constexpr int kBowWarps = 16;
+__global__ void __launch_bounds__(32 * kBowWarps) k_bow_resolve(const BowDev* __restrict__ BD, int mode, float nn_ratio, int check_orientation) {
     extern __shared__ uint8_t s_matched[];  // side-B feature already matched in this call (vpMapPointMatches / vbMatched2)
     __shared__ int s_hist[kBowHisto];
+    __shared__ int s_nrec, s_nmatches;
     const BowDev& D = BD[blockIdx.x];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < D.nB; i += 32) s_matched[i] = 0;
-    for (int i = lane; i < D.n_out; i += 32) D.match[i] = -1;
-    if (lane < kBowHisto) s_hist[lane] = 0;
-    __syncwarp();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < D.nB; i += blockDim.x) s_matched[i] = 0;
+    for (int i = threadIdx.x; i < D.n_out; i += blockDim.x) D.match[i] = -1;
+    if (threadIdx.x < kBowHisto) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_nrec = s_nmatches = 0;
+    __syncthreads();
     const float factor = kBowHisto / 360.0f;
-    int nmatches = 0, nrec = 0;
-    for (int q = 0; q < D.nq; q++) {
-        const int o0 = D.q_off[q], c = D.q_off[q + 1] - o0;
-        if (c == 0) continue;
-        const unsigned int* cd = D.cand + o0;
-        unsigned best = 0xFFFFFFFFu;
-        for (int base = 0; base < c; base += 32) {
-            unsigned key = 0xFFFFFFFFu;
-            if (base + lane < c) {
-                const unsigned e = cd[base + lane];
-                if (!s_matched[e & 0xFFFFu]) key = ((e >> 16) << 16) | (unsigned)(base + lane);
-            }
+    // The reference walks the queries in order and a feature of side B can be taken once: an ordered process — but only among the
+    // queries of one node, because a feature belongs to one node.  One warp replays a group (node); the groups run side by side.
+    const int ng = D.n_groups > 0 ? D.n_groups : 1;
+    int nmatches = 0;
+    for (int gi = warp; gi < ng; gi += kBowWarps) {
+        const int q0 = D.n_groups > 0 ? D.g_off[gi] : 0, q1 = D.n_groups > 0 ? D.g_off[gi + 1] : D.nq;
+        for (int q = q0; q < q1; q++) {
+            const int o0 = D.q_off[q], c = D.q_off[q + 1] - o0;
+            if (c == 0) continue;
+            const unsigned int* cd = D.cand + o0;
+            unsigned best = 0xFFFFFFFFu;
+            for (int base = 0; base < c; base += 32) {
+                unsigned key = 0xFFFFFFFFu;
+                if (base + lane < c) {
+                    const unsigned e = cd[base + lane];
+                    if (!s_matched[e & 0xFFFFu]) key = ((e >> 16) << 16) | (unsigned)(base + lane);
+                }
 #pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
-            best = min(best, key);
-        }
-        if (best == 0xFFFFFFFFu) continue;
-        const int pb = (int)(best & 0xFFFFu), bestDist1 = (int)(best >> 16);
-        if (mode == 0 ? bestDist1 > kBowThLow : bestDist1 >= kBowThLow) continue;
-        unsigned second = 0xFFFFFFFFu;
-        for (int base = 0; base < c; base += 32) {
-            unsigned key = 0xFFFFFFFFu;
-            const int pos = base + lane;
-            if (pos < c && pos != pb) {
-                const unsigned e = cd[pos];
-                if (!s_matched[e & 0xFFFFu]) key = e >> 16;
+                for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
+                best = min(best, key);
             }
+            if (best == 0xFFFFFFFFu) continue;
+            const int pb = (int)(best & 0xFFFFu), bestDist1 = (int)(best >> 16);
+            if (mode == 0 ? bestDist1 > kBowThLow : bestDist1 >= kBowThLow) continue;
+            unsigned second = 0xFFFFFFFFu;
+            for (int base = 0; base < c; base += 32) {
+                unsigned key = 0xFFFFFFFFu;
+                const int pos = base + lane;
+                if (pos < c && pos != pb) {
+                    const unsigned e = cd[pos];
+                    if (!s_matched[e & 0xFFFFu]) key = e >> 16;
+                }
 #pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
-            second = min(second, key);
-        }
-        const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)second;
-        if (!((float)bestDist1 < __fmul_rn(nn_ratio, (float)bestDist2))) continue;
-        const int idxB = (int)(cd[pb] & 0xFFFFu), idxA = D.q_idx[q];
-        const int slot = mode == 0 ? idxB : idxA;
-        if (lane == 0) {
-            s_matched[idxB] = 1;
-            D.match[slot] = mode == 0 ? idxA : idxB;
-        }
-        if (check_orientation) {
-            float rot = __fsub_rn(D.angA[idxA], D.angB[idxB]);
-            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-            int bin = (int)roundf(__fmul_rn(rot, factor));
-            if (bin == kBowHisto) bin = 0;
+                for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
+                second = min(second, key);
+            }
+            const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)second;
+            if (!((float)bestDist1 < __fmul_rn(nn_ratio, (float)bestDist2))) continue;
+            const int idxB = (int)(cd[pb] & 0xFFFFu), idxA = D.q_idx[q];
+            const int slot = mode == 0 ? idxB : idxA;
             if (lane == 0) {
-                D.rec[2 * nrec] = slot;
-                D.rec[2 * nrec + 1] = bin;
-                s_hist[bin]++;
+                s_matched[idxB] = 1;
+                D.match[slot] = mode == 0 ? idxA : idxB;
             }
-            nrec++;
+            if (check_orientation) {
+                float rot = __fsub_rn(D.angA[idxA], D.angB[idxB]);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, factor));
+                if (bin == kBowHisto) bin = 0;
+                if (lane == 0) {
+                    const int k = atomicAdd(&s_nrec, 1);  // (the records are a set: the histogram rule below does not look at their order)
+                    D.rec[2 * k] = slot;
+                    D.rec[2 * k + 1] = bin;
+                    atomicAdd(&s_hist[bin], 1);
+                }
+            }
+            nmatches++;
+            __syncwarp();
         }
-        nmatches++;
-        __syncwarp();
     }
+    if (lane == 0 && nmatches) atomicAdd(&s_nmatches, nmatches);
+    __syncthreads();
+    if (warp != 0) return;
+    nmatches = s_nmatches;
     if (check_orientation) {
-        __syncwarp();
+        const int nrec = s_nrec;
         // ComputeThreeMaxima (ORBmatcher.cc:2035-2077)
         int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
         for (int i = 0; i < kBowHisto; i++) {
@@ -443,8 +460,9 @@ PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, con
     PL_CHECK_ARG(h && n >= 0 && (mode == 0 || mode == 1) && (n == 0 || (a && b && match_out && n_matches)));
     if (n == 0) return PL_OK;
     // merge-join of the feature vectors (ORBmatcher.cc:276-381 / :758-851): queries and candidates in processing order
-    std::vector<std::vector<int>> q_idx(n), q_off(n);
+    std::vector<std::vector<int>> q_idx(n), q_off(n), g_off(n);
     std::vector<std::vector<unsigned>> cand(n);
+    std::vector<uint8_t> seenA, seenB;
     size_t bytes = padb(sizeof(BowDev) * (size_t)n);
     int max_nq = 0, max_nB = 0;
     for (int i = 0; i < n; i++) {
@@ -456,22 +474,36 @@ PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, con
         for (int k = 0; k + 1 < A.n_nodes; k++) PL_CHECK_ARG(A.node_id[k] < A.node_id[k + 1]);
         for (int k = 0; k + 1 < B.n_nodes; k++) PL_CHECK_ARG(B.node_id[k] < B.node_id[k + 1]);
         q_off[i].push_back(0);
+        g_off[i].push_back(0);
+        // the nodes can be replayed side by side only if no feature of either side sits in two of the joined nodes (true for a
+        // DBoW2 feature vector; the views are caller data, so it is checked)
+        bool disjoint = true;
+        seenA.assign((size_t)A.n, 0);
+        seenB.assign((size_t)B.n, 0);
         int ka = 0, kb = 0;
         while (ka < A.n_nodes && kb < B.n_nodes) {
             if (A.node_id[ka] == B.node_id[kb]) {
+                for (int pb = B.node_off[kb]; pb < B.node_off[kb + 1]; pb++) {
+                    const unsigned ib = B.feat_idx[pb];
+                    PL_CHECK_ARG(ib < (unsigned)B.n);
+                    if (seenB[ib]) disjoint = false;
+                    seenB[ib] = 1;
+                }
                 for (int pa = A.node_off[ka]; pa < A.node_off[ka + 1]; pa++) {
                     const unsigned ia = A.feat_idx[pa];
                     PL_CHECK_ARG(ia < (unsigned)A.n);
+                    if (seenA[ia]) disjoint = false;
+                    seenA[ia] = 1;
                     if (A.valid && !A.valid[ia]) continue;
                     for (int pb = B.node_off[kb]; pb < B.node_off[kb + 1]; pb++) {
                         const unsigned ib = B.feat_idx[pb];
-                        PL_CHECK_ARG(ib < (unsigned)B.n);
                         if (mode == 1 && B.valid && !B.valid[ib]) continue;  // !pMP2 || isBad (:797-802)
                         cand[i].push_back(ib);
                     }
                     q_idx[i].push_back((int)ia);
                     q_off[i].push_back((int)cand[i].size());
                 }
+                if ((int)q_idx[i].size() > g_off[i].back()) g_off[i].push_back((int)q_idx[i].size());
                 ka++;
                 kb++;
             } else if (A.node_id[ka] < B.node_id[kb]) {
@@ -480,8 +512,9 @@ PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, con
                 kb = (int)(std::lower_bound(B.node_id + kb, B.node_id + B.n_nodes, A.node_id[ka]) - B.node_id);
             }
         }
+        if (!disjoint) g_off[i].assign(1, 0);  // one group with every query: the plain ordered replay
         const size_t nq = q_idx[i].size(), n_out = (size_t)(mode == 0 ? B.n : A.n);
-        bytes += padb(nq * 4) + padb((nq + 1) * 4) + padb(cand[i].size() * 4) + padb((size_t)A.n * 32) + padb((size_t)B.n * 32) + padb((size_t)A.n * 4) +
+        bytes += padb(g_off[i].size() * 4) + padb(nq * 4) + padb((nq + 1) * 4) + padb(cand[i].size() * 4) + padb((size_t)A.n * 32) + padb((size_t)B.n * 32) + padb((size_t)A.n * 4) +
                  padb((size_t)B.n * 4) + padb(n_out * 4) + padb(nq * 8 + 8) + padb(8);
         max_nq = std::max(max_nq, (int)nq);
         max_nB = std::max(max_nB, B.n);
@@ -501,6 +534,8 @@ PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, con
         D.n_out = mode == 0 ? B.n : A.n;
         D.q_idx = h->in.put(q_idx[i].data(), q_idx[i].size());
         D.q_off = h->in.put(q_off[i].data(), q_off[i].size());
+        D.g_off = h->in.put(g_off[i].data(), g_off[i].size());
+        D.n_groups = (int)g_off[i].size() - 1;
         D.cand = const_cast<unsigned int*>(h->in.put(cand[i].data(), cand[i].size()));
         D.descA = (const uint4*)h->in.put(A.desc, (size_t)A.n * 32);
         D.descB = (const uint4*)h->in.put(B.desc, (size_t)B.n * 32);
@@ -519,7 +554,7 @@ PL_API int pl_orb_search_bow_batch(pl_match* h, int n, const pl_bow_view* a, con
     }
     const size_t sm = (size_t)std::max(max_nB, 1);
     if (sm > 48 * 1024) PL_CUDA_TRY(cudaFuncSetAttribute(k_bow_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_bow_resolve<<<n, 32, sm, st>>>(d_bd, mode, nn_ratio, check_orientation);
+    k_bow_resolve<<<n, 32 * kBowWarps, sm, st>>>(d_bd, mode, nn_ratio, check_orientation);
     h->last_launches++;
     PL_CUDA_TRY(cudaGetLastError());
     // results live in the same packed buffer: one copy back

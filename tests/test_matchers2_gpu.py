@@ -73,6 +73,30 @@ def test_search_by_bow_c6_c7(seed, nA, nB, nodes, mode, api, oracle):
         assert o[1] > 150
 
 
+def test_search_by_bow_feature_in_two_nodes(api, oracle):
+    """The nodes of a call are replayed side by side because a feature belongs to one node.  A caller-built view that lists a
+    feature under two nodes makes them depend on each other: the library detects it and replays the call in one ordered pass."""
+    N = api.N
+    rng = np.random.default_rng(11)
+    n = 600
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    descb = matchgen.noisy(desc, rng, 0.05)
+    ang = rng.uniform(0, 360, n).astype(np.float32)
+    nodes = rng.integers(0, 20, n)
+    fva = {int(k): [int(i) for i in np.nonzero(nodes == k)[0]] for k in np.unique(nodes)}
+    fvb = {k: list(v) for k, v in fva.items()}
+    for k in list(fvb)[:-1]:  # every node of side B also lists the first features of the next node
+        nxt = sorted(fvb)[sorted(fvb).index(k) + 1]
+        fvb[k] = sorted(set(fvb[k]) | set(fva[nxt][:5]))
+    keep = []
+    a = N.make_bow_view(ang, desc, None, fva, keep)
+    b = N.make_bow_view(ang, descb, None, fvb, keep)
+    for mode in (0, 1):
+        g = api.DescriptorMatcher().SearchByBoWBatch([a], [b], mode, 0.9, True)[0]
+        o = oracle.search_bow(a, b, mode, 0.9, True)
+        assert np.array_equal(g[0], o[0]) and g[1] == o[1]
+
+
 def test_search_by_bow_batched(api, oracle):
     N = api.N
     rng = np.random.default_rng(5)
