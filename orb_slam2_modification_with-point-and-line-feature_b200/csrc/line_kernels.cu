@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap (the driver entry point is looked up at run time: no link against libcuda)
+
 #include "pl_common.cuh"
 #include "pl_glibc_sincos.cuh"
 
@@ -1476,6 +1478,117 @@ __global__ void __launch_bounds__(256) k_sobel3(LineGeom g, const uint8_t* __res
     dyo[o] = (short)gy;
 }
 
+// ---- the two kernels above fused, the source tile staged by TMA ----
+// GaussianBlur(5x5) and both Sobel(3x3) derivatives in one pass: a CTA owns a 64 x 32 tile of the image; one elected thread issues a
+// cp.async.bulk.tensor load of the (64 + 6) x (32 + 6) source tile (box 96 x 38 x 1 of the (cols, rows, frames) tensor: out-of-range
+// elements arrive as zeros) and everybody waits on the mbarrier; the edge CTAs then mirror the border into the halo
+// (BORDER_REFLECT_101 of the blur; the Sobel's own reflection of the BLURRED image is the blur of the reflected source because
+// the kernel is symmetric, so the same halo serves both); horizontal and vertical blur passes through shared memory; each thread
+// writes eight dx and eight dy values with one 16-byte store each.  The blurred image never goes to HBM: 1 byte read and 4 bytes
+// written per pixel instead of 2 + 5.
+// (the box starts at a multiple of 16 bytes in x — the TMA unit faults on an unaligned inner coordinate — so the tile carries 16
+// columns of halo on the left, of which 3 are used)
+constexpr int kFsTW = 64, kFsTH = 32, kFsBoxW = 96, kFsXOff = 16, kFsBoxH = kFsTH + 6;
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__global__ void __launch_bounds__(256) k_blur5_sobel3_tma(LineGeom g, const __grid_constant__ CUtensorMap tmap, short* __restrict__ dxo,
+                                                          short* __restrict__ dyo) {
+    __shared__ __align__(128) uint8_t s_in[kFsBoxH * kFsBoxW];      // source tile, origin (x0 - 16, y0 - 3)
+    __shared__ uint16_t s_h[kFsBoxH * (kFsTW + 4)];                 // horizontal pass, columns x0 - 1 .. x0 + 64
+    __shared__ __align__(16) uint8_t s_b[(kFsTH + 2) * (kFsTW + 8)];  // blurred tile, origin (x0 - 1, y0 - 1)
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int f = blockIdx.z, tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFsTW, y0 = blockIdx.y * kFsTH;
+    const unsigned bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kFsBoxH * kFsBoxW) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(s_in)),
+                     "l"(&tmap), "r"(bar), "r"(x0 - kFsXOff), "r"(y0 - 3), "r"(f)
+                     : "memory");
+    }
+    __syncthreads();  // (the barrier's initialisation is visible to everybody before anybody waits on it)
+    mbar_wait_parity(bar, 0);
+    // BORDER_REFLECT_101: only the CTAs on the image's edge have anything to mirror
+    const bool edge_x = x0 == 0 || x0 + kFsTW + 3 > g.cols, edge_y = y0 == 0 || y0 + kFsTH + 3 > g.rows;
+    if (edge_x) {
+        for (int i = tid; i < kFsBoxH * (kFsTW + 6); i += 256) {
+            const int r = i / (kFsTW + 6), c = i - r * (kFsTW + 6);
+            const int x = x0 - 3 + c;
+            if (x < 0 || x >= g.cols) s_in[r * kFsBoxW + kFsXOff - 3 + c] = s_in[r * kFsBoxW + (reflect101(x, g.cols) - (x0 - kFsXOff))];
+        }
+        __syncthreads();
+    }
+    if (edge_y) {
+        for (int i = tid; i < kFsBoxH * (kFsTW + 6); i += 256) {
+            const int r = i / (kFsTW + 6), c = i - r * (kFsTW + 6);
+            const int y = y0 - 3 + r;
+            if (y < 0 || y >= g.rows) s_in[r * kFsBoxW + kFsXOff - 3 + c] = s_in[(reflect101(y, g.rows) - (y0 - 3)) * kFsBoxW + kFsXOff - 3 + c];
+        }
+        __syncthreads();
+    }
+    // horizontal pass {14, 62, 104, 62, 14}: two outputs per step from one 8-byte window
+    for (int i = tid; i < kFsBoxH * ((kFsTW + 2) / 2); i += 256) {
+        const int r = i / ((kFsTW + 2) / 2), c = (i - r * ((kFsTW + 2) / 2)) * 2;
+        const uint8_t* p = s_in + r * kFsBoxW + kFsXOff - 3 + c;
+        const unsigned a0 = 14u * (p[0] + p[4]) + 62u * (p[1] + p[3]) + 104u * p[2];
+        const unsigned a1 = 14u * (p[1] + p[5]) + 62u * (p[2] + p[4]) + 104u * p[3];
+        *reinterpret_cast<unsigned*>(s_h + r * (kFsTW + 4) + c) = a0 | (a1 << 16);
+    }
+    __syncthreads();
+    // vertical pass -> blurred bytes (rounded as cv::GaussianBlur's fixed-point path rounds)
+    for (int i = tid; i < (kFsTH + 2) * ((kFsTW + 2) / 2); i += 256) {
+        const int r = i / ((kFsTW + 2) / 2), c = (i - r * ((kFsTW + 2) / 2)) * 2;
+        const uint16_t* p = s_h + r * (kFsTW + 4) + c;
+        constexpr int P = kFsTW + 4;
+        const unsigned v0 = *reinterpret_cast<const unsigned*>(p), v1 = *reinterpret_cast<const unsigned*>(p + P),
+                       v2 = *reinterpret_cast<const unsigned*>(p + 2 * P), v3 = *reinterpret_cast<const unsigned*>(p + 3 * P),
+                       v4 = *reinterpret_cast<const unsigned*>(p + 4 * P);
+        const unsigned lo = 14u * ((v0 & 0xffffu) + (v4 & 0xffffu)) + 62u * ((v1 & 0xffffu) + (v3 & 0xffffu)) + 104u * (v2 & 0xffffu);
+        const unsigned hi = 14u * ((v0 >> 16) + (v4 >> 16)) + 62u * ((v1 >> 16) + (v3 >> 16)) + 104u * (v2 >> 16);
+        uint8_t* q = s_b + r * (kFsTW + 8) + c;
+        q[0] = (uint8_t)((lo + 0x8000u) >> 16);
+        q[1] = (uint8_t)((hi + 0x8000u) >> 16);
+    }
+    __syncthreads();
+    // Sobel: thread = eight consecutive pixels of one row
+    {
+        const int r = tid >> 3, c = (tid & 7) * 8;
+        const int y = y0 + r, x = x0 + c;
+        if (y < g.rows && x < g.cols) {
+            const uint8_t* b0 = s_b + r * (kFsTW + 8) + c;  // blurred (x - 1, y - 1)
+            const uint8_t *b1 = b0 + (kFsTW + 8), *b2 = b1 + (kFsTW + 8);
+            short gx[8], gy[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                gx[k] = (short)((b0[k + 2] + 2 * b1[k + 2] + b2[k + 2]) - (b0[k] + 2 * b1[k] + b2[k]));
+                gy[k] = (short)((b2[k] + 2 * b2[k + 1] + b2[k + 2]) - (b0[k] + 2 * b0[k + 1] + b0[k + 2]));
+            }
+            const size_t o = (size_t)f * g.dpitch * g.rows + (size_t)y * g.dpitch + x;
+            if (x + 8 <= g.cols) {
+                *reinterpret_cast<int4*>(dxo + o) = *reinterpret_cast<const int4*>(gx);
+                *reinterpret_cast<int4*>(dyo + o) = *reinterpret_cast<const int4*>(gy);
+            } else {
+                for (int k = 0; k < 8 && x + k < g.cols; k++) {
+                    dxo[o + k] = gx[k];
+                    dyo[o + k] = gy[k];
+                }
+            }
+        }
+    }
+}
+
 constexpr int kLbdBands = 9, kLbdBandW = 7, kLbdRows = kLbdBands * kLbdBandW;  // 63
 struct LbdTabs { float gaussL[kLbdBandW * 3]; float gaussG[kLbdRows]; };
 
@@ -1669,6 +1782,8 @@ struct pl_line {
     // k_lsd_grow2 (role-specialised grower, one frame per CTA): shape for up to one frame per SM / for more frames than SMs
     struct Grow2Cfg { int threads = 0, occ = 0, pool_tiles = 0, pool_n = 0, split = 0; size_t smem = 0; } g2_few, g2_many;
     int lookahead = 4;
+    bool use_tma = true;      // PLSLAM_LINE_TMA=0: the two-kernel blur + Sobel path also for aligned inputs (test hook)
+    void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, through cudaGetDriverEntryPoint
     bool force_many = false;  // test hook (PLSLAM_LSD_FORCE_MANY): the many-frames shape also for small batches
     int poll_ns = 400;
     int reserved_sms = 0;          // SMs the region grower leaves to the kernels of other streams (pl_line_set_reserved_sms)
@@ -1768,6 +1883,22 @@ int line_ensure_out(pl_line* h, int cap) {
     return PL_OK;
 }
 
+// TMA descriptor of the caller's image batch as a (cols, rows, frames) tensor of bytes, box kFsBoxW x kFsBoxH x 1; false when the
+// layout cannot be described (strides and base must be multiples of 16 bytes)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool line_make_tmap(pl_line* h, CUtensorMap* out, const uint8_t* d_gray, int cols, int rows, int nf, size_t step, size_t frame_stride) {
+    if (!h->encode_tiled || (step & 15) || (frame_stride & 15) || ((uintptr_t)d_gray & 15)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nf};
+    const cuuint64_t strides[2] = {(cuuint64_t)step, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)kFsBoxW, (cuuint32_t)kFsBoxH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = ((EncodeTiledFn)h->encode_tiled)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)d_gray, dims, strides, box, estr,
+                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // one chunk; every pointer is a device pointer
 int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, size_t frame_stride, pl_keyline* d_kls, uint8_t* d_desc,
                       double* d_coef, int cap, int* d_nout) {
@@ -1828,10 +1959,16 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     launches++;
     {
         dim3 grid((G.cols + 63) / 64, (G.rows + 31) / 32, nf);
-        k_blur5<<<grid, 256, 0, st>>>(G, d_gray, step, frame_stride, h->d_blur5);
-        dim3 grid2((G.cols + 63) / 64, (G.rows + 3) / 4, nf);
-        k_sobel3<<<grid2, 256, 0, st>>>(G, h->d_blur5, h->d_dx, h->d_dy);
-        launches += 2;
+        CUtensorMap tmap;
+        if (h->use_tma && G.cols >= 8 && G.rows >= 8 && line_make_tmap(h, &tmap, d_gray, G.cols, G.rows, nf, step, frame_stride)) {
+            k_blur5_sobel3_tma<<<grid, 256, 0, st>>>(G, tmap, h->d_dx, h->d_dy);
+            launches += 1;
+        } else {  // the caller's pitch or base address is not 16-byte aligned: a tensor map cannot describe it
+            k_blur5<<<grid, 256, 0, st>>>(G, d_gray, step, frame_stride, h->d_blur5);
+            dim3 grid2((G.cols + 63) / 64, (G.rows + 3) / 4, nf);
+            k_sobel3<<<grid2, 256, 0, st>>>(G, h->d_blur5, h->d_dx, h->d_dy);
+            launches += 2;
+        }
     }
     if (prof) cudaEventRecord(h->ev[4], st);
     const int keep = std::min(G.max_lines, cap);
@@ -1977,6 +2114,15 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             h->grow_window = 128;
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots2, atoi(ev)));
             // ---- k_lsd_grow2: warps per CTA, CTAs per SM, private tile pool ----
+            if (const char* ev = getenv("PLSLAM_LINE_TMA")) h->use_tma = atoi(ev) != 0;
+            {
+                cudaDriverEntryPointQueryResult qres;
+                void* fn = nullptr;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                    h->encode_tiled = fn;
+                else
+                    (void)cudaGetLastError();
+            }
             if (const char* ev = getenv("PLSLAM_LSD_FORCE_MANY")) h->force_many = atoi(ev) != 0;
             if (const char* ev = getenv("PLSLAM_LSD_LOOKAHEAD")) h->lookahead = std::max(1, std::min(kSlots2, atoi(ev)));
             auto allow_smem = [&](const void* fn) {  // dynamic shared memory up to what the kernel's static part leaves

@@ -60,6 +60,27 @@ def test_knn2_full_size_properties(api, synth):
         assert idx[i].tolist() == order[:2].tolist() and dist[i].tolist() == d[order[:2]].tolist()
 
 
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_knn2_8k_16k_equal_cv2_bfmatcher_in_full(n, api, synth):
+    """Config 4 at its upper sizes, every row: indices and distances of cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) — what the
+    reference's LineMatcher calls (src/LineMatcher.cpp:497-503) — for the ORB-like and the LBD-like descriptor sets."""
+    cv2 = pytest.importorskip("cv2")
+    for seed_shift in (0, 1):
+        q, t = synth.descriptor_sets(n) if seed_shift == 0 else synth.descriptor_sets(n)[::-1]
+        idx, dist = api.DescriptorMatcher().knnMatch2(q, t)
+        m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)
+        ci = np.array([[a.trainIdx, b.trainIdx] for a, b in m], np.int32)
+        cd = np.array([[a.distance, b.distance] for a, b in m]).astype(np.int32)
+        assert np.array_equal(dist, cd)
+        # equal distances: cv2 keeps the first index it met, the library the lowest index: compare indices where the row is free of ties
+        same = idx == ci
+        if not same.all():
+            bad = np.nonzero(~same.all(axis=1))[0]
+            for i in bad:
+                d = np.unpackbits(q[i][None] ^ t, axis=1).sum(1)
+                assert (d == dist[i, 0]).sum() > 1 or (d == dist[i, 1]).sum() > 1, f"row {i}: indices differ without a tie"
+
+
 def test_candidates(api, oracle):
     rng = np.random.default_rng(5)
     q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
