@@ -51,6 +51,7 @@ struct PlStage {
     size_t cap = 0, cur = 0;
     int reserve(size_t bytes) {
         cur = 0;
+        overflow = false;
         jobs.clear();
         seen.clear();
         if (bytes <= cap) return PL_OK;
@@ -68,6 +69,7 @@ struct PlStage {
     // copies n elements into the pinned buffer; returns the DEVICE address they will have after upload()
     // Large arrays are not copied at once: the copy is recorded and executed by a few host threads in upload(), so the
     // source must stay alive until then (it always is: every put() happens inside the API call that uploads).
+    bool overflow = false;  // a put() / out() did not fit what reserve() was asked for (checked by upload())
     struct Job { size_t off; const void* src; size_t bytes; };
     std::vector<Job> jobs;
     // a large array that several instances of a batch share (the same local-map snapshot for consecutive frames, a frame that
@@ -76,6 +78,10 @@ struct PlStage {
     template <typename T>
     const T* put(const T* src, size_t n) {
         const size_t off = cur, bytes = n * sizeof(T);
+        if (off + pad(bytes) > cap) {  // the caller's reserve() sum and its put() sequence disagree: never write past the buffers
+            overflow = true;
+            return (const T*)d;
+        }
         if (n && src) {
             if (bytes >= (size_t)8 << 10) {
                 auto it = seen.find((const void*)src);
@@ -91,6 +97,10 @@ struct PlStage {
     }
     // executes the recorded copies (up to 4 threads when there is enough to copy) and sends the packed buffer to the device
     int upload(cudaStream_t st) {
+        if (overflow) {
+            pl::set_error("internal: a packed call needed more staging memory than it reserved");
+            return PL_ERR_CAPACITY;
+        }
         size_t total = 0;
         for (const Job& j : jobs) total += j.bytes;
         const int nt = total >= ((size_t)4 << 20) ? 4 : 1;
@@ -119,6 +129,11 @@ struct PlStage {
     template <typename T>
     T* out(size_t n, T** host_mirror = nullptr) {
         const size_t off = cur;
+        if (off + pad(n * sizeof(T)) > cap) {
+            overflow = true;
+            if (host_mirror) *host_mirror = (T*)h;
+            return (T*)d;
+        }
         cur += pad(n * sizeof(T));
         if (host_mirror) *host_mirror = (T*)(h + off);
         return (T*)(d + off);

@@ -225,6 +225,8 @@ PL_API int pl_hamming_candidates(pl_match* h, const uint8_t* q, int nq, const ui
                                  const int* cand_idx, int* dist_out) {
     PL_CHECK_ARG(h && q && t && cand_off && nq >= 0 && nt > 0);
     if (nq == 0) return PL_OK;
+    PL_CHECK_ARG(cand_off[0] == 0);
+    for (int i = 0; i < nq; i++) PL_CHECK_ARG(cand_off[i + 1] >= cand_off[i]);  // a CSR: offsets start at 0 and never decrease
     const int total = cand_off[nq];
     PL_CHECK_ARG(total >= 0 && (total == 0 || (cand_idx && dist_out)));
     if (total == 0) return PL_OK;

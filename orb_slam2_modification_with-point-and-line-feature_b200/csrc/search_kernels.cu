@@ -1069,6 +1069,10 @@ size_t frame_bytes(const pl_frame_view& F) {
 
 int check_frame(const pl_frame_view* F) {
     PL_CHECK_ARG(F && F->n >= 0 && F->n <= 65535 && F->scale_factors);
+    if (F->n > 32768) {  // k_frame_grid sorts (cell, index) pairs in shared memory: 4 bytes x the next power of two
+        set_error("a frame view with %d key points exceeds the 32768 the grid kernel can sort in shared memory", F->n);
+        return PL_ERR_CAPACITY;
+    }
     PL_CHECK_ARG(F->n == 0 || (F->keys_un && F->desc && F->u_right));
     PL_CHECK_ARG(F->n_levels >= 1 && F->n_levels <= kMaxLevels && F->max_x > F->min_x && F->max_y > F->min_y);
     return PL_OK;
