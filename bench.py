@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0, help="frames per extraction chunk (0 = whole sequence)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="frames of the cpu_baseline sample")
     ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the persistent LSD region grower leaves to the matcher kernels of the other streams")
+    ap.add_argument("--overlap-orb", type=int, default=1, help="device-resident step: let the line extractor start next to the ORB extractor instead of behind it")
+    ap.add_argument("--e2e-order", default="orb_first", choices=["orb_first", "together"], help="e2e leg: call the ORB extractor before the line extractor's thread starts, or both at once")
     ap.add_argument("--device-glue", type=int, default=1, help="e2e leg: Frame glue (UnprojectStereo, IsInFrustum) through the batched F-row calls instead of numpy")
     ap.add_argument("--c5-frames", type=int, default=4096, help="frames of the config-5 leg (batched offline extraction sharded frame-wise over the ranks); 0 = skip")
     ap.add_argument("--c5-chunk", type=int, default=512, help="frames per device-resident chunk of the config-5 leg")
@@ -84,7 +86,7 @@ def ncu_traffic_bytes(kernel):
 
 
 # the kernel whose ncu capture gives roofline.traffic for a stage of *_stage_ms
-KERNEL_OF_STAGE = {"lsd_grow": "k_lsd_grow", "lsd_scale_grad": "k_lsd_grad", "lsd_seed_sort": "k_lsd_scatter", "keylines_sobel": "k_sobel3",
+KERNEL_OF_STAGE = {"lsd_grow": "k_lsd_grow2", "lsd_scale_grad": "k_lsd_grad", "lsd_seed_sort": "k_lsd_scatter", "keylines_sobel": "k_blur5_sobel3_tma",
                    "lbd": "k_lbd_rows", "orb_pyramid": "k_pyr_resize", "orb_fast": "k_fast_cells", "orb_octree": "k_octree", "orb_blur": "k_blur7",
                    "orb_orient_brief": "k_orient_brief"}
 
@@ -251,8 +253,9 @@ def run_ours(a, rank, world, local_rank, dist):
         # the pipeline a caller runs: ORB extraction (short) first, the line extractor behind it on its own stream; the point
         # searches only need the ORB features, so their host-side packing and uploads overlap the line extraction
         gb.orb.extract_batch_dev(d_gray.data_ptr(), F, H, W, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
-        ev_orb.record(s_orb)
-        s_line.wait_event(ev_orb)
+        if not a.overlap_orb:
+            ev_orb.record(s_orb)
+            s_line.wait_event(ev_orb)
         gb.line.extract_batch_dev(d_gray.data_ptr(), F, H, W, W, W * H, MAXL, d_kls.data_ptr(), d_ldesc.data_ptr(), d_lco.data_ptr(), d_ln.data_ptr())
         gb.orb.sync()
         plan.replay("points")
@@ -305,8 +308,12 @@ def run_ours(a, rank, world, local_rank, dist):
         # ORB first (4-5 ms of device time), the line extractor right behind it on its own thread: next to the region grower's
         # resident CTAs the ORB kernels would only get what is left of every SM and arrive later, and the point side of the glue
         # needs them first
-        gb.orb.extract_batch_into(hg, kp_np, dd_np, nn_np)
-        lines_later = LinesLater()
+        if a.e2e_order == "orb_first":
+            gb.orb.extract_batch_into(hg, kp_np, dd_np, nn_np)
+            lines_later = LinesLater()
+        else:
+            lines_later = LinesLater()
+            gb.orb.extract_batch_into(hg, kp_np, dd_np, nn_np)
         orb = fe.FeatureList((kp_np[i, :nn_np[i]], dd_np[i, :nn_np[i]]) for i in range(F))
         orb.dense = (kp_np, nn_np)
         return e2e_fe.run(hg, depth, Tcw, sf, features=(orb, lines_later))
@@ -434,7 +441,7 @@ def run_ours(a, rank, world, local_rank, dist):
     ach = alg_bytes.get(dom, 0) * F / (stage[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6),
                 "traffic": ncu_traffic_bytes(KERNEL_OF_STAGE.get(dom, dom)), "traffic_kernel": KERNEL_OF_STAGE.get(dom, dom), "peak_source": peak_src,
-                "note": "k_lsd_grow is the ordered (sequential-semantics) region grower, run as speculative transactions with in-order commit (DESIGN.md 4.1): latency-bound, not a streaming kernel; the HBM fraction is printed for completeness only",
+                "note": "k_lsd_grow2 is the ordered (sequential-semantics) region grower, run as speculative transactions with in-order commit, one frame per CTA with a sequencer warp and grower warps (DESIGN.md 4.1): bound by dependent-load latency and instruction fetch, not a streaming kernel; the HBM fraction is printed for completeness only",
                 "per_kernel": rl}
 
     # ---- cpu_baseline: the oracle on one host core, bounded sample ----

@@ -1952,7 +1952,11 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         else if (c2.threads <= 512) k_lsd_grow2<512, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
         else k_lsd_grow2<1024, 1><<<ctas2, c2.threads, c2.smem, st>>>(G, g2, nf, gb);
     }
-    k_lsd_nfa<<<dim3(kNfaBlocksPerFrame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
+    {
+        // a warp per rectangle: few frames get more CTAs each, so that a single frame's ~1500 rectangles are one wave on the whole GPU
+        const int per_frame = std::max(kNfaBlocksPerFrame, std::min(256, (4 * h->num_sms + nf - 1) / nf));
+        k_lsd_nfa<<<dim3(per_frame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
+    }
     launches += 2;
     if (prof) cudaEventRecord(h->ev[3], st);
     k_line_finalize<<<nf, kFinThreads, 0, st>>>(G, h->d_qres, h->d_qvalid, h->d_nrects, h->d_segs, h->d_nsegs, h->d_resp, d_kls, d_nout, cap);

@@ -33,7 +33,7 @@ for r in rd:
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(PROF, f"{tag}_launch_list_summary.txt"), "w") as f:
     f.write(f"# {tag} - ncu launch list (gpu__time_duration.sum, --clock-control none) of\n")
-    f.write("#   python bench.py --frames 300 --steps 1 --warmup 1 --cpu-sample 4\n")
+    f.write("#   python bench.py --frames 300 --steps 1 --warmup 1 --cpu-sample 4 --kitti-frames 0 --c5-frames 0\n")
     f.write("# Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  Raw list: "
             f"{tag}_launches.csv\n")
     f.write(f"# total {tot:.1f} us over {sum(a[0] for a in agg.values())} launches\n")
