@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0, help="frames per extraction chunk (0 = whole sequence)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="frames of the cpu_baseline sample")
     ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the persistent LSD region grower leaves to the matcher kernels of the other streams")
+    ap.add_argument("--e2e-trace", type=int, default=0, help="print the time marks of the last end-to-end step to stderr")
     ap.add_argument("--overlap-orb", type=int, default=1, help="device-resident step: let the line extractor start next to the ORB extractor instead of behind it")
     ap.add_argument("--e2e-order", default="orb_first", choices=["orb_first", "together"], help="e2e leg: call the ORB extractor before the line extractor's thread starts, or both at once")
     ap.add_argument("--device-glue", type=int, default=1, help="e2e leg: Frame glue (UnprojectStereo, IsInFrustum) through the batched F-row calls instead of numpy")
@@ -301,7 +302,7 @@ def run_ours(a, rank, world, local_rank, dist):
             if self.err:
                 raise self.err[0]
             r = fe.FeatureList((kl_np[i, :ln_np[i]], ld_np[i, :ln_np[i]], lc_np[i, :ln_np[i]]) for i in range(F))
-            r.dense = (kl_np, ln_np)
+            r.dense = (kl_np, ln_np, ld_np)
             return r
 
     def step_e2e():
@@ -375,6 +376,14 @@ def run_ours(a, rank, world, local_rank, dist):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t1
     barrier()
+    if a.e2e_trace and rank == 0:
+        e2e_fe.trace = []
+        t1 = time.perf_counter()
+        step_e2e()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        sys.stderr.write("e2e step: " + " | ".join(f"{k} {1e3 * (t - t1):.1f}" for k, t in e2e_fe.trace) + f" | synced {1e3 * (t2 - t1):.1f}\n")
+        e2e_fe.trace = None
     assert s2 == summary, "e2e pass produced different matches than the plan pass"
     # ---- p50 single-frame latency (extract both + match), frame by frame ----
     gb1 = fe.GpuBackend(api, H, W, NFEAT, chunk=1, device=dev)

@@ -508,7 +508,9 @@ PL_API int pl_frame_lines_in_frustum_batch(pl_match* h, int n_frames, const floa
  * its row band (Hamming, level +-1, disparity range), the 11x11 SAD sub-pixel refinement over 11 shifts read from BOTH
  * extractors' mvImagePyramid (which never leaves the device), and the final 1.5*1.4*median outlier rule.  left / right = the two
  * extractors after operator() on the rectified pair (frame `frame` of their last call); keys = mvKeys / mvKeysRight (image
- * coordinates), bf = mbf, b = mb.  u_right / depth = mvuRight / mvDepth (-1 = no match).  n_left, n_right <= 16384. */
+ * coordinates), bf = mbf, b = mb.  u_right / depth = mvuRight / mvDepth (-1 = no match).  n_left, n_right <= 16384.
+ * Returns PL_ERR_CAPACITY (outputs filled) when one of the extractors had a frame over its key point capacity pending from the
+ * device-pointer API: this call waits for both extractors and therefore consumes that report. */
 PL_API int pl_frame_compute_stereo_matches(pl_match* h, pl_orb* left, pl_orb* right, int frame, const pl_keypoint* keys_left,
                                            const uint8_t* desc_left, int n_left, const pl_keypoint* keys_right, const uint8_t* desc_right,
                                            int n_right, float bf, float b, float* u_right, float* depth);

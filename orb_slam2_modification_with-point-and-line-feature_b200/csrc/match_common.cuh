@@ -49,7 +49,18 @@ struct PlStage {
     uint8_t* h = nullptr;
     uint8_t* d = nullptr;
     size_t cap = 0, cur = 0;
+    // An API call that returns early with an error after upload() leaves the copy out of the pinned buffer (and the kernels reading
+    // the device side) in flight: the next call must not refill or free the buffers under them.
+    cudaStream_t busy_stream = nullptr;
+    bool in_flight = false;
+    void quiesce() {
+        if (in_flight) {
+            (void)cudaStreamSynchronize(busy_stream);
+            in_flight = false;
+        }
+    }
     int reserve(size_t bytes) {
+        quiesce();
         cur = 0;
         overflow = false;
         jobs.clear();
@@ -122,6 +133,8 @@ struct PlStage {
             for (int t = 1; t < nt; t++) th[t - 1].join();
         }
         jobs.clear();
+        busy_stream = st;
+        in_flight = true;
         PL_CUDA_TRY(cudaMemcpyAsync(d, h, cur, cudaMemcpyHostToDevice, st));
         return PL_OK;
     }
@@ -139,6 +152,7 @@ struct PlStage {
         return (T*)(d + off);
     }
     void release() {
+        quiesce();
         if (h) cudaFreeHost(h);
         if (d) cudaFree(d);
         h = d = nullptr;

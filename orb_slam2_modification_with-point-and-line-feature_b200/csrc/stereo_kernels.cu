@@ -198,8 +198,13 @@ PL_API int pl_frame_compute_stereo_matches(pl_match* h, pl_orb* left, pl_orb* ri
     for (int i = 0; i < n_right; i++) PL_CHECK_ARG(keys_right[i].octave >= 0 && keys_right[i].octave < S.n_levels);
     PL_CUDA_TRY(cudaSetDevice(h->device));
     h->last_launches = 0;
-    if ((rc = pl_orb_sync(left)) != PL_OK && rc != PL_ERR_CAPACITY) return rc;   // the pyramids must be complete
+    // the pyramids must be complete.  pl_orb_sync reports (and clears) the sticky capacity word of an extractor: a frame that
+    // overflowed emitted no key points, so the matches are computed for what the caller passed, but the caller is told
+    bool overflowed = false;
+    if ((rc = pl_orb_sync(left)) != PL_OK && rc != PL_ERR_CAPACITY) return rc;
+    overflowed |= rc == PL_ERR_CAPACITY;
     if ((rc = pl_orb_sync(right)) != PL_OK && rc != PL_ERR_CAPACITY) return rc;
+    overflowed |= rc == PL_ERR_CAPACITY;
     const size_t nl = (size_t)n_left, nrr = (size_t)n_right;
     if ((rc = h->in.reserve(padb(nl * sizeof(pl_keypoint)) + padb(nl * 32) + padb(nrr * sizeof(pl_keypoint)) + padb(nrr * 32) + padb(nl * 4) * 3)) != PL_OK)
         return rc;
@@ -225,6 +230,10 @@ PL_API int pl_frame_compute_stereo_matches(pl_match* h, pl_orb* left, pl_orb* ri
     PL_CUDA_TRY(pl::stream_sync(st));
     memcpy(u_right, h_ur, nl * 4);
     memcpy(depth, h_d, nl * 4);
+    if (overflowed) {
+        pl::set_error("pl_frame_compute_stereo_matches: an extractor reported a frame over its key point capacity (outputs are filled)");
+        return PL_ERR_CAPACITY;
+    }
     return PL_OK;
 }
 

@@ -13,6 +13,8 @@ forms over lists of views, line_search_batch(line_frame_views, map_line_views).
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import _native as N
@@ -145,33 +147,49 @@ class FrameLite:
             for F, (kls, ldesc, _) in zip(frames, lines):
                 F.set_lines(kls, ldesc)
             return
-        offs = np.concatenate([[0], np.cumsum(counts)])
         dense = getattr(lines, "dense", None)
-        kl = dense[0][np.arange(dense[0].shape[1])[None, :] < counts[:, None]] if dense is not None else np.concatenate([l[0] for l in lines])
-        fidx = np.repeat(np.arange(n), counts)
         h, w = depth.shape[1:]
-        sx = np.clip(np.rint(kl["sx"]).astype(np.int64), 0, w - 1)
-        sy = np.clip(np.rint(kl["sy"]).astype(np.int64), 0, h - 1)
-        ex = np.clip(np.rint(kl["ex"]).astype(np.int64), 0, w - 1)
-        ey = np.clip(np.rint(kl["ey"]).astype(np.int64), 0, h - 1)
-        ds = depth[fidx, sy, sx].astype(np.float64)
-        de = depth[fidx, ey, ex].astype(np.float64)
         K = frames[0].K
-        Rwc = np.stack([F.Rwc for F in frames]).astype(np.float64)[fidx]
-        Ow = np.stack([F.Ow for F in frames]).astype(np.float64)[fidx]
+        Rwc = np.stack([F.Rwc for F in frames]).astype(np.float64)
+        Ow = np.stack([F.Ow for F in frames]).astype(np.float64)
+        if dense is not None and dense[0].ndim == 2 and len(dense[0]) == n:
+            # the extractor's own (n, max_lines) output: every row at once (rows beyond a frame's count are never looked at);
+            # the batched matmul is the per-frame `pc @ Rwc.T` of unproject_lines, row for row
+            kl = dense[0]
+            sxf, syf, exf, eyf = (np.ascontiguousarray(kl[k]) for k in ("sx", "sy", "ex", "ey"))
+            with np.errstate(invalid="ignore"):
+                sx = np.clip(np.rint(sxf).astype(np.int64), 0, w - 1)
+                sy = np.clip(np.rint(syf).astype(np.int64), 0, h - 1)
+                ex = np.clip(np.rint(exf).astype(np.int64), 0, w - 1)
+                ey = np.clip(np.rint(eyf).astype(np.int64), 0, h - 1)
+            base = (np.arange(n, dtype=np.int64) * (h * w))[:, None]
+            flat = depth.reshape(-1)
+            ds = flat[base + sy * w + sx].astype(np.float64)
+            de = flat[base + ey * w + ex].astype(np.float64)
+            RT = Rwc.transpose(0, 2, 1)
 
-        def lift(px, py, z):
-            pc = np.stack([(px - K["cx"]) * z / K["fx"], (py - K["cy"]) * z / K["fy"], z], 1)
-            return np.einsum("nij,nj->ni", Rwc, pc) + Ow
+            def lift(px, py, z):
+                pc = np.stack([(px - K["cx"]) * z / K["fx"], (py - K["cy"]) * z / K["fy"], z], 2)
+                return np.matmul(pc, RT) + Ow[:, None, :]
 
-        s3 = lift(kl["sx"].astype(np.float64), kl["sy"].astype(np.float64), ds)
-        e3 = lift(kl["ex"].astype(np.float64), kl["ey"].astype(np.float64), de)
-        ok = (ds > 0) & (de > 0)
-        for t, F in enumerate(frames):
-            a, b = offs[t], offs[t + 1]
-            F.kls, F.ldesc = lines[t][0], lines[t][1]
-            F.ds, F.de = ds[a:b], de[a:b]
-            F._ul = (s3[a:b], e3[a:b], ok[a:b])
+            with np.errstate(invalid="ignore", over="ignore"):
+                s3 = lift(sxf.astype(np.float64), syf.astype(np.float64), ds)
+                e3 = lift(exf.astype(np.float64), eyf.astype(np.float64), de)
+                ok = (ds > 0) & (de > 0)
+            for t, F in enumerate(frames):
+                c = counts[t]
+                F.kls, F.ldesc = lines[t][0], lines[t][1]
+                F.ds, F.de = ds[t, :c], de[t, :c]
+                F._ul = (s3[t, :c], e3[t, :c], ok[t, :c])
+            ld = dense[2] if len(dense) > 2 else None
+            if (ld is not None and kl.flags.c_contiguous and ld.flags.c_contiguous and ld.dtype == np.uint8 and ld.shape[:2] == kl.shape
+                    and kl.dtype == N.KL_DTYPE):
+                # what the line searches read, as whole-sequence arrays: their views are then built for all frames at once
+                frames[0]._seq = dict(kl=kl, ld=ld, s3=np.ascontiguousarray(s3), e3=np.ascontiguousarray(e3), ok=ok.astype(np.uint8), counts=counts,
+                                      tcw=np.stack([F.Tcw[:3].reshape(-1) for F in frames]).astype(f32))
+            return
+        for F, (kls, ldesc, _) in zip(frames, lines):  # features handed over as a list of per-frame arrays
+            F.set_lines(kls, ldesc)
 
     def view(self, claimed, keep):
         return N.make_frame_view(self.kps, self.desc, self.u_right, claimed, self.bounds, self.K, self.Tcw[:3].reshape(-1), self.sf, keep)
@@ -294,11 +312,41 @@ class TrackingFrontEnd:
             w = TrackingFrontEnd._chk_w[len(m)] = np.arange(1, len(m) + 1, dtype=np.int64)
         return int(np.dot(m.astype(np.int64), w) + (len(m) * (len(m) + 1)) // 2)   # sum((m + 1) * (i + 1))
 
+    def _dense_lineframe_views(self, seq, tt, F0, keep):
+        """pl_lineframe_view of frames tt, built as one structured array (same fields as N.make_lineframe_view fills)."""
+        a = np.zeros(len(tt), np.dtype(N.LineFrameView))
+        a["n"] = seq["counts"][tt]
+        a["kl"] = seq["kl"].ctypes.data + tt * seq["kl"].strides[0]
+        a["desc"] = seq["ld"].ctypes.data + tt * seq["ld"].strides[0]
+        a["tcw"] = seq["tcw"][tt]
+        for k in ("fx", "fy", "cx", "cy"):
+            a[k] = float(self.K[k])
+        a["min_x"], a["min_y"], a["max_x"], a["max_y"] = [float(b) for b in F0.bounds]
+        a["cols"], a["rows"] = int(F0.size[0]), int(F0.size[1])
+        keep += [a, seq]
+        return list((N.LineFrameView * len(tt)).from_buffer(a))
+
+    @staticmethod
+    def _dense_mapline_views(seq, tt, keep):
+        """pl_mapline_view of the lines of frames tt lifted to 3-D (the `last` side of D3)."""
+        a = np.zeros(len(tt), np.dtype(N.MapLineView))
+        a["n"] = seq["counts"][tt]
+        a["start3d"] = seq["s3"].ctypes.data + tt * seq["s3"].strides[0]
+        a["end3d"] = seq["e3"].ctypes.data + tt * seq["e3"].strides[0]
+        a["kl"] = seq["kl"].ctypes.data + tt * seq["kl"].strides[0]
+        a["desc"] = seq["ld"].ctypes.data + tt * seq["ld"].strides[0]
+        a["valid"] = seq["ok"].ctypes.data + tt * seq["ok"].strides[0]
+        keep += [a, seq]
+        return list((N.MapLineView * len(tt)).from_buffer(a))
+
     def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True, batch=True):
         """features = (orb, lines); `lines` may be a concurrent.futures.Future: the point side (Frame-lite, C3, C2) does not
         need the lines, so it proceeds while the line extractor is still running — the reference runs its two extractors
         in two threads for the same reason (Frame.cc:152-155)."""
         n = len(gray)
+        trace = getattr(self, "trace", None)   # optional list of (label, perf_counter) marks: where an end-to-end step goes
+        mark = (lambda s_: trace.append((s_, time.perf_counter()))) if trace is not None else (lambda s_: None)
+        mark("start")
         if features is None:
             orb = self.b.extract_orb(gray)
             lines = self.b.extract_lines(gray)
@@ -321,6 +369,7 @@ class TrackingFrontEnd:
             if t % self.kf_every == 0:
                 lm.add_keyframe_points(frames[t])
         summary = [dict(frame=t, n_kp=len(frames[t].kps)) for t in range(n)]
+        mark("frames built")
         # ---- C3: ORBmatcher(0.9).SearchByProjection(Cur, Last, th=15) (Tracking.cc:1244) ----
         c3_t = list(range(1, n))
         cvs = [frames[t].view(None, keep) for t in c3_t]
@@ -330,25 +379,35 @@ class TrackingFrontEnd:
             last = frames[t - 1]
             lvs.append(N.make_lastframe_view(last.depth > 0, last.unproject_points(), last.desc, last.kps["octave"], last.kps["angle"],
                                              self._has_obs(len(last.kps)), last.Tcw[:3].reshape(-1), keep))
-        # C2 inputs that do not depend on the C3 result (Frame::IsInFrustum of the local map): prepared before the first
-        # matcher call, so that all of this host work overlaps the line extraction still running on the device
+        # C2 inputs that do not depend on the C3 result (Frame::IsInFrustum of the local map): host work that overlaps the line
+        # extraction still running on the device — and, when the point searches have a thread of their own, the C3 search
         c2_t = [t for t in range(n) if len(maps[t][0])]
         fr = []
-        tmp = LocalMap()
-        k = 0
-        while k < len(c2_t):  # consecutive frames that see the same map snapshot are projected together
-            k1 = k
-            while k1 < len(c2_t) and maps[c2_t[k1]][0] is maps[c2_t[k]][0]:
-                k1 += 1
-            tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[c2_t[k]][:5]
-            fr += [(tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]], backend=self.b if self.device_glue else None)]
-            k = k1
+        mark("C3 views built")
+
+        def frustum_of_local_map():
+            tmp = LocalMap()
+            k = 0
+            while k < len(c2_t):  # consecutive frames that see the same map snapshot are projected together
+                k1 = k
+                while k1 < len(c2_t) and maps[c2_t[k1]][0] is maps[c2_t[k]][0]:
+                    k1 += 1
+                tmp.pos, tmp.desc, tmp.normal, tmp.max_d, tmp.min_d = maps[c2_t[k]][:5]
+                fr.extend((tmp.desc,) + r for r in tmp.frustum_group([frames[t] for t in c2_t[k:k1]], backend=self.b if self.device_glue else None))
+                k = k1
+            mark("frustum done")
+
+        import threading
+        fr_ready = threading.Event()
+
         def point_searches():
             r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
             claimed = [None] * n
             for t, (m3, n3) in zip(c3_t, r3):
                 summary[t].update(c3_matches=n3, c3_sum=self._chk(m3))
                 claimed[t] = (m3 >= 0).astype(np.int32)
+            mark("  [points] C3 done")
+            fr_ready.wait()
             # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
             fvs, mvs, inview = [], [], []
             for t, (mdesc, inv, u, v, xr, lvl, vc) in zip(c2_t, fr):
@@ -361,9 +420,11 @@ class TrackingFrontEnd:
                     fvs.append(frames[t].view(claimed[t], keep))
                 mvs.append(N.make_mappoint_view(mdesc, inv, u, v, xr, lvl, vc, None, keep))
                 inview.append(int(inv.sum()))
+            mark("  [points] C2 views built")
             r2 = self.b.search_local_points_batch(fvs, mvs, 3.0, 0.8) if batch else [self.b.search_local_points(f, m, 3.0, 0.8) for f, m in zip(fvs, mvs)]
             for t, iv, (m2, n2) in zip(c2_t, inview, r2):
                 summary[t].update(c2_in_view=iv, c2_matches=n2, c2_sum=self._chk(m2))
+            mark("  [points] C2 done")
 
         # The point searches and the line side do not depend on each other.  A backend whose line matcher has its own handle
         # (its own stream and staging buffers) lets the point searches run on a second host thread while this one prepares and
@@ -371,7 +432,6 @@ class TrackingFrontEnd:
         # of the other side.  Same calls, same inputs, same results — only the order in wall-clock time changes.
         worker = None
         if batch and getattr(self.b, "concurrent_sides", False):
-            import threading
             err = []
 
             def guarded():
@@ -379,13 +439,20 @@ class TrackingFrontEnd:
                     point_searches()
                 except BaseException as e:  # re-raised on the caller's thread
                     err.append(e)
+            # (projecting the local map while C3 runs was measured and loses: its short device calls then queue behind the
+            # search's kernels on a GPU the region grower already fills)
+            frustum_of_local_map()
+            fr_ready.set()
             worker = threading.Thread(target=guarded)
             worker.start()
         else:
+            frustum_of_local_map()
+            fr_ready.set()
             point_searches()
         # ---- line side of the caller state ----
         if hasattr(lines, "result"):
             lines = lines.result()
+        mark("lines ready")
         lmaps = []
         lm = LocalMap()
         FrameLite.attach_lines_batch(frames, lines, depth)
@@ -394,18 +461,30 @@ class TrackingFrontEnd:
             lmaps.append((lm.ls, lm.le, lm.lkl, lm.ldesc))
             if t % self.kf_every == 0:
                 lm.add_keyframe_lines(frames[t])
+        mark("lines attached, line maps built")
         # ---- D3: LineMatcher(0.9).SearchByProjection(Cur, Last) (Tracking.cc:1247) ----
         d3_t = [t for t in c3_t if len(frames[t - 1].kls) and len(frames[t].kls)]
         lcv, llv = [], []
         cur_view = {}  # the current-frame side of D3 and D5 is the same view
-        for t in d3_t:
-            F, last = frames[t], frames[t - 1]
-            s3, e3, okl = last.unproject_lines()
-            cur_view[t] = N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep)
-            lcv.append(cur_view[t])
-            llv.append(N.make_mapline_view(s3, e3, last.kls, last.ldesc, okl, keep))
+        seq = getattr(frames[0], "_seq", None) if n else None
+        if seq is not None and d3_t:
+            # the same views as below, for all frames at once: the line features are rows of the extractor's dense output
+            tt = np.asarray(d3_t, np.int64)
+            lcv = self._dense_lineframe_views(seq, tt, frames[0], keep)
+            llv = self._dense_mapline_views(seq, tt - 1, keep)
+            cur_view = dict(zip(d3_t, lcv))
+        else:
+            for t in d3_t:
+                F, last = frames[t], frames[t - 1]
+                s3, e3, okl = last.unproject_lines()
+                cur_view[t] = N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep)
+                lcv.append(cur_view[t])
+                llv.append(N.make_mapline_view(s3, e3, last.kls, last.ldesc, okl, keep))
+        mark("D3 views built")
+
         def d3_search(lcv=lcv, llv=llv):
             rd3 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
+            mark("  [d3] D3 searched")
             for t, (ml, nl, rel, npj) in zip(d3_t, rd3):
                 summary[t].update(d3_proj=npj, d3_matches=nl, d3_relaxed=rel, d3_sum=self._chk(ml))
 
@@ -435,12 +514,14 @@ class TrackingFrontEnd:
             if id(lkl) not in snap_view:
                 snap_view[id(lkl)] = N.make_mapline_view(ls, le, lkl, ldesc, np.ones(len(lkl), np.uint8), keep)
             llv.append(snap_view[id(lkl)])
+        mark("D5 views built")
         if two_handles:
             rd5 = self.b.line_search_batch(lcv, llv, True)
         else:
             rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
         for t, (ml, nl, rel, npj) in zip(d5_t, rd5):
             summary[t].update(d5_proj=npj, d5_matches=nl, d5_relaxed=rel, d5_sum=self._chk(ml))
+        mark("D5 done")
         if d3_worker is not None:
             d3_worker.join()
             if d3_err:
@@ -449,6 +530,7 @@ class TrackingFrontEnd:
             worker.join()
             if err:
                 raise err[0]
+        mark("end")
         return summary
 
 
@@ -501,4 +583,6 @@ class GpuBackend:
         return self.m.UnprojectBatch(off, xy, z, rwc, ow, K)
 
     def is_in_frustum_batch(self, *a):
-        return self.m.IsInFrustumBatch(*a)
+        # on the line side's handle: the caller's thread projects the local map while the point searches (self.m) run on theirs,
+        # and the line searches only start after it
+        return self.ml.IsInFrustumBatch(*a)

@@ -64,3 +64,38 @@ def test_worker_errors_surface_on_the_callers_thread(seq, feats, oracle):
 
     with pytest.raises(RuntimeError, match="boom"):
         fe.TrackingFrontEnd(Failing(ob)).run(gray, depth, T, ob.scale_factors(), features=feats, batch=True)
+
+
+def test_dense_feature_arrays_give_the_same_schedule(seq, feats, oracle):
+    """The extractors' own (n, capacity) output arrays (what the end-to-end leg of bench.py hands over) take the vectorised paths of
+    the glue — one pass over the sequence for the line endpoints, the views of the line searches built as structured arrays: the
+    summary must be the one of the per-frame lists."""
+    fe = importlib.import_module(PKG + ".frontend")
+    N = importlib.import_module(PKG + "._native")
+    gray, depth, T = seq
+    ob = oracle.OracleBackend(1000)
+    sf = ob.scale_factors()
+    ref = fe.TrackingFrontEnd(ob).run(gray, depth, T, sf, features=feats, batch=True)
+    orb_l, line_l = feats
+    n = len(gray)
+    cap = max(len(o[0]) for o in orb_l) + 7
+    kp = np.zeros((n, cap), N.KP_DTYPE)
+    dd = np.full((n, cap, 32), 0xAB, np.uint8)
+    nn = np.array([len(o[0]) for o in orb_l], np.int32)
+    ml = max(len(l[0]) for l in line_l) + 3
+    kl = np.zeros((n, ml), N.KL_DTYPE)
+    for k in ("sx", "sy", "ex", "ey"):
+        kl[k] = np.nan     # rows beyond a frame's count hold anything
+    ld = np.full((n, ml, 32), 0xCD, np.uint8)
+    lc = np.zeros((n, ml, 3), np.float64)
+    ln = np.array([len(l[0]) for l in line_l], np.int32)
+    for i in range(n):
+        kp[i, :nn[i]], dd[i, :nn[i]] = orb_l[i][0], orb_l[i][1]
+        kl[i, :ln[i]], ld[i, :ln[i]], lc[i, :ln[i]] = line_l[i][0], line_l[i][1], line_l[i][2]
+    orb = fe.FeatureList((kp[i, :nn[i]], dd[i, :nn[i]]) for i in range(n))
+    orb.dense = (kp, nn)
+    lines = fe.FeatureList((kl[i, :ln[i]], ld[i, :ln[i]], lc[i, :ln[i]]) for i in range(n))
+    lines.dense = (kl, ln, ld)
+    tfe = fe.TrackingFrontEnd(ThreadedOracle(ob))
+    assert tfe.run(gray, depth, T, sf, features=(orb, lines), batch=True) == ref
+    assert tfe.keepalive and any(isinstance(k, dict) and "s3" in k for k in tfe.keepalive)   # the dense path was the one taken
