@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the persistent LSD region grower leaves to the matcher kernels of the other streams")
     ap.add_argument("--e2e-trace", type=int, default=0, help="print the time marks of the last end-to-end step to stderr")
     ap.add_argument("--overlap-orb", type=int, default=1, help="device-resident step: let the line extractor start next to the ORB extractor instead of behind it")
+    ap.add_argument("--e2e-shared-upload", type=int, default=1, help="e2e leg, order orb_first: the line extractor reads the frames the ORB extractor staged in HBM (pl_orb_staged_images_dev + pl_line_extract_batch_from_dev) instead of uploading them again")
     ap.add_argument("--e2e-order", default="orb_first", choices=["orb_first", "together"], help="e2e leg: call the ORB extractor before the line extractor's thread starts, or both at once")
     ap.add_argument("--device-glue", type=int, default=1, help="e2e leg: Frame glue (UnprojectStereo, IsInFrustum) through the batched F-row calls instead of numpy")
     ap.add_argument("--c5-frames", type=int, default=4096, help="frames of the config-5 leg (batched offline extraction sharded frame-wise over the ranks); 0 = skip")
@@ -187,6 +188,9 @@ class RecordingBackend:
     def search_local_points_batch(self, *a):
         return self.plan.record("search_local_points_batch", *a)
 
+    def search_local_map_batch(self, *a):
+        return self.plan.record("search_local_map_batch", *a)
+
     def line_search_batch(self, *a):
         return self.plan.record("line_search_batch", *a)
 
@@ -286,14 +290,20 @@ def run_ours(a, rank, world, local_rank, dist):
     class LinesLater:
         """result() waits for the line extractor's thread (the line side of the glue asks for it)."""
 
-        def __init__(self):
+        def __init__(self, shared=False):
             self.err = []
+            self.shared = shared
             self.th = threading.Thread(target=self.work)
             self.th.start()
 
         def work(self):
             try:
-                gb.line.extract_batch_into(hg, MAXL, kl_np, ld_np, lc_np, ln_np)
+                if self.shared:  # the frames are in HBM already: the ORB extractor's call staged them (one upload per frame, as one cv::Mat serves both extractors)
+                    d, n, r, c_, st_, fs = gb.orb.staged_images()
+                    assert (n, r, c_) == (F, H, W), "the ORB extractor staged another batch"
+                    gb.line.extract_batch_from_dev_into(d, n, r, c_, st_, fs, MAXL, kl_np, ld_np, lc_np, ln_np)
+                else:
+                    gb.line.extract_batch_into(hg, MAXL, kl_np, ld_np, lc_np, ln_np)
             except BaseException as e:
                 self.err.append(e)
 
@@ -305,13 +315,15 @@ def run_ours(a, rank, world, local_rank, dist):
             r.dense = (kl_np, ln_np, ld_np)
             return r
 
+    shared_upload = bool(a.e2e_shared_upload) and a.e2e_order == "orb_first" and chunk >= F
+
     def step_e2e():
         # ORB first (4-5 ms of device time), the line extractor right behind it on its own thread: next to the region grower's
         # resident CTAs the ORB kernels would only get what is left of every SM and arrive later, and the point side of the glue
         # needs them first
         if a.e2e_order == "orb_first":
             gb.orb.extract_batch_into(hg, kp_np, dd_np, nn_np)
-            lines_later = LinesLater()
+            lines_later = LinesLater(shared=shared_upload)
         else:
             lines_later = LinesLater()
             gb.orb.extract_batch_into(hg, kp_np, dd_np, nn_np)
@@ -472,9 +484,9 @@ def run_ours(a, rank, world, local_rank, dist):
         "p50_ms_per_frame": round(p50, 3),
         "p50_note": "streaming mode: one frame at a time, ORB || LSD+LBD extraction then SearchByProjection(Cur, Last); images resident in HBM",
         "step_breakdown_ms": {"extract": round(t_ext * 1e3, 2), "match": round(t_match * 1e3, 2), "matcher_calls": len(plan.calls)},
-        "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(2 * F * W * H),
+        "e2e": {"value": round(F * e2e_steps * world / t_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int((1 if shared_upload else 2) * F * W * H),
                 "d2h_bytes_per_step": int(F * (cap * 60 + MAXL * (68 + 32 + 24) + 8)), "steps": e2e_steps,
-                "note": "through the plugin's host-buffer entry points: pl_orb_extract_batch and pl_line_extract_batch are called from two host threads (as the reference's Frame constructor calls its two extractors, Frame.cc:152-155) with pinned host images and pinned host outputs, each call doing its own upload (hence 2 x the image bytes) and read-back; caller glue (Frame-lite: numpy + the batched F-row calls of the library) and the point searches run while the line extractor is still working; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
+                "note": "through the plugin's host-buffer entry points: pl_orb_extract_batch and pl_line_extract_batch are called from two host threads (as the reference's Frame constructor calls its two extractors, Frame.cc:152-155) with pinned host images and pinned host outputs" + (": the ORB call uploads the frames, the line call (pl_line_extract_batch_from_dev) reads them where that call staged them in HBM (pl_orb_staged_images_dev) — one upload per frame, as one cv::Mat serves both extractors — and each reads its results back;" if shared_upload else ", each call doing its own upload (hence 2 x the image bytes) and read-back;") + " caller glue (Frame-lite: numpy + the batched F-row calls of the library) and the point searches run while the line extractor is still working; matcher calls with host arrays, the point searches on a second host thread while the line side is prepared and searched"},
         "gpu_launches": int(launches_per_step * a.steps),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "config3_kitti": kitti, "config5_sharded": c5,

@@ -161,6 +161,15 @@ PL_API int pl_line_extract(pl_line* h, const uint8_t* gray, int rows, int cols, 
 PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step,
                                  size_t frame_stride, int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs,
                                  int* n_out);
+/* The Frame constructor hands BOTH extractors the same image (Frame.cc:152-155): after a host-pointer call of the ORB extractor
+ * the frames of its last chunk are still staged in HBM.  pl_orb_staged_images_dev returns them (valid until the handle's next
+ * extract call; n_frames = the whole batch when it fitted one chunk, max_batch >= n), pl_line_extract_batch_from_dev is
+ * pl_line_extract_batch reading its images from device memory (results to host memory, synchronous) — so a frame travels to the
+ * device once. */
+PL_API int pl_orb_staged_images_dev(pl_orb* h, const uint8_t** d_images, int* n_frames, int* rows, int* cols, size_t* step, size_t* frame_stride);
+PL_API int pl_line_extract_batch_from_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols, size_t step,
+                                          size_t frame_stride, int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs,
+                                          int* n_out);
 PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols,
                                      size_t step, size_t frame_stride, int max_lines, pl_keyline* d_kls,
                                      uint8_t* d_desc, double* d_coeffs, int* d_n_out);
@@ -282,6 +291,29 @@ PL_API int pl_orb_search_last_frame_batch(pl_match* h, int n, const pl_frame_vie
                                           int mono, int check_orientation, int* const* match_of_feature, int* n_matches);
 PL_API int pl_orb_search_local_points_batch(pl_match* h, int n, const pl_frame_view* F, const pl_mappoint_view* mps, float th,
                                             float nn_ratio, int* const* match_of_feature, int* n_matches);
+
+/* Tracking::SearchLocalPoints (Tracking.cc:1746-1813) as one call per batch of frames: Frame::isInFrustum(pMP, 0.5) of every
+ * local map point (Frame.cc:345-401, with MapPoint::PredictScale, MapPoint.cc:416-431 — the F4 arithmetic of
+ * pl_frame_is_in_frustum_batch) followed by ORBmatcher(nn_ratio).SearchByProjection(mCurrentFrame, mvpLocalMapPoints, th)
+ * (ORBmatcher.cc:44-124 — C2).  What IsInFrustum leaves on the map points (mbTrackInView, mTrackProjX / Y / XR,
+ * mnTrackScaleLevel, mTrackViewCos) stays in HBM between the two: nothing per (frame, map point) crosses the host.
+ * maps = the distinct snapshots of the local map (consecutive frames between two key frames see the same one and share its
+ * upload), map_of_frame[i] = the snapshot of frame i, ow = n x 3 camera centres (Frame::mOw), F[i].claimed = features already
+ * matched (mvpMapPoints[idx] != NULL, e.g. by C3).  n_in_view[i] (nullable) = map points that passed IsInFrustum (what
+ * Tracking.cc:1792 counts with IncreaseVisible).  Results equal pl_frame_is_in_frustum_batch + pl_orb_search_local_points_batch. */
+typedef struct pl_localmap_view {
+    int n;
+    const float* world_pos;          /* n x 3  MapPoint::GetWorldPos */
+    const float* normal;             /* n x 3  MapPoint::GetNormal */
+    const uint8_t* desc;             /* n x 32 MapPoint::GetDescriptor */
+    const float* min_dist_inv;       /* MapPoint::GetMinDistanceInvariance */
+    const float* max_dist_inv;       /* MapPoint::GetMaxDistanceInvariance */
+    const float* max_dist;           /* mfMaxDistance, read by PredictScale */
+    const uint8_t* has_observations; /* nullable: all 1 */
+} pl_localmap_view;
+PL_API int pl_orb_search_local_map_batch(pl_match* h, int n, const pl_frame_view* F, const float* ow, int n_maps, const pl_localmap_view* maps,
+                                         const int* map_of_frame, float viewing_cos_limit, float log_scale_factor, float th, float nn_ratio,
+                                         int* const* match_of_feature, int* n_matches, int* n_in_view);
 
 /* D2: LineMatcher::LineMatching predicate (LineMatcher.cpp:1463-1504) evaluated for all pairs, followed by the
  * "last matching i wins, every hit counts" rule of LineMatcher::SearchByProjection (LineMatcher.cpp:215-233) and

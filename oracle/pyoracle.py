@@ -515,6 +515,37 @@ def frame_is_in_frustum_batch(tcw, ow, K, bounds, n_levels, log_sf, world_pos, n
     return iv, px, py, pxr, lv, vc
 
 
+class _MapPointView(C.Structure):
+    """layout of pl_mappoint_view (include/plslam_c.h)"""
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("track_in_view", C.c_void_p), ("proj_x", C.c_void_p), ("proj_y", C.c_void_p),
+                ("proj_xr", C.c_void_p), ("scale_level", C.c_void_p), ("view_cos", C.c_void_p), ("has_observations", C.c_void_p)]
+
+
+def _f32_at(addr, count):
+    return np.ctypeslib.as_array((C.c_float * count).from_address(addr)) if count else np.zeros(0, np.float32)
+
+
+def search_local_map(frame_view, ow, map_view, cos_limit, log_sf, th, nn_ratio):
+    """Tracking::SearchLocalPoints (Tracking.cc:1746-1813) for one frame: Frame::isInFrustum of every map point of the snapshot, then
+    ORBmatcher::SearchByProjection(F, localPoints, th) — the oracle twin of pl_orb_search_local_map_batch.
+    frame_view / map_view: pl_frame_view / pl_localmap_view structures -> (match_of_feature, nmatches, map points in view)."""
+    m = map_view.n
+    K = dict(fx=frame_view.fx, fy=frame_view.fy, cx=frame_view.cx, cy=frame_view.cy, bf=frame_view.bf)
+    tcw = np.array(list(frame_view.tcw), np.float32)
+    bounds = (frame_view.min_x, frame_view.min_y, frame_view.max_x, frame_view.max_y)
+    iv, px, py, pxr, lv, vc = frame_is_in_frustum_batch(tcw[None], np.asarray(ow, np.float32).reshape(1, 3), K, bounds, frame_view.n_levels, log_sf,
+                                                        _f32_at(map_view.world_pos, 3 * m), _f32_at(map_view.normal, 3 * m),
+                                                        _f32_at(map_view.min_dist_inv, m), _f32_at(map_view.max_dist_inv, m),
+                                                        _f32_at(map_view.max_dist, m), cos_limit)
+    mv = _MapPointView()
+    mv.n = m
+    mv.desc, mv.has_observations = map_view.desc, map_view.has_observations
+    mv.track_in_view, mv.proj_x, mv.proj_y, mv.proj_xr = iv.ctypes.data, px.ctypes.data, py.ctypes.data, pxr.ctypes.data
+    mv.scale_level, mv.view_cos = lv.ctypes.data, vc.ctypes.data
+    match, n = search_local_points(frame_view, mv, th, nn_ratio)
+    return match, n, int(iv.sum())
+
+
 def frame_lines_in_frustum_batch(tcw, start3d, end3d):
     tcw = np.ascontiguousarray(tcw, np.float32).reshape(-1, 12)
     s3 = np.ascontiguousarray(start3d, np.float64).reshape(-1, 3)
@@ -635,6 +666,9 @@ class OracleBackend:
 
     def search_local_points_batch(self, fvs, mvs, th, nn):
         return [search_local_points(f, m, th, nn) for f, m in zip(fvs, mvs)]
+
+    def search_local_map_batch(self, fvs, ow, maps, map_of_frame, cos_limit, log_sf, th, nn):
+        return [search_local_map(f, ow[i], maps[map_of_frame[i]], cos_limit, log_sf, th, nn) for i, f in enumerate(fvs)]
 
     def line_search_batch(self, cvs, lvs):
         return [line_search_by_projection(c, l) for c, l in zip(cvs, lvs)]

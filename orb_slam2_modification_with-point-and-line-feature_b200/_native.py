@@ -139,6 +139,27 @@ def make_mappoint_view(desc, in_view, proj_x, proj_y, proj_xr, level, view_cos, 
     return v
 
 
+class LocalMapView(C.Structure):
+    """pl_localmap_view: one snapshot of the local map for pl_orb_search_local_map_batch (IsInFrustum + C2 on the device)."""
+    _fields_ = [("n", C.c_int), ("world_pos", C.c_void_p), ("normal", C.c_void_p), ("desc", C.c_void_p), ("min_dist_inv", C.c_void_p),
+                ("max_dist_inv", C.c_void_p), ("max_dist", C.c_void_p), ("has_observations", C.c_void_p)]
+
+
+def make_localmap_view(world_pos, normal, desc, min_dist_inv, max_dist_inv, max_dist, has_obs, keep):
+    wp = _c(world_pos, np.float32).reshape(-1, 3)
+    no = _c(normal, np.float32).reshape(-1, 3)
+    desc = _c(desc, np.uint8).reshape(-1, 32)
+    mi, ma, mr = (_c(a, np.float32) for a in (min_dist_inv, max_dist_inv, max_dist))
+    ho = None if has_obs is None else _c(has_obs, np.uint8)
+    assert len(no) == len(wp) == len(desc) == len(mi) == len(ma) == len(mr)
+    keep += [wp, no, desc, mi, ma, mr, ho]
+    v = LocalMapView()
+    v.n = len(wp)
+    v.world_pos, v.normal, v.desc, v.min_dist_inv, v.max_dist_inv, v.max_dist = _addr(wp), _addr(no), _addr(desc), _addr(mi), _addr(ma), _addr(mr)
+    v.has_observations = _addr(ho)
+    return v
+
+
 def make_lastframe_view(valid, world_pos, desc, octave, angle, has_obs, tcw, keep):
     valid = _c(valid, np.uint8)
     wp = _c(world_pos, np.float32)

@@ -131,6 +131,12 @@ class ORBextractor:
                                            C.c_int(cap), ptr(cnt)))
         self._last = (min(n, self.max_batch) if n % self.max_batch == 0 else n % self.max_batch, rows, cols)
 
+    def staged_images(self):
+        """(device address, n_frames, rows, cols, step, frame_stride) of the images the last host-pointer extract call left in HBM."""
+        d, n, r, c_, st, fs = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+        check(N.lib().pl_orb_staged_images_dev(self._h, C.byref(d), C.byref(n), C.byref(r), C.byref(c_), C.byref(st), C.byref(fs)))
+        return d.value, n.value, r.value, c_.value, st.value, fs.value
+
     def extract_batch_dev(self, d_gray, n, rows, cols, step, frame_stride, d_kps, d_desc, cap, d_nout):
         """All pointers are raw device addresses (ints); asynchronous on the handle's stream."""
         check(N.lib().pl_orb_extract_batch_dev(self._h, ptr(d_gray), C.c_int(n), C.c_int(rows), C.c_int(cols),
@@ -226,6 +232,12 @@ class LineExtractor:
         assert kls.shape == (n, max_lines) and desc.shape == (n, max_lines, 32) and co.shape == (n, max_lines, 3) and len(cnt) >= n
         check(N.lib().pl_line_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(fr.strides[1]),
                                             C.c_size_t(fr.strides[0]), C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), ptr(cnt)))
+
+    def extract_batch_from_dev_into(self, d_gray, n, rows, cols, step, frame_stride, max_lines, kls, desc, co, cnt):
+        """pl_line_extract_batch_from_dev: images already in HBM (e.g. ORBextractor.staged_images()), caller-owned host outputs."""
+        assert kls.shape == (n, max_lines) and desc.shape == (n, max_lines, 32) and co.shape == (n, max_lines, 3) and len(cnt) >= n
+        check(N.lib().pl_line_extract_batch_from_dev(self._h, ptr(d_gray), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(step),
+                                                     C.c_size_t(frame_stride), C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), ptr(cnt)))
 
     def extract_batch_dev(self, d_gray, n, rows, cols, step, frame_stride, max_lines, d_kls, d_desc, d_coef, d_nout):
         check(N.lib().pl_line_extract_batch_dev(self._h, ptr(d_gray), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(step),
@@ -409,6 +421,22 @@ class DescriptorMatcher:
     def SearchByProjectionLocalPointsBatch(self, frame_views, mp_views, th, nn_ratio):
         return self._batch_points(N.lib().pl_orb_search_local_points_batch, frame_views, mp_views, N.MapPointView, C.c_float(th),
                                   C.c_float(nn_ratio))
+
+    def SearchLocalMapBatch(self, frame_views, ow, map_views, map_of_frame, viewing_cos_limit, log_scale_factor, th, nn_ratio):
+        """Tracking::SearchLocalPoints for n frames: Frame::IsInFrustum of the local map + ORBmatcher::SearchByProjection(F, localPoints)
+        in one call, the projections staying on the device -> [(match_of_feature, nmatches, map points in view)]."""
+        n = len(frame_views)
+        fa = self._view_array(frame_views, N.FrameView)
+        ma = self._view_array(map_views, N.LocalMapView)
+        ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+        mof = np.ascontiguousarray(map_of_frame, np.int32).reshape(-1)
+        assert ow.shape[0] == n and mof.shape[0] == n
+        outs = [np.empty(max(v.n, 1), np.int32) for v in frame_views]
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        cnt, inv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        check(N.lib().pl_orb_search_local_map_batch(self._h, C.c_int(n), fa, ptr(ow), C.c_int(len(map_views)), ma, ptr(mof), C.c_float(viewing_cos_limit),
+                                                    C.c_float(log_scale_factor), C.c_float(th), C.c_float(nn_ratio), ptrs, ptr(cnt), ptr(inv)))
+        return [(outs[i][:frame_views[i].n], int(cnt[i]), int(inv[i])) for i in range(n)]
 
     def SearchLinesByProjectionBatch(self, cur_views, line_views):
         """LineMatcher::SearchByProjection for n (frame, map lines) pairs ->

@@ -315,6 +315,25 @@ PL_API int pl_frame_is_in_frustum_batch(pl_match* h, int n_frames, const float* 
     return PL_OK;
 }
 
+}  // extern "C"
+
+namespace pl {
+// k_is_in_frustum for callers in other translation units (pl_orb_search_local_map_batch keeps the planes on the device)
+int launch_is_in_frustum(cudaStream_t st, int n_frames, const float* d_tcw, const float* d_ow, float fx, float fy, float cx, float cy, float bf,
+                         const float bounds[4], float log_sf, float cos_limit, int n_levels, int m, const float* d_pos, const float* d_normal,
+                         const float* d_min_inv, const float* d_max_inv, const float* d_max_raw, uint8_t* d_in_view, float* d_x, float* d_y,
+                         float* d_xr, int* d_lvl, float* d_vc) {
+    if (n_frames <= 0 || m <= 0) return PL_OK;
+    FrustumArgs A{fx, fy, cx, cy, bf, bounds[0], bounds[1], bounds[2], bounds[3], log_sf, cos_limit, n_levels, m};
+    k_is_in_frustum<<<dim3((m + 255) / 256, n_frames), 256, 0, st>>>(d_tcw, d_ow, A, d_pos, d_normal, d_min_inv, d_max_inv, d_max_raw, d_in_view, d_x,
+                                                                      d_y, d_xr, d_lvl, d_vc);
+    PL_CUDA_TRY(cudaGetLastError());
+    return PL_OK;
+}
+}  // namespace pl
+
+extern "C" {
+
 PL_API int pl_frame_lines_in_frustum_batch(pl_match* h, int n_frames, const float* tcw, int m, const double* start3d, const double* end3d,
                                            uint8_t* in_view) {
     PL_CHECK_ARG(h && n_frames >= 0 && m >= 0 && n_frames <= 65535);

@@ -2353,8 +2353,9 @@ PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_fr
     return PL_OK;
 }
 
-PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride,
-                                 int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs, int* n_out) {
+// host outputs; the images come from host memory (staged per chunk) or are already on the device
+static int line_extract_to_host(pl_line* h, const uint8_t* gray, bool gray_on_device, int n_frames, int rows, int cols, size_t step, size_t frame_stride,
+                                int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs, int* n_out) {
     PL_CHECK_ARG(h && kls && desc && coeffs && n_out);
     int rc = line_check_common(h, gray, n_frames, rows, cols, step, max_lines);
     if (rc != PL_OK) return rc;
@@ -2365,14 +2366,18 @@ PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, 
     h->last_launches = 0;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
-        // one copy per chunk when the caller's frames are dense and already have the staging pitch, else one strided copy per frame
-        if (step == in_pitch && frame_stride == in_pitch * (size_t)rows)
-            PL_CUDA_TRY(cudaMemcpyAsync(h->d_in, gray + (size_t)f0 * frame_stride, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->stream));
-        else
-            for (int f = 0; f < nf; f++)
-                PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride, step,
-                                              cols, rows, cudaMemcpyHostToDevice, h->stream));
-        rc = line_launch_chunk(h, h->d_in, nf, in_pitch, in_pitch * rows, h->d_kls, h->d_desc, h->d_coef, max_lines, h->d_nout);
+        if (gray_on_device) {
+            rc = line_launch_chunk(h, gray + (size_t)f0 * frame_stride, nf, step, frame_stride, h->d_kls, h->d_desc, h->d_coef, max_lines, h->d_nout);
+        } else {
+            // one copy per chunk when the caller's frames are dense and already have the staging pitch, else one strided copy per frame
+            if (step == in_pitch && frame_stride == in_pitch * (size_t)rows)
+                PL_CUDA_TRY(cudaMemcpyAsync(h->d_in, gray + (size_t)f0 * frame_stride, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->stream));
+            else
+                for (int f = 0; f < nf; f++)
+                    PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride, step,
+                                                  cols, rows, cudaMemcpyHostToDevice, h->stream));
+            rc = line_launch_chunk(h, h->d_in, nf, in_pitch, in_pitch * rows, h->d_kls, h->d_desc, h->d_coef, max_lines, h->d_nout);
+        }
         if (rc != PL_OK) return rc;
         PL_CUDA_TRY(cudaMemcpyAsync(n_out + f0, h->d_nout, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
         if ((rc = line_check_flags(h, nf)) != PL_OK) return rc;
@@ -2385,6 +2390,16 @@ PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, 
         PL_CUDA_TRY(pl::stream_sync(h->stream));
     }
     return PL_OK;
+}
+
+PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride,
+                                 int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs, int* n_out) {
+    return line_extract_to_host(h, gray, false, n_frames, rows, cols, step, frame_stride, max_lines, kls, desc, coeffs, n_out);
+}
+
+PL_API int pl_line_extract_batch_from_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride,
+                                          int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs, int* n_out) {
+    return line_extract_to_host(h, d_gray, true, n_frames, rows, cols, step, frame_stride, max_lines, kls, desc, coeffs, n_out);
 }
 
 PL_API int pl_line_extract(pl_line* h, const uint8_t* gray, int rows, int cols, size_t step, int max_lines, pl_keyline* kls,

@@ -172,6 +172,11 @@ struct pl_match {
 };
 
 namespace pl {
+// frame_kernels.cu: Frame::IsInFrustum of n_frames frames against one snapshot of m map points, device pointers throughout
+int launch_is_in_frustum(cudaStream_t st, int n_frames, const float* d_tcw, const float* d_ow, float fx, float fy, float cx, float cy, float bf,
+                         const float bounds[4], float log_sf, float cos_limit, int n_levels, int m, const float* d_pos, const float* d_normal,
+                         const float* d_min_inv, const float* d_max_inv, const float* d_max_raw, uint8_t* d_in_view, float* d_x, float* d_y,
+                         float* d_xr, int* d_lvl, float* d_vc);
 inline int match_scratch(pl_match* h, int slot, size_t bytes, void** out) {
     if (h->d_cap[slot] < bytes) {
         if (h->d_buf[slot]) cudaFree(h->d_buf[slot]);

@@ -910,6 +910,8 @@ struct pl_orb {
     int* h_flags = nullptr;  // pinned
     int* d_sticky = nullptr; // capacity flags of the device-pointer API since the last pl_orb_sync
     int last_batch = 0;      // frames of the last chunk (for debug reads)
+    int staged_frames = 0;   // frames of the caller's images in d_in after a host-pointer call (its last chunk), 0 = none
+    int staged_rows = 0, staged_cols = 0;
     int last_launches = 0;
     size_t oct_smem = 0;
     // optional per-stage timing (CUDA events on the launching stream)
@@ -1373,6 +1375,21 @@ PL_API int pl_orb_extract_batch_dev(pl_orb* h, const uint8_t* d_gray, int n_fram
     return PL_OK;
 }
 
+PL_API int pl_orb_staged_images_dev(pl_orb* h, const uint8_t** d_images, int* n_frames, int* rows, int* cols, size_t* step, size_t* frame_stride) {
+    PL_CHECK_ARG(h && d_images && n_frames && rows && cols && step && frame_stride);
+    if (h->staged_frames <= 0 || !h->d_in) {
+        set_error("no images staged: pl_orb_staged_images_dev follows a host-pointer extract call");
+        return PL_ERR_STATE;
+    }
+    *d_images = h->d_in;
+    *n_frames = h->staged_frames;
+    *rows = h->staged_rows;
+    *cols = h->staged_cols;
+    *step = align_up((size_t)h->staged_cols, 16);
+    *frame_stride = *step * (size_t)h->staged_rows;
+    return PL_OK;
+}
+
 PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step,
                                 size_t frame_stride, pl_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
     PL_CHECK_ARG(h && kps && desc && n_out && cap > 0);
@@ -1411,6 +1428,7 @@ PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, in
             for (int f = 0; f < nf; f++)
                 PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride,
                                               step, cols, rows, cudaMemcpyHostToDevice, h->stream));
+        h->staged_frames = nf; h->staged_rows = rows; h->staged_cols = cols;
         rc = launch_chunk(h, h->d_in, nf, in_pitch, in_pitch * rows, h->d_kps, h->d_desc, cap, h->d_nout);
         if (rc != PL_OK) return rc;
         PL_CUDA_TRY(cudaMemcpyAsync(n_out + f0, h->d_nout, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));

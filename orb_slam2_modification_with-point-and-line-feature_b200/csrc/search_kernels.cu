@@ -1093,6 +1093,20 @@ void put_frame(PlStage& st, const pl_frame_view& F, FrameDev& D) {
     D.inv_h = (float)kGridRows / (F.max_y - F.min_y);
 }
 
+// map points in view per instance (mnMatchesInliers bookkeeping of the caller: Tracking.cc:1792 counts them as visible)
+__global__ void __launch_bounds__(256) k_count_in_view(const SearchDev* __restrict__ SD, int* __restrict__ cnt) {
+    __shared__ int s;
+    const SearchDev& S = SD[blockIdx.x];
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int c = 0;
+    for (int i = threadIdx.x; i < S.np; i += blockDim.x) c += S.valid[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) cnt[blockIdx.x] = s;
+}
+
 struct BatchScratch {
     int *sorted_idx, *cell_start, *cand_n, *cand_off, *totals, *inst_base, *match, *rec, *out;
     unsigned int* cand;
@@ -1274,6 +1288,120 @@ PL_API int pl_orb_search_local_points_batch(pl_match* h, int n, const pl_frame_v
     const SearchDev* d_sd = h->in.put(sd.data(), (size_t)n);
     { int urc = h->in.upload(h->stream); if (urc != PL_OK) return urc; }
     return run_search<1>(h, sd, d_sd, n, total_feats, total_pts, total_n2, max_n2, max_np, max_feat, th, nn_ratio, 0, match_of_feature, n_matches);
+}
+
+PL_API int pl_orb_search_local_map_batch(pl_match* h, int n, const pl_frame_view* F, const float* ow, int n_maps, const pl_localmap_view* maps,
+                                         const int* map_of_frame, float viewing_cos_limit, float log_scale_factor, float th, float nn_ratio,
+                                         int* const* match_of_feature, int* n_matches, int* n_in_view) {
+    PL_CHECK_ARG(h && n >= 0 && n_maps >= 0 && log_scale_factor > 0.f);
+    PL_CHECK_ARG(n == 0 || (F && ow && maps && map_of_frame && match_of_feature && n_matches && n_maps > 0));
+    if (n == 0) return PL_OK;
+    size_t bytes = padb(sizeof(SearchDev) * (size_t)n) + padb((size_t)n * 48) + padb((size_t)n * 12);
+    for (int k = 0; k < n_maps; k++) {
+        const pl_localmap_view& M = maps[k];
+        PL_CHECK_ARG(M.n >= 0 && (M.n == 0 || (M.world_pos && M.normal && M.desc && M.min_dist_inv && M.max_dist_inv && M.max_dist)));
+        const size_t m = (size_t)M.n;
+        bytes += padb(m * 12) * 2 + padb(m * 32) + padb(m * 4) * 3 + padb(m);
+    }
+    int total_feats = 0, total_n2 = 0, max_n2 = 1, max_np = 0, max_feat = 0;
+    long long total_pts_ll = 0;
+    for (int i = 0; i < n; i++) {
+        int rc = check_frame(&F[i]);
+        if (rc != PL_OK) return rc;
+        PL_CHECK_ARG(map_of_frame[i] >= 0 && map_of_frame[i] < n_maps);
+        PL_CHECK_ARG(match_of_feature[i] != nullptr || F[i].n == 0);
+        bytes += frame_bytes(F[i]);
+        total_pts_ll += maps[map_of_frame[i]].n;
+    }
+    if (total_pts_ll > 0x7fffffffLL / 4) { set_error("too many (frame, map point) pairs in one batch"); return PL_ERR_CAPACITY; }
+    const int total_pts = (int)total_pts_ll;
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    int rc = h->in.reserve(bytes);
+    if (rc != PL_OK) return rc;
+    // what IsInFrustum leaves on the map points, per (frame, map point): device only
+    const size_t tp = (size_t)std::max(total_pts, 1), plane4 = padb(tp * 4);
+    void* p;
+    if ((rc = match_scratch(h, 16, padb(tp) + plane4 * 5, &p)) != PL_OK) return rc;
+    uint8_t* d_iv = (uint8_t*)p;
+    float* d_x = (float*)(d_iv + padb(tp));
+    float* d_y = (float*)((uint8_t*)d_x + plane4);
+    float* d_xr = (float*)((uint8_t*)d_y + plane4);
+    int* d_lvl = (int*)((uint8_t*)d_xr + plane4);
+    float* d_vc = (float*)((uint8_t*)d_lvl + plane4);
+    if ((rc = match_scratch(h, 17, (size_t)n * 4, &p)) != PL_OK) return rc;
+    int* d_cnt = (int*)p;
+    struct MapDev { const float *pos, *normal, *mi, *ma, *mr; const uint4* desc; const uint8_t* obs; };
+    std::vector<MapDev> md(n_maps);
+    for (int k = 0; k < n_maps; k++) {
+        const pl_localmap_view& M = maps[k];
+        const size_t m = (size_t)M.n;
+        md[k].pos = h->in.put(M.world_pos, m * 3);
+        md[k].normal = h->in.put(M.normal, m * 3);
+        md[k].desc = (const uint4*)h->in.put(M.desc, m * 32);
+        md[k].mi = h->in.put(M.min_dist_inv, m);
+        md[k].ma = h->in.put(M.max_dist_inv, m);
+        md[k].mr = h->in.put(M.max_dist, m);
+        md[k].obs = M.has_observations ? h->in.put(M.has_observations, m) : nullptr;
+    }
+    std::vector<float> tcw((size_t)n * 12);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 12; k++) tcw[(size_t)i * 12 + k] = F[i].tcw[k];
+    const float* d_tcw = h->in.put(tcw.data(), tcw.size());
+    const float* d_ow = h->in.put(ow, (size_t)n * 3);
+    std::vector<SearchDev> sd(n);
+    int pt = 0;
+    for (int i = 0; i < n; i++) {
+        SearchDev& S = sd[i];
+        memset(&S, 0, sizeof(S));
+        put_frame(h->in, F[i], S.F);
+        const MapDev& D = md[map_of_frame[i]];
+        const int m = maps[map_of_frame[i]].n;
+        S.np = m;
+        S.valid = d_iv + pt;
+        S.pdesc = D.desc;
+        S.level = d_lvl + pt;
+        S.proj_x = d_x + pt;
+        S.proj_y = d_y + pt;
+        S.proj_xr = d_xr + pt;
+        S.view_cos = d_vc + pt;
+        S.has_obs = D.obs;
+        int n2 = 1;
+        while (n2 < std::max(F[i].n, 1)) n2 <<= 1;
+        S.n2 = n2;
+        S.pt_base = pt; S.feat_base = total_feats; S.sort_base = total_n2;
+        pt += m; total_feats += F[i].n; total_n2 += n2;
+        max_n2 = std::max(max_n2, n2); max_np = std::max(max_np, m); max_feat = std::max(max_feat, F[i].n);
+    }
+    const SearchDev* d_sd = h->in.put(sd.data(), (size_t)n);
+    cudaStream_t st = h->stream;
+    { int urc = h->in.upload(st); if (urc != PL_OK) return urc; }
+    // Frame::IsInFrustum: consecutive frames that look at the same snapshot with the same camera are one launch
+    int launches = 0;
+    for (int i = 0; i < n;) {
+        int j = i + 1;
+        const pl_frame_view& A = F[i];
+        while (j < n && map_of_frame[j] == map_of_frame[i] && F[j].fx == A.fx && F[j].fy == A.fy && F[j].cx == A.cx && F[j].cy == A.cy &&
+               F[j].bf == A.bf && F[j].min_x == A.min_x && F[j].min_y == A.min_y && F[j].max_x == A.max_x && F[j].max_y == A.max_y &&
+               F[j].n_levels == A.n_levels && j - i < 65535)
+            j++;
+        const MapDev& D = md[map_of_frame[i]];
+        const float bounds[4] = {A.min_x, A.min_y, A.max_x, A.max_y};
+        const int b = sd[i].pt_base;
+        if ((rc = pl::launch_is_in_frustum(st, j - i, d_tcw + (size_t)i * 12, d_ow + (size_t)i * 3, A.fx, A.fy, A.cx, A.cy, A.bf, bounds, log_scale_factor,
+                                           viewing_cos_limit, A.n_levels, maps[map_of_frame[i]].n, D.pos, D.normal, D.mi, D.ma, D.mr, d_iv + b, d_x + b,
+                                           d_y + b, d_xr + b, d_lvl + b, d_vc + b)) != PL_OK)
+            return rc;
+        launches += maps[map_of_frame[i]].n > 0;
+        i = j;
+    }
+    k_count_in_view<<<n, 256, 0, st>>>(d_sd, d_cnt);
+    launches++;
+    rc = run_search<1>(h, sd, d_sd, n, total_feats, total_pts, total_n2, max_n2, max_np, max_feat, th, nn_ratio, 0, match_of_feature, n_matches);
+    h->last_launches += launches;
+    if (rc != PL_OK) return rc;
+    if (n_in_view) PL_CUDA_TRY(cudaMemcpy(n_in_view, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost));  // (the stream is idle: run_search waited for it)
+    return PL_OK;
 }
 
 PL_API int pl_orb_search_last_frame(pl_match* h, const pl_frame_view* Cur, const pl_lastframe_view* Last, float th, int mono,

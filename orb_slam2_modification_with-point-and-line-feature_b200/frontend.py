@@ -283,7 +283,7 @@ class TrackingFrontEnd:
     (`batch=True`, the offline / throughput mode) or frame by frame (`batch=False`, the streaming mode).  Both modes
     run the same searches on the same inputs and return the same summary."""
 
-    def __init__(self, backend, K=TUM1, keyframe_every=10, device_glue=False):
+    def __init__(self, backend, K=TUM1, keyframe_every=10, device_glue=False, fused_local_map=True):
         """device_glue: run the Frame glue (UnprojectStereo, IsInFrustum) through the backend's batched F-row calls instead of
         numpy.  Off by default for the throughput runs: while the ordered LSD stage owns every SM, work queued on the device
         waits for it, whereas the host cores are idle — the numpy path overlaps the line extraction, the device path queues
@@ -292,6 +292,7 @@ class TrackingFrontEnd:
         self.K = K
         self.kf_every = keyframe_every
         self.device_glue = device_glue
+        self.fused_local_map = fused_local_map
         self.keepalive = []  # arrays referenced by the views handed to the backend (views hold raw addresses)
 
     _chk_w = {}
@@ -399,6 +400,8 @@ class TrackingFrontEnd:
 
         import threading
         fr_ready = threading.Event()
+        # Tracking::SearchLocalPoints as ONE call (IsInFrustum + C2, the projections staying on the device) when the backend has it
+        fused = batch and self.fused_local_map and hasattr(self.b, "search_local_map_batch")
 
         def point_searches():
             r3 = self.b.search_last_frame_batch(cvs, lvs, 15.0) if batch else [self.b.search_last_frame(c, l, 15.0) for c, l in zip(cvs, lvs)]
@@ -407,6 +410,30 @@ class TrackingFrontEnd:
                 summary[t].update(c3_matches=n3, c3_sum=self._chk(m3))
                 claimed[t] = (m3 >= 0).astype(np.int32)
             mark("  [points] C3 done")
+            if fused:
+                fvs, snaps, snap_of, mof = [], [], {}, []
+                for t in c2_t:
+                    if t in cv_of:
+                        fv = type(cv_of[t]).from_buffer_copy(cv_of[t])
+                        keep.append(claimed[t])
+                        fv.claimed = claimed[t].__array_interface__["data"][0]
+                        fvs.append(fv)
+                    else:
+                        fvs.append(frames[t].view(claimed[t], keep))
+                    pos, desc, normal, max_d, min_d = maps[t][:5]
+                    if id(pos) not in snap_of:
+                        snap_of[id(pos)] = len(snaps)
+                        snaps.append(N.make_localmap_view(pos, normal, desc, min_d, max_d, max_d, None, keep))
+                    mof.append(snap_of[id(pos)])
+                sf_ = frames[0].sf
+                log_sf = float(f32(np.log(f32(sf_[1] / sf_[0]))))
+                mark("  [points] C2 views built")
+                r2 = self.b.search_local_map_batch(fvs, np.stack([frames[t].Ow for t in c2_t]).astype(f32) if c2_t else np.zeros((0, 3), f32),
+                                                   snaps, mof, 0.5, log_sf, 3.0, 0.8)
+                for t, (m2, n2, iv) in zip(c2_t, r2):
+                    summary[t].update(c2_in_view=iv, c2_matches=n2, c2_sum=self._chk(m2))
+                mark("  [points] C2 done")
+                return
             fr_ready.wait()
             # ---- C2: ORBmatcher(0.8).SearchByProjection(F, localPoints, th=3) (Tracking.cc:1812) ----
             fvs, mvs, inview = [], [], []
@@ -441,12 +468,14 @@ class TrackingFrontEnd:
                     err.append(e)
             # (projecting the local map while C3 runs was measured and loses: its short device calls then queue behind the
             # search's kernels on a GPU the region grower already fills)
-            frustum_of_local_map()
+            if not fused:
+                frustum_of_local_map()
             fr_ready.set()
             worker = threading.Thread(target=guarded)
             worker.start()
         else:
-            frustum_of_local_map()
+            if not fused:
+                frustum_of_local_map()
             fr_ready.set()
             point_searches()
         # ---- line side of the caller state ----
@@ -574,6 +603,9 @@ class GpuBackend:
 
     def search_local_points_batch(self, fvs, mvs, th, nn):
         return self.m.SearchByProjectionLocalPointsBatch(fvs, mvs, th, nn)
+
+    def search_local_map_batch(self, fvs, ow, maps, map_of_frame, cos_limit, log_sf, th, nn):
+        return self.m.SearchLocalMapBatch(fvs, ow, maps, map_of_frame, cos_limit, log_sf, th, nn)
 
     def line_search_batch(self, cvs, lvs, second=False):
         return (self.ml2 if second else self.ml).SearchLinesByProjectionBatch(cvs, lvs)

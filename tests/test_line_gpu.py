@@ -75,6 +75,30 @@ def test_batch_equals_single(api, synth, oracle):
     assert np.array_equal(d2, desc) and np.array_equal(n2, cnt) and np.array_equal(k2, kls)
 
 
+def test_line_extractor_reads_the_frames_the_orb_extractor_staged(api, synth):
+    """One upload per frame (Frame.cc:152-155 hands both extractors the same cv::Mat): pl_orb_staged_images_dev +
+    pl_line_extract_batch_from_dev give what pl_line_extract_batch gives from host memory; odd width (the staging pitch is padded)."""
+    N = api.N
+    for w, h in ((640, 480), (333, 250)):
+        frames = synth.frames(6100, 5, w, h)
+        orb = api.ORBextractor(500, 1.2, 8, 20, 7, max_cols=w, max_rows=h, max_batch=8)
+        cap = orb.max_keypoints()
+        kp, dd, nn = np.zeros((5, cap), N.KP_DTYPE), np.zeros((5, cap, 32), np.uint8), np.zeros(5, np.int32)
+        with pytest.raises(Exception):
+            orb.staged_images()          # nothing staged before the first host-pointer call
+        orb.extract_batch_into(frames, kp, dd, nn)
+        d, n, r, c, st, fs = orb.staged_images()
+        assert (n, r, c) == (5, h, w) and st % 16 == 0 and st >= w and fs == st * h
+        ex = api.LineExtractor(max_cols=w, max_rows=h, max_batch=8)
+        ref = ex.extract_batch(frames)
+        kl, ld, lc, ln = np.zeros((5, 80), N.KL_DTYPE), np.zeros((5, 80, 32), np.uint8), np.zeros((5, 80, 3), np.float64), np.zeros(5, np.int32)
+        ex.extract_batch_from_dev_into(d, n, r, c, st, fs, 80, kl, ld, lc, ln)
+        assert np.array_equal(ln, ref[3]) and ln.sum() > 50
+        for i in range(5):
+            assert np.array_equal(kl[i, :ln[i]], ref[0][i, :ln[i]]) and np.array_equal(ld[i, :ln[i]], ref[1][i, :ln[i]])
+            assert np.array_equal(lc[i, :ln[i]], ref[2][i, :ln[i]])
+
+
 def test_max_lines_parameter(api, synth, oracle):
     img = synth.frame(1000, 640, 480)
     ex = api.LineExtractor()

@@ -26,7 +26,8 @@ def feats(seq, oracle):
 class Recorder:
     """Wraps a backend and records every matcher call's outputs."""
 
-    NAMES = ("search_last_frame", "search_local_points", "search_last_frame_batch", "search_local_points_batch", "line_search_batch")
+    NAMES = ("search_last_frame", "search_local_points", "search_last_frame_batch", "search_local_points_batch", "line_search_batch",
+             "search_local_map_batch")
 
     def __init__(self, b):
         self.b = b
@@ -48,7 +49,9 @@ def _flatten(log):
     threads, so their relative order in the log is not defined."""
     out = []
     for k, r in log:
-        if k.endswith("_batch"):
+        if k == "search_local_map_batch":   # IsInFrustum + C2 in one call: its C2 part is compared with the frame-by-frame C2 calls
+            out += [("search_local_points", x[:2]) for x in r]
+        elif k.endswith("_batch"):
             out += [(k[:-6], x) for x in r]
         else:
             out.append((k, r))
@@ -98,6 +101,61 @@ def test_sequence_with_device_glue_bit_exact(seq, feats, api, oracle, pkg):
     for (kg, rg), (ko, ro) in zip(got, ref):
         assert kg == ko and np.array_equal(rg[0], ro[0]) and tuple(rg[1:]) == tuple(ro[1:]), kg
     assert sum(r.get("c2_matches", 0) for r in so) > 200 and sum(r.get("c3_matches", 0) for r in so) > 1000
+
+
+def test_search_local_map_equals_frustum_plus_search(api, oracle, synth):
+    """pl_orb_search_local_map_batch (Tracking::SearchLocalPoints: IsInFrustum + C2 with the projections left on the device) against
+    the oracle's two steps and against the library's own two calls: snapshots shared by runs of frames, an empty snapshot, an empty
+    frame, a snapshot used by two separate runs."""
+    import matchgen
+    N = api.N
+    rng = np.random.default_rng(77)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    K = synth.TUM1
+    log_sf = float(np.float32(np.log(np.float32(sf[1] / sf[0]))))
+    keep, snaps, raw = [], [], []
+    for m in (2500, 0, 900):
+        tcw, ow, Xw, nrm, mi, ma, mr = matchgen.frustum_case(rng, 4, m, K)
+        desc = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+        snaps.append(N.make_localmap_view(Xw, nrm, desc, mi, ma, mr, None, keep))
+        raw.append((tcw, ow, Xw, nrm, mi, ma, mr, desc))
+    mof = [0, 0, 0, 1, 2, 2, 0, 0]
+    nfeat = [800, 1000, 0, 500, 700, 300, 1200, 64]
+    fvs, ows, tcws = [], [], []
+    for i, (k, nf) in enumerate(zip(mof, nfeat)):
+        tcw, ow = raw[k][0][i % 4], raw[k][1][i % 4]
+        kp, desc, ur = matchgen.rand_frame(rng, nf, N)
+        m = snaps[k].n
+        if m and nf:   # features on top of projected map points, with their descriptors (so that there is something to match)
+            iv, px, py, pxr, lv, vc = oracle.frame_is_in_frustum_batch(tcw[None], ow[None], K, (0, 0, 640, 480), 8, log_sf, *raw[k][2:7])
+            vis = np.flatnonzero(iv[0])[: nf // 2]
+            kp["x"][: len(vis)] = px[0][vis] + rng.normal(0, 0.7, len(vis)).astype(np.float32)
+            kp["y"][: len(vis)] = py[0][vis] + rng.normal(0, 0.7, len(vis)).astype(np.float32)
+            kp["octave"][: len(vis)] = lv[0][vis]
+            desc[: len(vis)] = matchgen.noisy(raw[k][7][vis], rng, 0.06)
+        claimed = (rng.random(nf) < 0.1).astype(np.int32)
+        fvs.append(N.make_frame_view(kp, desc, ur, claimed, (0, 0, 640, 480), K, tcw, sf, keep))
+        ows.append(ow)
+        tcws.append(tcw)
+    ows = np.stack(ows)
+    m = api.DescriptorMatcher()
+    got = m.SearchLocalMapBatch(fvs, ows, snaps, mof, 0.5, log_sf, 3.0, 0.8)
+    total = 0
+    for i, (gm, gn, giv) in enumerate(got):
+        om, on, oiv = oracle.search_local_map(fvs[i], ows[i], snaps[mof[i]], 0.5, log_sf, 3.0, 0.8)
+        assert np.array_equal(gm, om) and gn == on and giv == oiv, i
+        total += gn
+    assert total > 500
+    # the library's own two calls give the same
+    for i in (0, 4, 7):
+        k = mof[i]
+        if snaps[k].n == 0:
+            continue
+        iv, px, py, pxr, lv, vc = m.IsInFrustumBatch(tcws[i][None], ows[i][None], K, (0, 0, 640, 480), 8, log_sf, *raw[k][2:7], 0.5)
+        mv = N.make_mappoint_view(raw[k][7], iv[0], px[0], py[0], pxr[0], lv[0], vc[0], None, keep)
+        (tm, tn), = m.SearchByProjectionLocalPointsBatch([fvs[i]], [mv], 3.0, 0.8)
+        assert np.array_equal(tm, got[i][0]) and tn == got[i][1] and int(iv[0].sum()) == got[i][2]
+    assert m.SearchLocalMapBatch([], np.zeros((0, 3), np.float32), snaps, [], 0.5, log_sf, 3.0, 0.8) == []
 
 
 def test_batch_with_ragged_and_empty_instances(api, oracle, synth):
