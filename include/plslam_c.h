@@ -186,6 +186,9 @@ PL_API int pl_line_set_reserved_sms(pl_line* h, int n);
 /* Measurement hooks: stages {0 blur+scale+gradient, 1 seed sort, 2 region growing/NFA, 3 KeyLines+blur5+Sobel, 4 LBD} */
 PL_API int pl_line_set_profiling(pl_line* h, int on);
 PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks);
+/* of stage 2 (grow + NFA) the part k_lsd_nfa takes after the grower has ended (what its tail helpers did not validate), accumulated like
+ * pl_line_stage_ms */
+PL_API int pl_line_nfa_ms(pl_line* h, float* ms);
 /* with profiling on, 16 values of frame `frame` of the last chunk from k_lsd_grow2's own clock64 accounting:
  * {0 sequencer cycles in commit-time re-growth, 1 cycles the frame was active, 2 sequencer cycles in commits (without the re-growth),
  *  3 tickets issued, 4 regions re-grown at commit, 5 regions committed, 6 tickets deferred, 7 tickets void, 8 sequencer cycles

@@ -1955,6 +1955,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     {
         // a warp per rectangle: few frames get more CTAs each, so that a single frame's ~1500 rectangles are one wave on the whole GPU
         const int per_frame = std::max(kNfaBlocksPerFrame, std::min(256, (4 * h->num_sms + nf - 1) / nf));
+        if (prof) cudaEventRecord(h->ev[6], st);  // (k_lsd_nfa alone: stage_ms[5])
         k_lsd_nfa<<<dim3(per_frame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
     }
     launches += 2;
@@ -1987,6 +1988,11 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
             float ms = 0;
             cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
             h->stage_ms[i] += ms;
+        }
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev[6], h->ev[3]);
+            h->stage_ms[5] += ms;
         }
         h->stage_chunks++;
     }
@@ -2316,6 +2322,12 @@ PL_API int pl_line_set_profiling(pl_line* h, int on) {
     h->stage_chunks = 0;
     return PL_OK;
 }
+PL_API int pl_line_nfa_ms(pl_line* h, float* ms) {
+    PL_CHECK_ARG(h && ms);
+    *ms = h->stage_ms[5];
+    return PL_OK;
+}
+
 PL_API int pl_line_stage_ms(pl_line* h, float* out5, int* chunks) {
     PL_CHECK_ARG(h && out5);
     for (int i = 0; i < 5; i++) out5[i] = h->stage_ms[i];

@@ -58,6 +58,9 @@ N.check(N.lib().pl_line_stage_ms(ex._h, N.ptr(out), C.byref(ch)))
 names = ["scale+grad", "seed_sort", "grow+nfa", "keylines+sobel", "lbd"]
 for i in range(5):
     print(f"  {names[i]:15s} {out[i]*1000/(a.frames*a.iters):9.2f} us/frame  ({out[i]/a.iters:.3f} ms per pass)")
+nfa = C.c_float()
+N.check(N.lib().pl_line_nfa_ms(ex._h, C.byref(nfa)))
+print(f"  of grow+nfa, k_lsd_nfa after the grower: {nfa.value / a.iters:.3f} ms per pass")
 print("lines/frame", float(d_n.float().mean().item()), "launches", ex.last_launches())
 ph = np.zeros(16, np.int64)
 N.check(N.lib().pl_line_grow_phases(ex._h, C.c_int(0), N.ptr(ph)))
