@@ -365,45 +365,52 @@ __global__ void __launch_bounds__(kResThreads) k_last_frame_resolve(const Search
         int p1 = resolve_load_chunk(s_cand, cand, off, cnt, p0, S.np, total, &s_p1, &s_overflow);
         if (p1 & (1 << 30)) { p0 = p1 & ~(1 << 30); continue; }
         if (warp == 0) {
+            // The replay is one dependent chain per point: nothing in it may wait for global memory.  The counts, offsets and
+            // observation flags of 32 points are fetched by the lanes at once; the rotation bins (which decide nothing here) are
+            // formed afterwards by the whole CTA from the (feature, point) pairs this loop records.
             int nmatches = s_nm, nrec = s_nrec;
             const int o0 = off[p0];
-            for (int i = p0; i < p1; i++) {
-                const int c = cnt[i];
-                if (c == 0) continue;
-                const unsigned int* cd = s_cand + (off[i] - o0);
-                unsigned best = 0xFFFFFFFFu;
-                for (int base = 0; base < c; base += 32) {
-                    unsigned key = 0xFFFFFFFFu;
-                    if (base + lane < c) {
-                        const unsigned e = cd[base + lane];
-                        if (!s_claimed[e & 0xFFFFu]) key = ((e >> 16) << 16) | (unsigned)(base + lane);  // dist, then candidate position
-                    }
-#pragma unroll
-                    for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
-                    best = min(best, key);
+            for (int g0 = p0; g0 < p1; g0 += 32) {
+                int my_c = 0, my_o = 0, my_obs = 1;
+                if (g0 + lane < p1) {
+                    my_c = cnt[g0 + lane];
+                    my_o = off[g0 + lane] - o0;
+                    if (S.has_obs) my_obs = S.has_obs[g0 + lane] != 0;
                 }
-                if (best == 0xFFFFFFFFu) continue;
-                const int bestDist = (int)(best >> 16);
-                if (bestDist <= th_dist) {
-                    const int bestIdx2 = (int)(cd[best & 0xFFFFu] & 0xFFFFu);
-                    if (lane == 0) {
-                        match[bestIdx2] = i;
-                        s_claimed[bestIdx2] = S.has_obs ? (S.has_obs[i] != 0) : 1;
-                    }
-                    nmatches++;
-                    if (check_orientation) {
-                        float rot = __fsub_rn(S.angle[i], C.keys[bestIdx2].angle);
-                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                        int bin = (int)roundf(__fmul_rn(rot, factor));
-                        if (bin == kHistoLen) bin = 0;
-                        if (lane == 0) {
-                            rec[2 * nrec] = bestIdx2;
-                            rec[2 * nrec + 1] = bin;
-                            s_hist[bin]++;
+                const int gn = min(32, p1 - g0);
+                for (int j = 0; j < gn; j++) {
+                    const int c = __shfl_sync(0xffffffffu, my_c, j);
+                    if (c == 0) continue;
+                    const int i = g0 + j;
+                    const unsigned int* cd = s_cand + __shfl_sync(0xffffffffu, my_o, j);
+                    unsigned best = 0xFFFFFFFFu;
+                    for (int base = 0; base < c; base += 32) {
+                        unsigned key = 0xFFFFFFFFu;
+                        if (base + lane < c) {
+                            const unsigned e = cd[base + lane];
+                            if (!s_claimed[e & 0xFFFFu]) key = ((e >> 16) << 16) | (unsigned)(base + lane);  // dist, then candidate position
                         }
-                        nrec++;
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
+                        best = min(best, key);
                     }
-                    __syncwarp();
+                    if (best == 0xFFFFFFFFu) continue;
+                    const int bestDist = (int)(best >> 16);
+                    if (bestDist <= th_dist) {
+                        const int bestIdx2 = (int)(cd[best & 0xFFFFu] & 0xFFFFu);
+                        const int obs = __shfl_sync(0xffffffffu, my_obs, j);
+                        if (lane == 0) {
+                            match[bestIdx2] = i;
+                            s_claimed[bestIdx2] = (uint8_t)obs;
+                            if (check_orientation) {
+                                rec[2 * nrec] = bestIdx2;
+                                rec[2 * nrec + 1] = i;
+                            }
+                        }
+                        nmatches++;
+                        nrec += check_orientation != 0;
+                        __syncwarp();
+                    }
                 }
             }
             if (lane == 0) { s_nm = nmatches; s_nrec = nrec; }
@@ -413,6 +420,18 @@ __global__ void __launch_bounds__(kResThreads) k_last_frame_resolve(const Search
     __syncthreads();
     int nmatches = s_nm;
     const int nrec = s_nrec;
+    if (check_orientation) {  // rotation bin of every match (ORBmatcher.cc:1847-1857), all threads
+        for (int k = tid; k < nrec; k += kResThreads) {
+            const int idx = rec[2 * k], i = rec[2 * k + 1];
+            float rot = __fsub_rn(S.angle[i], C.keys[idx].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == kHistoLen) bin = 0;
+            rec[2 * k + 1] = bin;
+            atomicAdd(&s_hist[bin], 1);
+        }
+        __syncthreads();
+    }
     if (warp == 0) {
         if (check_orientation) {
             __threadfence_block();
@@ -463,8 +482,9 @@ __global__ void __launch_bounds__(kResThreads) k_local_points_resolve(const Sear
     const int total = totals[blockIdx.x];
     int* match = match_all + S.feat_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // per feature: bit 7 = claimed, low bits = octave (the ratio test compares octaves: no global read inside the replay)
     for (int i = tid; i < F.n; i += kResThreads) {
-        s_claimed[i] = F.claimed ? (F.claimed[i] != 0) : 0;
+        s_claimed[i] = (uint8_t)(((F.claimed && F.claimed[i] != 0) ? 0x80 : 0) | (F.keys[i].octave & 0x7f));
         match[i] = -1;
     }
     if (tid == 0) { s_overflow = 0; s_nm = 0; }
@@ -475,17 +495,26 @@ __global__ void __launch_bounds__(kResThreads) k_local_points_resolve(const Sear
         if (warp == 0) {
             int nmatches = s_nm;
             const int o0 = off[p0];
-            for (int i = p0; i < p1; i++) {
-                const int c = cnt[i];
+            for (int g0 = p0; g0 < p1; g0 += 32) {
+              int my_c = 0, my_o = 0, my_obs = 1;  // counts, offsets, observation flags of 32 points, fetched at once
+              if (g0 + lane < p1) {
+                  my_c = cnt[g0 + lane];
+                  my_o = off[g0 + lane] - o0;
+                  if (S.has_obs) my_obs = S.has_obs[g0 + lane] != 0;
+              }
+              const int gn = min(32, p1 - g0);
+              for (int j = 0; j < gn; j++) {
+                const int c = __shfl_sync(0xffffffffu, my_c, j);
                 if (c == 0) continue;
-                const unsigned int* cd = s_cand + (off[i] - o0);
+                const int i = g0 + j;
+                const unsigned int* cd = s_cand + __shfl_sync(0xffffffffu, my_o, j);
                 // pass 1: first position of the minimum distance among the unclaimed candidates
                 unsigned best = 0xFFFFFFFFu;
                 for (int base = 0; base < c; base += 32) {
                     unsigned key = 0xFFFFFFFFu;
                     if (base + lane < c) {
                         const unsigned e = cd[base + lane];
-                        if (!s_claimed[e & 0xFFFFu]) key = ((e >> 16) << 16) | (unsigned)(base + lane);
+                        if (!(s_claimed[e & 0xFFFFu] & 0x80)) key = ((e >> 16) << 16) | (unsigned)(base + lane);
                     }
 #pragma unroll
                     for (int sft = 16; sft > 0; sft >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, sft));
@@ -501,7 +530,7 @@ __global__ void __launch_bounds__(kResThreads) k_local_points_resolve(const Sear
                     const int pos = base + lane;
                     if (pos < c && pos != pb) {
                         const unsigned e = cd[pos];
-                        if (!s_claimed[e & 0xFFFFu]) {
+                        if (!(s_claimed[e & 0xFFFFu] & 0x80)) {
                             const unsigned key = ((e >> 16) << 16) | (unsigned)pos;
                             if (pos < pb) kr = key; else ks = key;
                         }
@@ -515,23 +544,25 @@ __global__ void __launch_bounds__(kResThreads) k_local_points_resolve(const Sear
                     sk = min(sk, ks);
                 }
                 const int bestIdx = (int)(cd[pb] & 0xFFFFu);
-                const int bestLevel = F.keys[bestIdx].octave;
+                const int bestLevel = s_claimed[bestIdx] & 0x7f;
                 int bestDist2 = 256, bestLevel2 = -1;
                 if (rk != 0xFFFFFFFFu) {  // displaced running best of the prefix
                     bestDist2 = (int)(rk >> 16);
-                    bestLevel2 = F.keys[cd[rk & 0xFFFFu] & 0xFFFFu].octave;
+                    bestLevel2 = s_claimed[cd[rk & 0xFFFFu] & 0xFFFFu] & 0x7f;
                 }
                 if (sk != 0xFFFFFFFFu && (int)(sk >> 16) < bestDist2) {
                     bestDist2 = (int)(sk >> 16);
-                    bestLevel2 = F.keys[cd[sk & 0xFFFFu] & 0xFFFFu].octave;
+                    bestLevel2 = s_claimed[cd[sk & 0xFFFFu] & 0xFFFFu] & 0x7f;
                 }
                 if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nn_ratio, (float)bestDist2)) continue;
+                const int obs = __shfl_sync(0xffffffffu, my_obs, j);
                 if (lane == 0) {
                     match[bestIdx] = i;
-                    s_claimed[bestIdx] = S.has_obs ? (S.has_obs[i] != 0) : 1;
+                    if (obs) s_claimed[bestIdx] |= 0x80;
                 }
                 nmatches++;
                 __syncwarp();
+              }
             }
             if (lane == 0) s_nm = nmatches;
         }
