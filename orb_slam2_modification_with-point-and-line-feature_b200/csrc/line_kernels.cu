@@ -1153,7 +1153,15 @@ __device__ __noinline__ void lsd_nfa_one(const LineGeom& g, const float* __restr
     F.bits = nullptr; F.touched = nullptr; F.touched_buf = nullptr; F.reg_cap = 0; F.touched_cap = 0;
     F.ticket = 0; F.commit_head = nullptr;
     const double log_eps = 0.0;
-    LsdRect rec = queue[(size_t)f * g.seg_cap + t].rec;
+    // (the tail helpers read rectangles another SM queued during the same launch, chunk by chunk: a neighbour of an earlier chunk may
+    // sit in this SM's L1 from before it was written, so the words come from L2)
+    LsdRect rec;
+    {
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(&queue[(size_t)f * g.seg_cap + t].rec);
+        unsigned int* dst = reinterpret_cast<unsigned int*>(&rec);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(LsdRect) / 4); i++) dst[i] = __ldcg(src + i);
+    }
     const double log_nfa = lsd_rect_improve(F, T, rec, g.log_nt, log_eps);
     if (lane == 0) {
         LsdSeg sg;
@@ -1271,12 +1279,19 @@ namespace pl {
 constexpr int kNfaBlocksPerFrame = 32, kNfaThreads = 256;
 __global__ void __launch_bounds__(kNfaThreads, 4) k_lsd_nfa(LineGeom g, const float* __restrict__ angdeg, size_t plane,
                                                          const LsdQueueItem* __restrict__ queue, const int* __restrict__ n_rects,
-                                                         LsdSeg* __restrict__ qres, uint8_t* __restrict__ qvalid, NfaTabs T) {
-    const int f = blockIdx.y;
-    const int wid = blockIdx.x * (kNfaThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kNfaThreads / 32);
+                                                         LsdSeg* __restrict__ qres, uint8_t* __restrict__ qvalid, NfaTabs T, int* __restrict__ next) {
+    // rect_improve costs between one and 26 rectangle scans: the warps of a frame take rectangles from a counter (four at a time)
+    // instead of a fixed stride, so that no warp is left with the expensive ones
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int n = min(n_rects[f], g.seg_cap);
-    for (int t = wid; t < n; t += nw)
-        if (qvalid[(size_t)f * g.seg_cap + t] == kNfaTodo) lsd_nfa_one(g, angdeg + (size_t)f * plane, queue, qres, qvalid, T, f, t);
+    while (true) {
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(next + f, 4);
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        if (t0 >= n) break;
+        for (int t = t0; t < min(t0 + 4, n); t++)
+            if (qvalid[(size_t)f * g.seg_cap + t] == kNfaTodo) lsd_nfa_one(g, angdeg + (size_t)f * plane, queue, qres, qvalid, T, f, t);
+    }
 }
 
 }  // namespace pl
@@ -1776,6 +1791,7 @@ struct pl_line {
     int* d_frame_counter = nullptr;
     int* d_nfa_ctl = nullptr;
     unsigned int* d_nfa_items = nullptr;
+    int* d_nfa_next = nullptr;   // per frame: the next rectangle k_lsd_nfa hands out
     int* d_sticky = nullptr;  // capacity flags of the device-pointer API since the last pl_line_sync
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     int tail_nfa = 1;
@@ -1941,6 +1957,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         gb.flags = h->d_flags; gb.phase_cycles = prof ? h->d_phase : nullptr; gb.frame_counter = h->d_frame_counter; gb.plane = plane;
         gb.qres = h->d_qres; gb.qvalid = h->d_qvalid; gb.nfa_items = h->d_nfa_items; gb.nfa_ctl = h->d_nfa_ctl; gb.nfa_tabs = h->nfa_tabs;
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_ctl, 0, 4 * sizeof(int), st));
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_next, 0, sizeof(int) * nf, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
         const bool many2 = (nf > sms || h->force_many) && h->g2_many.threads > 0;
@@ -1956,7 +1973,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         // a warp per rectangle: few frames get more CTAs each, so that a single frame's ~1500 rectangles are one wave on the whole GPU
         const int per_frame = std::max(kNfaBlocksPerFrame, std::min(256, (4 * h->num_sms + nf - 1) / nf));
         if (prof) cudaEventRecord(h->ev[6], st);  // (k_lsd_nfa alone: stage_ms[5])
-        k_lsd_nfa<<<dim3(per_frame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs);
+        k_lsd_nfa<<<dim3(per_frame, nf), kNfaThreads, 0, st>>>(G, h->d_ang, plane, h->d_queue, h->d_nrects, h->d_qres, h->d_qvalid, h->nfa_tabs, h->d_nfa_next);
     }
     launches += 2;
     if (prof) cudaEventRecord(h->ev[3], st);
@@ -2223,6 +2240,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_frame_counter, 1);
     A(&h->d_nfa_ctl, 4);
     A(&h->d_nfa_items, B * kNfaChunksPerFrame);
+    A(&h->d_nfa_next, B);
     A(&h->d_sticky, 1);
     if (e == cudaSuccess) e = cudaMemset(h->d_sticky, 0, sizeof(int));
     A(&h->d_resp, B * seg_cap);
@@ -2280,7 +2298,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (h->stream) pl::stream_sync(h->stream);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
-                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
+                    h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_nfa_next, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_flags) cudaFreeHost(h->h_flags);

@@ -83,6 +83,19 @@ struct Grow2Shared {
 };
 __shared__ Grow2Shared g2s;
 
+// A full chunk of kNfaChunk committed rectangles of frame f goes to the queue of the tail helpers (bit 31: the chunk is full, its
+// size does not depend on the frame's final count).  Whole warp: the rectangle words were written by several lanes.
+__device__ __forceinline__ void g2_publish_chunk(const GrowBufs& B, int f, int chunk) {
+    if (chunk >= kNfaChunksPerFrame) return;
+    __threadfence();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const int b = atomicAdd(B.nfa_ctl + 0, 1);
+        *(volatile unsigned int*)(B.nfa_items + b) = 0x80000000u | ((unsigned)f * kNfaChunksPerFrame + (unsigned)chunk);
+    }
+    __syncwarp();
+}
+
 // =============================== sequencer (warp 0) ===============================
 // Returns -1 when the frame is finished, or the seed pixel of the head ticket when that ticket has to be grown now (deferred,
 // over a capacity, or in conflict with a region committed after its grower read the map): the kernel body calls lsd_grow_seed
@@ -121,6 +134,9 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
     constexpr bool prof = kProf;  // the clock64 accounting of pl_line_grow_phases is compiled into a copy of its own
     unsigned done_mask = 0;
     bool all_issued = kIssue ? ns == 0 : false;
+    // rectangles go to the validation queue of the tail helpers in chunks AS THEY ARE COMMITTED (not when the frame ends): CTAs that
+    // have finished their frame then find work from every frame that is still growing
+    const bool early_nfa = gs.tail_nfa != 0 && g2s.nf > 1;
     if (resume) {
         t_next = Q.t_next; head = Q.head; base = Q.base; n_rect = Q.n_rect;
         n_commit = Q.n_commit; n_void = Q.n_void; n_regrow = Q.n_regrow; n_defer = Q.n_defer;
@@ -153,6 +169,7 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
                     if (lane < (int)(sizeof(LsdRect) / 4))
                         reinterpret_cast<unsigned int*>(&q[n_rect].rec)[lane] = reinterpret_cast<const unsigned int*>(&s_res[0].rec)[lane];
                     n_rect++;
+                    if (early_nfa && (n_rect & (kNfaChunk - 1)) == 0) g2_publish_chunk(B, f, n_rect / kNfaChunk - 1);
                 } else if (lane == 0) {
                     atomicOr(B.flags + f, 1);
                 }
@@ -307,6 +324,7 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
                         if (n_rect < g.seg_cap) {
                             if (lane < (int)(sizeof(LsdRect) / 4)) reinterpret_cast<unsigned int*>(&q[n_rect].rec)[lane] = rc0;
                             n_rect++;
+                            if (early_nfa && (n_rect & (kNfaChunk - 1)) == 0) g2_publish_chunk(B, f, n_rect / kNfaChunk - 1);
                         } else if (lane == 0) {
                             atomicOr(B.flags + f, 1);
                         }
@@ -406,11 +424,12 @@ __device__ __noinline__ int g2_sequencer(int f, int resume) {
     __threadfence();
     const int nr = min(n_rect, g.seg_cap);
     const int nchunks = (nr + kNfaChunk - 1) / kNfaChunk;
-    if (nchunks > 0 && nchunks <= kNfaChunksPerFrame) {
+    const int first = early_nfa ? min(nr / kNfaChunk, kNfaChunksPerFrame) : 0;  // (the full chunks are in the queue already)
+    if (nchunks > first && nchunks <= kNfaChunksPerFrame) {
         int b0 = 0;
-        if (lane == 0) b0 = atomicAdd(B.nfa_ctl + 0, nchunks);
+        if (lane == 0) b0 = atomicAdd(B.nfa_ctl + 0, nchunks - first);
         b0 = __shfl_sync(FULL, b0, 0);
-        for (int i = lane; i < nchunks; i += 32) B.nfa_items[b0 + i] = (unsigned)f * kNfaChunksPerFrame + (unsigned)i;
+        for (int i = first + lane; i < nchunks; i += 32) B.nfa_items[b0 + i - first] = (unsigned)f * kNfaChunksPerFrame + (unsigned)i;
     }
     __threadfence();
     __syncwarp();
@@ -705,8 +724,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_lsd_grow2(LineGeom g_,
             }
             if (item == 0xfffffffeu) break;
             __threadfence();
+            const bool full = (item >> 31) != 0;
+            item &= 0x7fffffffu;
             const int fi = (int)(item / kNfaChunksPerFrame), ch = (int)(item % kNfaChunksPerFrame);
-            const int nr = min(B_.n_rects[fi], g_.seg_cap);
+            const int nr = full ? (ch + 1) * kNfaChunk : min(__ldcg(B_.n_rects + fi), g_.seg_cap);  // (written by another SM during this launch: not through L1)
             for (int t = ch * kNfaChunk; t < min(nr, (ch + 1) * kNfaChunk); t++)
                 lsd_nfa_one(g_, B_.angdeg + (size_t)fi * B_.plane, B_.queue, B_.qres, B_.qvalid, B_.nfa_tabs, fi, t);
         }
