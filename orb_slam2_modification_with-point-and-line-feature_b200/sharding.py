@@ -60,10 +60,19 @@ def pack_features(kps, desc, n, kls, ldesc, lco, ln):
     and the five row lists without padding.  Works on any device."""
     import torch
     cap, L = kps.shape[1], kls.shape[1]
-    pm = torch.arange(cap, device=kps.device)[None, :] < n[:, None].to(torch.int64)
-    lm = torch.arange(L, device=kls.device)[None, :] < ln[:, None].to(torch.int64)
-    return [n.to(torch.int32).contiguous(), ln.to(torch.int32).contiguous(), kps[pm].contiguous(), desc[pm].contiguous(), kls[lm].contiguous(),
-            ldesc[lm].contiguous(), lco[lm].contiguous()]
+
+    def rows(cnt, per_frame):
+        # flat row indices of the filled rows, frame after frame (what a boolean mask over (F, per_frame) would select, without the mask)
+        c = cnt.to(torch.int64).clamp(0, per_frame)
+        total = int(c.sum())
+        first = torch.arange(len(c), device=c.device, dtype=torch.int64) * per_frame - (torch.cumsum(c, 0) - c)
+        return torch.repeat_interleave(first, c, output_size=total) + torch.arange(total, device=c.device, dtype=torch.int64)
+
+    pi, li = rows(n, cap), rows(ln, L)
+    F = kps.shape[0]
+    return [n.to(torch.int32).contiguous(), ln.to(torch.int32).contiguous(), kps.reshape(F * cap, -1).index_select(0, pi),
+            desc.reshape(F * cap, -1).index_select(0, pi), kls.reshape(F * L, -1).index_select(0, li),
+            ldesc.reshape(F * L, -1).index_select(0, li), lco.reshape(F * L, -1).index_select(0, li)]
 
 
 def gather_features(parts, world: int, rank: int, dist, device=None):
