@@ -170,6 +170,11 @@ PL_API int pl_orb_staged_images_dev(pl_orb* h, const uint8_t** d_images, int* n_
 PL_API int pl_line_extract_batch_from_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols, size_t step,
                                           size_t frame_stride, int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs,
                                           int* n_out);
+/* Makes `stream` (a cudaStream_t, e.g. pl_orb_stream(orb)) wait for the point of the line extraction most recently enqueued on h at
+ * which its streaming stages (scale, gradient, seed sort) are done and its region grower is launched.  The grower holds its SMs for
+ * tens of milliseconds without filling them: work enqueued behind this point runs NEXT to it, whereas work started together with the
+ * line extractor first competes with the streaming stages for the whole GPU. */
+PL_API int pl_line_stream_wait_grow_start(pl_line* h, void* stream);
 PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols,
                                      size_t step, size_t frame_stride, int max_lines, pl_keyline* d_kls,
                                      uint8_t* d_desc, double* d_coeffs, int* d_n_out);

@@ -233,6 +233,10 @@ class LineExtractor:
         check(N.lib().pl_line_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(fr.strides[1]),
                                             C.c_size_t(fr.strides[0]), C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), ptr(cnt)))
 
+    def stream_wait_grow_start(self, stream):
+        """`stream` (raw cudaStream_t) waits until the region grower of the extraction last enqueued here has been launched."""
+        check(N.lib().pl_line_stream_wait_grow_start(self._h, C.c_void_p(stream)))
+
     def extract_batch_from_dev_into(self, d_gray, n, rows, cols, step, frame_stride, max_lines, kls, desc, co, cnt):
         """pl_line_extract_batch_from_dev: images already in HBM (e.g. ORBextractor.staged_images()), caller-owned host outputs."""
         assert kls.shape == (n, max_lines) and desc.shape == (n, max_lines, 32) and co.shape == (n, max_lines, 3) and len(cnt) >= n

@@ -1792,6 +1792,7 @@ struct pl_line {
     int* d_nfa_ctl = nullptr;
     unsigned int* d_nfa_items = nullptr;
     int* d_nfa_next = nullptr;   // per frame: the next rectangle k_lsd_nfa hands out
+    cudaEvent_t ev_grow = nullptr;  // recorded where the streaming stages of a chunk end and its region grower is launched
     int* d_sticky = nullptr;  // capacity flags of the device-pointer API since the last pl_line_sync
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
     int tail_nfa = 1;
@@ -1960,6 +1961,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_next, 0, sizeof(int) * nf, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
+        if (h->ev_grow) PL_CUDA_TRY(cudaEventRecord(h->ev_grow, st));
         const bool many2 = (nf > sms || h->force_many) && h->g2_many.threads > 0;
         const pl_line::Grow2Cfg& c2 = many2 ? h->g2_many : h->g2_few;
         Grow2Smem g2{h->grow_tiles, c2.pool_tiles, std::min(h->grow_window, kSlots2), h->lookahead, h->bits_words, h->tail_nfa, h->poll_ns, c2.pool_n, c2.split};
@@ -2296,6 +2298,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) pl::stream_sync(h->stream);
+    if (h->ev_grow) cudaEventDestroy(h->ev_grow);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
                     h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_nfa_next, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
@@ -2323,6 +2326,13 @@ PL_API int pl_line_sync(pl_line* h) {
     return PL_OK;
 }
 PL_API void* pl_line_stream(pl_line* h) { return h ? (void*)h->stream : nullptr; }
+PL_API int pl_line_stream_wait_grow_start(pl_line* h, void* stream) {
+    PL_CHECK_ARG(h);
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->ev_grow) PL_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_grow, cudaEventDisableTiming));
+    PL_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_grow, 0));
+    return PL_OK;
+}
 PL_API int pl_line_set_reserved_sms(pl_line* h, int n) {
     PL_CHECK_ARG(h && n >= 0 && n < std::max(h->num_sms, 1));
     h->reserved_sms = n;
