@@ -84,6 +84,8 @@ def gather_features(parts, world: int, rank: int, dist, device=None):
     def pad16(nbytes: int) -> int:
         return (nbytes + 15) & ~15
 
+    if world == 1:  # nothing travels
+        return parts, int(sum(t.numel() * t.element_size() for t in parts))
     # every part starts at a multiple of 16 bytes inside the buffer, so the receiver can view it with the part's own dtype
     raw = [t.reshape(-1).view(torch.uint8) for t in parts]
     chunks = []
@@ -94,8 +96,6 @@ def gather_features(parts, world: int, rank: int, dist, device=None):
             chunks.append(torch.zeros(extra, dtype=torch.uint8, device=b.device))
     flat = torch.cat(chunks) if chunks else torch.zeros(0, dtype=torch.uint8, device=device)
     sizes = torch.tensor([b.numel() for b in raw], dtype=torch.int64, device=flat.device)
-    if world == 1:
-        return parts, int(sizes.sum())
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)] if rank == 0 else None
     dist.gather(sizes, all_sizes, dst=0)
     if rank != 0:
