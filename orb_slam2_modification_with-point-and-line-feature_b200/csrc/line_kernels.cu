@@ -2103,6 +2103,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     const int tiles = (H + kTileRows - 1) / kTileRows + 1;
     const int seg_cap = (int)(plane / 8) + 1;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_grow, cudaEventDisableTiming);
     auto A = [&](auto** p, size_t n) {
         if (e == cudaSuccess) e = cudaMalloc((void**)p, n * sizeof(**p));
     };

@@ -99,6 +99,39 @@ def test_line_extractor_reads_the_frames_the_orb_extractor_staged(api, synth):
             assert np.array_equal(lc[i, :ln[i]], ref[2][i, :ln[i]])
 
 
+def test_orb_stream_can_wait_for_the_grower_launch(api, synth):
+    """pl_line_stream_wait_grow_start: the ORB extractor's stream waits for the point where the line extractor's streaming stages end;
+    both results are what they are without the dependency (and waiting on a handle that never extracted is a no-op)."""
+    import torch
+    N = api.N
+    frames = synth.frames(6200, 6)
+    d_in = torch.from_numpy(frames).cuda()
+    orb = api.ORBextractor(800, 1.2, 8, 20, 7, max_batch=8)
+    ex = api.LineExtractor(max_batch=8)
+    ex.stream_wait_grow_start(orb.stream())
+    cap = orb.max_keypoints()
+    ref_l = ex.extract_batch(frames)
+    ref_o = orb.extract_batch(frames)
+    d_kps = torch.zeros((6, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((6, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(6, dtype=torch.int32, device="cuda")
+    d_kls = torch.zeros((6, 80, 17), dtype=torch.float32, device="cuda")
+    d_ld = torch.zeros((6, 80, 32), dtype=torch.uint8, device="cuda")
+    d_lc = torch.zeros((6, 80, 3), dtype=torch.float64, device="cuda")
+    d_ln = torch.zeros(6, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        ex.extract_batch_dev(d_in.data_ptr(), 6, 480, 640, 640, 640 * 480, 80, d_kls.data_ptr(), d_ld.data_ptr(), d_lc.data_ptr(), d_ln.data_ptr())
+        ex.stream_wait_grow_start(orb.stream())
+        orb.extract_batch_dev(d_in.data_ptr(), 6, 480, 640, 640, 640 * 480, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+        orb.sync()
+        ex.sync()
+    n = d_n.cpu().numpy()
+    assert np.array_equal(n, ref_o[2]) and np.array_equal(d_ln.cpu().numpy(), ref_l[3])
+    dd, ld = d_desc.cpu().numpy(), d_ld.cpu().numpy()
+    for i in range(6):
+        assert np.array_equal(dd[i, :n[i]], ref_o[1][i, :n[i]]) and np.array_equal(ld[i, :ref_l[3][i]], ref_l[1][i, :ref_l[3][i]])
+
+
 def test_max_lines_parameter(api, synth, oracle):
     img = synth.frame(1000, 640, 480)
     ex = api.LineExtractor()
