@@ -1383,14 +1383,28 @@ __global__ void __launch_bounds__(kFinThreads) k_line_finalize(LineGeom g, const
             if ((b & pmask) == prefix) atomicAdd(&s_hist[(b >> shifts[lvl]) & (nb - 1)], 1);
         }
         __syncthreads();
-        if (tid == 0) {
-            int acc = 0, bin = nb - 1;
-            for (; bin >= 0; bin--) {
-                if (acc + s_hist[bin] >= need) break;
-                acc += s_hist[bin];
+        if (tid < 32) {
+            // the bin in which the running count from the top reaches `need`: every lane sums a block of bins, a warp scan finds the
+            // block, its lane walks it (one thread over 4096 bins was a third of this kernel's time)
+            const int per = nb / 32, hi = nb - 1 - tid * per;  // lane 0 owns the top block
+            int sum = 0;
+            for (int b = 0; b < per; b++) sum += s_hist[hi - b];
+            int above = sum;  // inclusive scan over the lanes (lane order = descending bins)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, above, o);
+                if (tid >= o) above += v;
             }
-            s_bin = bin;
-            s_need = need - acc;
+            const int before = above - sum;  // elements in the blocks above this lane's
+            if (before < need && above >= need) {  // exactly one lane (need >= 1 and the total is >= need)
+                int acc = before, bin = hi;
+                for (; bin > hi - per; bin--) {
+                    if (acc + s_hist[bin] >= need) break;
+                    acc += s_hist[bin];
+                }
+                s_bin = bin;
+                s_need = need - acc;
+            }
         }
         __syncthreads();
         prefix |= (unsigned)s_bin << shifts[lvl];
@@ -1410,14 +1424,28 @@ __global__ void __launch_bounds__(kFinThreads) k_line_finalize(LineGeom g, const
         }
     }
     __syncthreads();
-    if (tid == 0) {  // equal ones in index order (rare: exact float ties)
-        int k = s_sel, taken = 0;
-        for (int i = 0; i < n && taken < need; i++)
-            if (__float_as_uint(resp[i]) == thr) {
-                s_key[k++] = ((unsigned long long)(0xFFFFFFFFu - thr) << 32) | (unsigned)i;
-                taken++;
-            }
-        s_sel = k;
+    // the first `need` responses equal to the threshold, in index order.  Almost always there are exactly `need` of them (one): all
+    // threads look, and only a real tie between more than `need` equal responses is walked by one thread
+    const int n_greater = s_sel;
+    __syncthreads();
+    if (tid == 0) s_need = 0;  // (reused as the count of equal responses)
+    __syncthreads();
+    for (int i = tid; i < n; i += kFinThreads)
+        if (__float_as_uint(resp[i]) == thr) {
+            const int k = atomicAdd(&s_need, 1);
+            if (k < need) s_key[n_greater + k] = ((unsigned long long)(0xFFFFFFFFu - thr) << 32) | (unsigned)i;
+        }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_need > need) {  // exact float ties: lowest indices first
+            int k = n_greater, taken = 0;
+            for (int i = 0; i < n && taken < need; i++)
+                if (__float_as_uint(resp[i]) == thr) {
+                    s_key[k++] = ((unsigned long long)(0xFFFFFFFFu - thr) << 32) | (unsigned)i;
+                    taken++;
+                }
+        }
+        s_sel = n_greater + need;
     }
     __syncthreads();
     const int m = s_sel;  // == keep
