@@ -175,6 +175,10 @@ PL_API int pl_line_extract_batch_from_dev(pl_line* h, const uint8_t* d_gray, int
  * tens of milliseconds without filling them: work enqueued behind this point runs NEXT to it, whereas work started together with the
  * line extractor first competes with the streaming stages for the whole GPU. */
 PL_API int pl_line_stream_wait_grow_start(pl_line* h, void* stream);
+/* Tracking mode: with on != 0 the ~16 stream operations of a chunk of at most four frames are captured into a CUDA graph on first use
+ * and replayed as one launch while the call's pointers and sizes stay the same (a host-pointer pl_line_extract always qualifies: it
+ * stages into the handle's own buffers); other parameters re-capture.  Off by default (PLSLAM_LINE_GRAPH=1 turns it on at creation). */
+PL_API int pl_line_set_graph(pl_line* h, int on);
 PL_API int pl_line_extract_batch_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols,
                                      size_t step, size_t frame_stride, int max_lines, pl_keyline* d_kls,
                                      uint8_t* d_desc, double* d_coeffs, int* d_n_out);

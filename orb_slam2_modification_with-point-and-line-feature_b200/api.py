@@ -233,6 +233,10 @@ class LineExtractor:
         check(N.lib().pl_line_extract_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(fr.strides[1]),
                                             C.c_size_t(fr.strides[0]), C.c_int(max_lines), ptr(kls), ptr(desc), ptr(co), ptr(cnt)))
 
+    def set_graph(self, on=True):
+        """Small chunks (tracking mode) as one CUDA graph launch, re-used while the call's pointers and sizes stay the same."""
+        check(N.lib().pl_line_set_graph(self._h, C.c_int(int(on))))
+
     def stream_wait_grow_start(self, stream):
         """`stream` (raw cudaStream_t) waits until the region grower of the extraction last enqueued here has been launched."""
         check(N.lib().pl_line_stream_wait_grow_start(self._h, C.c_void_p(stream)))

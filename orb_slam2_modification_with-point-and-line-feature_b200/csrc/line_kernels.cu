@@ -1827,6 +1827,20 @@ struct pl_line {
     // k_lsd_grow2 (role-specialised grower, one frame per CTA): shape for up to one frame per SM / for more frames than SMs
     struct Grow2Cfg { int threads = 0, occ = 0, pool_tiles = 0, pool_n = 0, split = 0; size_t smem = 0; } g2_few, g2_many;
     int lookahead = 4;
+    // single-frame (tracking) mode: the chunk's launches as one CUDA graph, re-used while the call's parameters stay the same
+    bool use_graph = false;   // pl_line_set_graph / PLSLAM_LINE_GRAPH=1
+    bool capturing = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey {
+        const void *gray, *kls, *desc, *coef, *nout;
+        size_t step, frame_stride;
+        int nf, cap, rows, cols, max_lines;
+        bool operator==(const GraphKey& o) const {
+            return gray == o.gray && kls == o.kls && desc == o.desc && coef == o.coef && nout == o.nout && step == o.step &&
+                   frame_stride == o.frame_stride && nf == o.nf && cap == o.cap && rows == o.rows && cols == o.cols && max_lines == o.max_lines;
+        }
+    } graph_key{};
+    int graph_launches = 0;   // kernel launches inside the captured graph
     bool use_tma = true;      // PLSLAM_LINE_TMA=0: the two-kernel blur + Sobel path also for aligned inputs (test hook)
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, through cudaGetDriverEntryPoint
     bool force_many = false;  // test hook (PLSLAM_LSD_FORCE_MANY): the many-frames shape also for small batches
@@ -1945,8 +1959,8 @@ bool line_make_tmap(pl_line* h, CUtensorMap* out, const uint8_t* d_gray, int col
 }
 
 // one chunk; every pointer is a device pointer
-int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, size_t frame_stride, pl_keyline* d_kls, uint8_t* d_desc,
-                      double* d_coef, int cap, int* d_nout) {
+int line_launch_chunk_direct(pl_line* h, const uint8_t* d_gray, int nf, size_t step, size_t frame_stride, pl_keyline* d_kls, uint8_t* d_desc,
+                             double* d_coef, int cap, int* d_nout) {
     const LineGeom& G = h->geom;
     cudaStream_t st = h->stream;
     const size_t plane = h->plane;
@@ -1989,7 +2003,7 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_next, 0, sizeof(int) * nf, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
-        if (h->ev_grow) PL_CUDA_TRY(cudaEventRecord(h->ev_grow, st));
+        if (h->ev_grow && !h->capturing) PL_CUDA_TRY(cudaEventRecord(h->ev_grow, st));  // (an event recorded inside a capture cannot be waited for from outside)
         const bool many2 = (nf > sms || h->force_many) && h->g2_many.threads > 0;
         const pl_line::Grow2Cfg& c2 = many2 ? h->g2_many : h->g2_few;
         Grow2Smem g2{h->grow_tiles, c2.pool_tiles, std::min(h->grow_window, kSlots2), h->lookahead, h->bits_words, h->tail_nfa, h->poll_ns, c2.pool_n, c2.split};
@@ -2045,6 +2059,54 @@ int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, si
     }
     h->last_batch = nf;
     h->last_launches += launches;
+    return PL_OK;
+}
+
+// The launches of a small chunk are a fixed sequence of ~16 stream operations whose parameters only depend on the call's pointers
+// and sizes: in tracking mode (one frame per call, the same staging buffers every time) they are captured once and replayed as ONE
+// graph launch.  Anything that changes the parameters re-captures; profiling and large batches launch directly.
+int line_launch_chunk(pl_line* h, const uint8_t* d_gray, int nf, size_t step, size_t frame_stride, pl_keyline* d_kls, uint8_t* d_desc,
+                      double* d_coef, int cap, int* d_nout) {
+    if (!h->use_graph || h->profiling || nf > 4) return line_launch_chunk_direct(h, d_gray, nf, step, frame_stride, d_kls, d_desc, d_coef, cap, d_nout);
+    const pl_line::GraphKey key{d_gray, d_kls, d_desc, d_coef, d_nout, step, frame_stride, nf, cap, h->geom.rows, h->geom.cols, h->geom.max_lines};
+    if (h->graph_exec && key == h->graph_key) {
+        PL_CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
+        h->last_batch = nf;
+        h->last_launches += h->graph_launches;
+        return PL_OK;
+    }
+    if (h->graph_exec) {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+    PL_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+    const int before = h->last_launches;
+    const int rc = line_launch_chunk_direct(h, d_gray, nf, step, frame_stride, d_kls, d_desc, d_coef, cap, d_nout);
+    h->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
+    if (rc != PL_OK || ee != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        if (rc != PL_OK) return rc;
+        // the sequence could not be captured on this driver: launch it directly from now on
+        h->use_graph = false;
+        h->last_launches = before;
+        return line_launch_chunk_direct(h, d_gray, nf, step, frame_stride, d_kls, d_desc, d_coef, cap, d_nout);
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+        (void)cudaGetLastError();
+        h->graph_exec = nullptr;
+        h->use_graph = false;
+        h->last_launches = before;
+        return line_launch_chunk_direct(h, d_gray, nf, step, frame_stride, d_kls, d_desc, d_coef, cap, d_nout);
+    }
+    h->graph_key = key;
+    h->graph_launches = h->last_launches - before;
+    PL_CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
     return PL_OK;
 }
 
@@ -2173,6 +2235,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             if (const char* ev = getenv("PLSLAM_LSD_WINDOW")) h->grow_window = std::max(1, std::min(kSlots2, atoi(ev)));
             // ---- k_lsd_grow2: warps per CTA, CTAs per SM, private tile pool ----
             if (const char* ev = getenv("PLSLAM_LINE_TMA")) h->use_tma = atoi(ev) != 0;
+            if (const char* ev = getenv("PLSLAM_LINE_GRAPH")) h->use_graph = atoi(ev) != 0;
             {
                 cudaDriverEntryPointQueryResult qres;
                 void* fn = nullptr;
@@ -2328,6 +2391,7 @@ PL_API void pl_line_destroy(pl_line* h) {
     cudaSetDevice(h->device);
     if (h->stream) pl::stream_sync(h->stream);
     if (h->ev_grow) cudaEventDestroy(h->ev_grow);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     void* bufs[] = {h->d_in, h->d_scaled, h->d_big_bits, h->d_blur5, h->d_ang, h->d_g2, h->d_reg, h->d_seeds, h->d_maxg2, h->d_tile_off,
                     h->d_nseeds, h->d_nsegs, h->d_flags, h->d_nout, h->d_tile_hist, h->d_segs, h->d_resp, h->d_rowsum, h->d_fdesc,
                     h->d_dx, h->d_dy, h->d_xtab, h->d_ytab, h->d_kls, h->d_desc, h->d_coef, h->d_lgam, h->d_phase, h->d_qres, h->d_queue, h->d_qvalid, h->d_spec_reg, h->d_spec_touched, h->d_big_touched, h->d_pool_rect, h->d_small_buf, h->d_small_rect, h->d_frame_counter, h->d_nfa_ctl, h->d_nfa_items, h->d_nfa_next, h->d_sticky, h->d_rec, h->d_cs0, h->d_nrects};
@@ -2355,6 +2419,11 @@ PL_API int pl_line_sync(pl_line* h) {
     return PL_OK;
 }
 PL_API void* pl_line_stream(pl_line* h) { return h ? (void*)h->stream : nullptr; }
+PL_API int pl_line_set_graph(pl_line* h, int on) {
+    PL_CHECK_ARG(h);
+    h->use_graph = on != 0;
+    return PL_OK;
+}
 PL_API int pl_line_stream_wait_grow_start(pl_line* h, void* stream) {
     PL_CHECK_ARG(h);
     PL_CUDA_TRY(cudaSetDevice(h->device));

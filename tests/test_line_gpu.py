@@ -132,6 +132,27 @@ def test_orb_stream_can_wait_for_the_grower_launch(api, synth):
         assert np.array_equal(dd[i, :n[i]], ref_o[1][i, :n[i]]) and np.array_equal(ld[i, :ref_l[3][i]], ref_l[1][i, :ref_l[3][i]])
 
 
+def test_graph_replay_gives_the_same_lines(api, synth):
+    """pl_line_set_graph: a single-frame call captured once and replayed (host-pointer entry: same staging buffers every call), a call
+    with other parameters in between (re-capture), and a batch (direct launches) all give what the direct path gives."""
+    frames = synth.frames(6300, 6)
+    ref = api.LineExtractor(max_batch=8)
+    want = [ref.ExtractLineSegment(f) for f in frames]
+    ex = api.LineExtractor(max_batch=8)
+    ex.set_graph(True)
+    for rnd in range(2):
+        for f, w in zip(frames, want):
+            kl, ld, lc = ex.ExtractLineSegment(f)
+            assert np.array_equal(kl, w[0]) and np.array_equal(ld, w[1]) and np.array_equal(lc, w[2])
+        small = np.ascontiguousarray(frames[0][:240, :320])
+        ks, ds, cs = ex.ExtractLineSegment(small)          # other geometry: re-capture
+        kr, dr, cr = ref.ExtractLineSegment(small)
+        assert np.array_equal(ks, kr) and np.array_equal(ds, dr)
+        kb = ex.extract_batch(frames)                       # six frames: launched directly
+        rb = ref.extract_batch(frames)
+        assert np.array_equal(kb[3], rb[3]) and np.array_equal(kb[1], rb[1])
+
+
 def test_max_lines_parameter(api, synth, oracle):
     img = synth.frame(1000, 640, 480)
     ex = api.LineExtractor()
