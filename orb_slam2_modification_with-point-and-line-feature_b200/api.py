@@ -293,6 +293,31 @@ class LineExtractor:
         return out
 
 
+class _LineMatches:
+    """Sequence of (match_of_line, nmatches, used_relaxed, n_projected) per search, backed by dense arrays: `dense` =
+    (matches (n, max lines) padded with -1, nmatches, used_relaxed, n_projected)."""
+
+    def __init__(self, out, nl, cnt, rel, npj):
+        self.dense = (out, cnt, rel, npj)
+        self._nl = nl
+
+    def __len__(self):
+        return len(self._nl)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        out, cnt, rel, npj = self.dense
+        return out[i, :self._nl[i]], int(cnt[i]), int(rel[i]), int(npj[i])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class DescriptorMatcher:
     """Hamming searches shared by ORBmatcher (src/ORBmatcher.cc) and LineMatcher (src/LineMatcher.cpp)."""
 
@@ -407,6 +432,8 @@ class DescriptorMatcher:
     # ---- batched forms: n independent reference calls in one pass ----
     @staticmethod
     def _view_array(views, typ):
+        if isinstance(views, C.Array) and views._type_ is typ:  # the caller built the array of views itself
+            return views
         arr = (typ * len(views))()
         for i, v in enumerate(views):
             arr[i] = v
@@ -452,12 +479,15 @@ class DescriptorMatcher:
         n = len(cur_views)
         ca = self._view_array(cur_views, N.LineFrameView)
         la = self._view_array(line_views, N.MapLineView)
-        outs = [np.full(max(v.n, 1), -1, np.int32) for v in cur_views]
-        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        # one (n, max lines) result array, rows padded with -1; `dense` on the returned sequence hands it over whole
+        nl = np.frombuffer(ca, np.dtype(N.LineFrameView), count=n)["n"].astype(np.int64) if n else np.zeros(0, np.int64)
+        stride = max(int(nl.max()), 1) if n else 1
+        out = np.full((max(n, 1), stride), -1, np.int32)
+        ptrs = (out.ctypes.data + np.arange(max(n, 1), dtype=np.uint64) * np.uint64(stride * 4)).astype(np.uint64)
         cnt, rel, npj = (np.zeros(max(n, 1), np.int32) for _ in range(3))
-        nulls = (C.c_void_p * n)()
-        check(N.lib().pl_line_search_by_projection_batch(self._h, C.c_int(n), ca, la, ptrs, ptr(cnt), ptr(rel), nulls, nulls, ptr(npj)))
-        return [(outs[i][:cur_views[i].n], int(cnt[i]), int(rel[i]), int(npj[i])) for i in range(n)]
+        nulls = (C.c_void_p * max(n, 1))()
+        check(N.lib().pl_line_search_by_projection_batch(self._h, C.c_int(n), ca, la, ptr(ptrs), ptr(cnt), ptr(rel), nulls, nulls, ptr(npj)))
+        return _LineMatches(out[:n], nl, cnt[:n], rel[:n], npj[:n])
 
     # ---- C4 / C5: pose-based projection searches ----
     def _pose_points(self, fn, frame_views, pt_views, ow, log_sf, *scalars):

@@ -138,46 +138,62 @@ class FrameLite:
         return self._ul
 
     @staticmethod
-    def attach_lines_batch(frames, lines, depth):
+    def prepare_lines_batch(frames, depth):
+        """The part of attach_lines_batch that does not need the line features (pose stacks, the flat depth view): the caller runs
+        it while the line extractor is still working."""
+        if not len(frames) or not isinstance(depth, np.ndarray) or depth.ndim != 3:
+            return None
+        n = len(frames)
+        h, w = depth.shape[1:]
+        Rwc = np.stack([F.Rwc for F in frames]).astype(np.float64)
+        return dict(n=n, RT=np.ascontiguousarray(Rwc.transpose(0, 2, 1)), Ow=np.stack([F.Ow for F in frames]).astype(np.float64)[:, None, :],
+                    tcw=np.stack([F.Tcw[:3].reshape(-1) for F in frames]).astype(f32),
+                    base=(np.arange(n, dtype=np.int64) * (h * w))[:, None], flat=depth.reshape(-1))
+
+    @staticmethod
+    def attach_lines_batch(frames, lines, depth, prep=None):
         """set_lines + unproject_lines of a whole sequence in one vectorised pass (depth: the (n, h, w) array the frames were
         built from).  Same arithmetic as the per-frame methods."""
         n = len(frames)
-        counts = np.array([len(l[0]) for l in lines], np.int64)
+        dense = getattr(lines, "dense", None)
+        if dense is not None and len(dense) > 1 and len(dense[1]) == n:
+            counts = np.asarray(dense[1]).astype(np.int64)  # the extractor's own per-frame counts
+        else:
+            counts = np.array([len(l[0]) for l in lines], np.int64)
         if counts.sum() == 0 or not isinstance(depth, np.ndarray) or depth.ndim != 3:
             for F, (kls, ldesc, _) in zip(frames, lines):
                 F.set_lines(kls, ldesc)
             return
-        dense = getattr(lines, "dense", None)
         h, w = depth.shape[1:]
         K = frames[0].K
-        Rwc = np.stack([F.Rwc for F in frames]).astype(np.float64)
-        Ow = np.stack([F.Ow for F in frames]).astype(np.float64)
+        if prep is None or prep["n"] != n:
+            prep = FrameLite.prepare_lines_batch(frames, depth)
         if dense is not None and dense[0].ndim == 2 and len(dense[0]) == n:
             # the extractor's own (n, max_lines) output: every row at once (rows beyond a frame's count are never looked at);
             # the batched matmul is the per-frame `pc @ Rwc.T` of unproject_lines, row for row
             kl = dense[0]
-            sxf, syf, exf, eyf = (np.ascontiguousarray(kl[k]) for k in ("sx", "sy", "ex", "ey"))
+            m = kl.shape[1]
+            # start and end points go through the arithmetic together: xy[0] = (sx, sy), xy[1] = (ex, ey) of every line
+            xy = np.empty((2, n, m, 2), np.float64)
+            if kl.dtype == N.KL_DTYPE and kl.flags.c_contiguous:
+                raw = kl.view(np.float32).reshape(n, m, N.KL_DTYPE.itemsize // 4)   # sx, sy, ex, ey are words 7..10 of a KeyLine
+                xy[0], xy[1] = raw[:, :, 7:9], raw[:, :, 9:11]
+            else:
+                xy[0, :, :, 0], xy[0, :, :, 1], xy[1, :, :, 0], xy[1, :, :, 1] = kl["sx"], kl["sy"], kl["ex"], kl["ey"]
+            px, py = xy[..., 0], xy[..., 1]
             with np.errstate(invalid="ignore"):
-                sx = np.clip(np.rint(sxf).astype(np.int64), 0, w - 1)
-                sy = np.clip(np.rint(syf).astype(np.int64), 0, h - 1)
-                ex = np.clip(np.rint(exf).astype(np.int64), 0, w - 1)
-                ey = np.clip(np.rint(eyf).astype(np.int64), 0, h - 1)
-            base = (np.arange(n, dtype=np.int64) * (h * w))[:, None]
-            flat = depth.reshape(-1)
-            ds = flat[base + sy * w + sx].astype(np.float64)
-            de = flat[base + ey * w + ex].astype(np.float64)
-            RT = Rwc.transpose(0, 2, 1)
-
-            def lift(px, py, z):
-                pc = np.stack([(px - K["cx"]) * z / K["fx"], (py - K["cy"]) * z / K["fy"], z], 2)
-                return np.matmul(pc, RT) + Ow[:, None, :]
-
+                ix = np.minimum(np.maximum(np.rint(xy).astype(np.int64), 0), np.array([w - 1, h - 1], np.int64))   # np.clip per axis
+            base, flat, RT, Ow = prep["base"], prep["flat"], prep["RT"], prep["Ow"]
+            z = flat[base[None] + ix[..., 1] * w + ix[..., 0]].astype(np.float64)   # depth at the rounded end points
             with np.errstate(invalid="ignore", over="ignore"):
-                s3 = lift(sxf.astype(np.float64), syf.astype(np.float64), ds)
-                e3 = lift(exf.astype(np.float64), eyf.astype(np.float64), de)
+                pc = np.empty((2, n, m, 3), np.float64)
+                pc[..., 0] = (px - K["cx"]) * z / K["fx"]
+                pc[..., 1] = (py - K["cy"]) * z / K["fy"]
+                pc[..., 2] = z
+                P3 = np.matmul(pc, RT[None]) + Ow[None]
+                s3, e3, ds, de = P3[0], P3[1], z[0], z[1]
                 ok = (ds > 0) & (de > 0)
-            for t, F in enumerate(frames):
-                c = counts[t]
+            for t, (F, c) in enumerate(zip(frames, counts.tolist())):
                 F.kls, F.ldesc = lines[t][0], lines[t][1]
                 F.ds, F.de = ds[t, :c], de[t, :c]
                 F._ul = (s3[t, :c], e3[t, :c], ok[t, :c])
@@ -186,7 +202,7 @@ class FrameLite:
                     and kl.dtype == N.KL_DTYPE):
                 # what the line searches read, as whole-sequence arrays: their views are then built for all frames at once
                 frames[0]._seq = dict(kl=kl, ld=ld, s3=np.ascontiguousarray(s3), e3=np.ascontiguousarray(e3), ok=ok.astype(np.uint8), counts=counts,
-                                      tcw=np.stack([F.Tcw[:3].reshape(-1) for F in frames]).astype(f32))
+                                      tcw=prep["tcw"])
             return
         for F, (kls, ldesc, _) in zip(frames, lines):  # features handed over as a list of per-frame arrays
             F.set_lines(kls, ldesc)
@@ -235,6 +251,23 @@ class LocalMap:
             self.le = np.concatenate([self.le, e3[okl]])[-self.max_lines:]
             self.lkl = np.concatenate([self.lkl, F.kls[okl]])[-self.max_lines:]
             self.ldesc = np.concatenate([self.ldesc, F.ldesc[okl]])[-self.max_lines:]
+
+    @staticmethod
+    def line_snapshots_dense(seq, n, kf_every, max_lines=300):
+        """lmaps[t] = (ls, le, lkl, ldesc) of the local line map frame t sees, for a whole sequence at once: what calling
+        add_keyframe_lines on every kf_every-th frame leaves behind.  The map after a key frame is the trailing max_lines rows of
+        everything the key frames so far contributed, so every snapshot is a slice of ONE gathered array (no per-key-frame
+        concatenation of structured arrays)."""
+        kf = np.arange(0, n, kf_every)
+        sel = (np.arange(seq["kl"].shape[1])[None, :] < seq["counts"][kf][:, None]) & (seq["ok"][kf] != 0)
+        ls, le, lkl, ld = seq["s3"][kf][sel], seq["e3"][kf][sel], seq["kl"][kf][sel], seq["ld"][kf][sel]
+        hi = np.concatenate([[0], np.cumsum(sel.sum(1))]).astype(np.int64)   # snapshot k = the map after k key frames
+        lo = np.maximum(hi - max_lines, 0)
+        snaps = [(ls[a:b], le[a:b], lkl[a:b], ld[a:b]) for a, b in zip(lo.tolist(), hi.tolist())]
+        snap_of = np.zeros(n, np.int64)
+        snap_of[1:] = (np.arange(1, n) - 1) // kf_every + 1
+        where = dict(ls=ls, le=le, lkl=lkl, ld=ld, lo=lo, hi=hi, snap_of=snap_of, ones=np.ones(max(max_lines, 1), np.uint8))
+        return [snaps[k] for k in snap_of.tolist()], where
 
     # Frame::IsInFrustum (Frame.cc:345-401) + MapPoint::PredictScale (MapPoint.cc:416-431), vectorised float32 over the
     # frames that see the same snapshot of the map
@@ -325,7 +358,7 @@ class TrackingFrontEnd:
         a["min_x"], a["min_y"], a["max_x"], a["max_y"] = [float(b) for b in F0.bounds]
         a["cols"], a["rows"] = int(F0.size[0]), int(F0.size[1])
         keep += [a, seq]
-        return list((N.LineFrameView * len(tt)).from_buffer(a))
+        return (N.LineFrameView * len(tt)).from_buffer(a)
 
     @staticmethod
     def _dense_mapline_views(seq, tt, keep):
@@ -338,7 +371,37 @@ class TrackingFrontEnd:
         a["desc"] = seq["ld"].ctypes.data + tt * seq["ld"].strides[0]
         a["valid"] = seq["ok"].ctypes.data + tt * seq["ok"].strides[0]
         keep += [a, seq]
-        return list((N.MapLineView * len(tt)).from_buffer(a))
+        return (N.MapLineView * len(tt)).from_buffer(a)
+
+    @staticmethod
+    def _dense_snapshot_views(where, tt, keep):
+        """pl_mapline_view of the local line map frames tt see (the `map` side of D5): rows [lo, hi) of the gathered arrays of
+        LocalMap.line_snapshots_dense; frames between two key frames point at the same rows."""
+        k = where["snap_of"][tt]
+        lo, hi = where["lo"][k], where["hi"][k]
+        a = np.zeros(len(tt), np.dtype(N.MapLineView))
+        a["n"] = hi - lo
+        a["start3d"] = where["ls"].ctypes.data + lo * where["ls"].strides[0]
+        a["end3d"] = where["le"].ctypes.data + lo * where["le"].strides[0]
+        a["kl"] = where["lkl"].ctypes.data + lo * where["lkl"].strides[0]
+        a["desc"] = where["ld"].ctypes.data + lo * where["ld"].strides[0]
+        a["valid"] = where["ones"].ctypes.data
+        keep += [a, where]
+        return (N.MapLineView * len(tt)).from_buffer(a)
+
+    @staticmethod
+    def _line_results(summary, ts, res, tag):
+        """(match_of_line, nmatches, used_relaxed, n_projected) of every search into the summary; a result that carries its dense
+        arrays is summarised for all frames at once (rows are padded with -1, which adds nothing to sum((m + 1) * (i + 1)))."""
+        dense = getattr(res, "dense", None)
+        if dense is not None:
+            out, cnt, rel, npj = dense
+            chk = ((out.astype(np.int64) + 1) * np.arange(1, out.shape[1] + 1, dtype=np.int64)).sum(1) if len(out) else out
+            for t, c, nl, r, p_ in zip(ts, chk.tolist(), cnt.tolist(), rel.tolist(), npj.tolist()):
+                summary[t].update({tag + "_proj": p_, tag + "_matches": nl, tag + "_relaxed": r, tag + "_sum": c})
+            return
+        for t, (ml, nl, rel, npj) in zip(ts, res):
+            summary[t].update({tag + "_proj": npj, tag + "_matches": nl, tag + "_relaxed": rel, tag + "_sum": TrackingFrontEnd._chk(ml)})
 
     def run(self, gray, depth, Tcw, scale_factors, features=None, prior_noise=True, batch=True):
         """features = (orb, lines); `lines` may be a concurrent.futures.Future: the point side (Frame-lite, C3, C2) does not
@@ -479,29 +542,39 @@ class TrackingFrontEnd:
             fr_ready.set()
             point_searches()
         # ---- line side of the caller state ----
+        prep = FrameLite.prepare_lines_batch(frames, depth)  # what the line side can do before the lines are there
         if hasattr(lines, "result"):
             lines = lines.result()
         mark("lines ready")
-        lmaps = []
-        lm = LocalMap()
-        FrameLite.attach_lines_batch(frames, lines, depth)
-        for t in range(n):
-            summary[t].update(n_kl=len(lines[t][0]))
-            lmaps.append((lm.ls, lm.le, lm.lkl, lm.ldesc))
-            if t % self.kf_every == 0:
-                lm.add_keyframe_lines(frames[t])
+        FrameLite.attach_lines_batch(frames, lines, depth, prep)
+        seq = getattr(frames[0], "_seq", None) if n else None
+        if seq is not None:
+            for t, c in enumerate(seq["counts"].tolist()):
+                summary[t]["n_kl"] = c
+            lmaps, where = LocalMap.line_snapshots_dense(seq, n, self.kf_every)
+        else:
+            where = None
+            lmaps = []
+            lm = LocalMap()
+            for t in range(n):
+                summary[t].update(n_kl=len(lines[t][0]))
+                lmaps.append((lm.ls, lm.le, lm.lkl, lm.ldesc))
+                if t % self.kf_every == 0:
+                    lm.add_keyframe_lines(frames[t])
         mark("lines attached, line maps built")
         # ---- D3: LineMatcher(0.9).SearchByProjection(Cur, Last) (Tracking.cc:1247) ----
-        d3_t = [t for t in c3_t if len(frames[t - 1].kls) and len(frames[t].kls)]
+        if seq is not None:
+            has = seq["counts"] > 0
+            d3_t = [t for t in c3_t if has[t - 1] and has[t]]
+        else:
+            d3_t = [t for t in c3_t if len(frames[t - 1].kls) and len(frames[t].kls)]
         lcv, llv = [], []
         cur_view = {}  # the current-frame side of D3 and D5 is the same view
-        seq = getattr(frames[0], "_seq", None) if n else None
         if seq is not None and d3_t:
             # the same views as below, for all frames at once: the line features are rows of the extractor's dense output
             tt = np.asarray(d3_t, np.int64)
             lcv = self._dense_lineframe_views(seq, tt, frames[0], keep)
             llv = self._dense_mapline_views(seq, tt - 1, keep)
-            cur_view = dict(zip(d3_t, lcv))
         else:
             for t in d3_t:
                 F, last = frames[t], frames[t - 1]
@@ -514,8 +587,7 @@ class TrackingFrontEnd:
         def d3_search(lcv=lcv, llv=llv):
             rd3 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
             mark("  [d3] D3 searched")
-            for t, (ml, nl, rel, npj) in zip(d3_t, rd3):
-                summary[t].update(d3_proj=npj, d3_matches=nl, d3_relaxed=rel, d3_sum=self._chk(ml))
+            self._line_results(summary, d3_t, rd3, "d3")
 
         d3_worker = None
         two_handles = batch and getattr(self.b, "concurrent_sides", False)
@@ -533,10 +605,18 @@ class TrackingFrontEnd:
         else:
             d3_search()
         # ---- D5: LineMatcher(0.8).SearchByProjection(F, localLines) (Tracking.cc:1863) ----
-        d5_t = [t for t in c2_t if len(lmaps[t][2]) and len(frames[t].kls)]
+        if where is not None:
+            ok5 = (where["hi"] > where["lo"])[where["snap_of"]] & (seq["counts"] > 0)
+            d5_t = [t for t in c2_t if ok5[t]]
+        else:
+            d5_t = [t for t in c2_t if len(lmaps[t][2]) and len(frames[t].kls)]
         lcv, llv = [], []
         snap_view = {}  # frames between two key frames see the same snapshot of the local line map
-        for t in d5_t:
+        if where is not None and d5_t:
+            tt = np.asarray(d5_t, np.int64)
+            lcv = self._dense_lineframe_views(seq, tt, frames[0], keep)
+            llv = self._dense_snapshot_views(where, tt, keep)
+        for t in (d5_t if where is None else ()):
             F = frames[t]
             ls, le, lkl, ldesc = lmaps[t]
             lcv.append(cur_view[t] if t in cur_view else N.make_lineframe_view(F.kls, F.ldesc, None, F.Tcw[:3].reshape(-1), self.K, F.bounds, F.size, keep))
@@ -548,8 +628,7 @@ class TrackingFrontEnd:
             rd5 = self.b.line_search_batch(lcv, llv, True)
         else:
             rd5 = self.b.line_search_batch(lcv, llv) if batch else [self.b.line_search_batch([c], [l])[0] for c, l in zip(lcv, llv)]
-        for t, (ml, nl, rel, npj) in zip(d5_t, rd5):
-            summary[t].update(d5_proj=npj, d5_matches=nl, d5_relaxed=rel, d5_sum=self._chk(ml))
+        self._line_results(summary, d5_t, rd5, "d5")
         mark("D5 done")
         if d3_worker is not None:
             d3_worker.join()
