@@ -920,7 +920,25 @@ __device__ __noinline__ double lsd_nfa(const NfaTabs& T, int n, int k, double p,
         term *= mult_term;
         bin_tail += term;
         if (bin_term < 1) {
-            const double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+            // The reference evaluates pow() and log10() in every one of these iterations.  Both are decided without them
+            // almost always, with the same outcome:
+            //  * p <= 1/8, so mult_term < 1/7 here and pow(mult_term, m) < 2^-56 for m >= 20: 1 - pow(...) rounds to exactly 1;
+            //  * the stopping test compares err with 0.1 * |-log10(bin_tail) - log_nt| * bin_tail: a bracket of log10 that is
+            //    1e-7 wide (exponent + lg2.approx of the mantissa) settles it unless err is within 1e-5 of the bound, and only
+            //    then is the bound evaluated as the reference writes it.
+            const int m = n - i + 1;
+            const double one_minus_pow = m >= 20 ? 1.0 : 1 - pow(mult_term, (double)m);
+            const double err = term * (one_minus_pow / (1 - mult_term) - 1);
+            const int hi = __double2hiint(bin_tail), ex = (hi >> 20) & 0x7ff;
+            if (ex != 0 && ex != 0x7ff) {
+                const float mant = (float)__hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(bin_tail));   // [1, 2]
+                const double l10 = ((double)(ex - 1023) + (double)__log2f(mant)) * 0.30102999566398120;
+                const double a = fabs(-l10 - log_nt), base = tolerance * bin_tail;
+                if (a > 2e-5) {
+                    if (err < base * (a - 1e-5)) break;
+                    if (err > base * (a + 1e-5)) continue;
+                }
+            }
             if (err < tolerance * fabs(-log10(bin_tail) - log_nt) * bin_tail) break;
         }
     }
@@ -1082,13 +1100,13 @@ __device__ __noinline__ void lsd_improve_geometry(const LsdFrame& F, const NfaTa
     c.total = 0;
     c.alg[0] = 0;
     if (grp < ntrial) c = lsd_rect_scan(F, mine, pr, 1, sub, 6);
-    // reduce inside each 6-lane group (groups are not power-of-two wide: gather through shuffles)
-    int myn = 0, myk = 0;
-#pragma unroll 1
-    for (int l = 0; l < 30; ++l) {
-        const int ct = __shfl_sync(FULL, c.total, l), ca = __shfl_sync(FULL, c.alg[0], l);
-        if (lane == l / 6) { myn += ct; myk += ca; }
-    }
+    // reduce inside each 6-lane group: both counts of a lane in one word (a rectangle has far fewer than 2^31 pixels and the sums
+    // are formed in 64 bits), three shuffles to the group's first lane, then lane t fetches the sums of group t
+    unsigned long long both = ((unsigned long long)(unsigned)c.total << 32) | (unsigned)c.alg[0];
+    both += __shfl_down_sync(FULL, both, 3);                                                 // sub 0..2 hold pairs (sub, sub + 3)
+    both += __shfl_down_sync(FULL, both, 1) + __shfl_down_sync(FULL, both, 2);               // sub 0: all six
+    both = __shfl_sync(FULL, both, (lane < 5 ? lane : 0) * 6);
+    const int myn = (int)(both >> 32), myk = (int)(unsigned)both;
     double v = 0;
     if (lane < ntrial) v = lsd_nfa(T, myn, myk, S.rec.p, S.pj, log_nt);
     // replay: trial t's rectangle lives in group t
@@ -1139,6 +1157,7 @@ __device__ double lsd_rect_improve(const LsdFrame& F, const NfaTabs& T, LsdRect&
 // compacted in seed order.
 struct LsdQueueItem { LsdRect rec; };
 constexpr int kNfaChunk = 16;         // rectangles per work item of the tail helpers
+constexpr int kSmBusySlots = 512;     // per-SM counters behind nfa_ctl (indexed by %smid)
 constexpr int kNfaChunksPerFrame = 2048;  // item = frame * kNfaChunksPerFrame + chunk
 constexpr uint8_t kNfaTodo = 0xff;    // qvalid: rectangle not validated yet
 // rect_improve of rectangle t of frame f -> qres / qvalid (one warp)
@@ -1263,7 +1282,7 @@ struct GrowBufs {
     LsdSeg* qres;
     uint8_t* qvalid;
     unsigned int* nfa_items;  // [nf * kNfaChunksPerFrame] 0xffffffff = not published yet
-    int* nfa_ctl;             // [0] items published (tail), [1] items taken (cursor), [2] frames finished
+    int* nfa_ctl;             // [0] items published (tail), [1] items taken (cursor), [2] frames finished, [4 + smid] CTAs of that SM that still grow
     NfaTabs nfa_tabs;
 };
 
@@ -1823,7 +1842,7 @@ struct pl_line {
     cudaEvent_t ev_grow = nullptr;  // recorded where the streaming stages of a chunk end and its region grower is launched
     int* d_sticky = nullptr;  // capacity flags of the device-pointer API since the last pl_line_sync
     int bits_words = 0, num_sms = 0, grow_tiles = 0, grow_window = 128;
-    int tail_nfa = 1;
+    int tail_nfa = 2;  // 0: k_lsd_nfa validates everything afterwards; 1: CTAs that ran out of frames help; 2: ... but only from SMs on which nothing grows any more
     // k_lsd_grow2 (role-specialised grower, one frame per CTA): shape for up to one frame per SM / for more frames than SMs
     struct Grow2Cfg { int threads = 0, occ = 0, pool_tiles = 0, pool_n = 0, split = 0; size_t smem = 0; } g2_few, g2_many;
     int lookahead = 4;
@@ -1999,7 +2018,7 @@ int line_launch_chunk_direct(pl_line* h, const uint8_t* d_gray, int nf, size_t s
         gb.small_buf = h->d_small_buf; gb.small_rect = h->d_small_rect; gb.queue = h->d_queue; gb.n_rects = h->d_nrects;
         gb.flags = h->d_flags; gb.phase_cycles = prof ? h->d_phase : nullptr; gb.frame_counter = h->d_frame_counter; gb.plane = plane;
         gb.qres = h->d_qres; gb.qvalid = h->d_qvalid; gb.nfa_items = h->d_nfa_items; gb.nfa_ctl = h->d_nfa_ctl; gb.nfa_tabs = h->nfa_tabs;
-        PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_ctl, 0, 4 * sizeof(int), st));
+        PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_ctl, 0, (4 + kSmBusySlots) * sizeof(int), st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_next, 0, sizeof(int) * nf, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_nfa_items, 0xff, sizeof(unsigned int) * (size_t)nf * kNfaChunksPerFrame, st));
         PL_CUDA_TRY(cudaMemsetAsync(h->d_qvalid, 0xff, (size_t)nf * G.seg_cap, st));
@@ -2228,7 +2247,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
             // and the sparse private bitmap (a pool of 32x32-pixel tiles: the more, the fewer regions overflow)
             const int tiles = ((W + 31) / 32) * ((H + 31) / 32);
             h->grow_tiles = tiles;
-            if (const char* ev = getenv("PLSLAM_LSD_TAIL_NFA")) h->tail_nfa = atoi(ev) != 0;
+            if (const char* ev = getenv("PLSLAM_LSD_TAIL_NFA")) h->tail_nfa = std::max(0, std::min(2, atoi(ev)));
             if (const char* ev = getenv("PLSLAM_LSD_POLL_NS")) h->poll_ns = std::max(20, std::min(100000, atoi(ev)));
             if (const char* ev = getenv("PLSLAM_LSD_RESERVE_SMS")) h->reserved_sms = std::max(0, std::min(h->num_sms - 1, atoi(ev)));
             h->grow_window = 128;
@@ -2332,7 +2351,7 @@ PL_API int pl_line_create(pl_line** out, int device, int max_cols, int max_rows,
     A(&h->d_big_bits, max_fs * (size_t)h->bits_words);
     if (e == cudaSuccess) e = cudaMemset(h->d_big_bits, 0, max_fs * (size_t)h->bits_words * sizeof(unsigned int));
     A(&h->d_frame_counter, 1);
-    A(&h->d_nfa_ctl, 4);
+    A(&h->d_nfa_ctl, 4 + kSmBusySlots);
     A(&h->d_nfa_items, B * kNfaChunksPerFrame);
     A(&h->d_nfa_next, B);
     A(&h->d_sticky, 1);
