@@ -62,53 +62,82 @@ struct ExactTab {  // INTER_LINEAR_EXACT coefficients (8.8 fixed point)
 constexpr int kScTW = 64, kScTH = 16;                    // output tile
 constexpr int kScSW = kScTW * 5 / 4 + 4, kScSH = kScTH * 5 / 4 + 4;  // source tile bound (scale 1.25 + bilinear + slack)
 
+// Every stage works on four neighbouring pixels per thread and on the whole (constant-size) tile: no index divisions by run-time
+// widths, 32 / 64-bit shared-memory accesses, one 32-bit store per four output pixels.  Tile pixels outside the span an output
+// tile needs are computed and never read.
 __global__ void __launch_bounds__(256) k_lsd_scale(LineGeom g, const uint8_t* __restrict__ in, size_t in_pitch,
                                                    size_t in_frame_stride, const ExactTab* __restrict__ xtab,
                                                    const ExactTab* __restrict__ ytab, uint8_t* __restrict__ scaled,
                                                    size_t scaled_frame_stride) {
-    __shared__ uint8_t s_src[(kScSH + 4) * (kScSW + 4)];   // source tile + 2 px blur halo
-    __shared__ uint16_t s_h[(kScSH + 4) * kScSW];           // after horizontal pass
-    __shared__ uint8_t s_b[kScSH * kScSW];                  // blurred 8-bit
+    constexpr int SP = kScSW + 4;                    // source tile + 2 px blur halo, bytes per row (a multiple of 4)
+    constexpr int SR = kScSH + 4;
+    static_assert(SP % 4 == 0 && kScSW % 4 == 0, "tile rows are processed four pixels at a time");
+    __shared__ __align__(16) uint8_t s_src[SR * SP];
+    __shared__ __align__(16) uint16_t s_h[SR * kScSW];      // after the horizontal pass
+    __shared__ __align__(16) uint8_t s_b[kScSH * kScSW];    // blurred 8-bit
     const int f = blockIdx.z, tid = threadIdx.x;
     const int ox0 = blockIdx.x * kScTW, oy0 = blockIdx.y * kScTH;
-    const int ox1 = min(ox0 + kScTW, g.W) - 1, oy1 = min(oy0 + kScTH, g.H) - 1;
-    // source span needed by this output tile
-    const int sx0 = xtab[ox0].ofs, sx1 = min((int)xtab[ox1].ofs + 1, g.cols - 1);
-    const int sy0 = ytab[oy0].ofs, sy1 = min((int)ytab[oy1].ofs + 1, g.rows - 1);
-    const int sw = sx1 - sx0 + 1, sh = sy1 - sy0 + 1;  // <= kScSW, kScSH
+    const int sx0 = xtab[ox0].ofs, sy0 = ytab[oy0].ofs;   // first source column / row of this output tile
     const uint8_t* src = in + (size_t)f * in_frame_stride;
-    constexpr int SP = kScSW + 4;
-    for (int i = tid; i < (sh + 4) * (sw + 4); i += 256) {
-        int r = i / (sw + 4), c = i - r * (sw + 4);
-        int yy = reflect101(sy0 + r - 2, g.rows), xx = reflect101(sx0 + c - 2, g.cols);
-        s_src[r * SP + c] = __ldg(src + (size_t)yy * in_pitch + xx);
+    // ---- source tile (REFLECT_101 at the image border) ----
+    for (int i = tid; i < SR * (SP / 4); i += 256) {
+        const int r = i / (SP / 4), q = i - r * (SP / 4);
+        const uint8_t* row = src + (size_t)reflect101(sy0 + r - 2, g.rows) * in_pitch;
+        const int x = sx0 + 4 * q - 2;
+        uint32_t w;
+        if (x >= 0 && x + 3 < g.cols) {
+            w = (uint32_t)__ldg(row + x) | ((uint32_t)__ldg(row + x + 1) << 8) | ((uint32_t)__ldg(row + x + 2) << 16) | ((uint32_t)__ldg(row + x + 3) << 24);
+        } else {
+            w = (uint32_t)__ldg(row + reflect101(x, g.cols)) | ((uint32_t)__ldg(row + reflect101(x + 1, g.cols)) << 8) |
+                ((uint32_t)__ldg(row + reflect101(x + 2, g.cols)) << 16) | ((uint32_t)__ldg(row + reflect101(x + 3, g.cols)) << 24);
+        }
+        reinterpret_cast<uint32_t*>(s_src)[r * (SP / 4) + q] = w;
     }
     __syncthreads();
-    for (int i = tid; i < (sh + 4) * sw; i += 256) {
-        int r = i / sw, c = i - r * sw;
-        const uint8_t* p = s_src + r * SP + c;
-        s_h[r * kScSW + c] = (uint16_t)(4 * (p[0] + p[4]) + 56 * (p[1] + p[3]) + 136 * p[2]);
+    // ---- horizontal pass: h[c] = 4 (p[c] + p[c+4]) + 56 (p[c+1] + p[c+3]) + 136 p[c+2], 16 bits ----
+    for (int i = tid; i < SR * (kScSW / 4); i += 256) {
+        const int r = i / (kScSW / 4), q = i - r * (kScSW / 4);
+        const uint32_t w0 = reinterpret_cast<const uint32_t*>(s_src)[r * (SP / 4) + q], w1 = reinterpret_cast<const uint32_t*>(s_src)[r * (SP / 4) + q + 1];
+        const uint32_t p0 = w0 & 255u, p1 = (w0 >> 8) & 255u, p2 = (w0 >> 16) & 255u, p3 = w0 >> 24;
+        const uint32_t p4 = w1 & 255u, p5 = (w1 >> 8) & 255u, p6 = (w1 >> 16) & 255u, p7 = w1 >> 24;
+        const uint32_t h0 = 4u * (p0 + p4) + 56u * (p1 + p3) + 136u * p2, h1 = 4u * (p1 + p5) + 56u * (p2 + p4) + 136u * p3;
+        const uint32_t h2 = 4u * (p2 + p6) + 56u * (p3 + p5) + 136u * p4, h3 = 4u * (p3 + p7) + 56u * (p4 + p6) + 136u * p5;
+        reinterpret_cast<uint2*>(s_h)[r * (kScSW / 4) + q] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
     }
     __syncthreads();
-    for (int i = tid; i < sh * sw; i += 256) {
-        int r = i / sw, c = i - r * sw;
-        const uint16_t* p = s_h + r * kScSW + c;
-        uint32_t acc = 4u * (p[0] + p[4 * kScSW]) + 56u * (p[kScSW] + p[3 * kScSW]) + 136u * p[2 * kScSW];
-        s_b[r * kScSW + c] = (uint8_t)((acc + 0x8000u) >> 16);
+    // ---- vertical pass, rounded to 8 bits ----
+    for (int i = tid; i < kScSH * (kScSW / 4); i += 256) {
+        const int r = i / (kScSW / 4), q = i - r * (kScSW / 4);
+        const uint2* col = reinterpret_cast<const uint2*>(s_h) + r * (kScSW / 4) + q;
+        const uint2 v0 = col[0], v1 = col[kScSW / 4], v2 = col[2 * (kScSW / 4)], v3 = col[3 * (kScSW / 4)], v4 = col[4 * (kScSW / 4)];
+        auto tap = [](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4) { return (4u * (a0 + a4) + 56u * (a1 + a3) + 136u * a2 + 0x8000u) >> 16; };
+        const uint32_t b0 = tap(v0.x & 0xffffu, v1.x & 0xffffu, v2.x & 0xffffu, v3.x & 0xffffu, v4.x & 0xffffu);
+        const uint32_t b1 = tap(v0.x >> 16, v1.x >> 16, v2.x >> 16, v3.x >> 16, v4.x >> 16);
+        const uint32_t b2 = tap(v0.y & 0xffffu, v1.y & 0xffffu, v2.y & 0xffffu, v3.y & 0xffffu, v4.y & 0xffffu);
+        const uint32_t b3 = tap(v0.y >> 16, v1.y >> 16, v2.y >> 16, v3.y >> 16, v4.y >> 16);
+        reinterpret_cast<uint32_t*>(s_b)[r * (kScSW / 4) + q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
     __syncthreads();
-    uint8_t* dst = scaled + (size_t)f * scaled_frame_stride;
-    for (int i = tid; i < kScTW * kScTH; i += 256) {
-        int r = i / kScTW, c = i - r * kScTW;
-        int ox = ox0 + c, oy = oy0 + r;
-        if (ox >= g.W || oy >= g.H) continue;
-        const ExactTab tx = xtab[ox], ty = ytab[oy];
-        const int ax = tx.ofs - sx0, bx = min(tx.ofs + 1, g.cols - 1) - sx0;
-        const int ay = ty.ofs - sy0, by = min(ty.ofs + 1, g.rows - 1) - sy0;
-        uint32_t r0 = s_b[ay * kScSW + ax] * tx.c0 + s_b[ay * kScSW + bx] * tx.c1;
-        uint32_t r1 = s_b[by * kScSW + ax] * tx.c0 + s_b[by * kScSW + bx] * tx.c1;
-        dst[(size_t)oy * g.spitch + ox] = (uint8_t)((r0 * ty.c0 + r1 * ty.c1 + 32768u) >> 16);
+    // ---- resize: thread = four output pixels of a row ----
+    static_assert(kScTW * kScTH == 4 * 256, "one item per thread");
+    const int r = tid / (kScTW / 4), oy = oy0 + r, oxq = ox0 + 4 * (tid - r * (kScTW / 4));
+    if (oy >= g.H || oxq >= g.W) return;
+    const ExactTab ty = ytab[oy];
+    const int ay = ty.ofs - sy0, by = min(ty.ofs + 1, g.rows - 1) - sy0;
+    uint32_t outw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ox = oxq + k;
+        if (ox < g.W) {
+            const ExactTab tx = xtab[ox];
+            const int ax = tx.ofs - sx0, bx = min(tx.ofs + 1, g.cols - 1) - sx0;
+            const uint32_t r0 = s_b[ay * kScSW + ax] * tx.c0 + s_b[ay * kScSW + bx] * tx.c1;
+            const uint32_t r1 = s_b[by * kScSW + ax] * tx.c0 + s_b[by * kScSW + bx] * tx.c1;
+            outw |= (((r0 * ty.c0 + r1 * ty.c1 + 32768u) >> 16) & 255u) << (8 * k);
+        }
     }
+    // (the pitch is a multiple of 16 and the tile starts at a multiple of 64: an aligned word; columns beyond W are padding)
+    *reinterpret_cast<uint32_t*>(scaled + (size_t)f * scaled_frame_stride + (size_t)oy * g.spitch + oxq) = outw;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
