@@ -99,3 +99,57 @@ def test_dense_feature_arrays_give_the_same_schedule(seq, feats, oracle):
     tfe = fe.TrackingFrontEnd(ThreadedOracle(ob))
     assert tfe.run(gray, depth, T, sf, features=(orb, lines), batch=True) == ref
     assert tfe.keepalive and any(isinstance(k, dict) and "s3" in k for k in tfe.keepalive)   # the dense path was the one taken
+
+
+class DenseResultOracle(ThreadedOracle):
+    """line_search_batch answers the way the CUDA backend does: a sequence that carries the dense (n, max lines) match array."""
+
+    def line_search_batch(self, cvs, lvs, second=False):
+        api = importlib.import_module(PKG + ".api")
+        res = self.ob.line_search_batch(cvs, lvs)
+        nl = np.array([len(r[0]) for r in res], np.int64)
+        out = np.full((len(res), max(int(nl.max()) if len(nl) else 1, 1)), -1, np.int32)
+        for i, r in enumerate(res):
+            out[i, :nl[i]] = r[0]
+        return api._LineMatches(out, nl, *(np.array([r[k] for r in res], np.int32) for k in (1, 2, 3)))
+
+
+def test_dense_paths_with_frames_and_key_frames_without_lines(seq, feats, oracle):
+    """Frames without a single line (one of them a key frame) and a key frame none of whose lines has depth at both ends: the
+    snapshots of the local line map as slices of one gathered array, the D5 views built from them and the dense result summaries
+    must give what the per-frame path gives on the same features."""
+    fe = importlib.import_module(PKG + ".frontend")
+    N = importlib.import_module(PKG + "._native")
+    gray, depth, T = seq
+    depth = depth.copy()
+    depth[8] = 0.0           # key frame 8 (a key frame every 4 frames here) lifts nothing: its lines (and points) have no depth
+    ob = oracle.OracleBackend(1000)
+    sf = ob.scale_factors()
+    orb_l, line_l = feats
+    line_l = list(line_l)
+    for t in (0, 3):          # key frame 0 and frame 3 have no lines at all
+        line_l[t] = (line_l[t][0][:0], line_l[t][1][:0], line_l[t][2][:0])
+    ref = fe.TrackingFrontEnd(ob, keyframe_every=4).run(gray, depth, T, sf, features=(orb_l, line_l), batch=True)
+    assert sum(r.get("d5_matches", 0) for r in ref) > 0 and "d3_matches" not in ref[3] and "d3_matches" not in ref[4]
+    n = len(gray)
+    ml = 80
+    kl = np.zeros((n, ml), N.KL_DTYPE)
+    ld = np.zeros((n, ml, 32), np.uint8)
+    lc = np.zeros((n, ml, 3), np.float64)
+    ln = np.array([len(l[0]) for l in line_l], np.int32)
+    for i in range(n):
+        kl[i, :ln[i]], ld[i, :ln[i]], lc[i, :ln[i]] = line_l[i][0], line_l[i][1], line_l[i][2]
+    lines = fe.FeatureList((kl[i, :ln[i]], ld[i, :ln[i]], lc[i, :ln[i]]) for i in range(n))
+    lines.dense = (kl, ln, ld)
+    for backend in (ThreadedOracle(ob), DenseResultOracle(ob)):
+        assert fe.TrackingFrontEnd(backend, keyframe_every=4).run(gray, depth, T, sf, features=(orb_l, lines), batch=True) == ref
+
+
+def test_line_matches_sequence_behaves_like_the_list_it_replaces():
+    api = importlib.import_module(PKG + ".api")
+    out = np.array([[4, -1, 7], [2, -1, -1]], np.int32)
+    r = api._LineMatches(out, np.array([3, 1]), np.array([2, 1], np.int32), np.array([0, 1], np.int32), np.array([9, 5], np.int32))
+    assert len(r) == 2 and r[1][1:] == (1, 1, 5) and r[-1][0].tolist() == [2] and [x[0].tolist() for x in r] == [[4, -1, 7], [2]]
+    assert [x[1] for x in r[0:2]] == [2, 1]
+    with pytest.raises(IndexError):
+        r[2]
