@@ -204,17 +204,26 @@ class RecordingBackend:
     def extract_lines(self, frames):
         return self.feats[1]
 
-    def search_last_frame_batch(self, *a):
-        return self.plan.record("search_last_frame_batch", *a)
+    # The views are recorded as the C arrays the library reads (a caller that replays a schedule keeps its arrays of views, it
+    # does not rebuild them from Python lists before every call); the arrays they point to stay alive in the front end's keepalive.
+    def _arr(self, views, typ):
+        return self.gb.m._view_array(views, typ)
 
-    def search_local_points_batch(self, *a):
-        return self.plan.record("search_local_points_batch", *a)
+    def search_last_frame_batch(self, cvs, lvs, *a):
+        N = self.gb.api.N
+        return self.plan.record("search_last_frame_batch", self._arr(cvs, N.FrameView), self._arr(lvs, N.LastFrameView), *a)
 
-    def search_local_map_batch(self, *a):
-        return self.plan.record("search_local_map_batch", *a)
+    def search_local_points_batch(self, fvs, mvs, *a):
+        N = self.gb.api.N
+        return self.plan.record("search_local_points_batch", self._arr(fvs, N.FrameView), self._arr(mvs, N.MapPointView), *a)
 
-    def line_search_batch(self, *a):
-        return self.plan.record("line_search_batch", *a)
+    def search_local_map_batch(self, fvs, ow, maps, *a):
+        N = self.gb.api.N
+        return self.plan.record("search_local_map_batch", self._arr(fvs, N.FrameView), ow, self._arr(maps, N.LocalMapView), *a)
+
+    def line_search_batch(self, cvs, lvs, *a):
+        N = self.gb.api.N
+        return self.plan.record("line_search_batch", self._arr(cvs, N.LineFrameView), self._arr(lvs, N.MapLineView), *a)
 
     # the Frame glue of the plan pass goes through the same F-row calls as the end-to-end pass (not recorded: the device-resident
     # step replays the matcher calls only)

@@ -293,12 +293,13 @@ class LineExtractor:
         return out
 
 
-class _LineMatches:
-    """Sequence of (match_of_line, nmatches, used_relaxed, n_projected) per search, backed by dense arrays: `dense` =
-    (matches (n, max lines) padded with -1, nmatches, used_relaxed, n_projected)."""
+class _DenseRows:
+    """Sequence of per-search results (row of matches, scalar, scalar, ...) backed by dense arrays: `dense` = (rows (n, widest) —
+    a row is valid up to its own length —, the scalar columns...).  Stands in for the list of tuples the batched searches returned,
+    without building n small arrays and n tuples when the caller reads the dense arrays."""
 
-    def __init__(self, out, nl, cnt, rel, npj):
-        self.dense = (out, cnt, rel, npj)
+    def __init__(self, out, nl, *cols):
+        self.dense = (out,) + cols
         self._nl = nl
 
     def __len__(self):
@@ -311,11 +312,23 @@ class _LineMatches:
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        out, cnt, rel, npj = self.dense
-        return out[i, :self._nl[i]], int(cnt[i]), int(rel[i]), int(npj[i])
+        return (self.dense[0][i, :self._nl[i]],) + tuple(int(c[i]) for c in self.dense[1:])
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
+
+
+_LineMatches = _DenseRows   # (matches padded with -1, nmatches, used_relaxed, n_projected)
+
+
+def _dense_out(views, typ, fill=None):
+    """One (n, widest view) int32 array for the per-view outputs of a batched search + the array of row pointers the C ABI takes."""
+    n = len(views)
+    nl = np.frombuffer(views, np.dtype(typ), count=n)["n"].astype(np.int64) if n else np.zeros(0, np.int64)
+    stride = max(int(nl.max()), 1) if n else 1
+    out = np.empty((max(n, 1), stride), np.int32) if fill is None else np.full((max(n, 1), stride), fill, np.int32)
+    ptrs = (out.ctypes.data + np.arange(max(n, 1), dtype=np.uint64) * np.uint64(stride * 4)).astype(np.uint64)
+    return out, nl, ptrs
 
 
 class DescriptorMatcher:
@@ -443,11 +456,10 @@ class DescriptorMatcher:
         n = len(frame_views)
         fa = self._view_array(frame_views, N.FrameView)
         pa = self._view_array(pt_views, pt_type)
-        outs = [np.empty(max(v.n, 1), np.int32) for v in frame_views]
-        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        out, nl, ptrs = _dense_out(fa, N.FrameView)
         cnt = np.zeros(max(n, 1), np.int32)
-        check(fn(self._h, C.c_int(n), fa, pa, *scalars, ptrs, ptr(cnt)))
-        return [(outs[i][:frame_views[i].n], int(cnt[i])) for i in range(n)]
+        check(fn(self._h, C.c_int(n), fa, pa, *scalars, ptr(ptrs), ptr(cnt)))
+        return _DenseRows(out[:n], nl, cnt[:n]) if n else []
 
     def SearchByProjectionLastFrameBatch(self, cur_views, last_views, th, mono=False, check_orientation=True):
         return self._batch_points(N.lib().pl_orb_search_last_frame_batch, cur_views, last_views, N.LastFrameView, C.c_float(th),
@@ -466,12 +478,11 @@ class DescriptorMatcher:
         ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
         mof = np.ascontiguousarray(map_of_frame, np.int32).reshape(-1)
         assert ow.shape[0] == n and mof.shape[0] == n
-        outs = [np.empty(max(v.n, 1), np.int32) for v in frame_views]
-        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        out, nl, ptrs = _dense_out(fa, N.FrameView)
         cnt, inv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
         check(N.lib().pl_orb_search_local_map_batch(self._h, C.c_int(n), fa, ptr(ow), C.c_int(len(map_views)), ma, ptr(mof), C.c_float(viewing_cos_limit),
-                                                    C.c_float(log_scale_factor), C.c_float(th), C.c_float(nn_ratio), ptrs, ptr(cnt), ptr(inv)))
-        return [(outs[i][:frame_views[i].n], int(cnt[i]), int(inv[i])) for i in range(n)]
+                                                    C.c_float(log_scale_factor), C.c_float(th), C.c_float(nn_ratio), ptr(ptrs), ptr(cnt), ptr(inv)))
+        return _DenseRows(out[:n], nl, cnt[:n], inv[:n]) if n else []
 
     def SearchLinesByProjectionBatch(self, cur_views, line_views):
         """LineMatcher::SearchByProjection for n (frame, map lines) pairs ->
@@ -480,14 +491,11 @@ class DescriptorMatcher:
         ca = self._view_array(cur_views, N.LineFrameView)
         la = self._view_array(line_views, N.MapLineView)
         # one (n, max lines) result array, rows padded with -1; `dense` on the returned sequence hands it over whole
-        nl = np.frombuffer(ca, np.dtype(N.LineFrameView), count=n)["n"].astype(np.int64) if n else np.zeros(0, np.int64)
-        stride = max(int(nl.max()), 1) if n else 1
-        out = np.full((max(n, 1), stride), -1, np.int32)
-        ptrs = (out.ctypes.data + np.arange(max(n, 1), dtype=np.uint64) * np.uint64(stride * 4)).astype(np.uint64)
+        out, nl, ptrs = _dense_out(ca, N.LineFrameView, fill=-1)
         cnt, rel, npj = (np.zeros(max(n, 1), np.int32) for _ in range(3))
         nulls = (C.c_void_p * max(n, 1))()
         check(N.lib().pl_line_search_by_projection_batch(self._h, C.c_int(n), ca, la, ptr(ptrs), ptr(cnt), ptr(rel), nulls, nulls, ptr(npj)))
-        return _LineMatches(out[:n], nl, cnt[:n], rel[:n], npj[:n])
+        return _LineMatches(out[:n], nl, cnt[:n], rel[:n], npj[:n]) if n else []
 
     # ---- C4 / C5: pose-based projection searches ----
     def _pose_points(self, fn, frame_views, pt_views, ow, log_sf, *scalars):
