@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--orb-behind-prestages", type=int, default=0, help="device-resident step: enqueue the line extractor first and let the ORB extractor's stream wait until the region grower is launched (pl_line_stream_wait_grow_start)")
     ap.add_argument("--overlap-orb", type=int, default=1, help="device-resident step: let the line extractor start next to the ORB extractor instead of behind it")
     ap.add_argument("--e2e-shared-upload", type=int, default=1, help="e2e leg, order orb_first: the line extractor reads the frames the ORB extractor staged in HBM (pl_orb_staged_images_dev + pl_line_extract_batch_from_dev) instead of uploading them again")
-    ap.add_argument("--e2e-order", default="orb_first", choices=["orb_first", "together"], help="e2e leg: call the ORB extractor before the line extractor's thread starts, or both at once")
+    ap.add_argument("--e2e-order", default="orb_first", choices=["orb_first", "staged", "together"], help="e2e leg: call the ORB extractor before the line extractor's thread starts (default); staged: both at once on one upload (pl_orb_stage_batch / pl_orb_stream_wait_staged / pl_orb_extract_staged; measured: the ORB call then returns at 16-17 ms instead of 7 because its kernels only get what the resident growers leave, lines 2 ms earlier, points 5-8 ms later: 5,460-5,500 against 5,850-5,900 frames/s); together: both at once, two uploads")
     ap.add_argument("--device-glue", type=int, default=1, help="e2e leg: Frame glue (UnprojectStereo, IsInFrustum) through the batched F-row calls instead of numpy")
     ap.add_argument("--c5-frames", type=int, default=4096, help="frames of the config-5 leg (batched offline extraction sharded frame-wise over the ranks); 0 = skip")
     ap.add_argument("--c5-chunk", type=int, default=512, help="frames per device-resident chunk of the config-5 leg")
@@ -332,13 +332,15 @@ def run_ours(a, rank, world, local_rank, dist):
         def __init__(self, shared=False):
             self.err = []
             self.shared = shared
+            # (asked for on the caller's thread: the ORB handle may be inside pl_orb_extract_staged when the thread gets to run)
+            self.staged = gb.orb.staged_images() if shared else None
             self.th = threading.Thread(target=self.work)
             self.th.start()
 
         def work(self):
             try:
                 if self.shared:  # the frames are in HBM already: the ORB extractor's call staged them (one upload per frame, as one cv::Mat serves both extractors)
-                    d, n, r, c_, st_, fs = gb.orb.staged_images()
+                    d, n, r, c_, st_, fs = self.staged
                     assert (n, r, c_) == (F, H, W), "the ORB extractor staged another batch"
                     gb.line.extract_batch_from_dev_into(d, n, r, c_, st_, fs, MAXL, kl_np, ld_np, lc_np, ln_np)
                 else:
@@ -354,13 +356,21 @@ def run_ours(a, rank, world, local_rank, dist):
             r.dense = (kl_np, ln_np, ld_np)
             return r
 
-    shared_upload = bool(a.e2e_shared_upload) and a.e2e_order == "orb_first" and chunk >= F
+    staged_order = a.e2e_order == "staged" and chunk >= F
+    shared_upload = bool(a.e2e_shared_upload) and a.e2e_order in ("orb_first", "staged") and chunk >= F
 
     def step_e2e():
         # ORB first (4-5 ms of device time), the line extractor right behind it on its own thread: next to the region grower's
         # resident CTAs the ORB kernels would only get what is left of every SM and arrive later, and the point side of the glue
         # needs them first
-        if a.e2e_order == "orb_first":
+        if staged_order:
+            # one upload, both extractors at once: the ORB call in its two halves (pl_orb_stage_batch enqueues the copy and returns,
+            # pl_orb_extract_staged is the rest), the line extractor's thread started in between on the staged frames
+            gb.orb.stage_batch(hg)
+            gb.orb.stream_wait_staged(gb.line.stream())   # on the device: the line extractor's stream waits for the upload
+            lines_later = LinesLater(shared=True)
+            gb.orb.extract_staged_into(kp_np, dd_np, nn_np)
+        elif a.e2e_order in ("orb_first", "staged"):   # (staged needs the whole sequence in one chunk)
             gb.orb.extract_batch_into(hg, kp_np, dd_np, nn_np)
             lines_later = LinesLater(shared=shared_upload)
         else:

@@ -167,6 +167,15 @@ PL_API int pl_line_extract_batch(pl_line* h, const uint8_t* gray, int n_frames, 
  * pl_line_extract_batch reading its images from device memory (results to host memory, synchronous) — so a frame travels to the
  * device once. */
 PL_API int pl_orb_staged_images_dev(pl_orb* h, const uint8_t** d_images, int* n_frames, int* rows, int* cols, size_t* step, size_t* frame_stride);
+/* pl_orb_extract_batch in two halves, for ONE chunk (n_frames <= max_batch): pl_orb_stage_batch only enqueues the copy of the frames
+ * into the staging buffer and returns; pl_orb_extract_staged is the rest of the call (kernels, read-back, capacity check; synchronous,
+ * same results and error behaviour as pl_orb_extract_batch).  In between, pl_orb_stream_wait_staged makes another stream — the line
+ * extractor's, pl_line_stream() — wait for the staging copy, so that pl_line_extract_batch_from_dev on the staged frames
+ * (pl_orb_staged_images_dev) can be issued from the second host thread at once: the two extractors of the Frame constructor
+ * (Frame.cc:152-155) start together on one upload. */
+PL_API int pl_orb_stage_batch(pl_orb* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride);
+PL_API int pl_orb_stream_wait_staged(pl_orb* h, void* stream);
+PL_API int pl_orb_extract_staged(pl_orb* h, pl_keypoint* kps, uint8_t* desc, int cap, int* n_out);
 PL_API int pl_line_extract_batch_from_dev(pl_line* h, const uint8_t* d_gray, int n_frames, int rows, int cols, size_t step,
                                           size_t frame_stride, int max_lines, pl_keyline* kls, uint8_t* desc, double* coeffs,
                                           int* n_out);

@@ -131,6 +131,26 @@ class ORBextractor:
                                            C.c_int(cap), ptr(cnt)))
         self._last = (min(n, self.max_batch) if n % self.max_batch == 0 else n % self.max_batch, rows, cols)
 
+    def stage_batch(self, frames):
+        """pl_orb_stage_batch: enqueue the upload of one chunk of host frames and return (extract_staged_into does the rest)."""
+        fr = np.asarray(frames)
+        assert fr.dtype == np.uint8 and fr.ndim == 3 and fr.strides[2] == 1
+        n, rows, cols = fr.shape
+        check(N.lib().pl_orb_stage_batch(self._h, ptr(fr), C.c_int(n), C.c_int(rows), C.c_int(cols), C.c_size_t(fr.strides[1]), C.c_size_t(fr.strides[0])))
+        self._keep_staged = fr   # the copy is asynchronous: the host frames stay alive until extract_staged_into returns
+        self._last = (n, rows, cols)
+
+    def stream_wait_staged(self, stream):
+        """pl_orb_stream_wait_staged: `stream` (a raw cudaStream_t, e.g. LineExtractor.stream()) waits for the staging copy."""
+        check(N.lib().pl_orb_stream_wait_staged(self._h, C.c_void_p(stream)))
+
+    def extract_staged_into(self, kps, desc, cnt):
+        """pl_orb_extract_staged with caller-owned outputs (as extract_batch_into)."""
+        cap = kps.shape[1]
+        assert desc.shape[:2] == kps.shape[:2] and len(cnt) >= self._last[0] and kps.shape[0] >= self._last[0]
+        check(N.lib().pl_orb_extract_staged(self._h, ptr(kps), ptr(desc), C.c_int(cap), ptr(cnt)))
+        self._keep_staged = None
+
     def staged_images(self):
         """(device address, n_frames, rows, cols, step, frame_stride) of the images the last host-pointer extract call left in HBM."""
         d, n, r, c_, st, fs = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()

@@ -911,6 +911,8 @@ struct pl_orb {
     int* d_sticky = nullptr; // capacity flags of the device-pointer API since the last pl_orb_sync
     int last_batch = 0;      // frames of the last chunk (for debug reads)
     int staged_frames = 0;   // frames of the caller's images in d_in after a host-pointer call (its last chunk), 0 = none
+    cudaEvent_t ev_staged = nullptr;  // recorded behind the staging copy of pl_orb_stage_batch (pl_orb_stream_wait_staged)
+    bool staged_pending = false;      // pl_orb_stage_batch staged a batch that pl_orb_extract_staged has not processed yet
     int staged_rows = 0, staged_cols = 0;
     int last_launches = 0;
     size_t oct_smem = 0;
@@ -1283,6 +1285,7 @@ PL_API void pl_orb_destroy(pl_orb* h) {
     if (h->h_flags) cudaFreeHost(h->h_flags);
     for (int i = 0; i < 8; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->ev_staged) cudaEventDestroy(h->ev_staged);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1390,6 +1393,39 @@ PL_API int pl_orb_staged_images_dev(pl_orb* h, const uint8_t** d_images, int* n_
     return PL_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// the staging buffer of the host-pointer calls (max_batch frames at the staging pitch)
+int ensure_staging(pl_orb* h, int rows, int cols) {
+    const size_t need_in = (size_t)h->max_batch * align_up((size_t)cols, 16) * rows;
+    if (h->in_alloc < need_in) {
+        if (h->d_in) cudaFree(h->d_in);
+        h->d_in = nullptr; h->in_alloc = 0;
+        PL_CUDA_TRY(cudaMalloc((void**)&h->d_in, need_in));
+        h->in_alloc = need_in;
+    }
+    return PL_OK;
+}
+// nf frames from host memory into the staging buffer, asynchronously on the handle's stream: one copy when the caller's frames are
+// dense and already have the staging pitch, else one strided copy per frame
+int stage_frames(pl_orb* h, const uint8_t* gray, int nf, int rows, int cols, size_t step, size_t frame_stride) {
+    const size_t in_pitch = align_up((size_t)cols, 16);
+    if (step == in_pitch && frame_stride == in_pitch * (size_t)rows)
+        PL_CUDA_TRY(cudaMemcpyAsync(h->d_in, gray, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->stream));
+    else
+        for (int f = 0; f < nf; f++)
+            PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)f * frame_stride, step, cols, rows,
+                                          cudaMemcpyHostToDevice, h->stream));
+    h->staged_frames = nf; h->staged_rows = rows; h->staged_cols = cols;
+    return PL_OK;
+}
+int extract_batch_impl(pl_orb* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride, pl_keypoint* kps,
+                       uint8_t* desc, int cap, int* n_out, bool already_staged);
+}  // namespace
+
+extern "C" {
+
 PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step,
                                 size_t frame_stride, pl_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
     PL_CHECK_ARG(h && kps && desc && n_out && cap > 0);
@@ -1399,17 +1435,71 @@ PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, in
     }
     PL_CHECK_ARG(cols <= h->max_cols && rows <= h->max_rows && step >= (size_t)cols);
     PL_CUDA_TRY(cudaSetDevice(h->device));
+    h->staged_pending = false;
+    return extract_batch_impl(h, gray, n_frames, rows, cols, step, frame_stride, kps, desc, cap, n_out, false);
+}
+
+// The two halves of pl_orb_extract_batch for ONE chunk (n_frames <= max_batch).  pl_orb_stage_batch only enqueues the copy of the
+// frames into the staging buffer and returns; pl_orb_stream_wait_staged makes another stream (the line extractor's) wait for that
+// copy, so that pl_line_extract_batch_from_dev can start on the staged frames while pl_orb_extract_staged — the rest of the call:
+// kernels, read-back, capacity check — is still running.  One cv::Mat serves both extractors in the reference (Frame.cc:152-155).
+PL_API int pl_orb_stage_batch(pl_orb* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride) {
+    PL_CHECK_ARG(h != nullptr);
+    if (!gray || rows <= 0 || cols <= 0 || n_frames <= 0) {
+        set_error("empty image");
+        return PL_ERR_EMPTY;
+    }
+    PL_CHECK_ARG(cols <= h->max_cols && rows <= h->max_rows && step >= (size_t)cols);
+    if (n_frames > h->max_batch) {
+        set_error("pl_orb_stage_batch stages one chunk: %d frames exceed max_batch %d", n_frames, h->max_batch);
+        return PL_ERR_CAPACITY;
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    int rc = build_geometry(h, rows, cols);
+    if (rc != PL_OK) return rc;
+    if ((rc = ensure_staging(h, rows, cols)) != PL_OK) return rc;
+    if (!h->ev_staged) PL_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
+    if ((rc = stage_frames(h, gray, n_frames, rows, cols, step, frame_stride)) != PL_OK) return rc;
+    PL_CUDA_TRY(cudaEventRecord(h->ev_staged, h->stream));
+    h->staged_pending = true;
+    return PL_OK;
+}
+
+PL_API int pl_orb_stream_wait_staged(pl_orb* h, void* stream) {
+    PL_CHECK_ARG(h != nullptr);
+    if (!h->staged_pending || !h->ev_staged) {
+        set_error("nothing staged: pl_orb_stream_wait_staged follows pl_orb_stage_batch");
+        return PL_ERR_STATE;
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    PL_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_staged, 0));
+    return PL_OK;
+}
+
+PL_API int pl_orb_extract_staged(pl_orb* h, pl_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+    PL_CHECK_ARG(h && kps && desc && n_out && cap > 0);
+    if (!h->staged_pending || h->staged_frames <= 0) {
+        set_error("nothing staged: pl_orb_extract_staged follows pl_orb_stage_batch");
+        return PL_ERR_STATE;
+    }
+    PL_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t in_pitch = align_up((size_t)h->staged_cols, 16);
+    const int rc = extract_batch_impl(h, nullptr, h->staged_frames, h->staged_rows, h->staged_cols, in_pitch, in_pitch * (size_t)h->staged_rows, kps, desc,
+                                      cap, n_out, true);
+    h->staged_pending = false;
+    return rc;
+}
+
+}  // extern "C"
+
+namespace {
+int extract_batch_impl(pl_orb* h, const uint8_t* gray, int n_frames, int rows, int cols, size_t step, size_t frame_stride, pl_keypoint* kps,
+                       uint8_t* desc, int cap, int* n_out, bool already_staged) {
     int rc = build_geometry(h, rows, cols);
     if (rc != PL_OK) return rc;
     const size_t B = h->max_batch;
     const size_t in_pitch = align_up((size_t)cols, 16);
-    size_t need_in = B * in_pitch * rows;
-    if (h->in_alloc < need_in) {
-        if (h->d_in) cudaFree(h->d_in);
-        h->d_in = nullptr; h->in_alloc = 0;
-        PL_CUDA_TRY(cudaMalloc((void**)&h->d_in, need_in));
-        h->in_alloc = need_in;
-    }
+    if ((rc = ensure_staging(h, rows, cols)) != PL_OK) return rc;
     if (h->out_cap_alloc < cap) {
         if (h->d_kps) cudaFree(h->d_kps);
         if (h->d_desc) cudaFree(h->d_desc);
@@ -1421,14 +1511,7 @@ PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, in
     h->last_launches = 0;
     for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
         const int nf = std::min(h->max_batch, n_frames - f0);
-        // one copy per chunk when the caller's frames are dense and already have the staging pitch, else one strided copy per frame
-        if (step == in_pitch && frame_stride == in_pitch * (size_t)rows)
-            PL_CUDA_TRY(cudaMemcpyAsync(h->d_in, gray + (size_t)f0 * frame_stride, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->stream));
-        else
-            for (int f = 0; f < nf; f++)
-                PL_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * in_pitch * rows, in_pitch, gray + (size_t)(f0 + f) * frame_stride,
-                                              step, cols, rows, cudaMemcpyHostToDevice, h->stream));
-        h->staged_frames = nf; h->staged_rows = rows; h->staged_cols = cols;
+        if (!already_staged && (rc = stage_frames(h, gray + (size_t)f0 * frame_stride, nf, rows, cols, step, frame_stride)) != PL_OK) return rc;
         rc = launch_chunk(h, h->d_in, nf, in_pitch, in_pitch * rows, h->d_kps, h->d_desc, cap, h->d_nout);
         if (rc != PL_OK) return rc;
         PL_CUDA_TRY(cudaMemcpyAsync(n_out + f0, h->d_nout, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->stream));
@@ -1458,6 +1541,9 @@ PL_API int pl_orb_extract_batch(pl_orb* h, const uint8_t* gray, int n_frames, in
     }
     return PL_OK;
 }
+}  // namespace
+
+extern "C" {
 
 PL_API int pl_orb_extract(pl_orb* h, const uint8_t* gray, int rows, int cols, size_t step, pl_keypoint* kps, uint8_t* desc,
                           int cap, int* n_out) {

@@ -99,6 +99,54 @@ def test_line_extractor_reads_the_frames_the_orb_extractor_staged(api, synth):
             assert np.array_equal(lc[i, :ln[i]], ref[2][i, :ln[i]])
 
 
+@pytest.mark.gpu
+def test_orb_call_in_two_halves_with_the_line_extractor_started_in_between(api, synth):
+    """pl_orb_stage_batch + pl_orb_extract_staged give what pl_orb_extract_batch gives, and a line extractor whose stream waits
+    for the staging copy (pl_orb_stream_wait_staged) and that is called from a second host thread while the ORB half is still
+    running reads the same frames (Frame.cc:152-155: one image, two extractor threads)."""
+    import threading
+    N = api.N
+    for w, h in ((640, 480), (333, 250)):
+        frames = synth.frames(6200, 6, w, h)
+        orb = api.ORBextractor(700, 1.2, 8, 20, 7, max_cols=w, max_rows=h, max_batch=8)
+        cap = orb.max_keypoints()
+        ref = [np.zeros((6, cap), N.KP_DTYPE), np.zeros((6, cap, 32), np.uint8), np.zeros(6, np.int32)]
+        orb.extract_batch_into(frames, *ref)
+        ex = api.LineExtractor(max_cols=w, max_rows=h, max_batch=8)
+        lref = ex.extract_batch(frames)
+        with pytest.raises(Exception):
+            orb.extract_staged_into(*ref)        # nothing staged (the one-call entry leaves nothing pending)
+        with pytest.raises(Exception):
+            orb.stream_wait_staged(ex.stream())
+        for _ in range(2):
+            kp, dd, nn = np.zeros((6, cap), N.KP_DTYPE), np.zeros((6, cap, 32), np.uint8), np.zeros(6, np.int32)
+            kl, ld, lc, ln = np.zeros((6, 80), N.KL_DTYPE), np.zeros((6, 80, 32), np.uint8), np.zeros((6, 80, 3), np.float64), np.zeros(6, np.int32)
+            orb.stage_batch(frames)
+            orb.stream_wait_staged(ex.stream())
+            d, n, r, c, st, fs = orb.staged_images()
+            assert (n, r, c) == (6, h, w)
+            err = []
+
+            def lines():
+                try:
+                    ex.extract_batch_from_dev_into(d, n, r, c, st, fs, 80, kl, ld, lc, ln)
+                except BaseException as e:
+                    err.append(e)
+            th = threading.Thread(target=lines)
+            th.start()
+            orb.extract_staged_into(kp, dd, nn)
+            th.join()
+            assert not err
+            assert np.array_equal(nn, ref[2]) and nn.sum() > 1000
+            for i in range(6):
+                assert np.array_equal(kp[i, :nn[i]], ref[0][i, :nn[i]]) and np.array_equal(dd[i, :nn[i]], ref[1][i, :nn[i]])
+                assert np.array_equal(kl[i, :ln[i]], lref[0][i, :ln[i]]) and np.array_equal(ld[i, :ln[i]], lref[1][i, :ln[i]])
+            assert np.array_equal(ln, lref[3])
+        with pytest.raises(Exception):
+            orb.stage_batch(synth.frames(6200, 9, w, h))   # more than one chunk
+
+
+
 def test_orb_stream_can_wait_for_the_grower_launch(api, synth):
     """pl_line_stream_wait_grow_start: the ORB extractor's stream waits for the point where the line extractor's streaming stages end;
     both results are what they are without the dependency (and waiting on a handle that never extracted is a no-op)."""
