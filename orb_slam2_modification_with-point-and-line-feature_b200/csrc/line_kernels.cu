@@ -197,9 +197,10 @@ __device__ __forceinline__ double lsd_bin_coef(int maxq) {
 }
 
 // per-tile histograms: one warp walks kTileRows rows
+// (also leaves every pixel's bin, 0xffff = no gradient, in `bins` for k_lsd_scatter: the bin is a double sqrt + multiply per pixel)
 __global__ void __launch_bounds__(256) k_lsd_bin_count(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
                                                        size_t plane, const int* __restrict__ max_g2,
-                                                       unsigned short* __restrict__ tile_hist) {
+                                                       unsigned short* __restrict__ tile_hist, unsigned short* __restrict__ bins) {
     __shared__ int s_hist[8][kBins];
     const int f = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + w;
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(256) k_lsd_bin_count(LineGeom g, const float* 
             const size_t row = (size_t)f * plane + (size_t)y * g.W;
             for (int x = lane; x < g.W - 1; x += 32) {
                 int b = lsd_bin(angdeg[row + x], g2[row + x], coef);
+                bins[row + x] = (unsigned short)b;   // -1 -> 0xffff (kBins <= 0xffff)
                 if (b >= 0) atomicAdd(&s_hist[w][b], 1);
             }
         }
@@ -260,9 +262,8 @@ __global__ void __launch_bounds__(kBins) k_lsd_bin_scan(LineGeom g, const unsign
 }
 
 // stable scatter: seeds[f][pos] = raster index (y*W+x); order = bin descending, raster ascending inside a bin
-__global__ void __launch_bounds__(256) k_lsd_scatter(LineGeom g, const float* __restrict__ angdeg, const int* __restrict__ g2,
-                                                     size_t plane, const int* __restrict__ max_g2, const int* __restrict__ tile_off,
-                                                     unsigned int* __restrict__ seeds) {
+__global__ void __launch_bounds__(256) k_lsd_scatter(LineGeom g, const unsigned short* __restrict__ bins, size_t plane,
+                                                     const int* __restrict__ tile_off, unsigned int* __restrict__ seeds) {
     __shared__ int s_off[8][kBins];
     const int f = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + w;
@@ -270,7 +271,6 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(LineGeom g, const float* __
     const int* off = tile_off + ((size_t)f * g.n_tiles + tile) * kBins;
     for (int i = lane; i < kBins; i += 32) s_off[w][i] = off[i];
     __syncwarp();
-    const double coef = lsd_bin_coef(max_g2[f]);
     unsigned int* out = seeds + (size_t)f * plane;
     const int y0 = tile * kTileRows, y1 = min(y0 + kTileRows, g.H - 1);
     const unsigned lt = (1u << lane) - 1u;
@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(256) k_lsd_scatter(LineGeom g, const float* __
         for (int xb = 0; xb < g.W - 1; xb += 32) {
             const int x = xb + lane;
             int b = -1;
-            if (x < g.W - 1) b = lsd_bin(angdeg[row + x], g2[row + x], coef);
+            if (x < g.W - 1) {
+                const unsigned short bs = bins[row + x];
+                b = bs == 0xffffu ? -1 : (int)bs;
+            }
             const unsigned valid = __ballot_sync(0xffffffffu, b >= 0);
             if (b >= 0) {
                 const unsigned peers = __match_any_sync(valid, b);
@@ -2029,9 +2032,11 @@ int line_launch_chunk_direct(pl_line* h, const uint8_t* d_gray, int nf, size_t s
         launches++;
     }
     if (prof) cudaEventRecord(h->ev[1], st);
-    k_lsd_bin_count<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_hist);
+    // (the Sobel planes are written after the region grower: until then d_dx holds the per-pixel bins, W x H <= cols x rows of them per frame)
+    unsigned short* d_bins = reinterpret_cast<unsigned short*>(h->d_dx);
+    k_lsd_bin_count<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_hist, d_bins);
     k_lsd_bin_scan<<<nf, kBins, 0, st>>>(G, h->d_tile_hist, h->d_tile_off, h->d_nseeds);
-    k_lsd_scatter<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, h->d_ang, h->d_g2, plane, h->d_maxg2, h->d_tile_off, h->d_seeds);
+    k_lsd_scatter<<<dim3((G.n_tiles + 7) / 8, nf), 256, 0, st>>>(G, d_bins, plane, h->d_tile_off, h->d_seeds);
     launches += 3;
     if (prof) cudaEventRecord(h->ev[2], st);
     {
