@@ -115,3 +115,13 @@ class Vocabulary:
                                 _p(noff), _p(fidx))
         fv = {int(nid[i]): fidx[noff[i]:noff[i + 1]].copy() for i in range(nn.value)}
         return (wid[:nw.value].copy(), wv[:nw.value].copy()), fv
+
+
+def search_local_points(frame_view, mp_view, th, nn_ratio):
+    """C2 through the reference's own ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:72-183, with
+    Frame::GetFeaturesInArea / AssignFeaturesToGrid / PosInGrid of Frame.cc) -> (match_of_feature, nmatches), as
+    pyoracle.search_local_points."""
+    match = np.empty(max(frame_view.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().ref_orb_search_local_points(C.byref(frame_view), C.byref(mp_view), C.c_float(th), C.c_float(nn_ratio), _p(match), C.byref(n))
+    return match[:frame_view.n], n.value

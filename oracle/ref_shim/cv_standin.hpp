@@ -103,6 +103,7 @@ public:
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     Mat rowRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * step; m.rows = b - a; return m; }
+    Mat row(int r) const { return rowRange(r, r + 1); }
     Mat colRange(int a, int b) const { Mat m = *this; m.data = data + a; m.cols = b - a; return m; }
     Mat operator()(const Rect& r) const { Mat m = *this; m.data = data + (size_t)r.y * step + r.x; m.rows = r.height; m.cols = r.width; return m; }
     Mat clone() const {

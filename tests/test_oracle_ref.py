@@ -3,6 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, the rotation-histogram rule of C3 / C6 / C7 and G to reference
 code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+import importlib
 import os
 import sys
 
@@ -118,3 +119,37 @@ def test_vocabulary_transform_equals_dbow2(seed, k, L, scoring, weighting, n, le
     (ow, ov), ofv = orc.transform(feats, levelsup)
     assert np.array_equal(rw, ow) and np.array_equal(rv, ov)          # word ids and values: the same doubles
     assert sorted(rfv) == sorted(ofv) and all(np.array_equal(rfv[q], np.asarray(ofv[q], np.uint32)) for q in rfv)
+
+
+@pytest.mark.parametrize("seed,n,m,th", [(1, 1000, 2500, 3.0), (2, 50, 10, 1.0), (3, 2000, 300, 5.0), (4, 0, 20, 3.0), (5, 300, 0, 3.0),
+                                         (6, 1200, 3000, 1.0), (7, 800, 1500, 7.0)])
+def test_search_by_projection_of_local_points_equals_the_reference_code(seed, n, m, th, oracle, synth):
+    """C2: the reference's own ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:72-183) with its
+    RadiusByViewingCos and Frame::GetFeaturesInArea / AssignFeaturesToGrid / PosInGrid (Frame.cc:432-485, :265-287, :527-538), cut out
+    of the reference sources and compiled against stand-in Frame / MapPoint classes, against the oracle's restatement: dense,
+    colliding inputs (many map points compete for the same features, later points overwrite earlier matches unless the earlier point
+    has observations), claimed features, stereo and monocular features, points outside the image."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    kp, desc, ur = matchgen.rand_frame(rng, n, N)
+    ur[rng.random(n) < 0.3] = -1.0          # features without a stereo coordinate skip the right-image test
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    claimed = (rng.random(n) < 0.1).astype(np.int32)
+    keep = []
+    fv = N.make_frame_view(kp, desc, ur, claimed, (0, 0, 640, 480), synth.TUM1, np.eye(4, dtype=np.float32)[:3].reshape(-1), sf, keep)
+    src = rng.integers(0, max(n, 1), m)
+    mdesc = (desc[src] if n else rng.integers(0, 256, (m, 32), dtype=np.uint8)).copy()
+    mdesc ^= np.packbits(rng.random((m, 256)) < 0.05, axis=1, bitorder="little")
+    px = (kp["x"][src] if n else np.zeros(m)) + rng.normal(0, 3, m)
+    py = (kp["y"][src] if n else np.zeros(m)) + rng.normal(0, 3, m)
+    far = rng.random(m) < 0.05              # a few projections far outside the image: GetFeaturesInArea's early returns
+    px[far] += rng.choice([-2000.0, 2000.0], int(far.sum()))
+    py[far] += rng.choice([-2000.0, 2000.0], int(far.sum()))
+    lvl = np.clip((kp["octave"][src] if n else np.zeros(m, np.int64)) + rng.integers(0, 2, m), 0, 7)
+    mv = N.make_mappoint_view(mdesc, rng.random(m) < 0.9, px, py, px - 20, lvl, rng.uniform(0.99, 1.0, m), rng.random(m) < 0.5, keep)
+    for nn in (0.8, 0.6):
+        r = pyref.search_local_points(fv, mv, th, nn)
+        o = oracle.search_local_points(fv, mv, th, nn)
+        assert np.array_equal(r[0], o[0]) and r[1] == o[1]
+    if n >= 1000 and m >= 1000:
+        assert o[1] > 200
