@@ -125,3 +125,14 @@ def search_local_points(frame_view, mp_view, th, nn_ratio):
     n = C.c_int(0)
     lib().ref_orb_search_local_points(C.byref(frame_view), C.byref(mp_view), C.c_float(th), C.c_float(nn_ratio), _p(match), C.byref(n))
     return match[:frame_view.n], n.value
+
+
+def search_last_frame(cur_view, last_view, th, mono=False, check_orientation=True):
+    """C3 through the reference's own ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+    (ORBmatcher.cc:1710-1879; cv::Mat float expressions through the stand-in's gemm) -> (match_of_feature, nmatches), as
+    pyoracle.search_last_frame."""
+    match = np.empty(max(cur_view.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().ref_orb_search_last_frame(C.byref(cur_view), C.byref(last_view), C.c_float(th), C.c_int(int(mono)), C.c_int(int(check_orientation)),
+                                    _p(match), C.byref(n))
+    return match[:cur_view.n], n.value

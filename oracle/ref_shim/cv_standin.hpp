@@ -70,13 +70,15 @@ public:
     int rows, cols;
     size_t step;
     uchar* data;
+    size_t esz = 1;   // element size: 1 (CV_8U) or 4 (CV_32F: the 4x4 poses and 3x1 points of the matchers)
     Mat() : rows(0), cols(0), step(0), data(nullptr) {}
     Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(nullptr) { create(r, c, type); }
     Mat(Size sz, int type) : rows(0), cols(0), step(0), data(nullptr) { create(sz.height, sz.width, type); }
-    Mat(int r, int c, int /*type*/, void* ext, size_t st = 0) : rows(r), cols(c), step(st ? st : (size_t)c), data((uchar*)ext) {}
+    Mat(int r, int c, int type, void* ext, size_t st = 0)
+        : rows(r), cols(c), step(st ? st : (size_t)c * (type == CV_32F ? 4 : 1)), data((uchar*)ext), esz(type == CV_32F ? 4 : 1) {}
     void create(int r, int c, int type) {
-        const size_t esz = type == CV_32F ? 4 : 1;
-        if (r == rows && c == cols && data) return;  // (as cv::Mat::create: a matrix of the right size, ROI or not, is kept)
+        if (r == rows && c == cols && data && esz == (size_t)(type == CV_32F ? 4 : 1)) return;  // (as cv::Mat::create: a matrix of the right size, ROI or not, is kept)
+        esz = type == CV_32F ? 4 : 1;
         rows = r; cols = c; step = (size_t)c * esz;
         buf_ = std::shared_ptr<uchar>(new uchar[(size_t)r * step > 0 ? (size_t)r * step : 1], std::default_delete<uchar[]>());
         data = buf_.get();
@@ -104,11 +106,22 @@ public:
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     Mat rowRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * step; m.rows = b - a; return m; }
     Mat row(int r) const { return rowRange(r, r + 1); }
-    Mat colRange(int a, int b) const { Mat m = *this; m.data = data + a; m.cols = b - a; return m; }
+    Mat colRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * esz; m.cols = b - a; return m; }
+    Mat col(int c) const { return colRange(c, c + 1); }
+    // single-index access of a vector (3x1 or 1x3)
+    template <typename T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
+    template <typename T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
+    // ---- CV_32F matrix expressions, as far as the matchers write them: -A.t()*b, A*b, A*b+c.  cv::MatExpr turns each of them into
+    // ONE gemm; for CV_32F cv::gemm accumulates the products in double and rounds alpha*sum + beta*c to float once
+    // (GEMMSingleMul<float, double>): the stand-in evaluates them the same way. ----
+    struct TExpr { const Mat* m; double alpha; };
+    struct MulExpr;
+    TExpr t() const { return TExpr{this, 1.0}; }
+    Mat(const MulExpr& e);
     Mat operator()(const Rect& r) const { Mat m = *this; m.data = data + (size_t)r.y * step + r.x; m.rows = r.height; m.cols = r.width; return m; }
     Mat clone() const {
-        Mat m(rows, cols, CV_8UC1);
-        for (int y = 0; y < rows; y++) std::memcpy(m.ptr(y), ptr(y), (size_t)cols);
+        Mat m(rows, cols, esz == 4 ? CV_32F : CV_8UC1);
+        for (int y = 0; y < rows; y++) std::memcpy(m.ptr(y), ptr(y), (size_t)cols * esz);
         return m;
     }
     void copyTo(Mat& o) const {
@@ -118,6 +131,24 @@ public:
 private:
     std::shared_ptr<uchar> buf_;
 };
+struct Mat::MulExpr { Mat a, b; double alpha; bool ta; };
+inline Mat::TExpr operator-(const Mat::TExpr& e) { return Mat::TExpr{e.m, -e.alpha}; }
+inline Mat::MulExpr operator*(const Mat::TExpr& e, const Mat& b) { return Mat::MulExpr{*e.m, b, e.alpha, true}; }
+inline Mat::MulExpr operator*(const Mat& a, const Mat& b) { return Mat::MulExpr{a, b, 1.0, false}; }
+inline Mat gemm_f32(const Mat::MulExpr& e, const Mat* c) {
+    const int M = e.ta ? e.a.cols : e.a.rows, K = e.ta ? e.a.rows : e.a.cols, N = e.b.cols;
+    assert(e.a.esz == 4 && e.b.esz == 4 && e.b.rows == K && (!c || (c->rows == M && c->cols == N && c->esz == 4)));
+    Mat d(M, N, CV_32F);
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < N; j++) {
+            double s = 0;
+            for (int k = 0; k < K; k++) s += (double)(e.ta ? e.a.at<float>(k, i) : e.a.at<float>(i, k)) * (double)e.b.at<float>(k, j);
+            d.at<float>(i, j) = c ? (float)(s * e.alpha + (double)c->at<float>(i, j) * 1.0) : (float)(s * e.alpha);
+        }
+    return d;
+}
+inline Mat::Mat(const MulExpr& e) : rows(0), cols(0), step(0), data(nullptr) { *this = gemm_f32(e, nullptr); }
+inline Mat operator+(const Mat::MulExpr& e, const Mat& c) { return gemm_f32(e, &c); }
 
 // InputArray / OutputArray: thin handles on a Mat
 class _InputArray {

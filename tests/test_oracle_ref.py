@@ -153,3 +153,41 @@ def test_search_by_projection_of_local_points_equals_the_reference_code(seed, n,
         assert np.array_equal(r[0], o[0]) and r[1] == o[1]
     if n >= 1000 and m >= 1000:
         assert o[1] > 200
+
+
+@pytest.mark.parametrize("seed,n,m,th,dz", [(11, 1000, 1000, 15.0, 0.0), (12, 1000, 1000, 30.0, 0.3), (13, 64, 900, 7.0, 0.0), (14, 1500, 0, 15.0, 0.0),
+                                            (15, 1200, 1100, 15.0, -0.3), (16, 900, 1000, 7.0, 0.05)])
+def test_search_by_projection_of_the_last_frame_equals_the_reference_code(seed, n, m, th, dz, oracle, synth):
+    """C3: the reference's own ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+    (ORBmatcher.cc:1710-1879: forward / backward / neutral octave windows, claims, the stereo test, the rotation histogram with
+    ComputeThreeMaxima), cut out of the reference source and compiled against stand-in Frame / MapPoint classes, against the oracle's
+    restatement.  dz moves the last camera along z: > b selects the forward window, < -b the backward one."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    kp, desc, ur = matchgen.rand_frame(rng, n, N)
+    ur[rng.random(n) < 0.3] = -1.0
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    K = synth.TUM1
+    keep = []
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = rng.normal(0, 0.05, 3)
+    fv = N.make_frame_view(kp, desc, ur, (rng.random(n) < 0.05).astype(np.int32), (0, 0, 640, 480), K, T[:3].reshape(-1), sf, keep)
+    src = rng.integers(0, n, m)
+    z = rng.uniform(0.5, 6, m).astype(np.float32)
+    z[: m // 50] *= -1                                             # some points behind the camera
+    X = np.stack([(kp["x"][src] + rng.normal(0, 4, m) - K["cx"]) * z / K["fx"], (kp["y"][src] + rng.normal(0, 4, m) - K["cy"]) * z / K["fy"], z], 1)
+    X[: m // 20, 0] += 50.0                                        # and some that project outside the image
+    X = (X - T[:3, 3]).astype(np.float32)
+    ldesc = desc[src].copy()
+    ldesc ^= np.packbits(rng.random((m, 256)) < 0.06, axis=1, bitorder="little")
+    Tl = np.eye(4, dtype=np.float32)
+    Tl[2, 3] = dz
+    lv = N.make_lastframe_view(rng.random(m) < 0.95, X, ldesc, kp["octave"][src], rng.uniform(0, 360, m), rng.random(m) < 0.6,
+                               Tl[:3].reshape(-1), keep)
+    for mono in (False, True):
+        for ori in (True, False):
+            r = pyref.search_last_frame(fv, lv, th, mono, ori)
+            o = oracle.search_last_frame(fv, lv, th, mono, ori)
+            assert np.array_equal(r[0], o[0]) and r[1] == o[1], (mono, ori)
+    if m:
+        assert o[1] > 20
