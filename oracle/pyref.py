@@ -1,5 +1,6 @@
 """ctypes binding of oracle/_ref/libplref.so: the REFERENCE'S OWN hot-path code (src/ORBextractor.cc as a whole, DescriptorDistance
-and ComputeThreeMaxima cut out of src/ORBmatcher.cc / src/LineMatcher.cpp, the vendored DBoW2 vocabulary), compiled from the sources
+and ComputeThreeMaxima cut out of src/ORBmatcher.cc / src/LineMatcher.cpp, the two tracking searches
+ORBmatcher::SearchByProjection (local map points, last frame) with the Frame grid functions they call, the vendored DBoW2 vocabulary), compiled from the sources
 where they lie under /root/reference against the OpenCV stand-in of oracle/ref_shim/cv_standin.hpp (see oracle/ref_shim/Makefile).
 
 TEST INFRASTRUCTURE: tests/test_oracle_ref.py checks the oracle's restatements against it.  The library can only be BUILT where

@@ -1,8 +1,9 @@
 """CPU tests (-m "not gpu"): the oracle's restatements against THE REFERENCE'S OWN CODE, compiled from /root/reference into
 oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whole, DescriptorDistance / ComputeThreeMaxima cut out of
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
-are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, the rotation-histogram rule of C3 / C6 / C7 and G to reference
-code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
+frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), the rotation-histogram rule of C6 / C7 and G to
+reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
