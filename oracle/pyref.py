@@ -1,6 +1,7 @@
 """ctypes binding of oracle/_ref/libplref.so: the REFERENCE'S OWN hot-path code (src/ORBextractor.cc as a whole, DescriptorDistance
 and ComputeThreeMaxima cut out of src/ORBmatcher.cc / src/LineMatcher.cpp, the two tracking searches
-ORBmatcher::SearchByProjection (local map points, last frame) with the Frame grid functions they call, the vendored DBoW2 vocabulary), compiled from the sources
+ORBmatcher::SearchByProjection (local map points, last frame) with the Frame grid functions they call, both ORBmatcher::SearchByBoW
+overloads, the vendored DBoW2 vocabulary), compiled from the sources
 where they lie under /root/reference against the OpenCV stand-in of oracle/ref_shim/cv_standin.hpp (see oracle/ref_shim/Makefile).
 
 TEST INFRASTRUCTURE: tests/test_oracle_ref.py checks the oracle's restatements against it.  The library can only be BUILT where
@@ -137,3 +138,14 @@ def search_last_frame(cur_view, last_view, th, mono=False, check_orientation=Tru
     lib().ref_orb_search_last_frame(C.byref(cur_view), C.byref(last_view), C.c_float(th), C.c_int(int(mono)), C.c_int(int(check_orientation)),
                                     _p(match), C.byref(n))
     return match[:cur_view.n], n.value
+
+
+def search_bow(a_view, b_view, mode, nn_ratio, check_orientation=True):
+    """C6 / C7 through the reference's own ORBmatcher::SearchByBoW overloads (ORBmatcher.cc:247-407 mode 0: key frame A, frame B;
+    :729-880 mode 1: key frames A, B) -> (match vector, nmatches), as pyoracle.search_bow."""
+    sz = b_view.n if mode == 0 else a_view.n
+    match = np.empty(max(sz, 1), np.int32)
+    n = C.c_int(0)
+    lib().ref_orb_search_bow(C.byref(a_view), C.byref(b_view), C.c_int(mode), C.c_float(nn_ratio), C.c_int(int(check_orientation)), _p(match),
+                             C.byref(n))
+    return match[:sz], n.value

@@ -2,8 +2,8 @@
 oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whole, DescriptorDistance / ComputeThreeMaxima cut out of
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
-frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), the rotation-histogram rule of C6 / C7 and G to
-reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C6 and C7 (both ORBmatcher::SearchByBoW overloads) and G
+to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -192,3 +192,22 @@ def test_search_by_projection_of_the_last_frame_equals_the_reference_code(seed, 
             assert np.array_equal(r[0], o[0]) and r[1] == o[1], (mono, ori)
     if m:
         assert o[1] > 20
+
+
+@pytest.mark.parametrize("seed,nA,nB,nodes,mode", [(21, 1000, 1000, 100, 0), (22, 1000, 1000, 100, 1), (23, 300, 1500, 40, 0), (24, 1500, 300, 40, 1),
+                                                   (25, 0, 500, 10, 0), (26, 500, 0, 10, 1), (27, 2000, 2000, 400, 0), (28, 2000, 2000, 400, 1)])
+def test_search_by_bow_equals_the_reference_code(seed, nA, nB, nodes, mode, oracle):
+    """C6 / C7: the reference's own ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) and SearchByBoW(KeyFrame*, KeyFrame*, ...)
+    (ORBmatcher.cc:247-407, :729-880), cut out of the reference source and compiled against stand-in KeyFrame / Frame classes that
+    hold real DBoW2::FeatureVector maps, against the oracle's restatement over the flattened vectors: nodes present on one side only
+    (the lower_bound jumps), invalid map points, several features of one node competing, ratio and rotation tests."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    a, b, keep = matchgen.bow_case(rng, nA, nB, nodes, N, mode)
+    for nn in (0.7, 0.9):
+        for ori in (True, False):
+            r = pyref.search_bow(a, b, mode, nn, ori)
+            o = oracle.search_bow(a, b, mode, nn, ori)
+            assert np.array_equal(r[0], o[0]) and r[1] == o[1], (nn, ori)
+    if nA >= 1000 and nB >= 1000:
+        assert o[1] > 50
