@@ -149,3 +149,14 @@ def search_bow(a_view, b_view, mode, nn_ratio, check_orientation=True):
     lib().ref_orb_search_bow(C.byref(a_view), C.byref(b_view), C.c_int(mode), C.c_float(nn_ratio), C.c_int(int(check_orientation)), _p(match),
                              C.byref(n))
     return match[:sz], n.value
+
+
+def search_keyframe_points(cur_view, pt_view, log_sf, th, orb_dist, check_orientation=True):
+    """C4 through the reference's own ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist)
+    (ORBmatcher.cc:1891-2024, with MapPoint::PredictScale of MapPoint.cc; Ow comes from the frame's pose inside the function) ->
+    (match_of_feature, nmatches), as pyoracle.search_keyframe_points."""
+    match = np.empty(max(cur_view.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().ref_orb_search_keyframe_points(C.byref(cur_view), C.byref(pt_view), C.c_float(log_sf), C.c_float(th), C.c_int(int(orb_dist)),
+                                         C.c_int(int(check_orientation)), _p(match), C.byref(n))
+    return match[:cur_view.n], n.value

@@ -149,6 +149,21 @@ inline Mat gemm_f32(const Mat::MulExpr& e, const Mat* c) {
 }
 inline Mat::Mat(const MulExpr& e) : rows(0), cols(0), step(0), data(nullptr) { *this = gemm_f32(e, nullptr); }
 inline Mat operator+(const Mat::MulExpr& e, const Mat& c) { return gemm_f32(e, &c); }
+// a - b of two CV_32F matrices (element-wise float subtraction) and cv::norm (L2) of a CV_32F matrix: products accumulated in double
+inline Mat operator-(const Mat& a, const Mat& b) {
+    assert(a.esz == 4 && b.esz == 4 && a.rows == b.rows && a.cols == b.cols);
+    Mat d(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < a.cols; j++) d.at<float>(i, j) = a.at<float>(i, j) - b.at<float>(i, j);
+    return d;
+}
+inline double norm(const Mat& a) {
+    assert(a.esz == 4);
+    double s = 0;
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < a.cols; j++) s += (double)a.at<float>(i, j) * (double)a.at<float>(i, j);
+    return std::sqrt(s);
+}
 
 // InputArray / OutputArray: thin handles on a Mat
 class _InputArray {

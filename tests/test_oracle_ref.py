@@ -2,8 +2,8 @@
 oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whole, DescriptorDistance / ComputeThreeMaxima cut out of
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
-frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C6 and C7 (both ORBmatcher::SearchByBoW overloads) and G
-to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 (the relocalisation search with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads)
+and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -210,4 +210,22 @@ def test_search_by_bow_equals_the_reference_code(seed, nA, nB, nodes, mode, orac
             o = oracle.search_bow(a, b, mode, nn, ori)
             assert np.array_equal(r[0], o[0]) and r[1] == o[1], (nn, ori)
     if nA >= 1000 and nB >= 1000:
+        assert o[1] > 50
+
+
+@pytest.mark.parametrize("seed,n,m,th,orb_dist", [(31, 1200, 900, 10.0, 100), (32, 1200, 900, 3.0, 64), (33, 200, 1500, 10.0, 100), (34, 1000, 0, 10.0, 100),
+                                                  (35, 1500, 2000, 5.0, 80)])
+def test_search_by_projection_for_relocalisation_equals_the_reference_code(seed, n, m, th, orb_dist, oracle, synth):
+    """C4: the reference's own ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist)
+    (ORBmatcher.cc:1891-2024) with MapPoint::PredictScale (MapPoint.cc), cut out of the reference sources: camera centre from the
+    pose, the scale-invariance range, the predicted octave window, claimed features, the rotation histogram."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    fv, pv, ow, log_sf, keep = matchgen.pose_case(rng, n, m, N, synth.TUM1, sf, 2)
+    for ori in (True, False):
+        r = pyref.search_keyframe_points(fv, pv, log_sf, th, orb_dist, ori)
+        o = oracle.search_keyframe_points(fv, pv, ow, log_sf, th, orb_dist, ori)
+        assert np.array_equal(r[0], o[0]) and r[1] == o[1], ori
+    if n >= 1000 and m >= 900:
         assert o[1] > 50
