@@ -160,3 +160,15 @@ def search_keyframe_points(cur_view, pt_view, log_sf, th, orb_dist, check_orient
     lib().ref_orb_search_keyframe_points(C.byref(cur_view), C.byref(pt_view), C.c_float(log_sf), C.c_float(th), C.c_int(int(orb_dist)),
                                          C.c_int(int(check_orientation)), _p(match), C.byref(n))
     return match[:cur_view.n], n.value
+
+
+def search_sim3_points(kf_view, pt_view, log_sf, th):
+    """C5 through the reference's own ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th)
+    (ORBmatcher.cc:423-554, with KeyFrame::GetFeaturesInArea / IsInImage and MapPoint::PredictScale(dist, KeyFrame*)); the view's pose
+    is Scw.  -> (match_of_feature, nmatches, tcw (12,) and ow (3,) after the function's own division by the scale, ORBmatcher.cc:435-439:
+    what pyoracle.search_sim3_points / the C ABI take)."""
+    match = np.empty(max(kf_view.n, 1), np.int32)
+    n = C.c_int(0)
+    tcw, ow = np.zeros(12, np.float32), np.zeros(3, np.float32)
+    lib().ref_orb_search_sim3_points(C.byref(kf_view), C.byref(pt_view), C.c_float(log_sf), C.c_int(int(th)), _p(match), C.byref(n), _p(tcw), _p(ow))
+    return match[:kf_view.n], n.value, tcw, ow

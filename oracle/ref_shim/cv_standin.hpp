@@ -108,6 +108,7 @@ public:
     Mat row(int r) const { return rowRange(r, r + 1); }
     Mat colRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * esz; m.cols = b - a; return m; }
     Mat col(int c) const { return colRange(c, c + 1); }
+    double dot(const Mat& o) const;
     // single-index access of a vector (3x1 or 1x3)
     template <typename T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
     template <typename T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
@@ -157,6 +158,23 @@ inline Mat operator-(const Mat& a, const Mat& b) {
         for (int j = 0; j < a.cols; j++) d.at<float>(i, j) = a.at<float>(i, j) - b.at<float>(i, j);
     return d;
 }
+// A / s of a CV_32F matrix (cv::MatExpr: a scaled copy, the scale 1 / s applied in float) and Mat::dot (products accumulated in double)
+inline Mat operator/(const Mat& a, double s) {
+    assert(a.esz == 4);
+    const float alpha = (float)(1.0 / s);
+    Mat d(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < a.cols; j++) d.at<float>(i, j) = a.at<float>(i, j) * alpha;
+    return d;
+}
+inline double dot_f32(const Mat& a, const Mat& b) {
+    assert(a.esz == 4 && b.esz == 4 && a.rows * a.cols == b.rows * b.cols);
+    double s = 0;
+    const int n = a.rows * a.cols;
+    for (int i = 0; i < n; i++) s += (double)a.at<float>(i / a.cols, i % a.cols) * (double)b.at<float>(i / b.cols, i % b.cols);
+    return s;
+}
+inline double Mat::dot(const Mat& o) const { return dot_f32(*this, o); }
 inline double norm(const Mat& a) {
     assert(a.esz == 4);
     double s = 0;

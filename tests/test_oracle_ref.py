@@ -2,7 +2,7 @@
 oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whole, DescriptorDistance / ComputeThreeMaxima cut out of
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
-frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 (the relocalisation search with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads)
+frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads)
 and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
@@ -227,5 +227,31 @@ def test_search_by_projection_for_relocalisation_equals_the_reference_code(seed,
         r = pyref.search_keyframe_points(fv, pv, log_sf, th, orb_dist, ori)
         o = oracle.search_keyframe_points(fv, pv, ow, log_sf, th, orb_dist, ori)
         assert np.array_equal(r[0], o[0]) and r[1] == o[1], ori
+    if n >= 1000 and m >= 900:
+        assert o[1] > 50
+
+
+@pytest.mark.parametrize("seed,n,m,th,scale", [(41, 1200, 900, 10, 1.0), (42, 1200, 900, 3, 1.0), (43, 200, 1500, 10, 1.0), (44, 1000, 0, 10, 1.0),
+                                               (45, 1500, 2000, 5, 1.0), (46, 1200, 900, 10, 1.7)])
+def test_search_by_projection_with_a_sim3_equals_the_reference_code(seed, n, m, th, scale, oracle, synth):
+    """C5: the reference's own ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th)
+    (ORBmatcher.cc:423-554) with KeyFrame::GetFeaturesInArea / IsInImage (KeyFrame.cc) and MapPoint::PredictScale(dist, KeyFrame*),
+    cut out of the reference sources.  The reference divides the scale out of Scw itself; the oracle (like the C ABI) takes the pose
+    after that division, so it is fed the pose the reference-side call reports.  scale != 1: Scw = s [R | t]."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    fv, pv, ow, log_sf, keep = matchgen.pose_case(rng, n, m, N, synth.TUM1, sf, 3)
+    if scale != 1.0:
+        for k in range(12):
+            fv.tcw[k] = np.float32(fv.tcw[k] * np.float32(scale))
+    r = pyref.search_sim3_points(fv, pv, log_sf, th)
+    fv2 = type(fv).from_buffer_copy(fv)
+    for k in range(12):
+        fv2.tcw[k] = float(r[2][k])
+    o = oracle.search_sim3_points(fv2, pv, r[3], log_sf, th)
+    assert np.array_equal(r[0], o[0]) and r[1] == o[1]
+    if scale == 1.0:
+        assert np.allclose(r[2], np.array(list(fv.tcw), np.float32), atol=1e-6) and np.allclose(r[3], ow, atol=1e-6)
     if n >= 1000 and m >= 900:
         assert o[1] > 50
