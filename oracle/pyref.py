@@ -172,3 +172,13 @@ def search_sim3_points(kf_view, pt_view, log_sf, th):
     tcw, ow = np.zeros(12, np.float32), np.zeros(3, np.float32)
     lib().ref_orb_search_sim3_points(C.byref(kf_view), C.byref(pt_view), C.c_float(log_sf), C.c_int(int(th)), _p(match), C.byref(n), _p(tcw), _p(ow))
     return match[:kf_view.n], n.value, tcw, ow
+
+
+def line_search_by_projection(cur_view, line_view):
+    """D3 through the reference's own LineMatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame)
+    (LineMatcher.cpp:72-270, with LiangBarsky, UpdateKeyLineData, LineMatching, LineOverLap, ReprojectionError; Eigen and
+    cv::LineIterator through stand-ins) -> (match_of_line -> index of the last frame's line or -1, nmatches)."""
+    match = np.empty(max(cur_view.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().ref_line_search_by_projection(C.byref(cur_view), C.byref(line_view), _p(match), C.byref(n))
+    return match[:cur_view.n], n.value

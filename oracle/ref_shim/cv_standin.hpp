@@ -109,6 +109,14 @@ public:
     Mat colRange(int a, int b) const { Mat m = *this; m.data = data + (size_t)a * esz; m.cols = b - a; return m; }
     Mat col(int c) const { return colRange(c, c + 1); }
     double dot(const Mat& o) const;
+    // cv::Mat::push_back(row) of an 8-bit matrix (LineMatcher collects the descriptors of the projected lines that way)
+    void push_back(const Mat& r) {
+        assert(esz == 1 && r.esz == 1 && (rows == 0 || cols == r.cols));
+        Mat m(rows + r.rows, r.cols, CV_8UC1);
+        for (int y = 0; y < rows; y++) std::memcpy(m.ptr(y), ptr(y), (size_t)cols);
+        for (int y = 0; y < r.rows; y++) std::memcpy(m.ptr(rows + y), r.ptr(y), (size_t)r.cols);
+        *this = m;
+    }
     // single-index access of a vector (3x1 or 1x3)
     template <typename T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
     template <typename T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
@@ -232,6 +240,23 @@ inline void FAST(const Mat& img, std::vector<KeyPoint>& kps, int threshold, bool
     kps.clear();
     for (int i = 0; i < n; i++) kps.push_back(KeyPoint(xs[i], ys[i], 7.f, -1.f, rs[i]));
 }
+// cv::line_descriptor::KeyLine (opencv_contrib): the field order of pl_keyline
+namespace line_descriptor {
+struct KeyLine {
+    float angle;
+    int class_id, octave;
+    Point2f pt;
+    float response, size, startPointX, startPointY, endPointX, endPointY, sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY,
+        lineLength;
+    int numOfPixels;
+};
+}  // namespace line_descriptor
+// cv::LineIterator(img, pt1, pt2).count (8-connected, clipped to the image): the oracle's cv2-pinned restatement
+class LineIterator {
+public:
+    int count;
+    LineIterator(const Mat& img, Point2f a, Point2f b) : count(orc_line_iterator_count(a.x, a.y, b.x, b.y, img.cols, img.rows)) {}
+};
 // cv::FileStorage: DBoW2's YAML save / load (virtual members of the vocabulary template, so they must compile; never called —
 // the vocabulary is loaded with the reference's own loadFromTextFile)
 class FileNode {

@@ -255,3 +255,49 @@ def test_search_by_projection_with_a_sim3_equals_the_reference_code(seed, n, m, 
         assert np.allclose(r[2], np.array(list(fv.tcw), np.float32), atol=1e-6) and np.allclose(r[3], ow, atol=1e-6)
     if n >= 1000 and m >= 900:
         assert o[1] > 50
+
+
+def test_line_search_by_projection_equals_the_reference_code(oracle, synth, capfd):
+    """D3 (and with it the predicate D2): the reference's own LineMatcher::SearchByProjection(Frame& CurrentFrame, const Frame&
+    LastFrame) (LineMatcher.cpp:72-270) with LiangBarsky (incl. its round() and its horizontal-line test), UpdateKeyLineData,
+    LineMatching, LineOverLap and ReprojectionError, cut out of the reference source, against the oracle's restatement: consecutive
+    frames of the room sequence (real LSD / LBD features lifted with depth), with claimed lines, with a pose that puts lines behind
+    the camera and across the image border, and with so few matches that the relaxed second pass runs."""
+    fe = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200.frontend")
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    gray, depth, T = synth.room_sequence(6, 640, 480, workers=4)
+    ob = oracle.OracleBackend(1000)
+    lines = ob.extract_lines(gray)
+    orb = [(np.zeros(0, N.KP_DTYPE), np.zeros((0, 32), np.uint8))] * len(gray)
+    frames = fe.FrameLite.build_batch(orb, depth, [np.asarray(t, np.float32) for t in T], synth.TUM1, ob.scale_factors())
+    fe.FrameLite.attach_lines_batch(frames, lines, depth)
+    rng = np.random.default_rng(5)
+    total = relaxed = 0
+    for t in range(1, len(frames)):
+        F, last = frames[t], frames[t - 1]
+        s3, e3, okl = last.unproject_lines()
+        for variant in range(4):
+            keep = []
+            tcw = F.Tcw.copy()
+            claimed = None
+            ldesc = last.ldesc
+            if variant == 1:
+                claimed = (rng.random(len(F.kls)) < 0.3).astype(np.uint8)
+            elif variant == 2:      # turned and pushed forward: lines behind the camera, lines cut by the border
+                a = 0.6
+                R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+                tcw[:3, :3] = R @ tcw[:3, :3]
+                tcw[:3, 3] = R @ tcw[:3, 3] + np.array([0.3, 0.0, -2.5], np.float32)
+            elif variant == 3:      # descriptors of the last frame mostly destroyed: fewer than 20 % match, the relaxed pass runs
+                ldesc = last.ldesc.copy()
+                bad = rng.random(len(ldesc)) < 0.9
+                ldesc[bad] = rng.integers(0, 256, (int(bad.sum()), 32), dtype=np.uint8)
+            cv_ = N.make_lineframe_view(F.kls, F.ldesc, claimed, tcw[:3].reshape(-1), synth.TUM1, F.bounds, F.size, keep)
+            lv = N.make_mapline_view(s3, e3, last.kls, ldesc, okl, keep)
+            r = pyref.line_search_by_projection(cv_, lv)
+            o = oracle.line_search_by_projection(cv_, lv)
+            assert np.array_equal(r[0], o[0]) and r[1] == o[1], (t, variant)
+            total += o[1]
+            relaxed += o[2]
+    capfd.readouterr()   # (the reference function prints its timing)
+    assert total > 200 and relaxed >= 3
