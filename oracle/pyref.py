@@ -1,7 +1,8 @@
 """ctypes binding of oracle/_ref/libplref.so: the REFERENCE'S OWN hot-path code (src/ORBextractor.cc as a whole, DescriptorDistance
 and ComputeThreeMaxima cut out of src/ORBmatcher.cc / src/LineMatcher.cpp, the two tracking searches
 ORBmatcher::SearchByProjection (local map points, last frame) with the Frame grid functions they call, both ORBmatcher::SearchByBoW
-overloads, the vendored DBoW2 vocabulary), compiled from the sources
+overloads, the relocalisation and Sim3 searches, LineMatcher::SearchByProjection (last frame, local map) with LineMatching and
+LiangBarsky, the vendored DBoW2 vocabulary), compiled from the sources
 where they lie under /root/reference against the OpenCV stand-in of oracle/ref_shim/cv_standin.hpp (see oracle/ref_shim/Makefile).
 
 TEST INFRASTRUCTURE: tests/test_oracle_ref.py checks the oracle's restatements against it.  The library can only be BUILT where
@@ -174,11 +175,12 @@ def search_sim3_points(kf_view, pt_view, log_sf, th):
     return match[:kf_view.n], n.value, tcw, ow
 
 
-def line_search_by_projection(cur_view, line_view):
+def line_search_by_projection(cur_view, line_view, local_map=False):
     """D3 through the reference's own LineMatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame)
     (LineMatcher.cpp:72-270, with LiangBarsky, UpdateKeyLineData, LineMatching, LineOverLap, ReprojectionError; Eigen and
-    cv::LineIterator through stand-ins) -> (match_of_line -> index of the last frame's line or -1, nmatches)."""
+    cv::LineIterator through stand-ins); local_map: D5, SearchByProjection(Frame& F, const vector<MapLine*>& vpMapLines) (:755-952)
+    -> (match_of_line -> index of the last frame's / the map's line or -1, nmatches)."""
     match = np.empty(max(cur_view.n, 1), np.int32)
     n = C.c_int(0)
-    lib().ref_line_search_by_projection(C.byref(cur_view), C.byref(line_view), _p(match), C.byref(n))
+    lib().ref_line_search_by_projection(C.byref(cur_view), C.byref(line_view), C.c_int(int(local_map)), _p(match), C.byref(n))
     return match[:cur_view.n], n.value
