@@ -182,5 +182,5 @@ def line_search_by_projection(cur_view, line_view, local_map=False):
     -> (match_of_line -> index of the last frame's / the map's line or -1, nmatches)."""
     match = np.empty(max(cur_view.n, 1), np.int32)
     n = C.c_int(0)
-    lib().ref_line_search_by_projection(C.byref(cur_view), C.byref(line_view), C.c_int(int(local_map)), _p(match), C.byref(n))
+    lib().ref_line_search_by_projection(C.byref(cur_view), C.byref(line_view), C.c_int(int(local_map)), _p(match), C.byref(n))   # local_map: 0 = D3, 1 = D5, 2 = D4 (the key-frame overload, :527-753)
     return match[:cur_view.n], n.value

@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 / D3 / D5 (LineMatcher::SearchByProjection for the last frame and for the local map, LineMatching, LiangBarsky) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -258,7 +258,7 @@ def test_search_by_projection_with_a_sim3_equals_the_reference_code(seed, n, m, 
 
 
 def test_line_search_by_projection_equals_the_reference_code(oracle, synth, capfd):
-    """D3 and D5 (and with them the predicate D2): the reference's own LineMatcher::SearchByProjection(Frame& CurrentFrame, const Frame&
+    """D3, D4 and D5 (and with them the predicate D2): the reference's own LineMatcher::SearchByProjection(Frame& CurrentFrame, const Frame&
     LastFrame) (LineMatcher.cpp:72-270) with LiangBarsky (incl. its round() and its horizontal-line test), UpdateKeyLineData,
     LineMatching, LineOverLap and ReprojectionError, cut out of the reference source, against the oracle's restatement: consecutive
     frames of the room sequence (real LSD / LBD features lifted with depth), with claimed lines, with a pose that puts lines behind
@@ -299,6 +299,9 @@ def test_line_search_by_projection_equals_the_reference_code(oracle, synth, capf
             assert np.array_equal(r[0], o[0]) and r[1] == o[1], (t, variant)
             total += o[1]
             relaxed += o[2]
+            # D4: the last frame as a reference key frame (LineMatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* RefFrame), :527-753)
+            r4 = pyref.line_search_by_projection(cv_, lv, local_map=2)
+            assert np.array_equal(r4[0], o[0]) and r4[1] == o[1], (t, variant, "D4")
             # D5: the same lines as a local map (LineMatcher::SearchByProjection(Frame& F, const vector<MapLine*>&), :755-952): every
             # projection starts from a fresh KeyLine, the lines in view are those with depth at both ends
             lv5 = N.make_mapline_view(s3, e3, np.zeros(len(last.kls), N.KL_DTYPE), ldesc, okl, keep)
