@@ -184,3 +184,23 @@ def line_search_by_projection(cur_view, line_view, local_map=False):
     n = C.c_int(0)
     lib().ref_line_search_by_projection(C.byref(cur_view), C.byref(line_view), C.c_int(int(local_map)), _p(match), C.byref(n))   # local_map: 0 = D3, 1 = D5, 2 = D4 (the key-frame overload, :527-753)
     return match[:cur_view.n], n.value
+
+
+def frame_is_in_frustum_batch(tcw, ow, K, bounds, n_levels, log_sf, world_pos, normal, min_inv, max_inv, max_raw, cos_limit=0.5):
+    """F4 through the reference's own Frame::IsInFrustum(MapPoint*, viewingCosLimit) (Frame.cc:345-401) for n frames x m map points ->
+    (in_view, proj_x, proj_y, proj_xr, level, view_cos), as pyoracle.frame_is_in_frustum_batch (fields of points not in view are 0)."""
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(-1, 12)
+    ow = np.ascontiguousarray(ow, np.float32).reshape(-1, 3)
+    wp = np.ascontiguousarray(world_pos, np.float32).reshape(-1, 3)
+    no = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    mi, ma, mr = (np.ascontiguousarray(a, np.float32) for a in (min_inv, max_inv, max_raw))
+    n, m = len(tcw), len(wp)
+    b = np.asarray(bounds, np.float32)
+    iv = np.zeros((n, m), np.uint8)
+    px, py, pxr, vc = (np.zeros((n, m), np.float32) for _ in range(4))
+    lv = np.zeros((n, m), np.int32)
+    for i in range(n):
+        lib().ref_frame_is_in_frustum(_p(tcw[i]), _p(ow[i]), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]), C.c_float(K["cy"]),
+                                      C.c_float(K["bf"]), _p(b), C.c_int(n_levels), C.c_float(log_sf), C.c_int(m), _p(wp), _p(no), _p(mi), _p(ma), _p(mr),
+                                      C.c_float(cos_limit), _p(iv[i]), _p(px[i]), _p(py[i]), _p(pxr[i]), _p(lv[i]), _p(vc[i]))
+    return iv, px, py, pxr, lv, vc

@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), F4 (Frame::IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -310,3 +310,23 @@ def test_line_search_by_projection_equals_the_reference_code(oracle, synth, capf
             assert np.array_equal(r5[0], o5[0]) and r5[1] == o5[1], (t, variant, "D5")
     capfd.readouterr()   # (the reference function prints its timing)
     assert total > 200 and relaxed >= 3
+
+
+@pytest.mark.parametrize("seed,n_frames,m", [(51, 5, 4000), (52, 1, 300), (53, 3, 0), (54, 8, 2500)])
+def test_is_in_frustum_equals_the_reference_code(seed, n_frames, m, oracle, synth):
+    """F4: the reference's own Frame::IsInFrustum(MapPoint*, viewingCosLimit) (Frame.cc:345-401, with MapPoint::PredictScale), cut out
+    of the reference source, against the oracle's batched restatement: which map points are in view and, for those, the projection,
+    the right-image coordinate, the predicted level and the viewing cosine — bit for bit."""
+    rng = np.random.default_rng(seed)
+    K = synth.TUM1
+    tcw, ow, Xw, normal, mi, ma, mr = matchgen.frustum_case(rng, n_frames, m, K)
+    log_sf = float(np.float32(np.log(np.float32(1.2))))
+    for cos_limit in (0.5, 0.8):
+        r = pyref.frame_is_in_frustum_batch(tcw, ow, K, (0, 0, 640, 480), 8, log_sf, Xw, normal, mi, ma, mr, cos_limit)
+        o = oracle.frame_is_in_frustum_batch(tcw, ow, K, (0, 0, 640, 480), 8, log_sf, Xw, normal, mi, ma, mr, cos_limit)
+        assert np.array_equal(r[0], o[0])
+        v = o[0] != 0
+        for a, b in zip(r[1:], o[1:]):
+            assert np.array_equal(a[v], b[v])
+    if m >= 2500:
+        assert 0.05 < v.mean() < 0.95
