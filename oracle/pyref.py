@@ -204,3 +204,26 @@ def frame_is_in_frustum_batch(tcw, ow, K, bounds, n_levels, log_sf, world_pos, n
                                       C.c_float(K["bf"]), _p(b), C.c_int(n_levels), C.c_float(log_sf), C.c_int(m), _p(wp), _p(no), _p(mi), _p(ma), _p(mr),
                                       C.c_float(cos_limit), _p(iv[i]), _p(px[i]), _p(py[i]), _p(pxr[i]), _p(lv[i]), _p(vc[i]))
     return iv, px, py, pxr, lv, vc
+
+
+def frame_stereo_from_rgbd(depth, xy, x_un, bf):
+    """F2 through the reference's own Frame::ComputeStereoFromRGBD (Frame.cc:1065-1117), one frame: depth (rows, cols) float32,
+    xy = the raw key points, x_un = mvKeysUn[i].pt.x -> (mvDepth, mvuRight)."""
+    depth = np.ascontiguousarray(depth, np.float32)
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    xu = np.ascontiguousarray(x_un, np.float32)
+    d, ur = np.empty(max(len(xu), 1), np.float32), np.empty(max(len(xu), 1), np.float32)
+    lib().ref_frame_stereo_from_rgbd(_p(depth), C.c_int(depth.shape[0]), C.c_int(depth.shape[1]), C.c_int(len(xu)), _p(xy), _p(xu), C.c_float(bf), _p(d), _p(ur))
+    return d[:len(xu)], ur[:len(xu)]
+
+
+def frame_unproject(xy_un, z, rwc, ow, K):
+    """F3 through the reference's own Frame::UnprojectStereo (Frame.cc:1120-1134), one frame -> (world (n, 3), valid)."""
+    xy = np.ascontiguousarray(xy_un, np.float32).reshape(-1, 2)
+    z = np.ascontiguousarray(z, np.float32)
+    r = np.ascontiguousarray(rwc, np.float32).reshape(9)
+    o = np.ascontiguousarray(ow, np.float32).reshape(3)
+    w, v = np.empty((max(len(z), 1), 3), np.float32), np.empty(max(len(z), 1), np.uint8)
+    lib().ref_frame_unproject(C.c_int(len(z)), _p(xy), _p(z), _p(r), _p(o), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]), C.c_float(K["cy"]),
+                              _p(w), _p(v))
+    return w[:len(z)], v[:len(z)]

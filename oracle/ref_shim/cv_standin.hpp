@@ -158,6 +158,24 @@ inline Mat gemm_f32(const Mat::MulExpr& e, const Mat* c) {
 }
 inline Mat::Mat(const MulExpr& e) : rows(0), cols(0), step(0), data(nullptr) { *this = gemm_f32(e, nullptr); }
 inline Mat operator+(const Mat::MulExpr& e, const Mat& c) { return gemm_f32(e, &c); }
+// cv::Mat_<float>(r, c) << a, b, c: the comma initialiser
+template <typename T>
+struct Mat_ : Mat {
+    Mat_(int r, int c) : Mat(r, c, CV_32F) {}
+};
+template <typename T>
+struct MatCommaInit {
+    Mat m;
+    int idx;
+    MatCommaInit& operator,(T v) { m.at<T>(idx / m.cols, idx % m.cols) = v; idx++; return *this; }
+    operator Mat() const { return m; }
+};
+template <typename T>
+inline MatCommaInit<T> operator<<(const Mat_<T>& m, T v) {
+    MatCommaInit<T> ci{m, 0};
+    ci, v;
+    return ci;
+}
 // a - b of two CV_32F matrices (element-wise float subtraction) and cv::norm (L2) of a CV_32F matrix: products accumulated in double
 inline Mat operator-(const Mat& a, const Mat& b) {
     assert(a.esz == 4 && b.esz == 4 && a.rows == b.rows && a.cols == b.cols);

@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), F4 (Frame::IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -330,3 +330,31 @@ def test_is_in_frustum_equals_the_reference_code(seed, n_frames, m, oracle, synt
             assert np.array_equal(a[v], b[v])
     if m >= 2500:
         assert 0.05 < v.mean() < 0.95
+
+
+def test_stereo_from_rgbd_and_unproject_equal_the_reference_code(oracle, synth):
+    """F2 / F3: the reference's own Frame::ComputeStereoFromRGBD (Frame.cc:1065-1117) and Frame::UnprojectStereo (:1120-1134), cut out of
+    the reference source, against the oracle's batched restatements: depth at the truncated key-point position, the right-image
+    coordinate, and the lifted world point (mRwc * x3Dc + mOw as ONE gemm) — bit for bit."""
+    K = synth.TUM1
+    rng = np.random.default_rng(61)
+    nf, rows, cols = 4, 480, 640
+    depth = rng.uniform(0.3, 6, (nf, rows, cols)).astype(np.float32)
+    depth[rng.random(depth.shape) < 0.2] = 0
+    counts = [1000, 0, 700, 1]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    xy = np.stack([rng.uniform(0, cols - 0.01, off[-1]), rng.uniform(0, rows - 0.01, off[-1])], 1).astype(np.float32)
+    xun = (xy[:, 0] + rng.normal(0, 0.3, off[-1])).astype(np.float32)
+    d, ur = oracle.frame_stereo_from_rgbd_batch(depth, off, xy, xun, K["bf"])
+    T = np.stack([matchgen._pose(rng) for _ in range(nf)])
+    rwc = np.stack([t[:3, :3].T for t in T]).astype(np.float32)
+    ow = np.stack([matchgen._centre(t) for t in T])
+    xyu = np.stack([xun, xy[:, 1]], 1)
+    w, v = oracle.frame_unproject_batch(off, xyu, d, rwc, ow, K)
+    assert 0.5 < v.mean() < 0.95
+    for f in range(nf):
+        a, b = off[f], off[f + 1]
+        rd, rur = pyref.frame_stereo_from_rgbd(depth[f], xy[a:b], xun[a:b], K["bf"])
+        assert np.array_equal(rd, d[a:b]) and np.array_equal(rur, ur[a:b])
+        rw, rv = pyref.frame_unproject(xyu[a:b], d[a:b], rwc[f], ow[f], K)
+        assert np.array_equal(rv, v[a:b]) and np.array_equal(rw[rv != 0], w[a:b][rv != 0])
