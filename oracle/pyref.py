@@ -227,3 +227,14 @@ def frame_unproject(xy_un, z, rwc, ow, K):
     lib().ref_frame_unproject(C.c_int(len(z)), _p(xy), _p(z), _p(r), _p(o), C.c_float(K["fx"]), C.c_float(K["fy"]), C.c_float(K["cx"]), C.c_float(K["cy"]),
                               _p(w), _p(v))
     return w[:len(z)], v[:len(z)]
+
+
+def search_for_initialization(f1, f2, prev_matched, window_size, nn_ratio=0.9, check_orientation=True):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:573-717) through the reference's own function -> (vnMatches12, nmatches,
+    vbPrevMatched after the call), as pyoracle.search_for_initialization."""
+    pm = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m = np.empty(max(f1.n, 1), np.int32)
+    n = C.c_int(0)
+    lib().ref_orb_search_for_initialization(C.byref(f1), C.byref(f2), _p(pm), C.c_int(int(window_size)), C.c_float(nn_ratio),
+                                            C.c_int(int(check_orientation)), _p(m), C.byref(n))
+    return m[:f1.n], n.value, pm

@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -358,3 +358,20 @@ def test_stereo_from_rgbd_and_unproject_equal_the_reference_code(oracle, synth):
         assert np.array_equal(rd, d[a:b]) and np.array_equal(rur, ur[a:b])
         rw, rv = pyref.frame_unproject(xyu[a:b], d[a:b], rwc[f], ow[f], K)
         assert np.array_equal(rv, v[a:b]) and np.array_equal(rw[rv != 0], w[a:b][rv != 0])
+
+
+@pytest.mark.parametrize("seed,n1,n2,win", [(71, 1500, 1500, 100), (72, 1500, 1800, 30), (73, 400, 50, 100), (74, 0, 300, 100), (75, 300, 0, 100)])
+def test_search_for_initialization_equals_the_reference_code(seed, n1, n2, win, oracle, synth):
+    """E: the reference's own ORBmatcher::SearchForInitialization (ORBmatcher.cc:573-717), cut out of the reference source: level-0
+    features only, the one-to-one bookkeeping (a later, better match takes a feature of F2 away from an earlier one), ratio and
+    rotation tests, the update of vbPrevMatched."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    f1, f2, prev, keep = matchgen.init_case(rng, n1, n2, N, synth.TUM1, sf)
+    for ori in (True, False):
+        r = pyref.search_for_initialization(f1, f2, prev, win, 0.9, ori)
+        o = oracle.search_for_initialization(f1, f2, prev, win, 0.9, ori)
+        assert np.array_equal(r[0], o[0]) and r[1] == o[1] and np.array_equal(r[2], o[2]), ori
+    if n1 >= 1500 and n2 >= 1500:
+        assert o[1] > 100
