@@ -238,3 +238,13 @@ def search_for_initialization(f1, f2, prev_matched, window_size, nn_ratio=0.9, c
     lib().ref_orb_search_for_initialization(C.byref(f1), C.byref(f2), _p(pm), C.c_int(int(window_size)), C.c_float(nn_ratio),
                                             C.c_int(int(check_orientation)), _p(m), C.byref(n))
     return m[:f1.n], n.value, pm
+
+
+def distinctive_descriptors(desc, group_off):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:256-321) through the reference's own function, once per group of
+    observations -> index of the chosen descriptor inside each group (-1 for an empty group)."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(group_off, np.int32)
+    best = np.empty(max(len(off) - 1, 1), np.int32)
+    lib().ref_distinctive_descriptors(_p(d), _p(off), C.c_int(len(off) - 1), _p(best))
+    return best[:len(off) - 1]

@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization, MapPoint::ComputeDistinctiveDescriptors, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -375,3 +375,13 @@ def test_search_for_initialization_equals_the_reference_code(seed, n1, n2, win, 
         assert np.array_equal(r[0], o[0]) and r[1] == o[1] and np.array_equal(r[2], o[2]), ori
     if n1 >= 1500 and n2 >= 1500:
         assert o[1] > 100
+
+
+@pytest.mark.parametrize("seed,sizes", [(1, [1, 2, 3, 5, 8, 13, 40]), (2, [64, 33, 32, 31, 7]), (3, [150]), (5, [2] * 40 + [3] * 40 + [4] * 40)])
+def test_distinctive_descriptors_equal_the_reference_code(seed, sizes, oracle):
+    """E: the reference's own MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:256-321), cut out of the reference source: the
+    descriptor with the least median distance to the others, the median taken at index 0.5 * (N - 1) of the sorted row, the first
+    of equal medians winning."""
+    rng = np.random.default_rng(seed)
+    desc, off = matchgen.distinctive_case(rng, sizes)
+    assert np.array_equal(pyref.distinctive_descriptors(desc, off), oracle.distinctive_descriptors(desc, off))
