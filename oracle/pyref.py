@@ -248,3 +248,15 @@ def distinctive_descriptors(desc, group_off):
     best = np.empty(max(len(off) - 1, 1), np.int32)
     lib().ref_distinctive_descriptors(_p(d), _p(off), C.c_int(len(off) - 1), _p(best))
     return best[:len(off) - 1]
+
+
+def fuse(kf_view, pt_view, ow, log_sf, inv_level_sigma2, th):
+    """ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) (ORBmatcher.cc:1107-1277) through the reference's own
+    function -> (key-frame feature each map point was fused with or -1, nFused), as the first and third result of
+    pyoracle.fuse_candidates(..., variant=0)."""
+    bi = np.empty(max(pt_view.n, 1), np.int32)
+    n = C.c_int(0)
+    o = np.ascontiguousarray(ow, np.float32)
+    sg = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    lib().ref_orb_fuse(C.byref(kf_view), C.byref(pt_view), _p(o), C.c_float(log_sf), _p(sg), C.c_float(th), _p(bi), C.byref(n))
+    return bi[:pt_view.n], n.value

@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization, MapPoint::ComputeDistinctiveDescriptors, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization and Fuse, MapPoint::ComputeDistinctiveDescriptors, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -385,3 +385,21 @@ def test_distinctive_descriptors_equal_the_reference_code(seed, sizes, oracle):
     rng = np.random.default_rng(seed)
     desc, off = matchgen.distinctive_case(rng, sizes)
     assert np.array_equal(pyref.distinctive_descriptors(desc, off), oracle.distinctive_descriptors(desc, off))
+
+
+@pytest.mark.parametrize("seed,m,extra,th", [(81, 600, 300, 3.0), (82, 1500, 500, 3.0), (83, 200, 1000, 5.0), (84, 0, 400, 3.0), (85, 900, 0, 1.5)])
+def test_fuse_equals_the_reference_code(seed, m, extra, th, oracle, synth):
+    """E: the reference's own ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) (ORBmatcher.cc:1107-1277) with
+    KeyFrame::GetFeaturesInArea / IsInImage and MapPoint::PredictScale, cut out of the reference sources: the projection and distance
+    gates, the viewing-angle test, the octave window, the chi-square test on the (stereo / mono) reprojection error, the best
+    descriptor.  What the function does to the map point (AddObservation / Replace) is recorded, not carried out — as in the C ABI,
+    where that bookkeeping stays with the caller."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    fv, pv, ow, log_sf, inv_s2, keep = matchgen.fuse_case(rng, m, extra, N, synth.TUM1, sf)
+    r = pyref.fuse(fv, pv, ow, log_sf, inv_s2, th)
+    bi, bd, nf = oracle.fuse_candidates(fv, pv, ow, log_sf, inv_s2, th, 0)
+    assert np.array_equal(r[0], bi) and r[1] == nf
+    if m >= 600:
+        assert nf > 100
