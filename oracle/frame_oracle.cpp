@@ -9,6 +9,8 @@
 //   Frame::UnprojectStereo           src/Frame.cc:1120-1134 (and the KeyLine end-point twins :1140-1205)
 //   Frame::IsInFrustum(MapPoint*)    src/Frame.cc:345-401, MapPoint::PredictScale src/MapPoint.cc:416-431
 //   Frame::IsInFrustum(MapLine*)     src/Frame.cc:403-430
+// ComputeStereoFromRGBD, UnprojectStereo and IsInFrustum(MapPoint*) are PINNED bit-exactly to the reference's own functions
+// (oracle/_ref, tests/test_oracle_ref.py); the MapLine twin and ComputeStereoMatches are restated only.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
