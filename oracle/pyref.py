@@ -250,13 +250,16 @@ def distinctive_descriptors(desc, group_off):
     return best[:len(off) - 1]
 
 
-def fuse(kf_view, pt_view, ow, log_sf, inv_level_sigma2, th):
+def fuse(kf_view, pt_view, ow, log_sf, inv_level_sigma2, th, variant=0):
     """ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) (ORBmatcher.cc:1107-1277) through the reference's own
     function -> (key-frame feature each map point was fused with or -1, nFused), as the first and third result of
-    pyoracle.fuse_candidates(..., variant=0)."""
+    pyoracle.fuse_candidates(..., variant=0).  variant 1: the Sim3 overload Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (:1290-1427), the
+    view's pose being Scw; additionally returns the pose after the function's own division by the scale (tcw (12,), ow (3,))."""
     bi = np.empty(max(pt_view.n, 1), np.int32)
     n = C.c_int(0)
     o = np.ascontiguousarray(ow, np.float32)
     sg = np.ascontiguousarray(inv_level_sigma2, np.float32)
-    lib().ref_orb_fuse(C.byref(kf_view), C.byref(pt_view), _p(o), C.c_float(log_sf), _p(sg), C.c_float(th), _p(bi), C.byref(n))
-    return bi[:pt_view.n], n.value
+    tcw, ow2 = np.zeros(12, np.float32), np.zeros(3, np.float32)
+    lib().ref_orb_fuse(C.byref(kf_view), C.byref(pt_view), _p(o), C.c_float(log_sf), _p(sg), C.c_float(th), C.c_int(int(variant)), _p(bi), C.byref(n),
+                       _p(tcw), _p(ow2))
+    return (bi[:pt_view.n], n.value) if variant == 0 else (bi[:pt_view.n], n.value, tcw, ow2)

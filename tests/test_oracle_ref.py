@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization and Fuse, MapPoint::ComputeDistinctiveDescriptors, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization and both Fuse overloads, MapPoint::ComputeDistinctiveDescriptors, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -400,6 +400,28 @@ def test_fuse_equals_the_reference_code(seed, m, extra, th, oracle, synth):
     fv, pv, ow, log_sf, inv_s2, keep = matchgen.fuse_case(rng, m, extra, N, synth.TUM1, sf)
     r = pyref.fuse(fv, pv, ow, log_sf, inv_s2, th)
     bi, bd, nf = oracle.fuse_candidates(fv, pv, ow, log_sf, inv_s2, th, 0)
+    assert np.array_equal(r[0], bi) and r[1] == nf
+    if m >= 600:
+        assert nf > 100
+
+
+@pytest.mark.parametrize("seed,m,extra,th,scale", [(91, 600, 300, 4.0, 1.0), (92, 1500, 500, 4.0, 1.0), (93, 200, 1000, 6.0, 1.0), (94, 900, 0, 2.0, 1.0),
+                                                   (95, 600, 300, 4.0, 1.4)])
+def test_fuse_with_a_sim3_equals_the_reference_code(seed, m, extra, th, scale, oracle, synth):
+    """E: the reference's own ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1290-1427), cut
+    out of the reference source; as for C5 the oracle is fed the pose after the function's own division by the scale."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    fv, pv, ow, log_sf, inv_s2, keep = matchgen.fuse_case(rng, m, extra, N, synth.TUM1, sf)
+    if scale != 1.0:
+        for k in range(12):
+            fv.tcw[k] = np.float32(fv.tcw[k] * np.float32(scale))
+    r = pyref.fuse(fv, pv, ow, log_sf, inv_s2, th, variant=1)
+    fv2 = type(fv).from_buffer_copy(fv)
+    for k in range(12):
+        fv2.tcw[k] = float(r[2][k])
+    bi, bd, nf = oracle.fuse_candidates(fv2, pv, r[3], log_sf, inv_s2, th, 1)
     assert np.array_equal(r[0], bi) and r[1] == nf
     if m >= 600:
         assert nf > 100
