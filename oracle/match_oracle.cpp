@@ -10,8 +10,8 @@
 // PINNED TO REFERENCE CODE (oracle/_ref/libplref.so = the reference's own function definitions, cut out of /root/reference at build
 // time and compiled against stand-in Frame / KeyFrame / MapPoint / MapLine classes; tests/test_oracle_ref.py): DescriptorDistance,
 // ComputeThreeMaxima, every ORBmatcher search C2 - C7 (SearchByProjection x4, SearchByBoW x2), SearchForInitialization, both Fuse
-// overloads, MapPoint::ComputeDistinctiveDescriptors, and the LineMatcher searches D3 / D4 / D5 with the LineMatching predicate,
-// LiangBarsky and UpdateKeyLineData.  Still restated only: SearchBySim3, SearchForTriangulation, the kNN-ratio / MAD
+// overloads, SearchBySim3, MapPoint::ComputeDistinctiveDescriptors, and the LineMatcher searches D3 / D4 / D5 with the LineMatching predicate,
+// LiangBarsky and UpdateKeyLineData.  Still restated only: SearchForTriangulation, the kNN-ratio / MAD
 // rules of D6 (their kNN itself is pinned to cv2).
 #include <algorithm>
 #include <cstdint>

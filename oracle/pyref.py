@@ -263,3 +263,16 @@ def fuse(kf_view, pt_view, ow, log_sf, inv_level_sigma2, th, variant=0):
     lib().ref_orb_fuse(C.byref(kf_view), C.byref(pt_view), _p(o), C.c_float(log_sf), _p(sg), C.c_float(th), C.c_int(int(variant)), _p(bi), C.byref(n),
                        _p(tcw), _p(ow2))
     return (bi[:pt_view.n], n.value) if variant == 0 else (bi[:pt_view.n], n.value, tcw, ow2)
+
+
+def search_by_sim3(kf1, kf2, pts1, pts2, s12, R12, t12, log_sf1, log_sf2, th):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1441-1692) through the reference's own function -> (vpMatches12 as indices into key
+    frame 2's features, nFound, [sR21 | t21] and [sR12 | t12] (12,) as the function forms them: what pyoracle.search_by_sim3 takes)."""
+    r = np.ascontiguousarray(R12, np.float32).reshape(9)
+    t = np.ascontiguousarray(t12, np.float32).reshape(3)
+    m = np.empty(max(kf1.n, 1), np.int32)
+    n = C.c_int(0)
+    t21o, t12o = np.zeros(12, np.float32), np.zeros(12, np.float32)
+    lib().ref_orb_search_by_sim3(C.byref(kf1), C.byref(kf2), C.byref(pts1), C.byref(pts2), C.c_float(s12), _p(r), _p(t), C.c_float(log_sf1),
+                                 C.c_float(log_sf2), C.c_float(th), _p(m), C.byref(n), _p(t21o), _p(t12o))
+    return m[:kf1.n], n.value, t21o, t12o

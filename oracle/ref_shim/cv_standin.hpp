@@ -176,6 +176,27 @@ inline MatCommaInit<T> operator<<(const Mat_<T>& m, T v) {
     ci, v;
     return ci;
 }
+// s * A, s * A.t() (scaled copies, the scale applied in float) and -A * b (one gemm with alpha = -1) of CV_32F matrices
+inline Mat operator*(double s, const Mat& a) {
+    assert(a.esz == 4);
+    const float alpha = (float)s;
+    Mat d(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < a.cols; j++) d.at<float>(i, j) = a.at<float>(i, j) * alpha;
+    return d;
+}
+inline Mat operator*(double s, const Mat::TExpr& e) {
+    const Mat& a = *e.m;
+    assert(a.esz == 4);
+    const float alpha = (float)(s * e.alpha);
+    Mat d(a.cols, a.rows, CV_32F);
+    for (int i = 0; i < a.cols; i++)
+        for (int j = 0; j < a.rows; j++) d.at<float>(i, j) = a.at<float>(j, i) * alpha;
+    return d;
+}
+struct NegExpr { Mat m; };
+inline NegExpr operator-(const Mat& a) { return NegExpr{a}; }
+inline Mat::MulExpr operator*(const NegExpr& e, const Mat& b) { return Mat::MulExpr{e.m, b, -1.0, false}; }
 // a - b of two CV_32F matrices (element-wise float subtraction) and cv::norm (L2) of a CV_32F matrix: products accumulated in double
 inline Mat operator-(const Mat& a, const Mat& b) {
     assert(a.esz == 4 && b.esz == 4 && a.rows == b.rows && a.cols == b.cols);

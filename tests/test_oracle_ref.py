@@ -3,7 +3,7 @@ oracle/_ref/libplref.so (oracle/ref_shim/Makefile: src/ORBextractor.cc as a whol
 src/ORBmatcher.cc and src/LineMatcher.cpp, the vendored DBoW2 vocabulary) against an OpenCV stand-in whose image-processing functions
 are the oracle's cv2-pinned primitives.  This pins rows A1-A10, C1, D1, C2 and C3 as whole functions (ORBmatcher::SearchByProjection for the local map and for the last
 frame, cut out of src/ORBmatcher.cc with the Frame grid functions of src/Frame.cc), C4 and C5 (the relocalisation and Sim3 searches with MapPoint::PredictScale), C6 and C7 (both ORBmatcher::SearchByBoW overloads),
-D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization and both Fuse overloads, MapPoint::ComputeDistinctiveDescriptors, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
+D2 - D5 (LineMatcher::SearchByProjection for the last frame, a reference key frame and the local map, LineMatching, LiangBarsky), ORBmatcher::SearchForInitialization, SearchBySim3 and both Fuse overloads, MapPoint::ComputeDistinctiveDescriptors, F2 - F4 (Frame::ComputeStereoFromRGBD, UnprojectStereo, IsInFrustum) and G to reference code.  Skipped where neither the prebuilt library nor /root/reference exists."""
 import importlib
 import os
 import sys
@@ -425,3 +425,22 @@ def test_fuse_with_a_sim3_equals_the_reference_code(seed, m, extra, th, scale, o
     assert np.array_equal(r[0], bi) and r[1] == nf
     if m >= 600:
         assert nf > 100
+
+
+@pytest.mark.parametrize("seed,m,e1,e2,th", [(101, 800, 200, 300, 7.5), (102, 1500, 0, 0, 7.5), (103, 300, 900, 700, 10.0), (104, 0, 200, 200, 7.5)])
+def test_search_by_sim3_equals_the_reference_code(seed, m, e1, e2, th, oracle, synth):
+    """E: the reference's own ORBmatcher::SearchBySim3 (ORBmatcher.cc:1441-1692), cut out of the reference source: both projection
+    directions with their distance / octave gates and the final agreement test.  The oracle (like the C ABI) takes [sR21 | t21] and
+    [sR12 | t12]; it is fed the matrices the reference-side call reports."""
+    N = importlib.import_module("orb_slam2_modification_with-point-and-line-feature_b200._native")
+    rng = np.random.default_rng(seed)
+    sf = oracle.OrbOracle().tables()["scale_factors"]
+    kf1, kf2, p1, p2, t21, t12, lsf, keep = matchgen.sim3_case(rng, m, e1, e2, N, synth.TUM1, sf)
+    s12 = np.float32(1.02)
+    R12 = (t12[:, :3] / s12).astype(np.float32)
+    r = pyref.search_by_sim3(kf1, kf2, p1, p2, float(s12), R12, t12[:, 3], lsf, lsf, th)
+    assert np.allclose(r[2].reshape(3, 4), t21, atol=1e-5) and np.allclose(r[3].reshape(3, 4), t12, atol=1e-5)
+    o = oracle.search_by_sim3(kf1, kf2, p1, p2, r[2], r[3], lsf, lsf, th)
+    assert np.array_equal(r[0], o[0]) and r[1] == o[1]
+    if m >= 800:
+        assert o[1] > 100
